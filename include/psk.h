@@ -1,0 +1,186 @@
+/*
+ * psk.h -- C ABI of libpsk, the B200-native (sm_100a, fp64) implementation of
+ * the one data-parallel hot path of alexfikl/pyshocks:
+ *
+ *   apply_boundary -> WENO-JS reconstruction -> numerical flux -> flux-difference
+ *   RHS, fused with the SSPRK33 stage update; the CFL max-wavespeed reduction;
+ *   and the hand-derived discrete adjoint of the stage.
+ *
+ * The reference has no FFI: its extension point is functools.singledispatch
+ * registration on scheme / stepper / boundary types.
+ * Each entry point below names the reference function it stands in for
+ * (paths relative to /root/reference/src/pyshocks).  The Python shims in
+ * pyshocks_b200/ register these behind the same generic functions and call
+ * them through ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - every array is fp64 in DEVICE memory, owned by the caller;
+ *  - a "state" array holds `batch` rows of `nx = n + 2 g` cells, row stride
+ *    `ld` doubles (ld >= nx); row r, cell i lives at base[r * ld + i]; cells
+ *    [0, g) and [nx - g, nx) are ghost cells (grid.py:83-117);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    allocates nothing and never synchronises unless its name ends in _sync;
+ *  - return value: PSK_OK or a psk_status code (never a CPU fallback).
+ */
+#ifndef PSK_H
+#define PSK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSK_VERSION 100 /* 0.1.0 */
+
+typedef void *psk_stream_t; /* cudaStream_t */
+
+enum psk_status {
+  PSK_OK = 0,
+  PSK_E_INVALID = 1,     /* bad argument (NULL pointer, n <= 0, g too small, ...)   */
+  PSK_E_UNSUPPORTED = 2, /* valid in pyshocks but outside the hot-path scope         */
+  PSK_E_CUDA = 3,        /* a CUDA runtime call failed; see psk_last_cuda_error()    */
+  PSK_E_NONFINITE = 4    /* non-finite time step (timestepping.py:144-145)           */
+};
+
+/* equation family: burgers/schemes.py, advection/schemes.py, continuity/schemes.py */
+enum psk_equation { PSK_EQ_BURGERS = 0, PSK_EQ_ADVECTION = 1, PSK_EQ_CONTINUITY = 2 };
+
+/* numerical flux (scalar.py:91-322; names of burgers/__init__.py:62-72)
+ *   RUSANOV          scalar_flux_rusanov        (local Lax-Friedrichs, "rusanov")
+ *   LAX_FRIEDRICHS   scalar_flux_lax_friedrichs (global max speed,     "lf")
+ *   UPWIND           scalar_flux_upwind / upwind_flux (averaged-speed switch, "godunov")
+ *   ENGQUIST_OSHER   scalar_flux_engquist_osher (omega = 0,            "eo")      */
+enum psk_flux {
+  PSK_FLUX_RUSANOV = 0,
+  PSK_FLUX_LAX_FRIEDRICHS = 1,
+  PSK_FLUX_UPWIND = 2,
+  PSK_FLUX_ENGQUIST_OSHER = 3
+};
+
+/* reconstruction.py:127-163 (constant), :319-348 (WENOJS32 / WENOJS53) */
+enum psk_rec { PSK_REC_CONSTANT = 0, PSK_REC_WENOJS32 = 1, PSK_REC_WENOJS53 = 2 };
+
+/* ghost-cell fill applied at the top of every RHS (schemes.py:343)
+ *   PERIODIC  scalar.py:529-540
+ *   DIRICHLET scalar.py:418-427; desc.ghost holds the 2 g values g(t, x_ghost),
+ *             left ghosts first, evaluated on the host by the caller
+ *   NEUMANN   scalar.py:472-500; ghost = mirrored interior cell + desc.ghost[k],
+ *             desc.ghost holding side * (x[ifrom] - x[ito]) * g(t) per ghost cell
+ *   NONE      ghost cells are used as found (halo-exchanged slabs)              */
+enum psk_bc { PSK_BC_PERIODIC = 0, PSK_BC_DIRICHLET = 1, PSK_BC_NEUMANN = 2, PSK_BC_NONE = 3 };
+
+/* arithmetic contract
+ *   STRICT  every operation in the reference's order, no FMA contraction, IEEE
+ *           division: results are bit-identical to oracle/psk_oracle.c
+ *   FAST    same algorithm, re-associated for the FP64 pipe (FMA, shared
+ *           smoothness indicators, one division per reconstructed value);
+ *           agrees with STRICT to a few ulp per RHS evaluation               */
+enum psk_math { PSK_MATH_FAST = 0, PSK_MATH_STRICT = 1 };
+
+typedef struct psk_desc {
+  int32_t equation; /* enum psk_equation */
+  int32_t flux;     /* enum psk_flux     */
+  int32_t rec;      /* enum psk_rec      */
+  int32_t bc;       /* enum psk_bc       */
+  int32_t math;     /* enum psk_math     */
+  int32_t n;        /* interior cells per row                                    */
+  int32_t g;        /* ghost cells per side, >= stencil width of rec (1 / 2 / 3) */
+  int32_t batch;    /* rows (independent problems; 1 for a plain pyshocks array) */
+  int64_t ld;       /* row stride of state arrays, in doubles                    */
+  double dx;        /* cell size h; grid.dx is a constant array (grid.py:164)    */
+  double eps;       /* WENO-JS epsilon (reconstruction.py:325, :341)             */
+  const double *nu; /* NULL: nu = 1 (|alpha - 1| <= 1e-8); else nx - 1 per-face
+                       values grid.df ** (alpha - 1) (scalar.py:231-234)         */
+  const double *velocity; /* nx, advection / continuity only, shared by all rows */
+  const double *vel_l;    /* nx, left  values of reconstruct(velocity)  ("al")   */
+  const double *vel_r;    /* nx, right values of reconstruct(velocity)  ("ar")   */
+  const double *ghost;    /* DIRICHLET / NEUMANN data, 2 g doubles per row       */
+  int64_t ghost_ld;       /* row stride of ghost in doubles; 0 = shared          */
+} psk_desc;
+
+int psk_version(void);
+const char *psk_status_string(int status);
+/* last cudaError_t seen by this library on the calling thread (0 = none) */
+int psk_last_cuda_error(void);
+
+/* apply_boundary(bc, grid, t, u) -> w            schemes.py:431-442, scalar.py BCs.
+ * w may alias u. */
+int psk_apply_boundary(const psk_desc *d, const double *u, double *w, psk_stream_t stream);
+
+/* reconstruct(rec, grid, bc, f, f, .) -> (fl, fr)   reconstruction.py:79-118, :358-377.
+ * Zero-padded beyond the array ends like jnp.convolve(..., "same") (convolve.py:113-114). */
+int psk_reconstruct(const psk_desc *d, const double *f, double *fl, double *fr,
+                    psk_stream_t stream);
+
+/* numerical_flux(scheme, grid, bc, t, w) -> F[nx + 1]       schemes.py:321-336 and the
+ * registrations burgers/schemes.py:83-196, advection/schemes.py:121-129,
+ * continuity/schemes.py:93-110.  w already has its ghost cells set; F has row
+ * stride ld_f >= nx + 1 and F[0] = F[nx] = 0 (the reference's jnp.pad). */
+int psk_numerical_flux(const psk_desc *d, const double *w, double *flux, int64_t ld_f,
+                       psk_stream_t stream);
+
+/* apply_operator(scheme, grid, bc, t, u) -> L[nx]     schemes.py:339-346,
+ * advection/schemes.py:62-73.  Applies the boundary condition internally and
+ * evaluates ALL nx rows, ghost rows included, exactly like the reference. */
+int psk_apply_operator(const psk_desc *d, const double *u, double *rhs, psk_stream_t stream);
+
+/* max |u| per row, over the interior (interior_only != 0: the reduction inside
+ * predict_timestep, burgers/schemes.py:47, :124) or over all nx cells (the
+ * global Lax-Friedrichs speed, scalar.py:277).  out[batch]. */
+int psk_max_abs(const psk_desc *d, const double *u, int interior_only, double *out,
+                psk_stream_t stream);
+
+/* One fused SSPRK33 stage (timestepping.py:312-320 with apply_operator inlined):
+ *   stage 1: uout = uin + dt L(uin)                     (uin = u0)
+ *   stage 2: uout = 3/4 u0 + 1/4 (uin + dt L(uin))
+ *   stage 3: uout = 1/3 u0 + 2/3 (uin + dt L(uin))
+ *   stage 0: uout = L(uin)                              (plain RHS, interior fast path)
+ * dt: device pointer, row r uses dt[r * dt_stride] (dt_stride 0 = one shared value).
+ * active: optional per-row byte mask; rows with active[r] == 0 are left untouched.
+ * maxabs: optional [batch]; on return max over the interior of |uout| per row
+ *         (fused CFL reduction for the next predict_timestep); needs no pre-zeroing
+ *         ordering beyond being zero-filled by the caller before the launch.
+ * lf_speed: [batch] global max |w| per row; required for PSK_FLUX_LAX_FRIEDRICHS.
+ * ghost_rows != 0 also produces the nx - n ghost entries of uout exactly as the
+ * reference does (zero-padded stencils at the array ends); otherwise ghost cells
+ * of uout are not written. */
+int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const double *uin,
+                      double *uout, const double *dt, int64_t dt_stride,
+                      const uint8_t *active, const double *lf_speed, double *maxabs,
+                      int ghost_rows, psk_stream_t stream);
+
+/* Device-side step control of timestepping.step (timestepping.py:128-150) for
+ * Burgers-type schemes, per row r:
+ *   dt   = theta * (cfl_scale / maxabs[r])             (burgers/schemes.py:42-49, :121-127;
+ *                                                        cfl_scale = 0.5 dx_min^(2 - alpha))
+ *   dt   = min(dt, tfinal - t[r]) + 1e-15 ; t[r] += dt on the NEXT call (see t_next)
+ *   active[r] = t[r] < tfinal ;  *nonfinite |= !isfinite(dt)
+ * Writes dt[r]; t_next[r] = t[r] + dt for active rows. */
+int psk_step_control(int32_t batch, double theta, double cfl_scale, double tfinal,
+                     const double *maxabs,
+                     const double *t, double *t_next, double *dt, uint8_t *active,
+                     int32_t *nonfinite, psk_stream_t stream);
+
+/* out = J_L(u)^T v, the vector-Jacobian product of apply_operator w.r.t. u (all nx
+ * rows, boundary condition included); what jax.vjp(apply_operator) returns. */
+int psk_apply_operator_vjp(const psk_desc *d, const double *u, const double *v, double *out,
+                           psk_stream_t stream);
+
+/* One fused adjoint stage:  out = c_acc * acc + c_v * (v + dt J_L(x)^T v) [+ c_acc2 * acc2]
+ * The three calls of a reverse SSPRK33 step, given the recomputed
+ * forward stages k1, k2 of the checkpointed state u:
+ *   lam2 = 2/3 (p' + dt J(k2)^T p')
+ *   lam1 = 1/4 (lam2 + dt J(k1)^T lam2)
+ *   p    = 1/3 p' + 3/4 lam2 + (lam1 + dt J(u)^T lam1)
+ * acc / acc2 may be NULL when their coefficient is 0. */
+int psk_ssprk33_stage_adjoint(const psk_desc *d, const double *x, const double *v,
+                              const double *dt, int64_t dt_stride, double c_v,
+                              const double *acc, double c_acc, const double *acc2,
+                              double c_acc2, const double *lf_speed, double *out,
+                              psk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSK_H */

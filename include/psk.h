@@ -116,19 +116,24 @@ int psk_reconstruct(const psk_desc *d, const double *f, double *fl, double *fr,
 /* numerical_flux(scheme, grid, bc, t, w) -> F[nx + 1]       schemes.py:321-336 and the
  * registrations burgers/schemes.py:83-196, advection/schemes.py:121-129,
  * continuity/schemes.py:93-110.  w already has its ghost cells set; F has row
- * stride ld_f >= nx + 1 and F[0] = F[nx] = 0 (the reference's jnp.pad). */
+ * stride ld_f >= nx + 1 and F[0] = F[nx] = 0 (the reference's jnp.pad).
+ * lf_work: [batch] doubles of scratch, required for PSK_FLUX_LAX_FRIEDRICHS (receives the
+ * global speed max |w|, scalar.py:277), may be NULL otherwise. */
 int psk_numerical_flux(const psk_desc *d, const double *w, double *flux, int64_t ld_f,
-                       psk_stream_t stream);
+                       double *lf_work, psk_stream_t stream);
 
 /* apply_operator(scheme, grid, bc, t, u) -> L[nx]     schemes.py:339-346,
  * advection/schemes.py:62-73.  Applies the boundary condition internally and
- * evaluates ALL nx rows, ghost rows included, exactly like the reference. */
-int psk_apply_operator(const psk_desc *d, const double *u, double *rhs, psk_stream_t stream);
+ * evaluates ALL nx rows, ghost rows included, exactly like the reference.
+ * rhs must not alias u.  lf_work: see psk_numerical_flux. */
+int psk_apply_operator(const psk_desc *d, const double *u, double *rhs, double *lf_work,
+                       psk_stream_t stream);
 
-/* max |u| per row, over the interior (interior_only != 0: the reduction inside
- * predict_timestep, burgers/schemes.py:47, :124) or over all nx cells (the
- * global Lax-Friedrichs speed, scalar.py:277).  out[batch]. */
-int psk_max_abs(const psk_desc *d, const double *u, int interior_only, double *out,
+/* max |u| per row -> out[batch].  mode 1: over the interior (the reduction inside
+ * predict_timestep, burgers/schemes.py:47, :124); mode 0: over all nx stored cells;
+ * mode 2: over all nx cells after the boundary condition of d (the global
+ * Lax-Friedrichs speed, scalar.py:277).  NaN propagates like jnp.max. */
+int psk_max_abs(const psk_desc *d, const double *u, int mode, double *out,
                 psk_stream_t stream);
 
 /* One fused SSPRK33 stage (timestepping.py:312-320 with apply_operator inlined):
@@ -141,13 +146,14 @@ int psk_max_abs(const psk_desc *d, const double *u, int interior_only, double *o
  * maxabs: optional [batch]; on return max over the interior of |uout| per row
  *         (fused CFL reduction for the next predict_timestep); needs no pre-zeroing
  *         ordering beyond being zero-filled by the caller before the launch.
- * lf_speed: [batch] global max |w| per row; required for PSK_FLUX_LAX_FRIEDRICHS.
+ * lf_work: see psk_numerical_flux (one extra reduction pass over uin).
+ * uout must not alias uin (it may alias u0 in stage 3).
  * ghost_rows != 0 also produces the nx - n ghost entries of uout exactly as the
  * reference does (zero-padded stencils at the array ends); otherwise ghost cells
  * of uout are not written. */
 int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const double *uin,
                       double *uout, const double *dt, int64_t dt_stride,
-                      const uint8_t *active, const double *lf_speed, double *maxabs,
+                      const uint8_t *active, double *lf_work, double *maxabs,
                       int ghost_rows, psk_stream_t stream);
 
 /* Device-side step control of timestepping.step (timestepping.py:128-150) for
@@ -163,21 +169,25 @@ int psk_step_control(int32_t batch, double theta, double cfl_scale, double tfina
                      int32_t *nonfinite, psk_stream_t stream);
 
 /* out = J_L(u)^T v, the vector-Jacobian product of apply_operator w.r.t. u (all nx
- * rows, boundary condition included); what jax.vjp(apply_operator) returns. */
+ * rows, boundary condition included); what jax.vjp(apply_operator) returns, and the
+ * building block of the reference's adjoint_step (timestepping.py:174, :205-206).
+ * work: batch * (2 g + 2) doubles of scratch.  out must not alias u or v. */
 int psk_apply_operator_vjp(const psk_desc *d, const double *u, const double *v, double *out,
-                           psk_stream_t stream);
+                           double *work, psk_stream_t stream);
 
-/* One fused adjoint stage:  out = c_acc * acc + c_v * (v + dt J_L(x)^T v) [+ c_acc2 * acc2]
+/* One fused adjoint stage:  out = c_acc * acc + c_acc2 * acc2 + c_v * (v + dt J_L(x)^T v)
  * The three calls of a reverse SSPRK33 step, given the recomputed
- * forward stages k1, k2 of the checkpointed state u:
+ * forward stages k1, k2 of the checkpointed state u and the incoming adjoint p':
  *   lam2 = 2/3 (p' + dt J(k2)^T p')
  *   lam1 = 1/4 (lam2 + dt J(k1)^T lam2)
  *   p    = 1/3 p' + 3/4 lam2 + (lam1 + dt J(u)^T lam1)
- * acc / acc2 may be NULL when their coefficient is 0. */
+ * acc / acc2 may be NULL (their coefficient is then ignored).  dt as in
+ * psk_ssprk33_stage.  work: batch * (2 g + 2) doubles of scratch.  out must not alias
+ * x or v. */
 int psk_ssprk33_stage_adjoint(const psk_desc *d, const double *x, const double *v,
                               const double *dt, int64_t dt_stride, double c_v,
                               const double *acc, double c_acc, const double *acc2,
-                              double c_acc2, const double *lf_speed, double *out,
+                              double c_acc2, double *work, double *out,
                               psk_stream_t stream);
 
 #ifdef __cplusplus

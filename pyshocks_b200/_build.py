@@ -1,0 +1,58 @@
+"""In-tree build of ``libpsk.so`` (hand-written CUDA for sm_100a) with nvcc.
+
+The shared library is written next to the sources (``pyshocks_b200/csrc/libpsk.so``);
+it is git-ignored but travels with the repository snapshot to the GPU box.
+"""
+
+from __future__ import annotations
+
+import os
+import pathlib
+import shutil
+import subprocess
+
+CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
+LIB = CSRC / "libpsk.so"
+SOURCES = ("psk_forward.cu", "psk_adjoint.cu")
+HEADERS = ("psk_common.cuh", "psk_math.cuh", "../../include/psk.h")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC,-fvisibility=default",
+    "-Xptxas", "-v",
+]
+
+
+def nvcc() -> str:
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: libpsk.so cannot be built")
+    return exe
+
+
+def needs_build() -> bool:
+    if not LIB.exists():
+        return True
+    stamp = LIB.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES if (CSRC / s).exists()] + [CSRC / h for h in HEADERS]
+    return any(p.stat().st_mtime > stamp for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
+    """Compile every CUDA source into ``libpsk.so``; returns its path."""
+    if not force and not needs_build():
+        return LIB
+    srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
+    cmd = [nvcc(), *NVCC_FLAGS, "-o", str(LIB), *srcs]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    (CSRC / "build.log").write_text(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose or res.returncode != 0:
+        print(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed with exit code {res.returncode}; see {CSRC / 'build.log'}")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=False))

@@ -1,0 +1,376 @@
+// psk_adjoint.cu -- hand-derived discrete adjoint of the fused stage (sm_100a, fp64).
+//
+// The reference builds the dense Jacobian of one SSPRK33 step with jax.jacfwd and applies
+// its transpose (timestepping.py:174, :205-206): O(nx^2) work and memory per step.  Here the
+// transposed stencil is applied matrix-free, O(nx), one launch per stage:
+//
+//   out = c_acc acc + c_acc2 acc2 + c_v v + c_g dt J_L(x)^T v
+//
+// with L = apply_operator (boundary condition included) and J_L evaluated on ALL nx rows,
+// ghost rows included, exactly as the reference's full-array `advance` is differentiated
+// (SURVEY.md 3.3 "ghost rows" quirk).
+//
+// Kernel structure (adjoint_tile_kernel): the transpose of the forward tile kernel.
+//   * a CTA stages w = BC(x) and v for its cells plus halo in shared memory;
+//   * each thread owns R consecutive cells; pass 1 recomputes their face values, neighbours
+//     exchange one value each way, and the R + 1 face-flux derivatives give the cotangents
+//     of every face value (g_ur, g_ul) and the direct cell terms;
+//   * pass 2 pushes (g_ur, g_ul) through the WENO weights (psk_math.cuh, weno53_pair_vjp)
+//     and accumulates the 5-point scatter in registers; only the two-cell spill on each side
+//     goes through shared memory;
+//   * the first and last thread of a CTA are halo threads (they compute, they do not store),
+//     so no atomics are needed between tiles;
+//   * cotangents that land on ghost cells are parked in a per-row spill area and folded back
+//     onto the cells the boundary condition copied them from by a tiny second kernel (the
+//     transpose of apply_boundary), which also distributes the global Lax-Friedrichs speed
+//     cotangent onto the arg-max cells.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "psk_common.cuh"
+#include "psk_math.cuh"
+
+namespace psk {
+
+struct AdjParams {
+  const double *x;
+  const double *v;
+  const double *acc;
+  const double *acc2;
+  double *out;
+  const double *dt;  // nullptr -> 1
+  int64_t dt_stride;
+  double c_v, c_g, c_acc, c_acc2;
+  double *speed;   // [batch] global LF speed (input)
+  double *ga;      // [batch] cotangent of the LF speed (accumulated here)
+  double *gspill;  // [batch][2g] cotangents that landed on ghost cells
+  const double *nu;
+  const double *vel;
+  const double *vel_l;
+  const double *vel_r;
+  BcView bc;
+  int64_t ld;
+  double invdx, eps;
+  int tiles_per_row;
+};
+
+constexpr int kAdjHalo = 3;
+
+template <int R>
+__host__ __device__ __forceinline__ int adj_pad(int e) {
+  return e + e / R;
+}
+
+template <int EQ, int FLUX, int REC, int R>
+__global__ void __launch_bounds__(256)
+adjoint_tile_kernel(const AdjParams p) {
+  extern __shared__ double smem[];
+  const int nthreads = blockDim.x;
+  const int out_cells = (nthreads - 2) * R;
+  const int row = blockIdx.x / p.tiles_per_row;
+  const int tile = blockIdx.x - row * p.tiles_per_row;
+  const int nx = p.bc.nx, g = p.bc.g;
+  const int S = tile * out_cells - R;  // array index of the first cell of (halo) thread 0
+  const double *__restrict__ xrow = p.x + static_cast<int64_t>(row) * p.ld;
+  const double *__restrict__ vrow = p.v + static_cast<int64_t>(row) * p.ld;
+
+  // shared: w tile | v tile | XL | XR | SL (2 per thread) | SR (2 per thread) | warp sums
+  const int elems = nthreads * R + 2 * kAdjHalo;
+  double *tw = smem;
+  double *tv = tw + adj_pad<R>(elems) + 1;
+  double *xl = tv + adj_pad<R>(elems) + 1;
+  double *xr = xl + nthreads + 1;
+  double *sl = xr + nthreads + 1;
+  double *sr = sl + 2 * nthreads;
+  double *wsum = sr + 2 * nthreads;
+
+  for (int e = threadIdx.x; e < elems; e += nthreads) {
+    const int i = S - kAdjHalo + e;
+    tw[adj_pad<R>(e)] = load_w(p.bc, xrow, row, i);
+    tv[adj_pad<R>(e)] = (i >= 0 && i < nx) ? vrow[i] : 0.0;
+  }
+  __syncthreads();
+
+  const int t = threadIdx.x;
+  const int c0 = S + R * t;
+  double w[R + 2 * kAdjHalo], vw[R + 2];
+  {
+    const double *bw = tw + (R + 1) * t;
+    const double *bv = tv + (R + 1) * t;
+#pragma unroll
+    for (int k = 0; k < R + 2 * kAdjHalo; ++k) w[k] = bw[k + k / R];
+#pragma unroll
+    for (int k = 0; k < R + 2; ++k) vw[k] = bv[(k + 2) + (k + 2) / R];  // v[c0 - 1 + k]
+  }
+
+  // ---- pass 1: face values of the owned cells, neighbour exchange
+  double ul[R], ur[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int m = r + kAdjHalo;
+    Weno5Pair o = reconstruct_cell<REC, false>(w[m - 2], w[m - 1], w[m], w[m + 1], w[m + 2], p.eps);
+    ul[r] = o.ul;
+    ur[r] = o.ur;
+  }
+  xl[t] = ul[0];
+  xr[t + 1] = ur[R - 1];
+  if (t == 0) xr[0] = reconstruct_cell<REC, false>(w[0], w[1], w[2], w[3], w[4], p.eps).ur;
+  if (t == nthreads - 1)
+    xl[nthreads] =
+        reconstruct_cell<REC, false>(w[R + 1], w[R + 2], w[R + 3], w[R + 4], w[R + 5], p.eps).ul;
+  __syncthreads();
+  const double ur_left = xr[t];
+  const double ul_right = xl[t + 1];
+
+  // ---- face-flux derivatives: cotangents of the face values and direct cell terms
+  const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.speed[row] : 0.0;
+  const bool writer = (t >= 1 && t <= nthreads - 2);
+  double gur[R + 1], gul[R + 1];  // gur[f] belongs to cell c0 + f - 1, gul[f] to cell c0 + f
+  double dir[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) dir[r] = 0.0;
+  double ga_part = 0.0;
+#pragma unroll
+  for (int f = 0; f <= R; ++f) {
+    const int k = c0 + f;  // face between cells k - 1 and k
+    const bool valid = (k >= 1 && k <= nx - 1);
+    const double urj = (f == 0) ? ur_left : ur[f - 1];
+    const double ulp = (f == R) ? ul_right : ul[f];
+    double nu = 1.0, arj = 0.0, alp = 0.0, ck = 1.0, ckm1 = 1.0;
+    if (valid) {
+      if ((FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) && p.nu != nullptr)
+        nu = p.nu[k - 1];
+      if (EQ != PSK_EQ_BURGERS) {
+        arj = p.vel_r[k - 1];
+        alp = p.vel_l[k];
+      }
+      if (EQ == PSK_EQ_ADVECTION) {
+        ck = p.vel[k];
+        ckm1 = p.vel[k - 1];
+      }
+    }
+    // L[i] = -c_i (F[i+1] - F[i]) / dx  ->  gF[k] = (c_k v[k] - c_{k-1} v[k-1]) / dx
+    const double gF = valid ? (ck * vw[f + 1] - ckm1 * vw[f]) * p.invdx : 0.0;
+    const FaceGrad fg = face_flux_grad<EQ, FLUX>(urj, ulp, w[f + kAdjHalo - 1], w[f + kAdjHalo],
+                                                 speed, nu, arj, alp);
+    gur[f] = gF * fg.d_ur;
+    gul[f] = gF * fg.d_ul;
+    if (f >= 1) dir[f - 1] = fma(gF, fg.d_wj, dir[f - 1]);
+    if (f <= R - 1) dir[f] = fma(gF, fg.d_wp, dir[f]);
+    if (FLUX == PSK_FLUX_LAX_FRIEDRICHS && f >= 1 && writer) ga_part = fma(gF, fg.d_speed, ga_part);
+  }
+
+  // ---- pass 2: through the reconstruction, 5-point scatter kept in registers
+  double accw[R + 4];  // cotangents of cells c0 - 2 .. c0 + R + 1
+#pragma unroll
+  for (int k = 0; k < R + 4; ++k) accw[k] = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int m = r + kAdjHalo;
+    const Weno5Vjp d = reconstruct_cell_vjp<REC>(w[m - 2], w[m - 1], w[m], w[m + 1], w[m + 2], p.eps,
+                                                 gur[r + 1], gul[r]);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) accw[r + q] += d.d[q];
+  }
+  sl[2 * t] = accw[0];
+  sl[2 * t + 1] = accw[1];
+  sr[2 * t] = accw[R + 2];
+  sr[2 * t + 1] = accw[R + 3];
+  __syncthreads();
+
+  if (writer) {
+    const double cgdt =
+        p.c_g * (p.dt != nullptr ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 1.0);
+    const int64_t base = static_cast<int64_t>(row) * p.ld;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = c0 + r;
+      if (i < 0 || i >= nx) continue;
+      double gi = accw[r + 2] + dir[r];
+      if (r < 2) gi += sr[2 * (t - 1) + r];
+      if (r >= R - 2) gi += sl[2 * (t + 1) + (r - (R - 2))];
+      double lin = p.c_v * vw[r + 1];
+      if (p.acc != nullptr) lin = fma(p.c_acc, p.acc[base + i], lin);
+      if (p.acc2 != nullptr) lin = fma(p.c_acc2, p.acc2[base + i], lin);
+      const bool ghost = (p.bc.bc != PSK_BC_NONE) && (i < g || i >= nx - g);
+      if (ghost) {
+        p.out[base + i] = lin;  // ghost cells of x do not influence L: (J^T v)[ghost] = 0
+        p.gspill[static_cast<int64_t>(row) * 2 * g + (i < g ? i : i - p.bc.n)] = gi;
+      } else {
+        p.out[base + i] = fma(cgdt, gi, lin);
+      }
+    }
+  }
+
+  if (FLUX == PSK_FLUX_LAX_FRIEDRICHS) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ga_part += __shfl_xor_sync(0xffffffffu, ga_part, off);
+    const int lane = t & 31, wid = t >> 5;
+    if (lane == 0) wsum[wid] = ga_part;
+    __syncthreads();
+    if (t == 0) {
+      double s = 0.0;
+      for (int k = 0; k < (nthreads + 31) / 32; ++k) s += wsum[k];
+      atomicAdd(p.ga + row, s);
+    }
+  }
+}
+
+// transpose of apply_boundary + distribution of the Lax-Friedrichs speed cotangent; one CTA per row
+template <bool LF>
+__global__ void adjoint_boundary_kernel(const AdjParams p) {
+  const int row = blockIdx.x;
+  const int nx = p.bc.nx, g = p.bc.g, n = p.bc.n;
+  const double *__restrict__ xrow = p.x + static_cast<int64_t>(row) * p.ld;
+  double *orow = p.out + static_cast<int64_t>(row) * p.ld;
+  const double cgdt = p.c_g * (p.dt != nullptr ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 1.0);
+  // where apply_boundary copied ghost cell i from (-1: from nowhere)
+  auto source = [&](int i) -> int {
+    if (i >= g && i < nx - g) return i;
+    switch (p.bc.bc) {
+      case PSK_BC_PERIODIC: return i < g ? i + n : i - n;
+      case PSK_BC_NEUMANN: return i < g ? 2 * g - 1 - i : 2 * (nx - g) - 1 - i;
+      case PSK_BC_DIRICHLET: return -1;
+      default: return i;
+    }
+  };
+  if (p.bc.bc == PSK_BC_PERIODIC || p.bc.bc == PSK_BC_NEUMANN) {
+    for (int k = threadIdx.x; k < 2 * g; k += blockDim.x) {
+      const int i = k < g ? k : nx - 2 * g + k;
+      atomicAdd(orow + source(i), cgdt * p.gspill[static_cast<int64_t>(row) * 2 * g + k]);
+    }
+  }
+  if (LF) {
+    // jnp.max(jnp.abs(w)): the cotangent is shared equally between the tied arg-max cells
+    const double speed = p.speed[row];
+    __shared__ int count;
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x)
+      mine += (fabs(load_w(p.bc, xrow, row, i)) == speed) ? 1 : 0;
+    if (mine) atomicAdd(&count, mine);
+    __syncthreads();
+    const double share = cgdt * p.ga[row] / static_cast<double>(count > 0 ? count : 1);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+      const double wi = load_w(p.bc, xrow, row, i);
+      if (fabs(wi) == speed) {
+        const int src = source(i);
+        if (src >= 0) atomicAdd(orow + src, share * sign0(wi));
+      }
+    }
+  }
+}
+
+template <int EQ, int FLUX, int REC>
+int launch_adjoint(const AdjParams &p0, int batch, cudaStream_t st) {
+  constexpr int R = 4;
+  AdjParams p = p0;
+  const int nx = p.bc.nx;
+  int threads = (nx + R - 1) / R + 2;
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (threads < 32) threads = 32;
+  const int out_cells = (threads - 2) * R;
+  p.tiles_per_row = (nx + out_cells - 1) / out_cells;
+  const int elems = threads * R + 2 * kAdjHalo;
+  const size_t smem =
+      sizeof(double) * (2 * (adj_pad<R>(elems) + 1) + 2 * (threads + 1) + 4 * threads + 8);
+  const long long blocks = static_cast<long long>(p.tiles_per_row) * batch;
+  if (blocks > 2147483647LL) return PSK_E_INVALID;
+  adjoint_tile_kernel<EQ, FLUX, REC, R><<<static_cast<unsigned>(blocks), threads, smem, st>>>(p);
+  PSK_CUDA_OK(cudaGetLastError());
+  constexpr bool LF = (FLUX == PSK_FLUX_LAX_FRIEDRICHS);
+  if (LF || p.bc.bc == PSK_BC_PERIODIC || p.bc.bc == PSK_BC_NEUMANN) {
+    adjoint_boundary_kernel<LF><<<batch, LF ? 128 : 32, 0, st>>>(p);
+    PSK_CUDA_OK(cudaGetLastError());
+  }
+  return PSK_OK;
+}
+
+template <int EQ, int FLUX>
+int adjoint_rec(int rec, const AdjParams &p, int batch, cudaStream_t st) {
+  switch (rec) {
+    case PSK_REC_CONSTANT: return launch_adjoint<EQ, FLUX, PSK_REC_CONSTANT>(p, batch, st);
+    case PSK_REC_WENOJS32: return launch_adjoint<EQ, FLUX, PSK_REC_WENOJS32>(p, batch, st);
+    default: return launch_adjoint<EQ, FLUX, PSK_REC_WENOJS53>(p, batch, st);
+  }
+}
+
+// defined in psk_forward.cu
+int launch_max_abs_public(const psk_desc *d, const double *u, int mode, double *out, cudaStream_t st);
+
+static int run_adjoint(const psk_desc *d, const double *x, const double *v, const double *dt,
+                       int64_t dt_stride, double c_v, double c_g, const double *acc, double c_acc,
+                       const double *acc2, double c_acc2, double *work, double *out,
+                       cudaStream_t st) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (x == nullptr || v == nullptr || out == nullptr || work == nullptr) return PSK_E_INVALID;
+  if (out == x || out == v) return PSK_E_INVALID;  // tiles read their neighbours' cells
+  AdjParams p{};
+  p.x = x;
+  p.v = v;
+  p.acc = (acc != nullptr && c_acc != 0.0) ? acc : nullptr;
+  p.acc2 = (acc2 != nullptr && c_acc2 != 0.0) ? acc2 : nullptr;
+  p.out = out;
+  p.dt = dt;
+  p.dt_stride = dt_stride;
+  p.c_v = c_v;
+  p.c_g = c_g;
+  p.c_acc = c_acc;
+  p.c_acc2 = c_acc2;
+  p.speed = work;
+  p.ga = work + d->batch;
+  p.gspill = work + 2 * static_cast<int64_t>(d->batch);
+  p.nu = d->nu;
+  p.vel = d->velocity;
+  p.vel_l = d->vel_l;
+  p.vel_r = d->vel_r;
+  p.bc = make_bc_view(d);
+  p.ld = d->ld;
+  p.invdx = 1.0 / d->dx;
+  p.eps = d->eps;
+  const bool lf = d->equation == PSK_EQ_BURGERS && d->flux == PSK_FLUX_LAX_FRIEDRICHS;
+  if (lf) {
+    rc = launch_max_abs_public(d, x, 2, p.speed, st);
+    if (rc != PSK_OK) return rc;
+    PSK_CUDA_OK(cudaMemsetAsync(p.ga, 0, sizeof(double) * d->batch, st));
+  }
+  const int b = d->batch;
+  if (d->equation == PSK_EQ_ADVECTION)
+    return adjoint_rec<PSK_EQ_ADVECTION, PSK_FLUX_UPWIND>(d->rec, p, b, st);
+  if (d->equation == PSK_EQ_CONTINUITY)
+    return adjoint_rec<PSK_EQ_CONTINUITY, PSK_FLUX_UPWIND>(d->rec, p, b, st);
+  switch (d->flux) {
+    case PSK_FLUX_RUSANOV: return adjoint_rec<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV>(d->rec, p, b, st);
+    case PSK_FLUX_LAX_FRIEDRICHS:
+      return adjoint_rec<PSK_EQ_BURGERS, PSK_FLUX_LAX_FRIEDRICHS>(d->rec, p, b, st);
+    case PSK_FLUX_UPWIND: return adjoint_rec<PSK_EQ_BURGERS, PSK_FLUX_UPWIND>(d->rec, p, b, st);
+    default: return adjoint_rec<PSK_EQ_BURGERS, PSK_FLUX_ENGQUIST_OSHER>(d->rec, p, b, st);
+  }
+}
+
+}  // namespace psk
+
+using namespace psk;
+
+extern "C" {
+
+int psk_apply_operator_vjp(const psk_desc *d, const double *u, const double *v, double *out,
+                           double *work, psk_stream_t stream) {
+  return run_adjoint(d, u, v, nullptr, 0, 0.0, 1.0, nullptr, 0.0, nullptr, 0.0, work, out,
+                     static_cast<cudaStream_t>(stream));
+}
+
+int psk_ssprk33_stage_adjoint(const psk_desc *d, const double *x, const double *v, const double *dt,
+                              int64_t dt_stride, double c_v, const double *acc, double c_acc,
+                              const double *acc2, double c_acc2, double *work, double *out,
+                              psk_stream_t stream) {
+  if (dt == nullptr) return PSK_E_INVALID;
+  return run_adjoint(d, x, v, dt, dt_stride, c_v, c_v, acc, c_acc, acc2, c_acc2, work, out,
+                     static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,660 @@
+// psk_forward.cu -- forward hot path of libpsk: apply_boundary + WENO-JS reconstruction +
+// numerical flux + flux-difference RHS fused with the SSPRK33 stage combine, the CFL
+// max-wavespeed reduction, and the small parity entry points (reconstruct, numerical_flux,
+// apply_boundary).  Hand-written fp64 CUDA for sm_100a; no tensor cores (nothing here is a
+// contraction), no library calls.
+//
+// Tile kernel (stage_tile_kernel)
+//   * one CTA owns TILE = R * blockDim.x consecutive INTERIOR cells of one row;
+//   * the tile plus its 3-cell halo is staged once in shared memory with coalesced loads,
+//     the boundary condition being applied on the fly (ghost cells are never read from
+//     the state array for periodic / Dirichlet / Neumann rows);
+//   * every thread then owns R consecutive cells: first/second differences, smoothness
+//     indicators, nonlinear weights, fluxes and the stage update live in registers, so a
+//     stage reads u (and u0) once and writes once;
+//   * neighbouring threads exchange one left and one right face value through shared
+//     memory (a single __syncthreads) instead of recomputing them;
+//   * the shared tile is padded by one double every R entries so that the stride-R
+//     per-thread window reads are bank-conflict free.
+// Ghost ROWS of the output (which the reference also produces, from zero-padded stencils)
+// are written by a separate tiny kernel only on request.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "psk_common.cuh"
+#include "psk_math.cuh"
+
+namespace psk {
+
+thread_local int g_last_cuda_error = 0;
+
+struct StageParams {
+  const double *uin;   // state the RHS is evaluated on (k_{s-1})
+  const double *u0;    // state at the start of the step
+  double *uout;
+  const double *dt;
+  int64_t dt_stride;
+  const uint8_t *active;
+  const double *lf_speed;
+  unsigned long long *maxabs;
+  const double *nu;     // per-face dissipation scale or nullptr
+  const double *vel;    // advection / continuity
+  const double *vel_l;
+  const double *vel_r;
+  BcView bc;
+  int64_t ld;
+  double dx, invdx, eps;
+  int stage;
+  int tiles_per_row;
+  int vec_ok;  // rows are 16-byte aligned and every tile starts on an even cell
+};
+
+constexpr int kHalo = 3;
+
+template <int R>
+__host__ __device__ __forceinline__ int pad_index(int e) {
+  return e + e / R;
+}
+
+template <int EQ, int FLUX, int REC, bool STRICT, int R>
+__global__ void __launch_bounds__(256)
+stage_tile_kernel(const StageParams p) {
+  extern __shared__ double smem[];
+  const int nthreads = blockDim.x;
+  const int tile_cells = R * nthreads;
+  const int row = blockIdx.x / p.tiles_per_row;
+  const int tile = blockIdx.x - row * p.tiles_per_row;
+  if (p.active != nullptr && p.active[row] == 0) return;
+
+  const int g = p.bc.g;
+  const int n = p.bc.n;
+  const int s = tile * tile_cells;  // first interior cell of the tile (interior coordinates)
+  const double *__restrict__ urow = p.uin + static_cast<int64_t>(row) * p.ld;
+
+  // shared layout: padded tile | XL[nthreads + 1] | XR[nthreads + 1] | warp maxima
+  double *tile_w = smem;
+  const int tile_elems = tile_cells + 2 * kHalo;
+  double *xl = tile_w + pad_index<R>(tile_elems) + 1;
+  double *xr = xl + nthreads + 1;
+
+  // ---- stage the tile: element e <-> array index g + s - kHalo + e
+  for (int e = threadIdx.x; e < tile_elems; e += nthreads)
+    tile_w[pad_index<R>(e)] = load_w(p.bc, urow, row, g + s - kHalo + e);
+  __syncthreads();
+
+  // ---- per-thread window: cells c0 - 3 .. c0 + R + 2 (interior coordinates)
+  const int t = threadIdx.x;
+  const int c0 = s + R * t;
+  double v[R + 2 * kHalo];
+  {
+    const double *base = tile_w + (R + 1) * t;
+#pragma unroll
+    for (int k = 0; k < R + 2 * kHalo; ++k) v[k] = base[k + k / R];
+  }
+
+  // ---- face values of the R owned cells
+  double ul[R], ur[R];
+  if (REC == PSK_REC_WENOJS53 && !STRICT) {
+    // half first differences hd[k] = 0.5 (v[k+1] - v[k]), and 13/12 (second difference)^2
+    double hd[R + 5], pq[R + 4];
+#pragma unroll
+    for (int k = 0; k < R + 5; ++k) hd[k] = 0.5 * (v[k + 1] - v[k]);
+#pragma unroll
+    for (int k = 0; k < R + 4; ++k) {
+      double tt = hd[k + 1] - hd[k];  // centred at v[k + 1]
+      pq[k] = (13.0 / 3.0) * tt * tt;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int m = r + kHalo;  // window index of the cell
+      Weno5Pair o = weno53_pair_fast(v[m], hd[m - 2], hd[m - 1], hd[m], hd[m + 1], pq[m - 2],
+                                     pq[m - 1], pq[m], p.eps);
+      ul[r] = o.ul;
+      ur[r] = o.ur;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int m = r + kHalo;
+      Weno5Pair o =
+          reconstruct_cell<REC, STRICT>(v[m - 2], v[m - 1], v[m], v[m + 1], v[m + 2], p.eps);
+      ul[r] = o.ul;
+      ur[r] = o.ur;
+    }
+  }
+
+  // ---- exchange: ur of the cell left of c0 and ul of the cell right of c0 + R - 1
+  xl[t] = ul[0];
+  xr[t + 1] = ur[R - 1];
+  if (t == 0) {
+    Weno5Pair o = reconstruct_cell<REC, STRICT>(v[0], v[1], v[2], v[3], v[4], p.eps);
+    xr[0] = o.ur;  // cell c0 - 1
+  }
+  if (t == nthreads - 1) {
+    Weno5Pair o = reconstruct_cell<REC, STRICT>(v[R + 1], v[R + 2], v[R + 3], v[R + 4], v[R + 5],
+                                                 p.eps);
+    xl[nthreads] = o.ul;  // cell c0 + R
+  }
+  __syncthreads();
+  const double ur_left = xr[t];
+  const double ul_right = xl[t + 1];
+
+  // ---- fluxes at the R + 1 faces of the owned cells; face f sits between cells c0+f-1, c0+f
+  const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
+  double F[R + 1];
+#pragma unroll
+  for (int f = 0; f <= R; ++f) {
+    const double urj = (f == 0) ? ur_left : ur[f - 1];
+    const double ulp = (f == R) ? ul_right : ul[f];
+    const int j = g + c0 + f - 1;  // array index of the cell left of the face
+    double nu = 1.0, arj = 0.0, alp = 0.0;
+    if ((FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) && p.nu != nullptr)
+      nu = (j >= 0 && j < p.bc.nx - 1) ? p.nu[j] : 1.0;
+    if (EQ != PSK_EQ_BURGERS) {
+      const bool ok = (j >= 0 && j < p.bc.nx - 1);
+      arj = ok ? p.vel_r[j] : 0.0;
+      alp = ok ? p.vel_l[j + 1] : 0.0;
+    }
+    F[f] = face_flux<EQ, FLUX, STRICT>(urj, ulp, v[f + kHalo - 1], v[f + kHalo], speed, nu, arj,
+                                       alp);
+  }
+
+  // ---- RHS, stage combine, store
+  const double dt = (p.stage != 0) ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 0.0;
+  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
+  double out[R];
+  unsigned long long mx = 0ull;
+  const bool full = (c0 + R <= n);
+  double u0v[R];
+  if (p.stage >= 2) {
+    if (full && p.vec_ok && (R % 2 == 0)) {
+#pragma unroll
+      for (int r = 0; r < R; r += 2) {
+        double2 q = *reinterpret_cast<const double2 *>(p.u0 + off + r);
+        u0v[r] = q.x;
+        u0v[r + 1] = q.y;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) u0v[r] = (c0 + r < n) ? p.u0[off + r] : 0.0;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) u0v[r] = 0.0;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    double vel = 0.0;
+    if (EQ == PSK_EQ_ADVECTION) vel = (c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
+    const double L = rhs_from_faces<EQ, STRICT>(F[r], F[r + 1], vel, p.dx, p.invdx);
+    out[r] = stage_combine<STRICT>(p.stage, u0v[r], v[r + kHalo], dt, L);
+    if (c0 + r < n) {
+      const unsigned long long b = abs_bits(out[r]);
+      mx = b > mx ? b : mx;
+    }
+  }
+  if (full && p.vec_ok && (R % 2 == 0)) {
+#pragma unroll
+    for (int r = 0; r < R; r += 2)
+      *reinterpret_cast<double2 *>(p.uout + off + r) = make_double2(out[r], out[r + 1]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (c0 + r < n) p.uout[off + r] = out[r];
+  }
+
+  // ---- fused CFL reduction: max |uout| over the interior of the row
+  if (p.maxabs != nullptr) {
+    mx = warp_max_bits(mx);
+    unsigned long long *wm = reinterpret_cast<unsigned long long *>(xr + nthreads + 1);
+    const int lane = t & 31, wid = t >> 5;
+    if (lane == 0) wm[wid] = mx;
+    __syncthreads();
+    if (wid == 0) {
+      const int nw = (nthreads + 31) >> 5;
+      unsigned long long m2 = lane < nw ? wm[lane] : 0ull;
+      m2 = warp_max_bits(m2);
+      if (lane == 0) atomicMax(p.maxabs + row, m2);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// generic cell evaluation straight from global memory (zero padded, BC mapped): used for the
+// ghost rows of a stage / RHS, and by the small parity kernels below.
+
+template <int EQ, int FLUX, int REC, bool STRICT>
+__device__ double rhs_at_cell(const StageParams &p, const double *__restrict__ urow, int row,
+                              int i) {
+  const int nx = p.bc.nx;
+  double w[2 * kHalo + 3];  // w[i-4 .. i+4]
+#pragma unroll
+  for (int k = 0; k < 2 * kHalo + 3; ++k) w[k] = load_w(p.bc, urow, row, i - kHalo - 1 + k);
+  // cells i-1, i, i+1 sit at window positions 3, 4, 5
+  Weno5Pair cm = reconstruct_cell<REC, STRICT>(w[1], w[2], w[3], w[4], w[5], p.eps);
+  Weno5Pair cc = reconstruct_cell<REC, STRICT>(w[2], w[3], w[4], w[5], w[6], p.eps);
+  Weno5Pair cp = reconstruct_cell<REC, STRICT>(w[3], w[4], w[5], w[6], w[7], p.eps);
+  const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
+  double Flo = 0.0, Fhi = 0.0;  // jnp.pad(fnum, 1): the outermost faces carry zero flux
+  if (i >= 1) {
+    const int j = i - 1;
+    double nu = (p.nu != nullptr) ? p.nu[j] : 1.0;
+    double arj = (EQ != PSK_EQ_BURGERS) ? p.vel_r[j] : 0.0;
+    double alp = (EQ != PSK_EQ_BURGERS) ? p.vel_l[j + 1] : 0.0;
+    Flo = face_flux<EQ, FLUX, STRICT>(cm.ur, cc.ul, w[3], w[4], speed, nu, arj, alp);
+  }
+  if (i <= nx - 2) {
+    const int j = i;
+    double nu = (p.nu != nullptr) ? p.nu[j] : 1.0;
+    double arj = (EQ != PSK_EQ_BURGERS) ? p.vel_r[j] : 0.0;
+    double alp = (EQ != PSK_EQ_BURGERS) ? p.vel_l[j + 1] : 0.0;
+    Fhi = face_flux<EQ, FLUX, STRICT>(cc.ur, cp.ul, w[4], w[5], speed, nu, arj, alp);
+  }
+  const double vel = (EQ == PSK_EQ_ADVECTION) ? p.vel[i] : 0.0;
+  return rhs_from_faces<EQ, STRICT>(Flo, Fhi, vel, p.dx, p.invdx);
+}
+
+// one thread per ghost cell: 2 g cells per row
+template <int EQ, int FLUX, int REC, bool STRICT>
+__global__ void ghost_rows_kernel(const StageParams p, int batch) {
+  const int g = p.bc.g;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= batch * 2 * g) return;
+  const int row = idx / (2 * g);
+  const int k = idx - row * 2 * g;
+  if (p.active != nullptr && p.active[row] == 0) return;
+  const int i = k < g ? k : p.bc.nx - 2 * g + k;
+  const double *__restrict__ urow = p.uin + static_cast<int64_t>(row) * p.ld;
+  const double L = rhs_at_cell<EQ, FLUX, REC, STRICT>(p, urow, row, i);
+  const double dt = (p.stage != 0) ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 0.0;
+  const int64_t off = static_cast<int64_t>(row) * p.ld + i;
+  const double u0 = (p.stage >= 2) ? p.u0[off] : 0.0;
+  // the stage combine uses the RAW stored value of uin, not the boundary-filled one
+  p.uout[off] = stage_combine<STRICT>(p.stage, u0, urow[i], dt, L);
+}
+
+// ---------------------------------------------------------------------------
+// dispatch
+
+template <int EQ, int FLUX, int REC, bool STRICT>
+int launch_stage(const StageParams &p, int batch, int ghost_rows, cudaStream_t st) {
+  constexpr int R = 4;
+  const int n = p.bc.n;
+  int threads = (n + R - 1) / R;
+  threads = ((threads + 31) / 32) * 32;
+  if (threads > 256) threads = 256;
+  if (threads < 32) threads = 32;
+  const int tile_cells = R * threads;
+  StageParams q = p;
+  q.tiles_per_row = (n + tile_cells - 1) / tile_cells;
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.uin + p.bc.g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p.uout + p.bc.g) % 16 == 0) &&
+                       (p.u0 == nullptr || reinterpret_cast<uintptr_t>(p.u0 + p.bc.g) % 16 == 0) &&
+                       (p.ld % 2 == 0);
+  q.vec_ok = aligned ? 1 : 0;
+  const size_t smem = sizeof(double) * (pad_index<R>(tile_cells + 2 * kHalo) + 1 +
+                                        2 * (threads + 1) + 8 + 2);
+  const long long blocks = static_cast<long long>(q.tiles_per_row) * batch;
+  if (blocks > 2147483647LL) return PSK_E_INVALID;
+  stage_tile_kernel<EQ, FLUX, REC, STRICT, R>
+      <<<static_cast<unsigned>(blocks), threads, smem, st>>>(q);
+  PSK_CUDA_OK(cudaGetLastError());
+  if (ghost_rows) {
+    const int total = batch * 2 * p.bc.g;
+    ghost_rows_kernel<EQ, FLUX, REC, STRICT><<<(total + 127) / 128, 128, 0, st>>>(q, batch);
+    PSK_CUDA_OK(cudaGetLastError());
+  }
+  return PSK_OK;
+}
+
+template <int EQ, int FLUX, bool STRICT>
+int dispatch_rec(int rec, const StageParams &p, int batch, int ghost_rows, cudaStream_t st) {
+  switch (rec) {
+    case PSK_REC_CONSTANT:
+      return launch_stage<EQ, FLUX, PSK_REC_CONSTANT, STRICT>(p, batch, ghost_rows, st);
+    case PSK_REC_WENOJS32:
+      return launch_stage<EQ, FLUX, PSK_REC_WENOJS32, STRICT>(p, batch, ghost_rows, st);
+    default:
+      return launch_stage<EQ, FLUX, PSK_REC_WENOJS53, STRICT>(p, batch, ghost_rows, st);
+  }
+}
+
+template <bool STRICT>
+int dispatch_scheme(const psk_desc *d, const StageParams &p, int ghost_rows, cudaStream_t st) {
+  const int b = d->batch;
+  if (d->equation == PSK_EQ_ADVECTION)
+    return dispatch_rec<PSK_EQ_ADVECTION, PSK_FLUX_UPWIND, STRICT>(d->rec, p, b, ghost_rows, st);
+  if (d->equation == PSK_EQ_CONTINUITY)
+    return dispatch_rec<PSK_EQ_CONTINUITY, PSK_FLUX_UPWIND, STRICT>(d->rec, p, b, ghost_rows, st);
+  switch (d->flux) {
+    case PSK_FLUX_RUSANOV:
+      return dispatch_rec<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV, STRICT>(d->rec, p, b, ghost_rows, st);
+    case PSK_FLUX_LAX_FRIEDRICHS:
+      return dispatch_rec<PSK_EQ_BURGERS, PSK_FLUX_LAX_FRIEDRICHS, STRICT>(d->rec, p, b,
+                                                                           ghost_rows, st);
+    case PSK_FLUX_UPWIND:
+      return dispatch_rec<PSK_EQ_BURGERS, PSK_FLUX_UPWIND, STRICT>(d->rec, p, b, ghost_rows, st);
+    default:
+      return dispatch_rec<PSK_EQ_BURGERS, PSK_FLUX_ENGQUIST_OSHER, STRICT>(d->rec, p, b,
+                                                                           ghost_rows, st);
+  }
+}
+
+static StageParams make_params(const psk_desc *d) {
+  StageParams p{};
+  p.nu = d->nu;
+  p.vel = d->velocity;
+  p.vel_l = d->vel_l;
+  p.vel_r = d->vel_r;
+  p.bc = make_bc_view(d);
+  p.ld = d->ld;
+  p.dx = d->dx;
+  p.invdx = 1.0 / d->dx;
+  p.eps = d->eps;
+  return p;
+}
+
+// ---------------------------------------------------------------------------
+// small parity kernels (one thread per output entry)
+
+__global__ void apply_boundary_kernel(BcView b, const double *u, double *w, int64_t ld, int batch) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(batch) * b.nx) return;
+  const int row = static_cast<int>(idx / b.nx);
+  const int i = static_cast<int>(idx - static_cast<int64_t>(row) * b.nx);
+  const double val = load_w(b, u + static_cast<int64_t>(row) * ld, row, i);
+  if (w != u || i < b.g || i >= b.nx - b.g) w[static_cast<int64_t>(row) * ld + i] = val;
+}
+
+template <int REC, bool STRICT>
+__global__ void reconstruct_kernel(const double *f, double *fl, double *fr, int nx, int64_t ld,
+                                   int batch, double eps) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(batch) * nx) return;
+  const int row = static_cast<int>(idx / nx);
+  const int i = static_cast<int>(idx - static_cast<int64_t>(row) * nx);
+  const double *r = f + static_cast<int64_t>(row) * ld;
+  auto at = [&](int k) { return (k < 0 || k >= nx) ? 0.0 : r[k]; };
+  Weno5Pair o = reconstruct_cell<REC, STRICT>(at(i - 2), at(i - 1), at(i), at(i + 1), at(i + 2), eps);
+  fl[static_cast<int64_t>(row) * ld + i] = o.ul;
+  fr[static_cast<int64_t>(row) * ld + i] = o.ur;
+}
+
+// F[k], k = 0..nx, from w (ghost cells already set): BcView with bc = NONE
+template <int EQ, int FLUX, int REC, bool STRICT>
+__global__ void numerical_flux_kernel(const StageParams p, double *F, int64_t ld_f, int batch) {
+  const int nf = p.bc.nx + 1;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(batch) * nf) return;
+  const int row = static_cast<int>(idx / nf);
+  const int k = static_cast<int>(idx - static_cast<int64_t>(row) * nf);
+  double val = 0.0;
+  if (k >= 1 && k <= p.bc.nx - 1) {
+    const int j = k - 1;
+    const double *urow = p.uin + static_cast<int64_t>(row) * p.ld;
+    double w[6];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) w[m] = load_w(p.bc, urow, row, j - 2 + m);
+    Weno5Pair a = reconstruct_cell<REC, STRICT>(w[0], w[1], w[2], w[3], w[4], p.eps);
+    Weno5Pair b = reconstruct_cell<REC, STRICT>(w[1], w[2], w[3], w[4], w[5], p.eps);
+    const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
+    double nu = (p.nu != nullptr) ? p.nu[j] : 1.0;
+    double arj = (EQ != PSK_EQ_BURGERS) ? p.vel_r[j] : 0.0;
+    double alp = (EQ != PSK_EQ_BURGERS) ? p.vel_l[j + 1] : 0.0;
+    val = face_flux<EQ, FLUX, STRICT>(a.ur, b.ul, w[2], w[3], speed, nu, arj, alp);
+  }
+  F[static_cast<int64_t>(row) * ld_f + k] = val;
+}
+
+template <int EQ, int FLUX, bool STRICT>
+int launch_flux_rec(int rec, const StageParams &p, double *F, int64_t ld_f, int batch,
+                    cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(batch) * (p.bc.nx + 1);
+  const unsigned blocks = static_cast<unsigned>((total + 127) / 128);
+  switch (rec) {
+    case PSK_REC_CONSTANT:
+      numerical_flux_kernel<EQ, FLUX, PSK_REC_CONSTANT, STRICT><<<blocks, 128, 0, st>>>(p, F, ld_f, batch);
+      break;
+    case PSK_REC_WENOJS32:
+      numerical_flux_kernel<EQ, FLUX, PSK_REC_WENOJS32, STRICT><<<blocks, 128, 0, st>>>(p, F, ld_f, batch);
+      break;
+    default:
+      numerical_flux_kernel<EQ, FLUX, PSK_REC_WENOJS53, STRICT><<<blocks, 128, 0, st>>>(p, F, ld_f, batch);
+  }
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
+template <bool STRICT>
+int launch_flux(const psk_desc *d, const StageParams &p, double *F, int64_t ld_f, cudaStream_t st) {
+  const int b = d->batch;
+  if (d->equation == PSK_EQ_ADVECTION)
+    return launch_flux_rec<PSK_EQ_ADVECTION, PSK_FLUX_UPWIND, STRICT>(d->rec, p, F, ld_f, b, st);
+  if (d->equation == PSK_EQ_CONTINUITY)
+    return launch_flux_rec<PSK_EQ_CONTINUITY, PSK_FLUX_UPWIND, STRICT>(d->rec, p, F, ld_f, b, st);
+  switch (d->flux) {
+    case PSK_FLUX_RUSANOV:
+      return launch_flux_rec<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV, STRICT>(d->rec, p, F, ld_f, b, st);
+    case PSK_FLUX_LAX_FRIEDRICHS:
+      return launch_flux_rec<PSK_EQ_BURGERS, PSK_FLUX_LAX_FRIEDRICHS, STRICT>(d->rec, p, F, ld_f, b, st);
+    case PSK_FLUX_UPWIND:
+      return launch_flux_rec<PSK_EQ_BURGERS, PSK_FLUX_UPWIND, STRICT>(d->rec, p, F, ld_f, b, st);
+    default:
+      return launch_flux_rec<PSK_EQ_BURGERS, PSK_FLUX_ENGQUIST_OSHER, STRICT>(d->rec, p, F, ld_f, b, st);
+  }
+}
+
+// max |w| per row; mode 0: all nx stored cells, 1: interior cells, 2: all nx cells after the
+// boundary condition (the speed of the global Lax-Friedrichs flux, scalar.py:277)
+__global__ void max_abs_kernel(BcView b, const double *u, int64_t ld, int mode,
+                               unsigned long long *out, int chunks_per_row) {
+  const int row = blockIdx.x / chunks_per_row;
+  const int chunk = blockIdx.x - row * chunks_per_row;
+  const double *urow = u + static_cast<int64_t>(row) * ld;
+  const int lo = (mode == 1) ? b.g : 0;
+  const int hi = (mode == 1) ? b.nx - b.g : b.nx;
+  const int per = (hi - lo + chunks_per_row - 1) / chunks_per_row;
+  const int a = lo + chunk * per;
+  const int z = min(hi, a + per);
+  unsigned long long m = 0ull;
+  for (int i = a + threadIdx.x; i < z; i += blockDim.x) {
+    const double val = (mode == 2) ? load_w(b, urow, row, i) : urow[i];
+    const unsigned long long bits = abs_bits(val);
+    m = bits > m ? bits : m;
+  }
+  __shared__ unsigned long long wm[32];
+  m = warp_max_bits(m);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) wm[wid] = m;
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    unsigned long long m2 = lane < nw ? wm[lane] : 0ull;
+    m2 = warp_max_bits(m2);
+    if (lane == 0) atomicMax(out + row, m2);
+  }
+}
+
+static int launch_max_abs(const psk_desc *d, const double *u, int mode, double *out,
+                          cudaStream_t st) {
+  PSK_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double) * d->batch, st));
+  const int nx = d->n + 2 * d->g;
+  int chunks = 1;
+  // enough CTAs to fill the machine when there are few rows
+  while (static_cast<long long>(chunks) * d->batch < 2 * kSMs && nx / (chunks * 2) >= 2048) chunks *= 2;
+  const int threads = nx >= 1024 ? 256 : 128;
+  max_abs_kernel<<<static_cast<unsigned>(chunks) * d->batch, threads, 0, st>>>(
+      make_bc_view(d), u, d->ld, mode, reinterpret_cast<unsigned long long *>(out), chunks);
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
+int launch_max_abs_public(const psk_desc *d, const double *u, int mode, double *out,
+                          cudaStream_t st) {
+  return launch_max_abs(d, u, mode, out, st);
+}
+
+// timestepping.py:139-150 on the device, one thread per row
+__global__ void step_control_kernel(int batch, double theta, double cfl_scale, double tfinal,
+                                    const double *maxabs, const double *t, double *t_next,
+                                    double *dt, uint8_t *active, int *nonfinite) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= batch) return;
+  const double tr = t[r];
+  if (tr >= tfinal) {  // timestepping.py:133-134
+    active[r] = 0;
+    dt[r] = 0.0;
+    t_next[r] = tr;
+    return;
+  }
+  double step = __dmul_rn(theta, __ddiv_rn(cfl_scale, maxabs[r]));
+  const double dt_min = __dadd_rn(tfinal, -tr);
+  step = __dadd_rn(step < dt_min ? step : dt_min, 1.0e-15);  // timestepping.py:140-142
+  if (!isfinite(step)) atomicOr(nonfinite, 1);                // timestepping.py:144-145
+  active[r] = 1;
+  dt[r] = step;
+  t_next[r] = __dadd_rn(tr, step);
+}
+
+}  // namespace psk
+
+// ===========================================================================
+// C ABI
+
+using namespace psk;
+
+extern "C" {
+
+int psk_version(void) { return PSK_VERSION; }
+
+const char *psk_status_string(int status) {
+  switch (status) {
+    case PSK_OK: return "ok";
+    case PSK_E_INVALID: return "invalid argument";
+    case PSK_E_UNSUPPORTED: return "outside the supported hot path";
+    case PSK_E_CUDA: return "CUDA runtime error";
+    case PSK_E_NONFINITE: return "time step is not finite";
+    default: return "unknown status";
+  }
+}
+
+int psk_last_cuda_error(void) { return g_last_cuda_error; }
+
+int psk_apply_boundary(const psk_desc *d, const double *u, double *w, psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (u == nullptr || w == nullptr) return PSK_E_INVALID;
+  const BcView b = make_bc_view(d);
+  const int64_t total = static_cast<int64_t>(d->batch) * b.nx;
+  apply_boundary_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(b, u, w, d->ld, d->batch);
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
+int psk_reconstruct(const psk_desc *d, const double *f, double *fl, double *fr,
+                    psk_stream_t stream) {
+  if (d == nullptr || f == nullptr || fl == nullptr || fr == nullptr) return PSK_E_INVALID;
+  if (d->n <= 0 || d->batch <= 0 || d->g < 0 || d->ld < d->n + 2 * d->g) return PSK_E_INVALID;
+  if (d->rec < PSK_REC_CONSTANT || d->rec > PSK_REC_WENOJS53) return PSK_E_UNSUPPORTED;
+  const int nx = d->n + 2 * d->g;
+  const int64_t total = static_cast<int64_t>(d->batch) * nx;
+  const unsigned blocks = static_cast<unsigned>((total + 127) / 128);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool strict = d->math == PSK_MATH_STRICT;
+#define PSK_REC_LAUNCH(REC)                                                                  \
+  if (strict)                                                                                \
+    reconstruct_kernel<REC, true><<<blocks, 128, 0, st>>>(f, fl, fr, nx, d->ld, d->batch, d->eps); \
+  else                                                                                       \
+    reconstruct_kernel<REC, false><<<blocks, 128, 0, st>>>(f, fl, fr, nx, d->ld, d->batch, d->eps)
+  switch (d->rec) {
+    case PSK_REC_CONSTANT: PSK_REC_LAUNCH(PSK_REC_CONSTANT); break;
+    case PSK_REC_WENOJS32: PSK_REC_LAUNCH(PSK_REC_WENOJS32); break;
+    default: PSK_REC_LAUNCH(PSK_REC_WENOJS53);
+  }
+#undef PSK_REC_LAUNCH
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
+int psk_max_abs(const psk_desc *d, const double *u, int interior_only, double *out,
+                psk_stream_t stream) {
+  if (d == nullptr || u == nullptr || out == nullptr) return PSK_E_INVALID;
+  if (d->n <= 0 || d->batch <= 0 || d->g < 0 || d->ld < d->n + 2 * d->g) return PSK_E_INVALID;
+  if (interior_only == 2) {
+    int rc = check_desc(d);
+    if (rc != PSK_OK) return rc;
+  }
+  return launch_max_abs(d, u, interior_only, out, static_cast<cudaStream_t>(stream));
+}
+
+// global Lax-Friedrichs speed max |w| over all nx cells after the BC (scalar.py:277)
+static int lf_speed_pass(const psk_desc *d, const double *u, int bc_applied, double *lf_work,
+                         cudaStream_t st) {
+  if (d->equation != PSK_EQ_BURGERS || d->flux != PSK_FLUX_LAX_FRIEDRICHS) return PSK_OK;
+  if (lf_work == nullptr) return PSK_E_INVALID;
+  return launch_max_abs(d, u, bc_applied ? 0 : 2, lf_work, st);
+}
+
+int psk_numerical_flux(const psk_desc *d, const double *w, double *flux, int64_t ld_f,
+                       double *lf_work, psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (w == nullptr || flux == nullptr || ld_f < d->n + 2 * d->g + 1) return PSK_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = lf_speed_pass(d, w, 1, lf_work, st);
+  if (rc != PSK_OK) return rc;
+  StageParams p = make_params(d);
+  p.bc.bc = PSK_BC_NONE;  // the caller has applied the boundary condition already
+  p.uin = w;
+  p.lf_speed = lf_work;
+  return d->math == PSK_MATH_STRICT ? launch_flux<true>(d, p, flux, ld_f, st)
+                                    : launch_flux<false>(d, p, flux, ld_f, st);
+}
+
+int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const double *uin,
+                      double *uout, const double *dt, int64_t dt_stride, const uint8_t *active,
+                      double *lf_work, double *maxabs, int ghost_rows, psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (stage < 0 || stage > 3 || uin == nullptr || uout == nullptr) return PSK_E_INVALID;
+  if (stage != 0 && dt == nullptr) return PSK_E_INVALID;
+  if (stage >= 2 && u0 == nullptr) return PSK_E_INVALID;
+  if (uout == uin) return PSK_E_INVALID;  // tiles read their neighbours' cells
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = lf_speed_pass(d, uin, 0, lf_work, st);
+  if (rc != PSK_OK) return rc;
+  StageParams p = make_params(d);
+  p.uin = uin;
+  p.u0 = u0;
+  p.uout = uout;
+  p.dt = dt;
+  p.dt_stride = dt_stride;
+  p.active = active;
+  p.lf_speed = lf_work;
+  p.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
+  p.stage = stage;
+  return d->math == PSK_MATH_STRICT ? dispatch_scheme<true>(d, p, ghost_rows, st)
+                                    : dispatch_scheme<false>(d, p, ghost_rows, st);
+}
+
+int psk_apply_operator(const psk_desc *d, const double *u, double *rhs, double *lf_work,
+                       psk_stream_t stream) {
+  return psk_ssprk33_stage(d, 0, nullptr, u, rhs, nullptr, 0, nullptr, lf_work, nullptr, 1,
+                           stream);
+}
+
+int psk_step_control(int32_t batch, double theta, double cfl_scale, double tfinal,
+                     const double *maxabs, const double *t, double *t_next, double *dt,
+                     uint8_t *active, int32_t *nonfinite, psk_stream_t stream) {
+  if (batch <= 0 || maxabs == nullptr || t == nullptr || t_next == nullptr || dt == nullptr ||
+      active == nullptr || nonfinite == nullptr)
+    return PSK_E_INVALID;
+  step_control_kernel<<<(batch + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      batch, theta, cfl_scale, tfinal, maxabs, t, t_next, dt, active, nonfinite);
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+"""`HotPath`: one bound (equation, flux, reconstruction, boundary kind, grid) on the GPU.
+
+This is the layer right above the C ABI: it owns the small device-side tables a
+scheme needs (per-face dissipation ``nu``, velocity and its reconstruction, ghost
+data), builds the ``psk_desc`` for each call and launches the kernels of
+``libpsk.so`` on the current torch CUDA stream.  The pyshocks-shaped API
+(``apply_operator``, ``advance``, ...) in the sibling modules dispatches here.
+
+All state arrays are ``torch.float64`` CUDA tensors of shape ``(nx,)`` or
+``(batch, nx)`` with ``nx = n + 2 g`` (ghost cells included, as in the reference).
+"""
+
+from __future__ import annotations
+
+import ctypes as ct
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+_EQ = {"burgers": L.EQ_BURGERS, "advection": L.EQ_ADVECTION, "continuity": L.EQ_CONTINUITY}
+_FLUX = {
+    "rusanov": L.FLUX_RUSANOV,
+    "lf": L.FLUX_LAX_FRIEDRICHS,
+    "godunov": L.FLUX_UPWIND,
+    "upwind": L.FLUX_UPWIND,
+    "eo": L.FLUX_ENGQUIST_OSHER,
+}
+_REC = {"constant": L.REC_CONSTANT, "wenojs32": L.REC_WENOJS32, "wenojs53": L.REC_WENOJS53}
+_BC = {"periodic": L.BC_PERIODIC, "dirichlet": L.BC_DIRICHLET, "neumann": L.BC_NEUMANN, "none": L.BC_NONE}
+_MATH = {"fast": L.MATH_FAST, "strict": L.MATH_STRICT}
+
+
+def _dev(device: torch.device | str | None) -> torch.device:
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("pyshocks_b200 needs a CUDA device (B200); there is no CPU fallback")
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _like(u: torch.Tensor) -> torch.Tensor:
+    """uninitialised array with the shape AND row stride of ``u`` (views of padded storage
+    keep their stride, so all arrays of one launch share ``ld``)"""
+    return torch.empty_strided(u.shape, u.stride(), dtype=u.dtype, device=u.device)
+
+
+class HotPath:
+    def __init__(
+        self,
+        *,
+        equation: str,
+        flux: str,
+        rec: str,
+        bc: str,
+        n: int,
+        g: int,
+        dx: float,
+        eps: float,
+        math: str = "fast",
+        nu: np.ndarray | torch.Tensor | None = None,
+        velocity: np.ndarray | torch.Tensor | None = None,
+        device: torch.device | str | None = None,
+    ) -> None:
+        self.device = _dev(device)
+        self.equation, self.flux, self.rec, self.bc, self.math = equation, flux, rec, bc, math
+        self.n, self.g, self.nx = int(n), int(g), int(n) + 2 * int(g)
+        self.dx, self.eps = float(dx), float(eps)
+        self._nu = None if nu is None else self._table(nu)
+        self._vel = self._vel_l = self._vel_r = None
+        self._ghost: torch.Tensor | None = None
+        self._ghost_ld = 0
+        self._work: dict[tuple, torch.Tensor] = {}
+        if velocity is not None:
+            self._vel = self._table(velocity)
+            if self._vel.numel() != self.nx:
+                raise ValueError("velocity must have nx = n + 2 g entries")
+            # reconstruct(rec, grid, bc, a, a, a) once: velocity does not depend on time
+            # (advection/schemes.py:104-105, continuity/schemes.py:100-101)
+            self._vel_l, self._vel_r = self.reconstruct(self._vel)
+        elif equation != "burgers":
+            raise ValueError(f"{equation} schemes need a velocity array")
+
+    # {{{ helpers
+
+    def _table(self, a: np.ndarray | torch.Tensor) -> torch.Tensor:
+        if isinstance(a, torch.Tensor):
+            return a.detach().to(device=self.device, dtype=torch.float64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+
+    def workspace(self, key: str, shape: Sequence[int], dtype: torch.dtype = torch.float64) -> torch.Tensor:
+        k = (key, tuple(shape), dtype)
+        buf = self._work.get(k)
+        if buf is None:
+            buf = torch.zeros(tuple(shape), dtype=dtype, device=self.device)
+            self._work[k] = buf
+        return buf
+
+    def set_ghost(self, values: np.ndarray | torch.Tensor | None) -> None:
+        """Dirichlet values / Neumann offsets for the next calls: ``(2g,)`` shared by all
+        rows or ``(batch, 2g)``; left ghosts first (include/psk.h, enum psk_bc)."""
+        if values is None:
+            self._ghost, self._ghost_ld = None, 0
+            return
+        gh = self._table(values)
+        if gh.shape[-1] != 2 * self.g:
+            raise ValueError(f"ghost data needs 2 g = {2 * self.g} values per row")
+        self._ghost = gh
+        self._ghost_ld = 0 if gh.dim() == 1 else gh.stride(0)
+
+    def desc(self, batch: int, ld: int, *, bc: int | None = None) -> L.PskDesc:
+        d = L.PskDesc()
+        d.equation, d.flux, d.rec = _EQ[self.equation], _FLUX[self.flux], _REC[self.rec]
+        d.bc = _BC[self.bc] if bc is None else bc
+        d.math = _MATH[self.math]
+        d.n, d.g, d.batch, d.ld = self.n, self.g, batch, ld
+        d.dx, d.eps = self.dx, self.eps
+        d.nu = L.ptr(self._nu)
+        d.velocity, d.vel_l, d.vel_r = L.ptr(self._vel), L.ptr(self._vel_l), L.ptr(self._vel_r)
+        d.ghost, d.ghost_ld = L.ptr(self._ghost), self._ghost_ld
+        return d
+
+    def _state(self, u: torch.Tensor) -> tuple[int, int]:
+        batch, nx, ld = L.rows_of(u)
+        if nx != self.nx:
+            raise ValueError(f"array has {nx} cells per row, grid has nx = {self.nx}")
+        L.ptr(u)
+        if self._ghost is not None and self._ghost.dim() == 2 and self._ghost.shape[0] != batch:
+            raise ValueError("per-row ghost data does not match the batch size")
+        return batch, ld
+
+    def _lf_work(self, batch: int) -> torch.Tensor | None:
+        if self.equation == "burgers" and self.flux == "lf":
+            return self.workspace("lf", (batch,))
+        return None
+
+    # }}}
+
+    # {{{ parity entry points
+
+    def apply_boundary(self, u: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        batch, ld = self._state(u)
+        w = _like(u) if out is None else out
+        if L.rows_of(w)[2] != ld:
+            raise ValueError("output must share the row stride of the input")
+        d = self.desc(batch, ld)
+        L.check("psk_apply_boundary", L.lib().psk_apply_boundary(ct.byref(d), L.ptr(u), L.ptr(w), L.stream_ptr()))
+        return w
+
+    def reconstruct(self, f: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        batch, nx, ld = L.rows_of(f)
+        if nx != self.nx:
+            raise ValueError(f"array has {nx} cells per row, grid has nx = {self.nx}")
+        fl, fr = torch.empty_like(f), torch.empty_like(f)
+        if L.rows_of(fl)[2] != ld:
+            f = f.contiguous()
+            fl, fr = torch.empty_like(f), torch.empty_like(f)
+            ld = L.rows_of(f)[2]
+        d = self.desc(batch, ld)
+        L.check("psk_reconstruct", L.lib().psk_reconstruct(ct.byref(d), L.ptr(f), L.ptr(fl), L.ptr(fr), L.stream_ptr()))
+        return fl, fr
+
+    def numerical_flux(self, w: torch.Tensor) -> torch.Tensor:
+        batch, ld = self._state(w)
+        shape = (self.nx + 1,) if w.dim() == 1 else (batch, self.nx + 1)
+        F = torch.empty(shape, dtype=torch.float64, device=w.device)
+        d = self.desc(batch, ld, bc=L.BC_NONE)  # w already carries its boundary data
+        L.check(
+            "psk_numerical_flux",
+            L.lib().psk_numerical_flux(
+                ct.byref(d), L.ptr(w), L.ptr(F), self.nx + 1, L.ptr(self._lf_work(batch)), L.stream_ptr()
+            ),
+        )
+        return F
+
+    def apply_operator(self, u: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        batch, ld = self._state(u)
+        rhs = _like(u) if out is None else out
+        if L.rows_of(rhs)[2] != ld:
+            raise ValueError("output must share the row stride of the input")
+        d = self.desc(batch, ld)
+        L.check(
+            "psk_apply_operator",
+            L.lib().psk_apply_operator(ct.byref(d), L.ptr(u), L.ptr(rhs), L.ptr(self._lf_work(batch)), L.stream_ptr()),
+        )
+        return rhs
+
+    def max_abs(self, u: torch.Tensor, mode: int = 1, out: torch.Tensor | None = None) -> torch.Tensor:
+        batch, ld = self._state(u)
+        res = torch.empty((batch,), dtype=torch.float64, device=u.device) if out is None else out
+        d = self.desc(batch, ld)
+        L.check("psk_max_abs", L.lib().psk_max_abs(ct.byref(d), L.ptr(u), mode, L.ptr(res), L.stream_ptr()))
+        return res
+
+    # }}}
+
+    # {{{ discrete adjoint
+
+    def _adj_work(self, batch: int) -> torch.Tensor:
+        return self.workspace("adj", (batch * (2 * self.g + 2),))
+
+    def apply_operator_vjp(self, u: torch.Tensor, v: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """``J_L(u)^T v`` for ``L = apply_operator`` (what ``jax.vjp(apply_operator)`` returns)."""
+        batch, ld = self._state(u)
+        res = _like(u) if out is None else out
+        if L.rows_of(v)[2] != ld or L.rows_of(res)[2] != ld:
+            raise ValueError("all arrays must share one row stride")
+        d = self.desc(batch, ld)
+        L.check(
+            "psk_apply_operator_vjp",
+            L.lib().psk_apply_operator_vjp(
+                ct.byref(d), L.ptr(u), L.ptr(v), L.ptr(res), L.ptr(self._adj_work(batch)), L.stream_ptr()
+            ),
+        )
+        return res
+
+    def stage_adjoint(
+        self,
+        x: torch.Tensor,
+        v: torch.Tensor,
+        dt: torch.Tensor,
+        c_v: float,
+        out: torch.Tensor,
+        *,
+        acc: torch.Tensor | None = None,
+        c_acc: float = 0.0,
+        acc2: torch.Tensor | None = None,
+        c_acc2: float = 0.0,
+    ) -> torch.Tensor:
+        """``out = c_acc acc + c_acc2 acc2 + c_v (v + dt J_L(x)^T v)`` in one launch."""
+        batch, ld = self._state(x)
+        for a in (v, out, acc, acc2):
+            if a is not None and L.rows_of(a)[2] != ld:
+                raise ValueError("all arrays must share one row stride")
+        d = self.desc(batch, ld)
+        L.check(
+            "psk_ssprk33_stage_adjoint",
+            L.lib().psk_ssprk33_stage_adjoint(
+                ct.byref(d), L.ptr(x), L.ptr(v), L.ptr(dt), 0 if dt.numel() == 1 else 1, float(c_v),
+                L.ptr(acc), float(c_acc), L.ptr(acc2), float(c_acc2), L.ptr(self._adj_work(batch)),
+                L.ptr(out), L.stream_ptr(),
+            ),
+        )
+        return out
+
+    def ssprk33_step_adjoint(
+        self,
+        u: torch.Tensor,
+        dt: torch.Tensor,
+        p: torch.Tensor,
+        *,
+        out: torch.Tensor | None = None,
+        ghosts: Sequence[np.ndarray | torch.Tensor] | None = None,
+        stages: tuple[torch.Tensor, torch.Tensor] | None = None,
+    ) -> torch.Tensor:
+        """``(d advance / d u)^T p`` for one SSPRK33 step from the checkpointed state ``u``
+        (timestepping.py:205-206 without the dense Jacobian): recompute ``k1, k2``, then three
+        fused adjoint stages."""
+        if stages is None:
+            k1, k2 = _like(u), _like(u)
+            if ghosts is not None:
+                self.set_ghost(ghosts[0])
+            self.stage(1, u, u, k1, dt, ghost_rows=True)
+            if ghosts is not None:
+                self.set_ghost(ghosts[1])
+            self.stage(2, u, k1, k2, dt, ghost_rows=True)
+        else:
+            k1, k2 = stages
+        lam2, lam1 = _like(u), _like(u)
+        res = _like(u) if out is None else out
+        if ghosts is not None:
+            self.set_ghost(ghosts[2])
+        self.stage_adjoint(k2, p, dt, 2.0 / 3.0, lam2)
+        if ghosts is not None:
+            self.set_ghost(ghosts[1])
+        self.stage_adjoint(k1, lam2, dt, 1.0 / 4.0, lam1)
+        if ghosts is not None:
+            self.set_ghost(ghosts[0])
+        self.stage_adjoint(u, lam1, dt, 1.0, res, acc=p, c_acc=1.0 / 3.0, acc2=lam2, c_acc2=3.0 / 4.0)
+        return res
+
+    # }}}
+
+    # {{{ fused SSPRK33
+
+    def stage(
+        self,
+        stage: int,
+        u0: torch.Tensor | None,
+        uin: torch.Tensor,
+        uout: torch.Tensor,
+        dt: torch.Tensor | None,
+        *,
+        active: torch.Tensor | None = None,
+        maxabs: torch.Tensor | None = None,
+        ghost_rows: bool = False,
+    ) -> torch.Tensor:
+        batch, ld = self._state(uin)
+        if L.rows_of(uout)[2] != ld or (u0 is not None and L.rows_of(u0)[2] != ld):
+            raise ValueError("all stage arrays must share one row stride")
+        dt_stride = 0 if (dt is None or dt.numel() == 1) else 1
+        d = self.desc(batch, ld)
+        L.check(
+            "psk_ssprk33_stage",
+            L.lib().psk_ssprk33_stage(
+                ct.byref(d), stage, L.ptr(u0), L.ptr(uin), L.ptr(uout), L.ptr(dt), dt_stride,
+                L.raw_ptr(active), L.ptr(self._lf_work(batch)), L.ptr(maxabs), int(ghost_rows), L.stream_ptr(),
+            ),
+        )
+        return uout
+
+    def ssprk33_step(
+        self,
+        u: torch.Tensor,
+        dt: torch.Tensor,
+        *,
+        out: torch.Tensor | None = None,
+        ghosts: Sequence[np.ndarray | torch.Tensor] | None = None,
+        active: torch.Tensor | None = None,
+        maxabs: torch.Tensor | None = None,
+        ghost_rows: bool = False,
+        keep_stages: bool = False,
+    ) -> torch.Tensor | tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """One SSPRK33 step (timestepping.py:312-320) as three fused launches.
+
+        ``ghosts``: Dirichlet / Neumann data at the stage times ``t, t + dt, t + dt/2``.
+        """
+        k1, k2 = _like(u), _like(u)
+        res = _like(u) if out is None else out
+        if active is not None:
+            res.copy_(u)  # rows that are switched off keep their state
+        for s, (src, dst) in enumerate(((u, k1), (k1, k2), (k2, res)), start=1):
+            if ghosts is not None:
+                self.set_ghost(ghosts[s - 1])
+            self.stage(s, u, src, dst, dt, active=active, maxabs=maxabs if s == 3 else None, ghost_rows=ghost_rows)
+        return (k1, k2, res) if keep_stages else res
+
+    # }}}

@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the pyshocks hot path on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the configuration the metric "WENO5 Burgers
+cell-updates/s" is quoted on): an ensemble of B = 65536 independent inviscid Burgers
+problems x N = 4096 cells, fp64, WENO-JS5 + Rusanov (LLF) + SSPRK33, periodic, random
+smooth initial data, one shared fixed dt at CFL 0.4.  One "step" = one full SSPRK33 step
+(3 fused stage launches) of every cell of the ensemble.  With N GPUs every rank advances
+its own B rows (weak scaling, no collective in the data path).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
+reference path (oracle/psk_oracle.c, all host threads) on a bounded sample of the same
+workload; the reference itself is Python-on-JAX and JAX is not installable here.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "WENO5 Burgers cell-updates/s"
+UNIT = "cell-updates/s"
+N_CELLS = 4096
+GHOSTS = 3
+BATCH = 65536
+DOMAIN = (-1.5, 1.5)
+EPS = 1.0e-12
+CFL = 0.4
+ALGO_BYTES_PER_CELL_UPDATE = 64.0  # 16 + 24 + 24 B over the three stages
+
+
+def measured_peaks() -> tuple[float, str]:
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ensemble_coefficients(batch: int, seed: int) -> np.ndarray:
+    """c_b, A_{b,1..4}, phi_{b,1..4} of u0_b(x) = c_b + sum_k A_bk sin(2 pi k xhat + phi_bk)."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-0.5, 0.5, size=(batch, 1))
+    amp = rng.uniform(0.0, 1.0, size=(batch, 4)) / np.arange(1, 5)
+    phi = rng.uniform(0.0, 2.0 * np.pi, size=(batch, 4))
+    return np.concatenate([c, amp, phi], axis=1)
+
+
+def host_initial_condition(coef: np.ndarray, n: int, g: int) -> np.ndarray:
+    nx = n + 2 * g
+    xhat = (np.arange(nx) - g + 0.5) / n
+    u = np.repeat(coef[:, :1], nx, axis=1)
+    for k in range(4):
+        u += coef[:, 1 + k : 2 + k] * np.sin(2.0 * np.pi * (k + 1) * xhat[None, :] + coef[:, 5 + k : 6 + k])
+    return u
+
+
+# {{{ reference arm / cpu baseline: the C restatement on the host cores
+
+
+def cpu_port_throughput(target_seconds: float, steps: int | None = None) -> dict:
+    from oracle.c_oracle import COracle
+
+    cores = len(os.sched_getaffinity(0))
+    h = (DOMAIN[1] - DOMAIN[0]) / N_CELLS
+    # calibrate on a small slice, then size the sample
+    rows = max(cores, 8)
+    coef = ensemble_coefficients(rows, 20261017)
+    u0 = host_initial_condition(coef, N_CELLS, GHOSTS)
+    dt = CFL * h / np.abs(u0).max()
+    co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS, g=GHOSTS,
+                 batch=rows, dx=h, eps=EPS)
+    t0 = time.perf_counter()
+    co.solve_fixed_dt(u0, dt, 1)
+    rate = rows * N_CELLS / (time.perf_counter() - t0)  # cell-updates/s with all threads
+    nsteps = steps if steps is not None else 4
+    rows_s = int(min(BATCH, target_seconds * rate / (N_CELLS * nsteps)))
+    rows_s = max(cores, (rows_s // cores) * cores)
+    coef = ensemble_coefficients(rows_s, 20261017)
+    u0 = host_initial_condition(coef, N_CELLS, GHOSTS)
+    co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS, g=GHOSTS,
+                 batch=rows_s, dx=h, eps=EPS)
+    t0 = time.perf_counter()
+    co.solve_fixed_dt(u0, dt, nsteps)
+    wall = time.perf_counter() - t0
+    return {
+        "value": rows_s * N_CELLS * nsteps / wall,
+        "unit": UNIT,
+        "cores": cores,
+        "kind": "port",
+        "sample": f"{rows_s} rows x {N_CELLS} cells x {nsteps} SSPRK33 steps of the same ensemble "
+                  f"(C restatement oracle/psk_oracle.c, OpenMP over rows, {wall:.1f} s)",
+    }
+
+
+def run_reference(args: argparse.Namespace) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.c_oracle import COracle
+
+    cores = len(os.sched_getaffinity(0))
+    h = (DOMAIN[1] - DOMAIN[0]) / N_CELLS
+    # a "step" of the reference arm = one SSPRK33 step over a bounded sample of rows
+    rows = max(cores * 8, 64)
+    coef = ensemble_coefficients(rows, 20261017)
+    u0 = host_initial_condition(coef, N_CELLS, GHOSTS)
+    dt = CFL * h / np.abs(u0).max()
+    co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS, g=GHOSTS,
+                 batch=rows, dx=h, eps=EPS)
+    u = u0
+    for _ in range(args.warmup):
+        u = co.solve_fixed_dt(u, dt, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        u = co.solve_fixed_dt(u, dt, 1)
+    wall = time.perf_counter() - t0
+    value = rows * N_CELLS * args.steps / wall
+    sample = f"{rows} of {BATCH} rows x {N_CELLS} cells per step (bounded sample of the same ensemble)"
+    line = {
+        "impl": "reference",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus) | {"reference_arm": "CPU restatement of the reference path "
+                                               "(oracle/psk_oracle.c); JAX is not installable here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# }}}
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": f"batched Burgers ensemble B={BATCH} x N={N_CELLS} cells per GPU, fp64, WENO-JS5 + Rusanov(LLF) "
+                    f"+ SSPRK33, periodic, fixed dt at CFL {CFL} (BASELINE.json configs[2])",
+        "batch_per_gpu": BATCH, "cells": N_CELLS, "ghosts": GHOSTS,
+        "sharding": f"ensemble rows block-partitioned, {n_gpus} rank(s), no data-path collective",
+        "l2": "inputs (2.15 GB per state array) are larger than the 126 MB L2; no flush needed",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for ln in out.strip().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+def run_ours(args: argparse.Namespace) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from pyshocks_b200.ensemble import EnsembleSolver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    batch = args.batch
+    h = (DOMAIN[1] - DOMAIN[0]) / N_CELLS
+    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS,
+                            g=GHOSTS, dx=h, eps=EPS, batch=batch, math="fast", device=dev)
+    nx = solver.nx
+
+    # synthetic initial data of the named shape, evaluated on the device from host-drawn coefficients
+    coef = torch.from_numpy(ensemble_coefficients(batch, 20261017 + rank)).to(dev)
+    xhat = ((torch.arange(nx, device=dev, dtype=torch.float64) - GHOSTS + 0.5) / N_CELLS)[None, :]
+    u0 = coef[:, :1].repeat(1, nx)
+    for k in range(4):
+        u0 += coef[:, 1 + k : 2 + k] * torch.sin(2.0 * np.pi * (k + 1) * xhat + coef[:, 5 + k : 6 + k])
+    umax = u0.abs().max()
+    if world > 1:
+        dist.all_reduce(umax, op=dist.ReduceOp.MAX)
+    dt = torch.full((1,), CFL * h / float(umax), dtype=torch.float64, device=dev)
+    solver.load(u0)
+
+    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps
+    solver.solve_fixed_dt(None, dt, args.warmup)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = solver.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    solver.solve_fixed_dt(None, dt, args.steps)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    launches = solver.launches - launches0
+    clocks = sampler.stop() if sampler is not None else None
+    finite = bool(torch.isfinite(solver.u).all())
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    host_in = torch.empty((batch, nx), dtype=torch.float64, pin_memory=True)
+    host_out = torch.empty((batch, nx), dtype=torch.float64, pin_memory=True)
+    host_in.copy_(u0)
+    del u0
+    barrier()
+    t0 = time.perf_counter()
+    solver.load(host_in, non_blocking=True)
+    solver.solve_fixed_dt(None, dt, args.steps)
+    solver.store(host_out, non_blocking=True)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s)
+    bytes_state = batch * nx * 8
+
+    if rank == 0:
+        cells_per_step = batch * N_CELLS * world
+        value = cells_per_step * args.steps / (ms_total * 1e-3)
+        peak, peak_src = measured_peaks()
+        per_gpu = value / world
+        achieved = per_gpu * ALGO_BYTES_PER_CELL_UPDATE / 1e9
+        traffic = None
+        tf = ROOT / "profiles" / "traffic.json"
+        if tf.exists():
+            traffic = json.loads(tf.read_text()).get("stage_kernel_dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world) | {"batch_per_gpu": batch, "finite": finite},
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "psk::stage_tile_kernel (3 launches per step; 64 algorithmic bytes per cell-update)",
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_UPDATE / 3 * batch * N_CELLS,
+                "avg_launch_ms": ms_total / (3 * args.steps),
+            },
+            "e2e": {
+                "value": cells_per_step * args.steps / e2e_s, "unit": UNIT,
+                "h2d_bytes_per_step": bytes_state / args.steps, "d2h_bytes_per_step": bytes_state / args.steps,
+                "call": "EnsembleSolver.load(pinned host) -> solve_fixed_dt(K steps) -> store(pinned host)",
+                "seconds": e2e_s,
+            },
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_port_throughput(target_seconds=12.0)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--batch", type=int, default=BATCH, help="rows per GPU (default: the named config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", __file__, *sys.argv[1:]]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,9 @@ int psk_version(void);
 const char *psk_status_string(int status);
 /* last cudaError_t seen by this library on the calling thread (0 = none) */
 int psk_last_cuda_error(void);
+/* A/B switch between the two implementations of the fused stage (same results):
+ * 0 = warp-shuffle kernel (default), 1 = shared-memory tile kernel. */
+int psk_set_stage_variant(int variant);
 
 /* apply_boundary(bc, grid, t, u) -> w            schemes.py:431-442, scalar.py BCs.
  * w may alias u. */

@@ -155,18 +155,16 @@ static inline double min_nan(double x, double y) { return (x < y || x != x) ? x 
 
 typedef struct {
   const double *w;
+  const double *ul, *ur; /* reconstruct(w) */
   int nx;
   double lf_speed; /* global max |w| (scalar.py:277) */
 } row_ctx;
 
 static double face_flux(const psk_desc *d, const row_ctx *c, int j) {
   const double *w = c->w;
-  const int nx = c->nx;
-  double ulj, urj, ulp, urp;
-  reconstruct_cell(d->rec, d->eps, w, j, nx, &ulj, &urj);
-  reconstruct_cell(d->rec, d->eps, w, j + 1, nx, &ulp, &urp);
-  (void)ulj;
-  (void)urp;
+  /* reconstruct() returns whole arrays (reconstruction.py:377); the face j+1/2 uses the
+     right value of cell j and the left value of cell j+1 */
+  const double urj = c->ur[j], ulp = c->ul[j + 1];
   if (d->equation == PSK_EQ_BURGERS) {
     switch (d->flux) {
     case PSK_FLUX_RUSANOV:
@@ -209,10 +207,12 @@ static double max_abs_range(const double *w, int lo, int hi) {
   return seen_nan ? NAN : m;
 }
 
-/* F[0..nx]: jnp.pad(fnum, 1) */
-static void flux_row(const psk_desc *d, const double *w, double *F) {
+/* F[0..nx]: jnp.pad(fnum, 1); lr: scratch of 2 nx doubles for the reconstructed arrays */
+static void flux_row(const psk_desc *d, const double *w, double *F, double *lr) {
   const int nx = nx_of(d);
-  row_ctx c = {w, nx, 0.0};
+  double *ul = lr, *ur = lr + nx;
+  for (int i = 0; i < nx; ++i) reconstruct_cell(d->rec, d->eps, w, i, nx, ul + i, ur + i);
+  row_ctx c = {w, ul, ur, nx, 0.0};
   if (d->flux == PSK_FLUX_LAX_FRIEDRICHS && d->equation == PSK_EQ_BURGERS)
     c.lf_speed = max_abs_range(w, 0, nx);
   F[0] = 0.0;
@@ -221,15 +221,17 @@ static void flux_row(const psk_desc *d, const double *w, double *F) {
 }
 
 PSO_API int pso_numerical_flux(const psk_desc *d, const double *w, double *F, int64_t ld_f) {
-  for (int r = 0; r < d->batch; ++r) flux_row(d, w + (size_t)r * d->ld, F + (size_t)r * ld_f);
+  double *lr = (double *)malloc(sizeof(double) * 2 * (size_t)nx_of(d));
+  for (int r = 0; r < d->batch; ++r) flux_row(d, w + (size_t)r * d->ld, F + (size_t)r * ld_f, lr);
+  free(lr);
   return PSK_OK;
 }
 
-/* schemes.py:339-346, advection/schemes.py:62-73; scratch: w[nx], F[nx+1] */
+/* schemes.py:339-346, advection/schemes.py:62-73; scratch: w[nx], F[nx+1 .. 3nx+1] */
 static void rhs_row(const psk_desc *d, int r, const double *u, double *L, double *w, double *F) {
   const int nx = nx_of(d);
   apply_boundary_row(d, r, u, w);
-  flux_row(d, w, F);
+  flux_row(d, w, F, F + nx + 1);
   if (d->equation == PSK_EQ_ADVECTION) {
     for (int i = 0; i < nx; ++i) L[i] = ((-d->velocity[i]) * (F[i + 1] - F[i])) / d->dx;
   } else {
@@ -241,7 +243,7 @@ PSO_API int pso_apply_operator(const psk_desc *d, const double *u, double *L) {
   const int nx = nx_of(d);
 #pragma omp parallel
   {
-    double *w = (double *)malloc(sizeof(double) * (size_t)(2 * nx + 1));
+    double *w = (double *)malloc(sizeof(double) * (size_t)(4 * nx + 1));
     double *F = w + nx;
 #pragma omp for schedule(static)
     for (int r = 0; r < d->batch; ++r)
@@ -287,7 +289,7 @@ PSO_API int pso_ssprk33_step(const psk_desc *d, const double *u, const double *d
   const int64_t ghost_block = (d->ghost_ld ? (int64_t)d->batch * d->ghost_ld : 2 * d->g);
 #pragma omp parallel
   {
-    double *scratch = (double *)malloc(sizeof(double) * (size_t)(5 * nx + 1));
+    double *scratch = (double *)malloc(sizeof(double) * (size_t)(7 * nx + 1));
 #pragma omp for schedule(static)
     for (int r = 0; r < d->batch; ++r)
       step_row(d, r, ghost3, ghost_block, u + (size_t)r * d->ld, dt[(size_t)r * dt_stride],
@@ -303,8 +305,8 @@ PSO_API int pso_solve_fixed_dt(const psk_desc *d, double *u, double dt, int nste
   const int nx = nx_of(d);
 #pragma omp parallel
   {
-    double *scratch = (double *)malloc(sizeof(double) * (size_t)(6 * nx + 1));
-    double *tmp = scratch + 5 * nx + 1;
+    double *scratch = (double *)malloc(sizeof(double) * (size_t)(8 * nx + 1));
+    double *tmp = scratch + 7 * nx + 1;
 #pragma omp for schedule(static)
     for (int r = 0; r < d->batch; ++r) {
       double *row = u + (size_t)r * d->ld;
@@ -324,8 +326,8 @@ PSO_API int pso_solve_fixed_dt(const psk_desc *d, double *u, double dt, int nste
 PSO_API int pso_solve_adaptive(const psk_desc *d, double *u, double theta, double cfl_scale,
                                double tfinal, int max_steps, double *dt_hist) {
   const int nx = nx_of(d);
-  double *scratch = (double *)malloc(sizeof(double) * (size_t)(6 * nx + 1));
-  double *tmp = scratch + 5 * nx + 1;
+  double *scratch = (double *)malloc(sizeof(double) * (size_t)(8 * nx + 1));
+  double *tmp = scratch + 7 * nx + 1;
   double t = 0.0;
   int m = 0;
   while (!(t >= tfinal) && m < max_steps) {

@@ -8,6 +8,7 @@ import time, and every call raises :class:`PskError` on a non-zero status.
 from __future__ import annotations
 
 import ctypes as ct
+import os
 import pathlib
 
 import torch
@@ -74,6 +75,7 @@ def _load() -> ct.CDLL:
         "psk_version": ([], ct.c_int),
         "psk_status_string": ([ct.c_int], ct.c_char_p),
         "psk_last_cuda_error": ([], ct.c_int),
+        "psk_set_stage_variant": ([ct.c_int], ct.c_int),
         "psk_apply_boundary": ([D, vp, vp, vp], ct.c_int),
         "psk_reconstruct": ([D, vp, vp, vp, vp], ct.c_int),
         "psk_numerical_flux": ([D, vp, vp, i64, vp, vp], ct.c_int),
@@ -94,8 +96,10 @@ def _load() -> ct.CDLL:
 
 
 _lib = _load()
+if os.environ.get("PSK_STAGE_VARIANT"):  # A/B measurements only
+    _lib.psk_set_stage_variant(int(os.environ["PSK_STAGE_VARIANT"]))
 EXPORTS = (
-    "psk_version", "psk_status_string", "psk_last_cuda_error", "psk_apply_boundary",
+    "psk_version", "psk_status_string", "psk_last_cuda_error", "psk_set_stage_variant", "psk_apply_boundary",
     "psk_reconstruct", "psk_numerical_flux", "psk_apply_operator", "psk_max_abs",
     "psk_ssprk33_stage", "psk_step_control", "psk_apply_operator_vjp",
     "psk_ssprk33_stage_adjoint",

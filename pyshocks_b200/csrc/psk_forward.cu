@@ -221,6 +221,171 @@ stage_tile_kernel(const StageParams p) {
 }
 
 // ---------------------------------------------------------------------------
+// Warp kernel (stage_warp_kernel): the same stage without shared memory or block barriers.
+//   * one WARP owns 32 * R consecutive interior cells of one row; every lane loads its R
+//     cells with 128-bit loads straight into registers (one fully coalesced kilobyte per
+//     warp) and takes its 3-cell halo from the neighbouring lanes with shuffles;
+//   * only the first / last lane need cells outside the warp's chunk: six lanes issue one
+//     extra (boundary-condition aware) load and hand the values over by shuffle;
+//   * the left / right face values of the neighbouring cells also travel by shuffle;
+//   * no __syncthreads anywhere, so warps drift apart and hide each other's load latency.
+
+template <int EQ, int FLUX, int REC, bool STRICT, int R>
+__global__ void __launch_bounds__(256)
+stage_warp_kernel(const StageParams p, long long total_warps) {
+  static_assert(R == 4, "the shuffle pattern below is written for R = 4");
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (warp_id >= total_warps) return;
+  const int row = static_cast<int>(warp_id / p.tiles_per_row);
+  const int chunk = static_cast<int>(warp_id - static_cast<long long>(row) * p.tiles_per_row);
+  if (p.active != nullptr && p.active[row] == 0) return;
+
+  constexpr unsigned kFull = 0xffffffffu;
+  const int g = p.bc.g, n = p.bc.n;
+  const int s = chunk * (32 * R);
+  const int c0 = s + R * lane;
+  const double *__restrict__ urow = p.uin + static_cast<int64_t>(row) * p.ld;
+  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
+  const bool whole = (s + 32 * R <= n);
+  const bool vec = whole && p.vec_ok;
+
+  // ---- owned cells
+  double v[R + 2 * kHalo];
+  if (vec) {
+    const double2 q0 = *reinterpret_cast<const double2 *>(p.uin + off);
+    const double2 q1 = *reinterpret_cast<const double2 *>(p.uin + off + 2);
+    v[3] = q0.x; v[4] = q0.y; v[5] = q1.x; v[6] = q1.y;
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[kHalo + r] = load_w(p.bc, urow, row, g + c0 + r);
+  }
+  // ---- chunk halo: lanes 0..2 fetch cells s-3..s-1, lanes 29..31 fetch cells s+128..s+130
+  double h = 0.0;
+  if (lane < 3) h = load_w(p.bc, urow, row, g + s - 3 + lane);
+  if (lane >= 29) h = load_w(p.bc, urow, row, g + s + 32 * R + (lane - 29));
+  const double h1 = __shfl_sync(kFull, h, 1), h2 = __shfl_sync(kFull, h, 2);
+  const double h29 = __shfl_sync(kFull, h, 29), h30 = __shfl_sync(kFull, h, 30);
+  v[0] = __shfl_up_sync(kFull, v[4], 1);
+  v[1] = __shfl_up_sync(kFull, v[5], 1);
+  v[2] = __shfl_up_sync(kFull, v[6], 1);
+  v[7] = __shfl_down_sync(kFull, v[3], 1);
+  v[8] = __shfl_down_sync(kFull, v[4], 1);
+  v[9] = __shfl_down_sync(kFull, v[5], 1);
+  if (lane == 0) { v[0] = h; v[1] = h1; v[2] = h2; }
+  if (lane == 31) { v[7] = h29; v[8] = h30; v[9] = h; }
+
+  // ---- face values of the owned cells (+ the outer neighbour's for the edge lanes)
+  double ul[R], ur[R];
+  double ur_left, ul_right;
+  if (REC == PSK_REC_WENOJS53 && !STRICT) {
+    double hd[R + 5], pq[R + 4];
+#pragma unroll
+    for (int k = 0; k < R + 5; ++k) hd[k] = 0.5 * (v[k + 1] - v[k]);
+#pragma unroll
+    for (int k = 0; k < R + 4; ++k) {
+      const double tt = hd[k + 1] - hd[k];
+      pq[k] = (13.0 / 3.0) * tt * tt;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int m = r + kHalo;
+      const Weno5Pair o = weno53_pair_fast(v[m], hd[m - 2], hd[m - 1], hd[m], hd[m + 1], pq[m - 2],
+                                           pq[m - 1], pq[m], p.eps);
+      ul[r] = o.ul;
+      ur[r] = o.ur;
+    }
+    ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
+    ul_right = __shfl_down_sync(kFull, ul[0], 1);
+    if (lane == 0)
+      ur_left = weno53_pair_fast(v[2], hd[0], hd[1], hd[2], hd[3], pq[0], pq[1], pq[2], p.eps).ur;
+    if (lane == 31)
+      ul_right = weno53_pair_fast(v[7], hd[5], hd[6], hd[7], hd[8], pq[5], pq[6], pq[7], p.eps).ul;
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int m = r + kHalo;
+      const Weno5Pair o =
+          reconstruct_cell<REC, STRICT>(v[m - 2], v[m - 1], v[m], v[m + 1], v[m + 2], p.eps);
+      ul[r] = o.ul;
+      ur[r] = o.ur;
+    }
+    ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
+    ul_right = __shfl_down_sync(kFull, ul[0], 1);
+    if (lane == 0) ur_left = reconstruct_cell<REC, STRICT>(v[0], v[1], v[2], v[3], v[4], p.eps).ur;
+    if (lane == 31)
+      ul_right = reconstruct_cell<REC, STRICT>(v[5], v[6], v[7], v[8], v[9], p.eps).ul;
+  }
+
+  // ---- fluxes at the R + 1 faces; face f sits between cells c0 + f - 1 and c0 + f
+  const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
+  double F[R + 1];
+#pragma unroll
+  for (int f = 0; f <= R; ++f) {
+    const double urj = (f == 0) ? ur_left : ur[f - 1];
+    const double ulp = (f == R) ? ul_right : ul[f];
+    double nu = 1.0, arj = 0.0, alp = 0.0;
+    if ((FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) || EQ != PSK_EQ_BURGERS) {
+      const int j = g + c0 + f - 1;  // array index of the cell left of the face
+      const bool ok = (j >= 0 && j < p.bc.nx - 1);
+      if ((FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) && p.nu != nullptr)
+        nu = ok ? p.nu[j] : 1.0;
+      if (EQ != PSK_EQ_BURGERS) {
+        arj = ok ? p.vel_r[j] : 0.0;
+        alp = ok ? p.vel_l[j + 1] : 0.0;
+      }
+    }
+    F[f] = face_flux<EQ, FLUX, STRICT>(urj, ulp, v[f + kHalo - 1], v[f + kHalo], speed, nu, arj, alp);
+  }
+
+  // ---- RHS, stage combine, store
+  const double dt = (p.stage != 0) ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 0.0;
+  double u0v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) u0v[r] = 0.0;
+  if (p.stage >= 2) {
+    if (vec) {
+      const double2 q0 = *reinterpret_cast<const double2 *>(p.u0 + off);
+      const double2 q1 = *reinterpret_cast<const double2 *>(p.u0 + off + 2);
+      u0v[0] = q0.x; u0v[1] = q0.y; u0v[2] = q1.x; u0v[3] = q1.y;
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (c0 + r < n) u0v[r] = p.u0[off + r];
+    }
+  }
+  double out[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    double vel = 0.0;
+    if (EQ == PSK_EQ_ADVECTION) vel = (c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
+    const double L = rhs_from_faces<EQ, STRICT>(F[r], F[r + 1], vel, p.dx, p.invdx);
+    out[r] = stage_combine<STRICT>(p.stage, u0v[r], v[r + kHalo], dt, L);
+  }
+  if (vec) {
+    *reinterpret_cast<double2 *>(p.uout + off) = make_double2(out[0], out[1]);
+    *reinterpret_cast<double2 *>(p.uout + off + 2) = make_double2(out[2], out[3]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (c0 + r < n) p.uout[off + r] = out[r];
+  }
+
+  // ---- fused CFL reduction (only when asked for): max |uout| over the interior of the row
+  if (p.maxabs != nullptr) {
+    unsigned long long mx = 0ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (c0 + r < n) {
+        const unsigned long long b = abs_bits(out[r]);
+        mx = b > mx ? b : mx;
+      }
+    mx = warp_max_bits(mx);
+    if (lane == 0) atomicMax(p.maxabs + row, mx);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // generic cell evaluation straight from global memory (zero padded, BC mapped): used for the
 // ghost rows of a stage / RHS, and by the small parity kernels below.
 
@@ -277,8 +442,15 @@ __global__ void ghost_rows_kernel(const StageParams p, int batch) {
 // ---------------------------------------------------------------------------
 // dispatch
 
+// 0: warp kernel (default), 1: shared-memory tile kernel (kept for A/B measurements)
+static int g_stage_variant = 0;
+
+template <int EQ, int FLUX, int REC, bool STRICT>
+int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStream_t st);
+
 template <int EQ, int FLUX, int REC, bool STRICT>
 int launch_stage(const StageParams &p, int batch, int ghost_rows, cudaStream_t st) {
+  if (g_stage_variant == 0) return launch_stage_warp<EQ, FLUX, REC, STRICT>(p, batch, ghost_rows, st);
   constexpr int R = 4;
   const int n = p.bc.n;
   int threads = (n + R - 1) / R;
@@ -299,6 +471,33 @@ int launch_stage(const StageParams &p, int batch, int ghost_rows, cudaStream_t s
   if (blocks > 2147483647LL) return PSK_E_INVALID;
   stage_tile_kernel<EQ, FLUX, REC, STRICT, R>
       <<<static_cast<unsigned>(blocks), threads, smem, st>>>(q);
+  PSK_CUDA_OK(cudaGetLastError());
+  if (ghost_rows) {
+    const int total = batch * 2 * p.bc.g;
+    ghost_rows_kernel<EQ, FLUX, REC, STRICT><<<(total + 127) / 128, 128, 0, st>>>(q, batch);
+    PSK_CUDA_OK(cudaGetLastError());
+  }
+  return PSK_OK;
+}
+
+template <int EQ, int FLUX, int REC, bool STRICT>
+int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStream_t st) {
+  constexpr int R = 4;
+  StageParams q = p;
+  q.tiles_per_row = (p.bc.n + 32 * R - 1) / (32 * R);  // warp chunks per row
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.uin + p.bc.g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p.uout + p.bc.g) % 16 == 0) &&
+                       (p.u0 == nullptr || reinterpret_cast<uintptr_t>(p.u0 + p.bc.g) % 16 == 0) &&
+                       (p.ld % 2 == 0);
+  q.vec_ok = aligned ? 1 : 0;
+  const long long warps = static_cast<long long>(q.tiles_per_row) * batch;
+  // small problems: fewer warps per CTA so that the chunks spread over more SMs
+  int threads = 256;
+  while (threads > 32 && warps * 32 / threads < 2 * kSMs) threads >>= 1;
+  const long long blocks = (warps * 32 + threads - 1) / threads;
+  if (blocks > 2147483647LL) return PSK_E_INVALID;
+  stage_warp_kernel<EQ, FLUX, REC, STRICT, R>
+      <<<static_cast<unsigned>(blocks), threads, 0, st>>>(q, warps);
   PSK_CUDA_OK(cudaGetLastError());
   if (ghost_rows) {
     const int total = batch * 2 * p.bc.g;
@@ -527,6 +726,14 @@ using namespace psk;
 extern "C" {
 
 int psk_version(void) { return PSK_VERSION; }
+
+/* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
+ * kernel (default), 1 = shared-memory tile kernel */
+int psk_set_stage_variant(int variant) {
+  if (variant < 0 || variant > 1) return PSK_E_INVALID;
+  g_stage_variant = variant;
+  return PSK_OK;
+}
 
 const char *psk_status_string(int status) {
   switch (status) {

@@ -222,13 +222,48 @@ stage_tile_kernel(const StageParams p) {
 
 // ---------------------------------------------------------------------------
 // Warp kernel (stage_warp_kernel): the same stage without shared memory or block barriers.
-//   * one WARP owns 32 * R consecutive interior cells of one row; every lane loads its R
-//     cells with 128-bit loads straight into registers (one fully coalesced kilobyte per
-//     warp) and takes its 3-cell halo from the neighbouring lanes with shuffles;
-//   * only the first / last lane need cells outside the warp's chunk: six lanes issue one
-//     extra (boundary-condition aware) load and hand the values over by shuffle;
-//   * the left / right face values of the neighbouring cells also travel by shuffle;
-//   * no __syncthreads anywhere, so warps drift apart and hide each other's load latency.
+//   * one WARP covers 32 * R consecutive cells of one row; every lane loads its R cells
+//     with 128-bit loads straight into registers (one fully coalesced kilobyte per warp)
+//     and takes its 3-cell halo from the neighbouring lanes with shuffles;
+//   * lanes 0 and 31 are HALO lanes: they load and reconstruct like every other lane
+//     (uniform code, no divergent extra work) but store nothing, so a warp emits
+//     30 * R = 120 cells; the left / right face values of neighbouring cells also travel
+//     by shuffle;
+//   * no __syncthreads anywhere, so warps drift apart and hide each other's load latency;
+//   * FAST math works in sixths of the first differences and with fluxes scaled by a
+//     compile-time constant (folded into dt / dx), see psk_math.cuh.
+
+// FAST-path flux scaled by kFluxScale<EQ, FLUX> (4 F for Rusanov / Lax-Friedrichs, 2 F for
+// the other Burgers fluxes, F for advection / continuity): saves the halvings of u^2 / 2.
+template <int EQ, int FLUX>
+struct FluxScale {
+  static constexpr double value =
+      (EQ != PSK_EQ_BURGERS) ? 1.0
+                             : ((FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? 4.0 : 2.0);
+};
+
+template <int EQ, int FLUX>
+__device__ __forceinline__ double face_flux_scaled(double urj, double ulp, double wj, double wp,
+                                                   double speed, double nu, bool has_nu, double arj,
+                                                   double alp) {
+  if (EQ == PSK_EQ_BURGERS) {
+    if (FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) {
+      // 4 F = ul^2 + ur^2 - 2 a nu (ul - ur)      (scalar.py:231-249)
+      double a = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? speed : fmax(fabs(wp), fabs(wj));
+      if (has_nu) a *= nu;
+      return fma(-2.0 * a, ulp - urj, fma(urj, urj, ulp * ulp));
+    }
+    if (FLUX == PSK_FLUX_UPWIND) {
+      const double v = (urj + ulp) > 0.0 ? urj : ulp;  // scalar.py:129-130
+      return v * v;
+    }
+    const double vp = fmax(urj, 0.0), vm = fmin(ulp, 0.0);  // scalar.py:312-321, omega = 0
+    return fma(vp, vp, vm * vm);
+  }
+  const bool pos = (arj + alp) > 0.0;
+  if (EQ == PSK_EQ_ADVECTION) return pos ? urj : ulp;
+  return pos ? arj * urj : alp * ulp;
+}
 
 template <int EQ, int FLUX, int REC, bool STRICT, int R>
 __global__ void __launch_bounds__(256)
@@ -242,15 +277,16 @@ stage_warp_kernel(const StageParams p, long long total_warps) {
   if (p.active != nullptr && p.active[row] == 0) return;
 
   constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kOut = 30 * R;  // cells emitted per warp
   const int g = p.bc.g, n = p.bc.n;
-  const int s = chunk * (32 * R);
-  const int c0 = s + R * lane;
+  const int c0 = chunk * kOut - R + R * lane;  // first owned cell (interior coordinates)
   const double *__restrict__ urow = p.uin + static_cast<int64_t>(row) * p.ld;
   const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
-  const bool whole = (s + 32 * R <= n);
-  const bool vec = whole && p.vec_ok;
+  const bool inside = (c0 >= 0) && (c0 + R <= n);
+  const bool vec = inside && p.vec_ok;
+  const bool emit = (lane >= 1) && (lane <= 30);
 
-  // ---- owned cells
+  // ---- owned cells, then the 3-cell halos from the neighbouring lanes
   double v[R + 2 * kHalo];
   if (vec) {
     const double2 q0 = *reinterpret_cast<const double2 *>(p.uin + off);
@@ -260,47 +296,52 @@ stage_warp_kernel(const StageParams p, long long total_warps) {
 #pragma unroll
     for (int r = 0; r < R; ++r) v[kHalo + r] = load_w(p.bc, urow, row, g + c0 + r);
   }
-  // ---- chunk halo: lanes 0..2 fetch cells s-3..s-1, lanes 29..31 fetch cells s+128..s+130
-  double h = 0.0;
-  if (lane < 3) h = load_w(p.bc, urow, row, g + s - 3 + lane);
-  if (lane >= 29) h = load_w(p.bc, urow, row, g + s + 32 * R + (lane - 29));
-  const double h1 = __shfl_sync(kFull, h, 1), h2 = __shfl_sync(kFull, h, 2);
-  const double h29 = __shfl_sync(kFull, h, 29), h30 = __shfl_sync(kFull, h, 30);
+  double u0v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) u0v[r] = 0.0;
+  if (p.stage >= 2 && emit) {  // issued early: independent of everything below
+    if (vec) {
+      const double2 q0 = *reinterpret_cast<const double2 *>(p.u0 + off);
+      const double2 q1 = *reinterpret_cast<const double2 *>(p.u0 + off + 2);
+      u0v[0] = q0.x; u0v[1] = q0.y; u0v[2] = q1.x; u0v[3] = q1.y;
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (c0 + r >= 0 && c0 + r < n) u0v[r] = p.u0[off + r];
+    }
+  }
   v[0] = __shfl_up_sync(kFull, v[4], 1);
   v[1] = __shfl_up_sync(kFull, v[5], 1);
   v[2] = __shfl_up_sync(kFull, v[6], 1);
   v[7] = __shfl_down_sync(kFull, v[3], 1);
   v[8] = __shfl_down_sync(kFull, v[4], 1);
   v[9] = __shfl_down_sync(kFull, v[5], 1);
-  if (lane == 0) { v[0] = h; v[1] = h1; v[2] = h2; }
-  if (lane == 31) { v[7] = h29; v[8] = h30; v[9] = h; }
+  // (lane 0 keeps its own values in v[0..2], lane 31 in v[7..9]: finite, and never used
+  //  for anything that is stored)
 
-  // ---- face values of the owned cells (+ the outer neighbour's for the edge lanes)
+  // ---- face values of the owned cells
   double ul[R], ur[R];
-  double ur_left, ul_right;
   if (REC == PSK_REC_WENOJS53 && !STRICT) {
-    double hd[R + 5], pq[R + 4];
+    double t[R + 5], tw[R + 5], pq[R + 4];
+    const double eps9 = p.eps * (1.0 / 9.0);
 #pragma unroll
-    for (int k = 0; k < R + 5; ++k) hd[k] = 0.5 * (v[k + 1] - v[k]);
+    for (int k = 0; k < R + 5; ++k) {
+      t[k] = (1.0 / 6.0) * (v[k + 1] - v[k]);
+      tw[k] = t[k] + t[k];
+    }
 #pragma unroll
     for (int k = 0; k < R + 4; ++k) {
-      const double tt = hd[k + 1] - hd[k];
-      pq[k] = (13.0 / 3.0) * tt * tt;
+      const double dd = t[k + 1] - t[k];  // centred at v[k + 1]
+      pq[k] = fma((13.0 / 3.0) * dd, dd, eps9);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int m = r + kHalo;
-      const Weno5Pair o = weno53_pair_fast(v[m], hd[m - 2], hd[m - 1], hd[m], hd[m + 1], pq[m - 2],
-                                           pq[m - 1], pq[m], p.eps);
+      const Weno5Pair o = weno53_pair_sixths(v[m], t[m - 2], t[m - 1], t[m], t[m + 1], tw[m - 2],
+                                             tw[m - 1], tw[m], tw[m + 1], pq[m - 2], pq[m - 1], pq[m]);
       ul[r] = o.ul;
       ur[r] = o.ur;
     }
-    ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
-    ul_right = __shfl_down_sync(kFull, ul[0], 1);
-    if (lane == 0)
-      ur_left = weno53_pair_fast(v[2], hd[0], hd[1], hd[2], hd[3], pq[0], pq[1], pq[2], p.eps).ur;
-    if (lane == 31)
-      ul_right = weno53_pair_fast(v[7], hd[5], hd[6], hd[7], hd[8], pq[5], pq[6], pq[7], p.eps).ul;
   } else {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -310,76 +351,85 @@ stage_warp_kernel(const StageParams p, long long total_warps) {
       ul[r] = o.ul;
       ur[r] = o.ur;
     }
-    ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
-    ul_right = __shfl_down_sync(kFull, ul[0], 1);
-    if (lane == 0) ur_left = reconstruct_cell<REC, STRICT>(v[0], v[1], v[2], v[3], v[4], p.eps).ur;
-    if (lane == 31)
-      ul_right = reconstruct_cell<REC, STRICT>(v[5], v[6], v[7], v[8], v[9], p.eps).ul;
   }
+  const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
+  const double ul_right = __shfl_down_sync(kFull, ul[0], 1);
 
   // ---- fluxes at the R + 1 faces; face f sits between cells c0 + f - 1 and c0 + f
   const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
+  const bool has_nu = (FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) && (p.nu != nullptr);
   double F[R + 1];
 #pragma unroll
   for (int f = 0; f <= R; ++f) {
     const double urj = (f == 0) ? ur_left : ur[f - 1];
     const double ulp = (f == R) ? ul_right : ul[f];
     double nu = 1.0, arj = 0.0, alp = 0.0;
-    if ((FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) || EQ != PSK_EQ_BURGERS) {
+    if (has_nu || EQ != PSK_EQ_BURGERS) {
       const int j = g + c0 + f - 1;  // array index of the cell left of the face
       const bool ok = (j >= 0 && j < p.bc.nx - 1);
-      if ((FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) && p.nu != nullptr)
-        nu = ok ? p.nu[j] : 1.0;
+      if (has_nu) nu = ok ? p.nu[j] : 1.0;
       if (EQ != PSK_EQ_BURGERS) {
         arj = ok ? p.vel_r[j] : 0.0;
         alp = ok ? p.vel_l[j + 1] : 0.0;
       }
     }
-    F[f] = face_flux<EQ, FLUX, STRICT>(urj, ulp, v[f + kHalo - 1], v[f + kHalo], speed, nu, arj, alp);
+    if (STRICT)
+      F[f] = face_flux<EQ, FLUX, true>(urj, ulp, v[f + kHalo - 1], v[f + kHalo], speed, nu, arj, alp);
+    else
+      F[f] = face_flux_scaled<EQ, FLUX>(urj, ulp, v[f + kHalo - 1], v[f + kHalo], speed, nu, has_nu,
+                                        arj, alp);
   }
 
   // ---- RHS, stage combine, store
   const double dt = (p.stage != 0) ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 0.0;
-  double u0v[R];
+  double out[R];
+  if (STRICT) {
 #pragma unroll
-  for (int r = 0; r < R; ++r) u0v[r] = 0.0;
-  if (p.stage >= 2) {
+    for (int r = 0; r < R; ++r) {
+      double vel = 0.0;
+      if (EQ == PSK_EQ_ADVECTION) vel = (c0 + r >= 0 && c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
+      const double L = rhs_from_faces<EQ, true>(F[r], F[r + 1], vel, p.dx, p.invdx);
+      out[r] = stage_combine<true>(p.stage, u0v[r], v[r + kHalo], dt, L);
+    }
+  } else {
+    const double cL = p.invdx * (1.0 / FluxScale<EQ, FLUX>::value);
+    const double coef = (p.stage == 0) ? cL : dt * cL;  // dt / (scale dx)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double dF = F[r] - F[r + 1];
+      if (EQ == PSK_EQ_ADVECTION) dF *= (c0 + r >= 0 && c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
+      if (p.stage == 0) {
+        out[r] = coef * dF;
+      } else {
+        const double k = fma(coef, dF, v[r + kHalo]);
+        out[r] = (p.stage == 1) ? k
+                                : ((p.stage == 2) ? fma(0.25, k, 0.75 * u0v[r])
+                                                  : fma(2.0 / 3.0, k, (1.0 / 3.0) * u0v[r]));
+      }
+    }
+  }
+  if (emit) {
     if (vec) {
-      const double2 q0 = *reinterpret_cast<const double2 *>(p.u0 + off);
-      const double2 q1 = *reinterpret_cast<const double2 *>(p.u0 + off + 2);
-      u0v[0] = q0.x; u0v[1] = q0.y; u0v[2] = q1.x; u0v[3] = q1.y;
+      *reinterpret_cast<double2 *>(p.uout + off) = make_double2(out[0], out[1]);
+      *reinterpret_cast<double2 *>(p.uout + off + 2) = make_double2(out[2], out[3]);
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (c0 + r < n) u0v[r] = p.u0[off + r];
+        if (c0 + r >= 0 && c0 + r < n) p.uout[off + r] = out[r];
     }
-  }
-  double out[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    double vel = 0.0;
-    if (EQ == PSK_EQ_ADVECTION) vel = (c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
-    const double L = rhs_from_faces<EQ, STRICT>(F[r], F[r + 1], vel, p.dx, p.invdx);
-    out[r] = stage_combine<STRICT>(p.stage, u0v[r], v[r + kHalo], dt, L);
-  }
-  if (vec) {
-    *reinterpret_cast<double2 *>(p.uout + off) = make_double2(out[0], out[1]);
-    *reinterpret_cast<double2 *>(p.uout + off + 2) = make_double2(out[2], out[3]);
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (c0 + r < n) p.uout[off + r] = out[r];
   }
 
   // ---- fused CFL reduction (only when asked for): max |uout| over the interior of the row
   if (p.maxabs != nullptr) {
     unsigned long long mx = 0ull;
+    if (emit) {
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (c0 + r < n) {
-        const unsigned long long b = abs_bits(out[r]);
-        mx = b > mx ? b : mx;
-      }
+      for (int r = 0; r < R; ++r)
+        if (c0 + r >= 0 && c0 + r < n) {
+          const unsigned long long b = abs_bits(out[r]);
+          mx = b > mx ? b : mx;
+        }
+    }
     mx = warp_max_bits(mx);
     if (lane == 0) atomicMax(p.maxabs + row, mx);
   }
@@ -484,7 +534,7 @@ template <int EQ, int FLUX, int REC, bool STRICT>
 int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStream_t st) {
   constexpr int R = 4;
   StageParams q = p;
-  q.tiles_per_row = (p.bc.n + 32 * R - 1) / (32 * R);  // warp chunks per row
+  q.tiles_per_row = (p.bc.n + 30 * R - 1) / (30 * R);  // warp chunks per row (2 halo lanes)
   const bool aligned = (reinterpret_cast<uintptr_t>(p.uin + p.bc.g) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(p.uout + p.bc.g) % 16 == 0) &&
                        (p.u0 == nullptr || reinterpret_cast<uintptr_t>(p.u0 + p.bc.g) % 16 == 0) &&

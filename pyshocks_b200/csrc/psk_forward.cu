@@ -265,51 +265,72 @@ __device__ __forceinline__ double face_flux_scaled(double urj, double ulp, doubl
   return pos ? arj * urj : alp * ulp;
 }
 
-template <int EQ, int FLUX, int REC, bool STRICT, int R>
-__global__ void __launch_bounds__(256)
-stage_warp_kernel(const StageParams p, long long total_warps) {
-  static_assert(R == 4, "the shuffle pattern below is written for R = 4");
-  const int lane = threadIdx.x & 31;
-  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (warp_id >= total_warps) return;
-  const int row = static_cast<int>(warp_id / p.tiles_per_row);
-  const int chunk = static_cast<int>(warp_id - static_cast<long long>(row) * p.tiles_per_row);
-  if (p.active != nullptr && p.active[row] == 0) return;
+// where a lane's R cells live and how they may be accessed
+struct ChunkRef {
+  int row, c0;
+  int64_t off;
+  bool vec, emit, live;
+};
 
-  constexpr unsigned kFull = 0xffffffffu;
-  constexpr int kOut = 30 * R;  // cells emitted per warp
-  const int g = p.bc.g, n = p.bc.n;
-  const int c0 = chunk * kOut - R + R * lane;  // first owned cell (interior coordinates)
-  const double *__restrict__ urow = p.uin + static_cast<int64_t>(row) * p.ld;
-  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
-  const bool inside = (c0 >= 0) && (c0 + R <= n);
-  const bool vec = inside && p.vec_ok;
-  const bool emit = (lane >= 1) && (lane <= 30);
+template <int R>
+__device__ __forceinline__ ChunkRef chunk_ref(const StageParams &p, long long warp_id, int lane) {
+  ChunkRef c;
+  c.row = static_cast<int>(warp_id / p.tiles_per_row);
+  const int chunk = static_cast<int>(warp_id - static_cast<long long>(c.row) * p.tiles_per_row);
+  c.c0 = chunk * (30 * R) - R + R * lane;  // first owned cell (interior coordinates)
+  c.off = static_cast<int64_t>(c.row) * p.ld + p.bc.g + c.c0;
+  c.vec = (c.c0 >= 0) && (c.c0 + R <= p.bc.n) && p.vec_ok;
+  c.emit = (lane >= 1) && (lane <= 30);
+  c.live = (p.active == nullptr) || (p.active[c.row] != 0);
+  return c;
+}
 
-  // ---- owned cells, then the 3-cell halos from the neighbouring lanes
-  double v[R + 2 * kHalo];
-  if (vec) {
-    const double2 q0 = *reinterpret_cast<const double2 *>(p.uin + off);
-    const double2 q1 = *reinterpret_cast<const double2 *>(p.uin + off + 2);
-    v[3] = q0.x; v[4] = q0.y; v[5] = q1.x; v[6] = q1.y;
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r) v[kHalo + r] = load_w(p.bc, urow, row, g + c0 + r);
-  }
-  double u0v[R];
+// issue the global loads of one chunk: the lane's R cells of uin (boundary condition applied
+// where the lane touches ghost cells) and, for stages 2 and 3, of u0
+template <int R>
+__device__ __forceinline__ void chunk_load(const StageParams &p, const ChunkRef &c, double (&own)[R],
+                                           double (&u0v)[R]) {
 #pragma unroll
   for (int r = 0; r < R; ++r) u0v[r] = 0.0;
-  if (p.stage >= 2 && emit) {  // issued early: independent of everything below
-    if (vec) {
-      const double2 q0 = *reinterpret_cast<const double2 *>(p.u0 + off);
-      const double2 q1 = *reinterpret_cast<const double2 *>(p.u0 + off + 2);
+  if (!c.live) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) own[r] = 0.0;
+    return;
+  }
+  if (c.vec) {
+    const double2 q0 = *reinterpret_cast<const double2 *>(p.uin + c.off);
+    const double2 q1 = *reinterpret_cast<const double2 *>(p.uin + c.off + 2);
+    own[0] = q0.x; own[1] = q0.y; own[2] = q1.x; own[3] = q1.y;
+  } else {
+    const double *__restrict__ urow = p.uin + static_cast<int64_t>(c.row) * p.ld;
+#pragma unroll
+    for (int r = 0; r < R; ++r) own[r] = load_w(p.bc, urow, c.row, p.bc.g + c.c0 + r);
+  }
+  if (p.stage >= 2 && c.emit) {
+    if (c.vec) {
+      const double2 q0 = *reinterpret_cast<const double2 *>(p.u0 + c.off);
+      const double2 q1 = *reinterpret_cast<const double2 *>(p.u0 + c.off + 2);
       u0v[0] = q0.x; u0v[1] = q0.y; u0v[2] = q1.x; u0v[3] = q1.y;
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (c0 + r >= 0 && c0 + r < n) u0v[r] = p.u0[off + r];
+        if (c.c0 + r >= 0 && c.c0 + r < p.bc.n) u0v[r] = p.u0[c.off + r];
     }
   }
+}
+
+template <int EQ, int FLUX, int REC, bool STRICT, int R>
+__device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkRef &c, int lane,
+                                              const double (&own)[R], const double (&u0v)[R]) {
+  static_assert(R == 4, "the shuffle pattern below is written for R = 4");
+  constexpr unsigned kFull = 0xffffffffu;
+  const int g = p.bc.g, n = p.bc.n;
+  const int row = c.row, c0 = c.c0;
+  const int64_t off = c.off;
+  const bool vec = c.vec, emit = c.emit;
+  double v[R + 2 * kHalo];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[kHalo + r] = own[r];
   v[0] = __shfl_up_sync(kFull, v[4], 1);
   v[1] = __shfl_up_sync(kFull, v[5], 1);
   v[2] = __shfl_up_sync(kFull, v[6], 1);
@@ -435,6 +456,46 @@ stage_warp_kernel(const StageParams p, long long total_warps) {
   }
 }
 
+// one chunk per warp
+template <int EQ, int FLUX, int REC, bool STRICT, int R>
+__global__ void __launch_bounds__(256)
+stage_warp_kernel(const StageParams p, long long total_warps) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (warp_id >= total_warps) return;
+  const ChunkRef c = chunk_ref<R>(p, warp_id, lane);
+  if (!c.live) return;
+  double own[R], u0v[R];
+  chunk_load<R>(p, c, own, u0v);
+  chunk_compute<EQ, FLUX, REC, STRICT, R>(p, c, lane, own, u0v);
+}
+
+// persistent warps: each warp walks over chunks warp_id, warp_id + stride, ... and issues the
+// loads of its NEXT chunk before it computes the current one (register double buffering),
+// so the DRAM latency is covered by a full chunk of arithmetic instead of by occupancy
+template <int EQ, int FLUX, int REC, bool STRICT, int R>
+__global__ void __launch_bounds__(256, 3)
+stage_warp_persistent_kernel(const StageParams p, int total_warps) {
+  const int lane = threadIdx.x & 31;
+  const int stride = static_cast<int>((gridDim.x * blockDim.x) >> 5);
+  int w = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (w >= total_warps) return;
+  double own[R], u0v[R];
+  chunk_load<R>(p, chunk_ref<R>(p, w, lane), own, u0v);
+  for (; w < total_warps; w += stride) {
+    double nown[R], nu0v[R];
+    const int wn = w + stride;
+    if (wn < total_warps) chunk_load<R>(p, chunk_ref<R>(p, wn, lane), nown, nu0v);
+    const ChunkRef cur = chunk_ref<R>(p, w, lane);
+    if (cur.live) chunk_compute<EQ, FLUX, REC, STRICT, R>(p, cur, lane, own, u0v);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      own[r] = nown[r];
+      u0v[r] = nu0v[r];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // generic cell evaluation straight from global memory (zero padded, BC mapped): used for the
 // ghost rows of a stage / RHS, and by the small parity kernels below.
@@ -494,6 +555,8 @@ __global__ void ghost_rows_kernel(const StageParams p, int batch) {
 
 // 0: warp kernel (default), 1: shared-memory tile kernel (kept for A/B measurements)
 static int g_stage_variant = 0;
+static int g_warp_block = 256;  // threads per CTA of the warp kernel (tuning)
+static int g_persistent_ctas_per_sm = 0;  // 0: one chunk per warp (default, faster as measured); >0: persistent warps with register prefetch
 
 template <int EQ, int FLUX, int REC, bool STRICT>
 int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStream_t st);
@@ -542,12 +605,18 @@ int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStrea
   q.vec_ok = aligned ? 1 : 0;
   const long long warps = static_cast<long long>(q.tiles_per_row) * batch;
   // small problems: fewer warps per CTA so that the chunks spread over more SMs
-  int threads = 256;
+  int threads = g_warp_block;
   while (threads > 32 && warps * 32 / threads < 2 * kSMs) threads >>= 1;
   const long long blocks = (warps * 32 + threads - 1) / threads;
   if (blocks > 2147483647LL) return PSK_E_INVALID;
-  stage_warp_kernel<EQ, FLUX, REC, STRICT, R>
-      <<<static_cast<unsigned>(blocks), threads, 0, st>>>(q, warps);
+  const long long resident = static_cast<long long>(g_persistent_ctas_per_sm) * kSMs;
+  if (g_persistent_ctas_per_sm > 0 && blocks > 2 * resident && warps < 2147483647LL) {
+    stage_warp_persistent_kernel<EQ, FLUX, REC, STRICT, R>
+        <<<static_cast<unsigned>(resident), threads, 0, st>>>(q, static_cast<int>(warps));
+  } else {
+    stage_warp_kernel<EQ, FLUX, REC, STRICT, R>
+        <<<static_cast<unsigned>(blocks), threads, 0, st>>>(q, warps);
+  }
   PSK_CUDA_OK(cudaGetLastError());
   if (ghost_rows) {
     const int total = batch * 2 * p.bc.g;
@@ -780,6 +849,16 @@ int psk_version(void) { return PSK_VERSION; }
 /* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
  * kernel (default), 1 = shared-memory tile kernel */
 int psk_set_stage_variant(int variant) {
+  if (variant >= 1000) {  // 1000 + persistent CTAs per SM (0 = one chunk per warp)
+    g_persistent_ctas_per_sm = variant - 1000;
+    return PSK_OK;
+  }
+  if (variant >= 100) {  // 100 + threads per CTA of the warp kernel (32..256)
+    const int t = variant - 100;
+    if (t < 32 || t > 256 || (t % 32) != 0) return PSK_E_INVALID;
+    g_warp_block = t;
+    return PSK_OK;
+  }
   if (variant < 0 || variant > 1) return PSK_E_INVALID;
   g_stage_variant = variant;
   return PSK_OK;

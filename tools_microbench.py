@@ -20,9 +20,8 @@ def run(batch, n, steps, math="fast"):
     print(json.dumps({"batch": batch, "n": n, "steps": steps, "math": math, "ms_per_step": ms / steps, "cell_updates_per_s": cu, "hbm_frac_64B": cu * 64 / 6547.2e9}))
 
 from pyshocks_b200 import _lib
-for variant in (0, 1):
-    _lib.lib().psk_set_stage_variant(variant)
-    print("variant", variant)
-    for b, n in ((65536, 4096), (1024, 4096), (1, 1 << 26), (64, 256)):
-        run(b, n, 20)
-    run(65536, 4096, 5, "strict")
+for pers in (0, 3):
+    _lib.lib().psk_set_stage_variant(1000 + pers)
+    print("persistent CTAs/SM", pers)
+    run(65536, 4096, 20)
+    run(1, 1 << 26, 20)

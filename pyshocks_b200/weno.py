@@ -1,0 +1,54 @@
+"""WENO-JS stencil tables (``pyshocks/weno.py:54-98, :166-244``).
+
+In the reference these tables drive 18 small convolutions per right-hand side; here they are
+compiled into the kernels (``csrc/psk_math.cuh``).  The tables are kept for API parity and for
+the tests that pin the kernels' coefficients against them.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class Stencil:
+    a: np.ndarray | None
+    """Weights of the squared terms of the smoothness indicators."""
+    b: np.ndarray | None
+    """Stencils of the smoothness indicators."""
+    c: np.ndarray
+    """Interpolation stencils."""
+    d: np.ndarray
+    """Ideal weights."""
+
+
+def weno_js_32_coefficients() -> Stencil:
+    # weno.py:166-203 (taps listed i+1, i, i-1)
+    a = np.array([1.0])
+    b = np.array([[[0.0, 1.0, -1.0]], [[1.0, -1.0, 0.0]]])
+    c = np.array([[0.0, 3.0 / 2.0, -1.0 / 2.0], [1.0 / 2.0, 1.0 / 2.0, 0.0]])
+    d = np.array([[1.0 / 3.0, 2.0 / 3.0]]).T
+    return Stencil(a=a, b=b, c=c, d=d)
+
+
+def weno_js_53_coefficients() -> Stencil:
+    # weno.py:206-244 (taps listed i+2, i+1, i, i-1, i-2)
+    a = np.array([13.0 / 12.0, 1.0 / 4.0])
+    b = np.array(
+        [
+            [[0.0, 0.0, 1.0, -2.0, 1.0], [0.0, 0.0, 3.0, -4.0, 1.0]],
+            [[0.0, 1.0, -2.0, 1.0, 0.0], [0.0, 1.0, 0.0, -1.0, 0.0]],
+            [[1.0, -2.0, 1.0, 0.0, 0.0], [1.0, -4.0, 3.0, 0.0, 0.0]],
+        ]
+    )
+    c = np.array(
+        [
+            [0.0, 0.0, 11.0 / 6.0, -7.0 / 6.0, 2.0 / 6.0],
+            [0.0, 2.0 / 6.0, 5.0 / 6.0, -1.0 / 6.0, 0.0],
+            [-1.0 / 6.0, 5.0 / 6.0, 2.0 / 6.0, 0.0, 0.0],
+        ]
+    )
+    d = np.array([[1.0 / 10.0, 6.0 / 10.0, 3.0 / 10.0]]).T
+    return Stencil(a=a, b=b, c=c, d=d)

@@ -1,0 +1,393 @@
+"""The pyshocks-shaped API on the GPU: the reference's scripts and tests, re-run through
+``pyshocks_b200`` (same names, same call sequences), checked against golden vectors recorded
+from the reference and against the reference tests' own acceptance criteria."""
+
+from __future__ import annotations
+
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+from common import load_golden, max_rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _fast_math():
+    from pyshocks_b200 import config
+
+    config.set_math("fast")
+    yield
+    config.set_math("fast")
+
+
+def host(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy()
+
+
+# {{{ examples/burgers.py (BASELINE config 1)
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("sname", ["rusanov", "lf"])
+def test_examples_burgers_config1(sname: str, math: str) -> None:
+    """examples/burgers.py:42-60,120-193 with -s rusanov|lf -r wenojs53 -n 256, tfinal=1."""
+    import pyshocks_b200 as ps
+    from pyshocks_b200 import burgers, config, funcs, timestepping
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import PeriodicBoundary
+
+    config.set_math(math)
+    S = load_golden("solve_c1")
+    rec = make_reconstruction_from_name("wenojs53")
+    scheme = burgers.make_scheme_from_name(sname, rec=rec, alpha=1.0)
+    order = int(max(scheme.order, 1.0)) + 1
+    grid = ps.make_uniform_cell_grid(a=-1.5, b=1.5, n=256, nghosts=scheme.stencil_width)
+    quad = ps.make_leggauss_quadrature(grid, order=order)
+    u0 = ps.cell_average(quad, lambda x: funcs.burgers_tophat(grid, 0.0, x))
+    assert np.array_equal(host(u0), S[f"{sname}_u0"])
+    boundary = PeriodicBoundary()
+    scheme = ps.bind(scheme, grid, boundary)
+    theta = 1.0
+
+    def _predict_timestep(t_, u_):
+        return theta * ps.predict_timestep(scheme, grid, boundary, t_, u_)
+
+    def _apply_operator(t_, u_):
+        return ps.apply_operator(scheme, grid, boundary, t_, u_)
+
+    method = timestepping.SSPRK33(
+        predict_timestep=ps.jit(_predict_timestep), source=ps.jit(_apply_operator), checkpoint=None
+    )
+    dts = []
+    for event in timestepping.step(method, u0, tfinal=1.0):
+        dts.append(float(event.dt))
+        energy = ps.norm(grid, event.u, p=2, weighted=True)
+        tv = ps.norm(grid, event.u, p="tvd")
+    assert event.iteration == 171
+    assert method.source.bound is not None  # the jit() wrapper recognised apply_operator -> fused stages
+    uf = host(event.u)
+    i = grid.i_
+    if math == "strict":
+        assert np.array_equal(np.array(dts), S[f"{sname}_dt"])
+        assert np.array_equal(uf[i], S[f"{sname}_uf"][i])
+        assert max_rel(uf, S[f"{sname}_uf"]) < 1e-13  # ghost rows included
+    else:
+        assert max_rel(np.array(dts), S[f"{sname}_dt"]) < 1e-12
+        assert max_rel(uf[i], S[f"{sname}_uf"][i]) < 1e-12
+    assert float(energy) > 0 and float(tv) > 0
+
+
+def test_fused_advance_equals_generic_advance() -> None:
+    """advance() through an opaque callable (3 RHS launches + torch axpys, the reference's own
+    structure) and through the fused stage kernels agree bit for bit in STRICT mode."""
+    import pyshocks_b200 as ps
+    from pyshocks_b200 import burgers, config, funcs, timestepping
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import make_dirichlet_boundary
+
+    config.set_math("strict")
+    rec = make_reconstruction_from_name("wenojs53")
+    scheme = burgers.make_scheme_from_name("rusanov", rec=rec)
+    grid = ps.make_uniform_cell_grid(a=-1.5, b=1.5, n=200, nghosts=3)
+    bc = make_dirichlet_boundary(ga=lambda t, x: funcs.burgers_tophat(grid, t, x))
+    quad = ps.make_leggauss_quadrature(grid, order=4)
+    u0 = ps.cell_average(quad, lambda x: funcs.burgers_tophat(grid, 0.0, x))
+    opaque = timestepping.SSPRK33(
+        predict_timestep=lambda t, u: 1e-3,
+        source=lambda t, u: ps.apply_operator(scheme, grid, bc, t, u) + 0.0,  # "+ 0.0": not recognisable
+        checkpoint=None,
+    )
+    fused = timestepping.SSPRK33(
+        predict_timestep=lambda t, u: 1e-3, source=ps.bind_operator(scheme, grid, bc), checkpoint=None
+    )
+    dt = 2.0e-3
+    a = timestepping.advance(opaque, dt, 0.1, u0)
+    b = timestepping.advance(fused, dt, 0.1, u0)
+    assert torch.equal(a, b)
+
+
+# }}}
+
+# {{{ drivers/*-adjoint.py
+
+
+@pytest.mark.parametrize("which", ["burgers", "advection"])
+def test_adjoint_drivers_vs_reference(which: str) -> None:
+    """drivers/burgers-adjoint.py:68-97,205-212,269-315 and drivers/advection-adjoint.py:219-328 at
+    N=48: forward with an InMemoryCheckpoint, then adjoint_step with the drivers' BC on p."""
+    import pyshocks_b200 as ps
+    from pyshocks_b200 import advection, burgers, funcs, timestepping
+    from pyshocks_b200.checkpointing import InMemoryCheckpoint
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import make_dirichlet_boundary, make_neumann_boundary
+
+    A = load_golden("adjoint")
+    rec = make_reconstruction_from_name("wenojs53")
+    if which == "burgers":
+        key, tfinal, theta, tol = "burgers_rusanov_wenojs53", 0.4, 1.0, 1e-9
+        scheme = burgers.make_scheme_from_name("rusanov", rec=rec, alpha=1.0)
+        grid = ps.make_uniform_cell_grid(a=-1.5, b=1.5, n=48, nghosts=scheme.stencil_width)
+        quad = ps.make_leggauss_quadrature(grid, order=int(max(scheme.order, 1)) + 1)
+        u0 = ps.cell_average(quad, lambda x: funcs.burgers_tophat(grid, 0.0, x))
+        bc = make_dirichlet_boundary(ga=lambda t, x: funcs.burgers_tophat(grid, t, x))
+        pbc = make_neumann_boundary(lambda t: 0.0)
+    else:
+        key, tfinal, theta, tol = "advection_godunov_wenojs53_dirichlet", 0.5, 0.75, 1e-12
+        scheme = advection.make_scheme_from_name("godunov", rec=rec, velocity=None)
+        grid = ps.make_uniform_cell_grid(a=-1.0, b=1.0, n=48, nghosts=scheme.stencil_width)
+        quad = ps.make_leggauss_quadrature(grid, order=int(max(scheme.order, 1.0)) + 1)
+        from dataclasses import replace
+
+        velocity = ps.cell_average(quad, partial(funcs.ic_constant, grid, c=1.0))
+        scheme = replace(scheme, velocity=velocity)
+        func_ic = partial(funcs.ic_sine, grid, k=1)
+        u0 = ps.cell_average(quad, func_ic)
+        bc = make_dirichlet_boundary(lambda t, x: func_ic(x - 1.0 * t))
+        pbc = make_dirichlet_boundary(lambda t, x: torch.zeros_like(x))
+    # initial data are not on the hot path: torch's device sin() may differ from libm in the
+    # last bit, so start from the reference's own u0 (the Dirichlet data keep the device sin)
+    assert max_rel(host(u0), A[f"{key}_u0"]) < 1e-15
+    u0 = torch.from_numpy(A[f"{key}_u0"]).cuda()
+
+    stepper = timestepping.SSPRK33(
+        predict_timestep=ps.jit(lambda t_, u_: theta * ps.predict_timestep(scheme, grid, bc, t_, u_)),
+        source=ps.jit(lambda t_, u_: ps.apply_operator(scheme, grid, bc, t_, u_)),
+        checkpoint=InMemoryCheckpoint(basename="Iteration"),
+    )
+    for event in timestepping.step(stepper, u0, tfinal=tfinal):
+        pass
+    uf, maxit = event.u, event.iteration
+    assert maxit == int(A[f"{key}_maxit"])
+    assert max_rel(host(uf), A[f"{key}_chk_u"][maxit]) < 1e-12
+    ps_ = []
+    for ev in timestepping.adjoint_step(
+        stepper, uf, maxit=maxit, apply_boundary=lambda t, u, p: ps.apply_boundary(pbc, grid, t, p)
+    ):
+        ps_.append(host(ev.p))
+    err = max_rel(np.stack(ps_), A[f"{key}_p"])
+    print(f"{which}-adjoint driver: {maxit} steps, p vs reference max rel {err:.3e}")
+    assert err < tol
+
+
+# }}}
+
+# {{{ the reference's own tests, verbatim criteria
+
+
+@pytest.mark.parametrize("rec_name", ["constant", "wenojs32", "wenojs53"])
+@pytest.mark.parametrize("bc_type", ["periodic", "dirichlet"])
+def test_advection_vs_continuity(rec_name: str, bc_type: str) -> None:
+    """tests/test_finite_difference.py:30-84: |<u, A v> - <C u, v>| < 1e-15 for constant velocity."""
+    import pyshocks_b200 as ps
+    from pyshocks_b200 import advection, config, continuity
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import PeriodicBoundary, make_dirichlet_boundary
+
+    config.set_math("strict")
+    rec = make_reconstruction_from_name(rec_name)
+    grid = ps.make_uniform_cell_grid(a=-1.0, b=1.0, n=256, nghosts=rec.stencil_width)
+    boundary = PeriodicBoundary() if bc_type == "periodic" else make_dirichlet_boundary(lambda t, x: torch.zeros_like(x))
+    velocity = torch.ones_like(grid.x)
+    ascheme = advection.Godunov(rec=rec, velocity=velocity)
+    cscheme = continuity.Godunov(rec=rec, velocity=velocity)
+    i = grid.i_
+
+    def dot(x, y):
+        return (x[i] * grid.dx[i]) @ y[i]
+
+    aop = partial(ps.apply_operator, ascheme, grid, boundary, 0.0)
+    cop = partial(ps.apply_operator, cscheme, grid, boundary, 0.0)
+    u = torch.sin(2.0 * np.pi * grid.x)
+    v = torch.sin(2.0 * np.pi * grid.x)
+    error = abs(float(dot(u, aop(v)) - dot(cop(u), v)))
+    assert error < 1.0e-15
+
+
+def _evolve(case_scheme, case_bc, case_exact, n, *, dt, a=-1.0, b=1.0, tfinal=0.5):
+    """tests/test_convergence.py:111-214 (the `evolve` driver) without the plotting."""
+    import pyshocks_b200 as ps
+    import pyshocks_b200.timestepping as ts
+
+    grid = ps.make_uniform_cell_grid(a=a, b=b, n=n, nghosts=3)
+    bc = case_bc(grid)
+    scheme = ps.bind(case_scheme(grid, bc), grid, bc)
+    quad = ps.make_leggauss_quadrature(grid, order=5)
+    u0 = ps.cell_average(quad, lambda x: case_exact(grid, 0.0, x))
+    maxit, dt = ts.predict_maxit_from_timestep(tfinal, dt)
+    stepper = ts.SSPRK33(
+        predict_timestep=lambda _t, _u: dt,
+        source=ps.jit(lambda t_, u_: ps.apply_operator(scheme, grid, bc, t_, u_)),
+        checkpoint=None,
+    )
+    u = u0
+    for event in ts.step(stepper, u0, maxit=maxit):
+        u = event.u
+    uhat = ps.cell_average(quad, lambda x: case_exact(grid, tfinal, x))
+    h_max = float(torch.max(torch.diff(grid.f)))
+    error = float(ps.norm(grid, u - uhat, weighted=True) / ps.norm(grid, uhat, weighted=True))
+    return h_max, error
+
+
+@pytest.mark.parametrize(
+    ("rec_name", "order", "resolutions"),
+    [
+        ("constant", 1, list(range(80, 160 + 1, 16))),
+        ("wenojs32", 3, list(range(192, 384 + 1, 32))),
+        ("wenojs53", 5, list(range(32, 256 + 1, 32))),
+    ],
+)
+def test_advection_convergence(rec_name: str, order: int, resolutions: list[int]) -> None:
+    """tests/test_convergence.py:312-343,395-460: godunov + rec, periodic, ic_sine_sine, t=1,
+    dt = 8 (2/n)^(5/3): EOC >= order - 0.5."""
+    import pyshocks_b200 as ps
+    from pyshocks_b200 import advection, funcs
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import PeriodicBoundary
+
+    def make_scheme(grid, bc):
+        rec = make_reconstruction_from_name(rec_name)
+        return advection.make_scheme_from_name("godunov", rec=rec, velocity=torch.full_like(grid.x, 1.0))
+
+    eoc = ps.EOCRecorder(name=f"advection_godunov_{rec_name}")
+    for n in resolutions:
+        dt = 8.0 * (2.0 / n) ** (5.0 / 3.0)
+        h, err = _evolve(make_scheme, lambda grid: PeriodicBoundary(),
+                         lambda grid, t, x: funcs.ic_sine_sine(grid, x - 1.0 * t), n, dt=dt, tfinal=1.0)
+        eoc.add_data_point(h, err)
+    print(eoc)
+    assert eoc.estimated_order >= order - 0.5
+
+
+@pytest.mark.parametrize(("sname", "resolutions"), [
+    ("rusanov", list(range(64, 128 + 1, 16))),
+    ("lf", list(range(64, 128 + 1, 16))),
+    ("eo", list(range(32, 128 + 1, 16))),
+])
+def test_burgers_convergence(sname: str, resolutions: list[int]) -> None:
+    """tests/test_convergence.py:223-303: constant rec, Dirichlet Riemann data, alpha = 0.98, t = 1,
+    EOC >= 0.9 (exercises the nu = df^(alpha-1) branch of the Rusanov / LF kernels)."""
+    import pyshocks_b200 as ps
+    from pyshocks_b200 import burgers, funcs
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import make_dirichlet_boundary
+    from pyshocks_b200.timestepping import predict_timestep_from_resolutions
+
+    def make_scheme(grid, bc):
+        return burgers.make_scheme_from_name(sname, rec=make_reconstruction_from_name("constant"), alpha=0.98)
+
+    def make_bc(grid):
+        return make_dirichlet_boundary(ga=lambda t, x: funcs.burgers_riemann(grid, t, x),
+                                       gb=lambda t, x: funcs.burgers_riemann(grid, t, x))
+
+    dt = predict_timestep_from_resolutions(-1.0, 1.0, resolutions, umax=10.0)
+    eoc = ps.EOCRecorder(name=f"burgers_{sname}_constant")
+    for n in resolutions:
+        h, err = _evolve(make_scheme, make_bc, lambda grid, t, x: funcs.burgers_riemann(grid, t, x), n,
+                         dt=dt, tfinal=1.0)
+        eoc.add_data_point(h, err)
+    print(eoc)
+    assert eoc.estimated_order >= 1 - 0.1
+
+
+@pytest.mark.parametrize(("name", "order", "resolutions"), [
+    ("wenojs32", 3, list(range(192, 384 + 1, 32))),
+    ("wenojs53", 5, list(range(32, 256 + 1, 32))),
+])
+def test_weno_smooth_reconstruction_order_cell_values(name: str, order: int, resolutions: list[int]) -> None:
+    """tests/test_weno.py:288-338."""
+    import pyshocks_b200 as ps
+    from pyshocks_b200 import BoundaryType
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name, reconstruct
+
+    func = lambda x: torch.sin(2 * np.pi * x)  # noqa: E731
+    eoc_l, eoc_r = ps.EOCRecorder(name="ul"), ps.EOCRecorder(name="ur")
+    for n in resolutions:
+        rec = make_reconstruction_from_name(name)
+        grid = ps.make_uniform_cell_grid(-1.0, 1.0, n=n, nghosts=rec.stencil_width)
+        quad = ps.make_leggauss_quadrature(grid, order=order + 1)
+        u0 = ps.cell_average(quad, func)
+        ref = func(grid.f)
+        ul, ur = reconstruct(rec, grid, BoundaryType.Dirichlet, u0, u0, u0)
+        eoc_l.add_data_point(grid.h, float(ps.rnorm(grid, ul, ref[:-1], p=float("inf"))))
+        eoc_r.add_data_point(grid.h, float(ps.rnorm(grid, ur, ref[1:], p=float("inf"))))
+    assert eoc_l.satisfied(order - 0.5)
+    assert eoc_r.satisfied(order - 0.5)
+
+
+def test_ssprk33_temporal_order() -> None:
+    """tests/test_timestepping.py:26-99: order >= 2.9 on a scalar ODE through the generic path."""
+    import pyshocks_b200 as ps
+    import pyshocks_b200.timestepping as ts
+
+    eoc = ps.EOCRecorder(name="ssprk33")
+    tfinal = 4.0
+    for n in range(2, 7):
+        maxit, dt = ts.predict_maxit_from_timestep(tfinal, 1.0 / 2.0**n)
+        stepper = ts.SSPRK33(predict_timestep=lambda t, u, dt=dt: dt,
+                             source=lambda t, u: torch.exp(-t) * torch.ones_like(u), checkpoint=None)
+        u0 = torch.zeros(1, dtype=torch.float64, device="cuda")
+        for event in ts.step(stepper, u0, maxit=maxit):
+            pass
+        exact = 1.0 - np.exp(-float(event.t))
+        eoc.add_data_point(dt, abs(float(event.u[0]) - exact))
+    assert eoc.estimated_order >= 2.9
+
+
+# }}}
+
+# {{{ error behaviour of the boundary (SURVEY.md section 8b "errors")
+
+
+def test_error_behaviour() -> None:
+    import pyshocks_b200 as ps
+    from pyshocks_b200 import burgers, timestepping
+    from pyshocks_b200.checkpointing import InMemoryCheckpoint, load, save
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import PeriodicBoundary
+
+    with pytest.raises(ValueError):
+        ps.make_uniform_cell_grid(a=1.0, b=-1.0, n=16)  # grid.py:145-146
+    with pytest.raises(ValueError):
+        ps.make_uniform_cell_grid(a=-1.0, b=1.0, n=0)  # grid.py:148-149
+    with pytest.raises(ValueError):
+        make_reconstruction_from_name("muscl")  # outside the hot path
+    with pytest.raises(ValueError):
+        burgers.make_scheme_from_name("ssweno242")
+    rec = make_reconstruction_from_name("wenojs53")
+    grid = ps.make_uniform_cell_grid(a=-1.0, b=1.0, n=32, nghosts=3)
+    bc = PeriodicBoundary()
+
+    class Other(ps.SchemeBase):
+        pass
+
+    with pytest.raises(NotImplementedError):
+        ps.apply_operator(Other(rec=rec), grid, bc, 0.0, grid.x)  # schemes.py:166
+    with pytest.raises(NotImplementedError):
+        ps.predict_timestep(Other(rec=rec), grid, bc, 0.0, grid.x)  # schemes.py:190
+    scheme = burgers.Rusanov(rec=rec)
+    with pytest.raises(TypeError):
+        ps.apply_operator(scheme, grid, bc, 0.0, grid.x.cpu())  # no CPU fallback
+    with pytest.raises(ValueError):
+        ps.apply_operator(scheme, grid, bc, 0.0, grid.x[:-1].contiguous())  # scalar.py:227 shape assert
+    small = ps.make_uniform_cell_grid(a=-1.0, b=1.0, n=32, nghosts=2)
+    with pytest.raises(AssertionError):
+        ps.apply_operator(scheme, small, bc, 0.0, small.x)  # reconstruction.py:369 nghosts >= stencil
+    chk = InMemoryCheckpoint(basename="It")
+    save(chk, 0, {"m": 0})
+    with pytest.raises(KeyError):
+        save(chk, 0, {"m": 0})  # checkpointing.py:123-124
+    with pytest.raises(KeyError):
+        load(chk, 3)  # checkpointing.py:134-135
+    stepper = timestepping.SSPRK33(predict_timestep=lambda t, u: float("nan"), source=ps.bind_operator(scheme, grid, bc), checkpoint=None)
+    with pytest.raises(ValueError):
+        for _ in timestepping.step(stepper, torch.sin(grid.x), tfinal=float("inf")):  # timestepping.py:140-145
+            pass
+    with pytest.raises(ValueError):
+        next(timestepping.adjoint_step(stepper, grid.x, maxit=1))  # timestepping.py:162-163
+
+
+# }}}

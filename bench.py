@@ -77,15 +77,16 @@ def cpu_port_throughput(target_seconds: float, steps: int | None = None) -> dict
     cores = len(os.sched_getaffinity(0))
     h = (DOMAIN[1] - DOMAIN[0]) / N_CELLS
     # calibrate on a small slice, then size the sample
-    rows = max(cores, 8)
+    rows = max(4 * cores, 32)
     coef = ensemble_coefficients(rows, 20261017)
     u0 = host_initial_condition(coef, N_CELLS, GHOSTS)
     dt = CFL * h / np.abs(u0).max()
     co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS, g=GHOSTS,
                  batch=rows, dx=h, eps=EPS)
+    co.solve_fixed_dt(u0, dt, 1)  # thread pool start-up
     t0 = time.perf_counter()
-    co.solve_fixed_dt(u0, dt, 1)
-    rate = rows * N_CELLS / (time.perf_counter() - t0)  # cell-updates/s with all threads
+    co.solve_fixed_dt(u0, dt, 2)
+    rate = 2 * rows * N_CELLS / (time.perf_counter() - t0)  # cell-updates/s with all threads
     nsteps = steps if steps is not None else 4
     rows_s = int(min(BATCH, target_seconds * rate / (N_CELLS * nsteps)))
     rows_s = max(cores, (rows_s // cores) * cores)
@@ -158,48 +159,65 @@ def workload_config(n_gpus: int) -> dict:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md), through
+    NVML from a background thread (every 2 ms); falls back to one nvidia-smi query."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    REASONS = {
+        "hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+        "hw_power_brake_slowdown": 0x80,
+    }
 
     def __init__(self, index: int) -> None:
-        self.proc = None
+        import threading
+
+        self.index = index
+        self.sm: list[float] = []
+        self.mask = 0
+        self.max_mhz = None
+        self.power: list[float] = []
+        self._stop = threading.Event()
+        self._nvml = None
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self._nvml = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self) -> None:
+        nv = self._nvml
+        if nv is None:
+            return
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-            out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
-        for ln in out.strip().splitlines():
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if self._nvml is None or not self.sm:
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = (float(x) for x in out.strip().split(","))
+                return {"sm_mhz": a, "sm_max_mhz": b, "samples": 1, "reasons": ["sampled after the run (no NVML)"]}
+            except Exception:  # noqa: BLE001
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock query unavailable"]}
+        reasons = sorted(name for name, bit in self.REASONS.items() if self.mask & bit)
         return {
-            "sm_mhz": statistics.median(sm) if sm else None,
-            "sm_max_mhz": max(mx) if mx else None,
-            "samples": len(sm),
-            "reasons": sorted(reasons),
+            "sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz,
+            "power_w_max": max(self.power) if self.power else None, "samples": len(self.sm), "reasons": reasons,
         }
 
 
@@ -295,7 +313,7 @@ def run_ours(args: argparse.Namespace) -> None:
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "psk::stage_tile_kernel (3 launches per step; 64 algorithmic bytes per cell-update)",
+                "kernel": "psk::stage_warp_kernel (3 launches per step; 64 algorithmic bytes per cell-update)",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_UPDATE / 3 * batch * N_CELLS,
                 "avg_launch_ms": ms_total / (3 * args.steps),
             },
@@ -309,7 +327,7 @@ def run_ours(args: argparse.Namespace) -> None:
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_port_throughput(target_seconds=12.0)
+            line["cpu_baseline"] = cpu_port_throughput(target_seconds=15.0)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -55,11 +55,15 @@ class ShardedEnsemble:
         if self.world == 1:
             return local
         shapes = [shard_rows(self.global_batch, r, self.world)[1] for r in range(self.world)]
-        bufs = None
-        if self.rank == dst:
-            bufs = [torch.empty((rows, local.shape[1]), dtype=local.dtype, device=local.device) for rows in shapes]
-        dist.gather(local, bufs, dst=dst)
-        return torch.cat(bufs, dim=0) if bufs is not None else None
+        # NCCL collectives want equal shapes: pad every shard to the largest one
+        rows_max = max(shapes)
+        padded = torch.zeros((rows_max, local.shape[1]), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
+        bufs = [torch.empty_like(padded) for _ in range(self.world)]
+        dist.all_gather(bufs, padded)
+        if self.rank != dst:
+            return None
+        return torch.cat([b[:rows] for b, rows in zip(bufs, shapes)], dim=0)
 
 
 # {{{ halo exchange on a periodic ring

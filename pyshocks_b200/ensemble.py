@@ -59,7 +59,7 @@ class EnsembleSolver:
         self.col0 = (16 - self.g) % 16
         self.ld = ((self.col0 + self.nx + 15) // 16) * 16
         self._store = torch.zeros((3, self.batch, self.ld), dtype=torch.float64, device=dev)
-        self.u, self.k1, self.k2 = (self._store[i, :, self.col0 : self.col0 + self.nx] for i in range(3))
+        self.u, self.k1, self.k2 = self.views(self._store)
         self.t = torch.zeros(self.batch, dtype=torch.float64, device=dev)
         self.dt = torch.zeros(self.batch, dtype=torch.float64, device=dev)
         self.maxabs = torch.zeros(self.batch, dtype=torch.float64, device=dev)
@@ -69,6 +69,13 @@ class EnsembleSolver:
         self._graph: torch.cuda.CUDAGraph | None = None
         self._graph_key: tuple | None = None
         self.launches = 0  # kernels launched by this solver (bench.py reports it)
+
+    def new_states(self, count: int) -> list[torch.Tensor]:
+        """``count`` more ``(batch, nx)`` arrays with the solver's padded, aligned row layout."""
+        return self.views(torch.zeros((count, self.batch, self.ld), dtype=torch.float64, device=self.hp.device))
+
+    def views(self, store: torch.Tensor) -> list[torch.Tensor]:
+        return [store[i, :, self.col0 : self.col0 + self.nx] for i in range(store.shape[0])]
 
     # {{{ state I/O
 
@@ -187,3 +194,86 @@ class EnsembleSolver:
             dt_history=None if hist is None else hist[:steps].cpu().numpy(),
             steps_per_row=steps_per_row,
         )
+
+
+class AdjointEnsemble:
+    """Forward sweep with a device-resident tape and the discrete-adjoint reverse sweep for an
+    ensemble advanced with a fixed ``dt`` (BASELINE.json configs[4]: B = 4096 x N = 8192, 1000
+    steps, J = 1/2 sum ||u(T)||^2 over the interior).
+
+    The reference keeps every step's state (``InMemoryCheckpoint``, timestepping.py:130-131) and
+    builds a dense Jacobian per step.  Here the tape is two-level: every ``segment``-th state is
+    kept (``nsteps / segment`` arrays) and the states inside a segment are recomputed into a
+    ``segment``-deep scratch ring during the reverse sweep, so the memory is
+    ``(nsteps / segment + segment)`` states instead of ``nsteps`` (268 MB each at config 5); each
+    reverse step recomputes ``k1, k2`` (2 forward stage launches) and applies 3 fused adjoint
+    stage launches.  ``p`` carries zero cotangents in the ghost cells and no boundary condition
+    is imposed on it: ``backward`` returns the exact gradient of the discrete forward map."""
+
+    def __init__(self, solver: EnsembleSolver, *, nsteps: int, dt: float | torch.Tensor, segment: int | None = None) -> None:
+        self.s = solver
+        self.nsteps = int(nsteps)
+        if segment is None:
+            segment = max(1, int(round(self.nsteps**0.5)))
+        self.segment = int(min(max(segment, 1), max(self.nsteps, 1)))
+        dev = solver.hp.device
+        self.dt = dt if isinstance(dt, torch.Tensor) else torch.full((1,), float(dt), dtype=torch.float64, device=dev)
+        self.nseg = (self.nsteps + self.segment - 1) // self.segment
+        self.chk = solver.new_states(self.nseg + 1)  # states at steps 0, k, 2k, ...
+        self.ring = solver.new_states(self.segment)  # states inside the current segment
+        self.lam2, self.lam1, self.p, self.pn = solver.new_states(4)
+        self.launches = 0
+
+    def _advance(self, src: torch.Tensor, dst: torch.Tensor) -> None:
+        s, hp = self.s, self.s.hp
+        hp.stage(1, src, src, s.k1, self.dt)
+        hp.stage(2, src, s.k1, s.k2, self.dt)
+        hp.stage(3, src, s.k2, dst, self.dt)
+        self.launches += 3
+
+    def forward(self, u0: torch.Tensor | np.ndarray | None = None) -> torch.Tensor:
+        """Advance ``nsteps`` steps, keeping every ``segment``-th state; returns ``u(T)`` (a view)."""
+        s = self.s
+        if u0 is not None:
+            s.load(u0)
+        self.chk[0].copy_(s.u)
+        for m in range(self.nsteps):
+            self._advance(s.u, s.u)
+            if (m + 1) % self.segment == 0 or m + 1 == self.nsteps:
+                self.chk[(m + self.segment) // self.segment].copy_(s.u)
+        return s.u
+
+    def backward(self, pT: torch.Tensor) -> torch.Tensor:
+        """Reverse sweep: returns ``p(0) = (d u(T) / d u(0))^T pT`` (a view of an internal buffer)."""
+        s, hp = self.s, self.s.hp
+        p, pn = self.p, self.pn
+        p.copy_(pT)
+        for seg in range(self.nseg - 1, -1, -1):
+            m0 = seg * self.segment
+            m1 = min(m0 + self.segment, self.nsteps)
+            # recompute the states u^{m0} .. u^{m1 - 1} of this segment
+            self.ring[0].copy_(self.chk[seg])
+            for j in range(1, m1 - m0):
+                self._advance(self.ring[j - 1], self.ring[j])
+            for j in range(m1 - m0 - 1, -1, -1):
+                u = self.ring[j]
+                hp.stage(1, u, u, s.k1, self.dt)
+                hp.stage(2, u, s.k1, s.k2, self.dt)
+                hp.stage_adjoint(s.k2, p, self.dt, 2.0 / 3.0, self.lam2)
+                hp.stage_adjoint(s.k1, self.lam2, self.dt, 1.0 / 4.0, self.lam1)
+                hp.stage_adjoint(u, self.lam1, self.dt, 1.0, pn, acc=p, c_acc=1.0 / 3.0, acc2=self.lam2, c_acc2=3.0 / 4.0)
+                p, pn = pn, p
+                self.launches += 5 + (3 if hp.bc in ("periodic", "neumann") else 0)
+        self.p, self.pn = p, pn
+        return p
+
+    def gradient_half_l2(self, u0: torch.Tensor | np.ndarray | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+        """``J_b = 1/2 sum_i u_b(T)_i^2`` over the interior and ``dJ_b / du_b(0)`` for every row."""
+        s = self.s
+        uT = self.forward(u0)
+        g, n = s.g, s.n
+        J = 0.5 * (uT[:, g : g + n] ** 2).sum(dim=1)
+        pT = self.lam1  # scratch until the sweep starts
+        pT.zero_()
+        pT[:, g : g + n] = uT[:, g : g + n]
+        return J, self.backward(pT)

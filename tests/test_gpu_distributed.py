@@ -81,13 +81,20 @@ def _nccl_worker(rank: int, world: int, port: int, out: dict) -> None:
         from pyshocks_b200.distributed import DistRing, ShardedEnsemble, SlabSolver, shard_rows
         from pyshocks_b200.ensemble import EnsembleSolver
 
+        def mark(msg: str) -> None:
+            print(f"[rank {rank}] {msg}", flush=True)
+
+        mark("process group up")
         n, g, nsteps = 1 << 16, 3, 10
         dt = 0.4 * (3.0 / n) / 1.8
         ring = DistRing()
         ug = torch.from_numpy(_ic(n, g)).cuda()
         slab = SlabSolver(n_global=n, ring=ring, dx=3.0 / n)
         slab.load_interior(ug[slab.first : slab.first + slab.n_local])
+        mark("slab built")
         slab.solve_fixed_dt(dt, nsteps)
+        torch.cuda.synchronize()
+        mark("slab fixed-dt done")
         ref = _reference_periodic(n, dt, nsteps, "fast")
         ok = torch.equal(slab.interior(), ref[slab.first : slab.first + slab.n_local])
 
@@ -100,6 +107,7 @@ def _nccl_worker(rank: int, world: int, port: int, out: dict) -> None:
         u0 = torch.zeros((1, n + 2 * g), dtype=torch.float64, device="cuda")
         u0[0, g : g + n] = ug
         sres = single.solve_adaptive(u0, theta=0.8, tfinal=0.002, cfl_scale=0.5 * (3.0 / n), check_every=1)
+        mark("adaptive done")
         ok = ok and res.steps == sres.steps
         ok = ok and torch.equal(slab2.interior(), single.u[0, g + slab2.first : g + slab2.first + slab2.n_local])
 
@@ -111,6 +119,7 @@ def _nccl_worker(rank: int, world: int, port: int, out: dict) -> None:
         sh = ShardedEnsemble(batch=B, **kw)
         sh.solver.solve_fixed_dt(sh.local_rows(U), 1e-4, 5)
         full = sh.gather(dst=0)
+        mark("gather done")
         if rank == 0:
             one = EnsembleSolver(batch=B, **kw)
             one.solve_fixed_dt(U, 1e-4, 5)

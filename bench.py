@@ -333,8 +333,141 @@ def run_ours(args: argparse.Namespace) -> None:
         dist.destroy_process_group()
 
 
+def run_slab(args: argparse.Namespace) -> None:
+    """BASELINE.json configs[3]: ONE periodic Burgers grid of N = 2^30 cells, slab-decomposed over
+    the ranks with ring halo exchange (3 cells per side per stage), fixed dt at CFL 0.4."""
+    import torch
+    import torch.distributed as dist
+
+    from pyshocks_b200.distributed import DistRing, SlabSolver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
+    n_global = args.cells if args.cells else (1 << 30)
+    h = (DOMAIN[1] - DOMAIN[0]) / n_global
+    ring = DistRing()
+    slab = SlabSolver(n_global=n_global, ring=ring, dx=h, device=dev)
+    i = torch.arange(slab.first, slab.first + slab.n_local, device=dev, dtype=torch.float64)
+    slab.load_interior(0.5 + torch.sin(2.0 * np.pi * (i + 0.5) / n_global))
+    del i
+    dt = torch.full((1,), CFL * h / 1.5, dtype=torch.float64, device=dev)
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    slab.solve_fixed_dt(dt, args.warmup)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    slab.solve_fixed_dt(dt, args.steps)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        value = n_global * args.steps / (float(ms) * 1e-3)
+        peak, peak_src = measured_peaks()
+        achieved = value / world * ALGO_BYTES_PER_CELL_UPDATE / 1e9
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(ms) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"single periodic Burgers grid N={n_global} cells, slab-decomposed over {world} rank(s), "
+                                   "ring halo exchange 3 cells/side/stage (BASELINE.json configs[3])",
+                       "cells_per_gpu": slab.n_local, "halo_exchanges_per_step": 3},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src},
+            "gpu_launches": 3 * args.steps,
+        }), flush=True)
+    dist.destroy_process_group()
+
+
+def run_adjoint(args: argparse.Namespace) -> None:
+    """BASELINE.json configs[4]: B = 4096 x N = 8192 ensemble, K fixed-dt steps forward with a
+    two-level device tape, reverse sweep for J = 1/2 sum ||u(T)||^2; rows sharded over the ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from pyshocks_b200.ensemble import AdjointEnsemble, EnsembleSolver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    batch, n = (args.batch if args.batch != BATCH else 4096), (args.cells if args.cells else 8192)
+    h = (DOMAIN[1] - DOMAIN[0]) / n
+    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=GHOSTS,
+                            dx=h, eps=EPS, batch=batch, device=dev)
+    coef = torch.from_numpy(ensemble_coefficients(batch, 20261018 + rank)).to(dev)
+    xhat = ((torch.arange(solver.nx, device=dev, dtype=torch.float64) - GHOSTS + 0.5) / n)[None, :]
+    u0 = coef[:, :1].repeat(1, solver.nx)
+    for k in range(4):
+        u0 += coef[:, 1 + k : 2 + k] * torch.sin(2.0 * np.pi * (k + 1) * xhat + coef[:, 5 + k : 6 + k])
+    dt = CFL * h / float(u0.abs().max())
+    nsteps = args.steps
+    adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt)
+    small = AdjointEnsemble(solver, nsteps=4, dt=dt, segment=2)
+    small.gradient_half_l2(u0)  # warm-up of every kernel
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    if world > 1:
+        dist.barrier(device_ids=[local])
+    ev[0].record()
+    uT = adj.forward(u0)
+    ev[1].record()
+    pT = adj.lam1
+    pT.zero_()
+    pT[:, GHOSTS : GHOSTS + n] = uT[:, GHOSTS : GHOSTS + n]
+    grad = adj.backward(pT)
+    ev[2].record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    fwd_ms, bwd_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        cells = batch * n * world
+        adj_rate = cells * nsteps / (bwd_ms * 1e-3)
+        # reverse sweep, per cell-step: recompute k1, k2 (16 + 24 B), three adjoint stages (32 + 40 + 32 B),
+        # plus the segment recompute (64 B per forward step, amortised (segment - 1) / segment)
+        algo = 144.0 + 64.0 * (adj.segment - 1) / adj.segment
+        achieved = adj_rate / world * algo / 1e9
+        print(json.dumps({
+            "metric": "adjoint gradients/s", "value": batch * world / ((fwd_ms + bwd_ms) * 1e-3), "unit": "gradients/s",
+            "n_gpus": world, "steps": nsteps, "warmup": args.warmup, "ms_per_step": (fwd_ms + bwd_ms) / nsteps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"adjoint of a batched Burgers ensemble B={batch} x N={n} per GPU, {nsteps} fixed-dt SSPRK33 "
+                                   f"steps, two-level tape (segment {adj.segment}), J = 1/2 sum ||u(T)||^2 (BASELINE.json configs[4])",
+                       "forward_ms": fwd_ms, "reverse_ms": bwd_ms, "tape_states": len(adj.chk) + len(adj.ring),
+                       "adjoint_cell_updates_per_s": adj_rate, "forward_cell_updates_per_s": cells * nsteps / (fwd_ms * 1e-3),
+                       "grad_finite": bool(torch.isfinite(grad).all())},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_cell_step": algo},
+            "gpu_launches": adj.launches,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", choices=("ensemble", "slab", "adjoint"), default="ensemble",
+                    help="ensemble = the headline config (default); slab / adjoint = BASELINE configs 4 and 5")
+    ap.add_argument("--cells", type=int, default=0, help="override the cell count of the slab / adjoint workloads")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
@@ -352,6 +485,10 @@ def main() -> None:
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "slab":
+        run_slab(args)
+    elif args.workload == "adjoint":
+        run_adjoint(args)
     else:
         run_ours(args)
 

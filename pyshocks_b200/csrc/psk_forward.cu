@@ -456,6 +456,208 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
   }
 }
 
+// ---------------------------------------------------------------------------
+// The hot configuration, specialised: WENO-JS5, FAST math, nu = 1, every row active,
+// 16-byte aligned rows.  Same algorithm and data movement as stage_warp_kernel; what differs
+// is the bookkeeping: the grid is (chunk groups, rows) so no integer division is needed, the
+// stage is a template parameter, the Rusanov speed max(|w_j|, |w_j+1|) is an integer max of the
+// bit patterns (2 ALU compares + 2 selects instead of an emulated fp64 max), and the candidate
+// offsets reuse the smoothness stencils' linear forms (weno53_pair_lean).
+struct FastParams {
+  const double *uin;
+  const double *u0;
+  double *uout;
+  const double *dt;
+  const double *lf_speed;
+  unsigned long long *maxabs;
+  const double *vel;
+  const double *vel_l;
+  const double *vel_r;
+  BcView bc;
+  int64_t ld;
+  double coef;   // 1 / (flux scale * dx)
+  double eps9;   // eps / 9
+  int dt_stride;
+  int chunks_per_row;
+};
+
+__device__ __forceinline__ double umax_abs(double a, double b) {
+  const unsigned long long x = static_cast<unsigned long long>(__double_as_longlong(a)) & 0x7fffffffffffffffull;
+  const unsigned long long y = static_cast<unsigned long long>(__double_as_longlong(b)) & 0x7fffffffffffffffull;
+  return __longlong_as_double(static_cast<long long>(x > y ? x : y));
+}
+
+template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
+__global__ void __launch_bounds__(256)
+stage_warp_fast_kernel(const FastParams p) {
+  constexpr int R = 4;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kOut = 30 * R;
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chunk >= p.chunks_per_row) return;
+  const int row = blockIdx.y + blockIdx.z * gridDim.y;
+  const int g = p.bc.g, n = p.bc.n;
+  const int c0 = chunk * kOut - R + R * lane;
+  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
+  const bool inside = (c0 >= 0) && (c0 + R <= n);
+  const bool emit = (lane >= 1) && (lane <= 30);
+
+  double v[R + 2 * kHalo];
+  if (inside) {
+    const double2 q0 = *reinterpret_cast<const double2 *>(p.uin + off);
+    const double2 q1 = *reinterpret_cast<const double2 *>(p.uin + off + 2);
+    v[3] = q0.x; v[4] = q0.y; v[5] = q1.x; v[6] = q1.y;
+  } else {
+    const double *__restrict__ urow = p.uin + static_cast<int64_t>(row) * p.ld;
+#pragma unroll
+    for (int r = 0; r < R; ++r) v[kHalo + r] = load_w(p.bc, urow, row, g + c0 + r);
+  }
+  double u0v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) u0v[r] = 0.0;
+  if (STAGE >= 2 && emit) {
+    if (inside) {
+      const double2 q0 = *reinterpret_cast<const double2 *>(p.u0 + off);
+      const double2 q1 = *reinterpret_cast<const double2 *>(p.u0 + off + 2);
+      u0v[0] = q0.x; u0v[1] = q0.y; u0v[2] = q1.x; u0v[3] = q1.y;
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (c0 + r >= 0 && c0 + r < n) u0v[r] = p.u0[off + r];
+    }
+  }
+  v[0] = __shfl_up_sync(kFull, v[4], 1);
+  v[1] = __shfl_up_sync(kFull, v[5], 1);
+  v[2] = __shfl_up_sync(kFull, v[6], 1);
+  v[7] = __shfl_down_sync(kFull, v[3], 1);
+  v[8] = __shfl_down_sync(kFull, v[4], 1);
+  v[9] = __shfl_down_sync(kFull, v[5], 1);
+
+  double t[R + 5], pq[R + 4];
+#pragma unroll
+  for (int k = 0; k < R + 5; ++k) t[k] = (1.0 / 6.0) * (v[k + 1] - v[k]);
+#pragma unroll
+  for (int k = 0; k < R + 4; ++k) {
+    const double dd = t[k + 1] - t[k];
+    pq[k] = fma((13.0 / 3.0) * dd, dd, p.eps9);
+  }
+  double ul[R], ur[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int m = r + kHalo;
+    const Weno5Pair o = weno53_pair_lean(v[m], t[m - 2], t[m - 1], t[m], t[m + 1], pq[m - 2], pq[m - 1], pq[m]);
+    ul[r] = o.ul;
+    ur[r] = o.ur;
+  }
+  const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
+  const double ul_right = __shfl_down_sync(kFull, ul[0], 1);
+
+  const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
+  double F[R + 1];
+#pragma unroll
+  for (int f = 0; f <= R; ++f) {
+    const double urj = (f == 0) ? ur_left : ur[f - 1];
+    const double ulp = (f == R) ? ul_right : ul[f];
+    if (EQ == PSK_EQ_BURGERS) {
+      if (FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) {
+        const double a = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? speed : umax_abs(v[f + kHalo - 1], v[f + kHalo]);
+        F[f] = fma(-2.0 * a, ulp - urj, fma(urj, urj, ulp * ulp));  // 4 F
+      } else if (FLUX == PSK_FLUX_UPWIND) {
+        const double w = (urj + ulp) > 0.0 ? urj : ulp;
+        F[f] = w * w;  // 2 F
+      } else {
+        const double vp = fmax(urj, 0.0), vm = fmin(ulp, 0.0);
+        F[f] = fma(vp, vp, vm * vm);  // 2 F
+      }
+    } else {
+      const int j = g + c0 + f - 1;
+      const bool ok = (j >= 0 && j < p.bc.nx - 1);
+      const double arj = ok ? p.vel_r[j] : 0.0, alp = ok ? p.vel_l[j + 1] : 0.0;
+      const bool pos = (arj + alp) > 0.0;
+      F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? arj * urj : alp * ulp);
+    }
+  }
+
+  double coef = p.coef;
+  if (STAGE != 0) coef *= p.dt[static_cast<int64_t>(row) * p.dt_stride];
+  double out[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    double dF = F[r] - F[r + 1];
+    if (EQ == PSK_EQ_ADVECTION) dF *= (c0 + r >= 0 && c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
+    if (STAGE == 0) {
+      out[r] = coef * dF;
+    } else {
+      const double k = fma(coef, dF, v[r + kHalo]);
+      out[r] = (STAGE == 1) ? k
+                            : ((STAGE == 2) ? fma(0.25, k, 0.75 * u0v[r]) : fma(2.0 / 3.0, k, (1.0 / 3.0) * u0v[r]));
+    }
+  }
+  if (emit) {
+    if (inside) {
+      *reinterpret_cast<double2 *>(p.uout + off) = make_double2(out[0], out[1]);
+      *reinterpret_cast<double2 *>(p.uout + off + 2) = make_double2(out[2], out[3]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (c0 + r >= 0 && c0 + r < n) p.uout[off + r] = out[r];
+    }
+  }
+  if (WITH_MAX) {
+    unsigned long long mx = 0ull;
+    if (emit) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (c0 + r >= 0 && c0 + r < n) {
+          const unsigned long long b = abs_bits(out[r]);
+          mx = b > mx ? b : mx;
+        }
+    }
+    mx = warp_max_bits(mx);
+    if (lane == 0) atomicMax(p.maxabs + row, mx);
+  }
+}
+
+template <int EQ, int FLUX, int STAGE>
+int launch_fast_stage(const StageParams &p, int batch, cudaStream_t st) {
+  FastParams q{};
+  q.uin = p.uin; q.u0 = p.u0; q.uout = p.uout; q.dt = p.dt; q.lf_speed = p.lf_speed;
+  q.maxabs = p.maxabs; q.vel = p.vel; q.vel_l = p.vel_l; q.vel_r = p.vel_r; q.bc = p.bc; q.ld = p.ld;
+  q.coef = p.invdx / FluxScale<EQ, FLUX>::value;
+  q.eps9 = p.eps * (1.0 / 9.0);
+  q.dt_stride = static_cast<int>(p.dt_stride);
+  q.chunks_per_row = (p.bc.n + 119) / 120;
+  // warps per CTA: the divisor-friendly choice in 4..8 that wastes the fewest warps
+  int wpc = 8, best_waste = 1 << 30;
+  for (int w = 8; w >= 4; --w) {
+    const int waste = ((q.chunks_per_row + w - 1) / w) * w - q.chunks_per_row;
+    if (waste < best_waste) { best_waste = waste; wpc = w; }
+  }
+  if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
+  const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
+  const unsigned gy = batch < 65535 ? batch : 65535u;
+  if (batch % gy != 0 && batch > 65535) return PSK_E_UNSUPPORTED;  // caller falls back
+  const unsigned gz = batch / gy;
+  const dim3 grid(gx, gy, gz);
+  if (p.maxabs != nullptr)
+    stage_warp_fast_kernel<EQ, FLUX, STAGE, true><<<grid, wpc * 32, 0, st>>>(q);
+  else
+    stage_warp_fast_kernel<EQ, FLUX, STAGE, false><<<grid, wpc * 32, 0, st>>>(q);
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
+template <int EQ, int FLUX>
+int launch_fast(const StageParams &p, int batch, cudaStream_t st) {
+  switch (p.stage) {
+    case 0: return launch_fast_stage<EQ, FLUX, 0>(p, batch, st);
+    case 1: return launch_fast_stage<EQ, FLUX, 1>(p, batch, st);
+    case 2: return launch_fast_stage<EQ, FLUX, 2>(p, batch, st);
+    default: return launch_fast_stage<EQ, FLUX, 3>(p, batch, st);
+  }
+}
+
 // one chunk per warp
 template <int EQ, int FLUX, int REC, bool STRICT, int R>
 __global__ void __launch_bounds__(256)
@@ -468,6 +670,29 @@ stage_warp_kernel(const StageParams p, long long total_warps) {
   double own[R], u0v[R];
   chunk_load<R>(p, c, own, u0v);
   chunk_compute<EQ, FLUX, REC, STRICT, R>(p, c, lane, own, u0v);
+}
+
+// CH consecutive chunks per warp: all loads are issued first, then the chunks are computed one
+// after the other, so the DRAM latency of chunk c + 1 hides behind the arithmetic of chunk c
+template <int EQ, int FLUX, int REC, bool STRICT, int R, int CH>
+__global__ void __launch_bounds__(256)
+stage_warp_multi_kernel(const StageParams p, long long total_warps) {
+  const int lane = threadIdx.x & 31;
+  const long long group = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long first = group * CH;
+  if (first >= total_warps) return;
+  ChunkRef c[CH];
+  double own[CH][R], u0v[CH][R];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) {
+    const long long w = first + k < total_warps ? first + k : total_warps - 1;
+    c[k] = chunk_ref<R>(p, w, lane);
+    if (first + k >= total_warps) c[k].live = false;
+    chunk_load<R>(p, c[k], own[k], u0v[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < CH; ++k)
+    if (c[k].live) chunk_compute<EQ, FLUX, REC, STRICT, R>(p, c[k], lane, own[k], u0v[k]);
 }
 
 // persistent warps: each warp walks over chunks warp_id, warp_id + stride, ... and issues the
@@ -556,6 +781,8 @@ __global__ void ghost_rows_kernel(const StageParams p, int batch) {
 // 0: warp kernel (default), 1: shared-memory tile kernel (kept for A/B measurements)
 static int g_stage_variant = 0;
 static int g_warp_block = 256;  // threads per CTA of the warp kernel (tuning)
+static int g_use_fast = 1;  // specialised kernel for the hot configuration (stage_warp_fast_kernel)
+static int g_chunks_per_warp = 1;  // 1, 2 or 3 chunks per warp (stage_warp_multi_kernel)
 static int g_persistent_ctas_per_sm = 0;  // 0: one chunk per warp (default, faster as measured); >0: persistent warps with register prefetch
 
 template <int EQ, int FLUX, int REC, bool STRICT>
@@ -603,6 +830,36 @@ int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStrea
                        (p.u0 == nullptr || reinterpret_cast<uintptr_t>(p.u0 + p.bc.g) % 16 == 0) &&
                        (p.ld % 2 == 0);
   q.vec_ok = aligned ? 1 : 0;
+  if (g_use_fast && REC == PSK_REC_WENOJS53 && !STRICT && q.vec_ok && p.nu == nullptr && p.active == nullptr &&
+      (batch <= 65535 || batch % 65535 == 0 || batch % 32768 == 0)) {
+    int rc = PSK_E_UNSUPPORTED;
+    if (batch <= 65535 || batch % 65535 == 0) {
+      rc = launch_fast<EQ, FLUX>(q, batch, st);
+    } else {
+      // rows beyond the grid.y limit: split the batch into equal slices of 32768 rows
+      rc = PSK_OK;
+      for (int b0 = 0; b0 < batch && rc == PSK_OK; b0 += 32768) {
+        StageParams s2 = q;
+        s2.uin = q.uin + static_cast<int64_t>(b0) * q.ld;
+        s2.uout = q.uout + static_cast<int64_t>(b0) * q.ld;
+        if (q.u0 != nullptr) s2.u0 = q.u0 + static_cast<int64_t>(b0) * q.ld;
+        if (q.dt != nullptr) s2.dt = q.dt + static_cast<int64_t>(b0) * q.dt_stride;
+        if (q.lf_speed != nullptr) s2.lf_speed = q.lf_speed + b0;
+        if (q.maxabs != nullptr) s2.maxabs = q.maxabs + b0;
+        if (q.bc.ghost != nullptr) s2.bc.ghost = q.bc.ghost + static_cast<int64_t>(b0) * q.bc.ghost_ld;
+        rc = launch_fast<EQ, FLUX>(s2, 32768, st);
+      }
+    }
+    if (rc == PSK_OK) {
+      if (ghost_rows) {
+        const int total = batch * 2 * p.bc.g;
+        ghost_rows_kernel<EQ, FLUX, REC, STRICT><<<(total + 127) / 128, 128, 0, st>>>(q, batch);
+        PSK_CUDA_OK(cudaGetLastError());
+      }
+      return PSK_OK;
+    }
+    if (rc != PSK_E_UNSUPPORTED) return rc;
+  }
   const long long warps = static_cast<long long>(q.tiles_per_row) * batch;
   // small problems: fewer warps per CTA so that the chunks spread over more SMs
   int threads = g_warp_block;
@@ -613,6 +870,14 @@ int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStrea
   if (g_persistent_ctas_per_sm > 0 && blocks > 2 * resident && warps < 2147483647LL) {
     stage_warp_persistent_kernel<EQ, FLUX, REC, STRICT, R>
         <<<static_cast<unsigned>(resident), threads, 0, st>>>(q, static_cast<int>(warps));
+  } else if (g_chunks_per_warp == 2 && REC == PSK_REC_WENOJS53 && !STRICT) {
+    const long long groups = (warps + 1) / 2;
+    stage_warp_multi_kernel<EQ, FLUX, REC, STRICT, R, 2>
+        <<<static_cast<unsigned>((groups * 32 + threads - 1) / threads), threads, 0, st>>>(q, warps);
+  } else if (g_chunks_per_warp == 3 && REC == PSK_REC_WENOJS53 && !STRICT) {
+    const long long groups = (warps + 2) / 3;
+    stage_warp_multi_kernel<EQ, FLUX, REC, STRICT, R, 3>
+        <<<static_cast<unsigned>((groups * 32 + threads - 1) / threads), threads, 0, st>>>(q, warps);
   } else {
     stage_warp_kernel<EQ, FLUX, REC, STRICT, R>
         <<<static_cast<unsigned>(blocks), threads, 0, st>>>(q, warps);
@@ -849,6 +1114,15 @@ int psk_version(void) { return PSK_VERSION; }
 /* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
  * kernel (default), 1 = shared-memory tile kernel */
 int psk_set_stage_variant(int variant) {
+  if (variant >= 3000) {  // 3000 / 3001: specialised fast kernel off / on
+    g_use_fast = (variant - 3000) != 0;
+    return PSK_OK;
+  }
+  if (variant >= 2000) {  // 2000 + chunks per warp (1..3)
+    if (variant - 2000 < 1 || variant - 2000 > 3) return PSK_E_INVALID;
+    g_chunks_per_warp = variant - 2000;
+    return PSK_OK;
+  }
   if (variant >= 1000) {  // 1000 + persistent CTAs per SM (0 = one chunk per warp)
     g_persistent_ctas_per_sm = variant - 1000;
     return PSK_OK;

@@ -178,6 +178,39 @@ __device__ __forceinline__ Weno5Pair weno53_pair_sixths(double c, double tm2, do
   return out;
 }
 
+// Same quantities as weno53_pair_sixths with the candidate offsets written in terms of the
+// smoothness stencils' own linear forms (one instruction each, no doubled differences needed):
+//   s0 = 3 t(-1) - t(-2),  s2 = t(+1) - 3 t(0)
+//   right: q0 - c = 2 s0 - t(-1),  q1 - c = 2 t(0) + t(-1),   q2 - c = t(0) - s2
+//   left : q0 - c = -(s0 + t(-1)), q1 - c = -(2 t(-1) + t(0)), q2 - c = 2 s2 + t(0)
+__device__ __forceinline__ Weno5Pair weno53_pair_lean(double c, double tm2, double tm1, double tp0,
+                                                      double tp1, double pm1, double p0,
+                                                      double pp1) {
+  const double s0 = fma(3.0, tm1, -tm2);
+  const double s1 = tp0 + tm1;
+  const double s2 = fma(-3.0, tp0, tp1);
+  const double e0 = fma(s0, s0, pm1);
+  const double e1 = fma(s1, s1, p0);
+  const double e2 = fma(s2, s2, pp1);
+  const double e12 = e1 * e2, e02 = e0 * e2, e01 = e0 * e1;
+  const double w0 = e12 * e12, w1 = e02 * e02, w2 = e01 * e01;
+  const double a1 = 6.0 * w1, a2R = 3.0 * w2, a0L = 3.0 * w0;  // right (1,6,3), left (3,6,1)
+  const double rR0 = fma(2.0, s0, -tm1);
+  const double rR1 = fma(2.0, tp0, tm1);
+  const double rR2 = tp0 - s2;
+  const double nL0 = s0 + tm1;            // -(q0 - c), left
+  const double nL1 = fma(2.0, tm1, tp0);  // -(q1 - c), left
+  const double rL2 = fma(2.0, s2, tp0);
+  const double numR = fma(a2R, rR2, fma(a1, rR1, w0 * rR0));
+  const double numL = fma(w2, rL2, -fma(a1, nL1, a0L * nL0));
+  const double denR = (w0 + a1) + a2R;
+  const double denL = (a0L + a1) + w2;
+  Weno5Pair out;
+  out.ur = fma(numR, fast_rcp(denR), c);
+  out.ul = fma(numL, fast_rcp(denL), c);
+  return out;
+}
+
 // FAST pair straight from the five cell values (used where no sliding window exists)
 __device__ __forceinline__ Weno5Pair weno53_pair_fast_cells(double m2, double m1, double c, double p1,
                                                              double p2, double eps) {

@@ -138,6 +138,54 @@ class EnsembleSolver:
         self.t += float(nsteps) * dt
         return SolveResult(u=self.u, steps=nsteps, t=self.t)
 
+    def solve_fixed_dt_host(
+        self,
+        host_in: torch.Tensor,
+        host_out: torch.Tensor,
+        dt: float | torch.Tensor,
+        nsteps: int,
+        *,
+        groups: int = 8,
+        streams: int = 4,
+    ) -> SolveResult:
+        """Host-to-host call: ``host_in`` / ``host_out`` are (pinned) host tensors of shape
+        ``(batch, nx)``.  Rows are independent problems, so the batch is cut into ``groups`` row
+        blocks and each block runs upload -> ``nsteps`` steps -> download on its own stream: the
+        PCIe copies of one block overlap the arithmetic of the others (both copy engines busy)."""
+        if tuple(host_in.shape) != (self.batch, self.nx) or tuple(host_out.shape) != (self.batch, self.nx):
+            raise ValueError(f"expected host tensors of shape {(self.batch, self.nx)}")
+        dev = self.hp.device
+        if not isinstance(dt, torch.Tensor):
+            dt = torch.full((1,), float(dt), dtype=torch.float64, device=dev)
+        groups = max(1, min(groups, self.batch))
+        if not hasattr(self, "_streams") or len(self._streams) != streams:
+            self._streams = [torch.cuda.Stream(device=dev) for _ in range(streams)]
+        main = torch.cuda.current_stream(dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        per = (self.batch + groups - 1) // groups
+        hp = self.hp
+        for gi in range(groups):
+            b0, b1 = gi * per, min((gi + 1) * per, self.batch)
+            if b0 >= b1:
+                break
+            st = self._streams[gi % streams]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                u, k1, k2 = self.u[b0:b1], self.k1[b0:b1], self.k2[b0:b1]
+                dtg = dt if dt.numel() == 1 else dt[b0:b1]
+                u.copy_(host_in[b0:b1], non_blocking=True)
+                for _ in range(nsteps):
+                    hp.stage(1, u, u, k1, dtg)
+                    hp.stage(2, u, k1, k2, dtg)
+                    hp.stage(3, u, k2, u, dtg)
+                host_out[b0:b1].copy_(u, non_blocking=True)
+            self.launches += 3 * nsteps
+        for st in self._streams:
+            main.wait_stream(st)
+        self.t += float(nsteps) * dt
+        return SolveResult(u=self.u, steps=nsteps, t=self.t)
+
     def solve_adaptive(
         self,
         u0: torch.Tensor | np.ndarray | None,

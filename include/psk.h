@@ -106,6 +106,8 @@ int psk_last_cuda_error(void);
 /* A/B switch between the two implementations of the fused stage (same results):
  * 0 = warp-shuffle kernel (default), 1 = shared-memory tile kernel. */
 int psk_set_stage_variant(int variant);
+/* Same for the adjoint stage: 0 = warp-shuffle kernel where applicable (default), 1 = tile kernel. */
+int psk_set_adjoint_variant(int variant);
 
 /* apply_boundary(bc, grid, t, u) -> w            schemes.py:431-442, scalar.py BCs.
  * w may alias u. */

@@ -76,6 +76,7 @@ def _load() -> ct.CDLL:
         "psk_status_string": ([ct.c_int], ct.c_char_p),
         "psk_last_cuda_error": ([], ct.c_int),
         "psk_set_stage_variant": ([ct.c_int], ct.c_int),
+        "psk_set_adjoint_variant": ([ct.c_int], ct.c_int),
         "psk_apply_boundary": ([D, vp, vp, vp], ct.c_int),
         "psk_reconstruct": ([D, vp, vp, vp, vp], ct.c_int),
         "psk_numerical_flux": ([D, vp, vp, i64, vp, vp], ct.c_int),
@@ -96,10 +97,12 @@ def _load() -> ct.CDLL:
 
 
 _lib = _load()
+if os.environ.get("PSK_ADJOINT_VARIANT"):  # A/B measurements only
+    _lib.psk_set_adjoint_variant(int(os.environ["PSK_ADJOINT_VARIANT"]))
 if os.environ.get("PSK_STAGE_VARIANT"):  # A/B measurements only
     _lib.psk_set_stage_variant(int(os.environ["PSK_STAGE_VARIANT"]))
 EXPORTS = (
-    "psk_version", "psk_status_string", "psk_last_cuda_error", "psk_set_stage_variant", "psk_apply_boundary",
+    "psk_version", "psk_status_string", "psk_last_cuda_error", "psk_set_stage_variant", "psk_set_adjoint_variant", "psk_apply_boundary",
     "psk_reconstruct", "psk_numerical_flux", "psk_apply_operator", "psk_max_abs",
     "psk_ssprk33_stage", "psk_step_control", "psk_apply_operator_vjp",
     "psk_ssprk33_stage_adjoint",

@@ -217,6 +217,209 @@ adjoint_tile_kernel(const AdjParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// Warp form of the adjoint stage for WENO-JS5 (the transposed counterpart of
+// stage_warp_fast_kernel): one warp covers 128 consecutive cells, lanes 0 and 31 are halo lanes,
+// all neighbour traffic (3-cell halos of w, one cotangent value, one face value and the
+// two-cell scatter spill each way) goes through shuffles; no shared memory, no barriers.
+// Because a cell's cotangent reaches two cells further than its value did in the forward
+// sweep, the two edge lanes fetch one extra cell each.
+template <int EQ, int FLUX>
+__global__ void __launch_bounds__(256, 2)
+adjoint_warp_kernel(const AdjParams p, int chunks_per_row) {
+  constexpr int R = 4;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kOut = 30 * R;
+  const int lane = threadIdx.x & 31;
+  // chunk -1 covers the left ghost cells (interior coordinates -g .. -1)
+  const int chunk = static_cast<int>(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) - 1;
+  if (chunk >= chunks_per_row) return;
+  const int row = blockIdx.y + blockIdx.z * gridDim.y;
+  const int g = p.bc.g, n = p.bc.n, nx = p.bc.nx;
+  const int c0 = chunk * kOut - R + R * lane;  // interior coordinates; array index = g + c0
+  const int64_t base = static_cast<int64_t>(row) * p.ld;
+  const int64_t off = base + g + c0;
+  const bool inside = (c0 >= 0) && (c0 + R <= n);
+  const bool emit = (lane >= 1) && (lane <= 30);
+  const double *__restrict__ xrow = p.x + base;
+  const double *__restrict__ vrow = p.v + base;
+
+  // ---- forward state window and cotangent window
+  double w[R + 6], vc[R + 2];
+  if (inside) {
+    const double2 q0 = *reinterpret_cast<const double2 *>(p.x + off);
+    const double2 q1 = *reinterpret_cast<const double2 *>(p.x + off + 2);
+    w[3] = q0.x; w[4] = q0.y; w[5] = q1.x; w[6] = q1.y;
+    const double2 r0 = *reinterpret_cast<const double2 *>(p.v + off);
+    const double2 r1 = *reinterpret_cast<const double2 *>(p.v + off + 2);
+    vc[1] = r0.x; vc[2] = r0.y; vc[3] = r1.x; vc[4] = r1.y;
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = g + c0 + r;
+      w[3 + r] = load_w(p.bc, xrow, row, i);
+      vc[1 + r] = (i >= 0 && i < nx) ? vrow[i] : 0.0;
+    }
+  }
+  double extra = 0.0;  // lane 0: cell c0 - 1, lane 31: cell c0 + R
+  if (lane == 0) extra = load_w(p.bc, xrow, row, g + c0 - 1);
+  if (lane == 31) extra = load_w(p.bc, xrow, row, g + c0 + R);
+  w[0] = __shfl_up_sync(kFull, w[4], 1);
+  w[1] = __shfl_up_sync(kFull, w[5], 1);
+  w[2] = __shfl_up_sync(kFull, w[6], 1);
+  w[7] = __shfl_down_sync(kFull, w[3], 1);
+  w[8] = __shfl_down_sync(kFull, w[4], 1);
+  w[9] = __shfl_down_sync(kFull, w[5], 1);
+  if (lane == 0) w[2] = extra;
+  if (lane == 31) w[7] = extra;
+  vc[0] = __shfl_up_sync(kFull, vc[R], 1);
+  vc[R + 1] = __shfl_down_sync(kFull, vc[1], 1);
+
+  // ---- pass 1: face values
+  const double eps9 = p.eps * (1.0 / 9.0);
+  double t[R + 5], pq[R + 4];
+#pragma unroll
+  for (int k = 0; k < R + 5; ++k) t[k] = (1.0 / 6.0) * (w[k + 1] - w[k]);
+#pragma unroll
+  for (int k = 0; k < R + 4; ++k) {
+    const double dd = t[k + 1] - t[k];
+    pq[k] = fma((13.0 / 3.0) * dd, dd, eps9);
+  }
+  double ul[R], ur[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int m = r + 3;
+    const Weno5Pair o = weno53_pair_lean(w[m], t[m - 2], t[m - 1], t[m], t[m + 1], pq[m - 2], pq[m - 1], pq[m]);
+    ul[r] = o.ul;
+    ur[r] = o.ur;
+  }
+  const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
+  const double ul_right = __shfl_down_sync(kFull, ul[0], 1);
+
+  // ---- face-flux derivatives
+  const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.speed[row] : 0.0;
+  const bool has_nu = (FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) && (p.nu != nullptr);
+  double gur[R + 1], gul[R + 1], dir[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) dir[r] = 0.0;
+  double ga_part = 0.0;
+#pragma unroll
+  for (int f = 0; f <= R; ++f) {
+    const int k = g + c0 + f;  // array index of the face: between cells k - 1 and k
+    const bool valid = (k >= 1 && k <= nx - 1);
+    const double urj = (f == 0) ? ur_left : ur[f - 1];
+    const double ulp = (f == R) ? ul_right : ul[f];
+    double nu = 1.0, arj = 0.0, alp = 0.0, ck = 1.0, ckm1 = 1.0;
+    if (valid) {
+      if (has_nu) nu = p.nu[k - 1];
+      if (EQ != PSK_EQ_BURGERS) {
+        arj = p.vel_r[k - 1];
+        alp = p.vel_l[k];
+      }
+      if (EQ == PSK_EQ_ADVECTION) {
+        ck = p.vel[k];
+        ckm1 = p.vel[k - 1];
+      }
+    }
+    const double gF = valid ? (ck * vc[f + 1] - ckm1 * vc[f]) * p.invdx : 0.0;
+    const FaceGrad fg = face_flux_grad<EQ, FLUX>(urj, ulp, w[f + 2], w[f + 3], speed, nu, arj, alp);
+    gur[f] = gF * fg.d_ur;
+    gul[f] = gF * fg.d_ul;
+    if (f >= 1) dir[f - 1] = fma(gF, fg.d_wj, dir[f - 1]);
+    if (f <= R - 1) dir[f] = fma(gF, fg.d_wp, dir[f]);
+    if (FLUX == PSK_FLUX_LAX_FRIEDRICHS && f >= 1 && emit) ga_part = fma(gF, fg.d_speed, ga_part);
+  }
+
+  // ---- pass 2: through the reconstruction; 5-point scatter in registers
+  double accw[R + 4];
+#pragma unroll
+  for (int k = 0; k < R + 4; ++k) accw[k] = 0.0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int m = r + 3;
+    const Weno5Vjp d = weno53_pair_vjp_sixths(t[m - 2], t[m - 1], t[m], t[m + 1], pq[m - 2], pq[m - 1], pq[m],
+                                              gur[r + 1], gul[r]);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) accw[r + q] += d.d[q];
+  }
+  // spill: my contributions to the neighbour lanes' cells
+  const double from_right0 = __shfl_down_sync(kFull, accw[0], 1);  // next lane -> my cell R-2
+  const double from_right1 = __shfl_down_sync(kFull, accw[1], 1);  // next lane -> my cell R-1
+  const double from_left0 = __shfl_up_sync(kFull, accw[R + 2], 1);  // previous lane -> my cell 0
+  const double from_left1 = __shfl_up_sync(kFull, accw[R + 3], 1);  // previous lane -> my cell 1
+
+  if (emit) {
+    const double cgdt = p.c_g * (p.dt != nullptr ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 1.0);
+    double gi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) gi[r] = accw[r + 2] + dir[r];
+    gi[0] += from_left0;
+    gi[1] += from_left1;
+    gi[R - 2] += from_right0;
+    gi[R - 1] += from_right1;
+    double lin[R];
+    if (inside) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) lin[r] = p.c_v * vc[r + 1];
+      if (p.acc != nullptr) {
+        const double2 a0 = *reinterpret_cast<const double2 *>(p.acc + off);
+        const double2 a1 = *reinterpret_cast<const double2 *>(p.acc + off + 2);
+        lin[0] = fma(p.c_acc, a0.x, lin[0]); lin[1] = fma(p.c_acc, a0.y, lin[1]);
+        lin[2] = fma(p.c_acc, a1.x, lin[2]); lin[3] = fma(p.c_acc, a1.y, lin[3]);
+      }
+      if (p.acc2 != nullptr) {
+        const double2 a0 = *reinterpret_cast<const double2 *>(p.acc2 + off);
+        const double2 a1 = *reinterpret_cast<const double2 *>(p.acc2 + off + 2);
+        lin[0] = fma(p.c_acc2, a0.x, lin[0]); lin[1] = fma(p.c_acc2, a0.y, lin[1]);
+        lin[2] = fma(p.c_acc2, a1.x, lin[2]); lin[3] = fma(p.c_acc2, a1.y, lin[3]);
+      }
+      // inside => interior cells only (no ghost among them)
+      *reinterpret_cast<double2 *>(p.out + off) = make_double2(fma(cgdt, gi[0], lin[0]), fma(cgdt, gi[1], lin[1]));
+      *reinterpret_cast<double2 *>(p.out + off + 2) = make_double2(fma(cgdt, gi[2], lin[2]), fma(cgdt, gi[3], lin[3]));
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = g + c0 + r;
+        if (i < 0 || i >= nx) continue;
+        double l = p.c_v * vc[r + 1];
+        if (p.acc != nullptr) l = fma(p.c_acc, p.acc[base + i], l);
+        if (p.acc2 != nullptr) l = fma(p.c_acc2, p.acc2[base + i], l);
+        const bool ghost = (p.bc.bc != PSK_BC_NONE) && (i < g || i >= nx - g);
+        if (ghost) {
+          p.out[base + i] = l;
+          p.gspill[static_cast<int64_t>(row) * 2 * g + (i < g ? i : i - n)] = gi[r];
+        } else {
+          p.out[base + i] = fma(cgdt, gi[r], l);
+        }
+      }
+    }
+  }
+  if (FLUX == PSK_FLUX_LAX_FRIEDRICHS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ga_part += __shfl_xor_sync(kFull, ga_part, o);
+    if (lane == 0) atomicAdd(p.ga + row, ga_part);
+  }
+}
+
+template <int EQ, int FLUX>
+int launch_adjoint_warp(const AdjParams &p, int batch, cudaStream_t st) {
+  const int chunks = (p.bc.n + p.bc.g + 119) / 120;  // chunks 0 .. chunks-1 plus chunk -1
+  const int total = chunks + 1;
+  int wpc = 8, best_waste = 1 << 30;
+  for (int w = 8; w >= 4; --w) {
+    const int waste = ((total + w - 1) / w) * w - total;
+    if (waste < best_waste) { best_waste = waste; wpc = w; }
+  }
+  if (total < wpc) wpc = total;
+  const unsigned gx = static_cast<unsigned>((total + wpc - 1) / wpc);
+  const unsigned gy = batch < 65535 ? batch : 65535u;
+  if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
+  const dim3 grid(gx, gy, batch / gy);
+  adjoint_warp_kernel<EQ, FLUX><<<grid, wpc * 32, 0, st>>>(p, chunks);
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
 // transpose of apply_boundary + distribution of the Lax-Friedrichs speed cotangent; one CTA per row
 template <bool LF>
 __global__ void adjoint_boundary_kernel(const AdjParams p) {
@@ -263,10 +466,29 @@ __global__ void adjoint_boundary_kernel(const AdjParams p) {
   }
 }
 
+static int g_adjoint_variant = 0;  // 0: warp kernel where applicable, 1: tile kernel always
+
 template <int EQ, int FLUX, int REC>
 int launch_adjoint(const AdjParams &p0, int batch, cudaStream_t st) {
   constexpr int R = 4;
   AdjParams p = p0;
+  constexpr bool LFX = (FLUX == PSK_FLUX_LAX_FRIEDRICHS);
+  const bool aligned = (reinterpret_cast<uintptr_t>(p.x + p.bc.g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p.v + p.bc.g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(p.out + p.bc.g) % 16 == 0) &&
+                       (p.acc == nullptr || reinterpret_cast<uintptr_t>(p.acc + p.bc.g) % 16 == 0) &&
+                       (p.acc2 == nullptr || reinterpret_cast<uintptr_t>(p.acc2 + p.bc.g) % 16 == 0) &&
+                       (p.ld % 2 == 0);
+  if (REC == PSK_REC_WENOJS53 && g_adjoint_variant == 0 && aligned && p.bc.g == 3 &&
+      (batch <= 65535 || batch % 65535 == 0)) {
+    int rc = launch_adjoint_warp<EQ, FLUX>(p, batch, st);
+    if (rc != PSK_OK) return rc;
+    if (LFX || p.bc.bc == PSK_BC_PERIODIC || p.bc.bc == PSK_BC_NEUMANN) {
+      adjoint_boundary_kernel<LFX><<<batch, LFX ? 128 : 32, 0, st>>>(p);
+      PSK_CUDA_OK(cudaGetLastError());
+    }
+    return PSK_OK;
+  }
   const int nx = p.bc.nx;
   int threads = (nx + R - 1) / R + 2;
   threads = ((threads + 31) / 32) * 32;
@@ -357,6 +579,13 @@ static int run_adjoint(const psk_desc *d, const double *x, const double *v, cons
 using namespace psk;
 
 extern "C" {
+
+/* A/B switch for the adjoint stage: 0 = warp kernel where applicable (default), 1 = tile kernel */
+int psk_set_adjoint_variant(int variant) {
+  if (variant < 0 || variant > 1) return PSK_E_INVALID;
+  g_adjoint_variant = variant;
+  return PSK_OK;
+}
 
 int psk_apply_operator_vjp(const psk_desc *d, const double *u, const double *v, double *out,
                            double *work, psk_stream_t stream) {

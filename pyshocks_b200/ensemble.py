@@ -258,38 +258,62 @@ class AdjointEnsemble:
     stage launches.  ``p`` carries zero cotangents in the ghost cells and no boundary condition
     is imposed on it: ``backward`` returns the exact gradient of the discrete forward map."""
 
-    def __init__(self, solver: EnsembleSolver, *, nsteps: int, dt: float | torch.Tensor, segment: int | None = None) -> None:
+    def __init__(self, solver: EnsembleSolver, *, nsteps: int, dt: float | torch.Tensor,
+                 segment: int | None = None, memory_fraction: float = 0.7) -> None:
         self.s = solver
         self.nsteps = int(nsteps)
-        if segment is None:
-            segment = max(1, int(round(self.nsteps**0.5)))
-        self.segment = int(min(max(segment, 1), max(self.nsteps, 1)))
         dev = solver.hp.device
+        if segment is None:
+            segment = self._auto_segment(memory_fraction)
+        self.segment = int(min(max(segment, 1), max(self.nsteps, 1)))
         self.dt = dt if isinstance(dt, torch.Tensor) else torch.full((1,), float(dt), dtype=torch.float64, device=dev)
         self.nseg = (self.nsteps + self.segment - 1) // self.segment
         self.chk = solver.new_states(self.nseg + 1)  # states at steps 0, k, 2k, ...
-        self.ring = solver.new_states(self.segment)  # states inside the current segment
+        # states inside the current segment and the stages k1, k2 their recomputation produces
+        self.ring = solver.new_states(self.segment)
+        self.ring_k1 = solver.new_states(max(self.segment - 1, 0))
+        self.ring_k2 = solver.new_states(max(self.segment - 1, 0))
         self.lam2, self.lam1, self.p, self.pn = solver.new_states(4)
         self.launches = 0
 
-    def _advance(self, src: torch.Tensor, dst: torch.Tensor) -> None:
+    def _auto_segment(self, memory_fraction: float) -> int:
+        """Smallest segment length whose tape (nsteps / k checkpoints + 3 k ring arrays) fits in
+        ``memory_fraction`` of the free device memory: k = 1 keeps every state (no recompute)."""
+        s = self.s
+        state_bytes = s.batch * s.ld * 8
+        free, _ = torch.cuda.mem_get_info(s.hp.device)
+        budget = int(memory_fraction * free) // state_bytes - 8
+        for k in range(1, max(self.nsteps, 1) + 1):
+            if (self.nsteps + k - 1) // k + 1 + 3 * k <= budget:
+                return k
+        raise MemoryError("not enough device memory for the adjoint tape")
+
+    def _advance(self, src: torch.Tensor, dst: torch.Tensor, k1: torch.Tensor | None = None,
+                 k2: torch.Tensor | None = None) -> None:
         s, hp = self.s, self.s.hp
-        hp.stage(1, src, src, s.k1, self.dt)
-        hp.stage(2, src, s.k1, s.k2, self.dt)
-        hp.stage(3, src, s.k2, dst, self.dt)
+        k1 = s.k1 if k1 is None else k1
+        k2 = s.k2 if k2 is None else k2
+        hp.stage(1, src, src, k1, self.dt)
+        hp.stage(2, src, k1, k2, self.dt)
+        hp.stage(3, src, k2, dst, self.dt)
         self.launches += 3
 
     def forward(self, u0: torch.Tensor | np.ndarray | None = None) -> torch.Tensor:
-        """Advance ``nsteps`` steps, keeping every ``segment``-th state; returns ``u(T)`` (a view)."""
+        """Advance ``nsteps`` steps, keeping every ``segment``-th state; returns ``u(T)`` (a view of
+        the last checkpoint).  Stage 3 of a step that lands on a checkpoint writes straight into the
+        checkpoint buffer, so the tape costs no extra copies."""
         s = self.s
         if u0 is not None:
             s.load(u0)
         self.chk[0].copy_(s.u)
+        cur = self.chk[0]
+        scratch = [s.u, self.pn]  # ping-pong for the states between two checkpoints
         for m in range(self.nsteps):
-            self._advance(s.u, s.u)
-            if (m + 1) % self.segment == 0 or m + 1 == self.nsteps:
-                self.chk[(m + self.segment) // self.segment].copy_(s.u)
-        return s.u
+            on_chk = (m + 1) % self.segment == 0 or m + 1 == self.nsteps
+            dst = self.chk[(m + self.segment) // self.segment] if on_chk else scratch[m % 2]
+            self._advance(cur, dst)
+            cur = dst
+        return cur
 
     def backward(self, pT: torch.Tensor) -> torch.Tensor:
         """Reverse sweep: returns ``p(0) = (d u(T) / d u(0))^T pT`` (a view of an internal buffer)."""
@@ -299,19 +323,30 @@ class AdjointEnsemble:
         for seg in range(self.nseg - 1, -1, -1):
             m0 = seg * self.segment
             m1 = min(m0 + self.segment, self.nsteps)
-            # recompute the states u^{m0} .. u^{m1 - 1} of this segment
-            self.ring[0].copy_(self.chk[seg])
-            for j in range(1, m1 - m0):
-                self._advance(self.ring[j - 1], self.ring[j])
-            for j in range(m1 - m0 - 1, -1, -1):
-                u = self.ring[j]
-                hp.stage(1, u, u, s.k1, self.dt)
-                hp.stage(2, u, s.k1, s.k2, self.dt)
-                hp.stage_adjoint(s.k2, p, self.dt, 2.0 / 3.0, self.lam2)
-                hp.stage_adjoint(s.k1, self.lam2, self.dt, 1.0 / 4.0, self.lam1)
+            last = m1 - m0 - 1
+            # recompute the states u^{m0} .. u^{m1 - 1} of this segment; the recomputation also
+            # leaves the stages k1, k2 of every state but the last in the ring
+            if self.segment == 1:
+                ring0 = self.chk[seg]
+            else:
+                self.ring[0].copy_(self.chk[seg])
+                ring0 = self.ring[0]
+            for j in range(1, last + 1):
+                self._advance(ring0 if j == 1 else self.ring[j - 1], self.ring[j], self.ring_k1[j - 1], self.ring_k2[j - 1])
+            for j in range(last, -1, -1):
+                u = ring0 if j == 0 else self.ring[j]
+                if j == last:
+                    k1, k2 = s.k1, s.k2
+                    hp.stage(1, u, u, k1, self.dt)
+                    hp.stage(2, u, k1, k2, self.dt)
+                    self.launches += 2
+                else:
+                    k1, k2 = self.ring_k1[j], self.ring_k2[j]
+                hp.stage_adjoint(k2, p, self.dt, 2.0 / 3.0, self.lam2)
+                hp.stage_adjoint(k1, self.lam2, self.dt, 1.0 / 4.0, self.lam1)
                 hp.stage_adjoint(u, self.lam1, self.dt, 1.0, pn, acc=p, c_acc=1.0 / 3.0, acc2=self.lam2, c_acc2=3.0 / 4.0)
                 p, pn = pn, p
-                self.launches += 5 + (3 if hp.bc in ("periodic", "neumann") else 0)
+                self.launches += 3 + (3 if hp.bc in ("periodic", "neumann") else 0)
         self.p, self.pn = p, pn
         return p
 

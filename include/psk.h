@@ -173,6 +173,21 @@ int psk_step_control(int32_t batch, double theta, double cfl_scale, double tfina
                      const double *t, double *t_next, double *dt, uint8_t *active,
                      int32_t *nonfinite, psk_stream_t stream);
 
+/* The whole loop of timestepping.step (timestepping.py:128-152) with advance(SSPRK33) in ONE
+ * launch, one CTA per row, for rows that fit in shared memory (5 nx doubles <= 227 KB): the
+ * reference's own small-grid runs (examples/burgers.py) are launch-latency bound otherwise.
+ *   adaptive != 0: Burgers schemes, dt = theta * (cfl_scale / max|u_interior|), clamped to tfinal,
+ *                  + 1e-15, until t >= tfinal or max_steps;   adaptive == 0: max_steps steps of fixed_dt.
+ * Boundary data (d->ghost) must not depend on time.  u is advanced in place (all nx entries,
+ * ghost rows exactly like the reference).  t_out[batch], steps_out[batch] (negative: non-finite
+ * dt at step -1 - value); dt_hist: optional [batch][max_steps]; tape: optional
+ * [(max_steps + 1)][batch][ld] receiving the state before every step and the final state
+ * (the InMemoryCheckpoint contents, timestepping.py:130-131).  PSK_E_UNSUPPORTED if a row does
+ * not fit in shared memory. */
+int psk_solve_rows(const psk_desc *d, double *u, int adaptive, double theta, double cfl_scale,
+                   double tfinal, double fixed_dt, int max_steps, double *t_out,
+                   int32_t *steps_out, double *dt_hist, double *tape, psk_stream_t stream);
+
 /* out = J_L(u)^T v, the vector-Jacobian product of apply_operator w.r.t. u (all nx
  * rows, boundary condition included); what jax.vjp(apply_operator) returns, and the
  * building block of the reference's adjoint_step (timestepping.py:174, :205-206).

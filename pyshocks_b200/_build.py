@@ -13,13 +13,13 @@ import subprocess
 
 CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libpsk.so"
-SOURCES = ("psk_forward.cu", "psk_adjoint.cu")
+SOURCES = ("psk_forward.cu", "psk_adjoint.cu", "psk_solve.cu")
 HEADERS = ("psk_common.cuh", "psk_math.cuh", "../../include/psk.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "--shared", "-Xcompiler", "-fPIC,-fvisibility=default",
+    "-Xcompiler", "-fPIC,-fvisibility=default",
     "-Xptxas", "-v",
 ]
 
@@ -40,17 +40,36 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
-    """Compile every CUDA source into ``libpsk.so``; returns its path."""
+    """Compile every CUDA source (in parallel) and link them into ``libpsk.so``; returns its path."""
     if not force and not needs_build():
         return LIB
-    srcs = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
-    cmd = [nvcc(), *NVCC_FLAGS, "-o", str(LIB), *srcs]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    (CSRC / "build.log").write_text(" ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose or res.returncode != 0:
-        print(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError(f"nvcc failed with exit code {res.returncode}; see {CSRC / 'build.log'}")
+    from concurrent.futures import ThreadPoolExecutor
+
+    extra = os.environ.get("PSK_NVCC_EXTRA", "").split()
+    objdir = CSRC / "build"
+    objdir.mkdir(exist_ok=True)
+    srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
+
+    def compile_one(src: pathlib.Path) -> tuple[int, str, pathlib.Path]:
+        obj = objdir / (src.stem + ".o")
+        cmd = [nvcc(), *NVCC_FLAGS, *extra, "-c", "-o", str(obj), str(src)]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return res.returncode, " ".join(cmd) + "\n" + res.stdout + res.stderr, obj
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        results = list(pool.map(compile_one, srcs))
+    log = "".join(r[1] for r in results)
+    rc = max(r[0] for r in results)
+    if rc == 0:
+        cmd = [nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", str(LIB), *[str(r[2]) for r in results]]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        rc = res.returncode
+    (CSRC / "build.log").write_text(log)
+    if verbose or rc != 0:
+        print(log)
+    if rc != 0:
+        raise RuntimeError(f"nvcc failed with exit code {rc}; see {CSRC / 'build.log'}")
     return LIB
 
 

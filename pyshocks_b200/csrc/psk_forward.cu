@@ -463,6 +463,8 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
 // stage is a template parameter, the Rusanov speed max(|w_j|, |w_j+1|) is an integer max of the
 // bit patterns (2 ALU compares + 2 selects instead of an emulated fp64 max), and the candidate
 // offsets reuse the smoothness stencils' linear forms (weno53_pair_lean).
+static int g_fast_wpc_max = 8;  // largest CTA (in warps) the specialised kernel may use (tuning)
+
 struct FastParams {
   const double *uin;
   const double *u0;
@@ -487,8 +489,11 @@ __device__ __forceinline__ double umax_abs(double a, double b) {
   return __longlong_as_double(static_cast<long long>(x > y ? x : y));
 }
 
+#ifndef PSK_FAST_MIN_BLOCKS
+#define PSK_FAST_MIN_BLOCKS 4
+#endif
 template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PSK_FAST_MIN_BLOCKS)
 stage_warp_fast_kernel(const FastParams p) {
   constexpr int R = 4;
   constexpr unsigned kFull = 0xffffffffu;
@@ -630,7 +635,7 @@ int launch_fast_stage(const StageParams &p, int batch, cudaStream_t st) {
   q.chunks_per_row = (p.bc.n + 119) / 120;
   // warps per CTA: the divisor-friendly choice in 4..8 that wastes the fewest warps
   int wpc = 8, best_waste = 1 << 30;
-  for (int w = 8; w >= 4; --w) {
+  for (int w = g_fast_wpc_max; w >= 4; --w) {
     const int waste = ((q.chunks_per_row + w - 1) / w) * w - q.chunks_per_row;
     if (waste < best_waste) { best_waste = waste; wpc = w; }
   }
@@ -670,55 +675,6 @@ stage_warp_kernel(const StageParams p, long long total_warps) {
   double own[R], u0v[R];
   chunk_load<R>(p, c, own, u0v);
   chunk_compute<EQ, FLUX, REC, STRICT, R>(p, c, lane, own, u0v);
-}
-
-// CH consecutive chunks per warp: all loads are issued first, then the chunks are computed one
-// after the other, so the DRAM latency of chunk c + 1 hides behind the arithmetic of chunk c
-template <int EQ, int FLUX, int REC, bool STRICT, int R, int CH>
-__global__ void __launch_bounds__(256)
-stage_warp_multi_kernel(const StageParams p, long long total_warps) {
-  const int lane = threadIdx.x & 31;
-  const long long group = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long first = group * CH;
-  if (first >= total_warps) return;
-  ChunkRef c[CH];
-  double own[CH][R], u0v[CH][R];
-#pragma unroll
-  for (int k = 0; k < CH; ++k) {
-    const long long w = first + k < total_warps ? first + k : total_warps - 1;
-    c[k] = chunk_ref<R>(p, w, lane);
-    if (first + k >= total_warps) c[k].live = false;
-    chunk_load<R>(p, c[k], own[k], u0v[k]);
-  }
-#pragma unroll
-  for (int k = 0; k < CH; ++k)
-    if (c[k].live) chunk_compute<EQ, FLUX, REC, STRICT, R>(p, c[k], lane, own[k], u0v[k]);
-}
-
-// persistent warps: each warp walks over chunks warp_id, warp_id + stride, ... and issues the
-// loads of its NEXT chunk before it computes the current one (register double buffering),
-// so the DRAM latency is covered by a full chunk of arithmetic instead of by occupancy
-template <int EQ, int FLUX, int REC, bool STRICT, int R>
-__global__ void __launch_bounds__(256, 3)
-stage_warp_persistent_kernel(const StageParams p, int total_warps) {
-  const int lane = threadIdx.x & 31;
-  const int stride = static_cast<int>((gridDim.x * blockDim.x) >> 5);
-  int w = static_cast<int>((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (w >= total_warps) return;
-  double own[R], u0v[R];
-  chunk_load<R>(p, chunk_ref<R>(p, w, lane), own, u0v);
-  for (; w < total_warps; w += stride) {
-    double nown[R], nu0v[R];
-    const int wn = w + stride;
-    if (wn < total_warps) chunk_load<R>(p, chunk_ref<R>(p, wn, lane), nown, nu0v);
-    const ChunkRef cur = chunk_ref<R>(p, w, lane);
-    if (cur.live) chunk_compute<EQ, FLUX, REC, STRICT, R>(p, cur, lane, own, u0v);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      own[r] = nown[r];
-      u0v[r] = nu0v[r];
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -782,8 +738,6 @@ __global__ void ghost_rows_kernel(const StageParams p, int batch) {
 static int g_stage_variant = 0;
 static int g_warp_block = 256;  // threads per CTA of the warp kernel (tuning)
 static int g_use_fast = 1;  // specialised kernel for the hot configuration (stage_warp_fast_kernel)
-static int g_chunks_per_warp = 1;  // 1, 2 or 3 chunks per warp (stage_warp_multi_kernel)
-static int g_persistent_ctas_per_sm = 0;  // 0: one chunk per warp (default, faster as measured); >0: persistent warps with register prefetch
 
 template <int EQ, int FLUX, int REC, bool STRICT>
 int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStream_t st);
@@ -866,22 +820,8 @@ int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStrea
   while (threads > 32 && warps * 32 / threads < 2 * kSMs) threads >>= 1;
   const long long blocks = (warps * 32 + threads - 1) / threads;
   if (blocks > 2147483647LL) return PSK_E_INVALID;
-  const long long resident = static_cast<long long>(g_persistent_ctas_per_sm) * kSMs;
-  if (g_persistent_ctas_per_sm > 0 && blocks > 2 * resident && warps < 2147483647LL) {
-    stage_warp_persistent_kernel<EQ, FLUX, REC, STRICT, R>
-        <<<static_cast<unsigned>(resident), threads, 0, st>>>(q, static_cast<int>(warps));
-  } else if (g_chunks_per_warp == 2 && REC == PSK_REC_WENOJS53 && !STRICT) {
-    const long long groups = (warps + 1) / 2;
-    stage_warp_multi_kernel<EQ, FLUX, REC, STRICT, R, 2>
-        <<<static_cast<unsigned>((groups * 32 + threads - 1) / threads), threads, 0, st>>>(q, warps);
-  } else if (g_chunks_per_warp == 3 && REC == PSK_REC_WENOJS53 && !STRICT) {
-    const long long groups = (warps + 2) / 3;
-    stage_warp_multi_kernel<EQ, FLUX, REC, STRICT, R, 3>
-        <<<static_cast<unsigned>((groups * 32 + threads - 1) / threads), threads, 0, st>>>(q, warps);
-  } else {
-    stage_warp_kernel<EQ, FLUX, REC, STRICT, R>
-        <<<static_cast<unsigned>(blocks), threads, 0, st>>>(q, warps);
-  }
+  stage_warp_kernel<EQ, FLUX, REC, STRICT, R>
+      <<<static_cast<unsigned>(blocks), threads, 0, st>>>(q, warps);
   PSK_CUDA_OK(cudaGetLastError());
   if (ghost_rows) {
     const int total = batch * 2 * p.bc.g;
@@ -1114,17 +1054,13 @@ int psk_version(void) { return PSK_VERSION; }
 /* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
  * kernel (default), 1 = shared-memory tile kernel */
 int psk_set_stage_variant(int variant) {
+  if (variant >= 4000) {  // 4000 + max warps per CTA of the specialised kernel (4..8)
+    if (variant - 4000 < 4 || variant - 4000 > 8) return PSK_E_INVALID;
+    g_fast_wpc_max = variant - 4000;
+    return PSK_OK;
+  }
   if (variant >= 3000) {  // 3000 / 3001: specialised fast kernel off / on
     g_use_fast = (variant - 3000) != 0;
-    return PSK_OK;
-  }
-  if (variant >= 2000) {  // 2000 + chunks per warp (1..3)
-    if (variant - 2000 < 1 || variant - 2000 > 3) return PSK_E_INVALID;
-    g_chunks_per_warp = variant - 2000;
-    return PSK_OK;
-  }
-  if (variant >= 1000) {  // 1000 + persistent CTAs per SM (0 = one chunk per warp)
-    g_persistent_ctas_per_sm = variant - 1000;
     return PSK_OK;
   }
   if (variant >= 100) {  // 100 + threads per CTA of the warp kernel (32..256)
@@ -1268,3 +1204,4 @@ int psk_step_control(int32_t batch, double theta, double cfl_scale, double tfina
 }
 
 }  // extern "C"
+

@@ -283,6 +283,47 @@ class HotPath:
 
     # }}}
 
+    # {{{ whole solve in one launch (small rows)
+
+    def solve_rows(
+        self,
+        u: torch.Tensor,
+        *,
+        tfinal: float | None = None,
+        theta: float = 1.0,
+        cfl_scale: float | None = None,
+        fixed_dt: float | None = None,
+        max_steps: int,
+        record_dt: bool = False,
+        tape: bool = False,
+    ) -> dict:
+        """Advance ``u`` IN PLACE with the whole ``timestepping.step`` loop in one kernel launch
+        (one CTA per row, state in shared memory).  Adaptive (Burgers, ``cfl_scale`` given) or
+        ``max_steps`` steps of ``fixed_dt``.  Returns ``{"t", "steps", "dt", "tape"}`` (device tensors)."""
+        batch, ld = self._state(u)
+        adaptive = fixed_dt is None
+        if adaptive and (tfinal is None or cfl_scale is None):
+            raise ValueError("adaptive solves need tfinal and cfl_scale")
+        dev = u.device
+        t_out = torch.zeros(batch, dtype=torch.float64, device=dev)
+        steps = torch.zeros(batch, dtype=torch.int32, device=dev)
+        hist = torch.zeros((batch, max_steps), dtype=torch.float64, device=dev) if record_dt else None
+        tp = None
+        if tape:
+            tp = torch.zeros((max_steps + 1, batch, ld), dtype=torch.float64, device=dev)
+        d = self.desc(batch, ld)
+        L.check(
+            "psk_solve_rows",
+            L.lib().psk_solve_rows(
+                ct.byref(d), L.ptr(u), int(adaptive), float(theta), float(cfl_scale or 0.0),
+                float(tfinal if tfinal is not None else 0.0), float(fixed_dt or 0.0), int(max_steps),
+                L.ptr(t_out), L.raw_ptr(steps), L.ptr(hist), L.ptr(tp), L.stream_ptr(),
+            ),
+        )
+        return {"t": t_out, "steps": steps, "dt": hist, "tape": None if tp is None else tp[:, :, : self.nx]}
+
+    # }}}
+
     # {{{ fused SSPRK33
 
     def stage(

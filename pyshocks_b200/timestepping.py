@@ -16,7 +16,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 from functools import singledispatch
-from typing import Any, Callable, Iterator
+from typing import Any, Callable, ClassVar, Iterator
 
 import torch
 
@@ -280,3 +280,106 @@ def _advance_ssprk33(stepper: SSPRK33, dt: ScalarLike, t: ScalarLike, u: Array) 
     if ghost_data(bound.bc, bound.grid, t) is not None:
         ghosts = [ghost_data(bound.bc, bound.grid, tt) for tt in (t, t + dt, t + 0.5 * dt)]
     return hp.ssprk33_step(u, _as_dt(dt, u), ghosts=ghosts, ghost_rows=True)
+
+
+# {{{ RK44 / CKRK45 (timestepping.py:325-405): generic steppers -- each RHS is one fused
+# apply_operator launch (boundary fill + WENO + flux + flux difference), the stage combines are
+# the reference's own array expressions
+
+
+@dataclass(frozen=True)
+class RK44(Stepper):
+    """The classic fourth-order Runge-Kutta method with 4 stages (timestepping.py:328-343)."""
+
+
+@advance.register(RK44)
+def _advance_rk44(stepper: RK44, dt: ScalarLike, t: ScalarLike, u: Array) -> Array:
+    fn = stepper.source
+    k1 = dt * fn(t, u)
+    k2 = dt * fn(t + dt / 2, u + k1 / 2)
+    k3 = dt * fn(t + dt / 2, u + k2 / 2)
+    k4 = dt * fn(t + dt, u + k3)
+    return u + (k1 + 2 * k2 + 2 * k3 + k4) / 6
+
+
+@dataclass(frozen=True)
+class CKRK45(Stepper):
+    """Low-storage five-stage fourth-order method of Carpenter and Kennedy (timestepping.py:352-405)."""
+
+    a: ClassVar[tuple[float, ...]] = (
+        0.0,
+        -567301805773 / 1357537059087,
+        -2404267990393 / 2016746695238,
+        -3550918686646 / 2091501179385,
+        -1275806237668 / 842570457699,
+    )
+    b: ClassVar[tuple[float, ...]] = (
+        1432997174477 / 9575080441755,
+        5161836677717 / 13612068292357,
+        1720146321549 / 2090206949498,
+        3134564353537 / 4481467310338,
+        2277821191437 / 14882151754819,
+    )
+    c: ClassVar[tuple[float, ...]] = (
+        0.0,
+        1432997174477 / 9575080441755,
+        2526269341429 / 6820363962896,
+        2006345519317 / 3224310063776,
+        2802321613138 / 2924317926251,
+    )
+
+
+@advance.register(CKRK45)
+def _advance_ckrk45(stepper: CKRK45, dt: ScalarLike, t: ScalarLike, u: Array) -> Array:
+    fn = stepper.source
+    p = k = u
+    for i in range(len(stepper.a)):
+        k = stepper.a[i] * k + dt * fn(t + stepper.c[i] * dt, p)
+        p = p + stepper.b[i] * k
+    return p
+
+
+# }}}
+
+
+def solve(
+    scheme: Any,
+    grid: Any,
+    bc: Any,
+    u0: Array,
+    *,
+    tfinal: float,
+    theta: float = 1.0,
+    maxit: int = 1 << 14,
+    checkpoint: bool = False,
+) -> dict:
+    """``for event in step(SSPRK33(...), u0, tfinal=tfinal): pass`` as ONE kernel launch
+    (``psk_solve_rows``) for grids that fit in shared memory and boundary data that do not depend on
+    time: the CFL reduction, the dt clamp and the three fused stages of every step run on the
+    device.  Returns ``{"u", "t", "iteration", "dt", "states"}``; ``dt`` is the per-step history and
+    ``states`` (with ``checkpoint=True``) what an ``InMemoryCheckpoint`` would hold.
+
+    Not in the reference (its loop is a Python generator with a host read of dt per step,
+    timestepping.py:139-150); results are identical to the step-by-step path in STRICT mode."""
+    from .binding import hotpath_for
+    from .burgers.schemes import BurgersScheme, Rusanov
+
+    hp = hotpath_for(scheme, grid, bc, 0.0)
+    u = u0.clone()
+    if isinstance(scheme, BurgersScheme):
+        alpha = scheme.alpha if isinstance(scheme, Rusanov) else 1.0
+        cfl_scale = 0.5 * grid.h ** (2 - alpha) if isinstance(scheme, Rusanov) else 0.5 * grid.h
+        out = hp.solve_rows(u, tfinal=tfinal, theta=theta, cfl_scale=cfl_scale, max_steps=maxit,
+                            record_dt=True, tape=checkpoint)
+    else:
+        from .schemes import predict_timestep
+
+        dt = theta * float(predict_timestep(scheme, grid, bc, 0.0, u))
+        nsteps, dt = predict_maxit_from_timestep(tfinal, dt)
+        out = hp.solve_rows(u, fixed_dt=dt, max_steps=nsteps, record_dt=True, tape=checkpoint)
+    steps = out["steps"]
+    if bool((steps < 0).any()):
+        raise ValueError("Time step is not finite.")  # timestepping.py:144-145
+    nmax = int(steps.max())
+    return {"u": u, "t": out["t"], "iteration": steps, "dt": out["dt"][..., :nmax],
+            "states": None if out["tape"] is None else out["tape"][: nmax + 1]}

@@ -20,11 +20,7 @@ def run(batch, n, steps, math="fast"):
     print(json.dumps({"batch": batch, "n": n, "steps": steps, "math": math, "ms_per_step": ms / steps, "cell_updates_per_s": cu, "hbm_frac_64B": cu * 64 / 6547.2e9}))
 
 from pyshocks_b200 import _lib
-_lib.lib().psk_set_stage_variant(2001)
-for fast in (1, 0):
-    _lib.lib().psk_set_stage_variant(3000 + fast)
-    print("specialised fast kernel", fast)
+for wmax in (8, 6, 5, 4):
+    _lib.lib().psk_set_stage_variant(4000 + wmax)
+    print("max warps per CTA", wmax)
     run(65536, 4096, 20)
-    run(1024, 4096, 20)
-    run(1, 1 << 26, 20)
-    run(64, 256, 20)

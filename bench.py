@@ -148,6 +148,29 @@ def run_reference(args: argparse.Namespace) -> None:
 # }}}
 
 
+def measure_fp64_peak(dev) -> dict:
+    """DFMA throughput of this GPU (MEASURED_PEAKS.json has no fp64 figure): psk_dfma_probe, best of 5."""
+    import torch
+
+    from pyshocks_b200 import _lib as L
+
+    ctas, iters = 148 * 16, 2048
+    out = torch.empty(ctas * 256, dtype=torch.float64, device=dev)
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check("psk_dfma_probe", L.lib().psk_dfma_probe(L.ptr(out), ctas, iters, L.stream_ptr()))
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2.0 * 64 * iters * ctas * 256 / (e0.elapsed_time(e1) * 1e-3))
+    return {"tflops": best / 1e12, "how": "psk_dfma_probe: 16 independent DFMA chains per thread, 2368 CTAs x 256 threads, best of 6"}
+
+
+# algorithmic flops per cell-update (SURVEY.md 8d: 152 per cell-stage, divisions counted as 1)
+ALGO_FLOPS_PER_CELL_UPDATE = 456.0
+
+
 def workload_config(n_gpus: int) -> dict:
     return {
         "workload": f"batched Burgers ensemble B={BATCH} x N={N_CELLS} cells per GPU, fp64, WENO-JS5 + Rusanov(LLF) "
@@ -305,15 +328,23 @@ def run_ours(args: argparse.Namespace) -> None:
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
             traffic = json.loads(tf.read_text()).get("stage_kernel_dram_bytes_per_launch")
+        fp64 = measure_fp64_peak(dev)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world) | {"batch_per_gpu": batch, "finite": finite},
+            "roofline_fp64": {
+                "bound": "fp64", "achieved": per_gpu * ALGO_FLOPS_PER_CELL_UPDATE / 1e12, "peak": fp64["tflops"],
+                "unit": "TFLOP/s", "frac": per_gpu * ALGO_FLOPS_PER_CELL_UPDATE / 1e12 / fp64["tflops"],
+                "peak_source": fp64["how"],
+                "note": "456 algorithmic flop per cell-update (SURVEY.md 8d); the kernel executes ~62 FP64 "
+                        "instructions per cell-stage (DFMA counts 2 flop): ncu shows the FP64 pipe 80 % busy",
+            },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "psk::stage_warp_kernel (3 launches per step; 64 algorithmic bytes per cell-update)",
+                "kernel": "psk::stage_warp_fast_kernel (3 launches per step; 64 algorithmic bytes per cell-update)",
                 "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_UPDATE / 3 * batch * N_CELLS,
                 "avg_launch_ms": ms_total / (3 * args.steps),
             },

@@ -188,6 +188,10 @@ int psk_solve_rows(const psk_desc *d, double *u, int adaptive, double theta, dou
                    double tfinal, double fixed_dt, int max_steps, double *t_out,
                    int32_t *steps_out, double *dt_hist, double *tape, psk_stream_t stream);
 
+/* FP64 peak probe for the roofline (not part of the reference-facing surface): ctas x 256 threads,
+ * each executing iters x 64 DFMAs in 16 independent chains; out: ctas x 256 doubles. */
+int psk_dfma_probe(double *out, int ctas, int iters, psk_stream_t stream);
+
 /* out = J_L(u)^T v, the vector-Jacobian product of apply_operator w.r.t. u (all nx
  * rows, boundary condition included); what jax.vjp(apply_operator) returns, and the
  * building block of the reference's adjoint_step (timestepping.py:174, :205-206).

@@ -217,3 +217,35 @@ extern "C" int psk_solve_rows(const psk_desc *d, double *u, int adaptive, double
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return d->math == PSK_MATH_STRICT ? psk::solve_scheme<true>(d, p, st) : psk::solve_scheme<false>(d, p, st);
 }
+
+// ===========================================================================
+// FP64 peak probe for the roofline: 16 independent DFMA chains per thread, enough CTAs to fill
+// every SM.  MEASURED_PEAKS.json has no fp64 figure, bench.py measures it with this kernel.
+namespace psk {
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double *out, int iters, double a, double b) {
+  double x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = threadIdx.x * 1e-3 + k;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[k] = fma(x[k], a, b);
+    }
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc += x[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+}  // namespace psk
+
+/* Launch the DFMA probe: ctas * 256 threads, each doing iters * 64 DFMAs (16 independent chains); out needs ctas * 256
+ * doubles.  The caller times it (CUDA events) and computes 2 * 64 * iters * threads / seconds. */
+extern "C" int psk_dfma_probe(double *out, int ctas, int iters, psk_stream_t stream) {
+  if (out == nullptr || ctas <= 0 || iters <= 0) return PSK_E_INVALID;
+  psk::dfma_probe_kernel<<<ctas, 256, 0, static_cast<cudaStream_t>(stream)>>>(out, iters, 0.999999, 1.0e-6);
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}

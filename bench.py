@@ -371,7 +371,7 @@ def run_slab(args: argparse.Namespace) -> None:
     import torch
     import torch.distributed as dist
 
-    from pyshocks_b200.distributed import DistRing, SlabSolver
+    from pyshocks_b200.distributed import DistRing, PeerSlabSolver, SlabSolver
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -384,8 +384,14 @@ def run_slab(args: argparse.Namespace) -> None:
         dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
     n_global = args.cells if args.cells else (1 << 30)
     h = (DOMAIN[1] - DOMAIN[0]) / n_global
-    ring = DistRing()
-    slab = SlabSolver(n_global=n_global, ring=ring, dx=h, device=dev)
+    if args.transport == "nccl":
+        slab = SlabSolver(n_global=n_global, ring=DistRing(), dx=h, device=dev)
+        launches_per_step = 3
+    else:
+        slab = PeerSlabSolver(n_global=n_global, rank=rank, world=world, dx=h, device=dev,
+                              overlap=(args.transport == "p2p"))
+        slab.connect()
+        launches_per_step = 15 if slab.split else 9  # per stage: wait, (2 edge +) 1 stage kernel, push
     i = torch.arange(slab.first, slab.first + slab.n_local, device=dev, dtype=torch.float64)
     slab.load_interior(0.5 + torch.sin(2.0 * np.pi * (i + 0.5) / n_global))
     del i
@@ -406,6 +412,9 @@ def run_slab(args: argparse.Namespace) -> None:
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    if args.transport != "nccl":
+        slab.check()  # a ghost-cell wait that timed out would have produced garbage silently
+    finite = bool(torch.isfinite(slab.interior()).all().item())
     if rank == 0:
         value = n_global * args.steps / (float(ms) * 1e-3)
         peak, peak_src = measured_peaks()
@@ -416,11 +425,17 @@ def run_slab(args: argparse.Namespace) -> None:
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"single periodic Burgers grid N={n_global} cells, slab-decomposed over {world} rank(s), "
                                    "ring halo exchange 3 cells/side/stage (BASELINE.json configs[3])",
-                       "cells_per_gpu": slab.n_local, "halo_exchanges_per_step": 3},
+                       "cells_per_gpu": slab.n_local, "halo_exchanges_per_step": 3, "finite": finite,
+                       "transport": {"p2p": "NVLink peer stores + epoch flags, slab edges on a high-priority stream "
+                                            "overlapped with the interior",
+                                     "p2p-serial": "NVLink peer stores + epoch flags, no overlap",
+                                     "nccl": "NCCL send/recv pairs per stage"}[args.transport]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": launches_per_step * args.steps,
         }), flush=True)
+    if args.transport != "nccl":
+        slab.close()
     dist.destroy_process_group()
 
 
@@ -499,6 +514,8 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", choices=("ensemble", "slab", "adjoint"), default="ensemble",
                     help="ensemble = the headline config (default); slab / adjoint = BASELINE configs 4 and 5")
+    ap.add_argument("--transport", choices=("p2p", "p2p-serial", "nccl"), default="p2p",
+                    help="ghost-cell exchange of the slab workload")
     ap.add_argument("--cells", type=int, default=0, help="override the cell count of the slab / adjoint workloads")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

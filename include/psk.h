@@ -214,6 +214,37 @@ int psk_ssprk33_stage_adjoint(const psk_desc *d, const double *x, const double *
                               double c_acc2, double *work, double *out,
                               psk_stream_t stream);
 
+/* ---- slab decomposition of one large grid over several GPUs (BASELINE.json configs[3]) ----
+ * The reference is single-device (pyshocks/__init__.py:66); the only reference notion involved is
+ * the ghost-cell layout of grid.py:83-117: a slab array is [g | n_local | g] and its ghost cells
+ * are the neighbours' edge cells.  One process per GPU; the neighbours' arrays are mapped
+ * through CUDA IPC and written directly over NVLink. */
+#define PSK_IPC_HANDLE_BYTES 64
+
+/* cudaMalloc + zero-fill of `bytes` of peer-visible device memory on the current device;
+ * `handle` receives PSK_IPC_HANDLE_BYTES bytes to pass to the other processes.  Synchronous. */
+int psk_p2p_alloc(uint64_t bytes, void **ptr, unsigned char *handle);
+int psk_p2p_free(void *ptr);
+/* Map another process' psk_p2p_alloc allocation into this process (peer access is enabled
+ * lazily); *ptr is its base address here.  Synchronous. */
+int psk_p2p_open(const unsigned char *handle, void **ptr);
+int psk_p2p_close(void *ptr);
+
+/* Ghost-cell push: copy `count` doubles src_lo -> dst_lo (my first interior cells into the LEFT
+ * neighbour's right ghost slots) and src_hi -> dst_hi (my last interior cells into the RIGHT
+ * neighbour's left ghost slots), order the stores system-wide, then store `epoch` into
+ * *flag_lo and *flag_hi (flags living in the neighbours' memory).  Any of the two sides may be
+ * NULL.  One tiny launch. */
+int psk_halo_push(const double *src_lo, double *dst_lo, const double *src_hi, double *dst_hi,
+                  int32_t count, int64_t *flag_lo, int64_t *flag_hi, int64_t epoch,
+                  psk_stream_t stream);
+
+/* Stream-ordered wait: the launch completes once *flag_a >= epoch and *flag_b >= epoch (local
+ * flags written by the neighbours' psk_halo_push; either may be NULL), or after timeout_ns,
+ * in which case *timed_out is set to 1 (never a hang). */
+int psk_halo_wait(const int64_t *flag_a, const int64_t *flag_b, int64_t epoch, int64_t timeout_ns,
+                  int32_t *timed_out, psk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ import subprocess
 
 CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libpsk.so"
-SOURCES = ("psk_forward.cu", "psk_adjoint.cu", "psk_solve.cu")
+SOURCES = ("psk_forward.cu", "psk_adjoint.cu", "psk_solve.cu", "psk_p2p.cu")
 HEADERS = ("psk_common.cuh", "psk_math.cuh", "../../include/psk.h")
 
 NVCC_FLAGS = [

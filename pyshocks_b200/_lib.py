@@ -90,6 +90,12 @@ def _load() -> ct.CDLL:
         "psk_ssprk33_stage_adjoint": (
             [D, vp, vp, vp, i64, f64, vp, f64, vp, f64, vp, vp, vp], ct.c_int
         ),
+        "psk_p2p_alloc": ([ct.c_uint64, ct.POINTER(vp), ct.c_char_p], ct.c_int),
+        "psk_p2p_free": ([vp], ct.c_int),
+        "psk_p2p_open": ([ct.c_char_p, ct.POINTER(vp)], ct.c_int),
+        "psk_p2p_close": ([vp], ct.c_int),
+        "psk_halo_push": ([vp, vp, vp, vp, i32, vp, vp, i64, vp], ct.c_int),
+        "psk_halo_wait": ([vp, vp, i64, i64, vp, vp], ct.c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here = the library is stale: rebuild it
@@ -107,7 +113,8 @@ EXPORTS = (
     "psk_version", "psk_status_string", "psk_last_cuda_error", "psk_set_stage_variant", "psk_set_adjoint_variant", "psk_apply_boundary",
     "psk_reconstruct", "psk_numerical_flux", "psk_apply_operator", "psk_max_abs",
     "psk_ssprk33_stage", "psk_step_control", "psk_solve_rows", "psk_dfma_probe", "psk_apply_operator_vjp",
-    "psk_ssprk33_stage_adjoint",
+    "psk_ssprk33_stage_adjoint", "psk_p2p_alloc", "psk_p2p_free", "psk_p2p_open", "psk_p2p_close",
+    "psk_halo_push", "psk_halo_wait",
 )
 
 

@@ -30,6 +30,7 @@
 
 #include "psk_common.cuh"
 #include "psk_math.cuh"
+#include "psk_adjoint_math.cuh"
 
 namespace psk {
 
@@ -53,6 +54,7 @@ struct AdjParams {
   int64_t ld;
   double invdx, eps;
   int tiles_per_row;
+  int prescaled;  // gspill already carries the factor c_g dt (lean kernel)
 };
 
 constexpr int kAdjHalo = 3;
@@ -401,6 +403,222 @@ adjoint_warp_kernel(const AdjParams p, int chunks_per_row) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Lean warp form of the adjoint stage for the hot configuration (Burgers, Rusanov, WENO-JS5,
+// nu = 1, aligned rows) -- the transposed counterpart of stage_warp_fast_kernel.  Same data
+// layout as adjoint_warp_kernel (one warp = 128 consecutive cells, lanes 0 and 31 are halo
+// lanes, everything between lanes travels by shuffle), different arithmetic and schedule:
+//   * psk_adjoint_math.cuh: the derivative of the PRODUCT form of the weights (no 1 / e_k),
+//     accumulated on the seven first differences a lane touches; the conversion to cell
+//     cotangents is one subtraction per cell at the end;
+//   * every cotangent is pre-scaled by c_g dt / dx, so the epilogue is lin + gi;
+//   * all global loads (x, v, acc, acc2) are issued at the top and lin is formed at once;
+//   * the forward pass of a cell (Weno5State) is kept and reused by its VJP instead of being
+//     recomputed: cells are processed in the order fwd(3), fwd(0) | exchange | face(0), fwd(1),
+//     face(1), vjp(0), fwd(2), face(2), vjp(1), face(3), vjp(2), face(4), vjp(3), so at most three
+//     states are alive;
+//   * the Rusanov speed max(|w_j|, |w_j+1|), its arg-max and the signs are integer work on the
+//     bit patterns (ALU pipe), not FP64 compares;
+//   * CTAs of 4 warps: 4-5 CTAs per SM drift apart, so the load phase of one hides behind the
+//     arithmetic of the others.
+struct LeanFace {
+  double gR;  // cotangent of the right value of the left cell (j)
+  double gL;  // cotangent of the left value of the right cell (p)
+  double dj, dp;  // direct terms on w_j, w_p (through the speed)
+};
+
+// +-1, +-1/2 or 0 as a double: sign(w) times `half_exp` (0x3FF00000 -> 1, 0x3FE00000 -> 1/2, 0 -> 0)
+__device__ __forceinline__ double signed_unit(double w, unsigned hi_bits) {
+  const unsigned sign = static_cast<unsigned>(__double2hiint(w)) & 0x80000000u;
+  return __hiloint2double(static_cast<int>(sign | hi_bits), 0);
+}
+
+// hG = (1/2) c_g dt (v_p - v_j) / dx ;  Phi = 1/4 (urj^2 + ulp^2) - 1/2 a (ulp - urj)
+__device__ __forceinline__ LeanFace lean_face(double hG, double urj, double ulp, double wj, double wp) {
+  const unsigned long long bj = static_cast<unsigned long long>(__double_as_longlong(wj)) & 0x7fffffffffffffffull;
+  const unsigned long long bp = static_cast<unsigned long long>(__double_as_longlong(wp)) & 0x7fffffffffffffffull;
+  const double a = __longlong_as_double(static_cast<long long>(bj > bp ? bj : bp));
+  LeanFace o;
+  o.gR = hG * (urj + a);
+  o.gL = hG * (ulp - a);
+  const double da = hG * (urj - ulp);
+  // jnp.maximum: the larger argument takes the gradient, ties split 1/2 - 1/2; abs'(0) = 0
+  const unsigned ej = bj > bp ? 0x3FF00000u : ((bj == bp && bj != 0ull) ? 0x3FE00000u : 0u);
+  const unsigned ep = bp > bj ? 0x3FF00000u : ((bj == bp && bp != 0ull) ? 0x3FE00000u : 0u);
+  o.dj = da * signed_unit(wj, ej);
+  o.dp = da * signed_unit(wp, ep);
+  return o;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
+  constexpr int R = 4;
+  constexpr unsigned kFull = 0xffffffffu;
+  constexpr int kOut = 30 * R;
+  const int lane = threadIdx.x & 31;
+  const int chunk = static_cast<int>(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) - 1;
+  if (chunk >= chunks_per_row) return;
+  const int row = blockIdx.y + blockIdx.z * gridDim.y;
+  const int g = p.bc.g, n = p.bc.n, nx = p.bc.nx;
+  const int c0 = chunk * kOut - R + R * lane;  // interior coordinates; array index = g + c0
+  const int64_t base = static_cast<int64_t>(row) * p.ld;
+  const int64_t off = base + g + c0;
+  const bool inside = (c0 >= 0) && (c0 + R <= n);
+  const double *__restrict__ xrow = p.x + base;
+  const double *__restrict__ vrow = p.v + base;
+
+  // ---- all loads first: state window, cotangent window, linear terms
+  double w[R + 6], vc[R + 2], lin[R];
+  if (inside) {
+    const double2 q0 = *reinterpret_cast<const double2 *>(p.x + off);
+    const double2 q1 = *reinterpret_cast<const double2 *>(p.x + off + 2);
+    const double2 r0 = *reinterpret_cast<const double2 *>(p.v + off);
+    const double2 r1 = *reinterpret_cast<const double2 *>(p.v + off + 2);
+    double2 a0 = make_double2(0.0, 0.0), a1 = a0, b0 = a0, b1 = a0;
+    if (p.acc != nullptr) {
+      a0 = *reinterpret_cast<const double2 *>(p.acc + off);
+      a1 = *reinterpret_cast<const double2 *>(p.acc + off + 2);
+    }
+    if (p.acc2 != nullptr) {
+      b0 = *reinterpret_cast<const double2 *>(p.acc2 + off);
+      b1 = *reinterpret_cast<const double2 *>(p.acc2 + off + 2);
+    }
+    w[3] = q0.x; w[4] = q0.y; w[5] = q1.x; w[6] = q1.y;
+    vc[1] = r0.x; vc[2] = r0.y; vc[3] = r1.x; vc[4] = r1.y;
+    lin[0] = fma(p.c_acc2, b0.x, fma(p.c_acc, a0.x, p.c_v * r0.x));
+    lin[1] = fma(p.c_acc2, b0.y, fma(p.c_acc, a0.y, p.c_v * r0.y));
+    lin[2] = fma(p.c_acc2, b1.x, fma(p.c_acc, a1.x, p.c_v * r1.x));
+    lin[3] = fma(p.c_acc2, b1.y, fma(p.c_acc, a1.y, p.c_v * r1.y));
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = g + c0 + r;
+      const bool in_row = (i >= 0 && i < nx);
+      w[3 + r] = load_w(p.bc, xrow, row, i);
+      vc[1 + r] = in_row ? vrow[i] : 0.0;
+      double l = p.c_v * vc[1 + r];
+      if (in_row && p.acc != nullptr) l = fma(p.c_acc, p.acc[base + i], l);
+      if (in_row && p.acc2 != nullptr) l = fma(p.c_acc2, p.acc2[base + i], l);
+      lin[r] = l;
+    }
+  }
+  double extra = 0.0;  // lane 0: cell c0 - 1, lane 31: cell c0 + R
+  if (lane == 0) extra = load_w(p.bc, xrow, row, g + c0 - 1);
+  if (lane == 31) extra = load_w(p.bc, xrow, row, g + c0 + R);
+  const double cgdt = p.c_g * (p.dt != nullptr ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 1.0);
+
+  w[1] = __shfl_up_sync(kFull, w[5], 1);
+  w[2] = __shfl_up_sync(kFull, w[6], 1);
+  w[7] = __shfl_down_sync(kFull, w[3], 1);
+  w[8] = __shfl_down_sync(kFull, w[4], 1);
+  if (lane == 0) w[2] = extra;
+  if (lane == 31) w[7] = extra;
+  vc[0] = __shfl_up_sync(kFull, vc[R], 1);
+  vc[R + 1] = __shfl_down_sync(kFull, vc[1], 1);
+
+  // ---- (1/2) c_g dt (v_k - v_{k-1}) / dx for the faces of the lane; zero at the array ends
+  const double hs = 0.5 * cgdt * p.invdx;
+  double hG[R + 1];
+#pragma unroll
+  for (int f = 0; f <= R; ++f) {
+    const int k = g + c0 + f;  // array index of the face: between cells k - 1 and k
+    hG[f] = (k >= 1 && k <= nx - 1) ? (vc[f + 1] - vc[f]) * hs : 0.0;
+  }
+
+  // ---- first differences in sixths (t[k]: cells k, k+1 of the window) and (13/3) dd^2 + eps/9
+  const double eps9 = p.eps * (1.0 / 9.0);
+  double t[R + 4], pq[R + 3];  // used: t[1..7], pq[1..6]
+#pragma unroll
+  for (int k = 1; k <= R + 3; ++k) t[k] = (1.0 / 6.0) * (w[k + 1] - w[k]);
+#pragma unroll
+  for (int k = 1; k <= R + 2; ++k) {
+    const double dd = t[k + 1] - t[k];
+    pq[k] = fma((13.0 / 3.0) * dd, dd, eps9);
+  }
+  // cell r (window index r + 3) uses t[r+1 .. r+4], pq[r+1 .. r+3]; its cotangents go to Tk[r .. r+3]
+  double Tk[R + 3];
+#pragma unroll
+  for (int k = 0; k < R + 3; ++k) Tk[k] = 0.0;
+  double o[R];
+
+  const Weno5State F3 = weno53_state(t[4], t[5], t[6], t[7], pq[4], pq[5], pq[6]);
+  const Weno5State F0 = weno53_state(t[1], t[2], t[3], t[4], pq[1], pq[2], pq[3]);
+  const double ur3 = w[6] + F3.uR, ul0 = w[3] + F0.uL;
+  const double ur_left = __shfl_up_sync(kFull, ur3, 1);
+  const double ul_right = __shfl_down_sync(kFull, ul0, 1);
+
+  const LeanFace f0 = lean_face(hG[0], ur_left, ul0, w[2], w[3]);
+  const Weno5State F1 = weno53_state(t[2], t[3], t[4], t[5], pq[2], pq[3], pq[4]);
+  const LeanFace f1 = lean_face(hG[1], w[3] + F0.uR, w[4] + F1.uL, w[3], w[4]);
+  o[0] = (f0.dp + f1.dj) + (f1.gR + f0.gL);
+  weno53_vjp_acc(F0, t[1], t[2], t[3], t[4], f1.gR, f0.gL, Tk[0], Tk[1], Tk[2], Tk[3]);
+
+  const Weno5State F2 = weno53_state(t[3], t[4], t[5], t[6], pq[3], pq[4], pq[5]);
+  const LeanFace f2 = lean_face(hG[2], w[4] + F1.uR, w[5] + F2.uL, w[4], w[5]);
+  o[1] = (f1.dp + f2.dj) + (f2.gR + f1.gL);
+  weno53_vjp_acc(F1, t[2], t[3], t[4], t[5], f2.gR, f1.gL, Tk[1], Tk[2], Tk[3], Tk[4]);
+
+  const LeanFace f3 = lean_face(hG[3], w[5] + F2.uR, w[6] + F3.uL, w[5], w[6]);
+  o[2] = (f2.dp + f3.dj) + (f3.gR + f2.gL);
+  weno53_vjp_acc(F2, t[3], t[4], t[5], t[6], f3.gR, f2.gL, Tk[2], Tk[3], Tk[4], Tk[5]);
+
+  const LeanFace f4 = lean_face(hG[4], ur3, ul_right, w[6], w[7]);
+  o[3] = (f3.dp + f4.dj) + (f4.gR + f3.gL);
+  weno53_vjp_acc(F3, t[4], t[5], t[6], t[7], f4.gR, f3.gL, Tk[3], Tk[4], Tk[5], Tk[6]);
+
+  // ---- contributions of the neighbour lanes' cells to the first differences around my cells
+  const double fl5 = __shfl_up_sync(kFull, Tk[5], 1);
+  const double fl6 = __shfl_up_sync(kFull, Tk[6], 1);
+  const double fr0 = __shfl_down_sync(kFull, Tk[0], 1);
+  const double fr1 = __shfl_down_sync(kFull, Tk[1], 1);
+  Tk[1] += fl5;
+  Tk[2] += fl6;
+  Tk[4] += fr0;
+  Tk[5] += fr1;
+
+  if (lane >= 1 && lane <= 30) {
+    double gi[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) gi[r] = fma(1.0 / 6.0, Tk[r + 1] - Tk[r + 2], o[r]);
+    if (inside) {
+      // inside => interior cells only (no ghost among them)
+      *reinterpret_cast<double2 *>(p.out + off) = make_double2(lin[0] + gi[0], lin[1] + gi[1]);
+      *reinterpret_cast<double2 *>(p.out + off + 2) = make_double2(lin[2] + gi[2], lin[3] + gi[3]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int i = g + c0 + r;
+        if (i < 0 || i >= nx) continue;
+        const bool ghost = (p.bc.bc != PSK_BC_NONE) && (i < g || i >= nx - g);
+        if (ghost) {
+          // ghost cells of x do not influence L; what landed on them goes back through the
+          // transpose of apply_boundary (already scaled by c_g dt: p.prescaled)
+          p.out[base + i] = lin[r];
+          p.gspill[static_cast<int64_t>(row) * 2 * g + (i < g ? i : i - n)] = gi[r];
+        } else {
+          p.out[base + i] = lin[r] + gi[r];
+        }
+      }
+    }
+  }
+}
+
+template <int MINB>
+int launch_adjoint_lean(const AdjParams &p, int batch, cudaStream_t st) {
+  const int chunks = (p.bc.n + p.bc.g + 119) / 120;  // chunks 0 .. chunks-1 plus chunk -1
+  const int total = chunks + 1;
+  const int wpc = total < 4 ? total : 4;
+  const unsigned gx = static_cast<unsigned>((total + wpc - 1) / wpc);
+  const unsigned gy = batch < 65535 ? batch : 65535u;
+  if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
+  const dim3 grid(gx, gy, batch / gy);
+  adjoint_lean_kernel<MINB><<<grid, wpc * 32, 0, st>>>(p, chunks);
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
 template <int EQ, int FLUX>
 int launch_adjoint_warp(const AdjParams &p, int batch, cudaStream_t st) {
   const int chunks = (p.bc.n + p.bc.g + 119) / 120;  // chunks 0 .. chunks-1 plus chunk -1
@@ -427,7 +645,8 @@ __global__ void adjoint_boundary_kernel(const AdjParams p) {
   const int nx = p.bc.nx, g = p.bc.g, n = p.bc.n;
   const double *__restrict__ xrow = p.x + static_cast<int64_t>(row) * p.ld;
   double *orow = p.out + static_cast<int64_t>(row) * p.ld;
-  const double cgdt = p.c_g * (p.dt != nullptr ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 1.0);
+  const double cgdt =
+      p.prescaled ? 1.0 : p.c_g * (p.dt != nullptr ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 1.0);
   // where apply_boundary copied ghost cell i from (-1: from nowhere)
   auto source = [&](int i) -> int {
     if (i >= g && i < nx - g) return i;
@@ -466,7 +685,10 @@ __global__ void adjoint_boundary_kernel(const AdjParams p) {
   }
 }
 
-static int g_adjoint_variant = 0;  // 0: warp kernel where applicable, 1: tile kernel always
+// 0: lean warp kernel for the hot configuration, warp kernel for the other WENO-JS5 cases;
+// 1: tile kernel always; 2: warp kernel (no lean kernel); 3..5: lean kernel compiled for
+// 3 / 4 / 5 CTAs of 128 threads per SM (register budgets 168 / 128 / 96)
+static int g_adjoint_variant = 0;
 
 template <int EQ, int FLUX, int REC>
 int launch_adjoint(const AdjParams &p0, int batch, cudaStream_t st) {
@@ -479,9 +701,19 @@ int launch_adjoint(const AdjParams &p0, int batch, cudaStream_t st) {
                        (p.acc == nullptr || reinterpret_cast<uintptr_t>(p.acc + p.bc.g) % 16 == 0) &&
                        (p.acc2 == nullptr || reinterpret_cast<uintptr_t>(p.acc2 + p.bc.g) % 16 == 0) &&
                        (p.ld % 2 == 0);
-  if (REC == PSK_REC_WENOJS53 && g_adjoint_variant == 0 && aligned && p.bc.g == 3 &&
+  if (REC == PSK_REC_WENOJS53 && g_adjoint_variant != 1 && aligned && p.bc.g == 3 &&
       (batch <= 65535 || batch % 65535 == 0)) {
-    int rc = launch_adjoint_warp<EQ, FLUX>(p, batch, st);
+    int rc;
+    if (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV && p.nu == nullptr && g_adjoint_variant != 2) {
+      p.prescaled = 1;
+      switch (g_adjoint_variant) {
+        case 3: rc = launch_adjoint_lean<3>(p, batch, st); break;
+        case 5: rc = launch_adjoint_lean<5>(p, batch, st); break;
+        default: rc = launch_adjoint_lean<4>(p, batch, st); break;
+      }
+    } else {
+      rc = launch_adjoint_warp<EQ, FLUX>(p, batch, st);
+    }
     if (rc != PSK_OK) return rc;
     if (LFX || p.bc.bc == PSK_BC_PERIODIC || p.bc.bc == PSK_BC_NEUMANN) {
       adjoint_boundary_kernel<LFX><<<batch, LFX ? 128 : 32, 0, st>>>(p);
@@ -580,9 +812,9 @@ using namespace psk;
 
 extern "C" {
 
-/* A/B switch for the adjoint stage: 0 = warp kernel where applicable (default), 1 = tile kernel */
+/* A/B switch for the adjoint stage (see g_adjoint_variant) */
 int psk_set_adjoint_variant(int variant) {
-  if (variant < 0 || variant > 1) return PSK_E_INVALID;
+  if (variant < 0 || variant > 5) return PSK_E_INVALID;
   g_adjoint_variant = variant;
   return PSK_OK;
 }

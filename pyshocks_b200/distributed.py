@@ -9,7 +9,12 @@ Two partitionings:
 * **slab decomposition** of one very large periodic grid -- contiguous slabs of ``n / G`` cells
   per GPU on a ring; every RHS needs the 3 cells next to each slab edge from the neighbour
   (24 B per side per stage: latency, not bandwidth), and a CFL-adaptive ``dt`` needs one
-  ``all_reduce(MAX)`` of a single double per step (:class:`SlabSolver`).
+  ``all_reduce(MAX)`` of a single double per step.  Two transports:
+  :class:`PeerSlabSolver` (default for the bench) stores the edge cells straight into the
+  neighbours' ghost slots through NVLink peer memory (``psk_halo_push`` / ``psk_halo_wait``,
+  epoch flags, no host involvement) and overlaps the exchange with the interior cells by
+  running the slab edges on a high-priority stream; :class:`SlabSolver` is the plain NCCL
+  send/recv version (the baseline it is measured against, and the gloo-testable one).
 
 The reference has no distributed path at all (platform forced to one CPU device,
 ``pyshocks/__init__.py:66``); these are the new workloads of BASELINE.json configs 3-5.
@@ -22,7 +27,9 @@ from typing import Protocol, Sequence
 import torch
 import torch.distributed as dist
 
-from .ensemble import EnsembleSolver, SolveResult
+from . import _lib as L
+from .ensemble import EnsembleSolver, SolveResult, row_layout
+from .path import HotPath
 
 
 def shard_rows(batch: int, rank: int, world: int) -> tuple[int, int]:
@@ -219,3 +226,307 @@ class SlabSolver:
             self.step(s.dt, maxabs=s.maxabs)
             m += 1
         return SolveResult(u=s.u, steps=m, t=s.t)
+
+
+# {{{ peer-memory transport (NVLink stores + epoch flags) with edge / interior overlap
+
+_FLAG_WORDS = 16  # two int64 flags, padded to a 128-byte line of their own
+
+
+class _RawDeviceMemory:
+    """``__cuda_array_interface__`` carrier for memory torch did not allocate."""
+
+    def __init__(self, ptr: int, words: int, typestr: str) -> None:
+        self.__cuda_array_interface__ = {
+            "shape": (words,), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+
+class PeerSlabMemory:
+    """Peer-visible storage of one slab: ``u, k1, k2`` (``ld`` doubles each, the aligned row
+    layout of :func:`row_layout`) followed by two epoch flags.  ``handle`` (64 bytes) lets
+    another process map it (``psk_p2p_open``)."""
+
+    def __init__(self, n_local: int, g: int, device: torch.device) -> None:
+        import ctypes as ct
+
+        self.n_local, self.g = int(n_local), int(g)
+        self.col0, self.ld = row_layout(self.n_local, self.g)
+        self.words = 3 * self.ld + _FLAG_WORDS
+        self.device = torch.device(device)
+        ptr = ct.c_void_p()
+        handle = ct.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            L.check("psk_p2p_alloc", L.lib().psk_p2p_alloc(8 * self.words, ct.byref(ptr), handle))
+        self.ptr = int(ptr.value)
+        self.handle = bytes(handle.raw)
+        self._raw = _RawDeviceMemory(self.ptr, self.words, "<f8")
+        flat = torch.as_tensor(self._raw, device=self.device)
+        self.store = flat[: 3 * self.ld].view(3, 1, self.ld)
+        self._raw_flags = _RawDeviceMemory(self.ptr + 8 * 3 * self.ld, 2, "<i8")
+        self.flags = torch.as_tensor(self._raw_flags, device=self.device)
+
+    def describe(self) -> dict:
+        return {"handle": self.handle, "n_local": self.n_local}
+
+    def close(self) -> None:
+        if self.ptr:
+            torch.cuda.synchronize(self.device)
+            self.store = self.flags = None
+            L.check("psk_p2p_free", L.lib().psk_p2p_free(self.ptr))
+            self.ptr = 0
+
+
+class PeerRing:
+    """Addresses of the two ring neighbours' ghost slots and flags, as seen from this process."""
+
+    def __init__(self, mem: PeerSlabMemory, rank: int, world: int, left: tuple[int, int], right: tuple[int, int],
+                 group: dist.ProcessGroup | None = None, opened: Sequence[int] = ()) -> None:
+        self.mem, self.rank, self.world, self.group = mem, rank, world, group
+        self.distributed = False  # True: the neighbours are other processes (torch.distributed is up)
+        self._opened = list(opened)
+        g = mem.g
+        (lbase, ln), (rbase, rn) = left, right
+        lcol0, lld = row_layout(ln, g)
+        rcol0, rld = row_layout(rn, g)
+        # array a of the LEFT neighbour: its right ghost cells; of the RIGHT neighbour: its left ghost cells
+        self.dst_lo = [lbase + 8 * (a * lld + lcol0 + g + ln) for a in range(3)]
+        self.dst_hi = [rbase + 8 * (a * rld + rcol0) for a in range(3)]
+        # I am the left neighbour's RIGHT neighbour (its flag 1) and the right neighbour's LEFT one (flag 0)
+        self.flag_lo = lbase + 8 * 3 * lld + 8
+        self.flag_hi = rbase + 8 * 3 * rld
+        base = mem.ptr
+        self.src_lo = [base + 8 * (a * mem.ld + mem.col0 + g) for a in range(3)]
+        self.src_hi = [base + 8 * (a * mem.ld + mem.col0 + mem.n_local) for a in range(3)]
+        self.my_flags = (base + 8 * 3 * mem.ld, base + 8 * 3 * mem.ld + 8)
+
+    @classmethod
+    def connect(cls, mem: PeerSlabMemory, group: dist.ProcessGroup | None = None) -> "PeerRing":
+        """Exchange IPC handles over ``torch.distributed`` and map the two neighbours."""
+        import ctypes as ct
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        descs: list = [None] * world
+        dist.all_gather_object(descs, mem.describe(), group=group)
+        opened: dict[int, int] = {rank: mem.ptr}
+        for r in {(rank - 1) % world, (rank + 1) % world} - {rank}:
+            p = ct.c_void_p()
+            with torch.cuda.device(mem.device):
+                L.check("psk_p2p_open", L.lib().psk_p2p_open(descs[r]["handle"], ct.byref(p)))
+            opened[r] = int(p.value)
+        lr, rr = (rank - 1) % world, (rank + 1) % world
+        ring = cls(mem, rank, world, (opened[lr], descs[lr]["n_local"]), (opened[rr], descs[rr]["n_local"]),
+                   group=group, opened=[v for k, v in opened.items() if k != rank])
+        ring.distributed = world > 1
+        dist.barrier(group=group)  # every rank has mapped its neighbours before anyone pushes
+        return ring
+
+    @classmethod
+    def local(cls, mems: Sequence[PeerSlabMemory], r: int) -> "PeerRing":
+        """Ring between slabs held by one process (single-GPU tests of the same protocol)."""
+        world = len(mems)
+        lm, rm = mems[(r - 1) % world], mems[(r + 1) % world]
+        return cls(mems[r], r, world, (lm.ptr, lm.n_local), (rm.ptr, rm.n_local))
+
+    def all_max(self, x: torch.Tensor) -> None:
+        if self.distributed:
+            dist.all_reduce(x, op=dist.ReduceOp.MAX, group=self.group)
+
+    def close(self) -> None:
+        for p in self._opened:
+            L.check("psk_p2p_close", L.lib().psk_p2p_close(p))
+        self._opened = []
+
+
+class PeerSlabSolver:
+    """One rank's slab of a single periodic 1-D Burgers grid, ghost cells exchanged through peer
+    memory and overlapped with the interior.
+
+    Per stage ``uout = stage(u0, uin)``:
+
+    * **edge stream** (high priority): wait until both neighbours' pushes of ``uin``'s ghost cells
+      have arrived (``psk_halo_wait`` on local flags) -> stage kernel on the first and the last
+      ``edge`` cells of the slab -> ``psk_halo_push`` of ``uout``'s outermost ``g`` cells into the
+      neighbours' ghost slots + their flags (epoch + 1);
+    * **main stream**: stage kernel on the interior ``[edge, n - edge)``, which depends only on
+      local data of the previous stage, so the NVLink round trip hides behind it.
+
+    Events order edge(s) after interior(s - 1) and interior(s) after edge(s - 1); the time loop
+    never touches the host.  A slab too short to split runs wait -> stage -> push on one stream.
+    The arithmetic per cell is the same kernel on the same neighbours, so the result is
+    bit-identical to the undecomposed solve."""
+
+    def __init__(self, *, n_global: int, rank: int, world: int, dx: float, flux: str = "rusanov",
+                 rec: str = "wenojs53", eps: float = 1.0e-12, math: str = "fast", edge: int = 7680,
+                 overlap: bool = True, device: torch.device | str | None = None,
+                 timeout_s: float = 20.0) -> None:
+        self.rank, self.world = rank, world
+        self.first, self.n_local = shard_rows(n_global, rank, world)
+        self.g = g = {"constant": 1, "wenojs32": 2, "wenojs53": 3}[rec]
+        if self.n_local < 2 * g:
+            raise ValueError("slabs must hold at least 2 g cells")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.mem = PeerSlabMemory(self.n_local, g, dev)
+        kw = dict(equation="burgers", flux=flux, rec=rec, bc="none", g=g, dx=dx, eps=eps, math=math, device=dev)
+        self.solver = EnsembleSolver(n=self.n_local, batch=1, store=self.mem.store, **kw)
+        edge = (int(edge) // 16) * 16
+        self.split = bool(overlap) and edge >= 16 and self.n_local >= 4 * edge
+        self.edge = edge if self.split else 0
+        if self.split:
+            self.hp_edge = HotPath(n=self.edge, **kw)
+            self.hp_mid = HotPath(n=self.n_local - 2 * self.edge, **kw)
+            self.edge_stream = torch.cuda.Stream(device=dev, priority=-1)
+            self.ev_main, self.ev_edge = torch.cuda.Event(), torch.cuda.Event()
+        self.ring: PeerRing | None = None
+        self.epoch = 0
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.timeout_ns = int(timeout_s * 1e9)
+        self.exchanges = 0
+        self.launches = 0
+
+    # {{{ set-up
+
+    def connect(self, group: dist.ProcessGroup | None = None) -> None:
+        self.ring = PeerRing.connect(self.mem, group)
+
+    def attach(self, ring: PeerRing) -> None:
+        self.ring = ring
+
+    def close(self) -> None:
+        if self.ring is not None:
+            torch.cuda.synchronize(self.mem.device)
+            if self.ring.distributed:
+                dist.barrier(group=self.ring.group)  # nobody frees memory a neighbour still writes
+            distributed, group = self.ring.distributed, self.ring.group
+            self.ring.close()
+            self.ring = None
+            if distributed:
+                dist.barrier(group=group)  # ... and nobody frees memory a neighbour still has mapped
+        self.solver = None
+        self.mem.close()
+
+    @property
+    def u(self) -> torch.Tensor:
+        return self.solver.u
+
+    def interior(self) -> torch.Tensor:
+        return self.solver.u[0, self.g : self.g + self.n_local]
+
+    def load_interior(self, u_local: torch.Tensor) -> None:
+        """``u_local``: this rank's ``n_local`` interior cells; announces them to the neighbours."""
+        self.solver.u[0, self.g : self.g + self.n_local].copy_(u_local)
+        self._push(0)
+        if self.split:
+            main = torch.cuda.current_stream()
+            self.ev_main.record(main)
+            self.ev_edge.record(main)
+
+    # }}}
+
+    # {{{ exchange primitives
+
+    def _push(self, a: int) -> None:
+        r = self.ring
+        self.epoch += 1
+        L.check("psk_halo_push", L.lib().psk_halo_push(
+            r.src_lo[a], r.dst_lo[a], r.src_hi[a], r.dst_hi[a], self.g, r.flag_lo, r.flag_hi, self.epoch,
+            L.stream_ptr()))
+        self.exchanges += 1
+        self.launches += 1
+
+    def _wait(self) -> None:
+        r = self.ring
+        L.check("psk_halo_wait", L.lib().psk_halo_wait(
+            r.my_flags[0], r.my_flags[1], self.epoch, self.timeout_ns, L.raw_ptr(self.timed_out), L.stream_ptr()))
+        self.launches += 1
+
+    def check(self) -> None:
+        """Host-side check (synchronises): did a wait give up on a neighbour?"""
+        if int(self.timed_out.item()) != 0:
+            raise RuntimeError(f"rank {self.rank}: a neighbour's ghost cells did not arrive within {self.timeout_ns / 1e9:.0f} s")
+
+    # }}}
+
+    def _sub(self, a: torch.Tensor, start: int, n: int) -> torch.Tensor:
+        return a[:, start : start + n + 2 * self.g]
+
+    def _stage(self, stage: int, u0: torch.Tensor, uin: torch.Tensor, uout: torch.Tensor, a_out: int,
+               dt: torch.Tensor, maxabs: torch.Tensor | None) -> None:
+        s = self.solver
+        if not self.split:
+            self._wait()
+            s.hp.stage(stage, u0, uin, uout, dt, maxabs=maxabs)
+            self._push(a_out)
+            self.launches += 1
+            return
+        main = torch.cuda.current_stream()
+        E, e, n = self.edge_stream, self.edge, self.n_local
+        E.wait_event(self.ev_main)     # interior of the previous stage (its cells feed the edge stencils)
+        main.wait_event(self.ev_edge)  # edges of the previous stage (they feed the interior stencils)
+        with torch.cuda.stream(E):
+            self._wait()
+            for start in (0, n - e):
+                self.hp_edge.stage(stage, self._sub(u0, start, e), self._sub(uin, start, e), self._sub(uout, start, e),
+                                   dt, maxabs=maxabs)
+            self._push(a_out)
+            self.ev_edge.record(E)
+        self.hp_mid.stage(stage, self._sub(u0, e, n - 2 * e), self._sub(uin, e, n - 2 * e),
+                          self._sub(uout, e, n - 2 * e), dt, maxabs=maxabs)
+        self.ev_main.record(main)
+        self.launches += 3
+
+    def run_stage(self, stage: int, dt: torch.Tensor, maxabs: torch.Tensor | None = None) -> None:
+        """Stage 1, 2 or 3 of the current SSPRK33 step (halo wait, kernels, halo push)."""
+        s = self.solver
+        if stage == 1:
+            if self.split:
+                # dt / maxabs were produced on the main stream: the edge stream must see them
+                self.ev_main.record(torch.cuda.current_stream())
+            self._stage(1, s.u, s.u, s.k1, 1, dt, None)
+        elif stage == 2:
+            self._stage(2, s.u, s.k1, s.k2, 2, dt, None)
+        else:
+            self._stage(3, s.u, s.k2, s.u, 0, dt, maxabs)
+
+    def step(self, dt: torch.Tensor, maxabs: torch.Tensor | None = None) -> None:
+        for stage in (1, 2, 3):
+            self.run_stage(stage, dt, maxabs)
+
+    def join(self) -> None:
+        """Main stream waits for the edge stream (before anything else reads the state)."""
+        if self.split:
+            torch.cuda.current_stream().wait_event(self.ev_edge)
+
+    def solve_fixed_dt(self, dt: float | torch.Tensor, nsteps: int) -> SolveResult:
+        if not isinstance(dt, torch.Tensor):
+            dt = torch.full((1,), float(dt), dtype=torch.float64, device=self.mem.device)
+        for _ in range(nsteps):
+            self.step(dt)
+        self.join()
+        return SolveResult(u=self.solver.u, steps=nsteps, t=self.solver.t)
+
+    def solve_adaptive(self, *, theta: float, tfinal: float, cfl_scale: float, max_steps: int = 1 << 20) -> SolveResult:
+        """timestepping.py:128-152 on the decomposed grid (see :meth:`SlabSolver.solve_adaptive`)."""
+        s = self.solver
+        s.t.zero_()
+        s.nonfinite.zero_()
+        s.hp.max_abs(s.u, 1, out=s.maxabs)
+        m = 0
+        while m < max_steps:
+            self.ring.all_max(s.maxabs)
+            L.check("psk_step_control", L.lib().psk_step_control(
+                1, float(theta), float(cfl_scale), float(tfinal), L.ptr(s.maxabs), L.ptr(s.t), L.ptr(s.t),
+                L.ptr(s.dt), L.raw_ptr(s.active), L.raw_ptr(s.nonfinite), L.stream_ptr()))
+            if int(s.active.item()) == 0:
+                break
+            if int(s.nonfinite.item()) != 0:
+                raise ValueError("Time step is not finite.")
+            s.maxabs.zero_()
+            self.step(s.dt, maxabs=s.maxabs)
+            self.join()
+            m += 1
+        self.check()
+        return SolveResult(u=s.u, steps=m, t=s.t)
+
+
+# }}}

@@ -31,6 +31,13 @@ class SolveResult:
     steps_per_row: np.ndarray | None = None
 
 
+def row_layout(n: int, g: int) -> tuple[int, int]:
+    """``(col0, ld)`` of the padded row layout: the first interior cell sits at column 16 of a row
+    whose stride is a multiple of 16 doubles (128-byte aligned vector accesses)."""
+    col0 = (16 - g) % 16
+    return col0, ((col0 + n + 2 * g + 15) // 16) * 16
+
+
 class EnsembleSolver:
     def __init__(
         self,
@@ -48,6 +55,7 @@ class EnsembleSolver:
         nu: np.ndarray | None = None,
         velocity: np.ndarray | None = None,
         device: torch.device | str | None = None,
+        store: torch.Tensor | None = None,
     ) -> None:
         self.hp = HotPath(
             equation=equation, flux=flux, rec=rec, bc=bc, n=n, g=g, dx=dx, eps=eps, math=math,
@@ -55,10 +63,13 @@ class EnsembleSolver:
         )
         self.batch, self.n, self.g, self.nx = int(batch), int(n), int(g), int(n) + 2 * int(g)
         dev = self.hp.device
-        # first interior cell at column 16 of a row whose stride is a multiple of 16 doubles
-        self.col0 = (16 - self.g) % 16
-        self.ld = ((self.col0 + self.nx + 15) // 16) * 16
-        self._store = torch.zeros((3, self.batch, self.ld), dtype=torch.float64, device=dev)
+        self.col0, self.ld = row_layout(self.n, self.g)
+        if store is None:
+            store = torch.zeros((3, self.batch, self.ld), dtype=torch.float64, device=dev)
+        elif tuple(store.shape) != (3, self.batch, self.ld) or store.dtype != torch.float64:
+            # caller-owned storage (peer-visible memory of the slab decomposition)
+            raise ValueError(f"store must be float64 of shape {(3, self.batch, self.ld)}")
+        self._store = store
         self.u, self.k1, self.k2 = self.views(self._store)
         self.t = torch.zeros(self.batch, dtype=torch.float64, device=dev)
         self.dt = torch.zeros(self.batch, dtype=torch.float64, device=dev)

@@ -64,6 +64,91 @@ def test_local_slabs_equal_undecomposed(world: int, math: str) -> None:
     assert torch.equal(out, ref)
 
 
+@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_peer_memory_slabs_equal_undecomposed(world: int, overlap: bool) -> None:
+    """The peer-memory protocol (psk_halo_push / psk_halo_wait, epoch flags, edge stream +
+    interior stream) with every slab held by this process: bit-identical to the periodic solve."""
+    from pyshocks_b200.distributed import PeerRing, PeerSlabSolver
+
+    n, g, nsteps = 6151, 3, 9
+    dt = 0.4 * (3.0 / n) / 1.8
+    ref = _reference_periodic(n, dt, nsteps, "fast")
+    ug = torch.from_numpy(_ic(n, g)).cuda()
+    slabs = [PeerSlabSolver(n_global=n, rank=r, world=world, dx=3.0 / n, edge=256, overlap=overlap, timeout_s=5.0)
+             for r in range(world)]
+    try:
+        assert all(s.split == overlap for s in slabs)
+        for r, s in enumerate(slabs):
+            s.attach(PeerRing.local([t.mem for t in slabs], r))
+        for s in slabs:
+            s.load_interior(ug[s.first : s.first + s.n_local])
+        dtt = torch.full((1,), dt, dtype=torch.float64, device="cuda")
+        for _ in range(nsteps):
+            for stage in (1, 2, 3):  # stage by stage: every wait depends on pushes enqueued before it
+                for s in slabs:
+                    s.run_stage(stage, dtt)
+        for s in slabs:
+            s.join()
+            s.check()
+        out = torch.cat([s.interior() for s in slabs])
+        assert torch.equal(out, ref)
+        assert all(s.exchanges == 3 * nsteps + 1 for s in slabs)
+    finally:
+        for s in slabs:
+            s.ring = None
+            s.solver = None
+            s.mem.close()
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_peer_memory_adaptive_single_slab(math: str) -> None:
+    """timestepping.step's dt logic on a (one-slab) peer-memory ring: same dt sequence as the
+    single-array adaptive solve; bit-identical state in STRICT mode (FAST: the slab runs the
+    specialised kernel, the single-array solver the general one -- a few ulp per step)."""
+    from pyshocks_b200.distributed import PeerRing, PeerSlabSolver
+    from pyshocks_b200.ensemble import EnsembleSolver
+
+    n, g = 1 << 14, 3
+    ug = torch.from_numpy(_ic(n, g)).cuda()
+    akw = dict(theta=0.8, tfinal=0.004, cfl_scale=0.5 * (3.0 / n))
+    single = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=g,
+                            dx=3.0 / n, eps=1e-12, batch=1, math=math)
+    u0 = torch.zeros((1, n + 2 * g), dtype=torch.float64, device="cuda")
+    u0[0, g : g + n] = ug
+    sres = single.solve_adaptive(u0, check_every=1, **akw)
+    ps = PeerSlabSolver(n_global=n, rank=0, world=1, dx=3.0 / n, edge=512, math=math, timeout_s=5.0)
+    try:
+        ps.attach(PeerRing.local([ps.mem], 0))
+        ps.load_interior(ug)
+        pres = ps.solve_adaptive(**akw)
+        assert ps.split and pres.steps == sres.steps
+        assert float(ps.solver.t[0]) == float(single.t[0])
+        diff = float((ps.interior() - single.u[0, g : g + n]).abs().max())
+        assert diff == 0.0 if math == "strict" else diff <= 1e-13
+    finally:
+        ps.ring = None
+        ps.solver = None
+        ps.mem.close()
+
+
+def test_halo_wait_gives_up_instead_of_hanging() -> None:
+    from pyshocks_b200 import _lib as L
+
+    flags = torch.zeros(2, dtype=torch.int64, device="cuda")
+    timed_out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.check("psk_halo_wait", L.lib().psk_halo_wait(flags.data_ptr(), flags.data_ptr() + 8, 1, int(0.05e9),
+                                                   timed_out.data_ptr(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(timed_out.item()) == 1
+    flags.fill_(3)
+    timed_out.zero_()
+    L.check("psk_halo_wait", L.lib().psk_halo_wait(flags.data_ptr(), flags.data_ptr() + 8, 3, int(5e9),
+                                                   timed_out.data_ptr(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    assert int(timed_out.item()) == 0
+
+
 def _free_port() -> int:
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -78,7 +163,7 @@ def _nccl_worker(rank: int, world: int, port: int, out: dict) -> None:
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from pyshocks_b200.distributed import DistRing, ShardedEnsemble, SlabSolver, shard_rows
+        from pyshocks_b200.distributed import DistRing, PeerSlabSolver, ShardedEnsemble, SlabSolver, shard_rows
         from pyshocks_b200.ensemble import EnsembleSolver
 
         def mark(msg: str) -> None:
@@ -98,18 +183,42 @@ def _nccl_worker(rank: int, world: int, port: int, out: dict) -> None:
         ref = _reference_periodic(n, dt, nsteps, "fast")
         ok = torch.equal(slab.interior(), ref[slab.first : slab.first + slab.n_local])
 
-        # adaptive dt: all ranks must agree with the single-GPU adaptive solve
-        slab2 = SlabSolver(n_global=n, ring=ring, dx=3.0 / n)
-        slab2.load_interior(ug[slab2.first : slab2.first + slab2.n_local])
-        res = slab2.solve_adaptive(theta=0.8, tfinal=0.002, cfl_scale=0.5 * (3.0 / n))
-        single = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=g,
-                                dx=3.0 / n, eps=1e-12, batch=1)
-        u0 = torch.zeros((1, n + 2 * g), dtype=torch.float64, device="cuda")
-        u0[0, g : g + n] = ug
-        sres = single.solve_adaptive(u0, theta=0.8, tfinal=0.002, cfl_scale=0.5 * (3.0 / n), check_every=1)
-        mark("adaptive done")
-        ok = ok and res.steps == sres.steps
-        ok = ok and torch.equal(slab2.interior(), single.u[0, g + slab2.first : g + slab2.first + slab2.n_local])
+        # peer-memory transport (CUDA IPC over NVLink), with and without the edge / interior overlap
+        for overlap in (False, True):
+            ps = PeerSlabSolver(n_global=n, rank=rank, world=world, dx=3.0 / n, edge=1024, overlap=overlap)
+            ps.connect()
+            ps.load_interior(ug[ps.first : ps.first + ps.n_local])
+            ps.solve_fixed_dt(dt, nsteps)
+            ps.check()
+            ok = ok and torch.equal(ps.interior(), ref[ps.first : ps.first + ps.n_local])
+            ok = ok and ps.split == overlap
+            ps.close()
+            mark(f"peer slabs overlap={overlap} ok={ok}")
+        # adaptive dt: every rank takes the same dt sequence as the single-GPU adaptive solve.  The
+        # single-array solver runs the general kernel (row mask), the slabs the specialised one: two FAST
+        # implementations agree to a few ulp per step, the STRICT ones bit for bit; the two slab
+        # transports run the same kernels on the same cells and must agree bit for bit in both modes.
+        akw = dict(theta=0.8, tfinal=0.002, cfl_scale=0.5 * (3.0 / n))
+        for math in ("strict", "fast"):
+            pa = PeerSlabSolver(n_global=n, rank=rank, world=world, dx=3.0 / n, edge=1024, math=math)
+            pa.connect()
+            pa.load_interior(ug[pa.first : pa.first + pa.n_local])
+            pres = pa.solve_adaptive(**akw)
+            slab2 = SlabSolver(n_global=n, ring=ring, dx=3.0 / n, math=math)
+            slab2.load_interior(ug[slab2.first : slab2.first + slab2.n_local])
+            res = slab2.solve_adaptive(**akw)
+            single = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=g,
+                                    dx=3.0 / n, eps=1e-12, batch=1, math=math)
+            u0 = torch.zeros((1, n + 2 * g), dtype=torch.float64, device="cuda")
+            u0[0, g : g + n] = ug
+            sres = single.solve_adaptive(u0, check_every=1, **akw)
+            mine = single.u[0, g + pa.first : g + pa.first + pa.n_local]
+            diff = float((pa.interior() - mine).abs().max())
+            mark(f"adaptive {math}: steps peer {pres.steps} / nccl {res.steps} / single {sres.steps}; max diff {diff:.3e}")
+            ok = ok and res.steps == sres.steps and pres.steps == sres.steps
+            ok = ok and torch.equal(pa.interior(), slab2.interior())
+            ok = ok and (diff == 0.0 if math == "strict" else diff <= 1e-13)
+            pa.close()
 
         # row-sharded ensemble == unsharded ensemble
         B, nn = 37, 512

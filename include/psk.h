@@ -245,6 +245,29 @@ int psk_halo_push(const double *src_lo, double *dst_lo, const double *src_hi, do
 int psk_halo_wait(const int64_t *flag_a, const int64_t *flag_b, int64_t epoch, int64_t timeout_ns,
                   int32_t *timed_out, psk_stream_t stream);
 
+/* The same exchange FUSED into the stage kernel (one launch per stage, nothing else on the
+ * exchange path): the warps that read ghost cells spin on the local flags wait_lo / wait_hi
+ * until they reach wait_epoch (the neighbours' pushes of uin's edge cells), every other warp
+ * starts at once; the lanes that store uout's first / last g cells also store them to
+ * peer_lo / peer_hi (the neighbours' ghost slots of their uout array) and then raise
+ * *flag_lo / *flag_hi to wait_epoch + 1.  NULL pointers switch a side off. */
+typedef struct psk_halo_link {
+  const int64_t *wait_lo, *wait_hi; /* LOCAL flags, written by the left / right neighbour        */
+  int64_t wait_epoch;
+  double *peer_lo, *peer_hi;        /* left neighbour's right ghost slots / right neighbour's left */
+  int64_t *flag_lo, *flag_hi;       /* the neighbours' flags this rank raises                     */
+  int64_t timeout_ns;               /* a spin gives up after this long and sets *timed_out        */
+  int32_t *timed_out;
+} psk_halo_link;
+
+/* psk_ssprk33_stage (stages 1-3, one row, boundary kind NONE, dt shared) with the exchange
+ * above.  PSK_E_UNSUPPORTED outside the hot configuration (Burgers + Rusanov + WENO-JS5, FAST
+ * math, g = 3, n % 4 == 0, aligned rows): fall back to psk_halo_wait / psk_ssprk33_stage /
+ * psk_halo_push. */
+int psk_ssprk33_stage_p2p(const psk_desc *d, int stage, const double *u0, const double *uin,
+                          double *uout, const double *dt, double *maxabs, const psk_halo_link *link,
+                          psk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

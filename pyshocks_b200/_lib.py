@@ -52,6 +52,22 @@ class PskDesc(ct.Structure):
     ]
 
 
+class PskHaloLink(ct.Structure):
+    """``psk_halo_link`` of include/psk.h (device pointers as integers)."""
+
+    _fields_ = [
+        ("wait_lo", _dp),
+        ("wait_hi", _dp),
+        ("wait_epoch", ct.c_int64),
+        ("peer_lo", _dp),
+        ("peer_hi", _dp),
+        ("flag_lo", _dp),
+        ("flag_hi", _dp),
+        ("timeout_ns", ct.c_int64),
+        ("timed_out", _dp),
+    ]
+
+
 class PskError(RuntimeError):
     def __init__(self, fn: str, status: int) -> None:
         detail = _lib.psk_status_string(status).decode()
@@ -96,6 +112,7 @@ def _load() -> ct.CDLL:
         "psk_p2p_close": ([vp], ct.c_int),
         "psk_halo_push": ([vp, vp, vp, vp, i32, vp, vp, i64, vp], ct.c_int),
         "psk_halo_wait": ([vp, vp, i64, i64, vp, vp], ct.c_int),
+        "psk_ssprk33_stage_p2p": ([D, ct.c_int, vp, vp, vp, vp, vp, ct.POINTER(PskHaloLink), vp], ct.c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here = the library is stale: rebuild it
@@ -114,7 +131,7 @@ EXPORTS = (
     "psk_reconstruct", "psk_numerical_flux", "psk_apply_operator", "psk_max_abs",
     "psk_ssprk33_stage", "psk_step_control", "psk_solve_rows", "psk_dfma_probe", "psk_apply_operator_vjp",
     "psk_ssprk33_stage_adjoint", "psk_p2p_alloc", "psk_p2p_free", "psk_p2p_open", "psk_p2p_close",
-    "psk_halo_push", "psk_halo_wait",
+    "psk_halo_push", "psk_halo_wait", "psk_ssprk33_stage_p2p",
 )
 
 

@@ -451,26 +451,31 @@ __device__ __forceinline__ LeanFace lean_face(double hG, double urj, double ulp,
   return o;
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB)
-adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
+// own cells of a lane: state, cotangent, linear part of the result; plus the one cell the
+// two edge lanes need beyond the shuffled halo (lane 0: cell c0 - 1, lane 31: cell c0 + R)
+struct LeanIn {
+  double w[4], v[4], lin[4];
+  double extra;
+};
+
+__device__ __forceinline__ void lean_lin(const AdjParams &p, LeanIn &in, const double2 &r0, const double2 &r1,
+                                         const double2 &a0, const double2 &a1, const double2 &b0,
+                                         const double2 &b1) {
+  in.v[0] = r0.x; in.v[1] = r0.y; in.v[2] = r1.x; in.v[3] = r1.y;
+  in.lin[0] = fma(p.c_acc2, b0.x, fma(p.c_acc, a0.x, p.c_v * r0.x));
+  in.lin[1] = fma(p.c_acc2, b0.y, fma(p.c_acc, a0.y, p.c_v * r0.y));
+  in.lin[2] = fma(p.c_acc2, b1.x, fma(p.c_acc, a1.x, p.c_v * r1.x));
+  in.lin[3] = fma(p.c_acc2, b1.y, fma(p.c_acc, a1.y, p.c_v * r1.y));
+}
+
+// synchronous loads (all issued before the first use)
+__device__ __forceinline__ void lean_load(const AdjParams &p, int row, int c0, int lane, bool inside,
+                                          LeanIn &in) {
   constexpr int R = 4;
-  constexpr unsigned kFull = 0xffffffffu;
-  constexpr int kOut = 30 * R;
-  const int lane = threadIdx.x & 31;
-  const int chunk = static_cast<int>(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) - 1;
-  if (chunk >= chunks_per_row) return;
-  const int row = blockIdx.y + blockIdx.z * gridDim.y;
-  const int g = p.bc.g, n = p.bc.n, nx = p.bc.nx;
-  const int c0 = chunk * kOut - R + R * lane;  // interior coordinates; array index = g + c0
+  const int g = p.bc.g, nx = p.bc.nx;
   const int64_t base = static_cast<int64_t>(row) * p.ld;
   const int64_t off = base + g + c0;
-  const bool inside = (c0 >= 0) && (c0 + R <= n);
   const double *__restrict__ xrow = p.x + base;
-  const double *__restrict__ vrow = p.v + base;
-
-  // ---- all loads first: state window, cotangent window, linear terms
-  double w[R + 6], vc[R + 2], lin[R];
   if (inside) {
     const double2 q0 = *reinterpret_cast<const double2 *>(p.x + off);
     const double2 q1 = *reinterpret_cast<const double2 *>(p.x + off + 2);
@@ -485,36 +490,49 @@ adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
       b0 = *reinterpret_cast<const double2 *>(p.acc2 + off);
       b1 = *reinterpret_cast<const double2 *>(p.acc2 + off + 2);
     }
-    w[3] = q0.x; w[4] = q0.y; w[5] = q1.x; w[6] = q1.y;
-    vc[1] = r0.x; vc[2] = r0.y; vc[3] = r1.x; vc[4] = r1.y;
-    lin[0] = fma(p.c_acc2, b0.x, fma(p.c_acc, a0.x, p.c_v * r0.x));
-    lin[1] = fma(p.c_acc2, b0.y, fma(p.c_acc, a0.y, p.c_v * r0.y));
-    lin[2] = fma(p.c_acc2, b1.x, fma(p.c_acc, a1.x, p.c_v * r1.x));
-    lin[3] = fma(p.c_acc2, b1.y, fma(p.c_acc, a1.y, p.c_v * r1.y));
+    in.w[0] = q0.x; in.w[1] = q0.y; in.w[2] = q1.x; in.w[3] = q1.y;
+    lean_lin(p, in, r0, r1, a0, a1, b0, b1);
   } else {
+    const double *__restrict__ vrow = p.v + base;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int i = g + c0 + r;
       const bool in_row = (i >= 0 && i < nx);
-      w[3 + r] = load_w(p.bc, xrow, row, i);
-      vc[1 + r] = in_row ? vrow[i] : 0.0;
-      double l = p.c_v * vc[1 + r];
+      in.w[r] = load_w(p.bc, xrow, row, i);
+      in.v[r] = in_row ? vrow[i] : 0.0;
+      double l = p.c_v * in.v[r];
       if (in_row && p.acc != nullptr) l = fma(p.c_acc, p.acc[base + i], l);
       if (in_row && p.acc2 != nullptr) l = fma(p.c_acc2, p.acc2[base + i], l);
-      lin[r] = l;
+      in.lin[r] = l;
     }
   }
-  double extra = 0.0;  // lane 0: cell c0 - 1, lane 31: cell c0 + R
-  if (lane == 0) extra = load_w(p.bc, xrow, row, g + c0 - 1);
-  if (lane == 31) extra = load_w(p.bc, xrow, row, g + c0 + R);
+  in.extra = 0.0;
+  if (lane == 0) in.extra = load_w(p.bc, xrow, row, g + c0 - 1);
+  if (lane == 31) in.extra = load_w(p.bc, xrow, row, g + c0 + R);
+}
+
+// everything after the loads: window exchange, forward states, faces, VJPs, spill exchange, store
+__device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, int c0, int lane, bool inside,
+                                                   const LeanIn &in) {
+  constexpr int R = 4;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int g = p.bc.g, n = p.bc.n, nx = p.bc.nx;
+  const int64_t base = static_cast<int64_t>(row) * p.ld;
+  const int64_t off = base + g + c0;
   const double cgdt = p.c_g * (p.dt != nullptr ? p.dt[static_cast<int64_t>(row) * p.dt_stride] : 1.0);
 
+  double w[R + 6], vc[R + 2];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    w[3 + r] = in.w[r];
+    vc[1 + r] = in.v[r];
+  }
   w[1] = __shfl_up_sync(kFull, w[5], 1);
   w[2] = __shfl_up_sync(kFull, w[6], 1);
   w[7] = __shfl_down_sync(kFull, w[3], 1);
   w[8] = __shfl_down_sync(kFull, w[4], 1);
-  if (lane == 0) w[2] = extra;
-  if (lane == 31) w[7] = extra;
+  if (lane == 0) w[2] = in.extra;
+  if (lane == 31) w[7] = in.extra;
   vc[0] = __shfl_up_sync(kFull, vc[R], 1);
   vc[R + 1] = __shfl_down_sync(kFull, vc[1], 1);
 
@@ -584,8 +602,8 @@ adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
     for (int r = 0; r < R; ++r) gi[r] = fma(1.0 / 6.0, Tk[r + 1] - Tk[r + 2], o[r]);
     if (inside) {
       // inside => interior cells only (no ghost among them)
-      *reinterpret_cast<double2 *>(p.out + off) = make_double2(lin[0] + gi[0], lin[1] + gi[1]);
-      *reinterpret_cast<double2 *>(p.out + off + 2) = make_double2(lin[2] + gi[2], lin[3] + gi[3]);
+      *reinterpret_cast<double2 *>(p.out + off) = make_double2(in.lin[0] + gi[0], in.lin[1] + gi[1]);
+      *reinterpret_cast<double2 *>(p.out + off + 2) = make_double2(in.lin[2] + gi[2], in.lin[3] + gi[3]);
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -595,14 +613,29 @@ adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
         if (ghost) {
           // ghost cells of x do not influence L; what landed on them goes back through the
           // transpose of apply_boundary (already scaled by c_g dt: p.prescaled)
-          p.out[base + i] = lin[r];
+          p.out[base + i] = in.lin[r];
           p.gspill[static_cast<int64_t>(row) * 2 * g + (i < g ? i : i - n)] = gi[r];
         } else {
-          p.out[base + i] = lin[r] + gi[r];
+          p.out[base + i] = in.lin[r] + gi[r];
         }
       }
     }
   }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
+  constexpr int R = 4;
+  const int lane = threadIdx.x & 31;
+  const int chunk = static_cast<int>(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) - 1;
+  if (chunk >= chunks_per_row) return;
+  const int row = blockIdx.y + blockIdx.z * gridDim.y;
+  const int c0 = chunk * 30 * R - R + R * lane;  // interior coordinates; array index = g + c0
+  const bool inside = (c0 >= 0) && (c0 + R <= p.bc.n);
+  LeanIn in;
+  lean_load(p, row, c0, lane, inside, in);
+  lean_compute_store(p, row, c0, lane, inside, in);
 }
 
 template <int MINB>

@@ -492,45 +492,56 @@ __device__ __forceinline__ double umax_abs(double a, double b) {
 #ifndef PSK_FAST_MIN_BLOCKS
 #define PSK_FAST_MIN_BLOCKS 4
 #endif
-template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
-__global__ void __launch_bounds__(256, PSK_FAST_MIN_BLOCKS)
-stage_warp_fast_kernel(const FastParams p) {
-  constexpr int R = 4;
-  constexpr unsigned kFull = 0xffffffffu;
-  constexpr int kOut = 30 * R;
-  const int lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (chunk >= p.chunks_per_row) return;
-  const int row = blockIdx.y + blockIdx.z * gridDim.y;
-  const int g = p.bc.g, n = p.bc.n;
-  const int c0 = chunk * kOut - R + R * lane;
-  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
-  const bool inside = (c0 >= 0) && (c0 + R <= n);
-  const bool emit = (lane >= 1) && (lane <= 30);
+// own cells of a lane: stage input and (stages 2, 3) the step's initial state
+struct FastIn {
+  double v[4], u0[4];
+};
 
-  double v[R + 2 * kHalo];
+template <int STAGE>
+__device__ __forceinline__ void fast_load(const FastParams &p, int row, int c0, int lane, bool inside,
+                                          FastIn &in) {
+  constexpr int R = 4;
+  const int g = p.bc.g, n = p.bc.n;
+  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
+  const bool emit = (lane >= 1) && (lane <= 30);
   if (inside) {
     const double2 q0 = *reinterpret_cast<const double2 *>(p.uin + off);
     const double2 q1 = *reinterpret_cast<const double2 *>(p.uin + off + 2);
-    v[3] = q0.x; v[4] = q0.y; v[5] = q1.x; v[6] = q1.y;
+    in.v[0] = q0.x; in.v[1] = q0.y; in.v[2] = q1.x; in.v[3] = q1.y;
   } else {
     const double *__restrict__ urow = p.uin + static_cast<int64_t>(row) * p.ld;
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[kHalo + r] = load_w(p.bc, urow, row, g + c0 + r);
+    for (int r = 0; r < R; ++r) in.v[r] = load_w(p.bc, urow, row, g + c0 + r);
   }
-  double u0v[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) u0v[r] = 0.0;
+  for (int r = 0; r < R; ++r) in.u0[r] = 0.0;
   if (STAGE >= 2 && emit) {
     if (inside) {
       const double2 q0 = *reinterpret_cast<const double2 *>(p.u0 + off);
       const double2 q1 = *reinterpret_cast<const double2 *>(p.u0 + off + 2);
-      u0v[0] = q0.x; u0v[1] = q0.y; u0v[2] = q1.x; u0v[3] = q1.y;
+      in.u0[0] = q0.x; in.u0[1] = q0.y; in.u0[2] = q1.x; in.u0[3] = q1.y;
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r)
-        if (c0 + r >= 0 && c0 + r < n) u0v[r] = p.u0[off + r];
+        if (c0 + r >= 0 && c0 + r < n) in.u0[r] = p.u0[off + r];
     }
+  }
+}
+
+template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
+__device__ __forceinline__ void fast_compute_store(const FastParams &p, int row, int c0, int lane, bool inside,
+                                                   const FastIn &in, double (&out)[4]) {
+  constexpr int R = 4;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int g = p.bc.g, n = p.bc.n;
+  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
+  const bool emit = (lane >= 1) && (lane <= 30);
+  double v[R + 2 * kHalo];
+  double u0v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    v[kHalo + r] = in.v[r];
+    u0v[r] = in.u0[r];
   }
   v[0] = __shfl_up_sync(kFull, v[4], 1);
   v[1] = __shfl_up_sync(kFull, v[5], 1);
@@ -586,7 +597,6 @@ stage_warp_fast_kernel(const FastParams p) {
 
   double coef = p.coef;
   if (STAGE != 0) coef *= p.dt[static_cast<int64_t>(row) * p.dt_stride];
-  double out[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     double dF = F[r] - F[r + 1];
@@ -621,6 +631,113 @@ stage_warp_fast_kernel(const FastParams p) {
     }
     mx = warp_max_bits(mx);
     if (lane == 0) atomicMax(p.maxabs + row, mx);
+  }
+}
+
+template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
+__global__ void __launch_bounds__(256, PSK_FAST_MIN_BLOCKS)
+stage_warp_fast_kernel(const FastParams p) {
+  constexpr int R = 4;
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chunk >= p.chunks_per_row) return;
+  const int row = blockIdx.y + blockIdx.z * gridDim.y;
+  const int c0 = chunk * 30 * R - R + R * lane;
+  const bool inside = (c0 >= 0) && (c0 + R <= p.bc.n);
+  FastIn in;
+  double out[4];
+  fast_load<STAGE>(p, row, c0, lane, inside, in);
+  fast_compute_store<EQ, FLUX, STAGE, WITH_MAX>(p, row, c0, lane, inside, in, out);
+}
+
+// ---------------------------------------------------------------------------
+// The specialised stage kernel FUSED with the ghost-cell exchange of a slab-decomposed grid
+// (one row per GPU, boundary kind NONE, Burgers + Rusanov): one launch per stage and no other
+// kernel, stream or event on the exchange path.
+//   * the warps whose windows reach into the ghost cells (chunk 0; the chunks covering cells
+//     >= n - 4) spin on the LOCAL epoch flags their neighbours raise -- every other warp of the
+//     grid starts at once, so the NVLink latency hides behind the interior of the same launch;
+//   * ghost cells are read with ld.volatile (they were written by another GPU while this
+//     kernel may already have been running);
+//   * the lane that stores cells 0..2 also stores them into the LEFT neighbour's right ghost
+//     slots, the lane that stores cells n-3..n-1 into the RIGHT neighbour's left ghost slots
+//     (peer pointers over NVLink), each followed by __threadfence_system() and a release store
+//     of epoch + 1 to that neighbour's flag.
+// A neighbour's ghost slots of `uout` are free to be overwritten: it last read them two
+// stages ago, and this warp has just seen its push of the previous stage.
+struct HaloLink {
+  const long long *wait_lo, *wait_hi;
+  long long wait_epoch;
+  double *peer_lo, *peer_hi;
+  long long *flag_lo, *flag_hi;
+  unsigned long long timeout_ns;
+  int *timed_out;
+};
+
+__device__ __forceinline__ void halo_spin(const long long *flag, long long epoch, unsigned long long timeout_ns,
+                                          int *timed_out) {
+  unsigned long long t0 = 0ull;
+  bool timing = false;
+  while (true) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= epoch) return;
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (!timing) {
+      t0 = now;
+      timing = true;
+    } else if (now - t0 > timeout_ns) {
+      if (timed_out != nullptr) atomicExch(timed_out, 1);
+      return;
+    }
+    __nanosleep(32);
+  }
+}
+
+template <int STAGE, bool WITH_MAX>
+__global__ void __launch_bounds__(256, PSK_FAST_MIN_BLOCKS)
+stage_warp_fast_p2p_kernel(const FastParams p, const HaloLink h) {
+  constexpr int R = 4;
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chunk >= p.chunks_per_row) return;
+  const int g = p.bc.g, n = p.bc.n, nx = p.bc.nx;
+  const int c0 = chunk * 30 * R - R + R * lane;
+  const bool inside = (c0 >= 0) && (c0 + R <= n);
+  const bool emit = (lane >= 1) && (lane <= 30);
+  if (chunk == 0 && h.wait_lo != nullptr) halo_spin(h.wait_lo, h.wait_epoch, h.timeout_ns, h.timed_out);
+  if (chunk * 30 * R + 31 * R > n && h.wait_hi != nullptr) halo_spin(h.wait_hi, h.wait_epoch, h.timeout_ns, h.timed_out);
+  FastIn in;
+  if (inside) {
+    fast_load<STAGE>(p, 0, c0, lane, true, in);
+  } else {
+    const volatile double *urow = p.uin;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = g + c0 + r;
+      in.v[r] = (i >= 0 && i < nx) ? urow[i] : 0.0;
+      in.u0[r] = 0.0;
+      if (STAGE >= 2 && emit && c0 + r >= 0 && c0 + r < n) in.u0[r] = p.u0[i];
+    }
+  }
+  double out[4];
+  fast_compute_store<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV, STAGE, WITH_MAX>(p, 0, c0, lane, inside, in, out);
+  if (emit && inside) {
+    if (c0 == 0 && h.peer_lo != nullptr) {
+      h.peer_lo[0] = out[0];
+      h.peer_lo[1] = out[1];
+      h.peer_lo[2] = out[2];
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_lo), "l"(h.wait_epoch + 1) : "memory");
+    }
+    if (c0 == n - R && h.peer_hi != nullptr) {
+      h.peer_hi[0] = out[1];
+      h.peer_hi[1] = out[2];
+      h.peer_hi[2] = out[3];
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_hi), "l"(h.wait_epoch + 1) : "memory");
+    }
   }
 }
 
@@ -1183,6 +1300,65 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
   p.stage = stage;
   return d->math == PSK_MATH_STRICT ? dispatch_scheme<true>(d, p, ghost_rows, st)
                                     : dispatch_scheme<false>(d, p, ghost_rows, st);
+}
+
+int psk_ssprk33_stage_p2p(const psk_desc *d, int stage, const double *u0, const double *uin,
+                          double *uout, const double *dt, double *maxabs, const psk_halo_link *link,
+                          psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (link == nullptr || stage < 1 || stage > 3 || uin == nullptr || uout == nullptr || dt == nullptr)
+    return PSK_E_INVALID;
+  if (stage >= 2 && u0 == nullptr) return PSK_E_INVALID;
+  if (uout == uin || link->timeout_ns <= 0) return PSK_E_INVALID;
+  if ((link->peer_lo != nullptr && link->flag_lo == nullptr) || (link->peer_hi != nullptr && link->flag_hi == nullptr))
+    return PSK_E_INVALID;
+  // the fused form exists for the hot configuration only; callers fall back to
+  // psk_halo_wait -> psk_ssprk33_stage -> psk_halo_push otherwise
+  const bool aligned = (reinterpret_cast<uintptr_t>(uin + d->g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0) &&
+                       (u0 == nullptr || reinterpret_cast<uintptr_t>(u0 + d->g) % 16 == 0);
+  if (d->equation != PSK_EQ_BURGERS || d->flux != PSK_FLUX_RUSANOV || d->rec != PSK_REC_WENOJS53 ||
+      d->math != PSK_MATH_FAST || d->bc != PSK_BC_NONE || d->batch != 1 || d->g != 3 || d->nu != nullptr ||
+      d->n % 4 != 0 || d->n < 8 || !aligned)
+    return PSK_E_UNSUPPORTED;
+  FastParams q{};
+  q.uin = uin; q.u0 = u0; q.uout = uout; q.dt = dt;
+  q.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
+  q.bc = make_bc_view(d);
+  q.ld = d->ld;
+  q.coef = (1.0 / d->dx) / FluxScale<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV>::value;
+  q.eps9 = d->eps * (1.0 / 9.0);
+  q.dt_stride = 0;
+  q.chunks_per_row = (d->n + 119) / 120;
+  HaloLink h{};
+  h.wait_lo = reinterpret_cast<const long long *>(link->wait_lo);
+  h.wait_hi = reinterpret_cast<const long long *>(link->wait_hi);
+  h.wait_epoch = link->wait_epoch;
+  h.peer_lo = link->peer_lo;
+  h.peer_hi = link->peer_hi;
+  h.flag_lo = reinterpret_cast<long long *>(link->flag_lo);
+  h.flag_hi = reinterpret_cast<long long *>(link->flag_hi);
+  h.timeout_ns = static_cast<unsigned long long>(link->timeout_ns);
+  h.timed_out = link->timed_out;
+  // 5 warps per CTA: 6 CTAs (30 warps) per SM at 64 registers, the shape the plain launcher
+  // picks for long single rows
+  const int wpc = q.chunks_per_row < 5 ? q.chunks_per_row : 5;
+  const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define PSK_P2P_LAUNCH(STAGE)                                                        \
+  if (maxabs != nullptr)                                                             \
+    stage_warp_fast_p2p_kernel<STAGE, true><<<gx, wpc * 32, 0, st>>>(q, h);          \
+  else                                                                               \
+    stage_warp_fast_p2p_kernel<STAGE, false><<<gx, wpc * 32, 0, st>>>(q, h)
+  switch (stage) {
+    case 1: PSK_P2P_LAUNCH(1); break;
+    case 2: PSK_P2P_LAUNCH(2); break;
+    default: PSK_P2P_LAUNCH(3);
+  }
+#undef PSK_P2P_LAUNCH
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
 }
 
 int psk_apply_operator(const psk_desc *d, const double *u, double *rhs, double *lf_work,

@@ -351,6 +351,11 @@ class PeerSlabSolver:
     * **main stream**: stage kernel on the interior ``[edge, n - edge)``, which depends only on
       local data of the previous stage, so the NVLink round trip hides behind it.
 
+    ``fused=True`` (default whenever the configuration allows it): none of the above -- ONE launch
+    per stage (``psk_ssprk33_stage_p2p``); inside the kernel only the warps that read ghost cells
+    wait for the neighbours' flags, and the lanes that produce the slab's outermost cells store
+    them into the neighbours' ghost slots and raise their flags.
+
     Events order edge(s) after interior(s - 1) and interior(s) after edge(s - 1); the time loop
     never touches the host.  A slab too short to split runs wait -> stage -> push on one stream.
     The arithmetic per cell is the same kernel on the same neighbours, so the result is
@@ -358,7 +363,7 @@ class PeerSlabSolver:
 
     def __init__(self, *, n_global: int, rank: int, world: int, dx: float, flux: str = "rusanov",
                  rec: str = "wenojs53", eps: float = 1.0e-12, math: str = "fast", edge: int = 7680,
-                 overlap: bool = True, device: torch.device | str | None = None,
+                 overlap: bool = True, fused: bool | None = None, device: torch.device | str | None = None,
                  timeout_s: float = 20.0) -> None:
         self.rank, self.world = rank, world
         self.first, self.n_local = shard_rows(n_global, rank, world)
@@ -369,8 +374,15 @@ class PeerSlabSolver:
         self.mem = PeerSlabMemory(self.n_local, g, dev)
         kw = dict(equation="burgers", flux=flux, rec=rec, bc="none", g=g, dx=dx, eps=eps, math=math, device=dev)
         self.solver = EnsembleSolver(n=self.n_local, batch=1, store=self.mem.store, **kw)
+        # fused: the exchange lives inside the stage kernel (psk_ssprk33_stage_p2p), one launch per
+        # stage; available for the hot configuration only
+        can_fuse = (flux == "rusanov" and rec == "wenojs53" and math == "fast" and self.n_local % 4 == 0
+                    and self.n_local >= 8)
+        if fused and not can_fuse:
+            raise ValueError("the fused exchange needs rusanov + wenojs53 + fast math and n_local % 4 == 0")
+        self.fused = can_fuse if fused is None else bool(fused)
         edge = (int(edge) // 16) * 16
-        self.split = bool(overlap) and edge >= 16 and self.n_local >= 4 * edge
+        self.split = (not self.fused) and bool(overlap) and edge >= 16 and self.n_local >= 4 * edge
         self.edge = edge if self.split else 0
         if self.split:
             self.hp_edge = HotPath(n=self.edge, **kw)
@@ -450,9 +462,31 @@ class PeerSlabSolver:
     def _sub(self, a: torch.Tensor, start: int, n: int) -> torch.Tensor:
         return a[:, start : start + n + 2 * self.g]
 
+    def _stage_fused(self, stage: int, u0: torch.Tensor, uin: torch.Tensor, uout: torch.Tensor, a_out: int,
+                     dt: torch.Tensor, maxabs: torch.Tensor | None) -> None:
+        import ctypes as ct
+
+        r, hp = self.ring, self.solver.hp
+        link = L.PskHaloLink()
+        link.wait_lo, link.wait_hi, link.wait_epoch = r.my_flags[0], r.my_flags[1], self.epoch
+        link.peer_lo, link.peer_hi = r.dst_lo[a_out], r.dst_hi[a_out]
+        link.flag_lo, link.flag_hi = r.flag_lo, r.flag_hi
+        link.timeout_ns, link.timed_out = self.timeout_ns, L.raw_ptr(self.timed_out)
+        batch, ld = hp._state(uin)
+        d = hp.desc(batch, ld)
+        L.check("psk_ssprk33_stage_p2p", L.lib().psk_ssprk33_stage_p2p(
+            ct.byref(d), stage, L.ptr(u0), L.ptr(uin), L.ptr(uout), L.ptr(dt), L.ptr(maxabs), ct.byref(link),
+            L.stream_ptr()))
+        self.epoch += 1
+        self.exchanges += 1
+        self.launches += 1
+
     def _stage(self, stage: int, u0: torch.Tensor, uin: torch.Tensor, uout: torch.Tensor, a_out: int,
                dt: torch.Tensor, maxabs: torch.Tensor | None) -> None:
         s = self.solver
+        if self.fused:
+            self._stage_fused(stage, u0, uin, uout, a_out, dt, maxabs)
+            return
         if not self.split:
             self._wait()
             s.hp.stage(stage, u0, uin, uout, dt, maxabs=maxabs)

@@ -64,21 +64,23 @@ def test_local_slabs_equal_undecomposed(world: int, math: str) -> None:
     assert torch.equal(out, ref)
 
 
-@pytest.mark.parametrize("overlap", [False, True])
+@pytest.mark.parametrize("mode", ["serial", "overlap", "fused"])
 @pytest.mark.parametrize("world", [1, 2, 3])
-def test_peer_memory_slabs_equal_undecomposed(world: int, overlap: bool) -> None:
-    """The peer-memory protocol (psk_halo_push / psk_halo_wait, epoch flags, edge stream +
-    interior stream) with every slab held by this process: bit-identical to the periodic solve."""
+def test_peer_memory_slabs_equal_undecomposed(world: int, mode: str) -> None:
+    """The peer-memory protocol with every slab held by this process: bit-identical to the
+    periodic solve.  serial: psk_halo_wait -> stage -> psk_halo_push; overlap: slab edges on a
+    second stream; fused: the exchange inside the stage kernel (psk_ssprk33_stage_p2p)."""
     from pyshocks_b200.distributed import PeerRing, PeerSlabSolver
 
-    n, g, nsteps = 6151, 3, 9
+    n, g, nsteps = (6144 if mode == "fused" else 6151), 3, 9
     dt = 0.4 * (3.0 / n) / 1.8
     ref = _reference_periodic(n, dt, nsteps, "fast")
     ug = torch.from_numpy(_ic(n, g)).cuda()
-    slabs = [PeerSlabSolver(n_global=n, rank=r, world=world, dx=3.0 / n, edge=256, overlap=overlap, timeout_s=5.0)
+    slabs = [PeerSlabSolver(n_global=n, rank=r, world=world, dx=3.0 / n, edge=256, overlap=(mode == "overlap"),
+                            fused=(mode == "fused"), timeout_s=5.0)
              for r in range(world)]
     try:
-        assert all(s.split == overlap for s in slabs)
+        assert all(s.split == (mode == "overlap") and s.fused == (mode == "fused") for s in slabs)
         for r, s in enumerate(slabs):
             s.attach(PeerRing.local([t.mem for t in slabs], r))
         for s in slabs:
@@ -122,7 +124,7 @@ def test_peer_memory_adaptive_single_slab(math: str) -> None:
         ps.attach(PeerRing.local([ps.mem], 0))
         ps.load_interior(ug)
         pres = ps.solve_adaptive(**akw)
-        assert ps.split and pres.steps == sres.steps
+        assert ps.fused == (math == "fast") and ps.split == (math == "strict") and pres.steps == sres.steps
         assert float(ps.solver.t[0]) == float(single.t[0])
         diff = float((ps.interior() - single.u[0, g : g + n]).abs().max())
         assert diff == 0.0 if math == "strict" else diff <= 1e-13
@@ -184,16 +186,17 @@ def _nccl_worker(rank: int, world: int, port: int, out: dict) -> None:
         ok = torch.equal(slab.interior(), ref[slab.first : slab.first + slab.n_local])
 
         # peer-memory transport (CUDA IPC over NVLink), with and without the edge / interior overlap
-        for overlap in (False, True):
-            ps = PeerSlabSolver(n_global=n, rank=rank, world=world, dx=3.0 / n, edge=1024, overlap=overlap)
+        for mode in ("serial", "overlap", "fused"):
+            ps = PeerSlabSolver(n_global=n, rank=rank, world=world, dx=3.0 / n, edge=1024, overlap=(mode == "overlap"),
+                                fused=(mode == "fused"))
             ps.connect()
             ps.load_interior(ug[ps.first : ps.first + ps.n_local])
             ps.solve_fixed_dt(dt, nsteps)
             ps.check()
             ok = ok and torch.equal(ps.interior(), ref[ps.first : ps.first + ps.n_local])
-            ok = ok and ps.split == overlap
+            ok = ok and ps.split == (mode == "overlap") and ps.fused == (mode == "fused")
             ps.close()
-            mark(f"peer slabs overlap={overlap} ok={ok}")
+            mark(f"peer slabs {mode} ok={ok}")
         # adaptive dt: every rank takes the same dt sequence as the single-GPU adaptive solve.  The
         # single-array solver runs the general kernel (row mask), the slabs the specialised one: two FAST
         # implementations agree to a few ulp per step, the STRICT ones bit for bit; the two slab

@@ -4,11 +4,12 @@ import numpy as np, torch
 sys.path.insert(0, "/root/repo")
 from pyshocks_b200.ensemble import EnsembleSolver
 
-def run(batch, n, steps, math="fast"):
+def run(batch, n, steps, math="fast", tag=""):
     h = 3.0 / n
     s = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=3, dx=h, eps=1e-12, batch=batch, math=math)
     x = torch.linspace(0, 1, s.nx, device="cuda", dtype=torch.float64)
-    u0 = 0.5 + torch.sin(2 * np.pi * x)[None, :] * torch.rand(batch, 1, device="cuda", dtype=torch.float64)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(1)
+    u0 = 0.5 + torch.sin(2 * np.pi * x)[None, :] * torch.rand(batch, 1, device="cuda", dtype=torch.float64, generator=gen)
     s.load(u0)
     dt = 0.4 * h / 1.5
     s.solve_fixed_dt(None, dt, 3)
@@ -17,10 +18,12 @@ def run(batch, n, steps, math="fast"):
     e0.record(); s.solve_fixed_dt(None, dt, steps); e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     cu = batch * n * steps / (ms * 1e-3)
-    print(json.dumps({"batch": batch, "n": n, "steps": steps, "math": math, "ms_per_step": ms / steps, "cell_updates_per_s": cu, "hbm_frac_64B": cu * 64 / 6547.2e9}))
+    print(json.dumps({"tag": tag, "batch": batch, "n": n, "steps": steps, "ms_per_step": ms / steps, "cell_updates_per_s": cu, "hbm_frac_64B": cu * 64 / 6547.2e9}))
+    return s.u.clone()
 
 from pyshocks_b200 import _lib
-for wmax in (8, 6, 5, 4):
-    _lib.lib().psk_set_stage_variant(4000 + wmax)
-    print("max warps per CTA", wmax)
-    run(65536, 4096, 20)
+a = run(65536, 4096, 20, tag="one chunk per warp")
+_lib.lib().psk_set_stage_variant(5001)
+b = run(65536, 4096, 20, tag="persistent + cp.async prefetch")
+print("bitwise equal:", torch.equal(a, b))
+_lib.lib().psk_set_stage_variant(5000)

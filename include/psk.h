@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PSK_VERSION 100 /* 0.1.0 */
+#define PSK_VERSION 101 /* 0.1.1 */
 
 typedef void *psk_stream_t; /* cudaStream_t */
 
@@ -55,11 +55,16 @@ enum psk_flux {
   PSK_FLUX_RUSANOV = 0,
   PSK_FLUX_LAX_FRIEDRICHS = 1,
   PSK_FLUX_UPWIND = 2,
-  PSK_FLUX_ENGQUIST_OSHER = 3
+  PSK_FLUX_ENGQUIST_OSHER = 3,
+  /* Burgers ESWENO32 scheme (burgers/schemes.py:205-256, "esweno32"): the UPWIND flux plus the
+   * dissipative flux built from the ESWENO weights; needs PSK_REC_ESWENO32 */
+  PSK_FLUX_ESWENO = 4
 };
 
-/* reconstruction.py:127-163 (constant), :319-348 (WENOJS32 / WENOJS53) */
-enum psk_rec { PSK_REC_CONSTANT = 0, PSK_REC_WENOJS32 = 1, PSK_REC_WENOJS53 = 2 };
+/* reconstruction.py:127-163 (constant), :319-348 (WENOJS32 / WENOJS53), :386-439 (ESWENO32:
+ * the JS-3 stencils with the weights of weno.py:284-296; desc.eps and desc.delta carry its
+ * parameters, weno.py:263-281) */
+enum psk_rec { PSK_REC_CONSTANT = 0, PSK_REC_WENOJS32 = 1, PSK_REC_WENOJS53 = 2, PSK_REC_ESWENO32 = 3 };
 
 /* ghost-cell fill applied at the top of every RHS (schemes.py:343)
  *   PERIODIC  scalar.py:529-540
@@ -97,6 +102,7 @@ typedef struct psk_desc {
   const double *vel_r;    /* nx, right values of reconstruct(velocity)  ("ar")   */
   const double *ghost;    /* DIRICHLET / NEUMANN data, 2 g doubles per row       */
   int64_t ghost_ld;       /* row stride of ghost in doubles; 0 = shared          */
+  double delta;           /* ESWENO32 delta (reconstruction.py:396; burgers/schemes.py:241) */
 } psk_desc;
 
 int psk_version(void);

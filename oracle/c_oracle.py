@@ -16,8 +16,8 @@ HERE = pathlib.Path(__file__).resolve().parent
 LIB = HERE / "libpsk_oracle.so"
 
 EQUATION = {"burgers": 0, "advection": 1, "continuity": 2}
-FLUX = {"rusanov": 0, "lf": 1, "godunov": 2, "eo": 3}
-REC = {"constant": 0, "wenojs32": 1, "wenojs53": 2}
+FLUX = {"rusanov": 0, "lf": 1, "godunov": 2, "eo": 3, "esweno32": 4}
+REC = {"constant": 0, "wenojs32": 1, "wenojs53": 2, "esweno32": 3}
 BC = {"periodic": 0, "dirichlet": 1, "neumann": 2, "none": 3}
 
 _dp = ct.POINTER(ct.c_double)
@@ -42,6 +42,7 @@ class Desc(ct.Structure):
         ("vel_r", _dp),
         ("ghost", _dp),
         ("ghost_ld", ct.c_int64),
+        ("delta", ct.c_double),
     ]
 
 
@@ -88,6 +89,7 @@ class COracle:
         batch: int,
         dx: float,
         eps: float,
+        delta: float = 0.0,
         nu: np.ndarray | None = None,
         velocity: np.ndarray | None = None,
     ) -> None:
@@ -98,7 +100,7 @@ class COracle:
         d.equation, d.flux, d.rec, d.bc = EQUATION[equation], FLUX[flux], REC[rec], BC[bc]
         d.math = 1
         d.n, d.g, d.batch, d.ld = n, g, batch, self.nx
-        d.dx, d.eps = dx, eps
+        d.dx, d.eps, d.delta = dx, eps, delta
         d.nu = _p(self.keep["nu"])
         self.d = d
         if velocity is not None:

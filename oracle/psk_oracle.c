@@ -82,6 +82,25 @@ static double weno32_side(double m1, double c, double p1, double eps) {
   return (al0 / tot) * q0 + (al1 / tot) * q1;
 }
 
+/* ESWENO32 (weno.py:284-296 on the JS-3 stencils): alpha_k = d_k (1 + tau / (eps + beta_k)),
+   tau = (u[i+1] - 2 u[i] + u[i-1])^2, zero at the two ends of the array (jnp.pad).
+   Returns the right-face value; *om0 (optional) receives omega_0 (weno.py:296, row 0). */
+static double esweno32_side(double m1, double c, double p1, double eps, int tau_zero, double *om0) {
+  double c0 = m1 * -1.0 + c * 1.0;
+  double c1 = (m1 * 0.0 + c * -1.0) + p1 * 1.0;
+  double b0 = 1.0 * (c0 * c0);
+  double b1 = 1.0 * (c1 * c1);
+  double q0 = m1 * (-1.0 / 2.0) + c * (3.0 / 2.0);
+  double q1 = (m1 * 0.0 + c * (1.0 / 2.0)) + p1 * (1.0 / 2.0);
+  double tt = (p1 - 2.0 * c) + m1; /* u[2:] - 2 * u[1:-1] + u[:-2] */
+  double tau = tau_zero ? 0.0 : tt * tt;
+  double al0 = (1.0 / 3.0) * (1.0 + tau / (eps + b0));
+  double al1 = (2.0 / 3.0) * (1.0 + tau / (eps + b1));
+  double tot = al0 + al1;
+  if (om0) *om0 = al0 / tot;
+  return (al0 / tot) * q0 + (al1 / tot) * q1;
+}
+
 /* (fl[i], fr[i]) of reconstruct() at cell i of a zero-padded array
    (reconstruction.py:153-163, :358-377: left value = right value of the reversed array) */
 static void reconstruct_cell(int rec, double eps, const double *w, int i, int nx, double *fl,
@@ -89,6 +108,12 @@ static void reconstruct_cell(int rec, double eps, const double *w, int i, int nx
   if (rec == PSK_REC_CONSTANT) {
     *fl = w[i];
     *fr = w[i];
+  } else if (rec == PSK_REC_ESWENO32) {
+    /* reconstruction.py:436-437; on the reversed array tau reads (m1 - 2 c) + p1 */
+    double m1 = at0(w, i - 1, nx), c = w[i], p1 = at0(w, i + 1, nx);
+    int edge = (i == 0 || i == nx - 1);
+    *fr = esweno32_side(m1, c, p1, eps, edge, NULL);
+    *fl = esweno32_side(p1, c, m1, eps, edge, NULL);
   } else if (rec == PSK_REC_WENOJS32) {
     double m1 = at0(w, i - 1, nx), c = w[i], p1 = at0(w, i + 1, nx);
     *fr = weno32_side(m1, c, p1, eps);
@@ -176,10 +201,20 @@ static double face_flux(const psk_desc *d, const row_ctx *c, int j) {
       double nu = d->nu ? d->nu[j] : 1.0;
       return 0.5 * (fl + fr) - ((0.5 * a) * nu) * (ulp - urj);
     }
-    case PSK_FLUX_UPWIND: {
-      /* scalar.py:123-132 with a = u (burgers/schemes.py:89) */
+    case PSK_FLUX_UPWIND:
+    case PSK_FLUX_ESWENO: {
+      /* scalar.py:123-132 with a = u (burgers/schemes.py:89, :255) */
       double aavg = (urj + ulp) / 2.0;
-      return aavg > 0.0 ? burgers_flux(urj) : burgers_flux(ulp);
+      double fnum = aavg > 0.0 ? burgers_flux(urj) : burgers_flux(ulp);
+      if (d->flux == PSK_FLUX_UPWIND) return fnum;
+      /* burgers/schemes.py:237-256: omega_0 of cells j, j+1; mu (Equation 37 of Yamaleev2009) */
+      double omj, omp;
+      esweno32_side(at0(w, j - 1, c->nx), w[j], w[j + 1], d->eps, j == 0, &omj);
+      esweno32_side(w[j], w[j + 1], at0(w, j + 2, c->nx), d->eps, j + 1 == c->nx - 1, &omp);
+      double dom = omp - omj;
+      double mu = sqrt(dom * dom + d->delta * d->delta) / 8.0;
+      double gnum = (-(mu + dom / 8.0)) * (w[j + 1] - w[j]);
+      return fnum + gnum;
     }
     case PSK_FLUX_ENGQUIST_OSHER: {
       /* scalar.py:311-322 with omega = 0 (burgers/schemes.py:184) */

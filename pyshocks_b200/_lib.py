@@ -18,8 +18,8 @@ LIB_PATH = CSRC / "libpsk.so"
 
 # enum values of include/psk.h
 EQ_BURGERS, EQ_ADVECTION, EQ_CONTINUITY = 0, 1, 2
-FLUX_RUSANOV, FLUX_LAX_FRIEDRICHS, FLUX_UPWIND, FLUX_ENGQUIST_OSHER = 0, 1, 2, 3
-REC_CONSTANT, REC_WENOJS32, REC_WENOJS53 = 0, 1, 2
+FLUX_RUSANOV, FLUX_LAX_FRIEDRICHS, FLUX_UPWIND, FLUX_ENGQUIST_OSHER, FLUX_ESWENO = 0, 1, 2, 3, 4
+REC_CONSTANT, REC_WENOJS32, REC_WENOJS53, REC_ESWENO32 = 0, 1, 2, 3
 BC_PERIODIC, BC_DIRICHLET, BC_NEUMANN, BC_NONE = 0, 1, 2, 3
 MATH_FAST, MATH_STRICT = 0, 1
 
@@ -49,6 +49,7 @@ class PskDesc(ct.Structure):
         ("vel_r", _dp),
         ("ghost", _dp),
         ("ghost_ld", ct.c_int64),
+        ("delta", ct.c_double),
     ]
 
 

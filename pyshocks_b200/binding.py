@@ -116,8 +116,9 @@ def hotpath_for(scheme: SchemeBase, grid: Any, bc: Boundary, t: Any = None, *, m
             nu = np.diff(grid.x_host) ** (spec["alpha"] - 1)  # grid.df ** (alpha - 1), scalar.py:231-232
         hp = HotPath(
             equation=spec["equation"], flux=spec["flux"], rec=scheme.rec.name, bc=kind,
-            n=grid.x.shape[0] - 2 * grid.nghosts, g=grid.nghosts, dx=grid.h, eps=getattr(scheme.rec, "eps", 0.0),
+            n=grid.x.shape[0] - 2 * grid.nghosts, g=grid.nghosts, dx=grid.h, eps=float(getattr(scheme.rec, "eps", 0.0)),
             math=math, nu=nu, velocity=spec["velocity"], device=grid.x.device,
+            delta=float(getattr(scheme.rec, "delta", 0.0)),
         )
         cache[key] = hp
     if t is not None:

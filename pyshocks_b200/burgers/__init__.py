@@ -6,6 +6,7 @@ from dataclasses import fields
 from typing import Any
 
 from .schemes import (
+    ESWENO32,
     BurgersScheme,
     EngquistOsher,
     FiniteVolumeScheme,
@@ -20,6 +21,7 @@ _SCHEMES: dict[str, type[BurgersScheme]] = {
     "rusanov": Rusanov,
     "lf": LaxFriedrichs,
     "eo": EngquistOsher,
+    "esweno32": ESWENO32,
 }
 
 
@@ -35,6 +37,6 @@ def make_scheme_from_name(name: str, **kwargs: Any) -> BurgersScheme:
 
 
 __all__ = (
-    "BurgersScheme", "EngquistOsher", "FiniteVolumeScheme", "Godunov", "LaxFriedrichs", "Rusanov",
+    "ESWENO32", "BurgersScheme", "EngquistOsher", "FiniteVolumeScheme", "Godunov", "LaxFriedrichs", "Rusanov",
     "make_scheme_from_name", "scheme_ids",
 )

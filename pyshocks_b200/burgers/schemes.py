@@ -1,20 +1,22 @@
 """Finite-volume schemes for the inviscid Burgers equation
-(``pyshocks/burgers/schemes.py:30-196``): Godunov, Rusanov (LLF), LaxFriedrichs (global),
-EngquistOsher.  ESWENO32 / SSMUSCL / FluxSplitRusanov / SSWENO242 are different algorithms
+(``pyshocks/burgers/schemes.py:30-256``): Godunov, Rusanov (LLF), LaxFriedrichs (global),
+EngquistOsher, ESWENO32.  SSMUSCL / FluxSplitRusanov / SSWENO242 are different algorithms
 and outside the hot path."""
 
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass, field, replace
 from typing import Any
 
 import torch
 
+from .. import reconstruction
 from ..binding import hotpath_for, kernel_spec
 from ..schemes import (
     Boundary,
     ConservationLawScheme,
     SchemeBase,
+    bind,
     flux,
     numerical_flux,
     predict_timestep,
@@ -76,6 +78,30 @@ class EngquistOsher(FiniteVolumeScheme):
 def _predict_timestep_burgers_rusanov(scheme: Rusanov, grid: Any, bc: Boundary, t: ScalarLike, u: Array) -> Array:
     # burgers/schemes.py:121-127
     return 0.5 * grid.dx_min ** (2 - scheme.alpha) / _interior_speed(scheme, grid, bc, u)
+
+
+@dataclass(frozen=True, eq=False)
+class ESWENO32(FiniteVolumeScheme):
+    """Third-order Energy Stable WENO scheme (burgers/schemes.py:205-216): the upwind flux of
+    the ESWENO32 reconstruction plus the dissipative flux built from its weights."""
+
+    def __post_init__(self) -> None:
+        if not isinstance(self.rec, reconstruction.ESWENO32):
+            raise TypeError("ESWENO32 scheme requires the ESWENO32 reconstruction.")
+
+
+@bind.register(ESWENO32)
+def _bind_burgers_esweno32(scheme: ESWENO32, grid: Any, bc: Boundary) -> ESWENO32:
+    # burgers/schemes.py:219-227: the parameters recommended by Carpenter (u0 = 1)
+    from ..weno import es_weno_parameters
+
+    eps, delta = es_weno_parameters(grid, torch.ones_like(grid.x))
+    return replace(scheme, rec=replace(scheme.rec, eps=float(eps), delta=float(delta)))
+
+
+@kernel_spec.register(ESWENO32)
+def _spec_esweno32(scheme: ESWENO32) -> dict:
+    return {"equation": "burgers", "flux": "esweno32", "alpha": 1.0, "velocity": None}
 
 
 @kernel_spec.register(Godunov)

@@ -796,6 +796,8 @@ static int run_adjoint(const psk_desc *d, const double *x, const double *v, cons
   if (rc != PSK_OK) return rc;
   if (x == nullptr || v == nullptr || out == nullptr || work == nullptr) return PSK_E_INVALID;
   if (out == x || out == v) return PSK_E_INVALID;  // tiles read their neighbours' cells
+  // the adjoint drivers of the reference run WENO-JS schemes; no ESWENO32 transpose is built
+  if (d->rec == PSK_REC_ESWENO32 || d->flux == PSK_FLUX_ESWENO) return PSK_E_UNSUPPORTED;
   AdjParams p{};
   p.x = x;
   p.v = v;

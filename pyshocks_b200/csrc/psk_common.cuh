@@ -26,7 +26,7 @@ inline int cuda_fail(cudaError_t e) {
   } while (0)
 
 inline int rec_halo(int rec) {
-  return rec == PSK_REC_WENOJS53 ? 3 : (rec == PSK_REC_WENOJS32 ? 2 : 1);
+  return rec == PSK_REC_WENOJS53 ? 3 : ((rec == PSK_REC_WENOJS32 || rec == PSK_REC_ESWENO32) ? 2 : 1);
 }
 
 // Validates what every entry point relies on; returns PSK_OK or an error code.
@@ -35,8 +35,10 @@ inline int check_desc(const psk_desc *d) {
   if (d->n <= 0 || d->batch <= 0 || d->g < 0) return PSK_E_INVALID;
   if (d->ld < static_cast<int64_t>(d->n) + 2 * d->g) return PSK_E_INVALID;
   if (d->equation < PSK_EQ_BURGERS || d->equation > PSK_EQ_CONTINUITY) return PSK_E_UNSUPPORTED;
-  if (d->flux < PSK_FLUX_RUSANOV || d->flux > PSK_FLUX_ENGQUIST_OSHER) return PSK_E_UNSUPPORTED;
-  if (d->rec < PSK_REC_CONSTANT || d->rec > PSK_REC_WENOJS53) return PSK_E_UNSUPPORTED;
+  if (d->flux < PSK_FLUX_RUSANOV || d->flux > PSK_FLUX_ESWENO) return PSK_E_UNSUPPORTED;
+  if (d->rec < PSK_REC_CONSTANT || d->rec > PSK_REC_ESWENO32) return PSK_E_UNSUPPORTED;
+  // "ESWENO32 scheme requires the ESWENO32 reconstruction" (burgers/schemes.py:214-216)
+  if (d->flux == PSK_FLUX_ESWENO && d->rec != PSK_REC_ESWENO32) return PSK_E_INVALID;
   if (d->bc < PSK_BC_PERIODIC || d->bc > PSK_BC_NONE) return PSK_E_UNSUPPORTED;
   if (d->math != PSK_MATH_FAST && d->math != PSK_MATH_STRICT) return PSK_E_INVALID;
   // advection / continuity only come with the upwind ("godunov") flux

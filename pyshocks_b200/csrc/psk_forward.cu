@@ -45,6 +45,7 @@ struct StageParams {
   BcView bc;
   int64_t ld;
   double dx, invdx, eps;
+  double delta;  // ESWENO32
   int stage;
   int tiles_per_row;
   int vec_ok;  // rows are 16-byte aligned and every tile starts on an even cell
@@ -253,7 +254,7 @@ __device__ __forceinline__ double face_flux_scaled(double urj, double ulp, doubl
       if (has_nu) a *= nu;
       return fma(-2.0 * a, ulp - urj, fma(urj, urj, ulp * ulp));
     }
-    if (FLUX == PSK_FLUX_UPWIND) {
+    if (FLUX == PSK_FLUX_UPWIND || FLUX == PSK_FLUX_ESWENO) {
       const double v = (urj + ulp) > 0.0 ? urj : ulp;  // scalar.py:129-130
       return v * v;
     }
@@ -375,6 +376,17 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
   }
   const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
   const double ul_right = __shfl_down_sync(kFull, ul[0], 1);
+  // ESWENO32 scheme: omega_0 of cells c0 - 1 .. c0 + R (burgers/schemes.py:237-240)
+  double om[R + 2];
+  if (FLUX == PSK_FLUX_ESWENO) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int m = r + kHalo;
+      om[r + 1] = esweno32_cell<STRICT>(v[m - 1], v[m], v[m + 1], p.eps, false).om0;
+    }
+    om[0] = __shfl_up_sync(kFull, om[R], 1);
+    om[R + 1] = __shfl_down_sync(kFull, om[1], 1);
+  }
 
   // ---- fluxes at the R + 1 faces; face f sits between cells c0 + f - 1 and c0 + f
   const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
@@ -399,6 +411,10 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
     else
       F[f] = face_flux_scaled<EQ, FLUX>(urj, ulp, v[f + kHalo - 1], v[f + kHalo], speed, nu, has_nu,
                                         arj, alp);
+    if (FLUX == PSK_FLUX_ESWENO) {
+      const double gn = esweno_gnum<STRICT>(om[f], om[f + 1], v[f + kHalo - 1], v[f + kHalo], p.delta);
+      F[f] = STRICT ? sadd(F[f], gn) : F[f] + gn;
+    }
   }
 
   // ---- RHS, stage combine, store
@@ -806,9 +822,17 @@ __device__ double rhs_at_cell(const StageParams &p, const double *__restrict__ u
 #pragma unroll
   for (int k = 0; k < 2 * kHalo + 3; ++k) w[k] = load_w(p.bc, urow, row, i - kHalo - 1 + k);
   // cells i-1, i, i+1 sit at window positions 3, 4, 5
-  Weno5Pair cm = reconstruct_cell<REC, STRICT>(w[1], w[2], w[3], w[4], w[5], p.eps);
-  Weno5Pair cc = reconstruct_cell<REC, STRICT>(w[2], w[3], w[4], w[5], w[6], p.eps);
-  Weno5Pair cp = reconstruct_cell<REC, STRICT>(w[3], w[4], w[5], w[6], w[7], p.eps);
+  // ESWENO32: tau is zero at the two ends of the array (weno.py:292)
+  const bool zm = (i - 1 <= 0) || (i - 1 >= nx - 1), zc = (i <= 0) || (i >= nx - 1), zp = (i + 1 <= 0) || (i + 1 >= nx - 1);
+  Weno5Pair cm = reconstruct_cell<REC, STRICT>(w[1], w[2], w[3], w[4], w[5], p.eps, zm);
+  Weno5Pair cc = reconstruct_cell<REC, STRICT>(w[2], w[3], w[4], w[5], w[6], p.eps, zc);
+  Weno5Pair cp = reconstruct_cell<REC, STRICT>(w[3], w[4], w[5], w[6], w[7], p.eps, zp);
+  double omm = 0.0, omc = 0.0, omp = 0.0;
+  if (FLUX == PSK_FLUX_ESWENO) {
+    omm = esweno32_cell<STRICT>(w[2], w[3], w[4], p.eps, zm).om0;
+    omc = esweno32_cell<STRICT>(w[3], w[4], w[5], p.eps, zc).om0;
+    omp = esweno32_cell<STRICT>(w[4], w[5], w[6], p.eps, zp).om0;
+  }
   const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
   double Flo = 0.0, Fhi = 0.0;  // jnp.pad(fnum, 1): the outermost faces carry zero flux
   if (i >= 1) {
@@ -817,6 +841,10 @@ __device__ double rhs_at_cell(const StageParams &p, const double *__restrict__ u
     double arj = (EQ != PSK_EQ_BURGERS) ? p.vel_r[j] : 0.0;
     double alp = (EQ != PSK_EQ_BURGERS) ? p.vel_l[j + 1] : 0.0;
     Flo = face_flux<EQ, FLUX, STRICT>(cm.ur, cc.ul, w[3], w[4], speed, nu, arj, alp);
+    if (FLUX == PSK_FLUX_ESWENO) {
+      const double gn = esweno_gnum<true>(omm, omc, w[3], w[4], p.delta);
+      Flo = STRICT ? sadd(Flo, gn) : Flo + gn;
+    }
   }
   if (i <= nx - 2) {
     const int j = i;
@@ -824,6 +852,10 @@ __device__ double rhs_at_cell(const StageParams &p, const double *__restrict__ u
     double arj = (EQ != PSK_EQ_BURGERS) ? p.vel_r[j] : 0.0;
     double alp = (EQ != PSK_EQ_BURGERS) ? p.vel_l[j + 1] : 0.0;
     Fhi = face_flux<EQ, FLUX, STRICT>(cc.ur, cp.ul, w[4], w[5], speed, nu, arj, alp);
+    if (FLUX == PSK_FLUX_ESWENO) {
+      const double gn = esweno_gnum<true>(omc, omp, w[4], w[5], p.delta);
+      Fhi = STRICT ? sadd(Fhi, gn) : Fhi + gn;
+    }
   }
   const double vel = (EQ == PSK_EQ_ADVECTION) ? p.vel[i] : 0.0;
   return rhs_from_faces<EQ, STRICT>(Flo, Fhi, vel, p.dx, p.invdx);
@@ -861,7 +893,9 @@ int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStrea
 
 template <int EQ, int FLUX, int REC, bool STRICT>
 int launch_stage(const StageParams &p, int batch, int ghost_rows, cudaStream_t st) {
-  if (g_stage_variant == 0) return launch_stage_warp<EQ, FLUX, REC, STRICT>(p, batch, ghost_rows, st);
+  // the tile kernel has no ESWENO32 form
+  if (g_stage_variant == 0 || REC == PSK_REC_ESWENO32)
+    return launch_stage_warp<EQ, FLUX, REC, STRICT>(p, batch, ghost_rows, st);
   constexpr int R = 4;
   const int n = p.bc.n;
   int threads = (n + R - 1) / R;
@@ -955,6 +989,8 @@ int dispatch_rec(int rec, const StageParams &p, int batch, int ghost_rows, cudaS
       return launch_stage<EQ, FLUX, PSK_REC_CONSTANT, STRICT>(p, batch, ghost_rows, st);
     case PSK_REC_WENOJS32:
       return launch_stage<EQ, FLUX, PSK_REC_WENOJS32, STRICT>(p, batch, ghost_rows, st);
+    case PSK_REC_ESWENO32:
+      return launch_stage<EQ, FLUX, PSK_REC_ESWENO32, STRICT>(p, batch, ghost_rows, st);
     default:
       return launch_stage<EQ, FLUX, PSK_REC_WENOJS53, STRICT>(p, batch, ghost_rows, st);
   }
@@ -975,6 +1011,8 @@ int dispatch_scheme(const psk_desc *d, const StageParams &p, int ghost_rows, cud
                                                                            ghost_rows, st);
     case PSK_FLUX_UPWIND:
       return dispatch_rec<PSK_EQ_BURGERS, PSK_FLUX_UPWIND, STRICT>(d->rec, p, b, ghost_rows, st);
+    case PSK_FLUX_ESWENO:  // check_desc: only with the ESWENO32 reconstruction
+      return launch_stage<PSK_EQ_BURGERS, PSK_FLUX_ESWENO, PSK_REC_ESWENO32, STRICT>(p, b, ghost_rows, st);
     default:
       return dispatch_rec<PSK_EQ_BURGERS, PSK_FLUX_ENGQUIST_OSHER, STRICT>(d->rec, p, b,
                                                                            ghost_rows, st);
@@ -992,6 +1030,7 @@ static StageParams make_params(const psk_desc *d) {
   p.dx = d->dx;
   p.invdx = 1.0 / d->dx;
   p.eps = d->eps;
+  p.delta = d->delta;
   return p;
 }
 
@@ -1016,7 +1055,8 @@ __global__ void reconstruct_kernel(const double *f, double *fl, double *fr, int 
   const int i = static_cast<int>(idx - static_cast<int64_t>(row) * nx);
   const double *r = f + static_cast<int64_t>(row) * ld;
   auto at = [&](int k) { return (k < 0 || k >= nx) ? 0.0 : r[k]; };
-  Weno5Pair o = reconstruct_cell<REC, STRICT>(at(i - 2), at(i - 1), at(i), at(i + 1), at(i + 2), eps);
+  Weno5Pair o = reconstruct_cell<REC, STRICT>(at(i - 2), at(i - 1), at(i), at(i + 1), at(i + 2), eps,
+                                              i == 0 || i == nx - 1);
   fl[static_cast<int64_t>(row) * ld + i] = o.ul;
   fr[static_cast<int64_t>(row) * ld + i] = o.ur;
 }
@@ -1036,13 +1076,20 @@ __global__ void numerical_flux_kernel(const StageParams p, double *F, int64_t ld
     double w[6];
 #pragma unroll
     for (int m = 0; m < 6; ++m) w[m] = load_w(p.bc, urow, row, j - 2 + m);
-    Weno5Pair a = reconstruct_cell<REC, STRICT>(w[0], w[1], w[2], w[3], w[4], p.eps);
-    Weno5Pair b = reconstruct_cell<REC, STRICT>(w[1], w[2], w[3], w[4], w[5], p.eps);
+    const bool za = (j == 0), zb = (j + 1 == p.bc.nx - 1);  // ESWENO32: tau = 0 at the array ends
+    Weno5Pair a = reconstruct_cell<REC, STRICT>(w[0], w[1], w[2], w[3], w[4], p.eps, za);
+    Weno5Pair b = reconstruct_cell<REC, STRICT>(w[1], w[2], w[3], w[4], w[5], p.eps, zb);
     const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
     double nu = (p.nu != nullptr) ? p.nu[j] : 1.0;
     double arj = (EQ != PSK_EQ_BURGERS) ? p.vel_r[j] : 0.0;
     double alp = (EQ != PSK_EQ_BURGERS) ? p.vel_l[j + 1] : 0.0;
     val = face_flux<EQ, FLUX, STRICT>(a.ur, b.ul, w[2], w[3], speed, nu, arj, alp);
+    if (FLUX == PSK_FLUX_ESWENO) {
+      const double omj = esweno32_cell<STRICT>(w[1], w[2], w[3], p.eps, za).om0;
+      const double omp = esweno32_cell<STRICT>(w[2], w[3], w[4], p.eps, zb).om0;
+      const double gn = esweno_gnum<true>(omj, omp, w[2], w[3], p.delta);
+      val = STRICT ? sadd(val, gn) : val + gn;
+    }
   }
   F[static_cast<int64_t>(row) * ld_f + k] = val;
 }
@@ -1058,6 +1105,9 @@ int launch_flux_rec(int rec, const StageParams &p, double *F, int64_t ld_f, int 
       break;
     case PSK_REC_WENOJS32:
       numerical_flux_kernel<EQ, FLUX, PSK_REC_WENOJS32, STRICT><<<blocks, 128, 0, st>>>(p, F, ld_f, batch);
+      break;
+    case PSK_REC_ESWENO32:
+      numerical_flux_kernel<EQ, FLUX, PSK_REC_ESWENO32, STRICT><<<blocks, 128, 0, st>>>(p, F, ld_f, batch);
       break;
     default:
       numerical_flux_kernel<EQ, FLUX, PSK_REC_WENOJS53, STRICT><<<blocks, 128, 0, st>>>(p, F, ld_f, batch);
@@ -1080,6 +1130,8 @@ int launch_flux(const psk_desc *d, const StageParams &p, double *F, int64_t ld_f
       return launch_flux_rec<PSK_EQ_BURGERS, PSK_FLUX_LAX_FRIEDRICHS, STRICT>(d->rec, p, F, ld_f, b, st);
     case PSK_FLUX_UPWIND:
       return launch_flux_rec<PSK_EQ_BURGERS, PSK_FLUX_UPWIND, STRICT>(d->rec, p, F, ld_f, b, st);
+    case PSK_FLUX_ESWENO:
+      return launch_flux_rec<PSK_EQ_BURGERS, PSK_FLUX_ESWENO, STRICT>(PSK_REC_ESWENO32, p, F, ld_f, b, st);
     default:
       return launch_flux_rec<PSK_EQ_BURGERS, PSK_FLUX_ENGQUIST_OSHER, STRICT>(d->rec, p, F, ld_f, b, st);
   }
@@ -1220,7 +1272,7 @@ int psk_reconstruct(const psk_desc *d, const double *f, double *fl, double *fr,
                     psk_stream_t stream) {
   if (d == nullptr || f == nullptr || fl == nullptr || fr == nullptr) return PSK_E_INVALID;
   if (d->n <= 0 || d->batch <= 0 || d->g < 0 || d->ld < d->n + 2 * d->g) return PSK_E_INVALID;
-  if (d->rec < PSK_REC_CONSTANT || d->rec > PSK_REC_WENOJS53) return PSK_E_UNSUPPORTED;
+  if (d->rec < PSK_REC_CONSTANT || d->rec > PSK_REC_ESWENO32) return PSK_E_UNSUPPORTED;
   const int nx = d->n + 2 * d->g;
   const int64_t total = static_cast<int64_t>(d->batch) * nx;
   const unsigned blocks = static_cast<unsigned>((total + 127) / 128);
@@ -1234,6 +1286,7 @@ int psk_reconstruct(const psk_desc *d, const double *f, double *fl, double *fr,
   switch (d->rec) {
     case PSK_REC_CONSTANT: PSK_REC_LAUNCH(PSK_REC_CONSTANT); break;
     case PSK_REC_WENOJS32: PSK_REC_LAUNCH(PSK_REC_WENOJS32); break;
+    case PSK_REC_ESWENO32: PSK_REC_LAUNCH(PSK_REC_ESWENO32); break;
     default: PSK_REC_LAUNCH(PSK_REC_WENOJS53);
   }
 #undef PSK_REC_LAUNCH

@@ -230,17 +230,87 @@ __device__ __forceinline__ double weno32_side_fast(double m1, double c, double p
 }
 
 // ---------------------------------------------------------------------------
+// ESWENO32 (reconstruction.py:386-439, weno.py:284-296): the JS-3 stencils with
+//   alpha_k = d_k (1 + tau / (eps + beta_k)),  tau = (u[i+1] - 2 u[i] + u[i-1])^2,
+// tau being ZERO at the two ends of the array (jnp.pad of the interior expression), which only
+// the ghost-row / parity kernels ever see (tau_zero).  om0 is omega_0 of the right-value
+// weights, the quantity the dissipative flux of the Burgers ESWENO32 scheme is built from
+// (burgers/schemes.py:237-247).
+struct EsCell {
+  double ul, ur, om0;
+};
+
+__device__ __forceinline__ double esweno32_side_strict(double m1, double c, double p1, double eps,
+                                                       bool tau_zero, double *om0) {
+  double c0 = sadd(smul(m1, -1.0), smul(c, 1.0));
+  double c1 = sadd(sadd(smul(m1, 0.0), smul(c, -1.0)), smul(p1, 1.0));
+  double b0 = smul(1.0, smul(c0, c0));
+  double b1 = smul(1.0, smul(c1, c1));
+  double q0 = sadd(smul(m1, -1.0 / 2.0), smul(c, 3.0 / 2.0));
+  double q1 = sadd(sadd(smul(m1, 0.0), smul(c, 1.0 / 2.0)), smul(p1, 1.0 / 2.0));
+  double tt = sadd(ssub(p1, smul(2.0, c)), m1);
+  double tau = tau_zero ? 0.0 : smul(tt, tt);
+  double al0 = smul(1.0 / 3.0, sadd(1.0, sdiv(tau, sadd(eps, b0))));
+  double al1 = smul(2.0 / 3.0, sadd(1.0, sdiv(tau, sadd(eps, b1))));
+  double tot = sadd(al0, al1);
+  if (om0 != nullptr) *om0 = sdiv(al0, tot);
+  return sadd(smul(sdiv(al0, tot), q0), smul(sdiv(al1, tot), q1));
+}
+
+template <bool STRICT>
+__device__ __forceinline__ EsCell esweno32_cell(double m1, double c, double p1, double eps,
+                                                bool tau_zero) {
+  EsCell o;
+  if (STRICT) {
+    o.ur = esweno32_side_strict(m1, c, p1, eps, tau_zero, &o.om0);
+    o.ul = esweno32_side_strict(p1, c, m1, eps, tau_zero, nullptr);
+    return o;
+  }
+  // FAST: with e_k = eps + beta_k, A0 = (e0 + tau) e1, A1 = (e1 + tau) e0:
+  //   right  omega = (A0, 2 A1) / (A0 + 2 A1),  q - c = (d0, d1) / 2
+  //   left   omega = (A1, 2 A0) / (A1 + 2 A0),  q - c = (-d1, -d0) / 2
+  const double d0 = c - m1, d1 = p1 - c;
+  const double e0 = fma(d0, d0, eps), e1 = fma(d1, d1, eps);
+  const double tt = d1 - d0;
+  const double tau = tau_zero ? 0.0 : tt * tt;
+  const double A0 = (e0 + tau) * e1, A1 = (e1 + tau) * e0;
+  const double iR = fast_rcp(fma(2.0, A1, A0)), iL = fast_rcp(fma(2.0, A0, A1));
+  o.om0 = A0 * iR;
+  o.ur = fma(0.5 * fma(A0, d0, 2.0 * (A1 * d1)), iR, c);
+  o.ul = fma(-0.5 * fma(A1, d1, 2.0 * (A0 * d0)), iL, c);
+  return o;
+}
+
+// dissipative flux of the Burgers ESWENO32 scheme at the face between cells j and j+1
+// (burgers/schemes.py:243-247): mu = sqrt((om_p - om_j)^2 + delta^2) / 8,
+// g = -(mu + (om_p - om_j) / 8) (w_p - w_j).  FAST returns 2 g (the scale of the upwind flux).
+template <bool STRICT>
+__device__ __forceinline__ double esweno_gnum(double omj, double omp, double wj, double wp, double delta) {
+  if (STRICT) {
+    const double dom = ssub(omp, omj);
+    const double mu = sdiv(__dsqrt_rn(sadd(smul(dom, dom), smul(delta, delta))), 8.0);
+    return smul(-sadd(mu, sdiv(dom, 8.0)), ssub(wp, wj));
+  }
+  const double dom = omp - omj;
+  return -0.25 * (sqrt(fma(dom, dom, delta * delta)) + dom) * (wp - wj);
+}
+
+// ---------------------------------------------------------------------------
 // generic per-cell reconstruction (no sliding window): (ul, ur) of cell with
 // stencil values v[-2..2] (v points at the cell); used by the edge/naive kernels
 // and by the tile kernel for STRICT math and the non-JS5 reconstructions.
 
 template <int REC, bool STRICT>
 __device__ __forceinline__ Weno5Pair reconstruct_cell(double m2, double m1, double c, double p1,
-                                                       double p2, double eps) {
+                                                       double p2, double eps, bool tau_zero = false) {
   Weno5Pair o;
   if (REC == PSK_REC_CONSTANT) {
     o.ul = c;
     o.ur = c;  // reconstruction.py:153-163
+  } else if (REC == PSK_REC_ESWENO32) {
+    const EsCell e = esweno32_cell<STRICT>(m1, c, p1, eps, tau_zero);
+    o.ul = e.ul;
+    o.ur = e.ur;
   } else if (REC == PSK_REC_WENOJS32) {
     if (STRICT) {
       o.ur = weno32_side_strict(m1, c, p1, eps);
@@ -281,8 +351,9 @@ __device__ __forceinline__ double face_flux(double urj, double ulp, double wj, d
       double ss = fma(urj, urj, ulp * ulp);
       return fma(-0.5 * (a * nu), ulp - urj, 0.25 * ss);
     }
-    if (FLUX == PSK_FLUX_UPWIND) {
-      // scalar.py:123-132 with a = u: where((ur[j] + ul[j+1]) / 2 > 0, f(ur[j]), f(ul[j+1]))
+    if (FLUX == PSK_FLUX_UPWIND || FLUX == PSK_FLUX_ESWENO) {
+      // scalar.py:123-132 with a = u: where((ur[j] + ul[j+1]) / 2 > 0, f(ur[j]), f(ul[j+1]));
+      // the ESWENO32 scheme adds esweno_gnum to this (burgers/schemes.py:255-256)
       double aavg = STRICT ? sdiv(sadd(urj, ulp), 2.0) : 0.5 * (urj + ulp);
       double v = aavg > 0.0 ? urj : ulp;
       return STRICT ? sdiv(smul(v, v), 2.0) : 0.5 * (v * v);

@@ -205,6 +205,8 @@ extern "C" int psk_solve_rows(const psk_desc *d, double *u, int adaptive, double
   if (rc != PSK_OK) return rc;
   if (u == nullptr || t_out == nullptr || steps_out == nullptr || max_steps <= 0) return PSK_E_INVALID;
   if (adaptive && d->equation != PSK_EQ_BURGERS) return PSK_E_UNSUPPORTED;  // state-independent dt: pass it fixed
+  // no single-launch form of ESWENO32: callers fall back to the step-by-step path
+  if (d->rec == PSK_REC_ESWENO32 || d->flux == PSK_FLUX_ESWENO) return PSK_E_UNSUPPORTED;
   psk::SolveParams p{};
   p.u = u; p.t_out = t_out; p.steps_out = steps_out; p.dt_hist = dt_hist; p.tape = tape;
   p.nu = d->nu; p.vel = d->velocity; p.vel_l = d->vel_l; p.vel_r = d->vel_r;

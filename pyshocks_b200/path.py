@@ -27,8 +27,10 @@ _FLUX = {
     "godunov": L.FLUX_UPWIND,
     "upwind": L.FLUX_UPWIND,
     "eo": L.FLUX_ENGQUIST_OSHER,
+    "esweno32": L.FLUX_ESWENO,
 }
-_REC = {"constant": L.REC_CONSTANT, "wenojs32": L.REC_WENOJS32, "wenojs53": L.REC_WENOJS53}
+_REC = {"constant": L.REC_CONSTANT, "wenojs32": L.REC_WENOJS32, "wenojs53": L.REC_WENOJS53,
+        "esweno32": L.REC_ESWENO32}
 _BC = {"periodic": L.BC_PERIODIC, "dirichlet": L.BC_DIRICHLET, "neumann": L.BC_NEUMANN, "none": L.BC_NONE}
 _MATH = {"fast": L.MATH_FAST, "strict": L.MATH_STRICT}
 
@@ -63,8 +65,10 @@ class HotPath:
         nu: np.ndarray | torch.Tensor | None = None,
         velocity: np.ndarray | torch.Tensor | None = None,
         device: torch.device | str | None = None,
+        delta: float = 0.0,
     ) -> None:
         self.device = _dev(device)
+        self.delta = float(delta)  # ESWENO32 only
         self.equation, self.flux, self.rec, self.bc, self.math = equation, flux, rec, bc, math
         self.n, self.g, self.nx = int(n), int(g), int(n) + 2 * int(g)
         self.dx, self.eps = float(dx), float(eps)
@@ -116,7 +120,7 @@ class HotPath:
         d.bc = _BC[self.bc] if bc is None else bc
         d.math = _MATH[self.math]
         d.n, d.g, d.batch, d.ld = self.n, self.g, batch, ld
-        d.dx, d.eps = self.dx, self.eps
+        d.dx, d.eps, d.delta = self.dx, self.eps, self.delta
         d.nu = L.ptr(self._nu)
         d.velocity, d.vel_l, d.vel_r = L.ptr(self._vel), L.ptr(self._vel_l), L.ptr(self._vel_r)
         d.ghost, d.ghost_ld = L.ptr(self._ghost), self._ghost_ld

@@ -52,3 +52,18 @@ def weno_js_53_coefficients() -> Stencil:
     )
     d = np.array([[1.0 / 10.0, 6.0 / 10.0, 3.0 / 10.0]]).T
     return Stencil(a=a, b=b, c=c, d=d)
+
+
+def es_weno_parameters(grid, u0):  # noqa: ANN001, ANN201
+    """``(eps, delta)`` of the ESWENO32 scheme from the grid and the initial condition
+    (weno.py:263-281, Equations 65-66 of Yamaleev & Carpenter 2009).  Evaluated on the host
+    (a one-off scalar at bind time), in the reference's expression order."""
+    import torch
+
+    i = grid.i_
+    u0h = u0.detach().cpu().numpy() if isinstance(u0, torch.Tensor) else np.asarray(u0, dtype=np.float64)
+    dx = np.full_like(u0h, grid.h)
+    dx_min = np.float64(grid.h)
+    eps = np.sum(dx[i] * np.abs(u0h[i])) * dx_min**2
+    delta = dx_min**2
+    return eps, delta

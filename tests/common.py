@@ -22,7 +22,7 @@ def oracle_setup(case: C.Case):
     rec = po.make_reconstruction(case.rec)
     grid = po.make_grid(case.a, case.b, case.n, case.g)
     velocity = None if case.equation == "burgers" else C.velocity_for(case)
-    scheme = po.Scheme(case.equation, case.flux, rec, alpha=case.alpha, velocity=velocity)
+    scheme = po.bind(po.Scheme(case.equation, case.flux, rec, alpha=case.alpha, velocity=velocity), grid)
     if case.bc == "periodic":
         bc = po.Periodic()
     else:

@@ -16,8 +16,8 @@ import numpy as np
 @dataclass(frozen=True)
 class Case:
     equation: str  # burgers | advection | continuity
-    flux: str  # rusanov | lf | godunov | eo
-    rec: str  # constant | wenojs32 | wenojs53
+    flux: str  # rusanov | lf | godunov | eo | esweno32
+    rec: str  # constant | wenojs32 | wenojs53 | esweno32
     bc: str  # periodic | dirichlet
     alpha: float = 1.0
     n: int = 64
@@ -29,7 +29,7 @@ class Case:
 
     @property
     def g(self) -> int:
-        return {"constant": 1, "wenojs32": 2, "wenojs53": 3}[self.rec]
+        return {"constant": 1, "wenojs32": 2, "wenojs53": 3, "esweno32": 2}[self.rec]
 
     @property
     def key(self) -> str:
@@ -60,6 +60,16 @@ def rhs_cases() -> list[Case]:
         ["smooth", "rough"],
     ):
         cases.append(Case(eq, "godunov", rec, bc, a=-1.0, b=1.0, velocity=vel, state=state))
+    # ESWENO32 (appended so that the keys above keep their order): the Burgers scheme with its
+    # dissipative flux (burgers/schemes.py:205-256), and the reconstruction alone behind the
+    # upwind fluxes (tests/test_convergence.py:402 of the reference runs advection this way)
+    for bc, state in itertools.product(["periodic", "dirichlet"], ["smooth", "rough"]):
+        cases.append(Case("burgers", "esweno32", "esweno32", bc, state=state))
+    for eq, bc, vel, state in itertools.product(
+        ["advection", "continuity"], ["periodic", "dirichlet"], ["one", "varying"], ["smooth", "rough"]
+    ):
+        cases.append(Case(eq, "godunov", "esweno32", bc, a=-1.0, b=1.0, velocity=vel, state=state))
+    cases.append(Case("burgers", "godunov", "esweno32", "periodic", state="rough"))
     return cases
 
 

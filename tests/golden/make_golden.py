@@ -120,6 +120,26 @@ def golden_weno() -> dict[str, np.ndarray]:
             ul, ur = reconstruct(rec, grid, BoundaryType.Dirichlet, uj, uj, uj)
             out[f"{k}_ul"] = A(ul)
             out[f"{k}_ur"] = A(ur)
+    # ESWENO32 weights (weno.py:284-296) and reconstruction (reconstruction.py:413-439)
+    from pyshocks.weno import es_weno_weights
+
+    rec = make_reconstruction_from_name("esweno32")
+    g = rec.stencil_width
+    n = 64 + 2 * g
+    theta = np.linspace(0.0, 2.0 * np.pi, n)
+    for label, u in (
+        ("sine", np.sin(theta)),
+        ("step", (theta < np.pi).astype(np.float64)),
+        ("rough", np.sin(3 * theta) + (theta > 2.0) * 0.7 + 1e-3 * np.cos(40 * theta)),
+    ):
+        uj = jnp.array(u)
+        k = f"esweno32_{label}"
+        out[f"{k}_u"] = u
+        out[f"{k}_omega"] = A(es_weno_weights(rec.s, uj, eps=rec.eps))
+        grid = make_uniform_cell_grid(a=0.0, b=1.0, n=64, nghosts=g)
+        ul, ur = reconstruct(rec, grid, BoundaryType.Dirichlet, uj, uj, uj)
+        out[f"{k}_ul"] = A(ul)
+        out[f"{k}_ur"] = A(ur)
     return out
 
 
@@ -139,7 +159,10 @@ def golden_rhs() -> tuple[dict[str, np.ndarray], dict[str, np.ndarray]]:
         rhs[f"{k}_dt"] = A(predict_timestep(scheme, grid, bc, case.t, u))
 
         # one SSPRK33 step with a CFL-like dt (subset: rough states only)
-        if case.state == "rough" or case.rec == "wenojs53":
+        if case.rec == "esweno32":
+            rhs[f"{k}_eps"] = np.float64(scheme.rec.eps)
+            rhs[f"{k}_delta"] = np.float64(scheme.rec.delta)
+        if case.state == "rough" or case.rec in ("wenojs53", "esweno32"):
             dt = 0.3 * float(A(predict_timestep(scheme, grid, bc, case.t, u)))
             stepper = timestepping.SSPRK33(
                 predict_timestep=lambda t_, u_: dt,

@@ -40,8 +40,10 @@ def test_enum_values_match_header() -> None:
 
     assert enum("psk_equation") == {"PSK_EQ_BURGERS": L.EQ_BURGERS, "PSK_EQ_ADVECTION": L.EQ_ADVECTION, "PSK_EQ_CONTINUITY": L.EQ_CONTINUITY}
     assert enum("psk_flux") == {"PSK_FLUX_RUSANOV": L.FLUX_RUSANOV, "PSK_FLUX_LAX_FRIEDRICHS": L.FLUX_LAX_FRIEDRICHS,
-                                "PSK_FLUX_UPWIND": L.FLUX_UPWIND, "PSK_FLUX_ENGQUIST_OSHER": L.FLUX_ENGQUIST_OSHER}
-    assert enum("psk_rec") == {"PSK_REC_CONSTANT": L.REC_CONSTANT, "PSK_REC_WENOJS32": L.REC_WENOJS32, "PSK_REC_WENOJS53": L.REC_WENOJS53}
+                                "PSK_FLUX_UPWIND": L.FLUX_UPWIND, "PSK_FLUX_ENGQUIST_OSHER": L.FLUX_ENGQUIST_OSHER,
+                                "PSK_FLUX_ESWENO": L.FLUX_ESWENO}
+    assert enum("psk_rec") == {"PSK_REC_CONSTANT": L.REC_CONSTANT, "PSK_REC_WENOJS32": L.REC_WENOJS32, "PSK_REC_WENOJS53": L.REC_WENOJS53,
+                               "PSK_REC_ESWENO32": L.REC_ESWENO32}
     assert enum("psk_bc") == {"PSK_BC_PERIODIC": L.BC_PERIODIC, "PSK_BC_DIRICHLET": L.BC_DIRICHLET,
                               "PSK_BC_NEUMANN": L.BC_NEUMANN, "PSK_BC_NONE": L.BC_NONE}
     assert enum("psk_math") == {"PSK_MATH_FAST": L.MATH_FAST, "PSK_MATH_STRICT": L.MATH_STRICT}

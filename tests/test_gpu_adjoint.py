@@ -26,7 +26,9 @@ from test_oracle_golden import ADJ, ADJ_KEYS, adjoint_setup
 
 pytestmark = pytest.mark.gpu
 
-CASES = [c for c in C.rhs_cases()]
+# ESWENO32 has no transposed kernels (the reference's adjoint drivers run WENO-JS schemes);
+# tests/test_gpu_api.py checks that asking for its VJP raises
+CASES = [c for c in C.rhs_cases() if c.rec != "esweno32"]
 
 
 def tol_for(case: C.Case) -> float:

@@ -238,6 +238,7 @@ def _evolve(case_scheme, case_bc, case_exact, n, *, dt, a=-1.0, b=1.0, tfinal=0.
         ("constant", 1, list(range(80, 160 + 1, 16))),
         ("wenojs32", 3, list(range(192, 384 + 1, 32))),
         ("wenojs53", 5, list(range(32, 256 + 1, 32))),
+        ("esweno32", 3, list(range(32, 256 + 1, 32))),  # tests/test_convergence.py:402
     ],
 )
 def test_advection_convergence(rec_name: str, order: int, resolutions: list[int]) -> None:
@@ -296,6 +297,7 @@ def test_burgers_convergence(sname: str, resolutions: list[int]) -> None:
 @pytest.mark.parametrize(("name", "order", "resolutions"), [
     ("wenojs32", 3, list(range(192, 384 + 1, 32))),
     ("wenojs53", 5, list(range(32, 256 + 1, 32))),
+    ("esweno32", 3, list(range(192, 384 + 1, 32))),  # tests/test_weno.py:293
 ])
 def test_weno_smooth_reconstruction_order_cell_values(name: str, order: int, resolutions: list[int]) -> None:
     """tests/test_weno.py:288-338."""
@@ -490,3 +492,65 @@ def test_single_launch_solve_batched_rows_and_fixed_dt() -> None:
 
 
 # }}}
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("bc_name", ["periodic", "dirichlet"])
+def test_burgers_esweno32_scheme_through_the_api(bc_name: str, math: str) -> None:
+    """burgers/schemes.py:205-256 behind the generic functions: ``bind`` takes eps / delta from the
+    grid (weno.py:263-281), ``numerical_flux`` / ``apply_operator`` / ``predict_timestep`` / ``advance``
+    reproduce the golden vectors recorded from the reference (rough state: shock + exact zeros)."""
+    from functools import partial
+
+    import cases as C
+    from common import load_golden, max_rel
+
+    import pyshocks_b200 as ps
+    import pyshocks_b200.timestepping as ts
+    from pyshocks_b200 import burgers, config
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import PeriodicBoundary, make_dirichlet_boundary
+
+    RHS, ADV = load_golden("rhs"), load_golden("advance")
+    case = C.Case("burgers", "esweno32", "esweno32", bc_name, state="rough")
+    k = case.key
+    config.set_math(math)
+    try:
+        grid = ps.make_uniform_cell_grid(a=case.a, b=case.b, n=case.n, nghosts=case.g)
+        with pytest.raises(TypeError):
+            burgers.make_scheme_from_name("esweno32", rec=make_reconstruction_from_name("wenojs32"))
+        scheme = burgers.make_scheme_from_name("esweno32", rec=make_reconstruction_from_name("esweno32"))
+        if bc_name == "periodic":
+            bc = PeriodicBoundary()
+        else:
+            bc = make_dirichlet_boundary(
+                ga=lambda t, x: torch.from_numpy(C.dirichlet_values(case, float(t), x.cpu().numpy())).to(x.device))
+        scheme = ps.bind(scheme, grid, bc)
+        assert scheme.rec.eps == float(RHS[f"{k}_eps"]) and scheme.rec.delta == float(RHS[f"{k}_delta"])
+        u = torch.from_numpy(RHS[f"{k}_u"]).cuda()
+        w = ps.apply_boundary(bc, grid, case.t, u)
+        F = ps.numerical_flux(scheme, grid, bc, case.t, w).cpu().numpy()
+        L = ps.apply_operator(scheme, grid, bc, case.t, u).cpu().numpy()
+        dt_cfl = float(ps.predict_timestep(scheme, grid, bc, case.t, u))
+        assert dt_cfl == float(RHS[f"{k}_dt"])
+        dt = float(ADV[f"{k}_dt"])
+        stepper = ts.SSPRK33(predict_timestep=lambda t_, u_: dt, source=partial(ps.apply_operator, scheme, grid, bc),
+                             checkpoint=None)
+        out = ts.advance(stepper, dt, case.t, u).cpu().numpy()
+        core = slice(3, -3)
+        if math == "strict":
+            assert np.array_equal(F[core], RHS[f"{k}_f"][core])
+            assert np.array_equal(L[core], RHS[f"{k}_L"][core])
+            assert np.array_equal(out[core], ADV[f"{k}_out"][core])
+        else:
+            assert max_rel(F, RHS[f"{k}_f"]) < 5e-13
+            assert max_rel(L, RHS[f"{k}_L"]) < 5e-13
+            assert max_rel(out, ADV[f"{k}_out"]) < 1e-13
+        # no transposed ESWENO32 kernels: the adjoint raises like an unregistered type does
+        from pyshocks_b200.binding import hotpath_for
+
+        hp = hotpath_for(scheme, grid, bc)
+        with pytest.raises(Exception, match="outside"):
+            hp.apply_operator_vjp(u, torch.ones_like(u))
+    finally:
+        config.set_math("fast")

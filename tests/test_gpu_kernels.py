@@ -34,7 +34,7 @@ def hotpath_for(case: C.Case, math: str):
     nu = grid.df ** (case.alpha - 1) if abs(case.alpha - 1.0) > 1.0e-8 else None
     hp = HotPath(
         equation=case.equation, flux=case.flux, rec=case.rec, bc=case.bc, n=case.n, g=case.g,
-        dx=grid.h, eps=scheme.rec.eps, math=math, nu=nu, velocity=scheme.velocity,
+        dx=grid.h, eps=scheme.rec.eps, math=math, nu=nu, velocity=scheme.velocity, delta=scheme.rec.delta,
     )
     return hp, scheme, grid, bc
 
@@ -108,7 +108,7 @@ def test_reconstruct_matches_reference() -> None:
     from pyshocks_b200.path import HotPath
 
     G = load_golden("weno")
-    for name, g in (("wenojs32", 2), ("wenojs53", 3)):
+    for name, g in (("wenojs32", 2), ("wenojs53", 3), ("esweno32", 2)):
         eps = po.make_reconstruction(name).eps
         for label in ("sine", "step", "rough"):
             k = f"{name}_{label}"

@@ -29,7 +29,7 @@ def c_oracle_for(case: C.Case, scheme: po.Scheme, grid: po.OracleGrid, batch: in
     nu = grid.df ** (case.alpha - 1) if abs(case.alpha - 1.0) > 1.0e-8 else None
     return COracle(
         equation=case.equation, flux=case.flux, rec=case.rec, bc=case.bc, n=case.n, g=case.g,
-        batch=batch, dx=grid.h, eps=scheme.rec.eps, nu=nu, velocity=scheme.velocity,
+        batch=batch, dx=grid.h, eps=scheme.rec.eps, delta=scheme.rec.delta, nu=nu, velocity=scheme.velocity,
     )
 
 
@@ -59,6 +59,15 @@ def test_weno_pieces_bitwise() -> None:
             ul, ur = po.reconstruct(rec, u)
             assert np.array_equal(ul, G[f"{k}_ul"])
             assert np.array_equal(ur, G[f"{k}_ur"])
+    # ESWENO32: weno.py:284-296, reconstruction.py:413-439
+    rec = po.make_reconstruction("esweno32")
+    for label in ("sine", "step", "rough"):
+        k = f"esweno32_{label}"
+        u = G[f"{k}_u"]
+        assert np.array_equal(po.es_weno_weights(po._JS32, u, rec.eps), G[f"{k}_omega"])
+        ul, ur = po.reconstruct(rec, u)
+        assert np.array_equal(ul, G[f"{k}_ul"])
+        assert np.array_equal(ur, G[f"{k}_ur"])
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c.key)
@@ -67,6 +76,8 @@ def test_rhs_numpy_oracle_bitwise(case: C.Case) -> None:
     k = case.key
     u = RHS[f"{k}_u"]
     assert np.array_equal(u, C.state_for(case))
+    if case.flux == "esweno32":  # bind took eps, delta from the grid (burgers/schemes.py:217-227)
+        assert scheme.rec.eps == RHS[f"{k}_eps"] and scheme.rec.delta == RHS[f"{k}_delta"]
     w = po.apply_boundary(bc, grid, case.t, u)
     assert np.array_equal(w, RHS[f"{k}_w"])
     assert np.array_equal(po.numerical_flux(scheme, grid, w), RHS[f"{k}_f"])

@@ -403,11 +403,12 @@ def run_slab(args: argparse.Namespace) -> None:
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    slab.solve_fixed_dt(dt, args.warmup)
+    kw = {"graph": True} if (args.transport == "p2p" and args.graph) else {}
+    slab.solve_fixed_dt(dt, max(args.warmup, 6 if kw else 0), **kw)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    slab.solve_fixed_dt(dt, args.steps)
+    slab.solve_fixed_dt(dt, args.steps, **kw)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -427,6 +428,7 @@ def run_slab(args: argparse.Namespace) -> None:
             "config": {"workload": f"single periodic Burgers grid N={n_global} cells, slab-decomposed over {world} rank(s), "
                                    "ring halo exchange 3 cells/side/stage (BASELINE.json configs[3])",
                        "cells_per_gpu": slab.n_local, "halo_exchanges_per_step": 3, "finite": finite,
+                       "cuda_graph": bool(kw),
                        "transport": {"p2p": "exchange fused into the stage kernel: edge warps spin on local epoch flags, "
                                             "edge lanes store into the neighbours' ghost slots over NVLink (1 launch per stage)",
                                      "p2p-overlap": "NVLink peer stores + epoch flags, slab edges on a high-priority stream "
@@ -519,6 +521,7 @@ def main() -> None:
                     help="ensemble = the headline config (default); slab / adjoint = BASELINE configs 4 and 5")
     ap.add_argument("--transport", choices=("p2p", "p2p-overlap", "p2p-serial", "nccl"), default="p2p",
                     help="ghost-cell exchange of the slab workload")
+    ap.add_argument("--graph", action="store_true", help="slab workload, fused transport: replay a CUDA graph of two steps")
     ap.add_argument("--cells", type=int, default=0, help="override the cell count of the slab / adjoint workloads")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

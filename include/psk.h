@@ -264,6 +264,12 @@ typedef struct psk_halo_link {
   int64_t *flag_lo, *flag_hi;       /* the neighbours' flags this rank raises                     */
   int64_t timeout_ns;               /* a spin gives up after this long and sets *timed_out        */
   int32_t *timed_out;
+  /* Optional device-side epoch (for time loops replayed as CUDA graphs, where launch arguments
+   * cannot change): when epoch_in != NULL the epoch is *epoch_in + wait_epoch, and one lane
+   * stores epoch + 1 to *epoch_out for the next stage.  epoch_in / epoch_out must be two
+   * different slots (stage k reads slot k & 1 and writes slot (k + 1) & 1). */
+  const int64_t *epoch_in;
+  int64_t *epoch_out;
 } psk_halo_link;
 
 /* psk_ssprk33_stage (stages 1-3, one row, boundary kind NONE, dt shared) with the exchange

@@ -66,6 +66,8 @@ class PskHaloLink(ct.Structure):
         ("flag_hi", _dp),
         ("timeout_ns", ct.c_int64),
         ("timed_out", _dp),
+        ("epoch_in", _dp),
+        ("epoch_out", _dp),
     ]
 
 

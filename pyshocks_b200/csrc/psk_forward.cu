@@ -688,6 +688,8 @@ struct HaloLink {
   long long *flag_lo, *flag_hi;
   unsigned long long timeout_ns;
   int *timed_out;
+  const long long *epoch_in;  // optional device-side epoch (CUDA-graph replay)
+  long long *epoch_out;
 };
 
 __device__ __forceinline__ void halo_spin(const long long *flag, long long epoch, unsigned long long timeout_ns,
@@ -698,6 +700,8 @@ __device__ __forceinline__ void halo_spin(const long long *flag, long long epoch
     long long v;
     asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
     if (v >= epoch) return;
+    // sticky: once a wait has given up, no later wait spends its timeout again
+    if (timed_out != nullptr && *reinterpret_cast<volatile int *>(timed_out) != 0) return;
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     if (!timing) {
@@ -722,8 +726,13 @@ stage_warp_fast_p2p_kernel(const FastParams p, const HaloLink h) {
   const int c0 = chunk * 30 * R - R + R * lane;
   const bool inside = (c0 >= 0) && (c0 + R <= n);
   const bool emit = (lane >= 1) && (lane <= 30);
-  if (chunk == 0 && h.wait_lo != nullptr) halo_spin(h.wait_lo, h.wait_epoch, h.timeout_ns, h.timed_out);
-  if (chunk * 30 * R + 31 * R > n && h.wait_hi != nullptr) halo_spin(h.wait_hi, h.wait_epoch, h.timeout_ns, h.timed_out);
+  const bool edge_lo = (chunk == 0), edge_hi = (chunk * 30 * R + 31 * R > n);
+  long long epoch = h.wait_epoch;
+  // (the two pushing lanes live in chunk 0 and in the chunk holding cell n - 4: both edge chunks)
+  if (h.epoch_in != nullptr && (edge_lo || edge_hi))
+    epoch += *reinterpret_cast<const volatile long long *>(h.epoch_in);
+  if (edge_lo && h.wait_lo != nullptr) halo_spin(h.wait_lo, epoch, h.timeout_ns, h.timed_out);
+  if (edge_hi && h.wait_hi != nullptr) halo_spin(h.wait_hi, epoch, h.timeout_ns, h.timed_out);
   FastIn in;
   if (inside) {
     fast_load<STAGE>(p, 0, c0, lane, true, in);
@@ -745,15 +754,16 @@ stage_warp_fast_p2p_kernel(const FastParams p, const HaloLink h) {
       h.peer_lo[1] = out[1];
       h.peer_lo[2] = out[2];
       __threadfence_system();
-      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_lo), "l"(h.wait_epoch + 1) : "memory");
+      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_lo), "l"(epoch + 1) : "memory");
     }
     if (c0 == n - R && h.peer_hi != nullptr) {
       h.peer_hi[0] = out[1];
       h.peer_hi[1] = out[2];
       h.peer_hi[2] = out[3];
       __threadfence_system();
-      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_hi), "l"(h.wait_epoch + 1) : "memory");
+      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_hi), "l"(epoch + 1) : "memory");
     }
+    if (c0 == 0 && h.epoch_out != nullptr) *h.epoch_out = epoch + 1;
   }
 }
 
@@ -1394,6 +1404,11 @@ int psk_ssprk33_stage_p2p(const psk_desc *d, int stage, const double *u0, const 
   h.flag_hi = reinterpret_cast<long long *>(link->flag_hi);
   h.timeout_ns = static_cast<unsigned long long>(link->timeout_ns);
   h.timed_out = link->timed_out;
+  if ((link->epoch_in == nullptr) != (link->epoch_out == nullptr) ||
+      (link->epoch_in != nullptr && link->epoch_in == link->epoch_out))
+    return PSK_E_INVALID;
+  h.epoch_in = reinterpret_cast<const long long *>(link->epoch_in);
+  h.epoch_out = reinterpret_cast<long long *>(link->epoch_out);
   // 5 warps per CTA: 6 CTAs (30 warps) per SM at 64 registers, the shape the plain launcher
   // picks for long single rows
   const int wpc = q.chunks_per_row < 5 ? q.chunks_per_row : 5;

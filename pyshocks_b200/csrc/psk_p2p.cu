@@ -68,6 +68,8 @@ __global__ void halo_wait_kernel(const long long *flag_a, const long long *flag_
     if (!ok_a) ok_a = load_acquire_sys(flag_a) >= epoch;
     if (!ok_b) ok_b = load_acquire_sys(flag_b) >= epoch;
     if (ok_a && ok_b) return;
+    // sticky: once a wait has given up, no later wait spends its timeout again
+    if (timed_out != nullptr && *reinterpret_cast<volatile int *>(timed_out) != 0) return;
     if (global_timer_ns() - t0 > timeout_ns) {
       if (timed_out != nullptr) atomicExch(timed_out, 1);
       return;

@@ -87,6 +87,25 @@ def test_invalid_arguments_are_rejected_without_a_gpu() -> None:
     assert lib.psk_apply_operator(ct.byref(d), None, None, None, None) == L.E_UNSUPPORTED
     assert lib.psk_status_string(L.E_UNSUPPORTED).decode().startswith("outside")
     assert lib.psk_set_stage_variant(5) == L.E_INVALID
+    # ESWENO32: the Burgers scheme needs its own reconstruction (burgers/schemes.py:214-216)
+    d.equation, d.flux, d.rec = L.EQ_BURGERS, L.FLUX_ESWENO, L.REC_WENOJS32
+    assert lib.psk_apply_operator(ct.byref(d), None, None, None, None) == L.E_INVALID
+    # the fused peer-memory stage: argument checks and the scope of the fused kernel
+    link = L.PskHaloLink()
+    d.flux, d.rec, d.bc, d.math = L.FLUX_RUSANOV, L.REC_WENOJS53, L.BC_NONE, L.MATH_FAST
+    args = (ct.byref(d), 1, None, 1 << 12, 1 << 13, 1 << 14, None)
+    assert lib.psk_ssprk33_stage_p2p(*args, None, None) == L.E_INVALID  # no link
+    assert lib.psk_ssprk33_stage_p2p(*args, ct.byref(link), None) == L.E_INVALID  # timeout_ns <= 0
+    link.timeout_ns = 1
+    link.peer_lo = 1 << 15
+    assert lib.psk_ssprk33_stage_p2p(*args, ct.byref(link), None) == L.E_INVALID  # peer slot without a flag
+    link.peer_lo = None
+    d.math = L.MATH_STRICT
+    assert lib.psk_ssprk33_stage_p2p(*args, ct.byref(link), None) == L.E_UNSUPPORTED  # FAST math only
+    d.math, d.n, d.ld = L.MATH_FAST, 18, 24
+    assert lib.psk_ssprk33_stage_p2p(*args, ct.byref(link), None) == L.E_UNSUPPORTED  # n % 4 != 0
+    assert lib.psk_halo_push(None, None, None, None, 0, None, None, 1, None) == L.E_INVALID
+    assert lib.psk_halo_wait(None, None, 1, 10, None, None) == L.E_INVALID
 
 
 def test_product_never_touches_the_oracle() -> None:

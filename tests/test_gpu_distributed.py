@@ -134,6 +134,33 @@ def test_peer_memory_adaptive_single_slab(math: str) -> None:
         ps.mem.close()
 
 
+def test_fused_exchange_replayed_as_cuda_graph() -> None:
+    """Fixed-dt loop of the fused exchange as a replayed CUDA graph of two steps (device-side epoch in
+    two alternating slots) on a one-slab ring: bit-identical to the step-by-step solve, for an odd and
+    an even number of steps and across two calls that reuse the captured graph."""
+    from pyshocks_b200.distributed import PeerRing, PeerSlabSolver
+
+    n, g = 6144, 3
+    dt = 0.4 * (3.0 / n) / 1.8
+    ug = torch.from_numpy(_ic(n, g)).cuda()
+    ps = PeerSlabSolver(n_global=n, rank=0, world=1, dx=3.0 / n, timeout_s=5.0)
+    try:
+        assert ps.fused
+        ps.attach(PeerRing.local([ps.mem], 0))
+        ps.load_interior(ug)
+        dtt = torch.full((1,), dt, dtype=torch.float64, device="cuda")
+        ps.solve_fixed_dt(dtt, 11, graph=True)
+        ps.solve_fixed_dt(dtt, 8, graph=True)
+        ps.check()
+        assert ps._graph is not None and ps.exchanges == 3 * 19 + 1
+        assert torch.equal(ps.interior(), _reference_periodic(n, dt, 19, "fast"))
+    finally:
+        ps.ring = None
+        ps.solver = None
+        ps._graph = None
+        ps.mem.close()
+
+
 def test_halo_wait_gives_up_instead_of_hanging() -> None:
     from pyshocks_b200 import _lib as L
 
@@ -195,6 +222,12 @@ def _nccl_worker(rank: int, world: int, port: int, out: dict) -> None:
             ps.check()
             ok = ok and torch.equal(ps.interior(), ref[ps.first : ps.first + ps.n_local])
             ok = ok and ps.split == (mode == "overlap") and ps.fused == (mode == "fused")
+            if mode == "fused":  # ... and the same loop replayed as a CUDA graph, from the state reached so far
+                ps.solve_fixed_dt(dt, 9, graph=True)
+                ps.check()
+                ref2 = _reference_periodic(n, dt, nsteps + 9, "fast")
+                ok = ok and ps._graph is not None and torch.equal(ps.interior(), ref2[ps.first : ps.first + ps.n_local])
+                ps._graph = None
             ps.close()
             mark(f"peer slabs {mode} ok={ok}")
         # adaptive dt: every rank takes the same dt sequence as the single-GPU adaptive solve.  The

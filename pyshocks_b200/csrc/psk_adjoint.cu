@@ -512,8 +512,12 @@ __device__ __forceinline__ void lean_load(const AdjParams &p, int row, int c0, i
 }
 
 // everything after the loads: window exchange, forward states, faces, VJPs, spill exchange, store
+// slin: where the linear part was parked (shared memory, stride 128 doubles) or nullptr (in.lin);
+// RECOMP3: recompute the forward state of cell 3 before its faces instead of holding it since
+// the exchange at the top (39 more FP64 instructions per lane, 26 registers fewer in between)
+template <bool RECOMP3>
 __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, int c0, int lane, bool inside,
-                                                   const LeanIn &in) {
+                                                   const LeanIn &in, const double *slin) {
   constexpr int R = 4;
   constexpr unsigned kFull = 0xffffffffu;
   const int g = p.bc.g, n = p.bc.n, nx = p.bc.nx;
@@ -578,13 +582,16 @@ __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, 
   o[1] = (f1.dp + f2.dj) + (f2.gR + f1.gL);
   weno53_vjp_acc(F1, t[2], t[3], t[4], t[5], f2.gR, f1.gL, Tk[1], Tk[2], Tk[3], Tk[4]);
 
-  const LeanFace f3 = lean_face(hG[3], w[5] + F2.uR, w[6] + F3.uL, w[5], w[6]);
+  double t7b = t[7];
+  if (RECOMP3) asm volatile("" : "+d"(t7b));  // keeps the compiler from merging the two evaluations
+  const Weno5State F3b = RECOMP3 ? weno53_state(t[4], t[5], t[6], t7b, pq[4], pq[5], pq[6]) : F3;
+  const LeanFace f3 = lean_face(hG[3], w[5] + F2.uR, w[6] + F3b.uL, w[5], w[6]);
   o[2] = (f2.dp + f3.dj) + (f3.gR + f2.gL);
   weno53_vjp_acc(F2, t[3], t[4], t[5], t[6], f3.gR, f2.gL, Tk[2], Tk[3], Tk[4], Tk[5]);
 
-  const LeanFace f4 = lean_face(hG[4], ur3, ul_right, w[6], w[7]);
+  const LeanFace f4 = lean_face(hG[4], RECOMP3 ? w[6] + F3b.uR : ur3, ul_right, w[6], w[7]);
   o[3] = (f3.dp + f4.dj) + (f4.gR + f3.gL);
-  weno53_vjp_acc(F3, t[4], t[5], t[6], t[7], f4.gR, f3.gL, Tk[3], Tk[4], Tk[5], Tk[6]);
+  weno53_vjp_acc(F3b, t[4], t[5], t[6], t7b, f4.gR, f3.gL, Tk[3], Tk[4], Tk[5], Tk[6]);
 
   // ---- contributions of the neighbour lanes' cells to the first differences around my cells
   const double fl5 = __shfl_up_sync(kFull, Tk[5], 1);
@@ -597,13 +604,16 @@ __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, 
   Tk[5] += fr1;
 
   if (lane >= 1 && lane <= 30) {
-    double gi[R];
+    double gi[R], lin[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) gi[r] = fma(1.0 / 6.0, Tk[r + 1] - Tk[r + 2], o[r]);
+    for (int r = 0; r < R; ++r) {
+      gi[r] = fma(1.0 / 6.0, Tk[r + 1] - Tk[r + 2], o[r]);
+      lin[r] = (slin != nullptr) ? slin[128 * r] : in.lin[r];
+    }
     if (inside) {
       // inside => interior cells only (no ghost among them)
-      *reinterpret_cast<double2 *>(p.out + off) = make_double2(in.lin[0] + gi[0], in.lin[1] + gi[1]);
-      *reinterpret_cast<double2 *>(p.out + off + 2) = make_double2(in.lin[2] + gi[2], in.lin[3] + gi[3]);
+      *reinterpret_cast<double2 *>(p.out + off) = make_double2(lin[0] + gi[0], lin[1] + gi[1]);
+      *reinterpret_cast<double2 *>(p.out + off + 2) = make_double2(lin[2] + gi[2], lin[3] + gi[3]);
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -613,17 +623,18 @@ __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, 
         if (ghost) {
           // ghost cells of x do not influence L; what landed on them goes back through the
           // transpose of apply_boundary (already scaled by c_g dt: p.prescaled)
-          p.out[base + i] = in.lin[r];
+          p.out[base + i] = lin[r];
           p.gspill[static_cast<int64_t>(row) * 2 * g + (i < g ? i : i - n)] = gi[r];
         } else {
-          p.out[base + i] = in.lin[r] + gi[r];
+          p.out[base + i] = lin[r] + gi[r];
         }
       }
     }
   }
 }
 
-template <int MINB>
+// VAR bit 0: park the linear part in shared memory; bit 1: recompute the state of cell 3
+template <int MINB, int VAR>
 __global__ void __launch_bounds__(128, MINB)
 adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
   constexpr int R = 4;
@@ -635,10 +646,17 @@ adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
   const bool inside = (c0 >= 0) && (c0 + R <= p.bc.n);
   LeanIn in;
   lean_load(p, row, c0, lane, inside, in);
-  lean_compute_store(p, row, c0, lane, inside, in);
+  if (VAR & 1) {
+    __shared__ double slin[4][128];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) slin[r][threadIdx.x] = in.lin[r];
+    lean_compute_store<(VAR & 2) != 0>(p, row, c0, lane, inside, in, &slin[0][threadIdx.x]);
+  } else {
+    lean_compute_store<(VAR & 2) != 0>(p, row, c0, lane, inside, in, nullptr);
+  }
 }
 
-template <int MINB>
+template <int MINB, int VAR>
 int launch_adjoint_lean(const AdjParams &p, int batch, cudaStream_t st) {
   const int chunks = (p.bc.n + p.bc.g + 119) / 120;  // chunks 0 .. chunks-1 plus chunk -1
   const int total = chunks + 1;
@@ -647,7 +665,7 @@ int launch_adjoint_lean(const AdjParams &p, int batch, cudaStream_t st) {
   const unsigned gy = batch < 65535 ? batch : 65535u;
   if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
   const dim3 grid(gx, gy, batch / gy);
-  adjoint_lean_kernel<MINB><<<grid, wpc * 32, 0, st>>>(p, chunks);
+  adjoint_lean_kernel<MINB, VAR><<<grid, wpc * 32, 0, st>>>(p, chunks);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
 }
@@ -719,8 +737,9 @@ __global__ void adjoint_boundary_kernel(const AdjParams p) {
 }
 
 // 0: lean warp kernel for the hot configuration, warp kernel for the other WENO-JS5 cases;
-// 1: tile kernel always; 2: warp kernel (no lean kernel); 3..5: lean kernel compiled for
-// 3 / 4 / 5 CTAs of 128 threads per SM (register budgets 168 / 128 / 96)
+// 1: tile kernel always; 2: warp kernel (no lean kernel); 3, 5: lean kernel compiled for 3 / 5 CTAs
+// of 128 threads per SM (register budgets 168 / 96; the default is 4 CTAs, 128 registers, linear part
+// parked in shared memory, state of cell 3 recomputed); 6: 4 CTAs without those two measures
 static int g_adjoint_variant = 0;
 
 template <int EQ, int FLUX, int REC>
@@ -740,9 +759,10 @@ int launch_adjoint(const AdjParams &p0, int batch, cudaStream_t st) {
     if (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV && p.nu == nullptr && g_adjoint_variant != 2) {
       p.prescaled = 1;
       switch (g_adjoint_variant) {
-        case 3: rc = launch_adjoint_lean<3>(p, batch, st); break;
-        case 5: rc = launch_adjoint_lean<5>(p, batch, st); break;
-        default: rc = launch_adjoint_lean<4>(p, batch, st); break;
+        case 3: rc = launch_adjoint_lean<3, 0>(p, batch, st); break;
+        case 5: rc = launch_adjoint_lean<5, 3>(p, batch, st); break;
+        case 6: rc = launch_adjoint_lean<4, 0>(p, batch, st); break;
+        default: rc = launch_adjoint_lean<4, 3>(p, batch, st); break;
       }
     } else {
       rc = launch_adjoint_warp<EQ, FLUX>(p, batch, st);
@@ -849,7 +869,7 @@ extern "C" {
 
 /* A/B switch for the adjoint stage (see g_adjoint_variant) */
 int psk_set_adjoint_variant(int variant) {
-  if (variant < 0 || variant > 5) return PSK_E_INVALID;
+  if (variant < 0 || variant > 6) return PSK_E_INVALID;
   g_adjoint_variant = variant;
   return PSK_OK;
 }

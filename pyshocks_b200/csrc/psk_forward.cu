@@ -24,6 +24,7 @@
 
 #include "psk_common.cuh"
 #include "psk_math.cuh"
+#include "psk_fast_kernels.cuh"
 
 namespace psk {
 
@@ -50,8 +51,6 @@ struct StageParams {
   int tiles_per_row;
   int vec_ok;  // rows are 16-byte aligned and every tile starts on an even cell
 };
-
-constexpr int kHalo = 3;
 
 template <int R>
 __host__ __device__ __forceinline__ int pad_index(int e) {
@@ -233,15 +232,6 @@ stage_tile_kernel(const StageParams p) {
 //   * no __syncthreads anywhere, so warps drift apart and hide each other's load latency;
 //   * FAST math works in sixths of the first differences and with fluxes scaled by a
 //     compile-time constant (folded into dt / dx), see psk_math.cuh.
-
-// FAST-path flux scaled by kFluxScale<EQ, FLUX> (4 F for Rusanov / Lax-Friedrichs, 2 F for
-// the other Burgers fluxes, F for advection / continuity): saves the halvings of u^2 / 2.
-template <int EQ, int FLUX>
-struct FluxScale {
-  static constexpr double value =
-      (EQ != PSK_EQ_BURGERS) ? 1.0
-                             : ((FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? 4.0 : 2.0);
-};
 
 template <int EQ, int FLUX>
 __device__ __forceinline__ double face_flux_scaled(double urj, double ulp, double wj, double wp,
@@ -472,199 +462,8 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
   }
 }
 
-// ---------------------------------------------------------------------------
-// The hot configuration, specialised: WENO-JS5, FAST math, nu = 1, every row active,
-// 16-byte aligned rows.  Same algorithm and data movement as stage_warp_kernel; what differs
-// is the bookkeeping: the grid is (chunk groups, rows) so no integer division is needed, the
-// stage is a template parameter, the Rusanov speed max(|w_j|, |w_j+1|) is an integer max of the
-// bit patterns (2 ALU compares + 2 selects instead of an emulated fp64 max), and the candidate
-// offsets reuse the smoothness stencils' linear forms (weno53_pair_lean).
 static int g_fast_wpc_max = 8;  // largest CTA (in warps) the specialised kernel may use (tuning)
-
-struct FastParams {
-  const double *uin;
-  const double *u0;
-  double *uout;
-  const double *dt;
-  const double *lf_speed;
-  unsigned long long *maxabs;
-  const double *vel;
-  const double *vel_l;
-  const double *vel_r;
-  BcView bc;
-  int64_t ld;
-  double coef;   // 1 / (flux scale * dx)
-  double eps9;   // eps / 9
-  int dt_stride;
-  int chunks_per_row;
-};
-
-__device__ __forceinline__ double umax_abs(double a, double b) {
-  const unsigned long long x = static_cast<unsigned long long>(__double_as_longlong(a)) & 0x7fffffffffffffffull;
-  const unsigned long long y = static_cast<unsigned long long>(__double_as_longlong(b)) & 0x7fffffffffffffffull;
-  return __longlong_as_double(static_cast<long long>(x > y ? x : y));
-}
-
-#ifndef PSK_FAST_MIN_BLOCKS
-#define PSK_FAST_MIN_BLOCKS 4
-#endif
-// own cells of a lane: stage input and (stages 2, 3) the step's initial state
-struct FastIn {
-  double v[4], u0[4];
-};
-
-template <int STAGE>
-__device__ __forceinline__ void fast_load(const FastParams &p, int row, int c0, int lane, bool inside,
-                                          FastIn &in) {
-  constexpr int R = 4;
-  const int g = p.bc.g, n = p.bc.n;
-  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
-  const bool emit = (lane >= 1) && (lane <= 30);
-  if (inside) {
-    const double2 q0 = *reinterpret_cast<const double2 *>(p.uin + off);
-    const double2 q1 = *reinterpret_cast<const double2 *>(p.uin + off + 2);
-    in.v[0] = q0.x; in.v[1] = q0.y; in.v[2] = q1.x; in.v[3] = q1.y;
-  } else {
-    const double *__restrict__ urow = p.uin + static_cast<int64_t>(row) * p.ld;
-#pragma unroll
-    for (int r = 0; r < R; ++r) in.v[r] = load_w(p.bc, urow, row, g + c0 + r);
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) in.u0[r] = 0.0;
-  if (STAGE >= 2 && emit) {
-    if (inside) {
-      const double2 q0 = *reinterpret_cast<const double2 *>(p.u0 + off);
-      const double2 q1 = *reinterpret_cast<const double2 *>(p.u0 + off + 2);
-      in.u0[0] = q0.x; in.u0[1] = q0.y; in.u0[2] = q1.x; in.u0[3] = q1.y;
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (c0 + r >= 0 && c0 + r < n) in.u0[r] = p.u0[off + r];
-    }
-  }
-}
-
-template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
-__device__ __forceinline__ void fast_compute_store(const FastParams &p, int row, int c0, int lane, bool inside,
-                                                   const FastIn &in, double (&out)[4]) {
-  constexpr int R = 4;
-  constexpr unsigned kFull = 0xffffffffu;
-  const int g = p.bc.g, n = p.bc.n;
-  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
-  const bool emit = (lane >= 1) && (lane <= 30);
-  double v[R + 2 * kHalo];
-  double u0v[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    v[kHalo + r] = in.v[r];
-    u0v[r] = in.u0[r];
-  }
-  v[0] = __shfl_up_sync(kFull, v[4], 1);
-  v[1] = __shfl_up_sync(kFull, v[5], 1);
-  v[2] = __shfl_up_sync(kFull, v[6], 1);
-  v[7] = __shfl_down_sync(kFull, v[3], 1);
-  v[8] = __shfl_down_sync(kFull, v[4], 1);
-  v[9] = __shfl_down_sync(kFull, v[5], 1);
-
-  double t[R + 5], pq[R + 4];
-#pragma unroll
-  for (int k = 0; k < R + 5; ++k) t[k] = (1.0 / 6.0) * (v[k + 1] - v[k]);
-#pragma unroll
-  for (int k = 0; k < R + 4; ++k) {
-    const double dd = t[k + 1] - t[k];
-    pq[k] = fma((13.0 / 3.0) * dd, dd, p.eps9);
-  }
-  double ul[R], ur[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int m = r + kHalo;
-    const Weno5Pair o = weno53_pair_lean(v[m], t[m - 2], t[m - 1], t[m], t[m + 1], pq[m - 2], pq[m - 1], pq[m]);
-    ul[r] = o.ul;
-    ur[r] = o.ur;
-  }
-  const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
-  const double ul_right = __shfl_down_sync(kFull, ul[0], 1);
-
-  const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? p.lf_speed[row] : 0.0;
-  double F[R + 1];
-#pragma unroll
-  for (int f = 0; f <= R; ++f) {
-    const double urj = (f == 0) ? ur_left : ur[f - 1];
-    const double ulp = (f == R) ? ul_right : ul[f];
-    if (EQ == PSK_EQ_BURGERS) {
-      if (FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) {
-        const double a = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? speed : umax_abs(v[f + kHalo - 1], v[f + kHalo]);
-        F[f] = fma(-2.0 * a, ulp - urj, fma(urj, urj, ulp * ulp));  // 4 F
-      } else if (FLUX == PSK_FLUX_UPWIND) {
-        const double w = (urj + ulp) > 0.0 ? urj : ulp;
-        F[f] = w * w;  // 2 F
-      } else {
-        const double vp = fmax(urj, 0.0), vm = fmin(ulp, 0.0);
-        F[f] = fma(vp, vp, vm * vm);  // 2 F
-      }
-    } else {
-      const int j = g + c0 + f - 1;
-      const bool ok = (j >= 0 && j < p.bc.nx - 1);
-      const double arj = ok ? p.vel_r[j] : 0.0, alp = ok ? p.vel_l[j + 1] : 0.0;
-      const bool pos = (arj + alp) > 0.0;
-      F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? arj * urj : alp * ulp);
-    }
-  }
-
-  double coef = p.coef;
-  if (STAGE != 0) coef *= p.dt[static_cast<int64_t>(row) * p.dt_stride];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    double dF = F[r] - F[r + 1];
-    if (EQ == PSK_EQ_ADVECTION) dF *= (c0 + r >= 0 && c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
-    if (STAGE == 0) {
-      out[r] = coef * dF;
-    } else {
-      const double k = fma(coef, dF, v[r + kHalo]);
-      out[r] = (STAGE == 1) ? k
-                            : ((STAGE == 2) ? fma(0.25, k, 0.75 * u0v[r]) : fma(2.0 / 3.0, k, (1.0 / 3.0) * u0v[r]));
-    }
-  }
-  if (emit) {
-    if (inside) {
-      *reinterpret_cast<double2 *>(p.uout + off) = make_double2(out[0], out[1]);
-      *reinterpret_cast<double2 *>(p.uout + off + 2) = make_double2(out[2], out[3]);
-    } else {
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (c0 + r >= 0 && c0 + r < n) p.uout[off + r] = out[r];
-    }
-  }
-  if (WITH_MAX) {
-    unsigned long long mx = 0ull;
-    if (emit) {
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-        if (c0 + r >= 0 && c0 + r < n) {
-          const unsigned long long b = abs_bits(out[r]);
-          mx = b > mx ? b : mx;
-        }
-    }
-    mx = warp_max_bits(mx);
-    if (lane == 0) atomicMax(p.maxabs + row, mx);
-  }
-}
-
-template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
-__global__ void __launch_bounds__(256, PSK_FAST_MIN_BLOCKS)
-stage_warp_fast_kernel(const FastParams p) {
-  constexpr int R = 4;
-  const int lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (chunk >= p.chunks_per_row) return;
-  const int row = blockIdx.y + blockIdx.z * gridDim.y;
-  const int c0 = chunk * 30 * R - R + R * lane;
-  const bool inside = (c0 >= 0) && (c0 + R <= p.bc.n);
-  FastIn in;
-  double out[4];
-  fast_load<STAGE>(p, row, c0, lane, inside, in);
-  fast_compute_store<EQ, FLUX, STAGE, WITH_MAX>(p, row, c0, lane, inside, in, out);
-}
+static int g_fast_layout = 0;   // 0: 120 cells per warp (halo lanes), 1: 126 cells per warp, 2: 120 + shared t / pq
 
 // ---------------------------------------------------------------------------
 // The specialised stage kernel FUSED with the ghost-cell exchange of a slab-decomposed grid
@@ -767,6 +566,41 @@ stage_warp_fast_p2p_kernel(const FastParams p, const HaloLink h) {
   }
 }
 
+// Layout / occupancy / load-placement variants of the specialised kernel.  The registers-per-
+// thread (MINB) and late-u0 (LATE) variants exist for the hot configuration only (Burgers +
+// Rusanov); every other scheme gets the plain form of the selected layout.
+static int g_fast_minb = PSK_FAST_MIN_BLOCKS;  // CTAs of 256 threads per SM the compiler must fit (4: 64 registers, 3: 80)
+static int g_fast_late = 0;                    // 0: u0 loaded with the stage input, 1: after the reconstruction, 2: after the fluxes
+
+#define PSK_FAST_LAUNCH(KERNEL, MINB, LATE) \
+  KERNEL<EQ, FLUX, STAGE, WITH_MAX, MINB, LATE><<<grid, threads, 0, st>>>(q)
+#define PSK_FAST_LAUNCH_HOT(KERNEL)                                                \
+  do {                                                                             \
+    if (g_fast_minb == 3) {                                                        \
+      if (g_fast_late == 2) PSK_FAST_LAUNCH(KERNEL, 3, 2);                         \
+      else if (g_fast_late == 1) PSK_FAST_LAUNCH(KERNEL, 3, 1);                    \
+      else PSK_FAST_LAUNCH(KERNEL, 3, 0);                                          \
+    } else {                                                                       \
+      if (g_fast_late == 2) PSK_FAST_LAUNCH(KERNEL, PSK_FAST_MIN_BLOCKS, 2);       \
+      else if (g_fast_late == 1) PSK_FAST_LAUNCH(KERNEL, PSK_FAST_MIN_BLOCKS, 1);  \
+      else PSK_FAST_LAUNCH(KERNEL, PSK_FAST_MIN_BLOCKS, 0);                        \
+    }                                                                              \
+  } while (0)
+
+template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
+void launch_fast_layout(dim3 grid, int threads, cudaStream_t st, const FastParams &q) {
+  constexpr bool kHot = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV && !WITH_MAX && STAGE != 0);
+  if (g_fast_layout == 1) {
+    if constexpr (kHot) PSK_FAST_LAUNCH_HOT(stage_warp_fast126_kernel);
+    else PSK_FAST_LAUNCH(stage_warp_fast126_kernel, PSK_FAST_MIN_BLOCKS, 0);
+  } else if (g_fast_layout == 2) {
+    if constexpr (kHot) PSK_FAST_LAUNCH_HOT(stage_warp_fast_share_kernel);
+    else PSK_FAST_LAUNCH(stage_warp_fast_share_kernel, PSK_FAST_MIN_BLOCKS, 0);
+  } else {
+    stage_warp_fast_kernel<EQ, FLUX, STAGE, WITH_MAX><<<grid, threads, 0, st>>>(q);
+  }
+}
+
 template <int EQ, int FLUX, int STAGE>
 int launch_fast_stage(const StageParams &p, int batch, cudaStream_t st) {
   FastParams q{};
@@ -775,23 +609,19 @@ int launch_fast_stage(const StageParams &p, int batch, cudaStream_t st) {
   q.coef = p.invdx / FluxScale<EQ, FLUX>::value;
   q.eps9 = p.eps * (1.0 / 9.0);
   q.dt_stride = static_cast<int>(p.dt_stride);
-  q.chunks_per_row = (p.bc.n + 119) / 120;
-  // warps per CTA: the divisor-friendly choice in 4..8 that wastes the fewest warps
-  int wpc = 8, best_waste = 1 << 30;
-  for (int w = g_fast_wpc_max; w >= 4; --w) {
-    const int waste = ((q.chunks_per_row + w - 1) / w) * w - q.chunks_per_row;
-    if (waste < best_waste) { best_waste = waste; wpc = w; }
-  }
-  if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
+  const FastGeometry geo = fast_geometry(g_fast_layout, p.bc.n, g_fast_wpc_max);
+  q.chunks_per_row = geo.chunks_per_row;
+  const int wpc = geo.wpc;
   const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
   const unsigned gy = batch < 65535 ? batch : 65535u;
   if (batch % gy != 0 && batch > 65535) return PSK_E_UNSUPPORTED;  // caller falls back
   const unsigned gz = batch / gy;
   const dim3 grid(gx, gy, gz);
+  const int threads = wpc * 32;
   if (p.maxabs != nullptr)
-    stage_warp_fast_kernel<EQ, FLUX, STAGE, true><<<grid, wpc * 32, 0, st>>>(q);
+    launch_fast_layout<EQ, FLUX, STAGE, true>(grid, threads, st, q);
   else
-    stage_warp_fast_kernel<EQ, FLUX, STAGE, false><<<grid, wpc * 32, 0, st>>>(q);
+    launch_fast_layout<EQ, FLUX, STAGE, false>(grid, threads, st, q);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
 }
@@ -1233,6 +1063,15 @@ int psk_version(void) { return PSK_VERSION; }
 /* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
  * kernel (default), 1 = shared-memory tile kernel */
 int psk_set_stage_variant(int variant) {
+  if (variant >= 5000) {  // 5000 + 100 (3 - minb) + 10 late + layout of the specialised kernel
+    const int v = variant - 5000;
+    const int layout = v % 10, late = (v / 10) % 10, fewer = v / 100;
+    if (layout > 2 || late > 2 || fewer > 1) return PSK_E_INVALID;
+    g_fast_layout = layout;  // 0: 120 cells per warp, 1: 126, 2: 120 + shared t / pq
+    g_fast_late = late;
+    g_fast_minb = fewer ? 3 : PSK_FAST_MIN_BLOCKS;
+    return PSK_OK;
+  }
   if (variant >= 4000) {  // 4000 + max warps per CTA of the specialised kernel (4..8)
     if (variant - 4000 < 4 || variant - 4000 > 8) return PSK_E_INVALID;
     g_fast_wpc_max = variant - 4000;

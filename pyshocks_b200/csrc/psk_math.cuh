@@ -84,7 +84,11 @@ __device__ __forceinline__ double weno32_side_strict(double m1, double c, double
 // non-zero x (the WENO denominators are >= eps^4 > 0).
 __device__ __forceinline__ double fast_rcp(double x) {
   double y0;
+#ifdef PSK_HOST_EMU  // host build of the kernels for the CPU tests (tests/host/emu/cuda_runtime.h)
+  y0 = psk_emu_rcp_seed(x);
+#else
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+#endif
   double e = fma(-x, y0, 1.0);
   double t = fma(e, e, e);
   return fma(y0, t, y0);

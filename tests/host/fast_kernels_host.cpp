@@ -1,0 +1,146 @@
+// Host build (g++, no CUDA) of the specialised stage kernels, pyshocks_b200/csrc/psk_fast_kernels.cuh:
+// the very device code of the product, run under the warp emulation of tests/host/emu/cuda_runtime.h
+// (32 OS threads per warp, shuffles through barriers).  tests/test_fast_kernels_host.py checks
+// every layout variant against the CPU oracle with it -- indexing, halo traffic, boundary
+// handling, tails -- without a GPU.  Test infrastructure only.
+#include <cuda_runtime.h>  // tests/host/emu/cuda_runtime.h (-I tests/host/emu)
+
+#include <thread>
+#include <vector>
+
+#include "../../pyshocks_b200/csrc/psk_fast_kernels.cuh"
+
+namespace emu {
+thread_local emu_uint3 tid, bid, bdim, gdim;
+thread_local Warp *warp = nullptr;
+thread_local int lane = 0;
+}  // namespace emu
+
+namespace psk {
+thread_local int g_last_cuda_error = 0;
+}
+
+namespace {
+
+using Kernel = void (*)(const psk::FastParams);
+
+template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
+Kernel pick_layout(int layout, int late) {
+  constexpr bool kHot = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV);
+  constexpr int M = PSK_FAST_MIN_BLOCKS;
+  if (layout == 1) {
+    if constexpr (kHot) {
+      if (late == 1) return &psk::stage_warp_fast126_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 1>;
+      if (late == 2) return &psk::stage_warp_fast126_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 2>;
+    }
+    return &psk::stage_warp_fast126_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 0>;
+  }
+  if (layout == 2) {
+    if constexpr (kHot) {
+      if (late == 1) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 1>;
+      if (late == 2) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 2>;
+    }
+    return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 0>;
+  }
+  return &psk::stage_warp_fast_kernel<EQ, FLUX, STAGE, WITH_MAX>;
+}
+
+template <int EQ, int FLUX>
+Kernel pick_stage(int stage, bool with_max, int layout, int late) {
+  switch (stage * 2 + (with_max ? 1 : 0)) {
+    case 0: return pick_layout<EQ, FLUX, 0, false>(layout, late);
+    case 1: return pick_layout<EQ, FLUX, 0, true>(layout, late);
+    case 2: return pick_layout<EQ, FLUX, 1, false>(layout, late);
+    case 3: return pick_layout<EQ, FLUX, 1, true>(layout, late);
+    case 4: return pick_layout<EQ, FLUX, 2, false>(layout, late);
+    case 5: return pick_layout<EQ, FLUX, 2, true>(layout, late);
+    case 6: return pick_layout<EQ, FLUX, 3, false>(layout, late);
+    default: return pick_layout<EQ, FLUX, 3, true>(layout, late);
+  }
+}
+
+template <int EQ, int FLUX>
+double flux_scale() {
+  return psk::FluxScale<EQ, FLUX>::value;
+}
+
+}  // namespace
+
+extern "C" {
+
+// One stage of the specialised kernel over `batch` rows, launched with the product's own geometry
+// (psk::fast_geometry).  Returns 0, or -1 for a scheme the specialised kernels do not cover.
+int emu_fast_stage(int layout, int late, int equation, int flux, int stage, int with_max, int bc, int n, int g,
+                   int batch, long long ld, double dx, double eps, const double *uin, const double *u0,
+                   double *uout, const double *dt, int dt_stride, const double *ghost, long long ghost_ld,
+                   const double *lf_speed, unsigned long long *maxabs, const double *vel, const double *vel_l,
+                   const double *vel_r, int wpc_max) {
+  Kernel k = nullptr;
+  double scale = 1.0;
+  if (equation == PSK_EQ_BURGERS) {
+    switch (flux) {
+      case PSK_FLUX_RUSANOV:
+        k = pick_stage<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV>(stage, with_max, layout, late);
+        scale = flux_scale<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV>();
+        break;
+      case PSK_FLUX_LAX_FRIEDRICHS:
+        k = pick_stage<PSK_EQ_BURGERS, PSK_FLUX_LAX_FRIEDRICHS>(stage, with_max, layout, late);
+        scale = flux_scale<PSK_EQ_BURGERS, PSK_FLUX_LAX_FRIEDRICHS>();
+        break;
+      case PSK_FLUX_UPWIND:
+        k = pick_stage<PSK_EQ_BURGERS, PSK_FLUX_UPWIND>(stage, with_max, layout, late);
+        scale = flux_scale<PSK_EQ_BURGERS, PSK_FLUX_UPWIND>();
+        break;
+      case PSK_FLUX_ENGQUIST_OSHER:
+        k = pick_stage<PSK_EQ_BURGERS, PSK_FLUX_ENGQUIST_OSHER>(stage, with_max, layout, late);
+        scale = flux_scale<PSK_EQ_BURGERS, PSK_FLUX_ENGQUIST_OSHER>();
+        break;
+      default: return -1;
+    }
+  } else if (equation == PSK_EQ_ADVECTION && flux == PSK_FLUX_UPWIND) {
+    k = pick_stage<PSK_EQ_ADVECTION, PSK_FLUX_UPWIND>(stage, with_max, layout, late);
+  } else if (equation == PSK_EQ_CONTINUITY && flux == PSK_FLUX_UPWIND) {
+    k = pick_stage<PSK_EQ_CONTINUITY, PSK_FLUX_UPWIND>(stage, with_max, layout, late);
+  } else {
+    return -1;
+  }
+
+  psk::FastParams q{};
+  q.uin = uin; q.u0 = u0; q.uout = uout; q.dt = dt; q.lf_speed = lf_speed;
+  q.maxabs = with_max ? maxabs : nullptr;
+  q.vel = vel; q.vel_l = vel_l; q.vel_r = vel_r;
+  q.bc.ghost = ghost; q.bc.ghost_ld = ghost_ld; q.bc.bc = bc; q.bc.n = n; q.bc.g = g; q.bc.nx = n + 2 * g;
+  q.ld = ld;
+  q.coef = (1.0 / dx) / scale;
+  q.eps9 = eps * (1.0 / 9.0);
+  q.dt_stride = dt_stride;
+  const psk::FastGeometry geo = psk::fast_geometry(layout, n, wpc_max);
+  q.chunks_per_row = geo.chunks_per_row;
+  const unsigned gx = static_cast<unsigned>((geo.chunks_per_row + geo.wpc - 1) / geo.wpc);
+
+  emu::Warp warp;
+  pthread_barrier_init(&warp.bar, nullptr, 32);
+  std::vector<std::thread> lanes;
+  for (int lane = 0; lane < 32; ++lane) {
+    lanes.emplace_back([&, lane]() {
+      emu::warp = &warp;
+      emu::lane = lane;
+      emu::bdim = {static_cast<unsigned>(geo.wpc * 32), 1u, 1u};
+      emu::gdim = {gx, static_cast<unsigned>(batch), 1u};
+      for (unsigned by = 0; by < static_cast<unsigned>(batch); ++by)
+        for (unsigned bx = 0; bx < gx; ++bx)
+          for (int wi = 0; wi < geo.wpc; ++wi) {
+            emu::bid = {bx, by, 0u};
+            emu::tid = {static_cast<unsigned>(wi * 32 + lane), 0u, 0u};
+            k(q);
+          }
+    });
+  }
+  for (auto &t : lanes) t.join();
+  pthread_barrier_destroy(&warp.bar);
+  return 0;
+}
+
+int emu_chunks_per_row(int layout, int n) { return psk::fast_geometry(layout, n, 8).chunks_per_row; }
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""The specialised stage kernels of the product (pyshocks_b200/csrc/psk_fast_kernels.cuh: the
+120-cell warp layout, the 126-cell layout, the shared-difference layout and their late-u0
+forms) compiled for the HOST and run under a 32-thread warp emulation
+(tests/host/fast_kernels_host.cpp, tests/host/emu/cuda_runtime.h), against the C oracle
+(oracle/psk_oracle.c, the restatement of schemes.py:339-346 / scalar.py / reconstruction.py /
+timestepping.py:312-320).  What this pins without a GPU: the lane -> cell maps, the halo shuffles
+and halo loads, the row tails, the boundary conditions and that every layout performs the SAME
+arithmetic per cell (bitwise equal outputs)."""
+
+from __future__ import annotations
+
+import ctypes as ct
+import pathlib
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.c_oracle import BC, EQUATION, FLUX, COracle
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+G = 3
+EPS = 1.0e-12
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    out = tmp_path_factory.mktemp("emu") / "libfastemu.so"
+    subprocess.run([gxx, "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-pthread",
+                    "-I", str(ROOT / "tests" / "host" / "emu"), "-o", str(out),
+                    str(ROOT / "tests" / "host" / "fast_kernels_host.cpp")], check=True)
+    lib = ct.CDLL(str(out))
+    dp, up = ct.POINTER(ct.c_double), ct.POINTER(ct.c_ulonglong)
+    lib.emu_fast_stage.argtypes = [ct.c_int] * 10 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, dp,
+                                                     ct.c_int, dp, ct.c_longlong, dp, up, dp, dp, dp, ct.c_int]
+    lib.emu_fast_stage.restype = ct.c_int
+    lib.emu_chunks_per_row.argtypes = [ct.c_int, ct.c_int]
+    lib.emu_chunks_per_row.restype = ct.c_int
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ct.POINTER(ct.c_double))
+
+
+class Problem:
+    """one bound scheme on (batch, nx) host rows + the matching C oracle"""
+
+    def __init__(self, equation: str, flux: str, bc: str, n: int, batch: int, seed: int = 0) -> None:
+        self.equation, self.flux, self.bc, self.n, self.batch = equation, flux, bc, n, batch
+        self.nx = n + 2 * G
+        self.dx = 3.0 / n
+        rng = np.random.default_rng(seed)
+        x = (np.arange(self.nx) - G + 0.5) / n
+        self.u = np.stack([
+            rng.uniform(-0.5, 0.5) + sum(rng.uniform(0, 1 / k) * np.sin(2 * np.pi * k * x + rng.uniform(0, 6.28))
+                                          for k in range(1, 5))
+            for _ in range(batch)
+        ])
+        # a discontinuity in every row: the nonlinear weights leave their smooth-data values
+        self.u[:, G + n // 3 : G + n // 2] += 0.7
+        velocity = None
+        if equation != "burgers":
+            velocity = 1.0 + 0.3 * np.sin(2 * np.pi * x + 0.3)
+        self.co = COracle(equation=equation, flux=flux, rec="wenojs53", bc=bc, n=n, g=G, batch=batch,
+                          dx=self.dx, eps=EPS, velocity=velocity)
+        self.ghost = None
+        if bc in ("dirichlet", "neumann"):
+            self.ghost = rng.uniform(-0.2, 0.2, size=(batch, 2 * G)) * (1.0 if bc == "dirichlet" else self.dx)
+            self.co.set_ghost(self.ghost)
+        self.dt = (0.3 * self.dx / np.abs(self.u).max(axis=1)) * rng.uniform(0.5, 1.0, size=batch)
+
+    def stage(self, lib, layout: int, late: int, stage: int, uin, u0, with_max: bool = False, wpc_max: int = 8):
+        out = np.full_like(uin, np.nan)
+        maxabs = np.zeros(self.batch, dtype=np.uint64)
+        lf = None
+        if self.flux == "lf":
+            lf = np.abs(self.co.apply_boundary(uin)).max(axis=1)
+        k = self.co.keep
+        rc = lib.emu_fast_stage(layout, late, EQUATION[self.equation], FLUX[self.flux], stage, int(with_max),
+                                BC[self.bc], self.n, G, self.batch, self.nx, self.dx, EPS, _p(uin), _p(u0), _p(out),
+                                _p(self.dt), 1, _p(self.ghost), 0 if self.ghost is None else 2 * G, _p(lf),
+                                maxabs.ctypes.data_as(ct.POINTER(ct.c_ulonglong)), _p(k.get("v")), _p(k.get("vl")),
+                                _p(k.get("vr")), wpc_max)
+        assert rc == 0
+        return out, maxabs.view(np.float64)
+
+    def step(self, lib, layout: int, late: int = 0, with_max: bool = False):
+        k1, _ = self.stage(lib, layout, late, 1, self.u, self.u)
+        k1 = self.fill(k1)
+        k2, _ = self.stage(lib, layout, late, 2, k1, self.u)
+        k2 = self.fill(k2)
+        out, mx = self.stage(lib, layout, late, 3, k2, self.u, with_max=with_max)
+        return out, mx
+
+    def fill(self, a):
+        """the kernels write interior cells only; the stored ghost cells are never read for periodic /
+        Dirichlet / Neumann rows, so any finite filler will do"""
+        a = a.copy()
+        a[:, :G] = 123.0
+        a[:, self.nx - G :] = -321.0
+        return a
+
+    @property
+    def interior(self):
+        return slice(G, G + self.n)
+
+
+SCHEMES = [("burgers", "rusanov"), ("burgers", "lf"), ("burgers", "godunov"), ("burgers", "eo"),
+           ("advection", "godunov"), ("continuity", "godunov")]
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("equation,flux", SCHEMES)
+@pytest.mark.parametrize("bc", ["periodic", "dirichlet"])
+def test_step_matches_oracle(emu, layout: int, equation: str, flux: str, bc: str) -> None:
+    pb = Problem(equation, flux, bc, n=250, batch=2, seed=7)
+    got, _ = pb.step(emu, layout)
+    ref = pb.co.ssprk33_step(pb.u, pb.dt)
+    i = pb.interior
+    assert np.isfinite(got[:, i]).all()
+    err = np.abs(got[:, i] - ref[:, i]).max() / np.abs(ref[:, i]).max()
+    assert err < 2e-13, err
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 119, 120, 121, 125, 126, 127, 128, 129, 240, 252, 253, 379, 504, 1000])
+@pytest.mark.parametrize("bc", ["periodic", "neumann"])
+def test_layouts_are_bitwise_equal_at_row_tails(emu, n: int, bc: str) -> None:
+    """same arithmetic per cell whatever the lane / chunk a cell falls into, for every tail length"""
+    pb = Problem("burgers", "rusanov", bc, n=n, batch=2, seed=n)
+    ref = pb.co.ssprk33_step(pb.u, pb.dt)
+    i = pb.interior
+    base, mx0 = pb.step(emu, 0, with_max=True)
+    err = np.abs(base[:, i] - ref[:, i]).max() / np.abs(ref[:, i]).max()
+    assert err < 2e-13, err
+    assert np.array_equal(mx0, np.abs(base[:, i]).max(axis=1))
+    for layout in (1, 2):
+        for late in (0, 1, 2):
+            got, mx = pb.step(emu, layout, late, with_max=True)
+            assert np.array_equal(got[:, i], base[:, i]), (layout, late)
+            assert np.array_equal(mx, mx0)
+            # nothing outside the interior is written
+            assert np.isnan(got[:, :G]).all() and np.isnan(got[:, G + n :]).all()
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+def test_stage0_is_the_operator(emu, layout: int) -> None:
+    pb = Problem("burgers", "rusanov", "periodic", n=300, batch=1, seed=3)
+    got, _ = pb.stage(emu, layout, 0, 0, pb.u, pb.u)
+    ref = pb.co.apply_operator(pb.u)
+    i = pb.interior
+    assert np.abs(got[:, i] - ref[:, i]).max() <= 2e-13 * np.abs(ref[:, i]).max()
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+def test_shift_equivariance_is_bitwise(emu, layout: int) -> None:
+    """periodic rows: rolling the data by k cells rolls the result by k cells, bit for bit"""
+    pb = Problem("burgers", "rusanov", "periodic", n=504, batch=1, seed=5)
+    a, _ = pb.step(emu, layout)
+    i = pb.interior
+    for k in (1, 2, 3, 125, 377):
+        pb2 = Problem("burgers", "rusanov", "periodic", n=504, batch=1, seed=5)
+        pb2.u[:, i] = np.roll(pb.u[:, i], k, axis=1)
+        b, _ = pb2.step(emu, layout)
+        assert np.array_equal(np.roll(a[:, i], k, axis=1), b[:, i]), k
+
+
+def test_geometry(emu) -> None:
+    assert emu.emu_chunks_per_row(0, 4096) == 35
+    assert emu.emu_chunks_per_row(1, 4096) == 33
+    assert emu.emu_chunks_per_row(2, 4096) == 35
+    for n in (1, 126, 127, 252, 253):
+        assert emu.emu_chunks_per_row(1, n) == -(-n // 126)

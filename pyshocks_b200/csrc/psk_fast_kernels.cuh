@@ -258,16 +258,17 @@ __device__ __forceinline__ void fast_load_u0(const double *__restrict__ src, boo
   }
 }
 
-// Ties a pointer to a value the compiler has only late in the kernel, so that the loads
-// through it cannot be hoisted above that point (LATE variants: u0 is fetched after the
+// Ties an element offset to a value the compiler has only late in the kernel, so that the loads
+// at that offset cannot be hoisted above that point (LATE variants: u0 is fetched after the
 // reconstruction, which takes its 8 registers out of the most crowded part of the kernel).
-__device__ __forceinline__ const double *after(const double *ptr, double late) {
+// The offset, not the pointer, is laundered: the loads stay ld.global.
+__device__ __forceinline__ int64_t after(int64_t off, double late) {
 #ifndef PSK_HOST_EMU
-  asm volatile("" : "+l"(ptr) : "d"(late));
+  asm volatile("" : "+l"(off) : "d"(late));
 #else
   (void)late;
 #endif
-  return ptr;
+  return off;
 }
 
 // ---------------------------------------------------------------------------
@@ -333,7 +334,7 @@ stage_warp_fast126_kernel(const FastParams p) {
 
   double t[R + 3], pq[R + 2];
 #pragma unroll
-  for (int k = 0; k < R + 3; ++k) t[k] = (1.0 / 6.0) * (w[k + 1] - w[k]);
+  for (int k = 0; k < R + 3; ++k) t[k] = __dmul_rn(1.0 / 6.0, w[k + 1] - w[k]);
 #pragma unroll
   for (int k = 0; k < R + 2; ++k) {
     const double dd = t[k + 1] - t[k];
@@ -342,13 +343,13 @@ stage_warp_fast126_kernel(const FastParams p) {
   double ul[R], ur[R];  // of the cells c0-1 .. c0+2
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const Weno5Pair o = weno53_pair_lean(w[r + 2], t[r], t[r + 1], t[r + 2], t[r + 3], pq[r], pq[r + 1], pq[r + 2]);
+    const Weno5Pair o = weno53_pair_lean2(w[r + 2], t[r], t[r + 1], t[r + 2], t[r + 3], pq[r], pq[r + 1], pq[r + 2]);
     ul[r] = o.ul;
     ur[r] = o.ur;
   }
   const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);   // of cell c0-2
   const double ul_right = __shfl_down_sync(kFull, ul[0], 1);    // of cell c0+3
-  if (LATE == 1) fast_load_u0<STAGE>(after(p.u0 + off, ur[R - 1]), inside, n - c0, u0v);
+  if (LATE == 1) fast_load_u0<STAGE>(p.u0 + after(off, ur[R - 1]), inside, n - c0, u0v);
 
   // -2 s of the scaled Rusanov flux: -2 max(|a|, |b|) = the larger magnitude of -2|a|, -2|b|, one
   // DMUL per CELL (|.| is an operand modifier) instead of an FP64 abs per cell and a DMUL per face
@@ -387,7 +388,7 @@ stage_warp_fast126_kernel(const FastParams p) {
 #pragma unroll
   for (int r = 0; r < R - 1; ++r) dFa[r] = F[r + 1] - F[r + 2];
   dFa[R - 1] = __shfl_down_sync(kFull, F[0] - F[1], 1);
-  if (LATE == 2) fast_load_u0<STAGE>(after(p.u0 + off, dFa[0]), inside, n - c0, u0v);
+  if (LATE == 2) fast_load_u0<STAGE>(p.u0 + after(off, dFa[0]), inside, n - c0, u0v);
 
   double coef = p.coef;
   if (STAGE != 0) coef *= p.dt[static_cast<int64_t>(row) * p.dt_stride];
@@ -449,16 +450,14 @@ stage_warp_fast_share_kernel(const FastParams p) {
   double u0v[R] = {0.0, 0.0, 0.0, 0.0};
   if (LATE == 0 && emit) fast_load_u0<STAGE>(p.u0 + off, inside, n - c0, u0v);
 
-  // cells c0-1 .. c0+4 (the Rusanov speed of the two outer faces needs the two outer ones)
-  double w[R + 2];
+  double w[R + 1];  // cells c0-1 .. c0+3
 #pragma unroll
   for (int r = 0; r < R; ++r) w[1 + r] = in.v[r];
   w[0] = __shfl_up_sync(kFull, w[R], 1);
-  w[R + 1] = __shfl_down_sync(kFull, w[1], 1);
   // t[k]: sixth of the first difference over the interval (c0-2+k, c0-1+k), k = 0..6; own: k = 1..4
   double t[R + 3];
 #pragma unroll
-  for (int k = 1; k <= R; ++k) t[k] = (1.0 / 6.0) * (w[k] - w[k - 1]);
+  for (int k = 1; k <= R; ++k) t[k] = __dmul_rn(1.0 / 6.0, w[k] - w[k - 1]);
   t[0] = __shfl_up_sync(kFull, t[R], 1);
   t[R + 1] = __shfl_down_sync(kFull, t[1], 1);
   t[R + 2] = __shfl_down_sync(kFull, t[2], 1);
@@ -475,20 +474,21 @@ stage_warp_fast_share_kernel(const FastParams p) {
   double ul[R], ur[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    const Weno5Pair o = weno53_pair_lean(w[1 + r], t[r], t[r + 1], t[r + 2], t[r + 3], pq[r], pq[r + 1], pq[r + 2]);
+    const Weno5Pair o = weno53_pair_lean2(w[1 + r], t[r], t[r + 1], t[r + 2], t[r + 3], pq[r], pq[r + 1], pq[r + 2]);
     ul[r] = o.ul;
     ur[r] = o.ur;
   }
   const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
   const double ul_right = __shfl_down_sync(kFull, ul[0], 1);
-  if (LATE == 1 && emit) fast_load_u0<STAGE>(after(p.u0 + off, ur[R - 1]), inside, n - c0, u0v);
+  if (LATE == 1 && emit) fast_load_u0<STAGE>(p.u0 + after(off, ur[R - 1]), inside, n - c0, u0v);
 
   // -2 s of the scaled Rusanov flux as in stage_warp_fast126_kernel
   const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? -2.0 * p.lf_speed[row] : 0.0;
-  double m2[R + 2];  // cells c0-1 .. c0+4
+  double m2[R + 2];  // cells c0-1 .. c0+4, the last one from the lane to the right
   if (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV) {
 #pragma unroll
-    for (int j = 0; j < R + 2; ++j) m2[j] = -2.0 * fabs(w[j]);
+    for (int j = 0; j <= R; ++j) m2[j] = -2.0 * fabs(w[j]);
+    m2[R + 1] = __shfl_down_sync(kFull, m2[1], 1);
   }
   double F[R + 1];
 #pragma unroll
@@ -515,7 +515,7 @@ stage_warp_fast_share_kernel(const FastParams p) {
     }
   }
 
-  if (LATE == 2 && emit) fast_load_u0<STAGE>(after(p.u0 + off, F[0]), inside, n - c0, u0v);
+  if (LATE == 2 && emit) fast_load_u0<STAGE>(p.u0 + after(off, F[0]), inside, n - c0, u0v);
   double coef = p.coef;
   if (STAGE != 0) coef *= p.dt[static_cast<int64_t>(row) * p.dt_stride];
   double out[R];

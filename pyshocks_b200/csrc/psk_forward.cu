@@ -595,7 +595,7 @@ void launch_fast_layout(dim3 grid, int threads, cudaStream_t st, const FastParam
     else PSK_FAST_LAUNCH(stage_warp_fast126_kernel, PSK_FAST_MIN_BLOCKS, 0);
   } else if (g_fast_layout == 2) {
     if constexpr (kHot) PSK_FAST_LAUNCH_HOT(stage_warp_fast_share_kernel);
-    else PSK_FAST_LAUNCH(stage_warp_fast_share_kernel, PSK_FAST_MIN_BLOCKS, 0);
+    else PSK_FAST_LAUNCH(stage_warp_fast_share_kernel, PSK_FAST_MIN_BLOCKS, 1);  // LATE = 0 spills at 64 registers
   } else {
     stage_warp_fast_kernel<EQ, FLUX, STAGE, WITH_MAX><<<grid, threads, 0, st>>>(q);
   }

@@ -40,6 +40,7 @@ Kernel pick_layout(int layout, int late) {
       if (late == 1) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 1>;
       if (late == 2) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 2>;
     }
+    if (!kHot) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 1>;  // as launch_fast_layout
     return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 0>;
   }
   return &psk::stage_warp_fast_kernel<EQ, FLUX, STAGE, WITH_MAX>;

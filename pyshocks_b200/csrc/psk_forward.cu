@@ -334,13 +334,10 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
   // ---- face values of the owned cells
   double ul[R], ur[R];
   if (REC == PSK_REC_WENOJS53 && !STRICT) {
-    double t[R + 5], tw[R + 5], pq[R + 4];
+    double t[R + 5], pq[R + 4];
     const double eps9 = p.eps * (1.0 / 9.0);
 #pragma unroll
-    for (int k = 0; k < R + 5; ++k) {
-      t[k] = (1.0 / 6.0) * (v[k + 1] - v[k]);
-      tw[k] = t[k] + t[k];
-    }
+    for (int k = 0; k < R + 5; ++k) t[k] = __dmul_rn(1.0 / 6.0, v[k + 1] - v[k]);
 #pragma unroll
     for (int k = 0; k < R + 4; ++k) {
       const double dd = t[k + 1] - t[k];  // centred at v[k + 1]
@@ -349,8 +346,8 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int m = r + kHalo;
-      const Weno5Pair o = weno53_pair_sixths(v[m], t[m - 2], t[m - 1], t[m], t[m + 1], tw[m - 2],
-                                             tw[m - 1], tw[m], tw[m + 1], pq[m - 2], pq[m - 1], pq[m]);
+      // the same function as the specialised kernels: the two paths give the same bits
+      const Weno5Pair o = weno53_pair_lean(v[m], t[m - 2], t[m - 1], t[m], t[m + 1], pq[m - 2], pq[m - 1], pq[m]);
       ul[r] = o.ul;
       ur[r] = o.ur;
     }
@@ -463,7 +460,7 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
 }
 
 static int g_fast_wpc_max = 8;  // largest CTA (in warps) the specialised kernel may use (tuning)
-static int g_fast_layout = 0;   // 0: 120 cells per warp (halo lanes), 1: 126 cells per warp, 2: 120 + shared t / pq
+static int g_fast_layout = 2;   // 0: 120 cells per warp (halo lanes), 1: 126 cells per warp, 2: 120 + shared t / pq (default: +4 %)
 
 // ---------------------------------------------------------------------------
 // The specialised stage kernel FUSED with the ghost-cell exchange of a slab-decomposed grid
@@ -569,17 +566,19 @@ stage_warp_fast_p2p_kernel(const FastParams p, const HaloLink h) {
 // Layout / occupancy / load-placement variants of the specialised kernel.  The registers-per-
 // thread (MINB) and late-u0 (LATE) variants exist for the hot configuration only (Burgers +
 // Rusanov); every other scheme gets the plain form of the selected layout.
-static int g_fast_minb = PSK_FAST_MIN_BLOCKS;  // CTAs of 256 threads per SM the compiler must fit (4: 64 registers, 3: 80)
+static int g_fast_pf_rows = 0;  // L2 prefetch distance in rows (fast_prefetch), 0 = off
+static int g_fast_pf_mode = 1;
+static int g_fast_minb = PSK_FAST_MIN_BLOCKS;  // 4: CTAs of <= 256 threads, 64 registers; 5: CTAs of <= 224 threads, 58 registers (hot configuration only)
 static int g_fast_late = 0;                    // 0: u0 loaded with the stage input, 1: after the reconstruction, 2: after the fluxes
 
 #define PSK_FAST_LAUNCH(KERNEL, MINB, LATE) \
   KERNEL<EQ, FLUX, STAGE, WITH_MAX, MINB, LATE><<<grid, threads, 0, st>>>(q)
 #define PSK_FAST_LAUNCH_HOT(KERNEL)                                                \
   do {                                                                             \
-    if (g_fast_minb == 3) {                                                        \
-      if (g_fast_late == 2) PSK_FAST_LAUNCH(KERNEL, 3, 2);                         \
-      else if (g_fast_late == 1) PSK_FAST_LAUNCH(KERNEL, 3, 1);                    \
-      else PSK_FAST_LAUNCH(KERNEL, 3, 0);                                          \
+    if (g_fast_minb == 5) {                                                        \
+      if (g_fast_late == 2) PSK_FAST_LAUNCH(KERNEL, 5, 2);                         \
+      else if (g_fast_late == 1) PSK_FAST_LAUNCH(KERNEL, 5, 1);                    \
+      else PSK_FAST_LAUNCH(KERNEL, 5, 0);                                          \
     } else {                                                                       \
       if (g_fast_late == 2) PSK_FAST_LAUNCH(KERNEL, PSK_FAST_MIN_BLOCKS, 2);       \
       else if (g_fast_late == 1) PSK_FAST_LAUNCH(KERNEL, PSK_FAST_MIN_BLOCKS, 1);  \
@@ -609,8 +608,13 @@ int launch_fast_stage(const StageParams &p, int batch, cudaStream_t st) {
   q.coef = p.invdx / FluxScale<EQ, FLUX>::value;
   q.eps9 = p.eps * (1.0 / 9.0);
   q.dt_stride = static_cast<int>(p.dt_stride);
-  const FastGeometry geo = fast_geometry(g_fast_layout, p.bc.n, g_fast_wpc_max);
+  constexpr bool kHotCfg = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV && STAGE != 0);
+  const bool small_cta = kHotCfg && g_fast_minb == 5 && g_fast_layout != 0 && p.maxabs == nullptr;
+  const FastGeometry geo = fast_geometry(g_fast_layout, p.bc.n, (small_cta && g_fast_wpc_max > 7) ? 7 : g_fast_wpc_max);
   q.chunks_per_row = geo.chunks_per_row;
+  q.rows = batch;
+  q.pf_rows = g_fast_pf_rows;
+  q.pf_mode = g_fast_pf_mode;
   const int wpc = geo.wpc;
   const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
   const unsigned gy = batch < 65535 ? batch : 65535u;
@@ -1063,13 +1067,20 @@ int psk_version(void) { return PSK_VERSION; }
 /* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
  * kernel (default), 1 = shared-memory tile kernel */
 int psk_set_stage_variant(int variant) {
-  if (variant >= 5000) {  // 5000 + 100 (3 - minb) + 10 late + layout of the specialised kernel
+  if (variant >= 6000) {  // 6000 + 10 * (L2 prefetch distance in rows) + mode (1: per lane, 2: bulk); 6000 = off
+    const int v = variant - 6000;
+    if (v % 10 > 2 || v / 10 > 4096) return PSK_E_INVALID;
+    g_fast_pf_rows = (v % 10) ? v / 10 : 0;
+    g_fast_pf_mode = (v % 10) ? v % 10 : 1;
+    return PSK_OK;
+  }
+  if (variant >= 5000) {  // 5000 + 100 (5 CTAs of 224 threads) + 10 late + layout of the specialised kernel
     const int v = variant - 5000;
-    const int layout = v % 10, late = (v / 10) % 10, fewer = v / 100;
+    const int layout = v % 10, late = (v / 10) % 10, fewer = v / 100;  // "fewer" registers: 5 CTAs of 224 threads
     if (layout > 2 || late > 2 || fewer > 1) return PSK_E_INVALID;
     g_fast_layout = layout;  // 0: 120 cells per warp, 1: 126, 2: 120 + shared t / pq
     g_fast_late = late;
-    g_fast_minb = fewer ? 3 : PSK_FAST_MIN_BLOCKS;
+    g_fast_minb = fewer ? 5 : PSK_FAST_MIN_BLOCKS;
     return PSK_OK;
   }
   if (variant >= 4000) {  // 4000 + max warps per CTA of the specialised kernel (4..8)

@@ -144,85 +144,26 @@ __device__ __forceinline__ Weno5Pair weno53_pair_fast(double c, double dm2, doub
   return out;
 }
 
-// Leaner variant used by the warp kernel.  All quantities are in units of SIXTHS of the
-// first differences, t = (u[k+1] - u[k]) / 6 (tw = 2 t), which turns the candidate offsets
-// into small-integer combinations:
+// The pair used by every FAST WENO-JS5 stage kernel.  All quantities are in units of SIXTHS of the
+// first differences, t = (u[k+1] - u[k]) / 6, which turns the candidate offsets into small-integer
+// combinations,
 //   right: q0 - c = 5 t(-1) - 2 t(-2), q1 - c = 2 t(0) + t(-1), q2 - c = 4 t(0) - t(+1)
 //   left : q0 - c = t(-2) - 4 t(-1),   q1 - c = -(2 t(-1) + t(0)), q2 - c = 2 t(+1) - 5 t(0)
 // and the smoothness indicators into beta_k / 9 = (13/3) (second difference of t)^2 + s_k^2,
 // s0 = 3 t(-1) - t(-2), s1 = t(0) + t(-1), s2 = t(+1) - 3 t(0).  The common factor 9 and the
 // common factor 1/10 of the ideal weights (1, 6, 3)/10 cancel in the weights, so eps is
-// passed pre-divided (pm1, p0, pp1 = (13/3) dd^2 + eps / 9).
-__device__ __forceinline__ Weno5Pair weno53_pair_sixths(double c, double tm2, double tm1, double tp0,
-                                                        double tp1, double wm2, double wm1,
-                                                        double wp0, double wp1, double pm1,
-                                                        double p0, double pp1) {
-  const double s0 = fma(3.0, tm1, -tm2);
-  const double s1 = tp0 + tm1;
-  const double s2 = fma(-3.0, tp0, tp1);
-  const double e0 = fma(s0, s0, pm1);
-  const double e1 = fma(s1, s1, p0);
-  const double e2 = fma(s2, s2, pp1);
-  const double e12 = e1 * e2, e02 = e0 * e2, e01 = e0 * e1;
-  const double w0 = e12 * e12, w1 = e02 * e02, w2 = e01 * e01;
-  const double a1 = 6.0 * w1, a2R = 3.0 * w2, a0L = 3.0 * w0;  // right (1,6,3), left (3,6,1)
-  const double rR0 = fma(5.0, tm1, -wm2);
-  const double rR1 = wp0 + tm1;
-  const double rR2 = fma(4.0, tp0, -tp1);
-  const double rL0 = fma(-4.0, tm1, tm2);
-  const double rL1 = -(wm1 + tp0);
-  const double rL2 = fma(-5.0, tp0, wp1);
-  const double numR = fma(a2R, rR2, fma(a1, rR1, w0 * rR0));
-  const double numL = fma(w2, rL2, fma(a1, rL1, a0L * rL0));
-  const double denR = (w0 + a1) + a2R;
-  const double denL = (a0L + a1) + w2;
-  Weno5Pair out;
-  out.ur = fma(numR, fast_rcp(denR), c);
-  out.ul = fma(numL, fast_rcp(denL), c);
-  return out;
-}
-
-// Same quantities as weno53_pair_sixths with the candidate offsets written in terms of the
-// smoothness stencils' own linear forms (one instruction each, no doubled differences needed):
-//   s0 = 3 t(-1) - t(-2),  s2 = t(+1) - 3 t(0)
+// passed pre-divided (pm1, p0, pp1 = (13/3) dd^2 + eps / 9).  The candidate offsets are written
+// in the smoothness stencils' own linear forms (one instruction each):
 //   right: q0 - c = 2 s0 - t(-1),  q1 - c = 2 t(0) + t(-1),   q2 - c = t(0) - s2
 //   left : q0 - c = -(s0 + t(-1)), q1 - c = -(2 t(-1) + t(0)), q2 - c = 2 s2 + t(0)
-__device__ __forceinline__ Weno5Pair weno53_pair_lean(double c, double tm2, double tm1, double tp0,
-                                                      double tp1, double pm1, double p0,
-                                                      double pp1) {
-  const double s0 = fma(3.0, tm1, -tm2);
-  const double s1 = tp0 + tm1;
-  const double s2 = fma(-3.0, tp0, tp1);
-  const double e0 = fma(s0, s0, pm1);
-  const double e1 = fma(s1, s1, p0);
-  const double e2 = fma(s2, s2, pp1);
-  const double e12 = e1 * e2, e02 = e0 * e2, e01 = e0 * e1;
-  const double w0 = e12 * e12, w1 = e02 * e02, w2 = e01 * e01;
-  const double a1 = 6.0 * w1, a2R = 3.0 * w2, a0L = 3.0 * w0;  // right (1,6,3), left (3,6,1)
-  const double rR0 = fma(2.0, s0, -tm1);
-  const double rR1 = fma(2.0, tp0, tm1);
-  const double rR2 = tp0 - s2;
-  const double nL0 = s0 + tm1;            // -(q0 - c), left
-  const double nL1 = fma(2.0, tm1, tp0);  // -(q1 - c), left
-  const double rL2 = fma(2.0, s2, tp0);
-  const double numR = fma(a2R, rR2, fma(a1, rR1, w0 * rR0));
-  const double numL = fma(w2, rL2, -fma(a1, nL1, a0L * nL0));
-  const double denR = (w0 + a1) + a2R;
-  const double denL = (a0L + a1) + w2;
-  Weno5Pair out;
-  out.ur = fma(numR, fast_rcp(denR), c);
-  out.ul = fma(numL, fast_rcp(denL), c);
-  return out;
-}
-
-// weno53_pair_lean with the ideal-weight factors 3 folded into the candidate offsets instead of
-// the weights (two multiplications fewer per cell: 37 FP64 instructions for the two values):
+// and the ideal-weight factors 3 are folded into the offsets instead of the weights (37 FP64
+// instructions for the two values of a cell):
 //   right: N = W0 r0 + (6 W1) r1 + W2 (3 r2),   D = W0 + 6 W1 + 3 W2,   3 r2 = 3 (t(0) - s2) = t(+1) - 4 s2
 //   left : N = W0 (3 r0) + (6 W1) r1 + W2 r2,   D = 3 W0 + 6 W1 + W2,   3 r0 = -3 (s0 + t(-1)) = -(4 s0 + t(-2))
 // (3 t(0) = t(+1) - s2 and 3 t(-1) = s0 + t(-2) by the definitions of s2 and s0).  The one product
 // that feeds plain additions is written with __dmul_rn so that no compiler decision about
 // contraction can make the arithmetic of a cell depend on where the cell sits in a warp.
-__device__ __forceinline__ Weno5Pair weno53_pair_lean2(double c, double tm2, double tm1, double tp0,
+__device__ __forceinline__ Weno5Pair weno53_pair_lean(double c, double tm2, double tm1, double tp0,
                                                        double tp1, double pm1, double p0,
                                                        double pp1) {
   const double s0 = fma(3.0, tm1, -tm2);

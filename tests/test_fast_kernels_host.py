@@ -4,9 +4,8 @@ forms) compiled for the HOST and run under a 32-thread warp emulation
 (tests/host/fast_kernels_host.cpp, tests/host/emu/cuda_runtime.h), against the C oracle
 (oracle/psk_oracle.c, the restatement of schemes.py:339-346 / scalar.py / reconstruction.py /
 timestepping.py:312-320).  What this pins without a GPU: the lane -> cell maps, the halo shuffles
-and halo loads, the row tails, the boundary conditions and that the layouts perform the SAME
-arithmetic per cell wherever the cell sits (bitwise equal outputs between layouts 1 and 2,
-bitwise shift equivariance of each)."""
+and halo loads, the row tails, the boundary conditions and that every layout performs the SAME
+arithmetic per cell wherever the cell sits (bitwise equal outputs, bitwise shift equivariance)."""
 
 from __future__ import annotations
 
@@ -139,17 +138,11 @@ def test_layouts_are_bitwise_equal_at_row_tails(emu, n: int, bc: str) -> None:
     err = np.abs(base[:, i] - ref[:, i]).max() / np.abs(ref[:, i]).max()
     assert err < 2e-13, err
     assert np.array_equal(mx0, np.abs(base[:, i]).max(axis=1))
-    # layouts 1 and 2 share weno53_pair_lean2 (the factors 3 folded into the candidate offsets): equal
-    # to each other bit for bit, equal to layout 0 to rounding
-    first = None
     for layout in (1, 2):
         for late in (0, 1, 2):
             got, mx = pb.step(emu, layout, late, with_max=True)
-            if first is None:
-                first = got
-                assert np.abs(got[:, i] - base[:, i]).max() <= 5e-15 * np.abs(base[:, i]).max()
-            assert np.array_equal(got[:, i], first[:, i]), (layout, late)
-            assert np.array_equal(mx, np.abs(got[:, i]).max(axis=1))
+            assert np.array_equal(got[:, i], base[:, i]), (layout, late)
+            assert np.array_equal(mx, mx0)
             # nothing outside the interior is written
             assert np.isnan(got[:, :G]).all() and np.isnan(got[:, G + n :]).all()
 

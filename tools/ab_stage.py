@@ -2,8 +2,8 @@
 
 For every variant (psk_set_stage_variant(5000 + 100*fewer_ctas + 10*late + layout)):
   * parity against the C oracle on a small ensemble (the checker), difference from layout 0,
-    bitwise shift equivariance, the fused max-|u| path (adaptive solve) and a Dirichlet advection
-    case for the layouts themselves;
+    bitwise shift equivariance, the fused max-|u| path (adaptive solve) and the other Burgers
+    fluxes of the specialised kernel;
   * throughput of the BASELINE configs[2] ensemble (65536 x 4096, fixed dt), best of 3 x 20 steps.
 Writes one JSON line per variant to gpurun_out/ab_stage.jsonl and prints the ranking.
 """
@@ -129,34 +129,41 @@ def throughput(batch: int, n: int, steps: int = 20, reps: int = 3) -> float:
 
 def main() -> None:
     t_start = time.time()
-    quick = os.environ.get("AB_QUICK") == "1"
-    variants = [0, 1, 2, 11, 12, 21, 22, 101, 102, 111, 112, 121, 122]
-    if quick:
-        variants = [0, 1, 2, 12]
+    # (layout code for psk_set_stage_variant(5000 + .), prefetch code for psk_set_stage_variant(6000 + .))
+    specs = [(0, 0), (2, 0), (1, 0), (102, 0), (112, 0)]
+    for rows in (32, 64, 128, 256, 512):
+        specs += [(2, 10 * rows + 1), (2, 10 * rows + 2)]
+    specs += [(0, 1281), (102, 1281), (2, 0)]
+    if os.environ.get("AB_SPECS"):
+        specs = [tuple(int(x) for x in sp.split(":")) for sp in os.environ["AB_SPECS"].split(",")]
     batch = int(os.environ.get("AB_BATCH", "65536"))
     base: dict = {}
-    rows = []
+    rows_out = []
+    checked = set()
     with open(OUT / "ab_stage.jsonl", "w") as fh:
-        for v in variants:
+        for v, pf in specs:
             set_variant(v)
-            row = {"variant": v, "layout": v % 10, "late": (v // 10) % 10, "ctas_per_sm": 3 if v >= 100 else 4}
+            assert _lib.lib().psk_set_stage_variant(6000 + pf) == 0
+            row = {"variant": v, "prefetch": pf, "layout": v % 10, "late": (v // 10) % 10,
+                   "ctas_per_sm": 5 if v >= 100 else 4, "pf_rows": pf // 10, "pf_mode": pf % 10}
             try:
-                row.update(parity(v, base))
+                if (v, pf != 0) not in checked:  # prefetches are hints: one parity pass per layout, with and without
+                    row.update(parity(v, base))
+                    checked.add((v, pf != 0))
                 row["cell_updates_per_s"] = throughput(batch, 4096)
                 row["hbm_frac_64B"] = row["cell_updates_per_s"] * 64 / 6545.9e9
             except Exception as exc:  # noqa: BLE001  (scratch tool: record and go on)
                 row["error"] = repr(exc)
             row["t_wall"] = round(time.time() - t_start, 1)
-            rows.append(row)
+            rows_out.append(row)
             fh.write(json.dumps(row) + "\n")
             fh.flush()
             print(json.dumps(row), flush=True)
-    set_variant(0)
-    ok = [r for r in rows if "error" not in r and r["shift_bitwise"] and r["err_oracle"] < 1e-12]
+    set_variant(2)
+    _lib.lib().psk_set_stage_variant(6000)
+    ok = [r for r in rows_out if "error" not in r and r.get("shift_bitwise", True) and r.get("err_oracle", 0.0) < 1e-12]
     ok.sort(key=lambda r: -r["cell_updates_per_s"])
-    print("ranking:", [(r["variant"], f'{r["cell_updates_per_s"]:.4g}') for r in ok])
-    if ok:
-        (OUT / "ab_stage_best.txt").write_text(str(5000 + ok[0]["variant"]))
+    print("ranking:", [(r["variant"], r["prefetch"], f'{r["cell_updates_per_s"]:.4g}') for r in ok])
 
 
 if __name__ == "__main__":

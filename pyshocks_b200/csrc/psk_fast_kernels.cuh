@@ -64,9 +64,6 @@ struct FastParams {
   double eps9;   // eps / 9
   int dt_stride;
   int chunks_per_row;
-  int rows;      // rows of this launch
-  int pf_rows;   // L2 prefetch distance in rows (0: none)
-  int pf_mode;   // 1: every lane prefetches its own quad, 2: one bulk prefetch per warp
 };
 
 __device__ __forceinline__ double umax_abs(double a, double b) {
@@ -80,33 +77,6 @@ __device__ __forceinline__ double umax_neg(double a, double b) {
   const unsigned long long x = static_cast<unsigned long long>(__double_as_longlong(a));
   const unsigned long long y = static_cast<unsigned long long>(__double_as_longlong(b));
   return __longlong_as_double(static_cast<long long>(x > y ? x : y));
-}
-
-// L2 prefetch of the cells the same warp position will need `pf_rows` rows further down the
-// ensemble: the CTAs of one wave cover ~120 consecutive rows, so the lines a later wave will load
-// are pulled from HBM into L2 while this wave computes (more bytes in flight than the resident
-// warps' own load phases provide).  Nothing is prefetched beyond the rows of the launch.
-template <int STAGE>
-__device__ __forceinline__ void fast_prefetch(const FastParams &p, int row, int c0, int lane, bool inside) {
-#ifndef PSK_HOST_EMU
-  if (p.pf_rows == 0 || row + p.pf_rows >= p.rows) return;
-  const int64_t off = static_cast<int64_t>(row + p.pf_rows) * p.ld + p.bc.g + c0;
-  if (p.pf_mode == 1) {
-    if (inside) {
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.uin + off));
-      if (STAGE >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.u0 + off));
-    }
-  } else if (lane == 1) {  // lane 1 owns the first emitted cell of the chunk: c0 >= 0, 16-byte aligned
-    const int cells = (p.bc.n - c0) < 128 ? (p.bc.n - c0) & ~1 : 128;
-    if (cells > 0) {
-      const unsigned bytes = static_cast<unsigned>(cells) * 8u;
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.uin + off), "r"(bytes));
-      if (STAGE >= 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.u0 + off), "r"(bytes));
-    }
-  }
-#else
-  (void)p; (void)row; (void)c0; (void)lane; (void)inside;
-#endif
 }
 
 #ifndef PSK_FAST_MIN_BLOCKS
@@ -267,7 +237,6 @@ stage_warp_fast_kernel(const FastParams p) {
   FastIn in;
   double out[4];
   fast_load<STAGE>(p, row, c0, lane, inside, in);
-  fast_prefetch<STAGE>(p, row, c0, lane, inside);
   fast_compute_store<EQ, FLUX, STAGE, WITH_MAX>(p, row, c0, lane, inside, in, out);
 }
 
@@ -316,7 +285,7 @@ __device__ __forceinline__ int64_t after(int64_t off, double late) {
 // shuffle, after which every lane combines and stores its aligned quad (lane 31: the first
 // half of it).  FP64 work per warp is unchanged, emitted cells +5 %.
 template <int EQ, int FLUX, int STAGE, bool WITH_MAX, int MINB = PSK_FAST_MIN_BLOCKS, int LATE = 0>
-__global__ void __launch_bounds__(MINB == 5 ? 224 : 256, MINB)
+__global__ void __launch_bounds__(256, MINB)
 stage_warp_fast126_kernel(const FastParams p) {
   constexpr int R = 4;
   constexpr unsigned kFull = 0xffffffffu;
@@ -462,8 +431,13 @@ stage_warp_fast126_kernel(const FastParams p) {
 // squares pq of its OWN four cells only and gets the three t and two pq of its neighbours'
 // cells by shuffle instead of recomputing them from shuffled cell values: 12 FP64-pipe
 // instructions fewer per lane (237 -> 225) for 3 more double shuffles.
-template <int EQ, int FLUX, int STAGE, bool WITH_MAX, int MINB = PSK_FAST_MIN_BLOCKS, int LATE = 0>
-__global__ void __launch_bounds__(MINB == 5 ? 224 : 256, MINB)
+// THREADS x MINB: the CTA shape the register budget is set for (256 x 4: 64 registers, 28-32 warps
+// per SM; 224 x 5: 56 registers, 35 warps; ...).  PARK: u0 waits in shared memory between its load
+// (issued with the stage input, so the two latencies overlap) and the stage combine at the very
+// end, which takes its 8 registers out of the reconstruction.
+template <int EQ, int FLUX, int STAGE, bool WITH_MAX, int MINB = PSK_FAST_MIN_BLOCKS, int LATE = 0,
+          int THREADS = 256, bool PARK = false>
+__global__ void __launch_bounds__(THREADS, MINB)
 stage_warp_fast_share_kernel(const FastParams p) {
   constexpr int R = 4;
   constexpr unsigned kFull = 0xffffffffu;
@@ -480,7 +454,11 @@ stage_warp_fast_share_kernel(const FastParams p) {
   fast_load<0>(p, row, c0, lane, inside, in);  // the stage input only
   double u0v[R] = {0.0, 0.0, 0.0, 0.0};
   if (LATE == 0 && emit) fast_load_u0<STAGE>(p.u0 + off, inside, n - c0, u0v);
-  fast_prefetch<STAGE>(p, row, c0, lane, inside);
+  __shared__ double2 park[PARK ? 2 * THREADS : 1];
+  if (PARK && STAGE >= 2) {
+    park[threadIdx.x] = make_double2(u0v[0], u0v[1]);
+    park[THREADS + threadIdx.x] = make_double2(u0v[2], u0v[3]);
+  }
 
   double w[R + 1];  // cells c0-1 .. c0+3
 #pragma unroll
@@ -548,6 +526,13 @@ stage_warp_fast_share_kernel(const FastParams p) {
   }
 
   if (LATE == 2 && emit) fast_load_u0<STAGE>(p.u0 + after(off, F[0]), inside, n - c0, u0v);
+  if (PARK && STAGE >= 2) {  // (volatile: the compiler must not forward the parked values in registers)
+    const volatile double2 *pk = park;
+    u0v[0] = pk[threadIdx.x].x;
+    u0v[1] = pk[threadIdx.x].y;
+    u0v[2] = pk[THREADS + threadIdx.x].x;
+    u0v[3] = pk[THREADS + threadIdx.x].y;
+  }
   double coef = p.coef;
   if (STAGE != 0) coef *= p.dt[static_cast<int64_t>(row) * p.dt_stride];
   double out[R];

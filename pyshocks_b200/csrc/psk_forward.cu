@@ -563,38 +563,39 @@ stage_warp_fast_p2p_kernel(const FastParams p, const HaloLink h) {
   }
 }
 
-// Layout / occupancy / load-placement variants of the specialised kernel.  The registers-per-
-// thread (MINB) and late-u0 (LATE) variants exist for the hot configuration only (Burgers +
-// Rusanov); every other scheme gets the plain form of the selected layout.
-static int g_fast_pf_rows = 0;  // L2 prefetch distance in rows (fast_prefetch), 0 = off
-static int g_fast_pf_mode = 1;
-static int g_fast_minb = PSK_FAST_MIN_BLOCKS;  // 4: CTAs of <= 256 threads, 64 registers; 5: CTAs of <= 224 threads, 58 registers (hot configuration only)
-static int g_fast_late = 0;                    // 0: u0 loaded with the stage input, 1: after the reconstruction, 2: after the fluxes
+// Layout / occupancy variants of the specialised kernel.  The CTA shapes other than 256 x 4 and the
+// shared-memory parking of u0 exist for the hot configuration only (Burgers + Rusanov, shared-
+// difference layout); every other scheme gets the plain form of the selected layout.
+static int g_fast_occ = 0;   // CTA shape: 0: 256 threads x 4 CTAs per SM, 1: 224 x 5, 2: 224 x 6, 3: 160 x 8
+static int g_fast_park = 0;  // 1: u0 parked in shared memory during the reconstruction
+
+inline int fast_occ_threads(int occ) { return occ == 0 ? 256 : (occ == 3 ? 160 : 224); }
 
 #define PSK_FAST_LAUNCH(KERNEL, MINB, LATE) \
   KERNEL<EQ, FLUX, STAGE, WITH_MAX, MINB, LATE><<<grid, threads, 0, st>>>(q)
-#define PSK_FAST_LAUNCH_HOT(KERNEL)                                                \
-  do {                                                                             \
-    if (g_fast_minb == 5) {                                                        \
-      if (g_fast_late == 2) PSK_FAST_LAUNCH(KERNEL, 5, 2);                         \
-      else if (g_fast_late == 1) PSK_FAST_LAUNCH(KERNEL, 5, 1);                    \
-      else PSK_FAST_LAUNCH(KERNEL, 5, 0);                                          \
-    } else {                                                                       \
-      if (g_fast_late == 2) PSK_FAST_LAUNCH(KERNEL, PSK_FAST_MIN_BLOCKS, 2);       \
-      else if (g_fast_late == 1) PSK_FAST_LAUNCH(KERNEL, PSK_FAST_MIN_BLOCKS, 1);  \
-      else PSK_FAST_LAUNCH(KERNEL, PSK_FAST_MIN_BLOCKS, 0);                        \
-    }                                                                              \
-  } while (0)
+#define PSK_FAST_LAUNCH_SHARE(MINB, THREADS, PARK) \
+  stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, MINB, 0, THREADS, PARK><<<grid, threads, 0, st>>>(q)
 
 template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
 void launch_fast_layout(dim3 grid, int threads, cudaStream_t st, const FastParams &q) {
   constexpr bool kHot = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV && !WITH_MAX && STAGE != 0);
   if (g_fast_layout == 1) {
-    if constexpr (kHot) PSK_FAST_LAUNCH_HOT(stage_warp_fast126_kernel);
-    else PSK_FAST_LAUNCH(stage_warp_fast126_kernel, PSK_FAST_MIN_BLOCKS, 0);
+    PSK_FAST_LAUNCH(stage_warp_fast126_kernel, PSK_FAST_MIN_BLOCKS, 0);
   } else if (g_fast_layout == 2) {
-    if constexpr (kHot) PSK_FAST_LAUNCH_HOT(stage_warp_fast_share_kernel);
-    else PSK_FAST_LAUNCH(stage_warp_fast_share_kernel, PSK_FAST_MIN_BLOCKS, 1);  // LATE = 0 spills at 64 registers
+    if constexpr (kHot) {
+      switch (g_fast_occ * 2 + g_fast_park) {
+        case 1: PSK_FAST_LAUNCH_SHARE(4, 256, true); break;
+        case 2: PSK_FAST_LAUNCH_SHARE(5, 224, false); break;
+        case 3: PSK_FAST_LAUNCH_SHARE(5, 224, true); break;
+        case 4: PSK_FAST_LAUNCH_SHARE(6, 224, false); break;
+        case 5: PSK_FAST_LAUNCH_SHARE(6, 224, true); break;
+        case 6: PSK_FAST_LAUNCH_SHARE(8, 160, false); break;
+        case 7: PSK_FAST_LAUNCH_SHARE(8, 160, true); break;
+        default: PSK_FAST_LAUNCH_SHARE(4, 256, false); break;
+      }
+    } else {
+      PSK_FAST_LAUNCH(stage_warp_fast_share_kernel, PSK_FAST_MIN_BLOCKS, 1);  // LATE = 0 spills at 64 registers
+    }
   } else {
     stage_warp_fast_kernel<EQ, FLUX, STAGE, WITH_MAX><<<grid, threads, 0, st>>>(q);
   }
@@ -608,13 +609,13 @@ int launch_fast_stage(const StageParams &p, int batch, cudaStream_t st) {
   q.coef = p.invdx / FluxScale<EQ, FLUX>::value;
   q.eps9 = p.eps * (1.0 / 9.0);
   q.dt_stride = static_cast<int>(p.dt_stride);
+  // the CTA shapes of the occupancy variants cap the warps per CTA (hot configuration only)
   constexpr bool kHotCfg = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV && STAGE != 0);
-  const bool small_cta = kHotCfg && g_fast_minb == 5 && g_fast_layout != 0 && p.maxabs == nullptr;
-  const FastGeometry geo = fast_geometry(g_fast_layout, p.bc.n, (small_cta && g_fast_wpc_max > 7) ? 7 : g_fast_wpc_max);
+  int wpc_max = g_fast_wpc_max;
+  if (kHotCfg && g_fast_layout == 2 && p.maxabs == nullptr && fast_occ_threads(g_fast_occ) / 32 < wpc_max)
+    wpc_max = fast_occ_threads(g_fast_occ) / 32;
+  const FastGeometry geo = fast_geometry(g_fast_layout, p.bc.n, wpc_max);
   q.chunks_per_row = geo.chunks_per_row;
-  q.rows = batch;
-  q.pf_rows = g_fast_pf_rows;
-  q.pf_mode = g_fast_pf_mode;
   const int wpc = geo.wpc;
   const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
   const unsigned gy = batch < 65535 ? batch : 65535u;
@@ -1067,20 +1068,13 @@ int psk_version(void) { return PSK_VERSION; }
 /* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
  * kernel (default), 1 = shared-memory tile kernel */
 int psk_set_stage_variant(int variant) {
-  if (variant >= 6000) {  // 6000 + 10 * (L2 prefetch distance in rows) + mode (1: per lane, 2: bulk); 6000 = off
-    const int v = variant - 6000;
-    if (v % 10 > 2 || v / 10 > 4096) return PSK_E_INVALID;
-    g_fast_pf_rows = (v % 10) ? v / 10 : 0;
-    g_fast_pf_mode = (v % 10) ? v % 10 : 1;
-    return PSK_OK;
-  }
-  if (variant >= 5000) {  // 5000 + 100 (5 CTAs of 224 threads) + 10 late + layout of the specialised kernel
+  if (variant >= 5000) {  // 5000 + 100 (CTA shape) + 10 (park u0 in shared memory) + layout of the specialised kernel
     const int v = variant - 5000;
-    const int layout = v % 10, late = (v / 10) % 10, fewer = v / 100;  // "fewer" registers: 5 CTAs of 224 threads
-    if (layout > 2 || late > 2 || fewer > 1) return PSK_E_INVALID;
+    const int layout = v % 10, park = (v / 10) % 10, occ = v / 100;
+    if (layout > 2 || park > 1 || occ > 3) return PSK_E_INVALID;
     g_fast_layout = layout;  // 0: 120 cells per warp, 1: 126, 2: 120 + shared t / pq
-    g_fast_late = late;
-    g_fast_minb = fewer ? 5 : PSK_FAST_MIN_BLOCKS;
+    g_fast_park = park;
+    g_fast_occ = occ;  // 0: 256 x 4, 1: 224 x 5, 2: 224 x 6, 3: 160 x 8
     return PSK_OK;
   }
   if (variant >= 4000) {  // 4000 + max warps per CTA of the specialised kernel (4..8)

@@ -16,6 +16,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __shared__ static  // one process-wide array; every emulated thread touches its own slots
 
 typedef int cudaError_t;
 constexpr int cudaSuccess = 0;

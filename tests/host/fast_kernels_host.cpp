@@ -39,6 +39,7 @@ Kernel pick_layout(int layout, int late) {
     if constexpr (kHot) {
       if (late == 1) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 1>;
       if (late == 2) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 2>;
+      if (late == 3) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 0, 256, true>;  // PARK
     }
     if (!kHot) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 1>;  // as launch_fast_layout
     return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 0>;

@@ -139,7 +139,9 @@ def test_layouts_are_bitwise_equal_at_row_tails(emu, n: int, bc: str) -> None:
     assert err < 2e-13, err
     assert np.array_equal(mx0, np.abs(base[:, i]).max(axis=1))
     for layout in (1, 2):
-        for late in (0, 1, 2):
+        for late in (0, 1, 2, 3):  # 3: u0 parked in shared memory (shared-difference layout only)
+            if late == 3 and layout != 2:
+                continue
             got, mx = pb.step(emu, layout, late, with_max=True)
             assert np.array_equal(got[:, i], base[:, i]), (layout, late)
             assert np.array_equal(mx, mx0)

@@ -103,7 +103,34 @@ def parity(v: int, base: dict) -> dict:
     return res
 
 
-def throughput(batch: int, n: int, steps: int = 20, reps: int = 3) -> float:
+def sm_clock() -> int:
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(0)
+        return int(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+    except Exception:  # noqa: BLE001
+        return -1
+
+
+def main() -> None:
+    """interleaved rounds over the candidates on ONE solver (same buffers), after a thermal warm-up"""
+    t_start = time.time()
+    codes = [0, 2, 12, 102, 112, 302, 312, 202, 1]
+    if os.environ.get("AB_CODES"):
+        codes = [int(x) for x in os.environ["AB_CODES"].split(",")]
+    batch, n = int(os.environ.get("AB_BATCH", "65536")), 4096
+    rounds, steps = int(os.environ.get("AB_ROUNDS", "5")), int(os.environ.get("AB_STEPS", "30"))
+    base: dict = {}
+    par = {}
+    for v in codes:
+        set_variant(v)
+        try:
+            par[v] = parity(v, base)
+        except Exception as exc:  # noqa: BLE001  (scratch tool: record and go on)
+            par[v] = {"error": repr(exc)}
+        print(v, json.dumps(par[v]), flush=True)
     s = solver(batch, n)
     x = torch.linspace(0, 1, s.nx, device="cuda", dtype=torch.float64)
     gen = torch.Generator(device="cuda").manual_seed(1)
@@ -111,59 +138,39 @@ def throughput(batch: int, n: int, steps: int = 20, reps: int = 3) -> float:
     s.load(u0)
     del u0
     dt = 0.4 * (3.0 / n) / 1.5
-    s.solve_fixed_dt(None, dt, 3)
+    set_variant(codes[0])
+    s.solve_fixed_dt(None, dt, 400)  # ~1.5 s of load: clocks and temperature settle
     torch.cuda.synchronize()
-    best = 1e9
-    for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        s.solve_fixed_dt(None, dt, steps)
-        e1.record()
-        torch.cuda.synchronize()
-        best = min(best, e0.elapsed_time(e1))
-    assert bool(torch.isfinite(s.u).all())
-    del s
-    torch.cuda.empty_cache()
-    return batch * n * steps / (best * 1e-3)
-
-
-def main() -> None:
-    t_start = time.time()
-    # (layout code for psk_set_stage_variant(5000 + .), prefetch code for psk_set_stage_variant(6000 + .))
-    specs = [(0, 0), (2, 0), (1, 0), (102, 0), (112, 0)]
-    for rows in (32, 64, 128, 256, 512):
-        specs += [(2, 10 * rows + 1), (2, 10 * rows + 2)]
-    specs += [(0, 1281), (102, 1281), (2, 0)]
-    if os.environ.get("AB_SPECS"):
-        specs = [tuple(int(x) for x in sp.split(":")) for sp in os.environ["AB_SPECS"].split(",")]
-    batch = int(os.environ.get("AB_BATCH", "65536"))
-    base: dict = {}
-    rows_out = []
-    checked = set()
-    with open(OUT / "ab_stage.jsonl", "w") as fh:
-        for v, pf in specs:
+    samples: dict[int, list[float]] = {v: [] for v in codes}
+    clocks: dict[int, list[int]] = {v: [] for v in codes}
+    for r in range(rounds):
+        order = codes if r % 2 == 0 else codes[::-1]
+        for v in order:
             set_variant(v)
-            assert _lib.lib().psk_set_stage_variant(6000 + pf) == 0
-            row = {"variant": v, "prefetch": pf, "layout": v % 10, "late": (v // 10) % 10,
-                   "ctas_per_sm": 5 if v >= 100 else 4, "pf_rows": pf // 10, "pf_mode": pf % 10}
-            try:
-                if (v, pf != 0) not in checked:  # prefetches are hints: one parity pass per layout, with and without
-                    row.update(parity(v, base))
-                    checked.add((v, pf != 0))
-                row["cell_updates_per_s"] = throughput(batch, 4096)
-                row["hbm_frac_64B"] = row["cell_updates_per_s"] * 64 / 6545.9e9
-            except Exception as exc:  # noqa: BLE001  (scratch tool: record and go on)
-                row["error"] = repr(exc)
-            row["t_wall"] = round(time.time() - t_start, 1)
-            rows_out.append(row)
-            fh.write(json.dumps(row) + "\n")
-            fh.flush()
-            print(json.dumps(row), flush=True)
+            s.solve_fixed_dt(None, dt, 2)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            s.solve_fixed_dt(None, dt, steps)
+            e1.record()
+            clocks[v].append(sm_clock())
+            torch.cuda.synchronize()
+            samples[v].append(batch * n * steps / (e0.elapsed_time(e1) * 1e-3))
+    assert bool(torch.isfinite(s.u).all())
     set_variant(2)
-    _lib.lib().psk_set_stage_variant(6000)
-    ok = [r for r in rows_out if "error" not in r and r.get("shift_bitwise", True) and r.get("err_oracle", 0.0) < 1e-12]
-    ok.sort(key=lambda r: -r["cell_updates_per_s"])
-    print("ranking:", [(r["variant"], r["prefetch"], f'{r["cell_updates_per_s"]:.4g}') for r in ok])
+    rows = []
+    with open(OUT / "ab_stage.jsonl", "w") as fh:
+        for v in codes:
+            xs = sorted(samples[v])
+            row = {"variant": v, "layout": v % 10, "park": (v // 10) % 10, "occ": v // 100,
+                   "median": xs[len(xs) // 2], "min": xs[0], "max": xs[-1],
+                   "hbm_frac_64B_median": xs[len(xs) // 2] * 64 / 6545.9e9, "sm_mhz": clocks[v], **par[v]}
+            rows.append(row)
+            fh.write(json.dumps(row) + "\n")
+    rows.sort(key=lambda r: -r["median"])
+    for r in rows:
+        print(f'{r["variant"]:4d}  median {r["median"]:.4g}  [{r["min"]:.4g}, {r["max"]:.4g}]  frac {r["hbm_frac_64B_median"]:.3f}  '
+              f'clk {r["sm_mhz"]}  err {r.get("err_oracle")}  shift {r.get("shift_bitwise")}  {r.get("error", "")}')
+    print("wall", round(time.time() - t_start, 1))
 
 
 if __name__ == "__main__":

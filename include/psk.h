@@ -167,6 +167,17 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
                       const uint8_t *active, double *lf_work, double *maxabs,
                       int ghost_rows, psk_stream_t stream);
 
+/* One whole SSPRK33 step (timestepping.py:312-320: the three stages above) in ONE launch, for the
+ * hot configuration only: Burgers + Rusanov (nu = 1) + WENO-JS5, FAST math, periodic rows, g = 3,
+ * 16-byte aligned rows.  u is read once and uout written once; the stage values stay in registers
+ * (temporal blocking, psk_fast_kernels.cuh).  Bit-identical to three psk_ssprk33_stage calls.
+ * uout must not alias u.  active / maxabs as in psk_ssprk33_stage, except that rows with
+ * active[r] == 0 are COPIED to uout (the state ping-pongs between two arrays).  Ghost cells of uout
+ * are not written.  PSK_E_UNSUPPORTED outside that configuration: call psk_ssprk33_stage three
+ * times instead. */
+int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const double *dt,
+                     int64_t dt_stride, const uint8_t *active, double *maxabs, psk_stream_t stream);
+
 /* Device-side step control of timestepping.step (timestepping.py:128-150) for
  * Burgers-type schemes, per row r:
  *   dt   = theta * (cfl_scale / maxabs[r])             (burgers/schemes.py:42-49, :121-127;

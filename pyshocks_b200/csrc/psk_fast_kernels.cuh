@@ -573,4 +573,166 @@ stage_warp_fast_share_kernel(const FastParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// The whole SSPRK33 step of the hot configuration in ONE launch (temporal blocking over the three
+// stages; timestepping.py:312-320 with the RHS of schemes.py:339-346): Burgers + Rusanov,
+// WENO-JS5 FAST, periodic rows.  u is read once and u' written once: 16 B of HBM traffic per
+// cell-update instead of the 64 B of three stage launches, one load phase per step instead of
+// three, and the stage values k1, k2 never leave the registers.
+//
+//   * a warp owns a window of 32 R cells of one row (lane l: the cells R l .. R l + R - 1, R even);
+//     every stage is the shared-difference form of stage_warp_fast_share_kernel (own first
+//     differences / second-difference squares / -2|w|, the neighbours' by shuffle), applied to the
+//     stage values the lanes hold, so per cell the arithmetic is that of the stage kernels, bit
+//     for bit;
+//   * each stage invalidates 3 more cells at either end of the window (their stencils reach
+//     outside it; lanes 0 and 31 shuffle with themselves there, the values are finite garbage that
+//     never reaches a stored cell): after three stages the window cells [9, 32 R - 9) are valid,
+//     of which the aligned range [10, 32 R - 10) is stored.  Consecutive windows of a row start
+//     32 R - 20 cells apart;
+//   * window cells beyond the row ends are the periodic images (loaded through the slow path).
+// FP64 work per emitted cell is that of the stage kernels (32 R / (32 R - 20) against 32 / 30).
+struct StepParams {
+  const double *u;
+  double *uout;
+  const double *dt;
+  const uint8_t *active;  // rows with active[r] == 0 are copied through
+  unsigned long long *maxabs;
+  int64_t ld;
+  double coef;  // 1 / (4 dx)
+  double eps9;  // eps / 9
+  int dt_stride;
+  int chunks_per_row;
+  int n, g;
+};
+
+template <int R>
+struct StepGeometry {
+  static constexpr int kWindow = 32 * R;
+  static constexpr int kSkip = 10;                 // first stored window cell
+  static constexpr int kEmit = kWindow - 2 * kSkip;  // stored cells per warp
+};
+
+// one stage on the lane's R cells: a (stage input, own cells) -> L = coef * dF per own cell
+template <int R>
+__device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9, double (&dF)[R]) {
+  constexpr unsigned kFull = 0xffffffffu;
+  double w0 = __shfl_up_sync(kFull, a[R - 1], 1);  // cell own - 1
+  double t[R + 3];   // t[k]: interval (own - 2 + k, own - 1 + k); own: k = 1..R
+  t[1] = __dmul_rn(1.0 / 6.0, a[0] - w0);
+#pragma unroll
+  for (int k = 2; k <= R; ++k) t[k] = __dmul_rn(1.0 / 6.0, a[k - 1] - a[k - 2]);
+  t[0] = __shfl_up_sync(kFull, t[R], 1);
+  t[R + 1] = __shfl_down_sync(kFull, t[1], 1);
+  t[R + 2] = __shfl_down_sync(kFull, t[2], 1);
+  double pq[R + 2];  // centred at the cell own - 1 + k; own: k = 1..R
+#pragma unroll
+  for (int k = 1; k <= R; ++k) {
+    const double dd = t[k + 1] - t[k];
+    pq[k] = fma((13.0 / 3.0) * dd, dd, eps9);
+  }
+  pq[0] = __shfl_up_sync(kFull, pq[R], 1);
+  pq[R + 1] = __shfl_down_sync(kFull, pq[1], 1);
+  double m2[R + 2];  // -2 |w| of the cells own - 1 .. own + R
+  m2[0] = -2.0 * fabs(w0);
+#pragma unroll
+  for (int j = 1; j <= R; ++j) m2[j] = -2.0 * fabs(a[j - 1]);
+  m2[R + 1] = __shfl_down_sync(kFull, m2[1], 1);
+  double ul[R], ur[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const Weno5Pair o = weno53_pair_lean(a[r], t[r], t[r + 1], t[r + 2], t[r + 3], pq[r], pq[r + 1], pq[r + 2]);
+    ul[r] = o.ul;
+    ur[r] = o.ur;
+  }
+  const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
+  const double ul_right = __shfl_down_sync(kFull, ul[0], 1);
+  double F[R + 1];
+#pragma unroll
+  for (int f = 0; f <= R; ++f) {
+    const double urj = (f == 0) ? ur_left : ur[f - 1];
+    const double ulp = (f == R) ? ul_right : ul[f];
+    F[f] = fma(umax_neg(m2[f], m2[f + 1]), ulp - urj, fma(urj, urj, ulp * ulp));
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) dF[r] = F[r] - F[r + 1];
+}
+
+template <int R, bool WITH_MAX, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+step_warp_fused_kernel(const StepParams p) {
+  using Geo = StepGeometry<R>;
+  static_assert(R % 2 == 0, "aligned pairs");
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chunk >= p.chunks_per_row) return;
+  const int row = blockIdx.y + blockIdx.z * gridDim.y;
+  const int n = p.n;
+  const int c0 = chunk * Geo::kEmit - Geo::kSkip + R * lane;  // first own cell (interior coordinates)
+  const bool inside = (c0 >= 0) && (c0 + R <= n);
+  const int64_t base = static_cast<int64_t>(row) * p.ld + p.g;
+  // which own cells are stored: window cells [kSkip, kWindow - kSkip) that exist in the row
+  const int wc0 = R * lane;
+  bool st[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    st[r] = (wc0 + r >= Geo::kSkip) && (wc0 + r < Geo::kWindow - Geo::kSkip) && (c0 + r >= 0) && (c0 + r < n);
+
+  double u0[R];
+  if (inside) {
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+      const double2 q = *reinterpret_cast<const double2 *>(p.u + base + c0 + r);
+      u0[r] = q.x;
+      u0[r + 1] = q.y;
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      int c = (c0 + r) % n;  // periodic image (n >= 1)
+      if (c < 0) c += n;
+      u0[r] = p.u[base + c];
+    }
+  }
+  if (p.active != nullptr && p.active[row] == 0) {  // finished row: the state is carried over
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r]) p.uout[base + c0 + r] = u0[r];
+    return;
+  }
+  const double cdt = p.coef * p.dt[static_cast<int64_t>(row) * p.dt_stride];
+
+  double a[R], dF[R];
+  step_stage_rhs<R>(u0, p.eps9, dF);
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);  // k1
+  step_stage_rhs<R>(a, p.eps9, dF);
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);  // k2
+  step_stage_rhs<R>(a, p.eps9, dF);
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);  // u'
+
+  if (inside) {
+#pragma unroll
+    for (int r = 0; r < R; r += 2)
+      if (st[r]) *reinterpret_cast<double2 *>(p.uout + base + c0 + r) = make_double2(a[r], a[r + 1]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r]) p.uout[base + c0 + r] = a[r];
+  }
+  if (WITH_MAX) {
+    unsigned long long mx = 0ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r]) {
+        const unsigned long long b = abs_bits(a[r]);
+        mx = b > mx ? b : mx;
+      }
+    mx = warp_max_bits(mx);
+    if (lane == 0) atomicMax(p.maxabs + row, mx);
+  }
+}
+
 }  // namespace psk

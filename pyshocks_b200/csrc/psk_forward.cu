@@ -1054,6 +1054,68 @@ __global__ void step_control_kernel(int batch, double theta, double cfl_scale, d
   t_next[r] = __dadd_rn(tr, step);
 }
 
+// ---- whole-step kernel (step_warp_fused_kernel): cells per lane and CTA shape, tuning switch
+// psk_set_stage_variant(7000 + 10 R + shape); 7000 = off (three stage launches)
+static int g_step_variant = 0;
+
+template <int R, int THREADS, int MINB>
+int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cudaStream_t st) {
+  StepParams q = q0;
+  q.chunks_per_row = (n + StepGeometry<R>::kEmit - 1) / StepGeometry<R>::kEmit;
+  int wpc = THREADS / 32;
+  if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
+  const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
+  const unsigned gy = batch < 65535 ? batch : 65535u;
+  if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
+  const dim3 grid(gx, gy, batch / gy);
+  if (with_max)
+    step_warp_fused_kernel<R, true, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
+  else
+    step_warp_fused_kernel<R, false, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
+int launch_step_fused(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
+                      const uint8_t *active, double *maxabs, cudaStream_t st) {
+  StepParams q{};
+  q.u = u; q.uout = uout; q.dt = dt; q.active = active;
+  q.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
+  q.ld = d->ld;
+  q.coef = (1.0 / d->dx) / FluxScale<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV>::value;
+  q.eps9 = d->eps * (1.0 / 9.0);
+  q.dt_stride = static_cast<int>(dt_stride);
+  q.n = d->n;
+  q.g = d->g;
+  const bool mx = maxabs != nullptr;
+  int batch = d->batch;
+  // rows beyond the grid.y limit: equal slices of 32768 rows
+  if (batch > 65535 && batch % 65535 != 0) {
+    if (batch % 32768 != 0) return PSK_E_UNSUPPORTED;
+    for (int b0 = 0; b0 < batch; b0 += 32768) {
+      psk_desc d2 = *d;
+      d2.batch = 32768;
+      const int rc = launch_step_fused(&d2, u + static_cast<int64_t>(b0) * d->ld, uout + static_cast<int64_t>(b0) * d->ld,
+                                       dt + static_cast<int64_t>(b0) * dt_stride, dt_stride,
+                                       active != nullptr ? active + b0 : nullptr,
+                                       maxabs != nullptr ? maxabs + b0 : nullptr, st);
+      if (rc != PSK_OK) return rc;
+    }
+    return PSK_OK;
+  }
+  switch (g_step_variant) {
+    case 40: return launch_step_shape<4, 256, 3>(q, d->n, batch, mx, st);
+    case 41: return launch_step_shape<4, 256, 2>(q, d->n, batch, mx, st);
+    case 60: return launch_step_shape<6, 256, 2>(q, d->n, batch, mx, st);
+    case 61: return launch_step_shape<6, 192, 2>(q, d->n, batch, mx, st);
+    case 62: return launch_step_shape<6, 128, 3>(q, d->n, batch, mx, st);
+    case 80: return launch_step_shape<8, 256, 1>(q, d->n, batch, mx, st);
+    case 81: return launch_step_shape<8, 128, 3>(q, d->n, batch, mx, st);
+    case 82: return launch_step_shape<8, 192, 2>(q, d->n, batch, mx, st);
+    default: return PSK_E_UNSUPPORTED;
+  }
+}
+
 }  // namespace psk
 
 // ===========================================================================
@@ -1068,6 +1130,10 @@ int psk_version(void) { return PSK_VERSION; }
 /* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
  * kernel (default), 1 = shared-memory tile kernel */
 int psk_set_stage_variant(int variant) {
+  if (variant >= 7000) {  // 7000 + 10 R + shape: whole-step kernel (psk_ssprk33_step); 7000 = off
+    g_step_variant = variant - 7000;
+    return PSK_OK;
+  }
   if (variant >= 5000) {  // 5000 + 100 (CTA shape) + 10 (park u0 in shared memory) + layout of the specialised kernel
     const int v = variant - 5000;
     const int layout = v % 10, park = (v / 10) % 10, occ = v / 100;
@@ -1207,6 +1273,20 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
   p.stage = stage;
   return d->math == PSK_MATH_STRICT ? dispatch_scheme<true>(d, p, ghost_rows, st)
                                     : dispatch_scheme<false>(d, p, ghost_rows, st);
+}
+
+int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
+                     const uint8_t *active, double *maxabs, psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (u == nullptr || uout == nullptr || dt == nullptr || uout == u) return PSK_E_INVALID;
+  const bool aligned = (reinterpret_cast<uintptr_t>(u + d->g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0) && (d->ld % 2 == 0);
+  if (d->equation != PSK_EQ_BURGERS || d->flux != PSK_FLUX_RUSANOV || d->rec != PSK_REC_WENOJS53 ||
+      d->math != PSK_MATH_FAST || d->bc != PSK_BC_PERIODIC || d->g != 3 || d->nu != nullptr || !aligned ||
+      g_step_variant == 0)
+    return PSK_E_UNSUPPORTED;
+  return launch_step_fused(d, u, uout, dt, dt_stride, active, maxabs, static_cast<cudaStream_t>(stream));
 }
 
 int psk_ssprk33_stage_p2p(const psk_desc *d, int stage, const double *u0, const double *uin,

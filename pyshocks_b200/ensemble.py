@@ -79,7 +79,9 @@ class EnsembleSolver:
         self.row_steps = torch.zeros(self.batch, dtype=torch.int32, device=dev)
         self._graph: torch.cuda.CUDAGraph | None = None
         self._graph_key: tuple | None = None
+        self._graph_steps = 1
         self.launches = 0  # kernels launched by this solver (bench.py reports it)
+        self._fused: bool | None = None  # None: not tried yet; False: psk_ssprk33_step does not cover this scheme
 
     def new_states(self, count: int) -> list[torch.Tensor]:
         """``count`` more ``(batch, nx)`` arrays with the solver's padded, aligned row layout."""
@@ -110,6 +112,13 @@ class EnsembleSolver:
 
     def _step(self, dt: torch.Tensor, *, active: torch.Tensor | None, maxabs: torch.Tensor | None) -> None:
         hp = self.hp
+        # hot configuration: the whole step in one launch, u -> k1, and the two arrays swap roles
+        if self._fused is not False:
+            self._fused = hp.step_fused(self.u, self.k1, dt, active=active, maxabs=maxabs)
+            if self._fused:
+                self.u, self.k1 = self.k1, self.u
+                self.launches += 1
+                return
         hp.stage(1, self.u, self.u, self.k1, dt, active=active)
         hp.stage(2, self.u, self.k1, self.k2, dt, active=active)
         hp.stage(3, self.u, self.k2, self.u, dt, active=active, maxabs=maxabs)
@@ -129,20 +138,31 @@ class EnsembleSolver:
         if graph and nsteps > 0:
             key = ("fixed", dt.data_ptr(), dt.numel())
             if self._graph is None or self._graph_key != key:
-                # warm-up launch outside capture (lazy module loading), then capture one step
-                self._store[1:].zero_()
+                # warm-up launch outside capture (lazy module loading), then capture the steps.  The
+                # whole-step kernel ping-pongs between two arrays, so its graph holds TWO steps
+                # (u -> k1 -> u) and the captured pointers stay valid from replay to replay.
+                self.k1.zero_()
+                self.k2.zero_()
                 torch.cuda.synchronize()
                 saved = self.u.clone()
+                launches = self.launches
                 self._step(dt, active=None, maxabs=None)
+                per_graph = 2 if self._fused else 1
+                if self._fused:
+                    self.u, self.k1 = self.k1, self.u  # back to the array `saved` was taken from
                 self.u.copy_(saved)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._step(dt, active=None, maxabs=None)
+                    for _ in range(per_graph):
+                        self._step(dt, active=None, maxabs=None)
                 self.u.copy_(saved)
-                self._graph, self._graph_key = g, key
-            for _ in range(nsteps):
+                self.launches = launches  # (capture and warm-up are not steps of the solve)
+                self._graph, self._graph_key, self._graph_steps = g, key, per_graph
+            for _ in range(nsteps // self._graph_steps):
                 self._graph.replay()
-            self.launches += 3 * nsteps
+            self.launches += (1 if self._fused else 3) * (nsteps - nsteps % self._graph_steps)
+            for _ in range(nsteps % self._graph_steps):
+                self._step(dt, active=None, maxabs=None)
         else:
             for _ in range(nsteps):
                 self._step(dt, active=None, maxabs=None)

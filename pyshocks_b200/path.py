@@ -356,6 +356,32 @@ class HotPath:
         )
         return uout
 
+    def step_fused(
+        self,
+        u: torch.Tensor,
+        uout: torch.Tensor,
+        dt: torch.Tensor,
+        *,
+        active: torch.Tensor | None = None,
+        maxabs: torch.Tensor | None = None,
+    ) -> bool:
+        """One whole SSPRK33 step (timestepping.py:312-320) in ONE launch, ``u -> uout`` (no aliasing),
+        bit-identical to three :meth:`stage` calls.  Exists for the hot configuration only
+        (``psk_ssprk33_step``): returns ``False`` -- nothing launched -- anywhere else, and the caller
+        runs the three stages.  Rows with ``active == 0`` are copied to ``uout``."""
+        batch, ld = self._state(u)
+        if L.rows_of(uout)[2] != ld:
+            raise ValueError("all stage arrays must share one row stride")
+        d = self.desc(batch, ld)
+        rc = L.lib().psk_ssprk33_step(
+            ct.byref(d), L.ptr(u), L.ptr(uout), L.ptr(dt), 0 if dt.numel() == 1 else 1,
+            L.raw_ptr(active), L.ptr(maxabs), L.stream_ptr(),
+        )
+        if rc == L.E_UNSUPPORTED:
+            return False
+        L.check("psk_ssprk33_step", rc)
+        return True
+
     def ssprk33_step(
         self,
         u: torch.Tensor,

@@ -24,6 +24,32 @@ namespace {
 
 using Kernel = void (*)(const psk::FastParams);
 
+// every (block, warp) of a (gx, gy) grid of CTAs of wpc warps, one warp at a time: 32 lane threads
+// walk the same sequence and meet in the shuffles
+template <class Body>
+void run_grid(unsigned gx, unsigned gy, int wpc, Body body) {
+  emu::Warp warp;
+  pthread_barrier_init(&warp.bar, nullptr, 32);
+  std::vector<std::thread> lanes;
+  for (int lane = 0; lane < 32; ++lane) {
+    lanes.emplace_back([&, lane]() {
+      emu::warp = &warp;
+      emu::lane = lane;
+      emu::bdim = {static_cast<unsigned>(wpc * 32), 1u, 1u};
+      emu::gdim = {gx, gy, 1u};
+      for (unsigned by = 0; by < gy; ++by)
+        for (unsigned bx = 0; bx < gx; ++bx)
+          for (int wi = 0; wi < wpc; ++wi) {
+            emu::bid = {bx, by, 0u};
+            emu::tid = {static_cast<unsigned>(wi * 32 + lane), 0u, 0u};
+            body();
+          }
+    });
+  }
+  for (auto &t : lanes) t.join();
+  pthread_barrier_destroy(&warp.bar);
+}
+
 template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
 Kernel pick_layout(int layout, int late) {
   constexpr bool kHot = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV);
@@ -120,26 +146,39 @@ int emu_fast_stage(int layout, int late, int equation, int flux, int stage, int 
   q.chunks_per_row = geo.chunks_per_row;
   const unsigned gx = static_cast<unsigned>((geo.chunks_per_row + geo.wpc - 1) / geo.wpc);
 
-  emu::Warp warp;
-  pthread_barrier_init(&warp.bar, nullptr, 32);
-  std::vector<std::thread> lanes;
-  for (int lane = 0; lane < 32; ++lane) {
-    lanes.emplace_back([&, lane]() {
-      emu::warp = &warp;
-      emu::lane = lane;
-      emu::bdim = {static_cast<unsigned>(geo.wpc * 32), 1u, 1u};
-      emu::gdim = {gx, static_cast<unsigned>(batch), 1u};
-      for (unsigned by = 0; by < static_cast<unsigned>(batch); ++by)
-        for (unsigned bx = 0; bx < gx; ++bx)
-          for (int wi = 0; wi < geo.wpc; ++wi) {
-            emu::bid = {bx, by, 0u};
-            emu::tid = {static_cast<unsigned>(wi * 32 + lane), 0u, 0u};
-            k(q);
-          }
-    });
+  run_grid(gx, static_cast<unsigned>(batch), geo.wpc, [&]() { k(q); });
+  return 0;
+}
+
+// One whole SSPRK33 step with the fused kernel (R cells per lane), launched like launch_step_shape.
+int emu_fused_step(int R, int with_max, int n, int g, int batch, long long ld, double dx, double eps,
+                   const double *u, double *uout, const double *dt, int dt_stride, const unsigned char *active,
+                   unsigned long long *maxabs) {
+  psk::StepParams q{};
+  q.u = u; q.uout = uout; q.dt = dt; q.active = active;
+  q.maxabs = with_max ? maxabs : nullptr;
+  q.ld = ld;
+  q.coef = (1.0 / dx) / psk::FluxScale<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV>::value;
+  q.eps9 = eps * (1.0 / 9.0);
+  q.dt_stride = dt_stride;
+  q.n = n;
+  q.g = g;
+  void (*k)(const psk::StepParams) = nullptr;
+  int emit = 0;
+  switch (R * 2 + (with_max ? 1 : 0)) {
+    case 8: k = &psk::step_warp_fused_kernel<4, false, 256, 2>; emit = psk::StepGeometry<4>::kEmit; break;
+    case 9: k = &psk::step_warp_fused_kernel<4, true, 256, 2>; emit = psk::StepGeometry<4>::kEmit; break;
+    case 12: k = &psk::step_warp_fused_kernel<6, false, 256, 2>; emit = psk::StepGeometry<6>::kEmit; break;
+    case 13: k = &psk::step_warp_fused_kernel<6, true, 256, 2>; emit = psk::StepGeometry<6>::kEmit; break;
+    case 16: k = &psk::step_warp_fused_kernel<8, false, 256, 1>; emit = psk::StepGeometry<8>::kEmit; break;
+    case 17: k = &psk::step_warp_fused_kernel<8, true, 256, 1>; emit = psk::StepGeometry<8>::kEmit; break;
+    default: return -1;
   }
-  for (auto &t : lanes) t.join();
-  pthread_barrier_destroy(&warp.bar);
+  q.chunks_per_row = (n + emit - 1) / emit;
+  int wpc = 8;
+  if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
+  const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
+  run_grid(gx, static_cast<unsigned>(batch), wpc, [&]() { k(q); });
   return 0;
 }
 

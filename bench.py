@@ -324,10 +324,13 @@ def run_ours(args: argparse.Namespace) -> None:
         peak, peak_src = measured_peaks()
         per_gpu = value / world
         achieved = per_gpu * ALGO_BYTES_PER_CELL_UPDATE / 1e9
+        per_step = launches / max(args.steps, 1)  # 1: whole-step kernel, 3: one launch per stage
+        whole = per_step < 2
         traffic = None
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists():
-            traffic = json.loads(tf.read_text()).get("stage_kernel_dram_bytes_per_launch")
+            tj = json.loads(tf.read_text())
+            traffic = tj.get("step_kernel_dram_bytes_per_launch" if whole else "stage_kernel_dram_bytes_per_launch")
         fp64 = measure_fp64_peak(dev)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -338,15 +341,18 @@ def run_ours(args: argparse.Namespace) -> None:
                 "bound": "fp64", "achieved": per_gpu * ALGO_FLOPS_PER_CELL_UPDATE / 1e12, "peak": fp64["tflops"],
                 "unit": "TFLOP/s", "frac": per_gpu * ALGO_FLOPS_PER_CELL_UPDATE / 1e12 / fp64["tflops"],
                 "peak_source": fp64["how"],
-                "note": "456 algorithmic flop per cell-update (SURVEY.md 8d); the kernel executes ~62 FP64 "
-                        "instructions per cell-stage (DFMA counts 2 flop): ncu shows the FP64 pipe 80 % busy",
+                "note": "456 algorithmic flop per cell-update (SURVEY.md 8d); the kernels execute ~172 FP64 "
+                        "instructions per cell-update (DFMA counts 2 flop), so the algorithmic rate can exceed the "
+                        "DFMA peak; the FP64 pipe is the binding unit (DESIGN.md 8)",
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "psk::stage_warp_fast_kernel (3 launches per step; 64 algorithmic bytes per cell-update)",
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_UPDATE / 3 * batch * N_CELLS,
-                "avg_launch_ms": ms_total / (3 * args.steps),
+                "kernel": ("psk::step_warp_fused_kernel (1 launch per step: the three stages in registers; 64 "
+                           "algorithmic bytes per cell-update, 16 B of them actually moved)") if whole else
+                          "psk::stage_warp_fast_share_kernel (3 launches per step; 64 algorithmic bytes per cell-update)",
+                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_UPDATE / per_step * batch * N_CELLS,
+                "avg_launch_ms": ms_total / max(launches, 1),
             },
             "e2e": {
                 "value": cells_per_step * args.steps / e2e_s, "unit": UNIT,

@@ -1056,7 +1056,7 @@ __global__ void step_control_kernel(int batch, double theta, double cfl_scale, d
 
 // ---- whole-step kernel (step_warp_fused_kernel): cells per lane and CTA shape, tuning switch
 // psk_set_stage_variant(7000 + 10 R + shape); 7000 = off (three stage launches)
-static int g_step_variant = 0;
+static int g_step_variant = 62;  // R = 6, CTAs of 128 threads, 3 per SM (136 registers): 9.0e10 cell-updates/s on B200
 
 template <int R, int THREADS, int MINB>
 int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cudaStream_t st) {

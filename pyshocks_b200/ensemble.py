@@ -136,7 +136,7 @@ class EnsembleSolver:
         if not isinstance(dt, torch.Tensor):
             dt = torch.full((1,), float(dt), dtype=torch.float64, device=self.hp.device)
         if graph and nsteps > 0:
-            key = ("fixed", dt.data_ptr(), dt.numel())
+            key = ("fixed", dt.data_ptr(), dt.numel(), self.u.data_ptr())  # (the state may sit in either array)
             if self._graph is None or self._graph_key != key:
                 # warm-up launch outside capture (lazy module loading), then capture the steps.  The
                 # whole-step kernel ping-pongs between two arrays, so its graph holds TWO steps
@@ -316,6 +316,7 @@ class AdjointEnsemble:
         self.ring_k2 = solver.new_states(max(self.segment - 1, 0))
         self.lam2, self.lam1, self.p, self.pn = solver.new_states(4)
         self.launches = 0
+        self._fused: bool | None = None  # whether psk_ssprk33_step covers the scheme (None: not tried)
 
     def _auto_segment(self, memory_fraction: float) -> int:
         """Smallest segment length whose tape (nsteps / k checkpoints + 3 k ring arrays) fits in
@@ -332,6 +333,12 @@ class AdjointEnsemble:
     def _advance(self, src: torch.Tensor, dst: torch.Tensor, k1: torch.Tensor | None = None,
                  k2: torch.Tensor | None = None) -> None:
         s, hp = self.s, self.s.hp
+        # forward sweep (no stage values wanted): the whole step in one launch where it exists
+        if k1 is None and k2 is None and self._fused is not False:
+            self._fused = hp.step_fused(src, dst, self.dt)
+            if self._fused:
+                self.launches += 1
+                return
         k1 = s.k1 if k1 is None else k1
         k2 = s.k2 if k2 is None else k2
         hp.stage(1, src, src, k1, self.dt)

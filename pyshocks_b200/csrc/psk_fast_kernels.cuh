@@ -21,16 +21,15 @@ struct FluxScale {
                              : ((FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? 4.0 : 2.0);
 };
 
-// chunks (warps) per row and warps per CTA of the specialised kernels: layout 1 emits 126 cells
-// per warp, layouts 0 and 2 emit 120; the CTA size is the divisor-friendly choice in
-// 4..wpc_max that wastes the fewest warps
+// chunks (warps) per row and warps per CTA of the specialised stage kernels (120 emitted cells per
+// warp); the CTA size is the divisor-friendly choice in 4..wpc_max that wastes the fewest warps
 struct FastGeometry {
   int chunks_per_row, wpc;
 };
 
-inline FastGeometry fast_geometry(int layout, int n, int wpc_max) {
+inline FastGeometry fast_geometry(int n, int wpc_max) {
   FastGeometry geo;
-  geo.chunks_per_row = (layout == 1) ? (n + 125) / 126 : (n + 119) / 120;
+  geo.chunks_per_row = (n + 119) / 120;
   int wpc = 8, best_waste = 1 << 30;
   for (int w = wpc_max; w >= 4; --w) {
     const int waste = ((geo.chunks_per_row + w - 1) / w) * w - geo.chunks_per_row;
@@ -272,172 +271,20 @@ __device__ __forceinline__ int64_t after(int64_t off, double late) {
 }
 
 // ---------------------------------------------------------------------------
-// Layout variants of the specialised kernel (same arithmetic per cell, hence bitwise the same
-// results; selected with psk_set_stage_variant(5000 + k), k = 0 being stage_warp_fast_kernel).
-//
-// k = 1, stage_warp_fast126_kernel: 126 emitted cells per warp instead of 120.  Lane l still
-// loads and stores the ALIGNED quad A..A+3 (A = 126 chunk + 4 l), but reconstructs the cells
-// A-1..A+2, one to the left: its 8-cell window A-3..A+4 is its own quad, three cells of lane
-// l-1 and one of lane l+1 (the same 4 halo shuffles).  Lane 0 loads its three left halo cells
-// and lane 31 its one right halo cell straight from the row (4 predicated scalar loads per
-// warp, L1/L2 hits), so ALL 128 reconstructions of the warp are valid instead of 122: no
-// halo lanes.  The flux difference of cell A+3 comes back from lane l+1 with one more
-// shuffle, after which every lane combines and stores its aligned quad (lane 31: the first
-// half of it).  FP64 work per warp is unchanged, emitted cells +5 %.
-template <int EQ, int FLUX, int STAGE, bool WITH_MAX, int MINB = PSK_FAST_MIN_BLOCKS, int LATE = 0>
-__global__ void __launch_bounds__(256, MINB)
-stage_warp_fast126_kernel(const FastParams p) {
-  constexpr int R = 4;
-  constexpr unsigned kFull = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (chunk >= p.chunks_per_row) return;
-  const int row = blockIdx.y + blockIdx.z * gridDim.y;
-  const int g = p.bc.g, n = p.bc.n;
-  const int W = chunk * 126;
-  const int c0 = W + R * lane;  // first cell of the aligned quad (>= 0)
-  const bool inside = (c0 + R <= n);
-  const double *__restrict__ urow = p.uin + static_cast<int64_t>(row) * p.ld;
-  const int64_t off = static_cast<int64_t>(row) * p.ld + g + c0;
-  const int nst = (lane == 31) ? 2 : R;  // cells this lane stores
-
-  double w[R + 4];  // cells c0-3 .. c0+4; own quad in w[3..6]
-  double u0v[R];
-  if (inside) {
-    const double2 q0 = *reinterpret_cast<const double2 *>(p.uin + off);
-    const double2 q1 = *reinterpret_cast<const double2 *>(p.uin + off + 2);
-    w[3] = q0.x; w[4] = q0.y; w[5] = q1.x; w[6] = q1.y;
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r) w[3 + r] = load_w(p.bc, urow, row, g + c0 + r);
-  }
-  if (LATE == 0) fast_load_u0<STAGE>(p.u0 + off, inside, n - c0, u0v);
-  w[0] = __shfl_up_sync(kFull, w[4], 1);
-  w[1] = __shfl_up_sync(kFull, w[5], 1);
-  w[2] = __shfl_up_sync(kFull, w[6], 1);
-  w[7] = __shfl_down_sync(kFull, w[3], 1);
-  if (chunk > 0 && W + 128 < n) {  // warp-uniform: the halo cells are interior cells
-    if (lane == 0) {
-      w[0] = urow[g + W - 3];
-      w[1] = urow[g + W - 2];
-      w[2] = urow[g + W - 1];
-    }
-    if (lane == 31) w[7] = urow[g + W + 128];
-  } else {
-    if (lane == 0) {
-      w[0] = load_w(p.bc, urow, row, g + W - 3);
-      w[1] = load_w(p.bc, urow, row, g + W - 2);
-      w[2] = load_w(p.bc, urow, row, g + W - 1);
-    }
-    if (lane == 31) w[7] = load_w(p.bc, urow, row, g + W + 128);
-  }
-
-  double t[R + 3], pq[R + 2];
-#pragma unroll
-  for (int k = 0; k < R + 3; ++k) t[k] = __dmul_rn(1.0 / 6.0, w[k + 1] - w[k]);
-#pragma unroll
-  for (int k = 0; k < R + 2; ++k) {
-    const double dd = t[k + 1] - t[k];
-    pq[k] = fma((13.0 / 3.0) * dd, dd, p.eps9);
-  }
-  double ul[R], ur[R];  // of the cells c0-1 .. c0+2
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const Weno5Pair o = weno53_pair_lean(w[r + 2], t[r], t[r + 1], t[r + 2], t[r + 3], pq[r], pq[r + 1], pq[r + 2]);
-    ul[r] = o.ul;
-    ur[r] = o.ur;
-  }
-  const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);   // of cell c0-2
-  const double ul_right = __shfl_down_sync(kFull, ul[0], 1);    // of cell c0+3
-  if (LATE == 1) fast_load_u0<STAGE>(p.u0 + after(off, ur[R - 1]), inside, n - c0, u0v);
-
-  // -2 s of the scaled Rusanov flux: -2 max(|a|, |b|) = the larger magnitude of -2|a|, -2|b|, one
-  // DMUL per CELL (|.| is an operand modifier) instead of an FP64 abs per cell and a DMUL per face
-  const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? -2.0 * p.lf_speed[row] : 0.0;
-  double m2[R + 2];  // cells c0-2 .. c0+3
-  if (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV) {
-#pragma unroll
-    for (int j = 0; j < R + 2; ++j) m2[j] = -2.0 * fabs(w[j + 1]);
-  }
-  double F[R + 1];  // faces between the cells (c0-2+f, c0-1+f)
-#pragma unroll
-  for (int f = 0; f <= R; ++f) {
-    const double urj = (f == 0) ? ur_left : ur[f - 1];
-    const double ulp = (f == R) ? ul_right : ul[f];
-    if (EQ == PSK_EQ_BURGERS) {
-      if (FLUX == PSK_FLUX_RUSANOV || FLUX == PSK_FLUX_LAX_FRIEDRICHS) {
-        const double a2 = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? speed : umax_neg(m2[f], m2[f + 1]);
-        F[f] = fma(a2, ulp - urj, fma(urj, urj, ulp * ulp));
-      } else if (FLUX == PSK_FLUX_UPWIND) {
-        const double x = (urj + ulp) > 0.0 ? urj : ulp;
-        F[f] = x * x;
-      } else {
-        const double vp = fmax(urj, 0.0), vm = fmin(ulp, 0.0);
-        F[f] = fma(vp, vp, vm * vm);
-      }
-    } else {
-      const int j = g + c0 + f - 2;  // stored index of the cell left of the face
-      const bool ok = (j >= 0 && j < p.bc.nx - 1);
-      const double arj = ok ? p.vel_r[j] : 0.0, alp = ok ? p.vel_l[j + 1] : 0.0;
-      const bool pos = (arj + alp) > 0.0;
-      F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? arj * urj : alp * ulp);
-    }
-  }
-  // flux differences of the aligned quad: cells c0..c0+2 are this lane's, c0+3 is lane l+1's first
-  double dFa[R];
-#pragma unroll
-  for (int r = 0; r < R - 1; ++r) dFa[r] = F[r + 1] - F[r + 2];
-  dFa[R - 1] = __shfl_down_sync(kFull, F[0] - F[1], 1);
-  if (LATE == 2) fast_load_u0<STAGE>(p.u0 + after(off, dFa[0]), inside, n - c0, u0v);
-
-  double coef = p.coef;
-  if (STAGE != 0) coef *= p.dt[static_cast<int64_t>(row) * p.dt_stride];
-  double out[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    double dF = dFa[r];
-    if (EQ == PSK_EQ_ADVECTION) dF *= (c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
-    if (STAGE == 0) {
-      out[r] = coef * dF;
-    } else {
-      const double k = fma(coef, dF, w[3 + r]);
-      out[r] = (STAGE == 1) ? k
-                            : ((STAGE == 2) ? fma(0.25, k, 0.75 * u0v[r]) : fma(2.0 / 3.0, k, (1.0 / 3.0) * u0v[r]));
-    }
-  }
-  if (inside) {
-    *reinterpret_cast<double2 *>(p.uout + off) = make_double2(out[0], out[1]);
-    if (lane != 31) *reinterpret_cast<double2 *>(p.uout + off + 2) = make_double2(out[2], out[3]);
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (r < nst && c0 + r < n) p.uout[off + r] = out[r];
-  }
-  if (WITH_MAX) {
-    unsigned long long mx = 0ull;
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (r < nst && c0 + r < n) {
-        const unsigned long long b = abs_bits(out[r]);
-        mx = b > mx ? b : mx;
-      }
-    mx = warp_max_bits(mx);
-    if (lane == 0) atomicMax(p.maxabs + row, mx);
-  }
-}
-
-// k = 2, stage_warp_fast_share_kernel: the 120-cell layout of stage_warp_fast_kernel (halo
+// stage_warp_fast_share_kernel (default layout of the specialised kernel; same arithmetic per cell
+// as stage_warp_fast_kernel, hence bitwise the same results; psk_set_stage_variant(5000 + k) selects
+// k = 0: stage_warp_fast_kernel, k = 2: this one):
+// the 120-cell layout of stage_warp_fast_kernel (halo
 // lanes 0 and 31), but every lane computes the first differences t and the second-difference
 // squares pq of its OWN four cells only and gets the three t and two pq of its neighbours'
 // cells by shuffle instead of recomputing them from shuffled cell values: 12 FP64-pipe
 // instructions fewer per lane (237 -> 225) for 3 more double shuffles.
-// THREADS x MINB: the CTA shape the register budget is set for (256 x 4: 64 registers, 28-32 warps
-// per SM; 224 x 5: 56 registers, 35 warps; ...).  PARK: u0 waits in shared memory between its load
-// (issued with the stage input, so the two latencies overlap) and the stage combine at the very
-// end, which takes its 8 registers out of the reconstruction.
-template <int EQ, int FLUX, int STAGE, bool WITH_MAX, int MINB = PSK_FAST_MIN_BLOCKS, int LATE = 0,
-          int THREADS = 256, bool PARK = false>
-__global__ void __launch_bounds__(THREADS, MINB)
+// LATE: u0 is fetched after the reconstruction instead of with the stage input -- one more exposed
+// load latency (-6 % on the hot configuration, which therefore uses LATE = 0) but 8 registers fewer
+// in the most crowded part of the kernel, which the other fluxes / equations need to stay free of
+// spills at 64 registers.
+template <int EQ, int FLUX, int STAGE, bool WITH_MAX, int LATE = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV) ? 0 : 1>
+__global__ void __launch_bounds__(256, PSK_FAST_MIN_BLOCKS)
 stage_warp_fast_share_kernel(const FastParams p) {
   constexpr int R = 4;
   constexpr unsigned kFull = 0xffffffffu;
@@ -454,11 +301,6 @@ stage_warp_fast_share_kernel(const FastParams p) {
   fast_load<0>(p, row, c0, lane, inside, in);  // the stage input only
   double u0v[R] = {0.0, 0.0, 0.0, 0.0};
   if (LATE == 0 && emit) fast_load_u0<STAGE>(p.u0 + off, inside, n - c0, u0v);
-  __shared__ double2 park[PARK ? 2 * THREADS : 1];
-  if (PARK && STAGE >= 2) {
-    park[threadIdx.x] = make_double2(u0v[0], u0v[1]);
-    park[THREADS + threadIdx.x] = make_double2(u0v[2], u0v[3]);
-  }
 
   double w[R + 1];  // cells c0-1 .. c0+3
 #pragma unroll
@@ -492,7 +334,8 @@ stage_warp_fast_share_kernel(const FastParams p) {
   const double ul_right = __shfl_down_sync(kFull, ul[0], 1);
   if (LATE == 1 && emit) fast_load_u0<STAGE>(p.u0 + after(off, ur[R - 1]), inside, n - c0, u0v);
 
-  // -2 s of the scaled Rusanov flux as in stage_warp_fast126_kernel
+  // -2 s of the scaled Rusanov flux: -2 max(|a|, |b|) = the larger magnitude of -2|a|, -2|b|, one
+  // DMUL per CELL (|.| is an operand modifier) instead of an FP64 abs per cell and a DMUL per face
   const double speed = (FLUX == PSK_FLUX_LAX_FRIEDRICHS) ? -2.0 * p.lf_speed[row] : 0.0;
   double m2[R + 2];  // cells c0-1 .. c0+4, the last one from the lane to the right
   if (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV) {
@@ -525,14 +368,6 @@ stage_warp_fast_share_kernel(const FastParams p) {
     }
   }
 
-  if (LATE == 2 && emit) fast_load_u0<STAGE>(p.u0 + after(off, F[0]), inside, n - c0, u0v);
-  if (PARK && STAGE >= 2) {  // (volatile: the compiler must not forward the parked values in registers)
-    const volatile double2 *pk = park;
-    u0v[0] = pk[threadIdx.x].x;
-    u0v[1] = pk[threadIdx.x].y;
-    u0v[2] = pk[THREADS + threadIdx.x].x;
-    u0v[3] = pk[THREADS + threadIdx.x].y;
-  }
   double coef = p.coef;
   if (STAGE != 0) coef *= p.dt[static_cast<int64_t>(row) * p.dt_stride];
   double out[R];

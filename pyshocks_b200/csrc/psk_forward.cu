@@ -460,7 +460,7 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
 }
 
 static int g_fast_wpc_max = 8;  // largest CTA (in warps) the specialised kernel may use (tuning)
-static int g_fast_layout = 2;   // 0: 120 cells per warp (halo lanes), 1: 126 cells per warp, 2: 120 + shared t / pq (default: +4 %)
+static int g_fast_layout = 2;   // 0: neighbours' differences recomputed from shuffled cells, 2: shared by shuffle (default)
 
 // ---------------------------------------------------------------------------
 // The specialised stage kernel FUSED with the ghost-cell exchange of a slab-decomposed grid
@@ -563,42 +563,14 @@ stage_warp_fast_p2p_kernel(const FastParams p, const HaloLink h) {
   }
 }
 
-// Layout / occupancy variants of the specialised kernel.  The CTA shapes other than 256 x 4 and the
-// shared-memory parking of u0 exist for the hot configuration only (Burgers + Rusanov, shared-
-// difference layout); every other scheme gets the plain form of the selected layout.
-static int g_fast_occ = 0;   // CTA shape: 0: 256 threads x 4 CTAs per SM, 1: 224 x 5, 2: 224 x 6, 3: 160 x 8
-static int g_fast_park = 0;  // 1: u0 parked in shared memory during the reconstruction
-
-inline int fast_occ_threads(int occ) { return occ == 0 ? 256 : (occ == 3 ? 160 : 224); }
-
-#define PSK_FAST_LAUNCH(KERNEL, MINB, LATE) \
-  KERNEL<EQ, FLUX, STAGE, WITH_MAX, MINB, LATE><<<grid, threads, 0, st>>>(q)
-#define PSK_FAST_LAUNCH_SHARE(MINB, THREADS, PARK) \
-  stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, MINB, 0, THREADS, PARK><<<grid, threads, 0, st>>>(q)
-
+// Layout of the specialised stage kernel: shared differences (default) or the first form, which
+// recomputes the neighbours' differences from shuffled cell values (same bits; A/B switch).
 template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
 void launch_fast_layout(dim3 grid, int threads, cudaStream_t st, const FastParams &q) {
-  constexpr bool kHot = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV && !WITH_MAX && STAGE != 0);
-  if (g_fast_layout == 1) {
-    PSK_FAST_LAUNCH(stage_warp_fast126_kernel, PSK_FAST_MIN_BLOCKS, 0);
-  } else if (g_fast_layout == 2) {
-    if constexpr (kHot) {
-      switch (g_fast_occ * 2 + g_fast_park) {
-        case 1: PSK_FAST_LAUNCH_SHARE(4, 256, true); break;
-        case 2: PSK_FAST_LAUNCH_SHARE(5, 224, false); break;
-        case 3: PSK_FAST_LAUNCH_SHARE(5, 224, true); break;
-        case 4: PSK_FAST_LAUNCH_SHARE(6, 224, false); break;
-        case 5: PSK_FAST_LAUNCH_SHARE(6, 224, true); break;
-        case 6: PSK_FAST_LAUNCH_SHARE(8, 160, false); break;
-        case 7: PSK_FAST_LAUNCH_SHARE(8, 160, true); break;
-        default: PSK_FAST_LAUNCH_SHARE(4, 256, false); break;
-      }
-    } else {
-      PSK_FAST_LAUNCH(stage_warp_fast_share_kernel, PSK_FAST_MIN_BLOCKS, 1);  // LATE = 0 spills at 64 registers
-    }
-  } else {
+  if (g_fast_layout == 2)
+    stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX><<<grid, threads, 0, st>>>(q);
+  else
     stage_warp_fast_kernel<EQ, FLUX, STAGE, WITH_MAX><<<grid, threads, 0, st>>>(q);
-  }
 }
 
 template <int EQ, int FLUX, int STAGE>
@@ -609,12 +581,7 @@ int launch_fast_stage(const StageParams &p, int batch, cudaStream_t st) {
   q.coef = p.invdx / FluxScale<EQ, FLUX>::value;
   q.eps9 = p.eps * (1.0 / 9.0);
   q.dt_stride = static_cast<int>(p.dt_stride);
-  // the CTA shapes of the occupancy variants cap the warps per CTA (hot configuration only)
-  constexpr bool kHotCfg = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV && STAGE != 0);
-  int wpc_max = g_fast_wpc_max;
-  if (kHotCfg && g_fast_layout == 2 && p.maxabs == nullptr && fast_occ_threads(g_fast_occ) / 32 < wpc_max)
-    wpc_max = fast_occ_threads(g_fast_occ) / 32;
-  const FastGeometry geo = fast_geometry(g_fast_layout, p.bc.n, wpc_max);
+  const FastGeometry geo = fast_geometry(p.bc.n, g_fast_wpc_max);
   q.chunks_per_row = geo.chunks_per_row;
   const int wpc = geo.wpc;
   const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
@@ -1055,7 +1022,8 @@ __global__ void step_control_kernel(int batch, double theta, double cfl_scale, d
 }
 
 // ---- whole-step kernel (step_warp_fused_kernel): cells per lane and CTA shape, tuning switch
-// psk_set_stage_variant(7000 + 10 R + shape); 7000 = off (three stage launches)
+// psk_set_stage_variant(7000 + 10 R + shape): 62 = R 6, 128 x 3 (default), 60 = R 6, 256 x 2, 82 = R 8, 192 x 2;
+// 7000 = off (three stage launches)
 static int g_step_variant = 62;  // R = 6, CTAs of 128 threads, 3 per SM (136 registers): 9.0e10 cell-updates/s on B200
 
 template <int R, int THREADS, int MINB>
@@ -1104,13 +1072,8 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     return PSK_OK;
   }
   switch (g_step_variant) {
-    case 40: return launch_step_shape<4, 256, 3>(q, d->n, batch, mx, st);
-    case 41: return launch_step_shape<4, 256, 2>(q, d->n, batch, mx, st);
     case 60: return launch_step_shape<6, 256, 2>(q, d->n, batch, mx, st);
-    case 61: return launch_step_shape<6, 192, 2>(q, d->n, batch, mx, st);
     case 62: return launch_step_shape<6, 128, 3>(q, d->n, batch, mx, st);
-    case 80: return launch_step_shape<8, 256, 1>(q, d->n, batch, mx, st);
-    case 81: return launch_step_shape<8, 128, 3>(q, d->n, batch, mx, st);
     case 82: return launch_step_shape<8, 192, 2>(q, d->n, batch, mx, st);
     default: return PSK_E_UNSUPPORTED;
   }
@@ -1130,17 +1093,16 @@ int psk_version(void) { return PSK_VERSION; }
 /* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
  * kernel (default), 1 = shared-memory tile kernel */
 int psk_set_stage_variant(int variant) {
-  if (variant >= 7000) {  // 7000 + 10 R + shape: whole-step kernel (psk_ssprk33_step); 7000 = off
-    g_step_variant = variant - 7000;
+  if (variant >= 7000) {  // whole-step kernel (psk_ssprk33_step): 7062 (default) / 7060 / 7082 = cells per lane and CTA shape, 7000 = off
+    const int v = variant - 7000;
+    if (v != 0 && v != 60 && v != 62 && v != 82) return PSK_E_INVALID;
+    g_step_variant = v;
     return PSK_OK;
   }
-  if (variant >= 5000) {  // 5000 + 100 (CTA shape) + 10 (park u0 in shared memory) + layout of the specialised kernel
-    const int v = variant - 5000;
-    const int layout = v % 10, park = (v / 10) % 10, occ = v / 100;
-    if (layout > 2 || park > 1 || occ > 3) return PSK_E_INVALID;
-    g_fast_layout = layout;  // 0: 120 cells per warp, 1: 126, 2: 120 + shared t / pq
-    g_fast_park = park;
-    g_fast_occ = occ;  // 0: 256 x 4, 1: 224 x 5, 2: 224 x 6, 3: 160 x 8
+  if (variant >= 5000) {  // 5000 + layout of the specialised stage kernel (0 or 2)
+    const int layout = variant - 5000;
+    if (layout != 0 && layout != 2) return PSK_E_INVALID;
+    g_fast_layout = layout;
     return PSK_OK;
   }
   if (variant >= 4000) {  // 4000 + max warps per CTA of the specialised kernel (4..8)

@@ -50,26 +50,13 @@ void run_grid(unsigned gx, unsigned gy, int wpc, Body body) {
   pthread_barrier_destroy(&warp.bar);
 }
 
+// layout 0: stage_warp_fast_kernel, 2: stage_warp_fast_share_kernel with the u0 placement the product
+// uses for the scheme, 12: the other placement (late u0 <-> early u0)
 template <int EQ, int FLUX, int STAGE, bool WITH_MAX>
-Kernel pick_layout(int layout, int late) {
-  constexpr bool kHot = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV);
-  constexpr int M = PSK_FAST_MIN_BLOCKS;
-  if (layout == 1) {
-    if constexpr (kHot) {
-      if (late == 1) return &psk::stage_warp_fast126_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 1>;
-      if (late == 2) return &psk::stage_warp_fast126_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 2>;
-    }
-    return &psk::stage_warp_fast126_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 0>;
-  }
-  if (layout == 2) {
-    if constexpr (kHot) {
-      if (late == 1) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 1>;
-      if (late == 2) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 2>;
-      if (late == 3) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 0, 256, true>;  // PARK
-    }
-    if (!kHot) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 1>;  // as launch_fast_layout
-    return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, M, 0>;
-  }
+Kernel pick_layout(int layout, int /*late*/) {
+  constexpr int kDefault = (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV) ? 0 : 1;
+  if (layout == 2) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX>;
+  if (layout == 12) return &psk::stage_warp_fast_share_kernel<EQ, FLUX, STAGE, WITH_MAX, 1 - kDefault>;
   return &psk::stage_warp_fast_kernel<EQ, FLUX, STAGE, WITH_MAX>;
 }
 
@@ -142,7 +129,7 @@ int emu_fast_stage(int layout, int late, int equation, int flux, int stage, int 
   q.coef = (1.0 / dx) / scale;
   q.eps9 = eps * (1.0 / 9.0);
   q.dt_stride = dt_stride;
-  const psk::FastGeometry geo = psk::fast_geometry(layout, n, wpc_max);
+  const psk::FastGeometry geo = psk::fast_geometry(n, wpc_max);
   q.chunks_per_row = geo.chunks_per_row;
   const unsigned gx = static_cast<unsigned>((geo.chunks_per_row + geo.wpc - 1) / geo.wpc);
 
@@ -182,6 +169,6 @@ int emu_fused_step(int R, int with_max, int n, int g, int batch, long long ld, d
   return 0;
 }
 
-int emu_chunks_per_row(int layout, int n) { return psk::fast_geometry(layout, n, 8).chunks_per_row; }
+int emu_chunks_per_row(int n) { return psk::fast_geometry(n, 8).chunks_per_row; }
 
 }  // extern "C"

@@ -1,6 +1,7 @@
 """A/B of the specialised stage kernel's layout variants on the GPU box (scratch tool, not product).
 
-For every variant (psk_set_stage_variant(5000 + 100*fewer_ctas + 10*late + layout)):
+For every variant (v < 1000: psk_set_stage_variant(5000 + layout) with three stage launches per step;
+v >= 1000: the whole-step kernel psk_set_stage_variant(7000 + v - 1000)):
   * parity against the C oracle on a small ensemble (the checker), difference from layout 0,
     bitwise shift equivariance, the fused max-|u| path (adaptive solve) and the other Burgers
     fluxes of the specialised kernel;
@@ -125,7 +126,7 @@ def sm_clock() -> int:
 def main() -> None:
     """interleaved rounds over the candidates on ONE solver (same buffers), after a thermal warm-up"""
     t_start = time.time()
-    codes = [0, 2, 112, 1040, 1041, 1060, 1061, 1062, 1080, 1081, 1082]
+    codes = [0, 2, 1060, 1062, 1082]
     if os.environ.get("AB_CODES"):
         codes = [int(x) for x in os.environ["AB_CODES"].split(",")]
     batch, n = int(os.environ.get("AB_BATCH", "65536")), 4096
@@ -170,7 +171,7 @@ def main() -> None:
     with open(OUT / "ab_stage.jsonl", "w") as fh:
         for v in codes:
             xs = sorted(samples[v])
-            row = {"variant": v, "layout": v % 10, "park": (v // 10) % 10, "occ": v // 100,
+            row = {"variant": v,
                    "median": xs[len(xs) // 2], "min": xs[0], "max": xs[-1],
                    "hbm_frac_64B_median": xs[len(xs) // 2] * 64 / 6545.9e9, "sm_mhz": clocks[v], **par[v]}
             rows.append(row)

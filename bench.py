@@ -142,7 +142,7 @@ def run_reference(args: argparse.Namespace) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # }}}
@@ -366,7 +366,7 @@ def run_ours(args: argparse.Namespace) -> None:
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_port_throughput(target_seconds=15.0)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -427,7 +427,7 @@ def run_slab(args: argparse.Namespace) -> None:
         value = n_global * args.steps / (float(ms) * 1e-3)
         peak, peak_src = measured_peaks()
         achieved = value / world * ALGO_BYTES_PER_CELL_UPDATE / 1e9
-        print(json.dumps({
+        emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(ms) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -444,7 +444,7 @@ def run_slab(args: argparse.Namespace) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src},
             "gpu_launches": launches_per_step * args.steps,
-        }), flush=True)
+        })
     if args.transport != "nccl":
         slab.close()
     dist.destroy_process_group()
@@ -504,7 +504,7 @@ def run_adjoint(args: argparse.Namespace) -> None:
         # plus the segment recompute (64 B per forward step, amortised (segment - 1) / segment)
         algo = 144.0 + 64.0 * (adj.segment - 1) / adj.segment
         achieved = adj_rate / world * algo / 1e9
-        print(json.dumps({
+        emit({
             "metric": "adjoint gradients/s", "value": batch * world / ((fwd_ms + bwd_ms) * 1e-3), "unit": "gradients/s",
             "n_gpus": world, "steps": nsteps, "warmup": args.warmup, "ms_per_step": (fwd_ms + bwd_ms) / nsteps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -516,12 +516,27 @@ def run_adjoint(args: argparse.Namespace) -> None:
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_cell_step": algo},
             "gpu_launches": adj.launches,
-        }), flush=True)
+        })
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main() -> None:
+    # stdout carries the JSON line and nothing else: anything a library prints to fd 1 (NCCL's
+    # version banner at communicator creation) goes to stderr instead
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", choices=("ensemble", "slab", "adjoint"), default="ensemble",
                     help="ensemble = the headline config (default); slab / adjoint = BASELINE configs 4 and 5")

@@ -168,7 +168,8 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
                       int ghost_rows, psk_stream_t stream);
 
 /* One whole SSPRK33 step (timestepping.py:312-320: the three stages above) in ONE launch, for the
- * hot configuration only: Burgers + Rusanov (nu = 1) + WENO-JS5, FAST math, periodic rows, g = 3,
+ * hot configuration only: Burgers with the Rusanov (nu = 1), upwind or Engquist-Osher flux + WENO-JS5,
+ * FAST math, periodic rows, g = 3,
  * 16-byte aligned rows.  u is read once and uout written once; the stage values stay in registers
  * (temporal blocking, psk_fast_kernels.cuh).  Bit-identical to three psk_ssprk33_stage calls.
  * uout must not alias u.  active / maxabs as in psk_ssprk33_stage, except that rows with

@@ -410,8 +410,8 @@ stage_warp_fast_share_kernel(const FastParams p) {
 
 // ---------------------------------------------------------------------------
 // The whole SSPRK33 step of the hot configuration in ONE launch (temporal blocking over the three
-// stages; timestepping.py:312-320 with the RHS of schemes.py:339-346): Burgers + Rusanov,
-// WENO-JS5 FAST, periodic rows.  u is read once and u' written once: 16 B of HBM traffic per
+// stages; timestepping.py:312-320 with the RHS of schemes.py:339-346): Burgers with the Rusanov,
+// upwind ("Godunov") or Engquist-Osher flux, WENO-JS5 FAST, periodic rows.  u is read once and u' written once: 16 B of HBM traffic per
 // cell-update instead of the 64 B of three stage launches, one load phase per step instead of
 // three, and the stage values k1, k2 never leave the registers.
 //
@@ -434,7 +434,7 @@ struct StepParams {
   const uint8_t *active;  // rows with active[r] == 0 are copied through
   unsigned long long *maxabs;
   int64_t ld;
-  double coef;  // 1 / (4 dx)
+  double coef;  // 1 / (flux scale * dx): 4 for Rusanov, 2 for the upwind and Engquist-Osher fluxes
   double eps9;  // eps / 9
   int dt_stride;
   int chunks_per_row;
@@ -449,7 +449,7 @@ struct StepGeometry {
 };
 
 // one stage on the lane's R cells: a (stage input, own cells) -> L = coef * dF per own cell
-template <int R>
+template <int R, int FLUX>
 __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9, double (&dF)[R]) {
   constexpr unsigned kFull = 0xffffffffu;
   double w0 = __shfl_up_sync(kFull, a[R - 1], 1);  // cell own - 1
@@ -468,11 +468,13 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
   }
   pq[0] = __shfl_up_sync(kFull, pq[R], 1);
   pq[R + 1] = __shfl_down_sync(kFull, pq[1], 1);
-  double m2[R + 2];  // -2 |w| of the cells own - 1 .. own + R
-  m2[0] = -2.0 * fabs(w0);
+  double m2[R + 2];  // -2 |w| of the cells own - 1 .. own + R (Rusanov speed, as in the stage kernel)
+  if (FLUX == PSK_FLUX_RUSANOV) {
+    m2[0] = -2.0 * fabs(w0);
 #pragma unroll
-  for (int j = 1; j <= R; ++j) m2[j] = -2.0 * fabs(a[j - 1]);
-  m2[R + 1] = __shfl_down_sync(kFull, m2[1], 1);
+    for (int j = 1; j <= R; ++j) m2[j] = -2.0 * fabs(a[j - 1]);
+    m2[R + 1] = __shfl_down_sync(kFull, m2[1], 1);
+  }
   double ul[R], ur[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
@@ -487,13 +489,21 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
   for (int f = 0; f <= R; ++f) {
     const double urj = (f == 0) ? ur_left : ur[f - 1];
     const double ulp = (f == R) ? ul_right : ul[f];
-    F[f] = fma(umax_neg(m2[f], m2[f + 1]), ulp - urj, fma(urj, urj, ulp * ulp));
+    if (FLUX == PSK_FLUX_RUSANOV) {  // 4 F (scalar.py:231-249)
+      F[f] = fma(umax_neg(m2[f], m2[f + 1]), ulp - urj, fma(urj, urj, ulp * ulp));
+    } else if (FLUX == PSK_FLUX_UPWIND) {  // 2 F (scalar.py:123-132)
+      const double x = (urj + ulp) > 0.0 ? urj : ulp;
+      F[f] = x * x;
+    } else {  // Engquist-Osher, omega = 0: 2 F (scalar.py:311-322)
+      const double vp = fmax(urj, 0.0), vm = fmin(ulp, 0.0);
+      F[f] = fma(vp, vp, vm * vm);
+    }
   }
 #pragma unroll
   for (int r = 0; r < R; ++r) dF[r] = F[r] - F[r + 1];
 }
 
-template <int R, bool WITH_MAX, int THREADS, int MINB>
+template <int R, int FLUX, bool WITH_MAX, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 step_warp_fused_kernel(const StepParams p) {
   using Geo = StepGeometry<R>;
@@ -538,13 +548,13 @@ step_warp_fused_kernel(const StepParams p) {
   const double cdt = p.coef * p.dt[static_cast<int64_t>(row) * p.dt_stride];
 
   double a[R], dF[R];
-  step_stage_rhs<R>(u0, p.eps9, dF);
+  step_stage_rhs<R, FLUX>(u0, p.eps9, dF);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);  // k1
-  step_stage_rhs<R>(a, p.eps9, dF);
+  step_stage_rhs<R, FLUX>(a, p.eps9, dF);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);  // k2
-  step_stage_rhs<R>(a, p.eps9, dF);
+  step_stage_rhs<R, FLUX>(a, p.eps9, dF);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);  // u'
 

@@ -1026,7 +1026,7 @@ __global__ void step_control_kernel(int batch, double theta, double cfl_scale, d
 // 7000 = off (three stage launches)
 static int g_step_variant = 62;  // R = 6, CTAs of 128 threads, 3 per SM (136 registers): 9.0e10 cell-updates/s on B200
 
-template <int R, int THREADS, int MINB>
+template <int R, int FLUX, int THREADS, int MINB>
 int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cudaStream_t st) {
   StepParams q = q0;
   q.chunks_per_row = (n + StepGeometry<R>::kEmit - 1) / StepGeometry<R>::kEmit;
@@ -1037,9 +1037,9 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
   if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
   const dim3 grid(gx, gy, batch / gy);
   if (with_max)
-    step_warp_fused_kernel<R, true, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, true, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
   else
-    step_warp_fused_kernel<R, false, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
 }
@@ -1050,7 +1050,7 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
   q.u = u; q.uout = uout; q.dt = dt; q.active = active;
   q.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
   q.ld = d->ld;
-  q.coef = (1.0 / d->dx) / FluxScale<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV>::value;
+  q.coef = (1.0 / d->dx) / (d->flux == PSK_FLUX_RUSANOV ? 4.0 : 2.0);  // FluxScale<PSK_EQ_BURGERS, .>
   q.eps9 = d->eps * (1.0 / 9.0);
   q.dt_stride = static_cast<int>(dt_stride);
   q.n = d->n;
@@ -1071,10 +1071,18 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     }
     return PSK_OK;
   }
+  // the other Burgers fluxes: default shape only
+  if (d->flux == PSK_FLUX_UPWIND) return launch_step_shape<6, PSK_FLUX_UPWIND, 128, 3>(q, d->n, batch, mx, st);
+  if (d->flux == PSK_FLUX_ENGQUIST_OSHER)
+    return launch_step_shape<6, PSK_FLUX_ENGQUIST_OSHER, 128, 3>(q, d->n, batch, mx, st);
+  constexpr int kRus = PSK_FLUX_RUSANOV;
   switch (g_step_variant) {
-    case 60: return launch_step_shape<6, 256, 2>(q, d->n, batch, mx, st);
-    case 62: return launch_step_shape<6, 128, 3>(q, d->n, batch, mx, st);
-    case 82: return launch_step_shape<8, 192, 2>(q, d->n, batch, mx, st);
+    case 60: return launch_step_shape<6, kRus, 256, 2>(q, d->n, batch, mx, st);
+    case 62: return launch_step_shape<6, kRus, 128, 3>(q, d->n, batch, mx, st);
+    case 82: return launch_step_shape<8, kRus, 192, 2>(q, d->n, batch, mx, st);
+    case 83: return launch_step_shape<8, kRus, 256, 2>(q, d->n, batch, mx, st);
+    case 84: return launch_step_shape<8, kRus, 128, 4>(q, d->n, batch, mx, st);
+    case 103: return launch_step_shape<10, kRus, 128, 2>(q, d->n, batch, mx, st);
     default: return PSK_E_UNSUPPORTED;
   }
 }
@@ -1095,7 +1103,7 @@ int psk_version(void) { return PSK_VERSION; }
 int psk_set_stage_variant(int variant) {
   if (variant >= 7000) {  // whole-step kernel (psk_ssprk33_step): 7062 (default) / 7060 / 7082 = cells per lane and CTA shape, 7000 = off
     const int v = variant - 7000;
-    if (v != 0 && v != 60 && v != 62 && v != 82) return PSK_E_INVALID;
+    if (v != 0 && v != 60 && v != 62 && v != 82 && v != 83 && v != 84 && v != 103) return PSK_E_INVALID;
     g_step_variant = v;
     return PSK_OK;
   }
@@ -1244,7 +1252,8 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
   if (u == nullptr || uout == nullptr || dt == nullptr || uout == u) return PSK_E_INVALID;
   const bool aligned = (reinterpret_cast<uintptr_t>(u + d->g) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0) && (d->ld % 2 == 0);
-  if (d->equation != PSK_EQ_BURGERS || d->flux != PSK_FLUX_RUSANOV || d->rec != PSK_REC_WENOJS53 ||
+  const bool flux_ok = d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER;
+  if (d->equation != PSK_EQ_BURGERS || !flux_ok || d->rec != PSK_REC_WENOJS53 ||
       d->math != PSK_MATH_FAST || d->bc != PSK_BC_PERIODIC || d->g != 3 || d->nu != nullptr || !aligned ||
       g_step_variant == 0)
     return PSK_E_UNSUPPORTED;

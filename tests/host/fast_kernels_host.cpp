@@ -138,29 +138,34 @@ int emu_fast_stage(int layout, int late, int equation, int flux, int stage, int 
 }
 
 // One whole SSPRK33 step with the fused kernel (R cells per lane), launched like launch_step_shape.
-int emu_fused_step(int R, int with_max, int n, int g, int batch, long long ld, double dx, double eps,
+int emu_fused_step(int R, int flux, int with_max, int n, int g, int batch, long long ld, double dx, double eps,
                    const double *u, double *uout, const double *dt, int dt_stride, const unsigned char *active,
                    unsigned long long *maxabs) {
   psk::StepParams q{};
   q.u = u; q.uout = uout; q.dt = dt; q.active = active;
   q.maxabs = with_max ? maxabs : nullptr;
   q.ld = ld;
-  q.coef = (1.0 / dx) / psk::FluxScale<PSK_EQ_BURGERS, PSK_FLUX_RUSANOV>::value;
+  q.coef = (1.0 / dx) / (flux == PSK_FLUX_RUSANOV ? 4.0 : 2.0);
   q.eps9 = eps * (1.0 / 9.0);
   q.dt_stride = dt_stride;
   q.n = n;
   q.g = g;
   void (*k)(const psk::StepParams) = nullptr;
   int emit = 0;
-  switch (R * 2 + (with_max ? 1 : 0)) {
-    case 8: k = &psk::step_warp_fused_kernel<4, false, 256, 2>; emit = psk::StepGeometry<4>::kEmit; break;
-    case 9: k = &psk::step_warp_fused_kernel<4, true, 256, 2>; emit = psk::StepGeometry<4>::kEmit; break;
-    case 12: k = &psk::step_warp_fused_kernel<6, false, 256, 2>; emit = psk::StepGeometry<6>::kEmit; break;
-    case 13: k = &psk::step_warp_fused_kernel<6, true, 256, 2>; emit = psk::StepGeometry<6>::kEmit; break;
-    case 16: k = &psk::step_warp_fused_kernel<8, false, 256, 1>; emit = psk::StepGeometry<8>::kEmit; break;
-    case 17: k = &psk::step_warp_fused_kernel<8, true, 256, 1>; emit = psk::StepGeometry<8>::kEmit; break;
-    default: return -1;
-  }
+  constexpr int kRus = PSK_FLUX_RUSANOV, kUp = PSK_FLUX_UPWIND, kEo = PSK_FLUX_ENGQUIST_OSHER;
+#define EMU_STEP(RR, FL)                                                                                    \
+  do {                                                                                                      \
+    k = with_max ? &psk::step_warp_fused_kernel<RR, FL, true, 256, 1> : &psk::step_warp_fused_kernel<RR, FL, false, 256, 1>; \
+    emit = psk::StepGeometry<RR>::kEmit;                                                                    \
+  } while (0)
+  if (flux == kRus && R == 4) EMU_STEP(4, kRus);
+  else if (flux == kRus && R == 6) EMU_STEP(6, kRus);
+  else if (flux == kRus && R == 8) EMU_STEP(8, kRus);
+  else if (flux == kRus && R == 10) EMU_STEP(10, kRus);
+  else if (flux == kUp && R == 6) EMU_STEP(6, kUp);
+  else if (flux == kEo && R == 6) EMU_STEP(6, kEo);
+  else return -1;
+#undef EMU_STEP
   q.chunks_per_row = (n + emit - 1) / emit;
   int wpc = 8;
   if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;

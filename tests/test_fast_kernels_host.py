@@ -38,7 +38,7 @@ def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
     lib.emu_fast_stage.argtypes = [ct.c_int] * 10 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, dp,
                                                      ct.c_int, dp, ct.c_longlong, dp, up, dp, dp, dp, ct.c_int]
     lib.emu_fast_stage.restype = ct.c_int
-    lib.emu_fused_step.argtypes = [ct.c_int] * 5 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
+    lib.emu_fused_step.argtypes = [ct.c_int] * 6 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
                                                    ct.POINTER(ct.c_ubyte), up]
     lib.emu_fused_step.restype = ct.c_int
     lib.emu_chunks_per_row.argtypes = [ct.c_int]
@@ -177,12 +177,13 @@ def test_geometry(emu) -> None:
         assert emu.emu_chunks_per_row(n) == -(-n // 120)
 
 
-@pytest.mark.parametrize("R", [4, 6, 8])
+@pytest.mark.parametrize("R,flux", [(4, "rusanov"), (6, "rusanov"), (8, "rusanov"), (10, "rusanov"), (6, "godunov"),
+                                    (6, "eo")])
 @pytest.mark.parametrize("n", [16, 107, 108, 109, 172, 236, 237, 250, 472, 1000])
-def test_fused_step_is_the_three_stages_bit_for_bit(emu, R: int, n: int) -> None:
+def test_fused_step_is_the_three_stages_bit_for_bit(emu, R: int, flux: str, n: int) -> None:
     """psk_ssprk33_step's kernel (temporal blocking, R cells per lane): same bits as three stage
     launches, nothing written outside the interior, fused max |u'|, inactive rows copied through"""
-    pb = Problem("burgers", "rusanov", "periodic", n=n, batch=3, seed=100 + n)
+    pb = Problem("burgers", flux, "periodic", n=n, batch=3, seed=100 + n)
     i = pb.interior
     staged, _ = pb.step(emu, 2)
     ref = pb.co.ssprk33_step(pb.u, pb.dt)
@@ -190,7 +191,7 @@ def test_fused_step_is_the_three_stages_bit_for_bit(emu, R: int, n: int) -> None
     maxabs = np.zeros(pb.batch, dtype=np.uint64)
     active = np.array([1, 0, 1], dtype=np.uint8)
     u_in = pb.fill(pb.u)  # the stored ghost cells are never read
-    rc = emu.emu_fused_step(R, 1, n, G, pb.batch, pb.nx, pb.dx, EPS, _p(u_in), _p(out), _p(pb.dt), 1,
+    rc = emu.emu_fused_step(R, FLUX[flux], 1, n, G, pb.batch, pb.nx, pb.dx, EPS, _p(u_in), _p(out), _p(pb.dt), 1,
                             active.ctypes.data_as(ct.POINTER(ct.c_ubyte)),
                             maxabs.ctypes.data_as(ct.POINTER(ct.c_ulonglong)))
     assert rc == 0

@@ -1080,9 +1080,6 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     case 60: return launch_step_shape<6, kRus, 256, 2>(q, d->n, batch, mx, st);
     case 62: return launch_step_shape<6, kRus, 128, 3>(q, d->n, batch, mx, st);
     case 82: return launch_step_shape<8, kRus, 192, 2>(q, d->n, batch, mx, st);
-    case 83: return launch_step_shape<8, kRus, 256, 2>(q, d->n, batch, mx, st);
-    case 84: return launch_step_shape<8, kRus, 128, 4>(q, d->n, batch, mx, st);
-    case 103: return launch_step_shape<10, kRus, 128, 2>(q, d->n, batch, mx, st);
     default: return PSK_E_UNSUPPORTED;
   }
 }
@@ -1103,7 +1100,7 @@ int psk_version(void) { return PSK_VERSION; }
 int psk_set_stage_variant(int variant) {
   if (variant >= 7000) {  // whole-step kernel (psk_ssprk33_step): 7062 (default) / 7060 / 7082 = cells per lane and CTA shape, 7000 = off
     const int v = variant - 7000;
-    if (v != 0 && v != 60 && v != 62 && v != 82 && v != 83 && v != 84 && v != 103) return PSK_E_INVALID;
+    if (v != 0 && v != 60 && v != 62 && v != 82) return PSK_E_INVALID;
     g_step_variant = v;
     return PSK_OK;
   }

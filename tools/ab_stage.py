@@ -126,7 +126,7 @@ def sm_clock() -> int:
 def main() -> None:
     """interleaved rounds over the candidates on ONE solver (same buffers), after a thermal warm-up"""
     t_start = time.time()
-    codes = [2, 1060, 1062, 1082, 1083, 1084, 1103]
+    codes = [0, 2, 1060, 1062, 1082]
     if os.environ.get("AB_CODES"):
         codes = [int(x) for x in os.environ["AB_CODES"].split(",")]
     batch, n = int(os.environ.get("AB_BATCH", "65536")), 4096

@@ -357,8 +357,8 @@ def run_ours(args: argparse.Namespace) -> None:
             "e2e": {
                 "value": cells_per_step * args.steps / e2e_s, "unit": UNIT,
                 "h2d_bytes_per_step": bytes_state / args.steps, "d2h_bytes_per_step": bytes_state / args.steps,
-                "call": "EnsembleSolver.solve_fixed_dt_host(pinned host in, pinned host out, dt, K): 8 row blocks, "
-                        "upload / K steps / download pipelined over 4 streams",
+                "call": f"EnsembleSolver.solve_fixed_dt_host(pinned host in, pinned host out, dt, K): "
+                        f"{max(1, min(64, batch // 1024))} row blocks, upload / K steps / download pipelined over 4 streams",
                 "seconds": e2e_s,
             },
             "gpu_launches": launches,

@@ -176,18 +176,24 @@ class EnsembleSolver:
         dt: float | torch.Tensor,
         nsteps: int,
         *,
-        groups: int = 8,
+        groups: int | None = None,
         streams: int = 4,
     ) -> SolveResult:
         """Host-to-host call: ``host_in`` / ``host_out`` are (pinned) host tensors of shape
         ``(batch, nx)``.  Rows are independent problems, so the batch is cut into ``groups`` row
-        blocks and each block runs upload -> ``nsteps`` steps -> download on its own stream: the
+        blocks (default: blocks of at least 1024 rows, at most 64 blocks) and each block runs
+        upload -> ``nsteps`` steps -> download on its own stream: the
         PCIe copies of one block overlap the arithmetic of the others (both copy engines busy)."""
         if tuple(host_in.shape) != (self.batch, self.nx) or tuple(host_out.shape) != (self.batch, self.nx):
             raise ValueError(f"expected host tensors of shape {(self.batch, self.nx)}")
         dev = self.hp.device
         if not isinstance(dt, torch.Tensor):
             dt = torch.full((1,), float(dt), dtype=torch.float64, device=dev)
+        if groups is None:
+            # blocks of >= 1024 rows, at most 64 of them: the first upload and the last download are the only
+            # copies not hidden behind arithmetic (measured on B200, 65536 x 4096, 20 steps: 8 blocks 7.5e10,
+            # 16: 8.0e10, 32: 8.4e10, 64: 8.6e10 cell-updates/s; 4 streams beat 2 and 8)
+            groups = min(64, self.batch // 1024)
         groups = max(1, min(groups, self.batch))
         if not hasattr(self, "_streams") or len(self._streams) != streams:
             self._streams = [torch.cuda.Stream(device=dev) for _ in range(streams)]

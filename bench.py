@@ -394,11 +394,12 @@ def run_slab(args: argparse.Namespace) -> None:
         slab = SlabSolver(n_global=n_global, ring=DistRing(), dx=h, device=dev)
         launches_per_step = 3
     else:
-        slab = PeerSlabSolver(n_global=n_global, rank=rank, world=world, dx=h, device=dev,
+        whole = args.transport == "p2p-step"
+        slab = PeerSlabSolver(n_global=n_global, rank=rank, world=world, dx=h, device=dev, whole_step=whole,
                               overlap=(args.transport == "p2p-overlap"), fused=(args.transport == "p2p"))
         slab.connect()
-        # per stage: fused = 1 launch; else wait, (2 edge +) 1 stage kernel, push
-        launches_per_step = 3 if slab.fused else (15 if slab.split else 9)
+        # per stage: fused = 1 launch; else wait, (2 edge +) 1 stage kernel, push; whole step: wait, step, push
+        launches_per_step = 3 if (slab.fused or whole) else (15 if slab.split else 9)
     i = torch.arange(slab.first, slab.first + slab.n_local, device=dev, dtype=torch.float64)
     slab.load_interior(0.5 + torch.sin(2.0 * np.pi * (i + 0.5) / n_global))
     del i
@@ -432,14 +433,18 @@ def run_slab(args: argparse.Namespace) -> None:
             "ms_per_step": float(ms) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"single periodic Burgers grid N={n_global} cells, slab-decomposed over {world} rank(s), "
-                                   "ring halo exchange 3 cells/side/stage (BASELINE.json configs[3])",
-                       "cells_per_gpu": slab.n_local, "halo_exchanges_per_step": 3, "finite": finite,
+                                   + ("ring halo exchange 9 cells/side/step" if args.transport == "p2p-step" else
+                                      "ring halo exchange 3 cells/side/stage") + " (BASELINE.json configs[3])",
+                       "cells_per_gpu": slab.n_local,
+                       "halo_exchanges_per_step": 1 if args.transport == "p2p-step" else 3, "finite": finite,
                        "cuda_graph": bool(kw),
                        "transport": {"p2p": "exchange fused into the stage kernel: edge warps spin on local epoch flags, "
                                             "edge lanes store into the neighbours' ghost slots over NVLink (1 launch per stage)",
                                      "p2p-overlap": "NVLink peer stores + epoch flags, slab edges on a high-priority stream "
                                                     "overlapped with the interior",
                                      "p2p-serial": "NVLink peer stores + epoch flags, no overlap",
+                                     "p2p-step": "whole SSPRK33 step in one launch on a slab with 9 ghost cells; one "
+                                                 "exchange per step (NVLink peer stores + epoch flags, no overlap)",
                                      "nccl": "NCCL send/recv pairs per stage"}[args.transport]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src},
@@ -540,7 +545,7 @@ def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", choices=("ensemble", "slab", "adjoint"), default="ensemble",
                     help="ensemble = the headline config (default); slab / adjoint = BASELINE configs 4 and 5")
-    ap.add_argument("--transport", choices=("p2p", "p2p-overlap", "p2p-serial", "nccl"), default="p2p",
+    ap.add_argument("--transport", choices=("p2p", "p2p-overlap", "p2p-serial", "p2p-step", "nccl"), default="p2p",
                     help="ghost-cell exchange of the slab workload")
     ap.add_argument("--graph", action="store_true", help="slab workload, fused transport: replay a CUDA graph of two steps")
     ap.add_argument("--cells", type=int, default=0, help="override the cell count of the slab / adjoint workloads")

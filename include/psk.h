@@ -169,7 +169,8 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
 
 /* One whole SSPRK33 step (timestepping.py:312-320: the three stages above) in ONE launch, for the
  * hot configuration only: Burgers with the Rusanov (nu = 1), upwind or Engquist-Osher flux + WENO-JS5,
- * FAST math, periodic rows, g = 3,
+ * FAST math, periodic rows (g >= 3) or slabs of a larger grid (boundary kind NONE with g >= 9 ghost
+ * cells per side, filled by the caller before the call: the three stages reach 9 cells beyond the row),
  * 16-byte aligned rows.  u is read once and uout written once; the stage values stay in registers
  * (temporal blocking, psk_fast_kernels.cuh).  Bit-identical to three psk_ssprk33_stage calls.
  * uout must not alias u.  active / maxabs as in psk_ssprk33_stage, except that rows with

@@ -425,7 +425,9 @@ stage_warp_fast_share_kernel(const FastParams p) {
 //     never reaches a stored cell): after three stages the window cells [9, 32 R - 9) are valid,
 //     of which the aligned range [10, 32 R - 10) is stored.  Consecutive windows of a row start
 //     32 R - 20 cells apart;
-//   * window cells beyond the row ends are the periodic images (loaded through the slow path).
+//   * window cells beyond the row ends are the periodic images, or -- for a slab of a larger grid
+//     (boundary kind NONE, g >= 9 ghost cells filled by the neighbours before the step) -- the row's
+//     stored ghost cells (loaded through the slow path).
 // FP64 work per emitted cell is that of the stage kernels (32 R / (32 R - 20) against 32 / 30).
 struct StepParams {
   const double *u;
@@ -439,6 +441,7 @@ struct StepParams {
   int dt_stride;
   int chunks_per_row;
   int n, g;
+  int bc_none;  // 1: window cells beyond the row ends are the row's stored ghost cells (slab of a larger grid, g >= 9)
 };
 
 template <int R>
@@ -534,9 +537,14 @@ step_warp_fused_kernel(const StepParams p) {
   } else {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      int c = (c0 + r) % n;  // periodic image (n >= 1)
-      if (c < 0) c += n;
-      u0[r] = p.u[base + c];
+      int c = c0 + r;
+      if (p.bc_none) {  // ghost cells filled by the neighbouring slabs; further out: never reaches a stored cell
+        u0[r] = (c >= -p.g && c < n + p.g) ? p.u[base + c] : 0.0;
+      } else {
+        c %= n;  // periodic image (n >= 1)
+        if (c < 0) c += n;
+        u0[r] = p.u[base + c];
+      }
     }
   }
   if (p.active != nullptr && p.active[row] == 0) {  // finished row: the state is carried over

@@ -1055,6 +1055,7 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
   q.dt_stride = static_cast<int>(dt_stride);
   q.n = d->n;
   q.g = d->g;
+  q.bc_none = d->bc == PSK_BC_NONE ? 1 : 0;
   const bool mx = maxabs != nullptr;
   int batch = d->batch;
   // rows beyond the grid.y limit: equal slices of 32768 rows
@@ -1251,8 +1252,8 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
                        (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0) && (d->ld % 2 == 0);
   const bool flux_ok = d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER;
   if (d->equation != PSK_EQ_BURGERS || !flux_ok || d->rec != PSK_REC_WENOJS53 ||
-      d->math != PSK_MATH_FAST || d->bc != PSK_BC_PERIODIC || d->g != 3 || d->nu != nullptr || !aligned ||
-      g_step_variant == 0)
+      d->math != PSK_MATH_FAST || d->nu != nullptr || !aligned || g_step_variant == 0 ||
+      !((d->bc == PSK_BC_PERIODIC && d->g >= 3) || (d->bc == PSK_BC_NONE && d->g >= 9)))
     return PSK_E_UNSUPPORTED;
   return launch_step_fused(d, u, uout, dt, dt_stride, active, maxabs, static_cast<cudaStream_t>(stream));
 }

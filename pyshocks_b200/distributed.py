@@ -364,10 +364,22 @@ class PeerSlabSolver:
     def __init__(self, *, n_global: int, rank: int, world: int, dx: float, flux: str = "rusanov",
                  rec: str = "wenojs53", eps: float = 1.0e-12, math: str = "fast", edge: int = 7680,
                  overlap: bool = True, fused: bool | None = None, device: torch.device | str | None = None,
-                 timeout_s: float = 20.0) -> None:
+                 timeout_s: float = 20.0, whole_step: bool = False) -> None:
         self.rank, self.world = rank, world
         self.first, self.n_local = shard_rows(n_global, rank, world)
         self.g = g = {"constant": 1, "wenojs32": 2, "wenojs53": 3}[rec]
+        # whole_step: ONE exchange of 9 cells per side and ONE launch per step (psk_ssprk33_step on a
+        # slab with 9 ghost cells: three stages reach 9 cells beyond the slab) instead of three
+        # exchanges of 3 cells and three launches; the state ping-pongs between arrays 0 and 1
+        self.whole = bool(whole_step)
+        if self.whole:
+            if not (flux in ("rusanov", "godunov", "eo") and rec == "wenojs53" and math == "fast"):
+                raise ValueError("whole_step needs a Burgers flux other than lf, wenojs53 and fast math")
+            if fused:
+                raise ValueError("whole_step and the per-stage fused exchange exclude each other")
+            self.g = g = 9
+            fused, overlap = False, False
+        self._cur = 0  # array of the store that holds the state (whole_step: 0 or 1)
         if self.n_local < 2 * g:
             raise ValueError("slabs must hold at least 2 g cells")
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -430,7 +442,7 @@ class PeerSlabSolver:
     def load_interior(self, u_local: torch.Tensor) -> None:
         """``u_local``: this rank's ``n_local`` interior cells; announces them to the neighbours."""
         self.solver.u[0, self.g : self.g + self.n_local].copy_(u_local)
-        self._push(0)
+        self._push(self._cur)
         if self.split:
             main = torch.cuda.current_stream()
             self.ev_main.record(main)
@@ -533,6 +545,19 @@ class PeerSlabSolver:
             self._stage(3, s.u, s.k2, s.u, 0, dt, maxabs)
 
     def step(self, dt: torch.Tensor, maxabs: torch.Tensor | None = None) -> None:
+        if self.whole:
+            # wait for the neighbours' 9 edge cells of the current state -> the whole step in one launch
+            # -> push the new state's edge cells into the neighbours' ghost slots of the OTHER array
+            # (they last read those slots one step ago, before the push this wait has just seen)
+            s = self.solver
+            self._wait()
+            if not s.hp.step_fused(s.u, s.k1, dt, maxabs=maxabs):
+                raise RuntimeError("psk_ssprk33_step does not cover this slab configuration")
+            s.u, s.k1 = s.k1, s.u
+            self._cur ^= 1
+            self._push(self._cur)
+            self.launches += 1
+            return
         for stage in (1, 2, 3):
             self.run_stage(stage, dt, maxabs)
 

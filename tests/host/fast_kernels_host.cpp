@@ -138,7 +138,7 @@ int emu_fast_stage(int layout, int late, int equation, int flux, int stage, int 
 }
 
 // One whole SSPRK33 step with the fused kernel (R cells per lane), launched like launch_step_shape.
-int emu_fused_step(int R, int flux, int with_max, int n, int g, int batch, long long ld, double dx, double eps,
+int emu_fused_step(int R, int flux, int bc_none, int with_max, int n, int g, int batch, long long ld, double dx, double eps,
                    const double *u, double *uout, const double *dt, int dt_stride, const unsigned char *active,
                    unsigned long long *maxabs) {
   psk::StepParams q{};
@@ -150,6 +150,7 @@ int emu_fused_step(int R, int flux, int with_max, int n, int g, int batch, long 
   q.dt_stride = dt_stride;
   q.n = n;
   q.g = g;
+  q.bc_none = bc_none;
   void (*k)(const psk::StepParams) = nullptr;
   int emit = 0;
   constexpr int kRus = PSK_FLUX_RUSANOV, kUp = PSK_FLUX_UPWIND, kEo = PSK_FLUX_ENGQUIST_OSHER;

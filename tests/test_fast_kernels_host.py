@@ -38,7 +38,7 @@ def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
     lib.emu_fast_stage.argtypes = [ct.c_int] * 10 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, dp,
                                                      ct.c_int, dp, ct.c_longlong, dp, up, dp, dp, dp, ct.c_int]
     lib.emu_fast_stage.restype = ct.c_int
-    lib.emu_fused_step.argtypes = [ct.c_int] * 6 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
+    lib.emu_fused_step.argtypes = [ct.c_int] * 7 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
                                                    ct.POINTER(ct.c_ubyte), up]
     lib.emu_fused_step.restype = ct.c_int
     lib.emu_chunks_per_row.argtypes = [ct.c_int]
@@ -191,7 +191,7 @@ def test_fused_step_is_the_three_stages_bit_for_bit(emu, R: int, flux: str, n: i
     maxabs = np.zeros(pb.batch, dtype=np.uint64)
     active = np.array([1, 0, 1], dtype=np.uint8)
     u_in = pb.fill(pb.u)  # the stored ghost cells are never read
-    rc = emu.emu_fused_step(R, FLUX[flux], 1, n, G, pb.batch, pb.nx, pb.dx, EPS, _p(u_in), _p(out), _p(pb.dt), 1,
+    rc = emu.emu_fused_step(R, FLUX[flux], 0, 1, n, G, pb.batch, pb.nx, pb.dx, EPS, _p(u_in), _p(out), _p(pb.dt), 1,
                             active.ctypes.data_as(ct.POINTER(ct.c_ubyte)),
                             maxabs.ctypes.data_as(ct.POINTER(ct.c_ulonglong)))
     assert rc == 0
@@ -201,3 +201,29 @@ def test_fused_step_is_the_three_stages_bit_for_bit(emu, R: int, flux: str, n: i
         assert np.abs(out[r, i] - ref[r, i]).max() <= 2e-13 * np.abs(ref[r, i]).max()
         assert maxabs.view(np.float64)[r] == np.abs(out[r, i]).max()
     assert np.array_equal(out[1, i], pb.u[1, i]) and maxabs[1] == 0
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("n", [344, 1000])
+def test_fused_step_on_slabs_with_nine_ghost_cells(emu, world: int, n: int) -> None:
+    """boundary kind NONE: a slab's window cells beyond its ends are its stored ghost cells (9 per side,
+    the neighbours' edge cells); the slabs together give the bits of the undecomposed periodic row"""
+    pb = Problem("burgers", "rusanov", "periodic", n=n, batch=1, seed=n)
+    whole = np.full_like(pb.u, np.nan)
+    mx = np.zeros(1, dtype=np.uint64)
+    none_u8 = ct.POINTER(ct.c_ubyte)()
+    assert emu.emu_fused_step(6, FLUX["rusanov"], 0, 0, n, G, 1, pb.nx, pb.dx, EPS, _p(pb.u), _p(whole), _p(pb.dt), 1,
+                              none_u8, mx.ctypes.data_as(ct.POINTER(ct.c_ulonglong))) == 0
+    interior = pb.u[0, G : G + n]
+    g9, first, out = 9, 0, []
+    for r in range(world):
+        nl = n // world + (1 if r < n % world else 0)
+        idx = (np.arange(first - g9, first + nl + g9)) % n  # the slab with its neighbours' cells as ghosts
+        slab = np.ascontiguousarray(interior[idx][None, :])
+        res = np.full_like(slab, np.nan)
+        assert emu.emu_fused_step(6, FLUX["rusanov"], 1, 0, nl, g9, 1, nl + 2 * g9, pb.dx, EPS, _p(slab), _p(res),
+                                  _p(pb.dt), 1, none_u8, mx.ctypes.data_as(ct.POINTER(ct.c_ulonglong))) == 0
+        assert np.isnan(res[0, :g9]).all() and np.isnan(res[0, g9 + nl :]).all()
+        out.append(res[0, g9 : g9 + nl])
+        first += nl
+    assert np.array_equal(np.concatenate(out), whole[0, G : G + n])

@@ -103,6 +103,75 @@ def test_peer_memory_slabs_equal_undecomposed(world: int, mode: str) -> None:
             s.mem.close()
 
 
+@pytest.mark.parametrize("flux", ["rusanov", "eo"])
+@pytest.mark.parametrize("world,n,nsteps", [(1, 6151, 5), (2, 6151, 8), (3, 4099, 7), (4, 500, 6)])
+def test_whole_step_slabs_equal_undecomposed(world: int, n: int, nsteps: int, flux: str) -> None:
+    """whole_step=True: ONE launch (psk_ssprk33_step on a slab with 9 ghost cells) and ONE exchange of 9
+    cells per side per step, every slab held by this process: bit-identical to the periodic solve"""
+    from pyshocks_b200.distributed import PeerRing, PeerSlabSolver
+    from pyshocks_b200.ensemble import EnsembleSolver
+
+    g = 3
+    dt = 0.4 * (3.0 / n) / 1.8
+    single = EnsembleSolver(equation="burgers", flux=flux, rec="wenojs53", bc="periodic", n=n, g=g, dx=3.0 / n,
+                            eps=1e-12, batch=1)
+    u0 = np.zeros((1, n + 2 * g))
+    u0[0, g : g + n] = _ic(n, g)
+    single.solve_fixed_dt(torch.from_numpy(u0).cuda(), dt, nsteps)
+    ref = single.u[0, g : g + n]
+    ug = torch.from_numpy(_ic(n, g)).cuda()
+    slabs = [PeerSlabSolver(n_global=n, rank=r, world=world, dx=3.0 / n, flux=flux, whole_step=True, timeout_s=5.0)
+             for r in range(world)]
+    try:
+        assert all(s.whole and s.g == 9 and not s.fused and not s.split for s in slabs)
+        for r, s in enumerate(slabs):
+            s.attach(PeerRing.local([t.mem for t in slabs], r))
+        for s in slabs:
+            s.load_interior(ug[s.first : s.first + s.n_local])
+        dtt = torch.full((1,), dt, dtype=torch.float64, device="cuda")
+        for _ in range(nsteps):  # step by step: every wait depends on pushes enqueued before it
+            for s in slabs:
+                s.step(dtt)
+        for s in slabs:
+            s.join()
+            s.check()
+        out = torch.cat([s.interior() for s in slabs])
+        assert torch.equal(out, ref)
+        assert all(s.exchanges == nsteps + 1 and s.launches == 3 * nsteps + 1 for s in slabs)
+    finally:
+        for s in slabs:
+            s.ring = None
+            s.solver = None
+            s.mem.close()
+
+
+def test_whole_step_slab_adaptive() -> None:
+    """timestepping.step's dt logic on a one-slab whole-step ring: the dt sequence and the bits of the
+    single-array adaptive solve"""
+    from pyshocks_b200.distributed import PeerRing, PeerSlabSolver
+    from pyshocks_b200.ensemble import EnsembleSolver
+
+    n, g = 1 << 13, 3
+    ug = torch.from_numpy(_ic(n, g)).cuda()
+    akw = dict(theta=0.8, tfinal=0.004, cfl_scale=0.5 * (3.0 / n))
+    single = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=g,
+                            dx=3.0 / n, eps=1e-12, batch=1)
+    u0 = torch.zeros((1, n + 2 * g), dtype=torch.float64, device="cuda")
+    u0[0, g : g + n] = ug
+    sres = single.solve_adaptive(u0, check_every=1, **akw)
+    ps = PeerSlabSolver(n_global=n, rank=0, world=1, dx=3.0 / n, whole_step=True, timeout_s=5.0)
+    try:
+        ps.attach(PeerRing.local([ps.mem], 0))
+        ps.load_interior(ug)
+        pres = ps.solve_adaptive(**akw)
+        assert pres.steps == sres.steps and float(ps.solver.t[0]) == float(single.t[0])
+        assert torch.equal(ps.interior(), single.u[0, g : g + n])
+    finally:
+        ps.ring = None
+        ps.solver = None
+        ps.mem.close()
+
+
 @pytest.mark.parametrize("math", ["strict", "fast"])
 def test_peer_memory_adaptive_single_slab(math: str) -> None:
     """timestepping.step's dt logic on a (one-slab) peer-memory ring: same dt sequence as the

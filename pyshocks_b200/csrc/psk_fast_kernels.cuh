@@ -170,7 +170,7 @@ __device__ __forceinline__ void fast_compute_store(const FastParams &p, int row,
         F[f] = fma(-2.0 * a, ulp - urj, fma(urj, urj, ulp * ulp));  // 4 F
       } else if (FLUX == PSK_FLUX_UPWIND) {
         const double w = (urj + ulp) > 0.0 ? urj : ulp;
-        F[f] = w * w;  // 2 F
+        F[f] = __dmul_rn(w, w);  // 2 F; never contracted with the flux difference (same bits in every kernel)
       } else {
         const double vp = fmax(urj, 0.0), vm = fmin(ulp, 0.0);
         F[f] = fma(vp, vp, vm * vm);  // 2 F
@@ -180,7 +180,7 @@ __device__ __forceinline__ void fast_compute_store(const FastParams &p, int row,
       const bool ok = (j >= 0 && j < p.bc.nx - 1);
       const double arj = ok ? p.vel_r[j] : 0.0, alp = ok ? p.vel_l[j + 1] : 0.0;
       const bool pos = (arj + alp) > 0.0;
-      F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? arj * urj : alp * ulp);
+      F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? __dmul_rn(arj, urj) : __dmul_rn(alp, ulp));
     }
   }
 
@@ -354,7 +354,7 @@ stage_warp_fast_share_kernel(const FastParams p) {
         F[f] = fma(a2, ulp - urj, fma(urj, urj, ulp * ulp));
       } else if (FLUX == PSK_FLUX_UPWIND) {
         const double x = (urj + ulp) > 0.0 ? urj : ulp;
-        F[f] = x * x;
+        F[f] = __dmul_rn(x, x);  // never contracted with the flux difference (same bits in every kernel)
       } else {
         const double vp = fmax(urj, 0.0), vm = fmin(ulp, 0.0);
         F[f] = fma(vp, vp, vm * vm);
@@ -364,7 +364,7 @@ stage_warp_fast_share_kernel(const FastParams p) {
       const bool ok = (j >= 0 && j < p.bc.nx - 1);
       const double arj = ok ? p.vel_r[j] : 0.0, alp = ok ? p.vel_l[j + 1] : 0.0;
       const bool pos = (arj + alp) > 0.0;
-      F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? arj * urj : alp * ulp);
+      F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? __dmul_rn(arj, urj) : __dmul_rn(alp, ulp));
     }
   }
 
@@ -496,7 +496,7 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
       F[f] = fma(umax_neg(m2[f], m2[f + 1]), ulp - urj, fma(urj, urj, ulp * ulp));
     } else if (FLUX == PSK_FLUX_UPWIND) {  // 2 F (scalar.py:123-132)
       const double x = (urj + ulp) > 0.0 ? urj : ulp;
-      F[f] = x * x;
+      F[f] = __dmul_rn(x, x);  // never contracted with the flux difference (same bits in every kernel)
     } else {  // Engquist-Osher, omega = 0: 2 F (scalar.py:311-322)
       const double vp = fmax(urj, 0.0), vm = fmin(ulp, 0.0);
       F[f] = fma(vp, vp, vm * vm);

@@ -246,14 +246,14 @@ __device__ __forceinline__ double face_flux_scaled(double urj, double ulp, doubl
     }
     if (FLUX == PSK_FLUX_UPWIND || FLUX == PSK_FLUX_ESWENO) {
       const double v = (urj + ulp) > 0.0 ? urj : ulp;  // scalar.py:129-130
-      return v * v;
+      return __dmul_rn(v, v);  // never contracted with the flux difference (same bits in every kernel)
     }
     const double vp = fmax(urj, 0.0), vm = fmin(ulp, 0.0);  // scalar.py:312-321, omega = 0
     return fma(vp, vp, vm * vm);
   }
   const bool pos = (arj + alp) > 0.0;
   if (EQ == PSK_EQ_ADVECTION) return pos ? urj : ulp;
-  return pos ? arj * urj : alp * ulp;
+  return pos ? __dmul_rn(arj, urj) : __dmul_rn(alp, ulp);
 }
 
 // where a lane's R cells live and how they may be accessed

@@ -8,7 +8,7 @@ Workload (BASELINE.json configs[2], the configuration the metric "WENO5 Burgers
 cell-updates/s" is quoted on): an ensemble of B = 65536 independent inviscid Burgers
 problems x N = 4096 cells, fp64, WENO-JS5 + Rusanov (LLF) + SSPRK33, periodic, random
 smooth initial data, one shared fixed dt at CFL 0.4.  One "step" = one full SSPRK33 step
-(3 fused stage launches) of every cell of the ensemble.  With N GPUs every rank advances
+(one launch of the whole-step kernel, psk_ssprk33_step) of every cell of the ensemble.  With N GPUs every rank advances
 its own B rows (weak scaling, no collective in the data path).
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the

@@ -179,7 +179,7 @@ def test_geometry(emu) -> None:
 
 @pytest.mark.parametrize("R,flux", [(4, "rusanov"), (6, "rusanov"), (8, "rusanov"), (10, "rusanov"), (6, "godunov"),
                                     (6, "eo")])
-@pytest.mark.parametrize("n", [16, 107, 108, 109, 172, 236, 237, 250, 472, 1000])
+@pytest.mark.parametrize("n", [5, 16, 107, 108, 109, 172, 236, 237, 250, 472, 1000])
 def test_fused_step_is_the_three_stages_bit_for_bit(emu, R: int, flux: str, n: int) -> None:
     """psk_ssprk33_step's kernel (temporal blocking, R cells per lane): same bits as three stage
     launches, nothing written outside the interior, fused max |u'|, inactive rows copied through"""
@@ -227,3 +227,8 @@ def test_fused_step_on_slabs_with_nine_ghost_cells(emu, world: int, n: int) -> N
         out.append(res[0, g9 : g9 + nl])
         first += nl
     assert np.array_equal(np.concatenate(out), whole[0, G : G + n])
+
+
+def test_fused_step_at_the_bench_row_length(emu) -> None:
+    """the row length of BASELINE.json configs[2] (24 windows of 172 cells per row), default shape"""
+    test_fused_step_is_the_three_stages_bit_for_bit(emu, 6, "rusanov", 4096)

@@ -86,6 +86,11 @@ inline double __longlong_as_double(long long x) {
   std::memcpy(&r, &x, 8);
   return r;
 }
+inline int __double2hiint(double x) { return static_cast<int>(__double_as_longlong(x) >> 32); }
+inline double __hiloint2double(int hi, int lo) {
+  const unsigned long long b = (static_cast<unsigned long long>(static_cast<unsigned>(hi)) << 32) | static_cast<unsigned>(lo);
+  return __longlong_as_double(static_cast<long long>(b));
+}
 // compiled with -ffp-contract=off: the plain operators round once, like the _rn intrinsics
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dmul_rn(double a, double b) { return a * b; }

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PSK_VERSION 101 /* 0.1.1 */
+#define PSK_VERSION 102 /* 0.1.2: psk_ssprk33_step */
 
 typedef void *psk_stream_t; /* cudaStream_t */
 

@@ -332,6 +332,8 @@ def run_ours(args: argparse.Namespace) -> None:
             tj = json.loads(tf.read_text())
             traffic = tj.get("step_kernel_dram_bytes_per_launch" if whole else "stage_kernel_dram_bytes_per_launch")
         fp64 = measure_fp64_peak(dev)
+        # whole-step kernel: 922 per lane / (172 emitted cells / 32 lanes); stage kernels: (202 + 210 + 210) / (120 / 32)
+        fp64_per_update = 922 * 32 / 172 if whole else 622 * 32 / 120
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -341,9 +343,16 @@ def run_ours(args: argparse.Namespace) -> None:
                 "bound": "fp64", "achieved": per_gpu * ALGO_FLOPS_PER_CELL_UPDATE / 1e12, "peak": fp64["tflops"],
                 "unit": "TFLOP/s", "frac": per_gpu * ALGO_FLOPS_PER_CELL_UPDATE / 1e12 / fp64["tflops"],
                 "peak_source": fp64["how"],
-                "note": "456 algorithmic flop per cell-update (SURVEY.md 8d); the kernels execute ~172 FP64 "
-                        "instructions per cell-update (DFMA counts 2 flop), so the algorithmic rate can exceed the "
-                        "DFMA peak; the FP64 pipe is the binding unit (DESIGN.md 8)",
+                # the same bound in EXECUTED instructions: FP64-pipe warp instructions per cell-update (static
+                # SASS count of the kernel over the cells a warp emits, tools/sass_mix.py) against
+                # 64 lanes/clk/SM x 148 SMs at the SM clock sampled during the timed region
+                "executed_fp64_instr_per_cell_update": fp64_per_update,
+                "pipe_frac": (per_gpu * fp64_per_update / (148 * 64 * clocks["sm_mhz"] * 1e6)
+                              if clocks and clocks.get("sm_mhz") else None),
+                "note": "456 algorithmic flop per cell-update (SURVEY.md 8d) against the measured DFMA peak: the "
+                        "FMA-fused, re-associated kernel executes far fewer operations than the reference's arithmetic "
+                        "counts, so `frac` can exceed 1; `pipe_frac` is the occupancy of the FP64 pipe by the "
+                        "instructions actually executed (ncu: 84 %), the binding unit of this path (DESIGN.md 4.0, 8)",
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -545,12 +545,7 @@ def emit(line: dict) -> None:
 
 
 def main() -> None:
-    # stdout carries the JSON line and nothing else: anything a library prints to fd 1 (NCCL's
-    # version banner at communicator creation) goes to stderr instead
     global _JSON_OUT
-    sys.stdout.flush()
-    _JSON_OUT = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", choices=("ensemble", "slab", "adjoint"), default="ensemble",
                     help="ensemble = the headline config (default); slab / adjoint = BASELINE configs 4 and 5")
@@ -573,6 +568,11 @@ def main() -> None:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", __file__, *sys.argv[1:]]
         raise SystemExit(subprocess.call(cmd))
+    # stdout carries the JSON line and nothing else: anything a library prints to fd 1 (NCCL's
+    # version banner at communicator creation) goes to stderr instead
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     elif args.workload == "slab":

@@ -180,6 +180,14 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
 int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const double *dt,
                      int64_t dt_stride, const uint8_t *active, double *maxabs, psk_stream_t stream);
 
+/* psk_ssprk33_step that also stores the stage values k1, k2 (timestepping.py:314-317) -- what the reverse
+ * sweep recomputes from a checkpointed state before its three psk_ssprk33_stage_adjoint calls -- in one
+ * launch instead of two or three.  uout may be NULL (only k1, k2 wanted: the third stage is skipped).
+ * Burgers + Rusanov + WENO-JS5, FAST math, periodic rows, aligned rows; PSK_E_UNSUPPORTED elsewhere.
+ * Same bits as psk_ssprk33_stage.  No array may alias another. */
+int psk_ssprk33_step_stages(const psk_desc *d, const double *u, double *k1, double *k2, double *uout,
+                            const double *dt, int64_t dt_stride, psk_stream_t stream);
+
 /* Device-side step control of timestepping.step (timestepping.py:128-150) for
  * Burgers-type schemes, per row r:
  *   dt   = theta * (cfl_scale / maxabs[r])             (burgers/schemes.py:42-49, :121-127;

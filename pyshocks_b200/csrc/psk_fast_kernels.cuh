@@ -442,6 +442,7 @@ struct StepParams {
   int chunks_per_row;
   int n, g;
   int bc_none;  // 1: window cells beyond the row ends are the row's stored ghost cells (slab of a larger grid, g >= 9)
+  double *k1_out, *k2_out;  // STAGES kernels only: the stage values are stored too (uout may then be NULL)
 };
 
 template <int R>
@@ -506,7 +507,25 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
   for (int r = 0; r < R; ++r) dF[r] = F[r] - F[r + 1];
 }
 
-template <int R, int FLUX, bool WITH_MAX, int THREADS, int MINB>
+// a[0..R) -> dst on the stored cells of the lane (aligned pairs where the whole quad lies in the row)
+template <int R>
+__device__ __forceinline__ void step_store(double *dst, bool inside, const bool (&st)[R], const double (&a)[R]) {
+  if (inside) {
+#pragma unroll
+    for (int r = 0; r < R; r += 2)
+      if (st[r]) *reinterpret_cast<double2 *>(dst + r) = make_double2(a[r], a[r + 1]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r]) dst[r] = a[r];
+  }
+}
+
+// STAGES: the stage values k1, k2 are stored as well (they are valid on more than the stored range), and
+// the third stage is skipped when no uout is given: the recomputation of the reverse sweep, which needs
+// k1 and k2 of a checkpointed state (and the next state, inside a tape segment), in one launch
+// instead of two or three.
+template <int R, int FLUX, bool WITH_MAX, int THREADS, int MINB, bool STAGES = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 step_warp_fused_kernel(const StepParams p) {
   using Geo = StepGeometry<R>;
@@ -559,9 +578,14 @@ step_warp_fused_kernel(const StepParams p) {
   step_stage_rhs<R, FLUX>(u0, p.eps9, dF);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);  // k1
+  if (STAGES) step_store<R>(p.k1_out + base + c0, inside, st, a);
   step_stage_rhs<R, FLUX>(a, p.eps9, dF);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);  // k2
+  if (STAGES) {
+    step_store<R>(p.k2_out + base + c0, inside, st, a);
+    if (p.uout == nullptr) return;
+  }
   step_stage_rhs<R, FLUX>(a, p.eps9, dF);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);  // u'

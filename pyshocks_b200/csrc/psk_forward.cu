@@ -1026,7 +1026,7 @@ __global__ void step_control_kernel(int batch, double theta, double cfl_scale, d
 // 7000 = off (three stage launches)
 static int g_step_variant = 62;  // R = 6, CTAs of 128 threads, 3 per SM (136 registers): 9.0e10 cell-updates/s on B200
 
-template <int R, int FLUX, int THREADS, int MINB>
+template <int R, int FLUX, int THREADS, int MINB, bool STAGES = false>
 int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cudaStream_t st) {
   StepParams q = q0;
   q.chunks_per_row = (n + StepGeometry<R>::kEmit - 1) / StepGeometry<R>::kEmit;
@@ -1036,7 +1036,9 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
   const unsigned gy = batch < 65535 ? batch : 65535u;
   if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
   const dim3 grid(gx, gy, batch / gy);
-  if (with_max)
+  if (STAGES)
+    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, STAGES><<<grid, wpc * 32, 0, st>>>(q);
+  else if (with_max)
     step_warp_fused_kernel<R, FLUX, true, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
   else
     step_warp_fused_kernel<R, FLUX, false, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
@@ -1045,9 +1047,11 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
 }
 
 int launch_step_fused(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
-                      const uint8_t *active, double *maxabs, cudaStream_t st) {
+                      const uint8_t *active, double *maxabs, cudaStream_t st, double *k1_out = nullptr,
+                      double *k2_out = nullptr) {
   StepParams q{};
   q.u = u; q.uout = uout; q.dt = dt; q.active = active;
+  q.k1_out = k1_out; q.k2_out = k2_out;
   q.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
   q.ld = d->ld;
   q.coef = (1.0 / d->dx) / (d->flux == PSK_FLUX_RUSANOV ? 4.0 : 2.0);  // FluxScale<PSK_EQ_BURGERS, .>
@@ -1064,14 +1068,18 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     for (int b0 = 0; b0 < batch; b0 += 32768) {
       psk_desc d2 = *d;
       d2.batch = 32768;
-      const int rc = launch_step_fused(&d2, u + static_cast<int64_t>(b0) * d->ld, uout + static_cast<int64_t>(b0) * d->ld,
+      const int64_t o = static_cast<int64_t>(b0) * d->ld;
+      const int rc = launch_step_fused(&d2, u + o, uout != nullptr ? uout + o : nullptr,
                                        dt + static_cast<int64_t>(b0) * dt_stride, dt_stride,
                                        active != nullptr ? active + b0 : nullptr,
-                                       maxabs != nullptr ? maxabs + b0 : nullptr, st);
+                                       maxabs != nullptr ? maxabs + b0 : nullptr, st,
+                                       k1_out != nullptr ? k1_out + o : nullptr, k2_out != nullptr ? k2_out + o : nullptr);
       if (rc != PSK_OK) return rc;
     }
     return PSK_OK;
   }
+  if (k1_out != nullptr)  // stage values wanted (reverse sweep): Rusanov, default shape
+    return launch_step_shape<6, PSK_FLUX_RUSANOV, 128, 3, true>(q, d->n, batch, false, st);
   // the other Burgers fluxes: default shape only
   if (d->flux == PSK_FLUX_UPWIND) return launch_step_shape<6, PSK_FLUX_UPWIND, 128, 3>(q, d->n, batch, mx, st);
   if (d->flux == PSK_FLUX_ENGQUIST_OSHER)
@@ -1256,6 +1264,23 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
       !((d->bc == PSK_BC_PERIODIC && d->g >= 3) || (d->bc == PSK_BC_NONE && d->g >= 9)))
     return PSK_E_UNSUPPORTED;
   return launch_step_fused(d, u, uout, dt, dt_stride, active, maxabs, static_cast<cudaStream_t>(stream));
+}
+
+int psk_ssprk33_step_stages(const psk_desc *d, const double *u, double *k1, double *k2, double *uout,
+                            const double *dt, int64_t dt_stride, psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (u == nullptr || k1 == nullptr || k2 == nullptr || dt == nullptr) return PSK_E_INVALID;
+  if (uout == u || k1 == u || k2 == u || k1 == k2 || (uout != nullptr && (uout == k1 || uout == k2))) return PSK_E_INVALID;
+  const bool aligned = (reinterpret_cast<uintptr_t>(u + d->g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(k1 + d->g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(k2 + d->g) % 16 == 0) &&
+                       (uout == nullptr || reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0) && (d->ld % 2 == 0);
+  if (d->equation != PSK_EQ_BURGERS || d->flux != PSK_FLUX_RUSANOV || d->rec != PSK_REC_WENOJS53 ||
+      d->math != PSK_MATH_FAST || d->nu != nullptr || !aligned || g_step_variant == 0 ||
+      !(d->bc == PSK_BC_PERIODIC && d->g >= 3))
+    return PSK_E_UNSUPPORTED;
+  return launch_step_fused(d, u, uout, dt, dt_stride, nullptr, nullptr, static_cast<cudaStream_t>(stream), k1, k2);
 }
 
 int psk_ssprk33_stage_p2p(const psk_desc *d, int stage, const double *u0, const double *uin,

@@ -306,8 +306,12 @@ class AdjointEnsemble:
     is imposed on it: ``backward`` returns the exact gradient of the discrete forward map."""
 
     def __init__(self, solver: EnsembleSolver, *, nsteps: int, dt: float | torch.Tensor,
-                 segment: int | None = None, memory_fraction: float = 0.7) -> None:
+                 segment: int | None = None, memory_fraction: float = 0.7, fused_recompute: bool = False) -> None:
         self.s = solver
+        # fused_recompute: the reverse sweep recomputes (k1, k2[, next state]) of a state with ONE launch
+        # (psk_ssprk33_step_stages) instead of two or three stage launches.  Opt-in: validated on the CPU
+        # warp emulation (bit-identical stage values), not yet timed on a GPU.
+        self.fused_recompute = bool(fused_recompute)
         self.nsteps = int(nsteps)
         dev = solver.hp.device
         if segment is None:
@@ -343,6 +347,10 @@ class AdjointEnsemble:
         if k1 is None and k2 is None and self._fused is not False:
             self._fused = hp.step_fused(src, dst, self.dt)
             if self._fused:
+                self.launches += 1
+                return
+        if k1 is not None and k2 is not None and self.fused_recompute and self._fused is not False:
+            if hp.step_fused_stages(src, k1, k2, dst, self.dt):
                 self.launches += 1
                 return
         k1 = s.k1 if k1 is None else k1
@@ -391,9 +399,12 @@ class AdjointEnsemble:
                 u = ring0 if j == 0 else self.ring[j]
                 if j == last:
                     k1, k2 = s.k1, s.k2
-                    hp.stage(1, u, u, k1, self.dt)
-                    hp.stage(2, u, k1, k2, self.dt)
-                    self.launches += 2
+                    if self.fused_recompute and hp.step_fused_stages(u, k1, k2, None, self.dt):
+                        self.launches += 1
+                    else:
+                        hp.stage(1, u, u, k1, self.dt)
+                        hp.stage(2, u, k1, k2, self.dt)
+                        self.launches += 2
                 else:
                     k1, k2 = self.ring_k1[j], self.ring_k2[j]
                 hp.stage_adjoint(k2, p, self.dt, 2.0 / 3.0, self.lam2)

@@ -382,6 +382,25 @@ class HotPath:
         L.check("psk_ssprk33_step", rc)
         return True
 
+    def step_fused_stages(self, u: torch.Tensor, k1: torch.Tensor, k2: torch.Tensor, uout: torch.Tensor | None,
+                          dt: torch.Tensor) -> bool:
+        """The stage values ``k1, k2`` of the SSPRK33 step from ``u`` (timestepping.py:314-317) and, if
+        ``uout`` is given, the new state, in ONE launch (``psk_ssprk33_step_stages``): the recomputation
+        of the reverse sweep.  ``False`` -- nothing launched -- outside its configuration."""
+        batch, ld = self._state(u)
+        for a in (k1, k2, uout):
+            if a is not None and L.rows_of(a)[2] != ld:
+                raise ValueError("all stage arrays must share one row stride")
+        d = self.desc(batch, ld)
+        rc = L.lib().psk_ssprk33_step_stages(
+            ct.byref(d), L.ptr(u), L.ptr(k1), L.ptr(k2), L.ptr(uout), L.ptr(dt), 0 if dt.numel() == 1 else 1,
+            L.stream_ptr(),
+        )
+        if rc == L.E_UNSUPPORTED:
+            return False
+        L.check("psk_ssprk33_step_stages", rc)
+        return True
+
     def ssprk33_step(
         self,
         u: torch.Tensor,

@@ -175,6 +175,26 @@ int emu_fused_step(int R, int flux, int bc_none, int with_max, int n, int g, int
   return 0;
 }
 
+// The STAGES form of the whole-step kernel (psk_ssprk33_step_stages): k1, k2 stored, uout optional.
+int emu_fused_step_stages(int n, int g, int batch, long long ld, double dx, double eps, const double *u, double *k1,
+                          double *k2, double *uout, const double *dt, int dt_stride) {
+  psk::StepParams q{};
+  q.u = u; q.uout = uout; q.dt = dt; q.k1_out = k1; q.k2_out = k2;
+  q.ld = ld;
+  q.coef = (1.0 / dx) / 4.0;
+  q.eps9 = eps * (1.0 / 9.0);
+  q.dt_stride = dt_stride;
+  q.n = n;
+  q.g = g;
+  q.chunks_per_row = (n + psk::StepGeometry<6>::kEmit - 1) / psk::StepGeometry<6>::kEmit;
+  int wpc = 4;
+  if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
+  const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
+  run_grid(gx, static_cast<unsigned>(batch), wpc,
+           [&]() { psk::step_warp_fused_kernel<6, PSK_FLUX_RUSANOV, false, 128, 3, true>(q); });
+  return 0;
+}
+
 int emu_chunks_per_row(int n) { return psk::fast_geometry(n, 8).chunks_per_row; }
 
 }  // extern "C"

@@ -41,6 +41,8 @@ def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
     lib.emu_fused_step.argtypes = [ct.c_int] * 7 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
                                                    ct.POINTER(ct.c_ubyte), up]
     lib.emu_fused_step.restype = ct.c_int
+    lib.emu_fused_step_stages.argtypes = [ct.c_int] * 3 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, dp, dp, ct.c_int]
+    lib.emu_fused_step_stages.restype = ct.c_int
     lib.emu_chunks_per_row.argtypes = [ct.c_int]
     lib.emu_chunks_per_row.restype = ct.c_int
     return lib
@@ -232,3 +234,26 @@ def test_fused_step_on_slabs_with_nine_ghost_cells(emu, world: int, n: int) -> N
 def test_fused_step_at_the_bench_row_length(emu) -> None:
     """the row length of BASELINE.json configs[2] (24 windows of 172 cells per row), default shape"""
     test_fused_step_is_the_three_stages_bit_for_bit(emu, 6, "rusanov", 4096)
+
+
+@pytest.mark.parametrize("n", [16, 172, 173, 500, 1000])
+@pytest.mark.parametrize("with_uout", [True, False])
+def test_fused_step_with_stored_stages(emu, n: int, with_uout: bool) -> None:
+    """psk_ssprk33_step_stages: k1, k2 (and u') of one launch are the bits of the stage launches; without
+    uout the third stage is skipped and nothing else is written"""
+    pb = Problem("burgers", "rusanov", "periodic", n=n, batch=2, seed=7 * n)
+    i = pb.interior
+    k1s, _ = pb.stage(emu, 2, 0, 1, pb.u, pb.u)
+    k2s, _ = pb.stage(emu, 2, 0, 2, pb.fill(k1s), pb.u)
+    outs, _ = pb.stage(emu, 2, 0, 3, pb.fill(k2s), pb.u)
+    k1, k2, out = (np.full_like(pb.u, np.nan) for _ in range(3))
+    rc = emu.emu_fused_step_stages(n, G, pb.batch, pb.nx, pb.dx, EPS, _p(pb.fill(pb.u)), _p(k1), _p(k2),
+                                   _p(out) if with_uout else None, _p(pb.dt), 1)
+    assert rc == 0
+    assert np.array_equal(k1[:, i], k1s[:, i]) and np.array_equal(k2[:, i], k2s[:, i])
+    for a in (k1, k2, out):
+        assert np.isnan(a[:, :G]).all() and np.isnan(a[:, G + n :]).all()
+    if with_uout:
+        assert np.array_equal(out[:, i], outs[:, i])
+    else:
+        assert np.isnan(out).all()

@@ -5,6 +5,8 @@ tape (segment thinning + recompute) against the full tape."""
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -93,3 +95,23 @@ def test_two_level_tape_equals_full_tape(segment: int) -> None:
     adj = AdjointEnsemble(solver2, nsteps=nsteps, dt=dt, segment=segment)
     _, g2 = adj.gradient_half_l2(torch.from_numpy(u0).cuda())
     assert torch.equal(g2, g_ref)  # recomputed states are bit-identical to the stored ones
+
+
+@pytest.mark.skipif(os.environ.get("PSK_TEST_UNVERIFIED") != "1",
+                    reason="fused_recompute (psk_ssprk33_step_stages) is validated on the CPU warp emulation only; "
+                           "set PSK_TEST_UNVERIFIED=1 for its first GPU run")
+@pytest.mark.parametrize("segment", [1, 3, 25])
+def test_fused_recompute_gives_the_same_gradient(segment: int) -> None:
+    """reverse sweep with (k1, k2[, next state]) recomputed in one launch: same bits as with stage launches"""
+    from pyshocks_b200.ensemble import AdjointEnsemble
+
+    batch, n, nsteps = 5, 128, 25
+    solver, grid, u0, dt = _setup(batch, n)
+    ref = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=segment)
+    _, g_ref = ref.gradient_half_l2(torch.from_numpy(u0).cuda())
+    g_ref = g_ref.clone()
+    solver2, *_ = _setup(batch, n)
+    adj = AdjointEnsemble(solver2, nsteps=nsteps, dt=dt, segment=segment, fused_recompute=True)
+    _, g2 = adj.gradient_half_l2(torch.from_numpy(u0).cuda())
+    assert adj.launches < ref.launches
+    assert torch.equal(g2, g_ref)

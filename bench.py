@@ -4,16 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[2], the configuration the metric "WENO5 Burgers
-cell-updates/s" is quoted on): an ensemble of B = 65536 independent inviscid Burgers
-problems x N = 4096 cells, fp64, WENO-JS5 + Rusanov (LLF) + SSPRK33, periodic, random
-smooth initial data, one shared fixed dt at CFL 0.4.  One "step" = one full SSPRK33 step
-(one launch of the whole-step kernel, psk_ssprk33_step) of every cell of the ensemble.  With N GPUs every rank advances
-its own B rows (weak scaling, no collective in the data path).
+Headline workload (BASELINE.json configs[2], the configuration the metric "WENO5 Burgers
+cell-updates/s" is quoted on): an ensemble of B = 65536 independent inviscid Burgers problems x
+N = 4096 cells, fp64, WENO-JS5 + Rusanov (LLF) + SSPRK33, periodic, random smooth initial data,
+one shared fixed dt at CFL 0.4.  One "step" = one full SSPRK33 step of every cell of the ensemble
+(one launch of the whole-step kernel psk_ssprk33_step per rank).  With N GPUs the B rows are
+block-partitioned, B / N per rank (STRONG scaling, no collective in the data path); the weak
+figure (B rows per GPU) is reported beside it as `weak`.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
-reference path (oracle/psk_oracle.c, all host threads) on a bounded sample of the same
-workload; the reference itself is Python-on-JAX and JAX is not installable here.
+The same JSON line carries the other halves of the metric as sub-records, each measured in the
+same process right after the headline:
+
+  `slab`     BASELINE configs[3]: ONE periodic Burgers grid of 2^30 cells, slab-decomposed over
+             the N ranks, ghost cells exchanged through NVLink peer memory;
+  `adjoint`  BASELINE configs[4]: B = 4096 x N = 8192 ensemble (rows sharded over the ranks),
+             1000 fixed-dt steps forward with a device tape + the reverse sweep: gradients/s;
+  `parity`   64 sampled rows of the timed ensemble state against the C restatement of the
+             reference (oracle/psk_oracle.c) on the identical initial rows.
+
+`--impl reference` times the CPU restatement of the reference path (oracle/psk_oracle.c, all host
+threads) on a bounded sample of the same workload; the reference itself is Python-on-JAX and JAX is
+not installable here.  Prints ONE JSON line (rank 0).
 """
 
 from __future__ import annotations
@@ -41,6 +52,12 @@ DOMAIN = (-1.5, 1.5)
 EPS = 1.0e-12
 CFL = 0.4
 ALGO_BYTES_PER_CELL_UPDATE = 64.0  # 16 + 24 + 24 B over the three stages
+ALGO_FLOPS_PER_CELL_UPDATE = 456.0  # 152 per cell-stage, divisions counted as 1
+ADJ_ALGO_BYTES = 144.0  # reverse sweep per cell-step, per-stage streaming design
+CPU_SAMPLE_ROWS = 16384  # rows of the ensemble the CPU arm advances per step (0.55 GB: not cache resident)
+PARITY_ROWS = 64
+PARITY_TOL = 1.0e-12
+SMS, FP64_LANES_PER_SM = 148, 64
 
 
 def measured_peaks() -> tuple[float, str]:
@@ -68,42 +85,54 @@ def host_initial_condition(coef: np.ndarray, n: int, g: int) -> np.ndarray:
     return u
 
 
-# {{{ reference arm / cpu baseline: the C restatement on the host cores
+def device_initial_condition(coef, n: int, g: int, nx: int, dev):
+    import torch
+
+    xhat = ((torch.arange(nx, device=dev, dtype=torch.float64) - g + 0.5) / n)[None, :]
+    u0 = coef[:, :1].repeat(1, nx)
+    for k in range(4):
+        u0 += coef[:, 1 + k : 2 + k] * torch.sin(2.0 * np.pi * (k + 1) * xhat + coef[:, 5 + k : 6 + k])
+    return u0
 
 
-def cpu_port_throughput(target_seconds: float, steps: int | None = None) -> dict:
+def shard(total: int, rank: int, world: int) -> tuple[int, int]:
+    base, extra = divmod(total, world)
+    return rank * base + min(rank, extra), base + (1 if rank < extra else 0)
+
+
+# {{{ CPU arm: ONE protocol for `--impl reference` and for `cpu_baseline`
+
+
+def host_threads() -> int:
+    return len(os.sched_getaffinity(0))
+
+
+def cpu_port_steps(steps: int, warmup: int, threads: int | None = None) -> dict:
+    """`warmup` + `steps` SSPRK33 steps of a bounded sample (CPU_SAMPLE_ROWS rows of the ensemble, all
+    N_CELLS cells) on the C restatement, OpenMP over rows with an EXPLICIT thread count
+    (torch.distributed.run exports OMP_NUM_THREADS=1 to its workers)."""
+    from oracle import c_oracle
     from oracle.c_oracle import COracle
 
-    cores = len(os.sched_getaffinity(0))
+    want = host_threads() if threads is None else threads
+    used = c_oracle.set_threads(want)
     h = (DOMAIN[1] - DOMAIN[0]) / N_CELLS
-    # calibrate on a small slice, then size the sample
-    rows = max(4 * cores, 32)
-    coef = ensemble_coefficients(rows, 20261017)
-    u0 = host_initial_condition(coef, N_CELLS, GHOSTS)
-    dt = CFL * h / np.abs(u0).max()
+    rows = CPU_SAMPLE_ROWS
+    u = host_initial_condition(ensemble_coefficients(rows, 20261017), N_CELLS, GHOSTS)
+    dt = CFL * h / np.abs(u).max()
     co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS, g=GHOSTS,
                  batch=rows, dx=h, eps=EPS)
-    co.solve_fixed_dt(u0, dt, 1)  # thread pool start-up
+    for _ in range(warmup):
+        u = co.solve_fixed_dt(u, dt, 1)
     t0 = time.perf_counter()
-    co.solve_fixed_dt(u0, dt, 2)
-    rate = 2 * rows * N_CELLS / (time.perf_counter() - t0)  # cell-updates/s with all threads
-    nsteps = steps if steps is not None else 4
-    rows_s = int(min(BATCH, target_seconds * rate / (N_CELLS * nsteps)))
-    rows_s = max(cores, (rows_s // cores) * cores)
-    coef = ensemble_coefficients(rows_s, 20261017)
-    u0 = host_initial_condition(coef, N_CELLS, GHOSTS)
-    co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS, g=GHOSTS,
-                 batch=rows_s, dx=h, eps=EPS)
-    t0 = time.perf_counter()
-    co.solve_fixed_dt(u0, dt, nsteps)
+    for _ in range(steps):
+        u = co.solve_fixed_dt(u, dt, 1)
     wall = time.perf_counter() - t0
     return {
-        "value": rows_s * N_CELLS * nsteps / wall,
-        "unit": UNIT,
-        "cores": cores,
-        "kind": "port",
-        "sample": f"{rows_s} rows x {N_CELLS} cells x {nsteps} SSPRK33 steps of the same ensemble "
-                  f"(C restatement oracle/psk_oracle.c, OpenMP over rows, {wall:.1f} s)",
+        "value": rows * N_CELLS * steps / wall, "unit": UNIT, "cores": used, "kind": "port",
+        "sample": f"{rows} of {BATCH} rows x {N_CELLS} cells, {steps} SSPRK33 steps after {warmup} warm-up, one step per "
+                  f"call (C restatement oracle/psk_oracle.c, OpenMP over rows, {used} threads set explicitly, {wall:.1f} s)",
+        "seconds": wall,
     }
 
 
@@ -111,34 +140,17 @@ def run_reference(args: argparse.Namespace) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.c_oracle import COracle
-
-    cores = len(os.sched_getaffinity(0))
-    h = (DOMAIN[1] - DOMAIN[0]) / N_CELLS
-    # a "step" of the reference arm = one SSPRK33 step over a bounded sample of rows
-    rows = max(cores * 8, 64)
-    coef = ensemble_coefficients(rows, 20261017)
-    u0 = host_initial_condition(coef, N_CELLS, GHOSTS)
-    dt = CFL * h / np.abs(u0).max()
-    co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS, g=GHOSTS,
-                 batch=rows, dx=h, eps=EPS)
-    u = u0
-    for _ in range(args.warmup):
-        u = co.solve_fixed_dt(u, dt, 1)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        u = co.solve_fixed_dt(u, dt, 1)
-    wall = time.perf_counter() - t0
-    value = rows * N_CELLS * args.steps / wall
-    sample = f"{rows} of {BATCH} rows x {N_CELLS} cells per step (bounded sample of the same ensemble)"
+    res = cpu_port_steps(args.steps, args.warmup)
+    value = res["value"]
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus) | {"reference_arm": "CPU restatement of the reference path "
-                                               "(oracle/psk_oracle.c); JAX is not installable here"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "reference_arm": "CPU restatement of the reference path (oracle/psk_oracle.c); the reference is Python on "
+                         "JAX and JAX is not installable here",
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -149,7 +161,7 @@ def run_reference(args: argparse.Namespace) -> None:
 
 
 def measure_fp64_peak(dev) -> dict:
-    """DFMA throughput of this GPU (MEASURED_PEAKS.json has no fp64 figure): psk_dfma_probe, best of 5."""
+    """DFMA throughput of this GPU (MEASURED_PEAKS.json has no fp64 figure): psk_dfma_probe, best of 6."""
     import torch
 
     from pyshocks_b200 import _lib as L
@@ -164,20 +176,35 @@ def measure_fp64_peak(dev) -> dict:
         e1.record()
         torch.cuda.synchronize()
         best = max(best, 2.0 * 64 * iters * ctas * 256 / (e0.elapsed_time(e1) * 1e-3))
-    return {"tflops": best / 1e12, "how": "psk_dfma_probe: 16 independent DFMA chains per thread, 2368 CTAs x 256 threads, best of 6"}
+    return {"tflops": best / 1e12,
+            "how": "psk_dfma_probe in this run: 16 independent DFMA chains per thread, 2368 CTAs x 256 threads, best of 6"}
 
 
-# algorithmic flops per cell-update (152 per cell-stage, divisions counted as 1)
-ALGO_FLOPS_PER_CELL_UPDATE = 456.0
+def sass_counts() -> dict:
+    """Static FP64 instruction counts of the hot kernels (tools/sass_counts.py, regenerated by every
+    build); `fresh` says whether they were taken from the library this run loaded."""
+    f = ROOT / "profiles" / "sass_counts.json"
+    if not f.exists():
+        return {"kernels": {}, "fresh": False}
+    d = json.loads(f.read_text())
+    try:
+        import hashlib
+
+        lib = ROOT / "pyshocks_b200" / "csrc" / "libpsk.so"
+        d["fresh"] = hashlib.sha1(lib.read_bytes()).hexdigest() == d.get("library_sha1")
+    except OSError:
+        d["fresh"] = False
+    return d
 
 
 def workload_config(n_gpus: int) -> dict:
+    """Identical for both arms (the driver compares it)."""
     return {
-        "workload": f"batched Burgers ensemble B={BATCH} x N={N_CELLS} cells per GPU, fp64, WENO-JS5 + Rusanov(LLF) "
+        "workload": f"batched Burgers ensemble B={BATCH} x N={N_CELLS} cells, fp64, WENO-JS5 + Rusanov(LLF) "
                     f"+ SSPRK33, periodic, fixed dt at CFL {CFL} (BASELINE.json configs[2])",
-        "batch_per_gpu": BATCH, "cells": N_CELLS, "ghosts": GHOSTS,
-        "sharding": f"ensemble rows block-partitioned, {n_gpus} rank(s), no data-path collective",
-        "l2": "inputs (2.15 GB per state array) are larger than the 126 MB L2; no flush needed",
+        "batch": BATCH, "cells": N_CELLS, "ghosts": GHOSTS,
+        "sharding": f"ensemble rows block-partitioned over {n_gpus} rank(s), B / N rows each, no data-path collective",
+        "l2": "state arrays (2.15 GB / N per rank) are larger than the 126 MB L2 at every N <= 8; no flush needed",
     }
 
 
@@ -199,6 +226,7 @@ class ClockSampler:
         self.max_mhz = None
         self.power: list[float] = []
         self._stop = threading.Event()
+        self._pause = threading.Event()
         self._nvml = None
         try:
             import pynvml
@@ -217,13 +245,17 @@ class ClockSampler:
         if nv is None:
             return
         while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
-            except Exception:  # noqa: BLE001
-                pass
+            if not self._pause.is_set():
+                try:
+                    self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+                except Exception:  # noqa: BLE001
+                    pass
             time.sleep(0.002)
+
+    def pause(self, on: bool) -> None:
+        (self._pause.set if on else self._pause.clear)()
 
     def stop(self) -> dict:
         self._stop.set()
@@ -244,259 +276,430 @@ class ClockSampler:
         }
 
 
-def run_ours(args: argparse.Namespace) -> None:
-    import torch
-    import torch.distributed as dist
+class Ctx:
+    """One rank of the bench: device, process group, barrier, max-over-ranks reduction."""
 
+    def __init__(self) -> None:
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self) -> None:
+        if self.world > 1:
+            self.dist.barrier(device_ids=[self.local])
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, values: list[float]) -> list[float]:
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def gather(self, values: list[float]) -> list[list[float]]:
+        t = self.torch.tensor(values, dtype=self.torch.float64, device=self.dev)
+        if self.world == 1:
+            return [[float(x) for x in t]]
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [[float(x) for x in o] for o in out]
+
+    def close(self) -> None:
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def timed_steps(ctx: Ctx, fn, steps: int) -> float:
+    """max over ranks of the CUDA-event time (ms) of `fn(steps)`, bracketed by barrier + synchronize"""
+    torch = ctx.torch
+    ctx.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fn(steps)
+    e1.record()
+    ctx.barrier()
+    return ctx.max_over_ranks([e0.elapsed_time(e1)])[0]
+
+
+# {{{ headline: the ensemble (configs[2])
+
+
+def measure_ensemble(ctx: Ctx, args: argparse.Namespace) -> dict:
+    torch = ctx.torch
     from pyshocks_b200.ensemble import EnsembleSolver
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier() -> None:
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
-    batch = args.batch
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    first, rows = shard(args.batch, rank, world)
     h = (DOMAIN[1] - DOMAIN[0]) / N_CELLS
     solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS,
-                            g=GHOSTS, dx=h, eps=EPS, batch=batch, math="fast", device=dev)
+                            g=GHOSTS, dx=h, eps=EPS, batch=rows, math="fast", device=dev)
     nx = solver.nx
-
-    # synthetic initial data of the named shape, evaluated on the device from host-drawn coefficients
-    coef = torch.from_numpy(ensemble_coefficients(batch, 20261017 + rank)).to(dev)
-    xhat = ((torch.arange(nx, device=dev, dtype=torch.float64) - GHOSTS + 0.5) / N_CELLS)[None, :]
-    u0 = coef[:, :1].repeat(1, nx)
-    for k in range(4):
-        u0 += coef[:, 1 + k : 2 + k] * torch.sin(2.0 * np.pi * (k + 1) * xhat + coef[:, 5 + k : 6 + k])
+    # synthetic initial data of the named shape: coefficients drawn on the host for the WHOLE ensemble
+    # (the same rows whatever N), this rank's block evaluated on the device
+    coef = torch.from_numpy(ensemble_coefficients(args.batch, 20261017)[first : first + rows]).to(dev)
+    u0 = device_initial_condition(coef, N_CELLS, GHOSTS, nx, dev)
     umax = u0.abs().max()
     if world > 1:
-        dist.all_reduce(umax, op=dist.ReduceOp.MAX)
-    dt = torch.full((1,), CFL * h / float(umax), dtype=torch.float64, device=dev)
+        ctx.dist.all_reduce(umax, op=ctx.dist.ReduceOp.MAX)
+    dt_host = CFL * h / float(umax)
+    dt = torch.full((1,), dt_host, dtype=torch.float64, device=dev)
     solver.load(u0)
+    # the rows the parity check follows: their INITIAL state goes to the host now
+    prow = torch.linspace(0, rows - 1, min(PARITY_ROWS, rows), device=dev).round().long()
+    u0_sample = u0[prow].cpu().numpy()
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps
     solver.solve_fixed_dt(None, dt, args.warmup)
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(ctx.local) if rank == 0 else None
     launches0 = solver.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    solver.solve_fixed_dt(None, dt, args.steps)
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
+    ms_total = timed_steps(ctx, lambda k: solver.solve_fixed_dt(None, dt, k), args.steps)
     launches = solver.launches - launches0
-    clocks = sampler.stop() if sampler is not None else None
+    if sampler is not None:
+        sampler.pause(True)
     finite = bool(torch.isfinite(solver.u).all())
 
-    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
-    host_in = torch.empty((batch, nx), dtype=torch.float64, pin_memory=True)
-    host_out = torch.empty((batch, nx), dtype=torch.float64, pin_memory=True)
+    # ---- parity: the sampled rows after W + K steps against the C restatement on the identical initial rows
+    from oracle import c_oracle
+    from oracle.c_oracle import COracle
+
+    c_oracle.set_threads(max(1, host_threads() // world))
+    co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS, g=GHOSTS,
+                 batch=u0_sample.shape[0], dx=h, eps=EPS)
+    t0 = time.perf_counter()
+    ref = co.solve_fixed_dt(u0_sample, dt_host, args.warmup + args.steps)
+    parity_s = time.perf_counter() - t0
+    got = solver.u[prow].cpu().numpy()
+    i = slice(GHOSTS, GHOSTS + N_CELLS)
+    rel = float(np.abs(got[:, i] - ref[:, i]).max() / np.abs(ref[:, i]).max())
+    parity_rel = ctx.max_over_ranks([rel if np.isfinite(rel) else 1e300])[0]
+
+    # ---- host <-> device copy bandwidth with every rank copying at once (what bounds e2e at N > 1)
+    host_in = torch.empty((rows, nx), dtype=torch.float64, pin_memory=True)
+    host_out = torch.empty((rows, nx), dtype=torch.float64, pin_memory=True)
     host_in.copy_(u0)
     del u0
-    barrier()
+    bytes_state = rows * nx * 8
+    copy_ms = []
+    for src, dst in ((host_in, solver.k2), (solver.k2, host_out)):
+        dst.copy_(src, non_blocking=True)  # warm-up
+        ctx.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dst.copy_(src, non_blocking=True)
+        e1.record()
+        ctx.barrier()
+        copy_ms.append(e0.elapsed_time(e1))
+    per_rank_gbs = ctx.gather([bytes_state / (copy_ms[0] * 1e6), bytes_state / (copy_ms[1] * 1e6)])
+    copy_bound_ms = ctx.max_over_ranks([max(copy_ms)])[0]
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
     solver.solve_fixed_dt_host(host_in, host_out, dt, 1)  # warm-up of the copy streams
-    barrier()
+    ctx.barrier()
+    if sampler is not None:
+        sampler.pause(False)
     t0 = time.perf_counter()
     solver.solve_fixed_dt_host(host_in, host_out, dt, args.steps)
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_s = float(e2e_s)
-    bytes_state = batch * nx * 8
+    ctx.barrier()
+    e2e_s = ctx.max_over_ranks([time.perf_counter() - t0])[0]
+    clocks = sampler.stop() if sampler is not None else None
+    groups = max(1, min(64, rows // 1024))
+    del host_in, host_out, solver
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return {}
 
-    if rank == 0:
-        cells_per_step = batch * N_CELLS * world
-        value = cells_per_step * args.steps / (ms_total * 1e-3)
-        peak, peak_src = measured_peaks()
-        per_gpu = value / world
-        achieved = per_gpu * ALGO_BYTES_PER_CELL_UPDATE / 1e9
-        per_step = launches / max(args.steps, 1)  # 1: whole-step kernel, 3: one launch per stage
-        whole = per_step < 2
-        traffic = None
-        tf = ROOT / "profiles" / "traffic.json"
-        if tf.exists():
-            tj = json.loads(tf.read_text())
-            traffic = tj.get("step_kernel_dram_bytes_per_launch" if whole else "stage_kernel_dram_bytes_per_launch")
-        fp64 = measure_fp64_peak(dev)
-        # whole-step kernel: 922 per lane / (172 emitted cells / 32 lanes); stage kernels: (202 + 210 + 210) / (120 / 32)
-        fp64_per_update = 922 * 32 / 172 if whole else 622 * 32 / 120
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world) | {"batch_per_gpu": batch, "finite": finite},
-            "roofline_fp64": {
-                "bound": "fp64", "achieved": per_gpu * ALGO_FLOPS_PER_CELL_UPDATE / 1e12, "peak": fp64["tflops"],
-                "unit": "TFLOP/s", "frac": per_gpu * ALGO_FLOPS_PER_CELL_UPDATE / 1e12 / fp64["tflops"],
-                "peak_source": fp64["how"],
-                # the same bound in EXECUTED instructions: FP64-pipe warp instructions per cell-update (static
-                # SASS count of the kernel over the cells a warp emits, tools/sass_mix.py) against
-                # 64 lanes/clk/SM x 148 SMs at the SM clock sampled during the timed region
-                "executed_fp64_instr_per_cell_update": fp64_per_update,
-                "pipe_frac": (per_gpu * fp64_per_update / (148 * 64 * clocks["sm_mhz"] * 1e6)
-                              if clocks and clocks.get("sm_mhz") else None),
-                "note": "456 algorithmic flop per cell-update (SURVEY.md 8d) against the measured DFMA peak: the "
-                        "FMA-fused, re-associated kernel executes far fewer operations than the reference's arithmetic "
-                        "counts, so `frac` can exceed 1; `pipe_frac` is the occupancy of the FP64 pipe by the "
-                        "instructions actually executed (ncu: 84 %), the binding unit of this path (DESIGN.md 4.0, 8)",
-            },
-            "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": ("psk::step_warp_fused_kernel (1 launch per step: the three stages in registers; 64 "
-                           "algorithmic bytes per cell-update, 16 B of them actually moved)") if whole else
-                          "psk::stage_warp_fast_share_kernel (3 launches per step; 64 algorithmic bytes per cell-update)",
-                "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_UPDATE / per_step * batch * N_CELLS,
-                "avg_launch_ms": ms_total / max(launches, 1),
-            },
-            "e2e": {
-                "value": cells_per_step * args.steps / e2e_s, "unit": UNIT,
-                "h2d_bytes_per_step": bytes_state / args.steps, "d2h_bytes_per_step": bytes_state / args.steps,
-                "call": f"EnsembleSolver.solve_fixed_dt_host(pinned host in, pinned host out, dt, K): "
-                        f"{max(1, min(64, batch // 1024))} row blocks, upload / K steps / download pipelined over 4 streams",
-                "seconds": e2e_s,
-            },
-            "gpu_launches": launches,
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_port_throughput(target_seconds=15.0)
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    cells_per_step = args.batch * N_CELLS
+    value = cells_per_step * args.steps / (ms_total * 1e-3)
+    peak, peak_src = measured_peaks()
+    per_gpu = value / world
+    per_step = launches / max(args.steps, 1)  # 1: whole-step kernel, 3: one launch per stage
+    whole = per_step < 2
+    fp64 = measure_fp64_peak(dev)
+    sc = sass_counts()
+    k = sc["kernels"]
+    if whole and k.get("step_fused"):
+        per_update = k["step_fused"][0]["fp64"] * 32 / 172  # per lane / (172 emitted cells / 32 lanes)
+        kernel = k["step_fused"][0]["name"]
+    elif k.get("stage1"):
+        per_update = sum(k[s][0]["fp64"] for s in ("stage1", "stage2", "stage3")) * 32 / 120
+        kernel = "psk::stage_warp_fast_share_kernel x 3"
+    else:  # no count file: the figures of round 1
+        per_update, kernel = (922 * 32 / 172 if whole else 654 * 32 / 120), "(static counts missing)"
+    # FP64 pipe: every FP64-pipe warp instruction occupies one issue slot of the 64 lanes/clk/SM pipe, whatever it
+    # is (DFMA, DMUL, DADD); counted as one DFMA slot = 2 flop, against the DFMA rate measured in this run
+    slot_tflops = per_gpu * per_update * 2.0 / 1e12
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        tj = json.loads(tf.read_text())
+        per_cell = tj.get("step_kernel", {}).get("dram_bytes_per_cell_update_measured") if whole else None
+        if per_cell is not None:
+            traffic = per_cell * rows * N_CELLS  # per launch on this rank
+    achieved_hbm = per_gpu * ALGO_BYTES_PER_CELL_UPDATE / 1e9
+    agg = [sum(r[0] for r in per_rank_gbs), sum(r[1] for r in per_rank_gbs)]
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world),
+        "rows_per_gpu": rows, "finite": finite,
+        "parity": {
+            "max_rel": parity_rel, "tol": PARITY_TOL, "ok": bool(parity_rel <= PARITY_TOL),
+            "what": f"{min(PARITY_ROWS, rows)} evenly spaced rows per rank of the timed device state after "
+                    f"{args.warmup + args.steps} steps (FAST whole-step kernel) against oracle/psk_oracle.c advanced from "
+                    f"the identical initial rows; max |diff| / max |ref| over the interior, max over ranks",
+            "oracle_seconds": parity_s,
+        },
+        # the BINDING roofline of this path is the FP64 pipe (ncu: pipe 84 % busy, DRAM 16 %), so `roofline` is
+        # reported against it; the 64-B HBM figure of SURVEY.md 8(d) follows as `roofline_hbm`
+        "roofline": {
+            "bound": "fp64", "achieved": slot_tflops, "peak": fp64["tflops"], "unit": "TFLOP/s",
+            "frac": slot_tflops / fp64["tflops"], "traffic": traffic,
+            "kernel": kernel,
+            "definition": "executed FP64-pipe warp instructions per cell-update (static SASS count of the straight-line "
+                          "kernel per lane / cells a lane emits: profiles/sass_counts.json, regenerated by every build) x "
+                          "cell-updates/s x 2 flop per pipe slot, against the DFMA peak measured in this run",
+            "executed_fp64_instr_per_cell_update": per_update, "sass_counts_fresh": bool(sc.get("fresh")),
+            "peak_source": fp64["how"],
+            "algorithmic_flops": {"per_cell_update": ALGO_FLOPS_PER_CELL_UPDATE,
+                                  "tflops": per_gpu * ALGO_FLOPS_PER_CELL_UPDATE / 1e12,
+                                  "note": "SURVEY.md 8(d) count of the reference's arithmetic (divisions = 1 flop); the "
+                                          "FMA-fused, re-associated kernel executes fewer operations, so this can exceed the peak"},
+            "pipe_frac_at_sampled_clock": (per_gpu * per_update / (SMS * FP64_LANES_PER_SM * clocks["sm_mhz"] * 1e6)
+                                           if clocks and clocks.get("sm_mhz") else None),
+            "avg_launch_ms": ms_total / max(launches, 1),
+        },
+        "roofline_hbm": {
+            "bound": "hbm", "achieved": achieved_hbm, "peak": peak, "unit": "GB/s", "frac": achieved_hbm / peak,
+            "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_UPDATE / per_step * rows * N_CELLS,
+            "note": "64 algorithmic bytes per cell-update (three streaming stages, SURVEY.md 8d); the whole-step kernel "
+                    "moves 15.4 B of them (traffic: ncu dram bytes per launch, profiles/traffic.json scaled to this launch)",
+        },
+        "e2e": {
+            "value": cells_per_step * args.steps / e2e_s, "unit": UNIT,
+            "h2d_bytes_per_step": bytes_state * world / args.steps, "d2h_bytes_per_step": bytes_state * world / args.steps,
+            "call": f"EnsembleSolver.solve_fixed_dt_host(pinned host in, pinned host out, dt, K={args.steps}) per rank: "
+                    f"{groups} row blocks, upload / K steps / download pipelined over 4 streams",
+            "seconds": e2e_s,
+            "amortisation": f"ONE upload and ONE download of the state per call, amortised over K = {args.steps} steps "
+                            f"(at K = 1 the call is PCIe-bound: 2 x {bytes_state / 1e9:.2f} GB per rank per step)",
+            "h2d_gbs_per_rank": [r[0] for r in per_rank_gbs], "d2h_gbs_per_rank": [r[1] for r in per_rank_gbs],
+            "h2d_gbs": agg[0], "d2h_gbs": agg[1],
+            "copy_bound_seconds": copy_bound_ms * 1e-3,
+            "note": "h2d / d2h: one whole-state pinned copy per direction with every rank copying at the same time (CUDA "
+                    "events, per rank); copy_bound_seconds = the slower direction alone on the slowest rank: a floor of "
+                    "`seconds` that no kernel can lower",
+        },
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    return line
 
 
-def run_slab(args: argparse.Namespace) -> None:
-    """BASELINE.json configs[3]: ONE periodic Burgers grid of N = 2^30 cells, slab-decomposed over
-    the ranks with ring halo exchange (3 cells per side per stage), fixed dt at CFL 0.4."""
-    import torch
-    import torch.distributed as dist
+def measure_weak(ctx: Ctx, args: argparse.Namespace) -> dict:
+    """B rows PER GPU (round 1's headline): no collective, so it only shows that N ranks do not interfere."""
+    torch = ctx.torch
+    from pyshocks_b200.ensemble import EnsembleSolver
 
-    from pyshocks_b200.distributed import DistRing, PeerSlabSolver, SlabSolver
+    h = (DOMAIN[1] - DOMAIN[0]) / N_CELLS
+    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=N_CELLS,
+                            g=GHOSTS, dx=h, eps=EPS, batch=args.batch, math="fast", device=ctx.dev)
+    coef = torch.from_numpy(ensemble_coefficients(args.batch, 20261017 + ctx.rank)).to(ctx.dev)
+    u0 = device_initial_condition(coef, N_CELLS, GHOSTS, solver.nx, ctx.dev)
+    dt = torch.full((1,), CFL * h / 3.0, dtype=torch.float64, device=ctx.dev)  # |u0| < 0.5 + sum 1/k < 3
+    solver.load(u0)
+    del u0
+    solver.solve_fixed_dt(None, dt, args.warmup)
+    ms = timed_steps(ctx, lambda k: solver.solve_fixed_dt(None, dt, k), args.steps)
+    del solver
+    torch.cuda.empty_cache()
+    return {"value": args.batch * N_CELLS * ctx.world * args.steps / (ms * 1e-3), "unit": UNIT,
+            "rows_per_gpu": args.batch, "ms_per_step": ms / args.steps, "scaling": "weak"}
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    else:
-        dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
-    n_global = args.cells if args.cells else (1 << 30)
+
+# }}}
+
+# {{{ single huge grid (configs[3])
+
+
+def slab_window_check(slab, n_global: int, h: float, dt: float, nsteps: int, ctx: Ctx) -> dict:
+    """Size-independent parity of the decomposed solve: the domain of dependence of a cell is 9 cells per
+    step, so a window of the global grid advanced on its own by the C restatement (boundary kind NONE,
+    analytic initial data) must reproduce the slab's cells at the window centre.  Checked at this rank's
+    LAST cells -- the window reaches into the right neighbour's slab (or wraps around at N = 1), i.e.
+    the values that travelled through the ghost-cell exchange."""
+    from oracle import c_oracle
+    from oracle.c_oracle import COracle
+
+    halo = 9 * nsteps + 16
+    core = 2048
+    n_w = core + 2 * halo
+    start = slab.first + slab.n_local - core // 2 - halo  # global index of the first window cell
+    idx = (np.arange(start - GHOSTS, start + n_w + GHOSTS) % n_global).astype(np.float64)
+    u = (0.5 + np.sin(2.0 * np.pi * (idx + 0.5) / n_global))[None, :]
+    c_oracle.set_threads(1)
+    co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="none", n=n_w, g=GHOSTS, batch=1, dx=h, eps=EPS)
+    ref = co.solve_fixed_dt(u, dt, nsteps)[0, GHOSTS + halo : GHOSTS + halo + core // 2]
+    got = slab.interior()[slab.n_local - core // 2 :].cpu().numpy()
+    rel = float(np.abs(got - ref).max() / np.abs(ref).max())
+    rel = ctx.max_over_ranks([rel if np.isfinite(rel) else 1e300])[0]
+    return {"max_rel": rel, "tol": 1.0e-11, "ok": bool(rel <= 1.0e-11),
+            "what": f"the last {core // 2} cells of every rank's slab after {nsteps} steps against oracle/psk_oracle.c on a "
+                    f"{n_w}-cell window of the global grid around the slab edge (domain of dependence 9 cells per step); "
+                    "initial data evaluated on the host (device sin differs by an ulp); max over ranks"}
+
+
+def measure_slab(ctx: Ctx, args: argparse.Namespace, *, n_global: int, transport: str, steps: int, warmup: int,
+                 graph: bool = False, check: bool = True) -> dict:
+    torch = ctx.torch
+    from pyshocks_b200.distributed import DistRing, PeerRing, PeerSlabSolver, SlabSolver
+
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
     h = (DOMAIN[1] - DOMAIN[0]) / n_global
-    if args.transport == "nccl":
+    whole = transport in ("p2p-step", "p2p-step-fused")
+    if transport == "nccl":
         slab = SlabSolver(n_global=n_global, ring=DistRing(), dx=h, device=dev)
-        launches_per_step = 3
     else:
-        whole = args.transport == "p2p-step"
+        kw = {}
+        if transport == "p2p-step-fused":
+            kw["fused_step"] = True
         slab = PeerSlabSolver(n_global=n_global, rank=rank, world=world, dx=h, device=dev, whole_step=whole,
-                              overlap=(args.transport == "p2p-overlap"), fused=(args.transport == "p2p"))
-        slab.connect()
-        # per stage: fused = 1 launch; else wait, (2 edge +) 1 stage kernel, push; whole step: wait, step, push
-        launches_per_step = 3 if (slab.fused or whole) else (15 if slab.split else 9)
+                              overlap=(transport == "p2p-overlap"), fused=(transport == "p2p"), **kw)
+        if world > 1:
+            slab.connect()
+        else:
+            slab.attach(PeerRing.local([slab.mem], 0))
     i = torch.arange(slab.first, slab.first + slab.n_local, device=dev, dtype=torch.float64)
     slab.load_interior(0.5 + torch.sin(2.0 * np.pi * (i + 0.5) / n_global))
     del i
-    dt = torch.full((1,), CFL * h / 1.5, dtype=torch.float64, device=dev)
-
-    def barrier() -> None:
-        if world > 1:
-            dist.barrier(device_ids=[local])
-        torch.cuda.synchronize()
-
-    kw = {"graph": True} if (args.transport == "p2p" and args.graph) else {}
-    slab.solve_fixed_dt(dt, max(args.warmup, 6 if kw else 0), **kw)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    slab.solve_fixed_dt(dt, args.steps, **kw)
-    e1.record()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    if args.transport != "nccl":
+    dt_host = CFL * h / 1.5
+    dt = torch.full((1,), dt_host, dtype=torch.float64, device=dev)
+    kw = {"graph": True} if (transport == "p2p" and graph) else {}
+    warm = max(warmup, 6 if kw else 0)
+    slab.solve_fixed_dt(dt, warm, **kw)
+    l1 = getattr(slab, "launches", 0)
+    ms = timed_steps(ctx, lambda k: slab.solve_fixed_dt(dt, k, **kw), steps)
+    launches = (getattr(slab, "launches", 0) - l1) if transport != "nccl" else 3 * steps
+    if transport != "nccl":
         slab.check()  # a ghost-cell wait that timed out would have produced garbage silently
-    finite = bool(torch.isfinite(slab.interior()).all().item())
-    if rank == 0:
-        value = n_global * args.steps / (float(ms) * 1e-3)
-        peak, peak_src = measured_peaks()
-        achieved = value / world * ALGO_BYTES_PER_CELL_UPDATE / 1e9
-        emit({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": float(ms) / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"single periodic Burgers grid N={n_global} cells, slab-decomposed over {world} rank(s), "
-                                   + ("ring halo exchange 9 cells/side/step" if args.transport == "p2p-step" else
-                                      "ring halo exchange 3 cells/side/stage") + " (BASELINE.json configs[3])",
-                       "cells_per_gpu": slab.n_local,
-                       "halo_exchanges_per_step": 1 if args.transport == "p2p-step" else 3, "finite": finite,
-                       "cuda_graph": bool(kw),
-                       "transport": {"p2p": "exchange fused into the stage kernel: edge warps spin on local epoch flags, "
-                                            "edge lanes store into the neighbours' ghost slots over NVLink (1 launch per stage)",
-                                     "p2p-overlap": "NVLink peer stores + epoch flags, slab edges on a high-priority stream "
-                                                    "overlapped with the interior",
-                                     "p2p-serial": "NVLink peer stores + epoch flags, no overlap",
-                                     "p2p-step": "whole SSPRK33 step in one launch on a slab with 9 ghost cells; one "
-                                                 "exchange per step (NVLink peer stores + epoch flags, no overlap)",
-                                     "nccl": "NCCL send/recv pairs per stage"}[args.transport]},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src},
-            "gpu_launches": launches_per_step * args.steps,
-        })
-    if args.transport != "nccl":
-        slab.close()
-    dist.destroy_process_group()
+    finite = bool(ctx.max_over_ranks([0.0 if bool(torch.isfinite(slab.interior()).all().item()) else 1.0])[0] == 0.0)
+    parity = slab_window_check(slab, n_global, h, dt_host, warm + steps, ctx) if check else None
+    n_local = slab.n_local
+    if transport != "nccl":
+        if world > 1:
+            slab.close()
+        else:
+            slab.ring = None
+            slab.solver = None
+            slab._graph = None
+            slab.mem.close()
+    del slab
+    torch.cuda.empty_cache()
+    value = n_global * steps / (ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    achieved = value / world * ALGO_BYTES_PER_CELL_UPDATE / 1e9
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": ms / steps, "scaling": "strong", "cells": n_global, "cells_per_gpu": n_local,
+        "workload": f"single periodic Burgers grid N={n_global} cells, slab-decomposed over {world} rank(s) "
+                    "(BASELINE.json configs[3])",
+        "halo_exchanges_per_step": 1 if whole else 3, "halo_cells_per_side": 9 if whole else 3,
+        "transport": transport,
+        "transport_detail": {
+            "p2p": "exchange fused into the stage kernel: edge warps spin on local epoch flags, edge lanes store into the "
+                   "neighbours' ghost slots over NVLink (1 launch per stage)",
+            "p2p-overlap": "NVLink peer stores + epoch flags, slab edges on a high-priority stream overlapped with the interior",
+            "p2p-serial": "NVLink peer stores + epoch flags, no overlap",
+            "p2p-step": "whole SSPRK33 step in one launch on a slab with 9 ghost cells; one exchange per step "
+                        "(psk_halo_wait -> psk_ssprk33_step -> psk_halo_push: NVLink peer stores + epoch flags)",
+            "p2p-step-fused": "whole SSPRK33 step AND the 9-cell exchange in ONE launch: edge warps spin on local epoch "
+                              "flags, the lanes that store the slab's outermost 9 cells also store them into the "
+                              "neighbours' ghost slots over NVLink and raise their flags",
+            "nccl": "NCCL send/recv pairs per stage"}[transport],
+        "cuda_graph": bool(kw), "finite": finite, "parity": parity,
+        "roofline_hbm": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src},
+        "per_gpu_value": value / world,
+        "gpu_launches": launches,
+    }
 
 
-def run_adjoint(args: argparse.Namespace) -> None:
-    """BASELINE.json configs[4]: B = 4096 x N = 8192 ensemble, K fixed-dt steps forward with a
-    two-level device tape, reverse sweep for J = 1/2 sum ||u(T)||^2; rows sharded over the ranks."""
+# }}}
+
+# {{{ adjoint (configs[4])
+
+
+def adjoint_twin_check(dev, n: int, h: float, dt: float, u0_rows: np.ndarray, nsteps: int, kw: dict) -> dict:
+    """The product's gradient of J = 1/2 ||u(T)||^2 on a few rows of the benchmarked ensemble over a few
+    steps against reverse-mode differentiation of the reference arithmetic (oracle/torch_twin.py)."""
     import torch
-    import torch.distributed as dist
 
+    from oracle import pyshocks_oracle as po
+    from oracle import torch_twin as tt
     from pyshocks_b200.ensemble import AdjointEnsemble, EnsembleSolver
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    batch, n = (args.batch if args.batch != BATCH else 4096), (args.cells if args.cells else 8192)
+    rows = u0_rows.shape[0]
+    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=GHOSTS,
+                            dx=h, eps=EPS, batch=rows, device=dev)
+    adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, **(kw | {"segment": 2}))
+    _, grad = adj.gradient_half_l2(torch.from_numpy(u0_rows).to(dev))
+    grad = grad.cpu().numpy()
+    grid = po.make_grid(DOMAIN[0], DOMAIN[1], n, GHOSTS)
+    scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53"))
+    bc = po.Periodic()
+    worst = 0.0
+    for b in range(rows):
+        u = torch.from_numpy(u0_rows[b]).clone().requires_grad_(True)
+        x = u
+        for _ in range(nsteps):
+            x = tt.ssprk33_advance(lambda t_, y: tt.apply_operator(scheme, grid, bc, t_, y), dt, 0.0, x)
+        (gb,) = torch.autograd.grad(0.5 * (x[grid.interior] ** 2).sum(), u)
+        gb = gb.numpy()
+        i = grid.interior
+        worst = max(worst, float(np.abs(grad[b][i] - gb[i]).max() / np.abs(gb[i]).max()))
+    return {"max_rel": worst, "tol": 1.0e-12, "ok": bool(worst <= 1.0e-12),
+            "what": f"dJ/du0 of {rows} rows of this ensemble over {nsteps} steps (same kernels, two-level tape) against "
+                    "torch autograd through oracle/torch_twin.py (the stand-in for jax.jacfwd of the reference's advance)"}
+
+
+def measure_adjoint(ctx: Ctx, args: argparse.Namespace, *, batch_total: int, n: int, nsteps: int, check: bool = True) -> dict:
+    torch = ctx.torch
+    from pyshocks_b200.ensemble import AdjointEnsemble, EnsembleSolver
+
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    first, rows = shard(batch_total, rank, world)
     h = (DOMAIN[1] - DOMAIN[0]) / n
     solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=GHOSTS,
-                            dx=h, eps=EPS, batch=batch, device=dev)
-    coef = torch.from_numpy(ensemble_coefficients(batch, 20261018 + rank)).to(dev)
-    xhat = ((torch.arange(solver.nx, device=dev, dtype=torch.float64) - GHOSTS + 0.5) / n)[None, :]
-    u0 = coef[:, :1].repeat(1, solver.nx)
-    for k in range(4):
-        u0 += coef[:, 1 + k : 2 + k] * torch.sin(2.0 * np.pi * (k + 1) * xhat + coef[:, 5 + k : 6 + k])
-    dt = CFL * h / float(u0.abs().max())
-    nsteps = args.steps
-    adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt)
-    small = AdjointEnsemble(solver, nsteps=4, dt=dt, segment=2)
-    small.gradient_half_l2(u0)  # warm-up of every kernel
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                            dx=h, eps=EPS, batch=rows, device=dev)
+    coef_host = ensemble_coefficients(batch_total, 20261018)
+    coef = torch.from_numpy(coef_host[first : first + rows]).to(dev)
+    u0 = device_initial_condition(coef, n, GHOSTS, solver.nx, dev)
+    umax = u0.abs().max()
     if world > 1:
-        dist.barrier(device_ids=[local])
+        ctx.dist.all_reduce(umax, op=ctx.dist.ReduceOp.MAX)
+    dt = CFL * h / float(umax)
+    kw = {}
+    if os.environ.get("PSK_FUSED_REVERSE") is not None:  # A/B runs
+        kw["fused_reverse"] = os.environ["PSK_FUSED_REVERSE"] == "1"
+    if os.environ.get("PSK_FUSED_RECOMPUTE") is not None:
+        kw["fused_recompute"] = os.environ["PSK_FUSED_RECOMPUTE"] == "1"
+    seg = {"segment": int(os.environ["PSK_ADJ_SEGMENT"])} if os.environ.get("PSK_ADJ_SEGMENT") else {}
+    adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, **kw, **seg)
+    small = AdjointEnsemble(solver, nsteps=4, dt=dt, segment=2, **kw)
+    small.gradient_half_l2(u0)  # warm-up of every kernel
+    del small
+    ctx.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
     ev[0].record()
     uT = adj.forward(u0)
     ev[1].record()
@@ -505,34 +708,97 @@ def run_adjoint(args: argparse.Namespace) -> None:
     pT[:, GHOSTS : GHOSTS + n] = uT[:, GHOSTS : GHOSTS + n]
     grad = adj.backward(pT)
     ev[2].record()
-    torch.cuda.synchronize()
-    t = torch.tensor([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    fwd_ms, bwd_ms = float(t[0]), float(t[1])
-    if rank == 0:
-        peak, peak_src = measured_peaks()
-        cells = batch * n * world
-        adj_rate = cells * nsteps / (bwd_ms * 1e-3)
-        # reverse sweep, per cell-step: recompute k1, k2 (16 + 24 B), three adjoint stages (32 + 40 + 32 B),
-        # plus the segment recompute (64 B per forward step, amortised (segment - 1) / segment)
-        algo = 144.0 + 64.0 * (adj.segment - 1) / adj.segment
-        achieved = adj_rate / world * algo / 1e9
-        emit({
-            "metric": "adjoint gradients/s", "value": batch * world / ((fwd_ms + bwd_ms) * 1e-3), "unit": "gradients/s",
-            "n_gpus": world, "steps": nsteps, "warmup": args.warmup, "ms_per_step": (fwd_ms + bwd_ms) / nsteps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"adjoint of a batched Burgers ensemble B={batch} x N={n} per GPU, {nsteps} fixed-dt SSPRK33 "
-                                   f"steps, two-level tape (segment {adj.segment}), J = 1/2 sum ||u(T)||^2 (BASELINE.json configs[4])",
-                       "forward_ms": fwd_ms, "reverse_ms": bwd_ms, "tape_states": len(adj.chk) + len(adj.ring),
-                       "adjoint_cell_updates_per_s": adj_rate, "forward_cell_updates_per_s": cells * nsteps / (fwd_ms * 1e-3),
-                       "grad_finite": bool(torch.isfinite(grad).all())},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_cell_step": algo},
-            "gpu_launches": adj.launches,
-        })
-    if world > 1:
-        dist.destroy_process_group()
+    ctx.barrier()
+    fwd_ms, bwd_ms = ctx.max_over_ranks([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])])
+    grad_finite = bool(torch.isfinite(grad).all())
+    segment, tape_states, launches = adj.segment, len(adj.chk) + len(adj.ring), adj.launches
+    mode = getattr(adj, "reverse_mode", "recompute k1, k2 + 3 adjoint stage launches per reverse step")
+    u0_rows = u0[:2].cpu().numpy()
+    del adj, grad, uT, pT, u0, solver
+    torch.cuda.empty_cache()
+    parity = adjoint_twin_check(dev, n, h, dt, u0_rows, 6, kw) if (check and rank == 0) else None
+    torch.cuda.empty_cache()
+    peak, peak_src = measured_peaks()
+    cells = batch_total * n
+    adj_rate = cells * nsteps / (bwd_ms * 1e-3)
+    achieved = adj_rate / world * ADJ_ALGO_BYTES / 1e9
+    return {
+        "metric": "adjoint gradients/s", "value": batch_total / ((fwd_ms + bwd_ms) * 1e-3), "unit": "gradients/s",
+        "n_gpus": world, "steps": nsteps, "scaling": "strong",
+        "workload": f"adjoint of a batched Burgers ensemble B={batch_total} x N={n} (rows sharded over {world} rank(s)), "
+                    f"{nsteps} fixed-dt SSPRK33 steps, two-level tape (segment {segment}), J = 1/2 sum ||u(T)||^2 "
+                    "(BASELINE.json configs[4])",
+        "forward_ms": fwd_ms, "reverse_ms": bwd_ms, "ms_per_step": (fwd_ms + bwd_ms) / nsteps,
+        "tape_states": tape_states, "segment": segment, "reverse_mode": mode,
+        "adjoint_cell_updates_per_s": adj_rate, "forward_cell_updates_per_s": cells * nsteps / (fwd_ms * 1e-3),
+        "grad_finite": grad_finite, "parity": parity,
+        "roofline_hbm": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "peak_source": peak_src, "algorithmic_bytes_per_cell_step": ADJ_ALGO_BYTES,
+                         "note": "reverse sweep only, 144 B per cell-step (SURVEY.md 8d per-stage streaming design); the "
+                                 "segment recompute of the two-level tape is extra work inside reverse_ms, not extra credit"},
+        "gpu_launches": launches,
+    }
+
+
+# }}}
+
+
+def run_ours(args: argparse.Namespace) -> None:
+    ctx = Ctx()
+    line = measure_ensemble(ctx, args)
+    skip = set(filter(None, args.skip.split(",")))
+    subs: dict[str, dict] = {}
+
+    def sub(name: str, fn) -> None:
+        if name in skip:
+            return
+        try:
+            subs[name] = fn()
+        except Exception as exc:  # noqa: BLE001  (a failing sub-record must not take the headline with it)
+            import traceback
+
+            traceback.print_exc()
+            subs[name] = {"error": f"{type(exc).__name__}: {exc}"}
+            ctx.torch.cuda.empty_cache()
+
+    if ctx.world > 1:
+        sub("weak", lambda: measure_weak(ctx, args))
+    sub("slab", lambda: measure_slab(ctx, args, n_global=args.cells or (1 << 30), transport=args.transport,
+                                     steps=max(args.steps, 10), warmup=args.warmup))
+    sub("adjoint", lambda: measure_adjoint(ctx, args, batch_total=4096, n=8192, nsteps=args.adjoint_steps))
+    if ctx.rank == 0:
+        line.update(subs)
+        if not args.no_cpu_baseline:
+            res = cpu_port_steps(3, 1)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        emit(line)
+    ctx.close()
+
+
+def run_slab(args: argparse.Namespace) -> None:
+    """BASELINE.json configs[3] alone (profiling runs): `--workload slab [--transport ..] [--cells ..]`."""
+    ctx = Ctx()
+    if ctx.world == 1 and args.transport == "nccl":
+        ctx.dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1)
+    rec = measure_slab(ctx, args, n_global=args.cells or (1 << 30), transport=args.transport, steps=args.steps,
+                       warmup=args.warmup, graph=args.graph, check=not args.no_check)
+    if ctx.rank == 0:
+        rec.update({"higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": rec["workload"]}, "roofline": rec["roofline_hbm"]})
+        emit(rec)
+    ctx.close()
+
+
+def run_adjoint(args: argparse.Namespace) -> None:
+    """BASELINE.json configs[4] alone: `--workload adjoint [--steps K] [--cells n] [--batch B]`."""
+    ctx = Ctx()
+    rec = measure_adjoint(ctx, args, batch_total=(args.batch if args.batch != BATCH else 4096),
+                          n=args.cells or 8192, nsteps=args.steps, check=not args.no_check)
+    if ctx.rank == 0:
+        rec.update({"higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": rec["workload"]}, "roofline": rec["roofline_hbm"]})
+        emit(rec)
+    ctx.close()
 
 
 _JSON_OUT = None
@@ -547,18 +813,22 @@ def emit(line: dict) -> None:
 def main() -> None:
     global _JSON_OUT
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", choices=("ensemble", "slab", "adjoint"), default="ensemble",
-                    help="ensemble = the headline config (default); slab / adjoint = BASELINE configs 4 and 5")
-    ap.add_argument("--transport", choices=("p2p", "p2p-overlap", "p2p-serial", "p2p-step", "nccl"), default="p2p",
-                    help="ghost-cell exchange of the slab workload")
+    ap.add_argument("--workload", choices=("all", "slab", "adjoint"), default="all",
+                    help="all = the headline ensemble + the slab / adjoint sub-records (default); slab / adjoint = "
+                         "BASELINE configs 4 and 5 alone")
+    ap.add_argument("--transport", choices=("p2p", "p2p-overlap", "p2p-serial", "p2p-step", "p2p-step-fused", "nccl"),
+                    default="p2p-step", help="ghost-cell exchange of the slab workload")
     ap.add_argument("--graph", action="store_true", help="slab workload, fused transport: replay a CUDA graph of two steps")
     ap.add_argument("--cells", type=int, default=0, help="override the cell count of the slab / adjoint workloads")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--adjoint-steps", type=int, default=1000, help="steps of the adjoint sub-record (configs[4]: 1000)")
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    ap.add_argument("--batch", type=int, default=BATCH, help="rows per GPU (default: the named config)")
+    ap.add_argument("--batch", type=int, default=BATCH, help="rows of the WHOLE ensemble (default: the named config)")
+    ap.add_argument("--skip", default="", help="comma list of sub-records to skip: weak,slab,adjoint")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="slab / adjoint workloads: skip the oracle checks")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

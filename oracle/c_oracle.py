@@ -64,7 +64,14 @@ def lib() -> ct.CDLL:
         _lib.pso_solve_adaptive.argtypes = [
             ct.POINTER(Desc), _dp, ct.c_double, ct.c_double, ct.c_double, ct.c_int, _dp,
         ]
+        _lib.pso_set_threads.argtypes = [ct.c_int]
+        _lib.pso_set_threads.restype = ct.c_int
     return _lib
+
+
+def set_threads(nthreads: int) -> int:
+    """OpenMP threads of the row loops (0: leave as is); returns the count in use."""
+    return int(lib().pso_set_threads(int(nthreads)))
 
 
 def _p(a: np.ndarray | None):

@@ -19,6 +19,9 @@
  * Reference citations are relative to /root/reference/src/pyshocks.
  */
 #include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <stddef.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -272,6 +275,18 @@ static void rhs_row(const psk_desc *d, int r, const double *u, double *L, double
   } else {
     for (int i = 0; i < nx; ++i) L[i] = (-(F[i + 1] - F[i])) / d->dx;
   }
+}
+
+/* OpenMP thread count of the row loops (bench.py sets it to the affinity core count explicitly:
+   torch.distributed.run exports OMP_NUM_THREADS=1 to its workers).  Returns the count in use. */
+PSO_API int pso_set_threads(int nthreads) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+  return omp_get_max_threads();
+#else
+  (void)nthreads;
+  return 1;
+#endif
 }
 
 PSO_API int pso_apply_operator(const psk_desc *d, const double *u, double *L) {

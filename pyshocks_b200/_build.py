@@ -70,6 +70,10 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
         print(log)
     if rc != 0:
         raise RuntimeError(f"nvcc failed with exit code {rc}; see {CSRC / 'build.log'}")
+    # static FP64 instruction counts of the hot kernels (bench.py's pipe-occupancy figure) follow the library
+    tool = CSRC.parents[1] / "tools" / "sass_counts.py"
+    if tool.exists() and shutil.which("cuobjdump"):
+        subprocess.run([os.environ.get("PYTHON", "python"), str(tool)], capture_output=True, text=True)
     return LIB
 
 

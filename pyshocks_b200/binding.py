@@ -102,7 +102,9 @@ def hotpath_for(scheme: SchemeBase, grid: Any, bc: Boundary, t: Any = None, *, m
     kind = boundary_kind(bc)
     key = (id(grid), kind, math)
     cache = _paths(scheme)
-    hp = cache.get(key)
+    entry = cache.get(key)
+    # the entry keeps the grid alive (so its id cannot be reused) and is only trusted for that very grid
+    hp = entry[1] if (entry is not None and entry[0] is grid) else None
     if hp is None:
         from .grid import UniformGrid
 
@@ -120,7 +122,7 @@ def hotpath_for(scheme: SchemeBase, grid: Any, bc: Boundary, t: Any = None, *, m
             math=math, nu=nu, velocity=spec["velocity"], device=grid.x.device,
             delta=float(getattr(scheme.rec, "delta", 0.0)),
         )
-        cache[key] = hp
+        cache[key] = (grid, hp)
     if t is not None:
         gd = ghost_data(bc, grid, t)
         if gd is not None:

@@ -159,6 +159,10 @@ class SlabSolver:
 
     def __init__(self, *, n_global: int, ring: DistRing, flux: str = "rusanov", rec: str = "wenojs53",
                  dx: float, eps: float = 1.0e-12, math: str = "fast", device: torch.device | str | None = None) -> None:
+        if flux == "lf":
+            # the global Lax-Friedrichs speed is max|u| over the WHOLE grid (scalar.py:277): a slab only
+            # sees its own cells, so every rank would use a different dissipation
+            raise ValueError("slab decomposition does not support the global Lax-Friedrichs flux (use rusanov)")
         self.ring = ring
         self.first, self.n_local = shard_rows(n_global, ring.rank, ring.world)
         self.g = {"constant": 1, "wenojs32": 2, "wenojs53": 3}[rec]
@@ -365,6 +369,8 @@ class PeerSlabSolver:
                  rec: str = "wenojs53", eps: float = 1.0e-12, math: str = "fast", edge: int = 7680,
                  overlap: bool = True, fused: bool | None = None, device: torch.device | str | None = None,
                  timeout_s: float = 20.0, whole_step: bool = False) -> None:
+        if flux == "lf":
+            raise ValueError("slab decomposition does not support the global Lax-Friedrichs flux (use rusanov)")
         self.rank, self.world = rank, world
         self.first, self.n_local = shard_rows(n_global, rank, world)
         self.g = g = {"constant": 1, "wenojs32": 2, "wenojs53": 3}[rec]
@@ -605,6 +611,7 @@ class PeerSlabSolver:
         for _ in range(nsteps - done):
             self.step(dt)
         self.join()
+        self.check()  # a ghost-cell wait that gave up would otherwise yield a silently wrong state
         return SolveResult(u=self.solver.u, steps=nsteps, t=self.solver.t)
 
     def solve_adaptive(self, *, theta: float, tfinal: float, cfl_scale: float, max_steps: int = 1 << 20) -> SolveResult:

@@ -136,8 +136,10 @@ class HotPath:
         return batch, ld
 
     def _lf_work(self, batch: int) -> torch.Tensor | None:
+        # scratch is per launching stream: row blocks of one solver run concurrently on several streams
+        # (EnsembleSolver.solve_fixed_dt_host) and must not share the speed buffer
         if self.equation == "burgers" and self.flux == "lf":
-            return self.workspace("lf", (batch,))
+            return self.workspace(f"lf@{torch.cuda.current_stream(self.device).cuda_stream}", (batch,))
         return None
 
     # }}}
@@ -203,7 +205,7 @@ class HotPath:
     # {{{ discrete adjoint
 
     def _adj_work(self, batch: int) -> torch.Tensor:
-        return self.workspace("adj", (batch * (2 * self.g + 2),))
+        return self.workspace(f"adj@{torch.cuda.current_stream(self.device).cuda_stream}", (batch * (2 * self.g + 2),))
 
     def apply_operator_vjp(self, u: torch.Tensor, v: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """``J_L(u)^T v`` for ``L = apply_operator`` (what ``jax.vjp(apply_operator)`` returns)."""

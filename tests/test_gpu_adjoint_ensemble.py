@@ -5,8 +5,6 @@ tape (segment thinning + recompute) against the full tape."""
 
 from __future__ import annotations
 
-import os
-
 import numpy as np
 import pytest
 import torch
@@ -97,9 +95,6 @@ def test_two_level_tape_equals_full_tape(segment: int) -> None:
     assert torch.equal(g2, g_ref)  # recomputed states are bit-identical to the stored ones
 
 
-@pytest.mark.skipif(os.environ.get("PSK_TEST_UNVERIFIED") != "1",
-                    reason="fused_recompute (psk_ssprk33_step_stages) is validated on the CPU warp emulation only; "
-                           "set PSK_TEST_UNVERIFIED=1 for its first GPU run")
 @pytest.mark.parametrize("segment", [1, 3, 25])
 def test_fused_recompute_gives_the_same_gradient(segment: int) -> None:
     """reverse sweep with (k1, k2[, next state]) recomputed in one launch: same bits as with stage launches"""
@@ -107,7 +102,7 @@ def test_fused_recompute_gives_the_same_gradient(segment: int) -> None:
 
     batch, n, nsteps = 5, 128, 25
     solver, grid, u0, dt = _setup(batch, n)
-    ref = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=segment)
+    ref = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=segment, fused_recompute=False)
     _, g_ref = ref.gradient_half_l2(torch.from_numpy(u0).cuda())
     g_ref = g_ref.clone()
     solver2, *_ = _setup(batch, n)

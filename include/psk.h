@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PSK_VERSION 102 /* 0.1.2: psk_ssprk33_step */
+#define PSK_VERSION 103 /* 0.1.3: psk_ssprk33_step_adjoint */
 
 typedef void *psk_stream_t; /* cudaStream_t */
 
@@ -187,6 +187,26 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
  * Same bits as psk_ssprk33_stage.  No array may alias another. */
 int psk_ssprk33_step_stages(const psk_desc *d, const double *u, double *k1, double *k2, double *uout,
                             const double *dt, int64_t dt_stride, psk_stream_t stream);
+
+/* One whole REVERSE SSPRK33 step in ONE launch (psk_reverse_kernels.cuh): what adjoint_step computes per
+ * step as jax.jacfwd(advance)(dt, t, u).T @ p (timestepping.py:174, :198-209),
+ *     p_out = (d advance(dt, u) / d u)^T p_in,
+ * from the checkpointed state u alone: the stage values k1, k2 are recomputed inside the kernel, then the
+ * three adjoint stages of psk_ssprk33_stage_adjoint follow, with k1, k2, lam2, lam1 in shared memory
+ * (24 B of DRAM traffic per cell instead of the 144 B of five launches).  Rows are periodic RINGS of
+ * the n interior cells: only interior cells of u, p_in are read and only interior cells of p_out are
+ * written (the gradient of the interior -> interior map; no cotangent lives on ghost cells).
+ * Burgers + Rusanov (nu = 1) + WENO-JS5, FAST math, periodic, 16-byte aligned rows, n even;
+ * PSK_E_UNSUPPORTED elsewhere (recompute with psk_ssprk33_step_stages and call
+ * psk_ssprk33_stage_adjoint three times instead).  k1_out / k2_out: optional (both or neither), the
+ * recomputed stage values of the interior cells, bit-identical to psk_ssprk33_stage.
+ * p_out must not alias p_in or u. */
+int psk_ssprk33_step_adjoint(const psk_desc *d, const double *u, const double *p_in, const double *dt,
+                             int64_t dt_stride, double *p_out, double *k1_out, double *k2_out,
+                             psk_stream_t stream);
+
+/* A/B switch of psk_ssprk33_step_adjoint: cells per lane of its windows (12, 16, 20, 24; 0 = automatic). */
+int psk_set_reverse_variant(int variant);
 
 /* Device-side step control of timestepping.step (timestepping.py:128-150) for
  * Burgers-type schemes, per row r:

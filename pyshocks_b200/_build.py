@@ -13,8 +13,8 @@ import subprocess
 
 CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIB = CSRC / "libpsk.so"
-SOURCES = ("psk_forward.cu", "psk_adjoint.cu", "psk_solve.cu", "psk_p2p.cu")
-HEADERS = ("psk_common.cuh", "psk_math.cuh", "psk_fast_kernels.cuh", "psk_adjoint_math.cuh", "psk_adjoint_kernels.cuh", "../../include/psk.h")
+SOURCES = ("psk_forward.cu", "psk_adjoint.cu", "psk_reverse.cu", "psk_solve.cu", "psk_p2p.cu")
+HEADERS = ("psk_common.cuh", "psk_math.cuh", "psk_fast_kernels.cuh", "psk_adjoint_math.cuh", "psk_adjoint_kernels.cuh", "psk_reverse_kernels.cuh", "../../include/psk.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -104,6 +104,8 @@ def _load() -> ct.CDLL:
         "psk_ssprk33_stage": ([D, ct.c_int, vp, vp, vp, vp, i64, vp, vp, vp, ct.c_int, vp], ct.c_int),
         "psk_ssprk33_step": ([D, vp, vp, vp, i64, vp, vp, vp], ct.c_int),
         "psk_ssprk33_step_stages": ([D, vp, vp, vp, vp, vp, i64, vp], ct.c_int),
+        "psk_ssprk33_step_adjoint": ([D, vp, vp, vp, i64, vp, vp, vp, vp], ct.c_int),
+        "psk_set_reverse_variant": ([ct.c_int], ct.c_int),
         "psk_step_control": ([i32, f64, f64, f64, vp, vp, vp, vp, vp, vp, vp], ct.c_int),
         "psk_solve_rows": ([D, vp, ct.c_int, f64, f64, f64, f64, ct.c_int, vp, vp, vp, vp, vp], ct.c_int),
         "psk_dfma_probe": ([vp, ct.c_int, ct.c_int, vp], ct.c_int),
@@ -129,12 +131,14 @@ def _load() -> ct.CDLL:
 _lib = _load()
 if os.environ.get("PSK_ADJOINT_VARIANT"):  # A/B measurements only
     _lib.psk_set_adjoint_variant(int(os.environ["PSK_ADJOINT_VARIANT"]))
+if os.environ.get("PSK_REVERSE_VARIANT"):  # A/B measurements only
+    _lib.psk_set_reverse_variant(int(os.environ["PSK_REVERSE_VARIANT"]))
 if os.environ.get("PSK_STAGE_VARIANT"):  # A/B measurements only
     _lib.psk_set_stage_variant(int(os.environ["PSK_STAGE_VARIANT"]))
 EXPORTS = (
     "psk_version", "psk_status_string", "psk_last_cuda_error", "psk_set_stage_variant", "psk_set_adjoint_variant", "psk_apply_boundary",
     "psk_reconstruct", "psk_numerical_flux", "psk_apply_operator", "psk_max_abs",
-    "psk_ssprk33_stage", "psk_ssprk33_step", "psk_ssprk33_step_stages", "psk_step_control", "psk_solve_rows", "psk_dfma_probe", "psk_apply_operator_vjp",
+    "psk_ssprk33_stage", "psk_ssprk33_step", "psk_ssprk33_step_stages", "psk_ssprk33_step_adjoint", "psk_set_reverse_variant", "psk_step_control", "psk_solve_rows", "psk_dfma_probe", "psk_apply_operator_vjp",
     "psk_ssprk33_stage_adjoint", "psk_p2p_alloc", "psk_p2p_free", "psk_p2p_open", "psk_p2p_close",
     "psk_halo_push", "psk_halo_wait", "psk_ssprk33_stage_p2p",
 )

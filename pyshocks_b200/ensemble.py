@@ -307,8 +307,19 @@ class AdjointEnsemble:
     is imposed on it: ``backward`` returns the exact gradient of the discrete forward map."""
 
     def __init__(self, solver: EnsembleSolver, *, nsteps: int, dt: float | torch.Tensor,
-                 segment: int | None = None, memory_fraction: float = 0.7, fused_recompute: bool = True) -> None:
+                 segment: int | None = None, memory_fraction: float = 0.8, fused_recompute: bool = True,
+                 fused_reverse: bool | None = None) -> None:
         self.s = solver
+        # fused_reverse: ONE launch per reverse step (psk_ssprk33_step_adjoint: k1, k2 recomputed and the three
+        # adjoint stages applied inside the kernel) wherever that kernel exists (None: automatic); the
+        # stage values then never touch HBM, so the tape holds states only and the segment can be shorter
+        can = solver.hp.reverse_step_supported()
+        if fused_reverse and not can:
+            raise ValueError("the fused reverse step needs burgers + rusanov (alpha = 1) + wenojs53, fast math, periodic rows, even n")
+        self.fused_reverse = can if fused_reverse is None else bool(fused_reverse)
+        self.reverse_mode = ("1 launch per reverse step (psk_ssprk33_step_adjoint: recompute + 3 adjoint stages fused)"
+                             if self.fused_reverse else
+                             "recompute k1, k2 (1 launch) + 3 adjoint stage launches (+ 3 boundary transposes) per reverse step")
         # fused_recompute: the reverse sweep recomputes (k1, k2[, next state]) of a state with ONE launch
         # (psk_ssprk33_step_stages) instead of two or three stage launches; bit-identical stage values
         # (tests/test_gpu_adjoint_ensemble.py), 2 % off the reverse sweep of config 5.
@@ -323,9 +334,14 @@ class AdjointEnsemble:
         self.chk = solver.new_states(self.nseg + 1)  # states at steps 0, k, 2k, ...
         # states inside the current segment and the stages k1, k2 their recomputation produces
         self.ring = solver.new_states(self.segment)
-        self.ring_k1 = solver.new_states(max(self.segment - 1, 0))
-        self.ring_k2 = solver.new_states(max(self.segment - 1, 0))
-        self.lam2, self.lam1, self.p, self.pn = solver.new_states(4)
+        keep_stages = 0 if self.fused_reverse else max(self.segment - 1, 0)
+        self.ring_k1 = solver.new_states(keep_stages)
+        self.ring_k2 = solver.new_states(keep_stages)
+        if self.fused_reverse:
+            self.lam1, self.p, self.pn = solver.new_states(3)
+            self.lam2 = None
+        else:
+            self.lam2, self.lam1, self.p, self.pn = solver.new_states(4)
         self.launches = 0
         self._fused: bool | None = None  # whether psk_ssprk33_step covers the scheme (None: not tried)
 
@@ -336,8 +352,9 @@ class AdjointEnsemble:
         state_bytes = s.batch * s.ld * 8
         free, _ = torch.cuda.mem_get_info(s.hp.device)
         budget = int(memory_fraction * free) // state_bytes - 8
+        per_ring = 1 if self.fused_reverse else 3  # states only, or states + their stage values k1, k2
         for k in range(1, max(self.nsteps, 1) + 1):
-            if (self.nsteps + k - 1) // k + 1 + 3 * k <= budget:
+            if (self.nsteps + k - 1) // k + 1 + per_ring * k <= budget:
                 return k
         raise MemoryError("not enough device memory for the adjoint tape")
 
@@ -383,6 +400,20 @@ class AdjointEnsemble:
         s, hp = self.s, self.s.hp
         p, pn = self.p, self.pn
         p.copy_(pT)
+        if self.fused_reverse:
+            for seg in range(self.nseg - 1, -1, -1):
+                m0 = seg * self.segment
+                last = min(m0 + self.segment, self.nsteps) - m0 - 1
+                # the states u^{m0 + 1} .. u^{m0 + last} of this segment, one whole-step launch each
+                for j in range(1, last + 1):
+                    self._advance(self.chk[seg] if j == 1 else self.ring[j - 1], self.ring[j])
+                for j in range(last, -1, -1):
+                    if not hp.reverse_step_fused(self.chk[seg] if j == 0 else self.ring[j], p, self.dt, pn):
+                        raise RuntimeError("psk_ssprk33_step_adjoint does not cover this configuration")
+                    p, pn = pn, p
+                    self.launches += 1
+            self.p, self.pn = p, pn
+            return p
         for seg in range(self.nseg - 1, -1, -1):
             m0 = seg * self.segment
             m1 = min(m0 + self.segment, self.nsteps)

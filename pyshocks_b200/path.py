@@ -403,6 +403,34 @@ class HotPath:
         L.check("psk_ssprk33_step_stages", rc)
         return True
 
+    def reverse_step_supported(self) -> bool:
+        """whether :meth:`reverse_step_fused` exists for this scheme (the conditions of psk_ssprk33_step_adjoint;
+        the arrays must also be 16-byte aligned with an even row stride, which EnsembleSolver guarantees)"""
+        return (self.equation == "burgers" and self.flux == "rusanov" and self.rec == "wenojs53" and self.math == "fast"
+                and self.bc == "periodic" and self._nu is None and self.n % 2 == 0 and self.n >= 8 and self.g >= 3)
+
+    def reverse_step_fused(self, u: torch.Tensor, p: torch.Tensor, dt: torch.Tensor, out: torch.Tensor, *,
+                           stages: tuple[torch.Tensor, torch.Tensor] | None = None) -> bool:
+        """``out = (d advance(dt, u) / d u)^T p`` for one SSPRK33 step from the checkpointed state ``u`` in ONE
+        launch (``psk_ssprk33_step_adjoint``: ``k1, k2`` recomputed and the three adjoint stages applied inside
+        the kernel; timestepping.py:198-209 without the dense Jacobian).  Interior cells only (periodic rings);
+        ``stages``: optional arrays that receive the recomputed ``k1, k2``.  ``False`` -- nothing launched --
+        outside its configuration (the caller then runs :meth:`ssprk33_step_adjoint`)."""
+        batch, ld = self._state(u)
+        for a in (p, out) + (tuple(stages) if stages is not None else ()):
+            if L.rows_of(a)[2] != ld:
+                raise ValueError("all arrays must share one row stride")
+        d = self.desc(batch, ld)
+        k1, k2 = stages if stages is not None else (None, None)
+        rc = L.lib().psk_ssprk33_step_adjoint(
+            ct.byref(d), L.ptr(u), L.ptr(p), L.ptr(dt), 0 if dt.numel() == 1 else 1, L.ptr(out), L.ptr(k1), L.ptr(k2),
+            L.stream_ptr(),
+        )
+        if rc == L.E_UNSUPPORTED:
+            return False
+        L.check("psk_ssprk33_step_adjoint", rc)
+        return True
+
     def ssprk33_step(
         self,
         u: torch.Tensor,

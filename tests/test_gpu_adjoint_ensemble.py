@@ -102,11 +102,66 @@ def test_fused_recompute_gives_the_same_gradient(segment: int) -> None:
 
     batch, n, nsteps = 5, 128, 25
     solver, grid, u0, dt = _setup(batch, n)
-    ref = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=segment, fused_recompute=False)
+    ref = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=segment, fused_recompute=False, fused_reverse=False)
     _, g_ref = ref.gradient_half_l2(torch.from_numpy(u0).cuda())
     g_ref = g_ref.clone()
     solver2, *_ = _setup(batch, n)
-    adj = AdjointEnsemble(solver2, nsteps=nsteps, dt=dt, segment=segment, fused_recompute=True)
+    adj = AdjointEnsemble(solver2, nsteps=nsteps, dt=dt, segment=segment, fused_recompute=True, fused_reverse=False)
     _, g2 = adj.gradient_half_l2(torch.from_numpy(u0).cuda())
     assert adj.launches < ref.launches
     assert torch.equal(g2, g_ref)
+
+
+@pytest.mark.parametrize("n,variant", [(256, 0), (250, 12), (1000, 16), (1000, 20), (4096, 0), (74, 12), (600, 24)])
+def test_fused_reverse_step_matches_the_five_launch_path(n: int, variant: int) -> None:
+    """psk_ssprk33_step_adjoint (one launch: recompute + 3 adjoint stages in shared memory) against
+    psk_ssprk33_step_stages + 3 x psk_ssprk33_stage_adjoint on the same state: recomputed stage values
+    bit-identical, cotangent equal to round-off (the transposed stencil is summed in a different order)."""
+    from pyshocks_b200 import _lib as L
+    from pyshocks_b200.ensemble import AdjointEnsemble
+
+    batch = 5
+    solver, grid, u0, dt = _setup(batch, n)
+    assert L.lib().psk_set_reverse_variant(variant) == 0
+    try:
+        hp = solver.hp
+        u, k1, k2, k1f, k2f, p, out, ref = solver.new_states(8)
+        u.copy_(torch.from_numpy(u0).cuda())
+        rng = np.random.default_rng(n)
+        p[:, grid.g : grid.g + n] = torch.from_numpy(rng.standard_normal((batch, n))).cuda()
+        dtt = torch.full((1,), dt, dtype=torch.float64, device="cuda")
+        assert hp.reverse_step_fused(u, p, dtt, out, stages=(k1f, k2f))
+        assert hp.step_fused_stages(u, k1, k2, None, dtt)
+        i = slice(grid.g, grid.g + n)
+        assert torch.equal(k1f[:, i], k1[:, i]) and torch.equal(k2f[:, i], k2[:, i])
+        hp.ssprk33_step_adjoint(u, dtt, p, out=ref, stages=(k1, k2))
+        assert max_rel(out[:, i].cpu().numpy(), ref[:, i].cpu().numpy()) < 1e-13
+        assert float(out[:, : grid.g].abs().max()) == 0.0  # ghost cells are not written
+    finally:
+        L.lib().psk_set_reverse_variant(0)
+
+
+@pytest.mark.parametrize("segment", [1, 2, 5])
+def test_gradient_with_the_fused_reverse_step(segment: int) -> None:
+    """whole sweeps: fused reverse step against the stage-by-stage sweep and against the autograd twin"""
+    from pyshocks_b200.ensemble import AdjointEnsemble
+
+    batch, n, nsteps = 3, 128, 11
+    solver, grid, u0, dt = _setup(batch, n)
+    ref = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=segment, fused_reverse=False)
+    _, g_ref = ref.gradient_half_l2(torch.from_numpy(u0).cuda())
+    g_ref = g_ref.cpu().numpy().copy()
+    solver2, *_ = _setup(batch, n)
+    adj = AdjointEnsemble(solver2, nsteps=nsteps, dt=dt, segment=segment)
+    assert adj.fused_reverse and adj.lam2 is None
+    J, g2 = adj.gradient_half_l2(torch.from_numpy(u0).cuda())
+    assert adj.launches < ref.launches
+    assert max_rel(g2.cpu().numpy(), g_ref) < 1e-13
+    scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53"))
+    i = grid.interior
+    u = torch.from_numpy(u0[0]).clone().requires_grad_(True)
+    x = u
+    for _ in range(nsteps):
+        x = tt.ssprk33_advance(lambda t_, y: tt.apply_operator(scheme, grid, po.Periodic(), t_, y), dt, 0.0, x)
+    (gb,) = torch.autograd.grad(0.5 * (x[i] ** 2).sum(), u)
+    assert max_rel(g2[0].cpu().numpy(), gb.numpy()) < 1e-12

@@ -1,0 +1,127 @@
+"""The fused reverse SSPRK33 step of the product (pyshocks_b200/csrc/psk_reverse_kernels.cuh: recompute
+k1, k2 and apply the three transposed stages in one kernel -- what the reference's adjoint_step gets per
+step from jax.jacfwd(advance).T @ p, timestepping.py:174, :198-209) compiled for the HOST and run under
+the warp emulation of tests/host/emu/cuda_runtime.h.  Pins the lane-private streams, the exchanges at the
+run ends, the window overlap and the periodic wrap without a GPU: against reverse-mode differentiation
+of the reference arithmetic (oracle/torch_twin.py) and, for the recomputed stages, against the C oracle."""
+
+from __future__ import annotations
+
+import ctypes as ct
+import pathlib
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import pyshocks_oracle as po
+from oracle import torch_twin as tt
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+G = 3
+EPS = 1.0e-12
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    out = tmp_path_factory.mktemp("emu") / "librevemu.so"
+    subprocess.run([gxx, "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-pthread",
+                    "-I", str(ROOT / "tests" / "host" / "emu"), "-o", str(out),
+                    str(ROOT / "tests" / "host" / "reverse_kernel_host.cpp")], check=True)
+    lib = ct.CDLL(str(out))
+    dp = ct.POINTER(ct.c_double)
+    lib.emu_reverse_step.argtypes = [ct.c_int] * 4 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int, dp, dp, dp]
+    lib.emu_reverse_step.restype = ct.c_int
+    return lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ct.POINTER(ct.c_double))
+
+
+def _state(n: int, kind: str, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    x = (np.arange(n + 2 * G) - G + 0.5) / n
+    u = rng.uniform(-0.3, 0.3) + sum(rng.uniform(0, 1 / k) * np.sin(2 * np.pi * k * x + rng.uniform(0, 6.28))
+                                     for k in range(1, 4))
+    if kind == "tophat":
+        u = u + np.where((x > 0.3) & (x < 0.6), 0.8, 0.0)
+    return u
+
+
+def _aligned(batch: int, n: int) -> tuple[np.ndarray, int, int]:
+    """(storage, col0, ld): rows whose first interior cell is 16-byte aligned (ensemble.row_layout)"""
+    col0 = (16 - G) % 16
+    ld = ((col0 + n + 2 * G + 15) // 16) * 16
+    raw = np.zeros(batch * ld + 2)
+    off = 0 if (raw.ctypes.data + 8 * (col0 + G)) % 16 == 0 else 1
+    return raw[off : off + batch * ld].reshape(batch, ld), col0, ld
+
+
+def _run(emu, C: int, n: int, u: np.ndarray, p: np.ndarray, dt: float, stages: bool = False):
+    batch = u.shape[0]
+    nx = n + 2 * G
+    bufs = []
+    for src in (u, p, None, None, None):
+        a, col0, ld = _aligned(batch, n)
+        v = a[:, col0 : col0 + nx]
+        if src is not None:
+            v[:] = src
+        else:
+            v[:] = np.nan
+        bufs.append(v)
+    U, P, OUT, K1, K2 = bufs
+    dts = np.full(batch, dt)
+    rc = emu.emu_reverse_step(C, n, G, batch, ld, 3.0 / n, EPS, _p(U), _p(P), _p(dts), 1, _p(OUT),
+                              _p(K1) if stages else None, _p(K2) if stages else None)
+    assert rc == 0
+    return (OUT, K1, K2) if stages else OUT
+
+
+@pytest.mark.parametrize("C", [8, 12, 16, 20])
+@pytest.mark.parametrize("n,kind,tol", [(1000, "smooth", 3e-12), (300, "smooth", 3e-12), (74, "smooth", 3e-12),
+                                        (812, "tophat", 2e-9)])
+def test_fused_reverse_step_is_the_transposed_step_jacobian(emu, C: int, n: int, kind: str, tol: float) -> None:
+    # tolerance: three chained stages; the worst cells (next to an extremum, beta ~ eps) are the same ones with the
+    # same error for every run length C, i.e. round-off of the derivative itself, not of the tiling
+    rng = np.random.default_rng(n + C)
+    batch = 2
+    u = np.stack([_state(n, kind, 10 * n + b) for b in range(batch)])
+    p = rng.standard_normal((batch, n + 2 * G))
+    p[:, :G] = 0.0
+    p[:, n + G :] = 0.0
+    dt = 0.3 * (3.0 / n)
+    out = _run(emu, C, n, u, p, dt)
+    i = slice(G, G + n)
+    assert np.isfinite(out[:, i]).all()
+    assert np.isnan(out[:, :G]).all() and np.isnan(out[:, n + G :]).all()  # ghost cells are not written
+    scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53", EPS))
+    grid = po.make_grid(-1.5, 1.5, n, G)
+    for b in range(batch):
+        ref = tt.step_vjp(scheme, grid, po.Periodic(), dt, 0.0, u[b], p[b])
+        err = np.abs(out[b, i] - ref[i]).max() / np.abs(ref[i]).max()
+        assert err < tol, (b, err)
+
+
+@pytest.mark.parametrize("C,n", [(16, 1000), (12, 74), (20, 2000)])
+def test_recomputed_stage_values_match_the_oracle(emu, C: int, n: int) -> None:
+    """k1, k2 of timestepping.py:314-317 as the kernel recomputes them (FAST arithmetic: 1e-13 of the C oracle)"""
+    from oracle.c_oracle import COracle
+
+    batch = 2
+    u = np.stack([_state(n, "smooth", 7 * n + b) for b in range(batch)])
+    p = np.zeros_like(u)
+    dt = 0.3 * (3.0 / n)
+    _, k1, k2 = _run(emu, C, n, u, p, dt, stages=True)
+    co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=G, batch=batch,
+                 dx=3.0 / n, eps=EPS)
+    L = co.apply_operator(u)
+    r1 = u + dt * L
+    r2 = 0.75 * u + 0.25 * (r1 + dt * co.apply_operator(r1))
+    i = slice(G, G + n)
+    assert np.abs(k1[:, i] - r1[:, i]).max() < 1e-13 * np.abs(r1).max()
+    assert np.abs(k2[:, i] - r2[:, i]).max() < 1e-13 * np.abs(r2).max()

@@ -90,21 +90,26 @@ __device__ __forceinline__ double rev_flux4(double urj, double ulp, double m2j, 
   return fma(umax_neg(m2j, m2p), ulp - urj, fma(urj, urj, ulp * ulp));
 }
 
-template <int STAGE>
-__device__ __forceinline__ double rev_combine(double x, double u0, double cdt, double dF) {
+// stage 1: k1 = x + cdt dF; stage 2: k2 = 3/4 u0 + 1/4 (x + cdt dF) -- the expressions of the stage kernels
+__device__ __forceinline__ double rev_combine(bool stage2, double x, double u0, double cdt, double dF) {
   const double k = fma(cdt, dF, x);
-  return (STAGE == 1) ? k : fma(0.25, k, 0.75 * u0);
+  return stage2 ? fma(0.25, k, 0.75 * u0) : k;
 }
 
 // ---------------------------------------------------------------------------
-// forward stage on the lane's run: Y = x + cdt dF(X) (STAGE 1) or 3/4 U0 + 1/4 (x + cdt dF(X)) (STAGE 2),
+// forward stage on the lane's run: Y = x + cdt dF(X) (stage 1) or 3/4 U0 + 1/4 (x + cdt dF(X)) (stage 2),
 // then the two halo cells per side of Y from the neighbour lanes.  X holds run cells -2 .. C + 1.
-template <int C, int STAGE>
-__device__ __forceinline__ void rev_forward_stage(const LaneArray X, const LaneArray Y, const LaneArray U0,
+// The stage is a RUN-TIME argument (as is the mode of the adjoint stage below): both forward stages
+// and all three adjoint stages execute the same instructions, which keeps the kernel's code inside the
+// 32 KB instruction cache -- with one inlined copy per stage (61 KB) the warps of an SM, each at its own
+// place in the code, stalled on instruction fetch more than on anything else.
+template <int C>
+__device__ __forceinline__ void rev_forward_stage(bool stage2, const LaneArray X, const LaneArray Y, const LaneArray U0,
                                                   double cdt, double eps9) {
   constexpr unsigned kFull = 0xffffffffu;
   double ur_prev = 0.0, F_prev = 0.0;  // ur of cell j0 - 1, flux of the face (j0 - 2 | j0 - 1)
   double ul_first = 0.0, F_first = 0.0;  // ul of cell 0 and the flux of the face (0 | 1), for the end of the stream
+  double y_prev = 0.0;                   // result of the cell j0 - 2
 #pragma unroll 1
   for (int j0 = 0; j0 < C; j0 += 4) {
     double w[8];  // cells j0 - 2 .. j0 + 5
@@ -139,14 +144,19 @@ __device__ __forceinline__ void rev_forward_stage(const LaneArray X, const LaneA
       ul_first = ul[0];
       F_first = F[1];
     }
-    // cells j0 - 1 .. j0 + 2 are complete (the cell j0 - 1 of the first iteration is a halo slot, rewritten below)
+    // cells j0 - 1 .. j0 + 2 are complete; stored as the aligned pairs (j0 - 2, j0 - 1), (j0, j0 + 1) with
+    // the cell j0 - 2 carried from the previous iteration (run cells -2, -1 are halo slots, rewritten below)
+    double y[4];
+    const double2 ua = U0.ld2(j0 - 2), ub = U0.ld2(j0), uc = U0.ld2(j0 + 2);
+    const double u0v[4] = {ua.y, ub.x, ub.y, uc.x};
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      const int j = j0 - 1 + m;
       const double dF = (m == 0 ? F_prev : F[m - 1]) - F[m];
-      const double u0 = (STAGE == 2) ? U0.ld1(j) : 0.0;
-      Y.st1(j, rev_combine<STAGE>(w[m + 1], u0, cdt, dF));
+      y[m] = rev_combine(stage2, w[m + 1], u0v[m], cdt, dF);
     }
+    Y.st2(j0 - 2, y_prev, y[0]);
+    Y.st2(j0, y[1], y[2]);
+    y_prev = y[3];
     ur_prev = ur[3];
     F_prev = F[3];
   }
@@ -156,12 +166,13 @@ __device__ __forceinline__ void rev_forward_stage(const LaneArray X, const LaneA
   const double2 a = X.ld2(-2), b = X.ld2(0), c = X.ld2(C - 2), d = X.ld2(C);
   const double F0 = rev_flux4(ur_left, ul_first, -2.0 * fabs(a.y), -2.0 * fabs(b.x));
   const double FC = rev_flux4(ur_prev, ul_right, -2.0 * fabs(c.y), -2.0 * fabs(d.x));
-  const double y0 = rev_combine<STAGE>(b.x, (STAGE == 2) ? U0.ld1(0) : 0.0, cdt, F0 - F_first);
-  const double yl = rev_combine<STAGE>(c.y, (STAGE == 2) ? U0.ld1(C - 1) : 0.0, cdt, F_prev - FC);
-  const double y1 = Y.ld1(1), ym = Y.ld1(C - 2);
-  Y.st1(0, y0);
-  Y.st1(C - 1, yl);
-  Y.st2(-2, __shfl_up_sync(kFull, ym, 1), __shfl_up_sync(kFull, yl, 1));
+  const double2 uf = U0.ld2(0), ue = U0.ld2(C - 2);
+  const double y0 = rev_combine(stage2, b.x, uf.x, cdt, F0 - F_first);
+  const double yl = rev_combine(stage2, c.y, ue.y, cdt, F_prev - FC);
+  const double y1 = Y.ld2(0).y;  // cell 1 (cell 0 of that pair is still the provisional value)
+  Y.st2(0, y0, y1);
+  Y.st2(C - 2, y_prev, yl);
+  Y.st2(-2, __shfl_up_sync(kFull, y_prev, 1), __shfl_up_sync(kFull, yl, 1));
   Y.st2(C, __shfl_down_sync(kFull, y0, 1), __shfl_down_sync(kFull, y1, 1));
 }
 
@@ -173,8 +184,8 @@ __device__ __forceinline__ void rev_forward_stage(const LaneArray X, const LaneA
 // neighbours' values (OUT is the V of the next stage).
 //   MODE 0: as above without A;  MODE 1: also A = 1/3 V + 3/4 OUT (A aliases V: the accumulator
 //   1/3 p' + 3/4 lam2 of the last stage takes the place of p');  MODE 2: with the term + A.
-template <int C, int MODE>
-__device__ __forceinline__ void rev_adjoint_stage(const LaneArray X, const LaneArray V, const LaneArray OUT,
+template <int C>
+__device__ __forceinline__ void rev_adjoint_stage(const int MODE, const LaneArray X, const LaneArray V, const LaneArray OUT,
                                                   const LaneArray A, double c_v, double hs, double eps9,
                                                   double *park) {
   constexpr unsigned kFull = 0xffffffffu;
@@ -207,7 +218,7 @@ __device__ __forceinline__ void rev_adjoint_stage(const LaneArray X, const LaneA
     S = state_at(w);
     const double ul0 = w[2] + S.uL;
     ul_right = __shfl_down_sync(kFull, ul0, 1);
-    const double hG = hs * (V.ld1(0) - V.ld1(-1));
+    const double hG = hs * (V.ld2(0).x - V.ld2(-2).y);
     fp = lean_face(hG, ur_left, ul0, w[1], w[2]);
   }
   double Tprev = 0.0, Tc0 = 0.0, Tc1 = 0.0, Tc2 = 0.0;  // cotangents of the intervals (j0-3,j0-2) .. (j0,j0+1)
@@ -372,8 +383,8 @@ reverse_step_kernel(const RevParams p) {
   const double cdt = (0.25 * p.invdx) * dt;  // the forward flux is scaled by 4 (psk_fast_kernels.cuh)
 
   // ---- recomputation of the stage values (timestepping.py:314-317): P0 = u, P1 = k1, P2 = k2
-  rev_forward_stage<C, 1>(P0, P1, P0, cdt, eps9);
-  rev_forward_stage<C, 2>(P1, P2, P0, cdt, eps9);
+#pragma unroll 1
+  for (int st = 0; st < 2; ++st) rev_forward_stage<C>(st == 1, st == 0 ? P0 : P1, st == 0 ? P1 : P2, P0, cdt, eps9);
   if (p.dbg_k1 != nullptr) {
 #pragma unroll 1
     for (int j = 0; j < C; ++j) {
@@ -384,13 +395,18 @@ reverse_step_kernel(const RevParams p) {
       }
     }
   }
-  // ---- the three adjoint stages
+  // ---- the three adjoint stages (one body, executed three times)
+  //   ph 0: P0 = p';  lam2 = 2/3 (p' + dt J(k2)^T p') over k2 (P2), P0 = 1/3 p' + 3/4 lam2
+  //   ph 1:           lam1 = 1/4 (lam2 + dt J(k1)^T lam2) over k1 (P1)
+  //   ph 2: P2 = u (an L2 hit);  p = P0 + lam1 + dt J(u)^T lam1 over P0
   const double hs = 0.5 * p.invdx * dt;
-  rev_load_run<C>(p.pin, base, r0, n, inside, P0);                                        // P0 = p'
-  rev_adjoint_stage<C, 1>(P2, P0, P2, P0, 2.0 / 3.0, (2.0 / 3.0) * hs, eps9, park);       // P2 = lam2, P0 = 1/3 p' + 3/4 lam2
-  rev_adjoint_stage<C, 0>(P1, P2, P1, P0, 0.25, 0.25 * hs, eps9, park);                   // P1 = lam1
-  rev_load_run<C>(p.u, base, r0, n, inside, P2);                                          // P2 = u (an L2 hit)
-  rev_adjoint_stage<C, 2>(P2, P1, P0, P0, 1.0, hs, eps9, park);                           // P0 = p
+#pragma unroll 1
+  for (int ph = 0; ph < 3; ++ph) {
+    if (ph != 1) rev_load_run<C>(ph == 0 ? p.pin : p.u, base, r0, n, inside, ph == 0 ? P0 : P2);
+    const double cv = (ph == 0) ? (2.0 / 3.0) : ((ph == 1) ? 0.25 : 1.0);
+    const LaneArray X = (ph == 1) ? P1 : P2, V = (ph == 0) ? P0 : ((ph == 1) ? P2 : P1), OUT = (ph == 0) ? P2 : ((ph == 1) ? P1 : P0);
+    rev_adjoint_stage<C>(ph == 0 ? 1 : (ph == 1 ? 0 : 2), X, V, OUT, P0, cv, cv * hs, eps9, park);
+  }
 
   // ---- p of the stored window cells
   const int e0 = tile * Geo::kEmit + C * lane - kRevHalo;  // interior coordinate of the lane's first cell if stored

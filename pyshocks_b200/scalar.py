@@ -108,6 +108,11 @@ def _apply_boundary_kernel(bc: Boundary, grid: Any, t: ScalarLike, u: Array) -> 
 @apply_boundary.register(TwoSidedBoundary)
 def _apply_boundary_two_sided(bc: TwoSidedBoundary, grid: Any, t: ScalarLike, u: Array) -> Array:
     # scalar.py:375-382 (left then right; here one launch fills both sides)
+    if type(bc.left) is not type(bc.right):
+        # different kinds on the two sides: the reference applies them one after the other here, and raises
+        # NotImplementedError("Different boundaries on each side.") only where a scheme asks for
+        # bc.boundary_type (scalar.py:369-370) -- i.e. in numerical_flux / apply_operator, as this package does
+        return apply_boundary(bc.right, grid, t, apply_boundary(bc.left, grid, t, u))
     return _apply_boundary_kernel(bc, grid, t, u)
 
 

@@ -2,7 +2,8 @@
 
 In the reference these tables drive 18 small convolutions per right-hand side; here they are
 compiled into the kernels (``csrc/psk_math.cuh``).  The tables are kept for API parity and for
-the tests that pin the kernels' coefficients against them.
+the test that pins the kernels' coefficients against them
+(``tests/test_gpu_kernels.py::test_kernel_coefficients_are_those_of_the_stencil_tables``).
 """
 
 from __future__ import annotations

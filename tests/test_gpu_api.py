@@ -554,3 +554,30 @@ def test_burgers_esweno32_scheme_through_the_api(bc_name: str, math: str) -> Non
             hp.apply_operator_vjp(u, torch.ones_like(u))
     finally:
         config.set_math("fast")
+
+
+def test_mixed_kind_two_sided_boundary_like_the_reference() -> None:
+    """Dirichlet on the left, Neumann on the right: apply_boundary applies one side after the other
+    (scalar.py:375-382) and equals the two one-kind fills on their sides; a scheme asking for
+    bc.boundary_type raises NotImplementedError("Different boundaries on each side.") (scalar.py:369-370)."""
+    import pyshocks_b200 as ps
+    from pyshocks_b200 import burgers
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import (DirichletBoundary, NeumannBoundary, TwoSidedBoundary, make_dirichlet_boundary,
+                                      make_neumann_boundary)
+
+    grid = ps.make_uniform_cell_grid(a=-1.0, b=1.0, n=40, nghosts=3)
+    g = grid.nghosts
+    u = torch.sin(3.0 * grid.x) + 0.3
+    ga = lambda t, x: 0.25 + 0.0 * x + t  # noqa: E731
+    gb = lambda t: 0.7  # noqa: E731
+    mixed = TwoSidedBoundary(left=DirichletBoundary(side=-1, g=ga), right=NeumannBoundary(side=+1, g=gb))
+    w = ps.apply_boundary(mixed, grid, 0.5, u)
+    wd = ps.apply_boundary(make_dirichlet_boundary(ga), grid, 0.5, u)
+    wn = ps.apply_boundary(make_neumann_boundary(gb), grid, 0.5, u)
+    assert torch.equal(w[:g], wd[:g]) and torch.equal(w[g:-g], u[g:-g]) and torch.equal(w[-g:], wn[-g:])
+    with pytest.raises(NotImplementedError, match="Different boundaries"):
+        mixed.boundary_type
+    scheme = burgers.Rusanov(rec=make_reconstruction_from_name("wenojs53"))
+    with pytest.raises(NotImplementedError):
+        ps.apply_operator(scheme, grid, mixed, 0.5, u)

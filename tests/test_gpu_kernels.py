@@ -240,3 +240,41 @@ def test_host_to_host_pipelined_call_equals_device_resident_solve() -> None:
     torch.cuda.synchronize()
     i = slice(g, g + n)
     assert torch.equal(hout[:, i], ref[:, i])
+
+
+@pytest.mark.parametrize("name,g", [("wenojs32", 2), ("wenojs53", 3)])
+def test_kernel_coefficients_are_those_of_the_stencil_tables(name: str, g: int) -> None:
+    """The WENO-JS coefficients compiled into the kernels (csrc/psk_math.cuh) against the tables the package
+    exposes (pyshocks_b200/weno.py = pyshocks/weno.py:166-244), evaluated the way the reference evaluates them
+    (weno.py:114-157, :247-256: zero-padded "same" convolutions with the table rows): STRICT reconstruction
+    bit for bit away from the array ends, FAST to round-off."""
+    from pyshocks_b200 import weno
+    from pyshocks_b200.path import HotPath
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+
+    rec = make_reconstruction_from_name(name)
+    s = weno.weno_js_32_coefficients() if name == "wenojs32" else weno.weno_js_53_coefficients()
+    assert rec.s.c.shape == s.c.shape and np.array_equal(rec.s.d, s.d)
+    rng = np.random.default_rng(53)
+    x = np.linspace(0.0, 1.0, 97)
+    u = np.sin(2 * np.pi * x) + 0.3 * rng.standard_normal(x.size) * (x > 0.6)
+
+    def side(f: np.ndarray) -> np.ndarray:
+        beta = [sum(s.a[j] * np.convolve(f, s.b[i, j, :], mode="same") ** 2 for j in range(s.a.size))
+                for i in range(s.b.shape[0])]
+        alpha = [s.d[i, 0] / (rec.eps + beta[i]) ** 2 for i in range(len(beta))]
+        total = sum(alpha[1:], alpha[0])
+        return sum(((alpha[i] / total) * np.convolve(f, s.c[i, :], mode="same") for i in range(1, len(beta))),
+                   (alpha[0] / total) * np.convolve(f, s.c[0, :], mode="same"))
+
+    ur = side(u)
+    ul = side(u[::-1])[::-1]  # reconstruction.py:374-375
+    for math, tol in (("strict", 0.0), ("fast", 1.0e-14)):
+        hp = HotPath(equation="burgers", flux="rusanov", rec=name, bc="none", n=u.size - 2 * g, g=g, dx=1.0,
+                     eps=rec.eps, math=math)
+        gl, gr = (host(a) for a in hp.reconstruct(dev(u)))
+        i = slice(2, u.size - 2)  # the outermost cells see NumPy's BLAS summation order (DESIGN.md section 2)
+        if tol == 0.0:
+            assert np.array_equal(gl[i], ul[i]) and np.array_equal(gr[i], ur[i])
+        else:
+            assert max_rel(gl[i], ul[i]) < tol and max_rel(gr[i], ur[i]) < tol

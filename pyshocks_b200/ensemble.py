@@ -448,12 +448,58 @@ class AdjointEnsemble:
         return p
 
     def gradient_half_l2(self, u0: torch.Tensor | np.ndarray | None = None) -> tuple[torch.Tensor, torch.Tensor]:
-        """``J_b = 1/2 sum_i u_b(T)_i^2`` over the interior and ``dJ_b / du_b(0)`` for every row."""
+        """``J_b = 1/2 sum_i u_b(T)_i^2`` over the interior and ``dJ_b / du_b(0)`` for every row
+        (drivers/burgers-adjoint.py:296-315: forward sweep, then the adjoint sweep started from ``p(T) = u(T)``)."""
+        return self.gradient(u0)
+
+    def gradient(self, u0: torch.Tensor | np.ndarray | None = None,
+                 target: torch.Tensor | None = None) -> tuple[torch.Tensor, torch.Tensor]:
+        """``J_b = 1/2 sum_i (u_b(T)_i - target_b,i)^2`` over the interior (``target = None``: zero) and
+        ``dJ_b / du_b(0)``: one forward sweep onto the tape and one reverse sweep from ``p(T) = u(T) - target``."""
         s = self.s
         uT = self.forward(u0)
         g, n = s.g, s.n
-        J = 0.5 * (uT[:, g : g + n] ** 2).sum(dim=1)
         pT = self.lam1  # scratch until the sweep starts
         pT.zero_()
         pT[:, g : g + n] = uT[:, g : g + n]
+        if target is not None:
+            pT[:, g : g + n] -= target[:, g : g + n]
+        J = 0.5 * (pT[:, g : g + n] ** 2).sum(dim=1)
         return J, self.backward(pT)
+
+    def optimize(self, u0: torch.Tensor | np.ndarray, *, niter: int, step: float | torch.Tensor,
+                 target: torch.Tensor | None = None, callback=None) -> "OptimizeResult":
+        """The optimisation loop the adjoint drivers exist for (drivers/burgers-adjoint.py:269-315 run once per
+        iterate): ``niter`` steps of steepest descent on the initial condition,
+
+            u0 <- u0 - step * dJ/du0,    J = 1/2 ||u(T; u0) - target||^2  per row,
+
+        every iterate being one forward sweep onto the device tape and one reverse sweep (no host transfer
+        inside the loop; ``J`` is read back once at the end).  ``step``: a number or one value per row.
+        Returns the final initial conditions and the history of ``J`` (``niter + 1`` x batch: the last entry
+        is the objective of the returned iterate)."""
+        s = self.s
+        s.load(u0)
+        x = self.chk[0].new_empty(self.chk[0].shape)  # the iterate (forward() keeps its own copy in chk[0])
+        x.copy_(s.u)
+        g, n = s.g, s.n
+        step_t = step if isinstance(step, torch.Tensor) else torch.full((1,), float(step), dtype=torch.float64, device=x.device)
+        step_t = step_t.reshape(-1, 1)
+        hist = torch.zeros((niter + 1, s.batch), dtype=torch.float64, device=x.device)
+        for it in range(niter):
+            J, grad = self.gradient(x, target)
+            hist[it] = J
+            x[:, g : g + n] -= step_t * grad[:, g : g + n]
+            if callback is not None:
+                callback(it, J, grad)
+        uT = self.forward(x)
+        r = uT[:, g : g + n] if target is None else uT[:, g : g + n] - target[:, g : g + n]
+        hist[niter] = 0.5 * (r ** 2).sum(dim=1)
+        return OptimizeResult(u0=x, objective=hist.cpu().numpy(), iterations=niter)
+
+
+@dataclass
+class OptimizeResult:
+    u0: torch.Tensor  # (batch, nx) optimised initial conditions
+    objective: np.ndarray  # (iterations + 1, batch) history of J
+    iterations: int

@@ -117,3 +117,18 @@ def hash_key(key: str) -> int:
 def dirichlet_values(case: Case, t: float, xg: np.ndarray) -> np.ndarray:
     """Ghost-cell Dirichlet data g(t, x) used by the dirichlet cases."""
     return 0.2 + 0.1 * np.sin(3.0 * xg - 2.0 * t)
+
+
+STEPPERS = ("ForwardEuler", "RK44", "CKRK45")
+
+
+def stepper_cases() -> list[Case]:
+    """cases of ``steppers.npz``: one ``advance`` of every stepper besides SSPRK33; the Dirichlet cases
+    exercise the stage times ``t + c_i dt`` (the boundary data depend on time)"""
+    return [
+        Case("burgers", "rusanov", "wenojs53", "periodic", state="rough"),
+        Case("burgers", "lf", "wenojs53", "dirichlet", state="rough"),
+        Case("burgers", "eo", "wenojs32", "dirichlet", state="smooth"),
+        Case("advection", "godunov", "wenojs53", "dirichlet", velocity="varying", state="rough"),
+        Case("continuity", "godunov", "wenojs53", "periodic", velocity="varying", state="smooth"),
+    ]

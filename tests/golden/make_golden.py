@@ -18,6 +18,8 @@ Outputs (all small, committed):
 * ``rhs.npz``      apply_boundary, numerical_flux, apply_operator, predict_timestep
                    for every case of ``cases.rhs_cases()``
 * ``advance.npz``  one SSPRK33 ``advance`` per case (subset)
+* ``steppers.npz`` one ``advance`` of ForwardEuler / RK44 / CKRK45 (timestepping.py:289-405)
+                   for the cases of ``cases.stepper_cases()``
 * ``solve_c1.npz`` BASELINE config 1 (examples/burgers.py, N=256, t=1) for the
                    rusanov and lf schemes: dt history and final state
 * ``solve_c2.npz`` config-2 forward at reduced N (advection, Dirichlet, theta=.75)
@@ -175,6 +177,25 @@ def golden_rhs() -> tuple[dict[str, np.ndarray], dict[str, np.ndarray]]:
     return rhs, adv
 
 
+def golden_steppers() -> dict[str, np.ndarray]:
+    """timestepping.py:289-301 (ForwardEuler), :328-343 (RK44), :352-405 (CKRK45): one ``advance`` each"""
+    out: dict[str, np.ndarray] = {}
+    for case in C.stepper_cases():
+        scheme, grid, bc = build(case)
+        u = jnp.array(C.state_for(case))
+        dt = 0.3 * float(A(predict_timestep(scheme, grid, bc, case.t, u)))
+        out[f"{case.key}_u"] = A(u)
+        out[f"{case.key}_dt"] = np.float64(dt)
+        for name in C.STEPPERS:
+            stepper = getattr(timestepping, name)(
+                predict_timestep=lambda t_, u_: dt,
+                source=partial(apply_operator, scheme, grid, bc),
+                checkpoint=None,
+            )
+            out[f"{case.key}_{name}"] = A(timestepping.advance(stepper, dt, case.t, u))
+    return out
+
+
 def golden_solve_c1() -> dict[str, np.ndarray]:
     """examples/burgers.py:42-60,120-179 with -s rusanov|lf -r wenojs53 -n 256, tfinal=1."""
     out: dict[str, np.ndarray] = {}
@@ -325,10 +346,14 @@ def golden_adjoint() -> dict[str, np.ndarray]:
 
 def main() -> None:
     print("reference:", pyshocks.__file__)
+    if sys.argv[1:] == ["steppers"]:  # this file alone (the others are untouched by it)
+        np.savez_compressed(HERE / "steppers.npz", **golden_steppers())
+        return
     np.savez_compressed(HERE / "weno.npz", **golden_weno())
     rhs, adv = golden_rhs()
     np.savez_compressed(HERE / "rhs.npz", **rhs)
     np.savez_compressed(HERE / "advance.npz", **adv)
+    np.savez_compressed(HERE / "steppers.npz", **golden_steppers())
     np.savez_compressed(HERE / "solve_c1.npz", **golden_solve_c1())
     np.savez_compressed(HERE / "solve_c2.npz", **golden_solve_c2())
     np.savez_compressed(HERE / "adjoint.npz", **golden_adjoint())

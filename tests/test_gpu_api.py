@@ -581,3 +581,55 @@ def test_mixed_kind_two_sided_boundary_like_the_reference() -> None:
     scheme = burgers.Rusanov(rec=make_reconstruction_from_name("wenojs53"))
     with pytest.raises(NotImplementedError):
         ps.apply_operator(scheme, grid, mixed, 0.5, u)
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
+def test_other_steppers_match_reference_advance(math: str) -> None:
+    """ForwardEuler / RK44 / CKRK45 ``advance`` (timestepping.py:289-405) through the package API against the
+    vectors recorded from the reference (tests/golden/steppers.npz): every RHS of a stage is one fused
+    apply_operator launch, the combines are the reference's own array expressions, so STRICT results are
+    bit-identical on every cell away from the zero-padded array ends."""
+    from functools import partial
+
+    import cases as C
+    from common import load_golden, max_rel
+
+    import pyshocks_b200 as ps
+    import pyshocks_b200.timestepping as ts
+    from pyshocks_b200 import advection, burgers, config, continuity
+    from pyshocks_b200.reconstruction import make_reconstruction_from_name
+    from pyshocks_b200.scalar import PeriodicBoundary, make_dirichlet_boundary
+
+    G = load_golden("steppers")
+    config.set_math(math)
+    try:
+        for case in C.stepper_cases():
+            k = case.key
+            grid = ps.make_uniform_cell_grid(a=case.a, b=case.b, n=case.n, nghosts=case.g)
+            rec = make_reconstruction_from_name(case.rec)
+            if case.equation == "burgers":
+                scheme = burgers.make_scheme_from_name(case.flux, rec=rec, alpha=case.alpha)
+            else:
+                mod = advection if case.equation == "advection" else continuity
+                scheme = mod.make_scheme_from_name(case.flux, rec=rec, velocity=torch.from_numpy(C.velocity_for(case)).cuda())
+            if case.bc == "periodic":
+                bc = PeriodicBoundary()
+            else:
+                bc = make_dirichlet_boundary(
+                    ga=lambda t, x, case=case: torch.from_numpy(C.dirichlet_values(case, float(t), x.cpu().numpy())).to(x.device))
+            scheme = ps.bind(scheme, grid, bc)
+            u = torch.from_numpy(G[f"{k}_u"]).cuda()
+            dt = float(G[f"{k}_dt"])
+            for name in C.STEPPERS:
+                stepper = getattr(ts, name)(predict_timestep=lambda t_, u_: dt,
+                                            source=partial(ps.apply_operator, scheme, grid, bc), checkpoint=None)
+                out = ts.advance(stepper, dt, case.t, u).cpu().numpy()
+                ref = G[f"{k}_{name}"]
+                core = slice(case.g + 2, -(case.g + 2))
+                if math == "strict":
+                    assert np.array_equal(out[core], ref[core]), (k, name)
+                    assert max_rel(out, ref) < 1e-13, (k, name)
+                else:
+                    assert max_rel(out, ref) < 2e-13, (k, name)
+    finally:
+        config.set_math("fast")

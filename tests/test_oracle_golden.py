@@ -234,3 +234,17 @@ def test_adjoint_step_torch_twin_vs_reference(key: str) -> None:
     # of the SAME derivative differ at that level ("adjoint conditioning").
     tol = 1.0e-9 if ("burgers" in key and "wenojs53" in key and "periodic" not in key) else 1.0e-12
     assert max_rel(ps, ADJ[f"{key}_p"]) < tol
+
+
+@pytest.mark.parametrize("case", C.stepper_cases(), ids=lambda c: c.key)
+def test_other_steppers_numpy_oracle_bitwise(case: C.Case) -> None:
+    """ForwardEuler / RK44 / CKRK45 ``advance`` (timestepping.py:289-405) of the NumPy restatement against
+    the vectors recorded from the reference (steppers.npz); the Dirichlet cases cover the stage times."""
+    G = load_golden("steppers")
+    scheme, grid, bc = oracle_setup(case)
+    k = case.key
+    u, dt = G[f"{k}_u"], float(G[f"{k}_dt"])
+    assert np.array_equal(u, C.state_for(case))
+    for name in C.STEPPERS:
+        out = po.STEPPER_ADVANCE[name](lambda t, x: po.apply_operator(scheme, grid, bc, t, x), dt, case.t, u)
+        assert np.array_equal(out, G[f"{k}_{name}"]), name

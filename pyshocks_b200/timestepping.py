@@ -299,7 +299,10 @@ def _advance_rk44(stepper: RK44, dt: ScalarLike, t: ScalarLike, u: Array) -> Arr
     k2 = dt * fn(t + dt / 2, u + k1 / 2)
     k3 = dt * fn(t + dt / 2, u + k2 / 2)
     k4 = dt * fn(t + dt, u + k3)
-    return u + (k1 + 2 * k2 + 2 * k3 + k4) / 6
+    # a true division: torch divides a CUDA tensor by a Python scalar as a multiplication by its reciprocal,
+    # which is not the reference's `/ 6` in the last bit
+    six = torch.full((), 6.0, dtype=u.dtype, device=u.device)
+    return u + torch.div(k1 + 2 * k2 + 2 * k3 + k4, six)
 
 
 @dataclass(frozen=True)

@@ -120,6 +120,7 @@ def _load() -> ct.CDLL:
         "psk_halo_push": ([vp, vp, vp, vp, i32, vp, vp, i64, vp], ct.c_int),
         "psk_halo_wait": ([vp, vp, i64, i64, vp, vp], ct.c_int),
         "psk_ssprk33_stage_p2p": ([D, ct.c_int, vp, vp, vp, vp, vp, ct.POINTER(PskHaloLink), vp], ct.c_int),
+        "psk_ssprk33_step_p2p": ([D, vp, vp, vp, vp, ct.POINTER(PskHaloLink), vp], ct.c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here = the library is stale: rebuild it
@@ -140,7 +141,7 @@ EXPORTS = (
     "psk_reconstruct", "psk_numerical_flux", "psk_apply_operator", "psk_max_abs",
     "psk_ssprk33_stage", "psk_ssprk33_step", "psk_ssprk33_step_stages", "psk_ssprk33_step_adjoint", "psk_set_reverse_variant", "psk_step_control", "psk_solve_rows", "psk_dfma_probe", "psk_apply_operator_vjp",
     "psk_ssprk33_stage_adjoint", "psk_p2p_alloc", "psk_p2p_free", "psk_p2p_open", "psk_p2p_close",
-    "psk_halo_push", "psk_halo_wait", "psk_ssprk33_stage_p2p",
+    "psk_halo_push", "psk_halo_wait", "psk_ssprk33_stage_p2p", "psk_ssprk33_step_p2p",
 )
 
 

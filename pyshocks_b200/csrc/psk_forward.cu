@@ -1046,6 +1046,128 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
   return PSK_OK;
 }
 
+// ---------------------------------------------------------------------------
+// The whole-step kernel FUSED with the ghost-cell exchange of a slab-decomposed grid (one row per
+// GPU, boundary kind NONE, 9 ghost cells per side: the three stages of a step reach 9 cells beyond
+// the slab): ONE launch per step and nothing else on the exchange path.
+//   * the two warps whose windows reach into ghost cells (chunk 0 and the last chunk; the host makes
+//     sure that the last chunk holds at least 10 cells, so it is the only one on its side) spin on
+//     the LOCAL epoch flags until the neighbours' edge cells of the current state have arrived --
+//     every other warp of the grid starts at once, the NVLink round trip hides behind the interior;
+//   * ghost cells are read with ld.volatile;
+//   * the lanes that store the slab's first / last 9 cells also store them into the left / right
+//     neighbour's ghost slots of the array the new state lives in, then one lane of the warp raises
+//     that neighbour's flag to epoch + 1 (stores, __threadfence_system, __syncwarp, st.release.sys).
+// No write-after-read hazard: the neighbour last read those ghost slots one step ago, in the very warp
+// whose push of that step this warp has just waited for.  Arithmetic: step_stage_rhs, i.e. the bits of
+// step_warp_fused_kernel and of three stage launches.
+template <int R, int FLUX, bool WITH_MAX, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+step_warp_fused_p2p_kernel(const StepParams p, const HaloLink h) {
+  using Geo = StepGeometry<R>;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (chunk >= p.chunks_per_row) return;
+  const int n = p.n, g = p.g;
+  const int c0 = chunk * Geo::kEmit - Geo::kSkip + R * lane;
+  const bool inside = (c0 >= 0) && (c0 + R <= n);
+  const int64_t base = g;
+  const bool edge_lo = (chunk == 0), edge_hi = (chunk == p.chunks_per_row - 1);
+  const long long epoch = h.wait_epoch;
+  if (edge_lo && h.wait_lo != nullptr) halo_spin(h.wait_lo, epoch, h.timeout_ns, h.timed_out);
+  if (edge_hi && h.wait_hi != nullptr) halo_spin(h.wait_hi, epoch, h.timeout_ns, h.timed_out);
+  const int wc0 = R * lane;
+  bool st[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    st[r] = (wc0 + r >= Geo::kSkip) && (wc0 + r < Geo::kWindow - Geo::kSkip) && (c0 + r >= 0) && (c0 + r < n);
+  double u0[R];
+  if (inside) {
+#pragma unroll
+    for (int r = 0; r < R; r += 2) {
+      const double2 q = *reinterpret_cast<const double2 *>(p.u + base + c0 + r);
+      u0[r] = q.x;
+      u0[r + 1] = q.y;
+    }
+  } else {
+    const volatile double *urow = p.u;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int c = c0 + r;
+      u0[r] = (c >= -g && c < n + g) ? urow[base + c] : 0.0;
+    }
+  }
+  const double cdt = p.coef * p.dt[0];
+  double a[R], dF[R];
+  step_stage_rhs<R, FLUX>(u0, p.eps9, dF);
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);
+  step_stage_rhs<R, FLUX>(a, p.eps9, dF);
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);
+  step_stage_rhs<R, FLUX>(a, p.eps9, dF);
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);
+  step_store<R>(p.uout + base + c0, inside, st, a);
+  // ---- the slab's first / last 9 cells go to the neighbours' ghost slots, then their flags
+  if (edge_lo && h.peer_lo != nullptr) {
+    bool wrote = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r] && c0 + r < 9) {
+        h.peer_lo[c0 + r] = a[r];
+        wrote = true;
+      }
+    if (wrote) __threadfence_system();
+    __syncwarp(kFull);
+    if (lane == 0) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_lo), "l"(epoch + 1) : "memory");
+    }
+  }
+  if (edge_hi && h.peer_hi != nullptr) {
+    bool wrote = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r] && c0 + r >= n - 9) {
+        h.peer_hi[c0 + r - (n - 9)] = a[r];
+        wrote = true;
+      }
+    if (wrote) __threadfence_system();
+    __syncwarp(kFull);
+    if (lane == 0) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_hi), "l"(epoch + 1) : "memory");
+    }
+  }
+  if (WITH_MAX) {
+    unsigned long long mx = 0ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r]) {
+        const unsigned long long b = abs_bits(a[r]);
+        mx = b > mx ? b : mx;
+      }
+    mx = warp_max_bits(mx);
+    if (lane == 0) atomicMax(p.maxabs, mx);
+  }
+}
+
+template <int FLUX>
+int launch_step_p2p(const StepParams &q, const HaloLink &h, bool with_max, cudaStream_t st) {
+  constexpr int kThreads = 128, kMinB = 3;
+  int wpc = kThreads / 32;
+  if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
+  const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
+  if (with_max)
+    step_warp_fused_p2p_kernel<6, FLUX, true, kThreads, kMinB><<<gx, wpc * 32, 0, st>>>(q, h);
+  else
+    step_warp_fused_p2p_kernel<6, FLUX, false, kThreads, kMinB><<<gx, wpc * 32, 0, st>>>(q, h);
+  PSK_CUDA_OK(cudaGetLastError());
+  return PSK_OK;
+}
+
 int launch_step_fused(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
                       const uint8_t *active, double *maxabs, cudaStream_t st, double *k1_out = nullptr,
                       double *k2_out = nullptr) {
@@ -1345,6 +1467,49 @@ int psk_ssprk33_stage_p2p(const psk_desc *d, int stage, const double *u0, const 
 #undef PSK_P2P_LAUNCH
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
+}
+
+int psk_ssprk33_step_p2p(const psk_desc *d, const double *u, double *uout, const double *dt, double *maxabs,
+                         const psk_halo_link *link, psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (link == nullptr || u == nullptr || uout == nullptr || dt == nullptr || uout == u || link->timeout_ns <= 0)
+    return PSK_E_INVALID;
+  if ((link->peer_lo != nullptr && link->flag_lo == nullptr) || (link->peer_hi != nullptr && link->flag_hi == nullptr))
+    return PSK_E_INVALID;
+  if (link->epoch_in != nullptr || link->epoch_out != nullptr) return PSK_E_UNSUPPORTED;  // no graph replay here
+  const bool aligned = (reinterpret_cast<uintptr_t>(u + d->g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0);
+  const bool flux_ok = d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER;
+  constexpr int kEmit = StepGeometry<6>::kEmit;
+  const int chunks = (d->n + kEmit - 1) / kEmit;
+  // the last chunk must hold the slab's last 9 cells AND be the only one whose window reaches the right ghosts
+  const bool one_edge_chunk = d->n - (chunks - 1) * kEmit >= 10;
+  if (d->equation != PSK_EQ_BURGERS || !flux_ok || d->rec != PSK_REC_WENOJS53 || d->math != PSK_MATH_FAST ||
+      d->nu != nullptr || d->bc != PSK_BC_NONE || d->batch != 1 || d->g != 9 || d->n < 18 || !aligned || !one_edge_chunk)
+    return PSK_E_UNSUPPORTED;
+  StepParams q{};
+  q.u = u; q.uout = uout; q.dt = dt;
+  q.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
+  q.ld = d->ld;
+  q.coef = (1.0 / d->dx) / (d->flux == PSK_FLUX_RUSANOV ? 4.0 : 2.0);
+  q.eps9 = d->eps * (1.0 / 9.0);
+  q.n = d->n; q.g = d->g; q.bc_none = 1;
+  q.chunks_per_row = chunks;
+  HaloLink h{};
+  h.wait_lo = reinterpret_cast<const long long *>(link->wait_lo);
+  h.wait_hi = reinterpret_cast<const long long *>(link->wait_hi);
+  h.wait_epoch = link->wait_epoch;
+  h.peer_lo = link->peer_lo;
+  h.peer_hi = link->peer_hi;
+  h.flag_lo = reinterpret_cast<long long *>(link->flag_lo);
+  h.flag_hi = reinterpret_cast<long long *>(link->flag_hi);
+  h.timeout_ns = static_cast<unsigned long long>(link->timeout_ns);
+  h.timed_out = link->timed_out;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->flux == PSK_FLUX_UPWIND) return launch_step_p2p<PSK_FLUX_UPWIND>(q, h, maxabs != nullptr, st);
+  if (d->flux == PSK_FLUX_ENGQUIST_OSHER) return launch_step_p2p<PSK_FLUX_ENGQUIST_OSHER>(q, h, maxabs != nullptr, st);
+  return launch_step_p2p<PSK_FLUX_RUSANOV>(q, h, maxabs != nullptr, st);
 }
 
 int psk_apply_operator(const psk_desc *d, const double *u, double *rhs, double *lf_work,

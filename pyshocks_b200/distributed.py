@@ -368,7 +368,7 @@ class PeerSlabSolver:
     def __init__(self, *, n_global: int, rank: int, world: int, dx: float, flux: str = "rusanov",
                  rec: str = "wenojs53", eps: float = 1.0e-12, math: str = "fast", edge: int = 7680,
                  overlap: bool = True, fused: bool | None = None, device: torch.device | str | None = None,
-                 timeout_s: float = 20.0, whole_step: bool = False) -> None:
+                 timeout_s: float = 20.0, whole_step: bool = False, fused_step: bool | None = None) -> None:
         if flux == "lf":
             raise ValueError("slab decomposition does not support the global Lax-Friedrichs flux (use rusanov)")
         self.rank, self.world = rank, world
@@ -385,6 +385,12 @@ class PeerSlabSolver:
                 raise ValueError("whole_step and the per-stage fused exchange exclude each other")
             self.g = g = 9
             fused, overlap = False, False
+        elif fused_step:
+            raise ValueError("fused_step is a mode of whole_step")
+        # fused_step (whole_step only; None: wherever psk_ssprk33_step_p2p covers the slab): the 9-cell exchange
+        # lives INSIDE the whole-step kernel -- one launch per step instead of wait / step / push
+        self.fused_step = self.whole and (fused_step is None or bool(fused_step))
+        self._fused_step_required = bool(fused_step)
         self._cur = 0  # array of the store that holds the state (whole_step: 0 or 1)
         if self.n_local < 2 * g:
             raise ValueError("slabs must hold at least 2 g cells")
@@ -556,6 +562,12 @@ class PeerSlabSolver:
             # -> push the new state's edge cells into the neighbours' ghost slots of the OTHER array
             # (they last read those slots one step ago, before the push this wait has just seen)
             s = self.solver
+            if self.fused_step:
+                if self._step_fused_exchange(dt, maxabs):
+                    return
+                if self._fused_step_required:
+                    raise RuntimeError("psk_ssprk33_step_p2p does not cover this slab (its last chunk of 172 cells holds fewer than 10)")
+                self.fused_step = False  # this slab length: wait / step / push from now on
             self._wait()
             if not s.hp.step_fused(s.u, s.k1, dt, maxabs=maxabs):
                 raise RuntimeError("psk_ssprk33_step does not cover this slab configuration")
@@ -566,6 +578,32 @@ class PeerSlabSolver:
             return
         for stage in (1, 2, 3):
             self.run_stage(stage, dt, maxabs)
+
+    def _step_fused_exchange(self, dt: torch.Tensor, maxabs: torch.Tensor | None) -> bool:
+        """One launch: whole step + 9-cell exchange (``psk_ssprk33_step_p2p``); ``False`` if unsupported."""
+        import ctypes as ct
+
+        s, r = self.solver, self.ring
+        hp = s.hp
+        nxt = self._cur ^ 1
+        link = L.PskHaloLink()
+        link.wait_lo, link.wait_hi, link.wait_epoch = r.my_flags[0], r.my_flags[1], self.epoch
+        link.peer_lo, link.peer_hi = r.dst_lo[nxt], r.dst_hi[nxt]
+        link.flag_lo, link.flag_hi = r.flag_lo, r.flag_hi
+        link.timeout_ns, link.timed_out = self.timeout_ns, L.raw_ptr(self.timed_out)
+        batch, ld = hp._state(s.u)
+        d = hp.desc(batch, ld)
+        rc = L.lib().psk_ssprk33_step_p2p(ct.byref(d), L.ptr(s.u), L.ptr(s.k1), L.ptr(dt), L.ptr(maxabs), ct.byref(link),
+                                          L.stream_ptr())
+        if rc == L.E_UNSUPPORTED:
+            return False
+        L.check("psk_ssprk33_step_p2p", rc)
+        s.u, s.k1 = s.k1, s.u
+        self._cur = nxt
+        self.epoch += 1
+        self.exchanges += 1
+        self.launches += 1
+        return True
 
     def join(self) -> None:
         """Main stream waits for the edge stream (before anything else reads the state)."""

@@ -105,9 +105,11 @@ def test_peer_memory_slabs_equal_undecomposed(world: int, mode: str) -> None:
 
 @pytest.mark.parametrize("flux", ["rusanov", "eo"])
 @pytest.mark.parametrize("world,n,nsteps", [(1, 6151, 5), (2, 6151, 8), (3, 4099, 7), (4, 500, 6)])
-def test_whole_step_slabs_equal_undecomposed(world: int, n: int, nsteps: int, flux: str) -> None:
+@pytest.mark.parametrize("fused_step", [False, True])
+def test_whole_step_slabs_equal_undecomposed(world: int, n: int, nsteps: int, flux: str, fused_step: bool) -> None:
     """whole_step=True: ONE launch (psk_ssprk33_step on a slab with 9 ghost cells) and ONE exchange of 9
-    cells per side per step, every slab held by this process: bit-identical to the periodic solve"""
+    cells per side per step, every slab held by this process: bit-identical to the periodic solve.
+    fused_step: the exchange lives inside the kernel (psk_ssprk33_step_p2p), one launch per step in all."""
     from pyshocks_b200.distributed import PeerRing, PeerSlabSolver
     from pyshocks_b200.ensemble import EnsembleSolver
 
@@ -120,8 +122,11 @@ def test_whole_step_slabs_equal_undecomposed(world: int, n: int, nsteps: int, fl
     single.solve_fixed_dt(torch.from_numpy(u0).cuda(), dt, nsteps)
     ref = single.u[0, g : g + n]
     ug = torch.from_numpy(_ic(n, g)).cuda()
-    slabs = [PeerSlabSolver(n_global=n, rank=r, world=world, dx=3.0 / n, flux=flux, whole_step=True, timeout_s=5.0)
+    slabs = [PeerSlabSolver(n_global=n, rank=r, world=world, dx=3.0 / n, flux=flux, whole_step=True, timeout_s=5.0,
+                            fused_step=None if fused_step else False)
              for r in range(world)]
+    # psk_ssprk33_step_p2p needs the slab's last chunk of 172 cells to hold at least 10
+    covered = [s.n_local - ((s.n_local + 171) // 172 - 1) * 172 >= 10 for s in slabs]
     try:
         assert all(s.whole and s.g == 9 and not s.fused and not s.split for s in slabs)
         for r, s in enumerate(slabs):
@@ -137,7 +142,10 @@ def test_whole_step_slabs_equal_undecomposed(world: int, n: int, nsteps: int, fl
             s.check()
         out = torch.cat([s.interior() for s in slabs])
         assert torch.equal(out, ref)
-        assert all(s.exchanges == nsteps + 1 and s.launches == 3 * nsteps + 1 for s in slabs)
+        for s, cov in zip(slabs, covered):
+            one_launch = fused_step and cov
+            assert s.fused_step == one_launch
+            assert s.exchanges == nsteps + 1 and s.launches == (1 if one_launch else 3) * nsteps + 1
     finally:
         for s in slabs:
             s.ring = None
@@ -299,6 +307,17 @@ def _nccl_worker(rank: int, world: int, port: int, out: dict) -> None:
                 ps._graph = None
             ps.close()
             mark(f"peer slabs {mode} ok={ok}")
+        # whole step per launch on slabs with 9 ghost cells: wait / step / push, and the exchange inside the kernel
+        for fused_step in (False, None):
+            ps = PeerSlabSolver(n_global=n, rank=rank, world=world, dx=3.0 / n, whole_step=True, fused_step=fused_step)
+            ps.connect()
+            ps.load_interior(ug[ps.first : ps.first + ps.n_local])
+            ps.solve_fixed_dt(dt, nsteps)
+            ps.check()
+            ok = ok and torch.equal(ps.interior(), ref[ps.first : ps.first + ps.n_local])
+            ok = ok and ps.launches == (1 if ps.fused_step else 3) * nsteps + 1
+            mark(f"whole-step slabs fused_step={ps.fused_step} launches={ps.launches} ok={ok}")
+            ps.close()
         # adaptive dt: every rank takes the same dt sequence as the single-GPU adaptive solve.  The
         # single-array solver runs the general kernel (row mask), the slabs the specialised one: two FAST
         # implementations agree to a few ulp per step, the STRICT ones bit for bit; the two slab

@@ -570,9 +570,7 @@ def measure_slab(ctx: Ctx, args: argparse.Namespace, *, n_global: int, transport
     if transport == "nccl":
         slab = SlabSolver(n_global=n_global, ring=DistRing(), dx=h, device=dev)
     else:
-        kw = {}
-        if transport == "p2p-step-fused":
-            kw["fused_step"] = True
+        kw = {"fused_step": transport == "p2p-step-fused"} if whole else {}
         slab = PeerSlabSolver(n_global=n_global, rank=rank, world=world, dx=h, device=dev, whole_step=whole,
                               overlap=(transport == "p2p-overlap"), fused=(transport == "p2p"), **kw)
         if world > 1:
@@ -817,7 +815,7 @@ def main() -> None:
                     help="all = the headline ensemble + the slab / adjoint sub-records (default); slab / adjoint = "
                          "BASELINE configs 4 and 5 alone")
     ap.add_argument("--transport", choices=("p2p", "p2p-overlap", "p2p-serial", "p2p-step", "p2p-step-fused", "nccl"),
-                    default="p2p-step", help="ghost-cell exchange of the slab workload")
+                    default="p2p-step-fused", help="ghost-cell exchange of the slab workload")
     ap.add_argument("--graph", action="store_true", help="slab workload, fused transport: replay a CUDA graph of two steps")
     ap.add_argument("--cells", type=int, default=0, help="override the cell count of the slab / adjoint workloads")
     ap.add_argument("--gpus", type=int, default=1)

@@ -328,8 +328,8 @@ int psk_ssprk33_stage_p2p(const psk_desc *d, int stage, const double *u0, const 
  * cells of uout also store them to link->peer_lo / peer_hi (the neighbours' ghost slots of the array the
  * new state lives in, mapped with psk_p2p_open) and raise link->flag_lo / flag_hi to wait_epoch + 1.
  * epoch_in / epoch_out must be NULL.  Same bits as psk_ssprk33_step.  PSK_E_UNSUPPORTED outside Burgers +
- * {Rusanov (nu = 1), upwind, Engquist-Osher} + WENO-JS5 + FAST math, or when the slab's last chunk of 172
- * cells holds fewer than 10 (callers fall back to psk_halo_wait -> psk_ssprk33_step -> psk_halo_push). */
+ * {Rusanov (nu = 1), upwind, Engquist-Osher} + WENO-JS5 + FAST math, or for slabs shorter than 344 cells
+ * (callers fall back to psk_halo_wait -> psk_ssprk33_step -> psk_halo_push). */
 int psk_ssprk33_step_p2p(const psk_desc *d, const double *u, double *uout, const double *dt, double *maxabs,
                          const psk_halo_link *link, psk_stream_t stream);
 

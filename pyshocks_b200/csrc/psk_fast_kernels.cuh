@@ -443,6 +443,7 @@ struct StepParams {
   int n, g;
   int bc_none;  // 1: window cells beyond the row ends are the row's stored ghost cells (slab of a larger grid, g >= 9)
   double *k1_out, *k2_out;  // STAGES kernels only: the stage values are stored too (uout may then be NULL)
+  int shift;                // step_warp_fused_p2p_kernel only: the chunk grid starts this many cells left of the slab
 };
 
 template <int R>

@@ -488,8 +488,9 @@ struct HaloLink {
   long long *epoch_out;
 };
 
-__device__ __forceinline__ void halo_spin(const long long *flag, long long epoch, unsigned long long timeout_ns,
-                                          int *timed_out) {
+// (not inlined: the spin loop, its timer and its sleep stay out of the register allocation of the kernels)
+__device__ __noinline__ void halo_spin(const long long *flag, long long epoch, unsigned long long timeout_ns,
+                                       int *timed_out) {
   unsigned long long t0 = 0ull;
   bool timing = false;
   while (true) {
@@ -1061,16 +1062,32 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
 // No write-after-read hazard: the neighbour last read those ghost slots one step ago, in the very warp
 // whose push of that step this warp has just waited for.  Arithmetic: step_stage_rhs, i.e. the bits of
 // step_warp_fused_kernel and of three stage launches.
+// the cells `mask` selects among a lane's six go to dst[0..5]; then (whole warp) the neighbour's flag is raised
+__device__ __noinline__ void step_push_edge(double *dst, long long *flag, long long next_epoch, unsigned mask, int lane,
+                                            double a0, double a1, double a2, double a3, double a4, double a5) {
+  const double a[6] = {a0, a1, a2, a3, a4, a5};
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+    if (mask & (1u << r)) dst[r] = a[r];
+  if (mask != 0u) __threadfence_system();
+  __syncwarp(0xffffffffu);
+  if (lane == 0) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(flag), "l"(next_epoch) : "memory");
+  }
+}
+
 template <int R, int FLUX, bool WITH_MAX, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 step_warp_fused_p2p_kernel(const StepParams p, const HaloLink h) {
   using Geo = StepGeometry<R>;
-  constexpr unsigned kFull = 0xffffffffu;
+  static_assert(R == 6, "step_push_edge takes six cells");
   const int lane = threadIdx.x & 31;
   const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (chunk >= p.chunks_per_row) return;
   const int n = p.n, g = p.g;
-  const int c0 = chunk * Geo::kEmit - Geo::kSkip + R * lane;
+  // p.shift: the chunk grid starts `shift` cells left of the slab, so that BOTH end chunks hold >= 10 cells
+  const int c0 = chunk * Geo::kEmit - Geo::kSkip - p.shift + R * lane;
   const bool inside = (c0 >= 0) && (c0 + R <= n);
   const int64_t base = g;
   const bool edge_lo = (chunk == 0), edge_hi = (chunk == p.chunks_per_row - 1);
@@ -1112,34 +1129,18 @@ step_warp_fused_p2p_kernel(const StepParams p, const HaloLink h) {
   step_store<R>(p.uout + base + c0, inside, st, a);
   // ---- the slab's first / last 9 cells go to the neighbours' ghost slots, then their flags
   if (edge_lo && h.peer_lo != nullptr) {
-    bool wrote = false;
+    unsigned mask = 0u;
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      if (st[r] && c0 + r < 9) {
-        h.peer_lo[c0 + r] = a[r];
-        wrote = true;
-      }
-    if (wrote) __threadfence_system();
-    __syncwarp(kFull);
-    if (lane == 0) {
-      __threadfence_system();
-      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_lo), "l"(epoch + 1) : "memory");
-    }
+      if (st[r] && c0 + r < 9) mask |= 1u << r;
+    step_push_edge(h.peer_lo + c0, h.flag_lo, epoch + 1, mask, lane, a[0], a[1], a[2], a[3], a[4], a[5]);
   }
   if (edge_hi && h.peer_hi != nullptr) {
-    bool wrote = false;
+    unsigned mask = 0u;
 #pragma unroll
     for (int r = 0; r < R; ++r)
-      if (st[r] && c0 + r >= n - 9) {
-        h.peer_hi[c0 + r - (n - 9)] = a[r];
-        wrote = true;
-      }
-    if (wrote) __threadfence_system();
-    __syncwarp(kFull);
-    if (lane == 0) {
-      __threadfence_system();
-      asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(h.flag_hi), "l"(epoch + 1) : "memory");
-    }
+      if (st[r] && c0 + r >= n - 9) mask |= 1u << r;
+    step_push_edge(h.peer_hi + (c0 - (n - 9)), h.flag_hi, epoch + 1, mask, lane, a[0], a[1], a[2], a[3], a[4], a[5]);
   }
   if (WITH_MAX) {
     unsigned long long mx = 0ull;
@@ -1482,9 +1483,13 @@ int psk_ssprk33_step_p2p(const psk_desc *d, const double *u, double *uout, const
                        (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0);
   const bool flux_ok = d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER;
   constexpr int kEmit = StepGeometry<6>::kEmit;
-  const int chunks = (d->n + kEmit - 1) / kEmit;
-  // the last chunk must hold the slab's last 9 cells AND be the only one whose window reaches the right ghosts
-  const bool one_edge_chunk = d->n - (chunks - 1) * kEmit >= 10;
+  // each end chunk must hold the slab's 9 edge cells AND be the only one whose window reaches the ghost cells on
+  // its side, i.e. hold at least 10 cells: if the plain chunk grid leaves fewer in the last chunk, the grid is
+  // shifted left by half a chunk (first chunk 86 cells, last chunk r + 86)
+  const int rem = d->n % kEmit;
+  const int shift = (rem == 0 || rem >= 10) ? 0 : kEmit / 2;
+  const int chunks = (d->n + shift + kEmit - 1) / kEmit;
+  const bool one_edge_chunk = d->n >= 2 * kEmit;
   if (d->equation != PSK_EQ_BURGERS || !flux_ok || d->rec != PSK_REC_WENOJS53 || d->math != PSK_MATH_FAST ||
       d->nu != nullptr || d->bc != PSK_BC_NONE || d->batch != 1 || d->g != 9 || d->n < 18 || !aligned || !one_edge_chunk)
     return PSK_E_UNSUPPORTED;
@@ -1496,6 +1501,7 @@ int psk_ssprk33_step_p2p(const psk_desc *d, const double *u, double *uout, const
   q.eps9 = d->eps * (1.0 / 9.0);
   q.n = d->n; q.g = d->g; q.bc_none = 1;
   q.chunks_per_row = chunks;
+  q.shift = shift;
   HaloLink h{};
   h.wait_lo = reinterpret_cast<const long long *>(link->wait_lo);
   h.wait_hi = reinterpret_cast<const long long *>(link->wait_hi);

@@ -566,7 +566,7 @@ class PeerSlabSolver:
                 if self._step_fused_exchange(dt, maxabs):
                     return
                 if self._fused_step_required:
-                    raise RuntimeError("psk_ssprk33_step_p2p does not cover this slab (its last chunk of 172 cells holds fewer than 10)")
+                    raise RuntimeError("psk_ssprk33_step_p2p does not cover this slab (shorter than 344 cells)")
                 self.fused_step = False  # this slab length: wait / step / push from now on
             self._wait()
             if not s.hp.step_fused(s.u, s.k1, dt, maxabs=maxabs):

@@ -104,7 +104,8 @@ def test_peer_memory_slabs_equal_undecomposed(world: int, mode: str) -> None:
 
 
 @pytest.mark.parametrize("flux", ["rusanov", "eo"])
-@pytest.mark.parametrize("world,n,nsteps", [(1, 6151, 5), (2, 6151, 8), (3, 4099, 7), (4, 500, 6)])
+@pytest.mark.parametrize("world,n,nsteps", [(1, 6151, 5), (2, 6151, 8), (3, 4099, 7), (4, 500, 6), (2, 2 * 172 * 9 + 8, 6),
+                                            (1, 172 * 4 + 3, 5)])
 @pytest.mark.parametrize("fused_step", [False, True])
 def test_whole_step_slabs_equal_undecomposed(world: int, n: int, nsteps: int, flux: str, fused_step: bool) -> None:
     """whole_step=True: ONE launch (psk_ssprk33_step on a slab with 9 ghost cells) and ONE exchange of 9
@@ -125,8 +126,8 @@ def test_whole_step_slabs_equal_undecomposed(world: int, n: int, nsteps: int, fl
     slabs = [PeerSlabSolver(n_global=n, rank=r, world=world, dx=3.0 / n, flux=flux, whole_step=True, timeout_s=5.0,
                             fused_step=None if fused_step else False)
              for r in range(world)]
-    # psk_ssprk33_step_p2p needs the slab's last chunk of 172 cells to hold at least 10
-    covered = [s.n_local - ((s.n_local + 171) // 172 - 1) * 172 >= 10 for s in slabs]
+    # psk_ssprk33_step_p2p needs slabs of at least two chunks of 172 cells
+    covered = [s.n_local >= 344 for s in slabs]
     try:
         assert all(s.whole and s.g == 9 and not s.fused and not s.split for s in slabs)
         for r, s in enumerate(slabs):

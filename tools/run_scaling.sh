@@ -23,8 +23,11 @@ run() {  # run <bench args...>
 }
 run --transport p2p-step-fused --steps 20 --warmup 5
 run --transport p2p-step --steps 20 --warmup 5
+run --transport p2p --steps 20 --warmup 5
 for cells in 134217728 16777216 1048576; do
-  for tr in p2p-step-fused p2p-step p2p nccl; do
+  for tr in p2p-step-fused p2p nccl; do
     run --transport $tr --cells $cells --steps 100 --warmup 10
   done
 done
+run --transport p2p-step --cells 16777216 --steps 100 --warmup 10
+run --transport p2p-step --cells 1048576 --steps 100 --warmup 10

@@ -235,6 +235,31 @@ int psk_solve_rows(const psk_desc *d, double *u, int adaptive, double theta, dou
                    double tfinal, double fixed_dt, int max_steps, double *t_out,
                    int32_t *steps_out, double *dt_hist, double *tape, psk_stream_t stream);
 
+/* psk_solve_rows for step sizes and boundary data that are known in advance but change from step to step:
+ * `nsteps` steps with dt_table[m] (device, [nsteps]) -- e.g. the state-independent time step of the advection
+ * and continuity schemes clamped at tfinal (timestepping.py:139-142 with advection/schemes.py:51-59) -- and, if
+ * ghost_table != NULL, the Dirichlet / Neumann data of step m at the stage times t, t + dt, t + dt / 2
+ * (timestepping.py:314-319: what the user's g(t, x) returns, evaluated by the caller) as
+ * ghost_table[(3 m + stage) * block + ...], block = 2 g (d->ghost_ld == 0: shared by all rows) or
+ * batch * d->ghost_ld.  drivers/advection-adjoint.py (BASELINE config 2) in one launch.  tape as above. */
+int psk_solve_rows_tables(const psk_desc *d, double *u, int nsteps, const double *dt_table,
+                          const double *ghost_table, double *t_out, int32_t *steps_out, double *tape,
+                          psk_stream_t stream);
+
+/* The whole reverse sweep of adjoint_step (timestepping.py:155-215) in ONE call, from the tape of
+ * psk_solve_rows / psk_solve_rows_tables (state m at tape + m * tape_stride): for m = nsteps - 1 .. 0
+ *     p <- (d advance(dt_m, t_m, u_m) / d u)^T p,   then   p <- apply_boundary(pbc, p)   (pbc != NULL)
+ * with the kernels of psk_ssprk33_stage (recomputation of k1, k2, ghost rows included) and
+ * psk_ssprk33_stage_adjoint, enqueued back to back (6 launches per step, no host round trip).
+ * dt_table, ghost_table as in psk_solve_rows_tables.  pbc: descriptor of the boundary condition imposed on the
+ * adjoint variable after every step (the apply_boundary argument of adjoint_step; its data must not depend on
+ * time), same n, g, batch, ld as d.  p [batch][ld]: in p(T) (already passed through pbc), out p(0).
+ * states: scratch, 5 state arrays; work / lf_work as in psk_ssprk33_stage_adjoint / psk_ssprk33_stage.
+ * p_hist: optional [nsteps][batch][ld], p after step m (every AdjointStepCompleted.p). */
+int psk_ssprk33_adjoint_sweep(const psk_desc *d, const double *tape, int64_t tape_stride, int nsteps,
+                              const double *dt_table, const double *ghost_table, const psk_desc *pbc, double *p,
+                              double *states, double *work, double *lf_work, double *p_hist, psk_stream_t stream);
+
 /* FP64 peak probe for the roofline (not part of the reference-facing surface): ctas x 256 threads,
  * each executing iters x 64 DFMAs in 16 independent chains; out: ctas x 256 doubles. */
 int psk_dfma_probe(double *out, int ctas, int iters, psk_stream_t stream);

@@ -616,4 +616,58 @@ int psk_ssprk33_stage_adjoint(const psk_desc *d, const double *x, const double *
                      static_cast<cudaStream_t>(stream));
 }
 
+/* The whole reverse sweep of adjoint_step (timestepping.py:198-209) in ONE call: per step m = nsteps - 1 .. 0 the
+ * stage values of the checkpointed state are recomputed (2 launches) and the three adjoint stages applied (3
+ * launches), then the boundary condition of the adjoint variable (1 launch) -- all enqueued back to back from
+ * here, so a small grid pays kernel launches, not Python round trips. */
+int psk_ssprk33_adjoint_sweep(const psk_desc *d, const double *tape, int64_t tape_stride, int nsteps,
+                              const double *dt_table, const double *ghost_table, const psk_desc *pbc, double *p,
+                              double *states, double *work, double *lf_work, double *p_hist, psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (tape == nullptr || dt_table == nullptr || p == nullptr || states == nullptr || work == nullptr || nsteps <= 0)
+    return PSK_E_INVALID;
+  if (pbc != nullptr) {
+    rc = check_desc(pbc);
+    if (rc != PSK_OK) return rc;
+    if (pbc->n != d->n || pbc->g != d->g || pbc->batch != d->batch || pbc->ld != d->ld) return PSK_E_INVALID;
+  }
+  const int64_t state = static_cast<int64_t>(d->batch) * d->ld;
+  double *k1 = states, *k2 = states + state, *lam2 = states + 2 * state, *lam1 = states + 3 * state,
+         *pn = states + 4 * state;
+  const int64_t ghost_block = d->ghost_ld != 0 ? static_cast<int64_t>(d->batch) * d->ghost_ld : 2 * d->g;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double *cur = p, *nxt = pn;
+  for (int m = nsteps - 1; m >= 0; --m) {
+    const double *u = tape + static_cast<int64_t>(m) * tape_stride;
+    const double *dt = dt_table + m;
+    psk_desc ds[3] = {*d, *d, *d};  // boundary data at t, t + dt, t + dt / 2
+    if (ghost_table != nullptr)
+      for (int s = 0; s < 3; ++s) ds[s].ghost = ghost_table + (static_cast<int64_t>(3) * m + s) * ghost_block;
+    rc = psk_ssprk33_stage(&ds[0], 1, u, u, k1, dt, 0, nullptr, lf_work, nullptr, 1, stream);
+    if (rc != PSK_OK) return rc;
+    rc = psk_ssprk33_stage(&ds[1], 2, u, k1, k2, dt, 0, nullptr, lf_work, nullptr, 1, stream);
+    if (rc != PSK_OK) return rc;
+    rc = run_adjoint(&ds[2], k2, cur, dt, 0, 2.0 / 3.0, 2.0 / 3.0, nullptr, 0.0, nullptr, 0.0, work, lam2, st);
+    if (rc != PSK_OK) return rc;
+    rc = run_adjoint(&ds[1], k1, lam2, dt, 0, 0.25, 0.25, nullptr, 0.0, nullptr, 0.0, work, lam1, st);
+    if (rc != PSK_OK) return rc;
+    rc = run_adjoint(&ds[0], u, lam1, dt, 0, 1.0, 1.0, cur, 1.0 / 3.0, lam2, 0.75, work, nxt, st);
+    if (rc != PSK_OK) return rc;
+    if (pbc != nullptr) {  // p = apply_boundary(t, u, p) (timestepping.py:208-209)
+      rc = psk_apply_boundary(pbc, nxt, cur, stream);
+      if (rc != PSK_OK) return rc;
+    } else {
+      double *tmp = cur;
+      cur = nxt;
+      nxt = tmp;
+    }
+    if (p_hist != nullptr)
+      PSK_CUDA_OK(cudaMemcpyAsync(p_hist + static_cast<int64_t>(m) * state, cur, sizeof(double) * state,
+                                  cudaMemcpyDeviceToDevice, st));
+  }
+  if (cur != p) PSK_CUDA_OK(cudaMemcpyAsync(p, cur, sizeof(double) * state, cudaMemcpyDeviceToDevice, st));
+  return PSK_OK;
+}
+
 }  // extern "C"

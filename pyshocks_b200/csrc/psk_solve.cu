@@ -33,6 +33,9 @@ struct SolveParams {
   double dx, invdx, eps;
   double theta, cfl_scale, tfinal, fixed_dt;
   int adaptive, max_steps, batch;
+  const double *dt_table;     // optional [max_steps]: the step sizes (fixed mode)
+  const double *ghost_table;  // optional [max_steps][3][ghost_block]: boundary data at the three stage times
+  int64_t ghost_block;        // doubles per (step, stage): 2 g (shared by all rows) or batch * ghost_ld
 };
 
 __device__ __forceinline__ double block_max_abs(const double *a, int lo, int hi, unsigned long long *scratch) {
@@ -85,7 +88,7 @@ solve_rows_kernel(const SolveParams p) {
         break;
       }
     } else {
-      dt = p.fixed_dt;
+      dt = (p.dt_table != nullptr) ? p.dt_table[m] : p.fixed_dt;
     }
     if (p.dt_hist != nullptr && threadIdx.x == 0) p.dt_hist[static_cast<int64_t>(row) * p.max_steps + m] = dt;
 
@@ -93,12 +96,15 @@ solve_rows_kernel(const SolveParams p) {
     for (int stage = 1; stage <= 3; ++stage) {
       const double *src = (stage == 1) ? su : (stage == 2 ? s1 : s2);
       double *dst = (stage == 2) ? s2 : s1;  // stage 1: k1 -> s1, stage 2: k2 -> s2, stage 3: u' -> s1
+      // time-dependent boundary data: the values the user's g(t, x) takes at t, t + dt, t + dt / 2 (timestepping.py:314-319)
+      BcView bc = p.bc;
+      if (p.ghost_table != nullptr) bc.ghost = p.ghost_table + (static_cast<int64_t>(3) * m + (stage - 1)) * p.ghost_block;
       double speed = 0.0;
       if (FLUX == PSK_FLUX_LAX_FRIEDRICHS) {
         // max |w| over all cells after the boundary condition (scalar.py:277)
         unsigned long long mm = 0ull;
         for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-          const unsigned long long b = abs_bits(load_w(p.bc, src, row, i));
+          const unsigned long long b = abs_bits(load_w(bc, src, row, i));
           mm = b > mm ? b : mm;
         }
         mm = warp_max_bits(mm);
@@ -112,8 +118,8 @@ solve_rows_kernel(const SolveParams p) {
       // face values of every cell (zero padding beyond the array ends, BC in the ghost cells)
       for (int i = threadIdx.x; i < nx; i += blockDim.x) {
         const Weno5Pair o = reconstruct_cell<REC, STRICT>(
-            load_w(p.bc, src, row, i - 2), load_w(p.bc, src, row, i - 1), load_w(p.bc, src, row, i),
-            load_w(p.bc, src, row, i + 1), load_w(p.bc, src, row, i + 2), p.eps);
+            load_w(bc, src, row, i - 2), load_w(bc, src, row, i - 1), load_w(bc, src, row, i),
+            load_w(bc, src, row, i + 1), load_w(bc, src, row, i + 2), p.eps);
         sl[i] = o.ul;
         sr[i] = o.ur;
       }
@@ -124,14 +130,14 @@ solve_rows_kernel(const SolveParams p) {
           const int j = i - 1;
           const double nu = (p.nu != nullptr) ? p.nu[j] : 1.0;
           const double arj = (EQ != PSK_EQ_BURGERS) ? p.vel_r[j] : 0.0, alp = (EQ != PSK_EQ_BURGERS) ? p.vel_l[j + 1] : 0.0;
-          Flo = face_flux<EQ, FLUX, STRICT>(sr[j], sl[j + 1], load_w(p.bc, src, row, j), load_w(p.bc, src, row, j + 1),
+          Flo = face_flux<EQ, FLUX, STRICT>(sr[j], sl[j + 1], load_w(bc, src, row, j), load_w(bc, src, row, j + 1),
                                             speed, nu, arj, alp);
         }
         if (i <= nx - 2) {
           const int j = i;
           const double nu = (p.nu != nullptr) ? p.nu[j] : 1.0;
           const double arj = (EQ != PSK_EQ_BURGERS) ? p.vel_r[j] : 0.0, alp = (EQ != PSK_EQ_BURGERS) ? p.vel_l[j + 1] : 0.0;
-          Fhi = face_flux<EQ, FLUX, STRICT>(sr[j], sl[j + 1], load_w(p.bc, src, row, j), load_w(p.bc, src, row, j + 1),
+          Fhi = face_flux<EQ, FLUX, STRICT>(sr[j], sl[j + 1], load_w(bc, src, row, j), load_w(bc, src, row, j + 1),
                                             speed, nu, arj, alp);
         }
         const double vel = (EQ == PSK_EQ_ADVECTION) ? p.vel[i] : 0.0;
@@ -216,6 +222,30 @@ extern "C" int psk_solve_rows(const psk_desc *d, double *u, int adaptive, double
   p.dx = d->dx; p.invdx = 1.0 / d->dx; p.eps = d->eps;
   p.theta = theta; p.cfl_scale = cfl_scale; p.tfinal = tfinal; p.fixed_dt = fixed_dt;
   p.adaptive = adaptive; p.max_steps = max_steps; p.batch = d->batch;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return d->math == PSK_MATH_STRICT ? psk::solve_scheme<true>(d, p, st) : psk::solve_scheme<false>(d, p, st);
+}
+
+/* psk_solve_rows for step sizes and boundary data that are known in advance but change from step to step
+ * (state-independent dt clamped at tfinal, time-dependent Dirichlet data: drivers/advection-adjoint.py): */
+extern "C" int psk_solve_rows_tables(const psk_desc *d, double *u, int nsteps, const double *dt_table,
+                                     const double *ghost_table, double *t_out, int32_t *steps_out, double *tape,
+                                     psk_stream_t stream) {
+  int rc = psk::check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (u == nullptr || t_out == nullptr || steps_out == nullptr || nsteps <= 0 || dt_table == nullptr) return PSK_E_INVALID;
+  if (d->rec == PSK_REC_ESWENO32 || d->flux == PSK_FLUX_ESWENO) return PSK_E_UNSUPPORTED;
+  psk::SolveParams p{};
+  p.u = u; p.t_out = t_out; p.steps_out = steps_out; p.tape = tape;
+  p.nu = d->nu; p.vel = d->velocity; p.vel_l = d->vel_l; p.vel_r = d->vel_r;
+  p.bc = psk::make_bc_view(d);
+  p.ld = d->ld;
+  p.tape_stride = static_cast<int64_t>(d->batch) * d->ld;
+  p.dx = d->dx; p.invdx = 1.0 / d->dx; p.eps = d->eps;
+  p.max_steps = nsteps; p.batch = d->batch;
+  p.dt_table = dt_table;
+  p.ghost_table = ghost_table;
+  p.ghost_block = d->ghost_ld != 0 ? static_cast<int64_t>(d->batch) * d->ghost_ld : 2 * d->g;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return d->math == PSK_MATH_STRICT ? psk::solve_scheme<true>(d, p, st) : psk::solve_scheme<false>(d, p, st);
 }

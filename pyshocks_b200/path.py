@@ -328,6 +328,63 @@ class HotPath:
         )
         return {"t": t_out, "steps": steps, "dt": hist, "tape": None if tp is None else tp[:, :, : self.nx]}
 
+    def solve_rows_tables(self, u: torch.Tensor, dts: torch.Tensor, ghost_table: torch.Tensor | None = None, *,
+                          tape: bool = False) -> dict:
+        """:meth:`solve_rows` with one step size per step (``dts``: device ``(nsteps,)``) and, for boundary data
+        that depend on time, ``ghost_table``: device ``(nsteps, 3, 2 g)`` -- the Dirichlet values / Neumann
+        offsets at the stage times ``t, t + dt, t + dt / 2`` of every step (``psk_solve_rows_tables``)."""
+        batch, ld = self._state(u)
+        nsteps = int(dts.numel())
+        dev = u.device
+        t_out = torch.zeros(batch, dtype=torch.float64, device=dev)
+        steps = torch.zeros(batch, dtype=torch.int32, device=dev)
+        tp = torch.zeros((nsteps + 1, batch, ld), dtype=torch.float64, device=dev) if tape else None
+        if ghost_table is not None:
+            if tuple(ghost_table.shape) != (nsteps, 3, 2 * self.g) or not ghost_table.is_contiguous():
+                raise ValueError(f"ghost_table must be contiguous of shape {(nsteps, 3, 2 * self.g)}")
+        d = self.desc(batch, ld)
+        if ghost_table is not None:
+            d.ghost, d.ghost_ld = L.ptr(ghost_table), 0  # (validated as "present"; the kernel takes the table)
+        L.check(
+            "psk_solve_rows_tables",
+            L.lib().psk_solve_rows_tables(ct.byref(d), L.ptr(u), nsteps, L.ptr(dts), L.ptr(ghost_table), L.ptr(t_out),
+                                          L.raw_ptr(steps), L.ptr(tp), L.stream_ptr()),
+        )
+        return {"t": t_out, "steps": steps, "tape": tp}
+
+    def adjoint_sweep(self, tape: torch.Tensor, dts: torch.Tensor, p: torch.Tensor, *,
+                      ghost_table: torch.Tensor | None = None, p_boundary: "HotPath | None" = None,
+                      history: bool = False) -> torch.Tensor | None:
+        """The whole loop of ``adjoint_step`` (timestepping.py:198-209) in one call (``psk_ssprk33_adjoint_sweep``):
+        ``p`` (``(batch, nx)`` with the tape's row stride, already passed through the adjoint boundary condition)
+        is replaced by ``p(0)``.  ``tape``: ``(nsteps + 1, batch, ld)`` from :meth:`solve_rows` /
+        :meth:`solve_rows_tables`; ``p_boundary``: the binding whose boundary kind (and ghost data) is imposed on
+        ``p`` after every step.  Returns every intermediate ``p`` (``(nsteps, batch, ld)``) if ``history``."""
+        nsteps = int(dts.numel())
+        if tape.dim() != 3 or tape.shape[0] < nsteps + 1 or not tape.is_contiguous():
+            raise ValueError("tape must be contiguous of shape (nsteps + 1, batch, ld)")
+        batch, ld = tape.shape[1], tape.shape[2]
+        pb, pnx, pld = L.rows_of(p)
+        if (pb, pnx, pld if pb > 1 else ld) != (batch, self.nx, ld):
+            raise ValueError("p must be a (batch, nx) view with the row stride of the tape")
+        dev = tape.device
+        states = torch.empty((5, batch, ld), dtype=torch.float64, device=dev)
+        hist = torch.empty((nsteps, batch, ld), dtype=torch.float64, device=dev) if history else None
+        d = self.desc(batch, ld)
+        if ghost_table is not None:
+            d.ghost, d.ghost_ld = L.ptr(ghost_table), 0
+        pd = None
+        if p_boundary is not None:
+            pd = p_boundary.desc(batch, ld)
+        L.check(
+            "psk_ssprk33_adjoint_sweep",
+            L.lib().psk_ssprk33_adjoint_sweep(
+                ct.byref(d), L.ptr(tape), batch * ld, nsteps, L.ptr(dts), L.ptr(ghost_table),
+                ct.byref(pd) if pd is not None else None, L.ptr(p), L.ptr(states), L.ptr(self._adj_work(batch)),
+                L.ptr(self._lf_work(batch)), L.ptr(hist), L.stream_ptr()),
+        )
+        return hist
+
     # }}}
 
     # {{{ fused SSPRK33

@@ -18,6 +18,7 @@ from dataclasses import dataclass
 from functools import singledispatch
 from typing import Any, Callable, ClassVar, Iterator
 
+import numpy as np
 import torch
 
 from .checkpointing import Checkpoint, load, save
@@ -375,14 +376,114 @@ def solve(
         out = hp.solve_rows(u, tfinal=tfinal, theta=theta, cfl_scale=cfl_scale, max_steps=maxit,
                             record_dt=True, tape=checkpoint)
     else:
+        # state-independent time step (advection/schemes.py:51-59): the dt sequence of step() -- clamped at tfinal,
+        # + 1e-15 (timestepping.py:139-142) -- and the boundary data at every stage time are known in advance
         from .schemes import predict_timestep
 
-        dt = theta * float(predict_timestep(scheme, grid, bc, 0.0, u))
-        nsteps, dt = predict_maxit_from_timestep(tfinal, dt)
-        out = hp.solve_rows(u, fixed_dt=dt, max_steps=nsteps, record_dt=True, tape=checkpoint)
+        dts, ts = step_sizes(theta * float(predict_timestep(scheme, grid, bc, 0.0, u)), tfinal, maxit)
+        dts_dev = torch.tensor(dts, dtype=torch.float64, device=u.device)
+        table = ghost_table(bc, grid, ts, dts)
+        out = hp.solve_rows_tables(u, dts_dev, table, tape=checkpoint)
+        out["dt"] = dts_dev[None, :]
+        out["ghost_table"], out["ts"] = table, ts
     steps = out["steps"]
     if bool((steps < 0).any()):
         raise ValueError("Time step is not finite.")  # timestepping.py:144-145
     nmax = int(steps.max())
-    return {"u": u, "t": out["t"], "iteration": steps, "dt": out["dt"][..., :nmax],
-            "states": None if out["tape"] is None else out["tape"][: nmax + 1]}
+    res = {"u": u, "t": out["t"], "iteration": steps, "dt": out["dt"][..., :nmax],
+           "states": None if out["tape"] is None else out["tape"][: nmax + 1]}
+    if "ghost_table" in out:
+        res["ghost_table"], res["ts"] = out["ghost_table"], out["ts"]
+    return res
+
+
+def step_sizes(dt_cfl: float, tfinal: float, maxit: int | None = None) -> tuple[list[float], list[float]]:
+    """The ``dt`` and ``t`` sequences of :func:`step` for a state-independent ``predict_timestep``
+    (timestepping.py:128-150: ``dt = min(dt, tfinal - t) + 1e-15`` until ``t >= tfinal`` or ``maxit`` steps)."""
+    if not np.isfinite(dt_cfl):
+        raise ValueError(f"Time step is not finite: {dt_cfl!r}.")
+    dts: list[float] = []
+    ts: list[float] = []
+    t = 0.0
+    while not t >= tfinal and (maxit is None or len(dts) < maxit):
+        dt_min = tfinal - t
+        dt = (dt_cfl if dt_cfl < dt_min else dt_min) + 1.0e-15
+        ts.append(t)
+        dts.append(dt)
+        t = t + dt
+    return dts, ts
+
+
+def ghost_table(bc: Any, grid: Any, ts: list[float], dts: list[float]) -> torch.Tensor | None:
+    """``(nsteps, 3, 2 g)`` boundary data at the stage times ``t, t + dt, t + dt / 2`` of every step
+    (timestepping.py:314-319), evaluated with the user's ``g(t, x)`` exactly as ``apply_boundary`` does step
+    by step (scalar.py:424-425, :490-498); ``None`` for boundaries without data (periodic)."""
+    from .binding import ghost_data
+
+    if not ts or ghost_data(bc, grid, ts[0]) is None:
+        return None
+    rows = []
+    for t, dt in zip(ts, dts):
+        for tt in (t, t + dt, t + 0.5 * dt):
+            gd = ghost_data(bc, grid, tt)
+            rows.append(gd if isinstance(gd, torch.Tensor) else torch.from_numpy(np.asarray(gd, dtype=np.float64)))
+    dev = grid.x.device
+    return torch.stack([r.to(dev) for r in rows]).reshape(len(ts), 3, -1).contiguous()
+
+
+def adjoint_solve(
+    scheme: Any,
+    grid: Any,
+    bc: Any,
+    forward: dict,
+    p0: Array,
+    *,
+    p_boundary: Any = None,
+    history: bool = False,
+) -> dict:
+    """``for event in adjoint_step(stepper, p0, maxit=..., apply_boundary=...): pass`` in ONE call
+    (``psk_ssprk33_adjoint_sweep``) from the result of :func:`solve` with ``checkpoint=True``: every reverse
+    step is six kernel launches enqueued back to back, no host round trip.  ``p_boundary``: the boundary
+    condition the drivers impose on the adjoint variable after every step (homogeneous Dirichlet or
+    Neumann; its data must not depend on time).  Returns ``{"p": p(0), "history": (steps, nx) or None}``.
+
+    Not in the reference (its loop is a Python generator around a dense Jacobian, timestepping.py:155-215)."""
+    from .binding import boundary_kind, ghost_data, hotpath_for
+    from .path import HotPath
+
+    hp = hotpath_for(scheme, grid, bc, 0.0)
+    states = forward["states"]
+    if states is None:
+        raise ValueError("Adjoint time stepping requires a checkpoint.")  # timestepping.py:177-178
+    tape = states if states.dim() == 3 else states[:, None, :]
+    nsteps = tape.shape[0] - 1
+    # like adjoint_step, every reverse step uses dt = t_{m+1} - t_m of the ACCUMULATED times (timestepping.py:200-202),
+    # which is not always the forward dt_m in the last bit -- for the recomputed stages and the boundary data too
+    fdts = [float(x) for x in forward["dt"].reshape(-1)[:nsteps].cpu().numpy()]
+    ts = [0.0]
+    for dt in fdts:
+        ts.append(ts[-1] + dt)
+    rdts = [ts[m + 1] - ts[m] for m in range(nsteps)]
+    dts = torch.tensor(rdts, dtype=torch.float64, device=p0.device)
+    table = forward.get("ghost_table")
+    if table is not None and rdts != fdts:
+        table = ghost_table(bc, grid, ts[:-1], rdts)
+    p = p0.clone()
+    pb = None
+    if p_boundary is not None:
+        pb = HotPath(equation="burgers", flux="rusanov", rec="constant", bc=boundary_kind(p_boundary), n=hp.n, g=hp.g,
+                     dx=hp.dx, eps=0.0, device=p.device)
+        gd = ghost_data(p_boundary, grid, 0.0)
+        if gd is not None:
+            pb.set_ghost(gd)
+        p = pb.apply_boundary(p)  # timestepping.py:186-187
+    # p must share the row stride of the tape
+    buf = torch.zeros((1, tape.shape[2]), dtype=torch.float64, device=p.device) if p.dim() == 1 else None
+    if buf is not None:
+        buf[0, : hp.nx] = p
+        pv = buf[:, : hp.nx]
+    else:
+        pv = p
+    hist = hp.adjoint_sweep(tape.contiguous(), dts, pv, ghost_table=table, p_boundary=pb, history=history)
+    out_p = pv[0].clone() if p0.dim() == 1 else pv
+    return {"p": out_p, "history": None if hist is None else (hist[:, 0, : hp.nx] if p0.dim() == 1 else hist[..., : hp.nx])}

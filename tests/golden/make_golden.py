@@ -23,6 +23,8 @@ Outputs (all small, committed):
 * ``solve_c1.npz`` BASELINE config 1 (examples/burgers.py, N=256, t=1) for the
                    rusanov and lf schemes: dt history and final state
 * ``solve_c2.npz`` config-2 forward at reduced N (advection, Dirichlet, theta=.75)
+* ``solve_c2_4096.npz`` config-2 forward at its full size N = 4096 (2731 steps): dt history, three
+                   intermediate states and the final state
 * ``adjoint.npz``  ``adjoint_step`` sweeps (burgers-adjoint / advection-adjoint
                    driver set-ups at small N), every intermediate ``p``
 """
@@ -268,6 +270,23 @@ def golden_solve_c2() -> dict[str, np.ndarray]:
     return out
 
 
+def golden_solve_c2_full() -> dict[str, np.ndarray]:
+    """BASELINE config 2 at its full size: drivers/advection-adjoint.py:219-276 with -s godunov -r wenojs53
+    -n 4096 (Dirichlet exact-solution boundary, theta = 0.75, t = 1): 2731 steps of the forward solve."""
+    out: dict[str, np.ndarray] = {}
+    scheme, grid, bc, stepper, u0, velocity = _advection_driver(4096)
+    stepper = timestepping.SSPRK33(predict_timestep=stepper.predict_timestep, source=stepper.source, checkpoint=None)
+    dts = []
+    for event in timestepping.step(stepper, u0, tfinal=1.0):
+        dts.append(float(event.dt))
+        if event.iteration in (1, 100, 1000):
+            out[f"u{event.iteration:04d}"] = A(event.u)
+    out["u0"] = A(u0)
+    out["dt"] = np.array(dts)
+    out["uf"] = A(event.u)
+    return out
+
+
 def _record_adjoint(out, key, stepper, grid, u0, tfinal, p_boundary):
     for event in timestepping.step(stepper, u0, tfinal=tfinal):
         pass
@@ -349,6 +368,9 @@ def main() -> None:
     if sys.argv[1:] == ["steppers"]:  # this file alone (the others are untouched by it)
         np.savez_compressed(HERE / "steppers.npz", **golden_steppers())
         return
+    if sys.argv[1:] == ["c2full"]:
+        np.savez_compressed(HERE / "solve_c2_4096.npz", **golden_solve_c2_full())
+        return
     np.savez_compressed(HERE / "weno.npz", **golden_weno())
     rhs, adv = golden_rhs()
     np.savez_compressed(HERE / "rhs.npz", **rhs)
@@ -356,6 +378,7 @@ def main() -> None:
     np.savez_compressed(HERE / "steppers.npz", **golden_steppers())
     np.savez_compressed(HERE / "solve_c1.npz", **golden_solve_c1())
     np.savez_compressed(HERE / "solve_c2.npz", **golden_solve_c2())
+    np.savez_compressed(HERE / "solve_c2_4096.npz", **golden_solve_c2_full())
     np.savez_compressed(HERE / "adjoint.npz", **golden_adjoint())
     for f in sorted(HERE.glob("*.npz")):
         print(f"{f.name}: {f.stat().st_size / 1024:.1f} KiB")

@@ -1,0 +1,126 @@
+"""BASELINE config 2 (drivers/advection-adjoint.py -s godunov -r wenojs53 -n 4096: 2731 forward steps + the
+discrete-adjoint sweep) timed through the single-call path (timestepping.solve / adjoint_solve) and through the
+step-by-step API, with the CPU restatement beside it.  Prints one JSON line (-> profiles/)."""
+import json
+import sys
+import time
+from dataclasses import replace
+from functools import partial
+
+import numpy as np
+import torch
+
+sys.path.insert(0, "/root/repo")
+import pyshocks_b200 as ps  # noqa: E402
+from pyshocks_b200 import advection, funcs, timestepping  # noqa: E402
+from pyshocks_b200.checkpointing import InMemoryCheckpoint  # noqa: E402
+from pyshocks_b200.reconstruction import make_reconstruction_from_name  # noqa: E402
+from pyshocks_b200.scalar import make_dirichlet_boundary  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+rec = make_reconstruction_from_name("wenojs53")
+scheme = advection.make_scheme_from_name("godunov", rec=rec, velocity=None)
+grid = ps.make_uniform_cell_grid(a=-1.0, b=1.0, n=n, nghosts=scheme.stencil_width)
+quad = ps.make_leggauss_quadrature(grid, order=int(max(scheme.order, 1.0)) + 1)
+scheme = replace(scheme, velocity=ps.cell_average(quad, partial(funcs.ic_constant, grid, c=1.0)))
+func_ic = partial(funcs.ic_sine, grid, k=1)
+u0 = ps.cell_average(quad, func_ic)
+bc = make_dirichlet_boundary(lambda t, x: func_ic(x - 1.0 * t))
+pbc = make_dirichlet_boundary(lambda t, x: torch.zeros_like(x))
+
+
+def wall(fn, reps=3):
+    best, out = 1e30, None
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t0)
+    return best, out
+
+
+# single-call path (wall clock: includes the host evaluation of the boundary data at all 3 x 2731 stage times)
+t_fwd, fwd = wall(lambda: timestepping.solve(scheme, grid, bc, u0, tfinal=1.0, theta=0.75, checkpoint=True))
+nsteps = int(fwd["iteration"][0])
+t_rev, out = wall(lambda: timestepping.adjoint_solve(scheme, grid, bc, fwd, fwd["u"], p_boundary=pbc))
+# device time of the two launches alone (tables prepared)
+from pyshocks_b200.binding import hotpath_for  # noqa: E402
+
+hp = hotpath_for(scheme, grid, bc, 0.0)
+dts = fwd["dt"].reshape(-1).contiguous()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+u = u0.clone()
+torch.cuda.synchronize()
+ev[0].record()
+r = hp.solve_rows_tables(u, dts, fwd["ghost_table"], tape=True)
+ev[1].record()
+p = torch.zeros((1, r["tape"].shape[2]), dtype=torch.float64, device="cuda")
+p[0, : hp.nx] = u
+hp.adjoint_sweep(r["tape"], dts, p[:, : hp.nx], ghost_table=fwd["ghost_table"])
+ev[2].record()
+torch.cuda.synchronize()
+dev_fwd, dev_rev = ev[0].elapsed_time(ev[1]) * 1e-3, ev[1].elapsed_time(ev[2]) * 1e-3
+
+# step-by-step API (the reference's own loop structure: host reads dt, one advance / adjoint step per iteration)
+stepper = timestepping.SSPRK33(
+    predict_timestep=ps.jit(lambda t_, u_: 0.75 * ps.predict_timestep(scheme, grid, bc, t_, u_)),
+    source=ps.jit(lambda t_, u_: ps.apply_operator(scheme, grid, bc, t_, u_)),
+    checkpoint=InMemoryCheckpoint(basename="Iteration"),
+)
+
+
+def api_forward():
+    stepper.checkpoint.storage.clear()
+    for event in timestepping.step(stepper, u0, tfinal=1.0):
+        pass
+    return event
+
+
+t_api_fwd, event = wall(api_forward, reps=1)
+
+
+def api_reverse():
+    for ev_ in timestepping.adjoint_step(stepper, event.u, maxit=event.iteration,
+                                         apply_boundary=lambda t, u_, p_: ps.apply_boundary(pbc, grid, t, p_)):
+        pass
+    return ev_.p
+
+
+t_api_rev, p_api = wall(api_reverse, reps=1)
+same = bool(torch.equal(p_api, out["p"]))
+
+# CPU restatement (one row: one core), forward only -- the reference's adjoint is a dense (nx x nx) jacfwd per step
+from oracle import pyshocks_oracle as po  # noqa: E402
+from oracle.c_oracle import COracle  # noqa: E402
+
+ogrid = po.make_grid(-1.0, 1.0, n, 3)
+vel = po.cell_average(ogrid, lambda x: np.full_like(x, 1.0), 4)
+co = COracle(equation="advection", flux="godunov", rec="wenojs53", bc="dirichlet", n=n, g=3, batch=1, dx=ogrid.h,
+             eps=1e-12, velocity=vel)
+xg = np.concatenate([ogrid.x[:3], ogrid.x[-3:]])
+uu = u0.cpu().numpy()[None, :].copy()
+hdts = dts.cpu().numpy()
+t0 = time.perf_counter()
+t = 0.0
+for dt in hdts:
+    g3 = np.stack([po.ic_sine(ogrid, xg - tt, k=1) for tt in (t, t + dt, t + 0.5 * dt)])
+    uu = co.ssprk33_step(uu, dt, ghost3=g3)
+    t += dt
+t_c = time.perf_counter() - t0
+err = float(np.abs(uu[0, 3:-3] - fwd["u"].cpu().numpy()[3:-3]).max())
+print(json.dumps({
+    "config": f"BASELINE configs[1]: advection godunov + wenojs53, Dirichlet exact solution, n = {n}, theta = 0.75, t = 1",
+    "steps": nsteps, "cells": n,
+    "single_call": {"forward_s": t_fwd, "reverse_s": t_rev, "gradients_per_s": 1.0 / (t_fwd + t_rev),
+                    "device_forward_s": dev_fwd, "device_reverse_s": dev_rev,
+                    "device_gradients_per_s": 1.0 / (dev_fwd + dev_rev),
+                    "forward_cell_updates_per_s": n * nsteps / dev_fwd, "adjoint_cell_updates_per_s": n * nsteps / dev_rev,
+                    "note": "wall clock includes the host evaluation of the user's boundary function at 3 x steps stage "
+                            "times (forward) and the tables of the reverse sweep; device = the two launches / calls alone"},
+    "step_by_step_api": {"forward_s": t_api_fwd, "reverse_s": t_api_rev, "gradients_per_s": 1.0 / (t_api_fwd + t_api_rev),
+                         "same_bits_as_single_call": same},
+    "cpu_port_forward_s": t_c, "cpu_port_cell_updates_per_s": n * nsteps / t_c, "cpu_cores": 1,
+    "gpu_vs_cpu_port_forward_max_abs_diff": err,
+    "reference_adjoint": "dense jax.jacfwd Jacobian (nx x nx = 135 MB) per step, 2731 times: not runnable here",
+}))

@@ -180,6 +180,17 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
 int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const double *dt,
                      int64_t dt_stride, const uint8_t *active, double *maxabs, psk_stream_t stream);
 
+/* psk_ssprk33_step for rows with DIRICHLET boundary data (scalar.py:418-427) and for the advection / continuity
+ * equations: the whole step in one launch, the ghost cells of every stage input taking the data of that stage's
+ * time.  ghost3: three consecutive blocks of (d->ghost_ld != 0 ? batch * d->ghost_ld : 2 g) doubles -- what the
+ * user's g(t, x) returns at t, t + dt, t + dt / 2 (timestepping.py:314-319), rows at stride d->ghost_ld (0: one
+ * set for all rows), left ghost cells first; d->ghost is ignored.  Burgers + {Rusanov (nu = 1), upwind,
+ * Engquist-Osher}, advection, continuity (upwind flux); WENO-JS5, FAST math, 16-byte aligned rows;
+ * PSK_E_UNSUPPORTED elsewhere.  Same bits as three psk_ssprk33_stage calls with those data.  active / maxabs
+ * as in psk_ssprk33_step. */
+int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
+                        const double *ghost3, const uint8_t *active, double *maxabs, psk_stream_t stream);
+
 /* psk_ssprk33_step that also stores the stage values k1, k2 (timestepping.py:314-317) -- what the reverse
  * sweep recomputes from a checkpointed state before its three psk_ssprk33_stage_adjoint calls -- in one
  * launch instead of two or three.  uout may be NULL (only k1, k2 wanted: the third stage is skipped).

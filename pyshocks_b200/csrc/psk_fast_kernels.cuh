@@ -444,7 +444,54 @@ struct StepParams {
   int bc_none;  // 1: window cells beyond the row ends are the row's stored ghost cells (slab of a larger grid, g >= 9)
   double *k1_out, *k2_out;  // STAGES kernels only: the stage values are stored too (uout may then be NULL)
   int shift;                // step_warp_fused_p2p_kernel only: the chunk grid starts this many cells left of the slab
+  // DIRICHLET rows: boundary data at the three stage times t, t + dt, t + dt / 2 (timestepping.py:314-319) as three
+  // consecutive blocks of ghost_block doubles; row r of a block at + r * ghost_ld (0: one set for all rows); 2 g
+  // values per row, left ghost cells first
+  const double *ghost3;
+  int64_t ghost_ld, ghost_block;
+  // advection / continuity: velocity and its reconstruction (time independent), nx entries each
+  const double *vel, *vel_l, *vel_r;
 };
+
+// what the upwind switch of the advection / continuity flux needs at the R + 1 faces of a lane's cells
+// (advection/schemes.py:107-114, continuity/schemes.py:103-110): taken once per step, the velocity does not
+// depend on time.  pos bit f: (ar + al) > 0 at the face between the cells own + f - 1 and own + f
+template <int R>
+struct StepVel {
+  unsigned pos;
+  double ar[R + 1], al[R + 1];  // continuity only
+  double vc[R];                 // advection only: velocity of the own cells (0 outside the row)
+};
+
+template <int R, int EQ>
+__device__ __forceinline__ void step_load_vel(const StepParams &p, int c0, StepVel<R> &v) {
+  const int nx = p.n + 2 * p.g;
+  v.pos = 0u;
+#pragma unroll
+  for (int f = 0; f <= R; ++f) {
+    const int j = p.g + c0 + f - 1;  // array index of the cell left of the face
+    const bool ok = (j >= 0 && j < nx - 1);
+    const double arj = ok ? p.vel_r[j] : 0.0, alp = ok ? p.vel_l[j + 1] : 0.0;
+    if ((arj + alp) > 0.0) v.pos |= 1u << f;
+    v.ar[f] = arj;
+    v.al[f] = alp;
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) v.vc[r] = (EQ == PSK_EQ_ADVECTION && c0 + r >= 0 && c0 + r < p.n) ? p.vel[p.g + c0 + r] : 0.0;
+}
+
+// Dirichlet rows: the window cells that are ghost cells take the boundary data of `stage` (0, 1, 2); window
+// cells beyond the ghost cells never reach a stored cell
+template <int R>
+__device__ __forceinline__ void step_fill_ghosts(const StepParams &p, int row, int stage, int c0, double (&a)[R]) {
+  const double *gh = p.ghost3 + static_cast<int64_t>(stage) * p.ghost_block + static_cast<int64_t>(row) * p.ghost_ld;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int c = c0 + r;
+    if (c < 0) a[r] = (c >= -p.g) ? gh[c + p.g] : 0.0;
+    if (c >= p.n) a[r] = (c < p.n + p.g) ? gh[p.g + c - p.n] : 0.0;
+  }
+}
 
 template <int R>
 struct StepGeometry {
@@ -454,8 +501,9 @@ struct StepGeometry {
 };
 
 // one stage on the lane's R cells: a (stage input, own cells) -> L = coef * dF per own cell
-template <int R, int FLUX>
-__device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9, double (&dF)[R]) {
+template <int R, int FLUX, int EQ = PSK_EQ_BURGERS>
+__device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9, double (&dF)[R],
+                                               const StepVel<R> *vel = nullptr) {
   constexpr unsigned kFull = 0xffffffffu;
   double w0 = __shfl_up_sync(kFull, a[R - 1], 1);  // cell own - 1
   double t[R + 3];   // t[k]: interval (own - 2 + k, own - 1 + k); own: k = 1..R
@@ -474,7 +522,7 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
   pq[0] = __shfl_up_sync(kFull, pq[R], 1);
   pq[R + 1] = __shfl_down_sync(kFull, pq[1], 1);
   double m2[R + 2];  // -2 |w| of the cells own - 1 .. own + R (Rusanov speed, as in the stage kernel)
-  if (FLUX == PSK_FLUX_RUSANOV) {
+  if (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV) {
     m2[0] = -2.0 * fabs(w0);
 #pragma unroll
     for (int j = 1; j <= R; ++j) m2[j] = -2.0 * fabs(a[j - 1]);
@@ -494,7 +542,10 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
   for (int f = 0; f <= R; ++f) {
     const double urj = (f == 0) ? ur_left : ur[f - 1];
     const double ulp = (f == R) ? ul_right : ul[f];
-    if (FLUX == PSK_FLUX_RUSANOV) {  // 4 F (scalar.py:231-249)
+    if (EQ != PSK_EQ_BURGERS) {  // upwind by the sign of the averaged velocity, as in the stage kernels
+      const bool pos = (vel->pos >> f) & 1u;
+      F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? __dmul_rn(vel->ar[f], urj) : __dmul_rn(vel->al[f], ulp));
+    } else if (FLUX == PSK_FLUX_RUSANOV) {  // 4 F (scalar.py:231-249)
       F[f] = fma(umax_neg(m2[f], m2[f + 1]), ulp - urj, fma(urj, urj, ulp * ulp));
     } else if (FLUX == PSK_FLUX_UPWIND) {  // 2 F (scalar.py:123-132)
       const double x = (urj + ulp) > 0.0 ? urj : ulp;
@@ -505,7 +556,10 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
     }
   }
 #pragma unroll
-  for (int r = 0; r < R; ++r) dF[r] = F[r] - F[r + 1];
+  for (int r = 0; r < R; ++r) {
+    dF[r] = F[r] - F[r + 1];
+    if (EQ == PSK_EQ_ADVECTION) dF[r] *= vel->vc[r];  // non-conservative form (advection/schemes.py:73)
+  }
 }
 
 // a[0..R) -> dst on the stored cells of the lane (aligned pairs where the whole quad lies in the row)
@@ -526,7 +580,11 @@ __device__ __forceinline__ void step_store(double *dst, bool inside, const bool 
 // the third stage is skipped when no uout is given: the recomputation of the reverse sweep, which needs
 // k1 and k2 of a checkpointed state (and the next state, inside a tape segment), in one launch
 // instead of two or three.
-template <int R, int FLUX, bool WITH_MAX, int THREADS, int MINB, bool STAGES = false>
+// EQ / DIRICHLET: the same kernel for the advection and continuity equations (upwind flux with the velocity's
+// reconstruction) and for rows with Dirichlet boundary data -- the window cells that are ghost cells take the data
+// of each stage time before that stage, exactly where apply_boundary writes them (scalar.py:418-427).
+template <int R, int FLUX, bool WITH_MAX, int THREADS, int MINB, bool STAGES = false, int EQ = PSK_EQ_BURGERS,
+          bool DIRICHLET = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 step_warp_fused_kernel(const StepParams p) {
   using Geo = StepGeometry<R>;
@@ -558,7 +616,9 @@ step_warp_fused_kernel(const StepParams p) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       int c = c0 + r;
-      if (p.bc_none) {  // ghost cells filled by the neighbouring slabs; further out: never reaches a stored cell
+      if (DIRICHLET) {
+        u0[r] = (c >= 0 && c < n) ? p.u[base + c] : 0.0;  // ghost cells: step_fill_ghosts below
+      } else if (p.bc_none) {  // ghost cells filled by the neighbouring slabs; further out: never reaches a stored cell
         u0[r] = (c >= -p.g && c < n + p.g) ? p.u[base + c] : 0.0;
       } else {
         c %= n;  // periodic image (n >= 1)
@@ -574,20 +634,25 @@ step_warp_fused_kernel(const StepParams p) {
     return;
   }
   const double cdt = p.coef * p.dt[static_cast<int64_t>(row) * p.dt_stride];
+  StepVel<R> vel;
+  if (EQ != PSK_EQ_BURGERS) step_load_vel<R, EQ>(p, c0, vel);
+  if (DIRICHLET && !inside) step_fill_ghosts<R>(p, row, 0, c0, u0);
 
   double a[R], dF[R];
-  step_stage_rhs<R, FLUX>(u0, p.eps9, dF);
+  step_stage_rhs<R, FLUX, EQ>(u0, p.eps9, dF, &vel);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);  // k1
   if (STAGES) step_store<R>(p.k1_out + base + c0, inside, st, a);
-  step_stage_rhs<R, FLUX>(a, p.eps9, dF);
+  if (DIRICHLET && !inside) step_fill_ghosts<R>(p, row, 1, c0, a);
+  step_stage_rhs<R, FLUX, EQ>(a, p.eps9, dF, &vel);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);  // k2
   if (STAGES) {
     step_store<R>(p.k2_out + base + c0, inside, st, a);
     if (p.uout == nullptr) return;
   }
-  step_stage_rhs<R, FLUX>(a, p.eps9, dF);
+  if (DIRICHLET && !inside) step_fill_ghosts<R>(p, row, 2, c0, a);
+  step_stage_rhs<R, FLUX, EQ>(a, p.eps9, dF, &vel);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);  // u'
 

@@ -1027,7 +1027,7 @@ __global__ void step_control_kernel(int batch, double theta, double cfl_scale, d
 // 7000 = off (three stage launches)
 static int g_step_variant = 62;  // R = 6, CTAs of 128 threads, 3 per SM (136 registers): 9.0e10 cell-updates/s on B200
 
-template <int R, int FLUX, int THREADS, int MINB, bool STAGES = false>
+template <int R, int FLUX, int THREADS, int MINB, bool STAGES = false, int EQ = PSK_EQ_BURGERS, bool DIRICHLET = false>
 int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cudaStream_t st) {
   StepParams q = q0;
   q.chunks_per_row = (n + StepGeometry<R>::kEmit - 1) / StepGeometry<R>::kEmit;
@@ -1038,11 +1038,11 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
   if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
   const dim3 grid(gx, gy, batch / gy);
   if (STAGES)
-    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, STAGES><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, STAGES, EQ, DIRICHLET><<<grid, wpc * 32, 0, st>>>(q);
   else if (with_max)
-    step_warp_fused_kernel<R, FLUX, true, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, true, THREADS, MINB, false, EQ, DIRICHLET><<<grid, wpc * 32, 0, st>>>(q);
   else
-    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, false, EQ, DIRICHLET><<<grid, wpc * 32, 0, st>>>(q);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
 }
@@ -1171,13 +1171,17 @@ int launch_step_p2p(const StepParams &q, const HaloLink &h, bool with_max, cudaS
 
 int launch_step_fused(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
                       const uint8_t *active, double *maxabs, cudaStream_t st, double *k1_out = nullptr,
-                      double *k2_out = nullptr) {
+                      double *k2_out = nullptr, const double *ghost3 = nullptr) {
   StepParams q{};
   q.u = u; q.uout = uout; q.dt = dt; q.active = active;
+  q.ghost3 = ghost3;
+  q.ghost_ld = d->ghost_ld;
+  q.ghost_block = d->ghost_ld != 0 ? static_cast<int64_t>(d->batch) * d->ghost_ld : 2 * d->g;
+  q.vel = d->velocity; q.vel_l = d->vel_l; q.vel_r = d->vel_r;
   q.k1_out = k1_out; q.k2_out = k2_out;
   q.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
   q.ld = d->ld;
-  q.coef = (1.0 / d->dx) / (d->flux == PSK_FLUX_RUSANOV ? 4.0 : 2.0);  // FluxScale<PSK_EQ_BURGERS, .>
+  q.coef = (1.0 / d->dx) / (d->equation != PSK_EQ_BURGERS ? 1.0 : (d->flux == PSK_FLUX_RUSANOV ? 4.0 : 2.0));  // FluxScale
   q.eps9 = d->eps * (1.0 / 9.0);
   q.dt_stride = static_cast<int>(dt_stride);
   q.n = d->n;
@@ -1196,10 +1200,21 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
                                        dt + static_cast<int64_t>(b0) * dt_stride, dt_stride,
                                        active != nullptr ? active + b0 : nullptr,
                                        maxabs != nullptr ? maxabs + b0 : nullptr, st,
-                                       k1_out != nullptr ? k1_out + o : nullptr, k2_out != nullptr ? k2_out + o : nullptr);
+                                       k1_out != nullptr ? k1_out + o : nullptr, k2_out != nullptr ? k2_out + o : nullptr,
+                                       (ghost3 != nullptr && d->ghost_ld != 0) ? ghost3 + static_cast<int64_t>(b0) * d->ghost_ld
+                                                                               : ghost3);
       if (rc != PSK_OK) return rc;
     }
     return PSK_OK;
+  }
+  if (d->bc == PSK_BC_DIRICHLET) {  // rows with boundary data: default shape only
+    constexpr int kB = PSK_EQ_BURGERS, kUp = PSK_FLUX_UPWIND;
+    if (d->equation == PSK_EQ_ADVECTION) return launch_step_shape<6, kUp, 128, 3, false, PSK_EQ_ADVECTION, true>(q, d->n, batch, mx, st);
+    if (d->equation == PSK_EQ_CONTINUITY) return launch_step_shape<6, kUp, 128, 3, false, PSK_EQ_CONTINUITY, true>(q, d->n, batch, mx, st);
+    if (d->flux == PSK_FLUX_UPWIND) return launch_step_shape<6, kUp, 128, 3, false, kB, true>(q, d->n, batch, mx, st);
+    if (d->flux == PSK_FLUX_ENGQUIST_OSHER)
+      return launch_step_shape<6, PSK_FLUX_ENGQUIST_OSHER, 128, 3, false, kB, true>(q, d->n, batch, mx, st);
+    return launch_step_shape<6, PSK_FLUX_RUSANOV, 128, 3, false, kB, true>(q, d->n, batch, mx, st);
   }
   if (k1_out != nullptr)  // stage values wanted (reverse sweep): Rusanov, default shape
     return launch_step_shape<6, PSK_FLUX_RUSANOV, 128, 3, true>(q, d->n, batch, false, st);
@@ -1387,6 +1402,26 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
       !((d->bc == PSK_BC_PERIODIC && d->g >= 3) || (d->bc == PSK_BC_NONE && d->g >= 9)))
     return PSK_E_UNSUPPORTED;
   return launch_step_fused(d, u, uout, dt, dt_stride, active, maxabs, static_cast<cudaStream_t>(stream));
+}
+
+int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
+                        const double *ghost3, const uint8_t *active, double *maxabs, psk_stream_t stream) {
+  if (d == nullptr) return PSK_E_INVALID;
+  psk_desc d2 = *d;
+  if (ghost3 != nullptr) d2.ghost = ghost3;  // (check_desc wants boundary data for Dirichlet rows)
+  int rc = check_desc(&d2);
+  if (rc != PSK_OK) return rc;
+  if (u == nullptr || uout == nullptr || dt == nullptr || uout == u || ghost3 == nullptr) return PSK_E_INVALID;
+  const bool aligned = (reinterpret_cast<uintptr_t>(u + d->g) % 16 == 0) &&
+                       (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0) && (d->ld % 2 == 0);
+  const bool burgers_ok = d->equation == PSK_EQ_BURGERS && d->nu == nullptr &&
+                          (d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER);
+  const bool linear_ok = d->equation != PSK_EQ_BURGERS && d->flux == PSK_FLUX_UPWIND;
+  if (!(burgers_ok || linear_ok) || d->rec != PSK_REC_WENOJS53 || d->math != PSK_MATH_FAST || !aligned ||
+      g_step_variant == 0 || d->bc != PSK_BC_DIRICHLET || d->g < 3)
+    return PSK_E_UNSUPPORTED;
+  return launch_step_fused(&d2, u, uout, dt, dt_stride, active, maxabs, static_cast<cudaStream_t>(stream), nullptr,
+                           nullptr, ghost3);
 }
 
 int psk_ssprk33_step_stages(const psk_desc *d, const double *u, double *k1, double *k2, double *uout,

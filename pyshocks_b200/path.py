@@ -75,6 +75,7 @@ class HotPath:
         self._nu = None if nu is None else self._table(nu)
         self._vel = self._vel_l = self._vel_r = None
         self._ghost: torch.Tensor | None = None
+        self._ghost3: torch.Tensor | None = None
         self._ghost_ld = 0
         self._work: dict[tuple, torch.Tensor] = {}
         if velocity is not None:
@@ -105,6 +106,7 @@ class HotPath:
     def set_ghost(self, values: np.ndarray | torch.Tensor | None) -> None:
         """Dirichlet values / Neumann offsets for the next calls: ``(2g,)`` shared by all
         rows or ``(batch, 2g)``; left ghosts first (include/psk.h, enum psk_bc)."""
+        self._ghost3 = None
         if values is None:
             self._ghost, self._ghost_ld = None, 0
             return
@@ -113,6 +115,23 @@ class HotPath:
             raise ValueError(f"ghost data needs 2 g = {2 * self.g} values per row")
         self._ghost = gh
         self._ghost_ld = 0 if gh.dim() == 1 else gh.stride(0)
+
+    def ghost3(self, ghosts: Sequence[np.ndarray | torch.Tensor] | torch.Tensor | None = None) -> torch.Tensor | None:
+        """Boundary data of the three stage times as ONE device array ``(3, 2 g)`` or ``(3, batch, 2 g)`` (what
+        ``psk_ssprk33_step_bc`` takes); ``None``: the data of :meth:`set_ghost`, the same at all three times."""
+        if ghosts is None:
+            if self._ghost is None:
+                return None
+            if self._ghost3 is None:
+                self._ghost3 = torch.stack([self._ghost.contiguous()] * 3).contiguous()
+            return self._ghost3
+        if isinstance(ghosts, torch.Tensor):
+            g3 = ghosts.to(device=self.device, dtype=torch.float64).contiguous()
+        else:
+            g3 = torch.stack([self._table(x) for x in ghosts]).contiguous()
+        if g3.shape[0] != 3 or g3.shape[-1] != 2 * self.g or g3.dim() not in (2, 3):
+            raise ValueError(f"ghost data of a step: three sets of 2 g = {2 * self.g} values (per row)")
+        return g3
 
     def desc(self, batch: int, ld: int, *, bc: int | None = None) -> L.PskDesc:
         d = L.PskDesc()
@@ -423,15 +442,33 @@ class HotPath:
         *,
         active: torch.Tensor | None = None,
         maxabs: torch.Tensor | None = None,
+        ghosts: Sequence[np.ndarray | torch.Tensor] | torch.Tensor | None = None,
     ) -> bool:
         """One whole SSPRK33 step (timestepping.py:312-320) in ONE launch, ``u -> uout`` (no aliasing),
-        bit-identical to three :meth:`stage` calls.  Exists for the hot configuration only
-        (``psk_ssprk33_step``): returns ``False`` -- nothing launched -- anywhere else, and the caller
-        runs the three stages.  Rows with ``active == 0`` are copied to ``uout``."""
+        bit-identical to three :meth:`stage` calls.  Exists for the hot configurations only
+        (``psk_ssprk33_step``; ``psk_ssprk33_step_bc`` for Dirichlet rows, ``ghosts`` = their data at
+        ``t, t + dt, t + dt / 2``, default the data of :meth:`set_ghost` at all three): returns ``False`` --
+        nothing launched -- anywhere else, and the caller runs the three stages.  Rows with ``active == 0`` are
+        copied to ``uout``."""
         batch, ld = self._state(u)
         if L.rows_of(uout)[2] != ld:
             raise ValueError("all stage arrays must share one row stride")
         d = self.desc(batch, ld)
+        if self.bc == "dirichlet":
+            g3 = self.ghost3(ghosts)
+            if g3 is None:
+                raise ValueError("Dirichlet rows need boundary data (set_ghost or ghosts=)")
+            if g3.dim() == 3 and g3.shape[1] != batch:
+                raise ValueError("per-row ghost data does not match the batch size")
+            d.ghost, d.ghost_ld = L.ptr(g3), (0 if g3.dim() == 2 else 2 * self.g)
+            rc = L.lib().psk_ssprk33_step_bc(
+                ct.byref(d), L.ptr(u), L.ptr(uout), L.ptr(dt), 0 if dt.numel() == 1 else 1, L.ptr(g3),
+                L.raw_ptr(active), L.ptr(maxabs), L.stream_ptr(),
+            )
+            if rc == L.E_UNSUPPORTED:
+                return False
+            L.check("psk_ssprk33_step_bc", rc)
+            return True
         rc = L.lib().psk_ssprk33_step(
             ct.byref(d), L.ptr(u), L.ptr(uout), L.ptr(dt), 0 if dt.numel() == 1 else 1,
             L.raw_ptr(active), L.ptr(maxabs), L.stream_ptr(),

@@ -195,6 +195,45 @@ int emu_fused_step_stages(int n, int g, int batch, long long ld, double dx, doub
   return 0;
 }
 
+// psk_ssprk33_step_bc: the whole-step kernel on rows with Dirichlet data at the three stage times (ghost3: three
+// blocks of batch * ghost_ld or 2 g doubles), Burgers fluxes or the advection / continuity upwind flux.
+int emu_fused_step_bc(int equation, int flux, int with_max, int n, int g, int batch, long long ld, double dx, double eps,
+                      const double *u, double *uout, const double *dt, int dt_stride, const double *ghost3,
+                      long long ghost_ld, const double *vel, const double *vel_l, const double *vel_r,
+                      unsigned long long *maxabs) {
+  psk::StepParams q{};
+  q.u = u; q.uout = uout; q.dt = dt;
+  q.maxabs = with_max ? maxabs : nullptr;
+  q.ld = ld;
+  q.coef = (1.0 / dx) / (equation != PSK_EQ_BURGERS ? 1.0 : (flux == PSK_FLUX_RUSANOV ? 4.0 : 2.0));
+  q.eps9 = eps * (1.0 / 9.0);
+  q.dt_stride = dt_stride;
+  q.n = n;
+  q.g = g;
+  q.ghost3 = ghost3;
+  q.ghost_ld = ghost_ld;
+  q.ghost_block = ghost_ld != 0 ? static_cast<long long>(batch) * ghost_ld : 2 * g;
+  q.vel = vel; q.vel_l = vel_l; q.vel_r = vel_r;
+  void (*k)(const psk::StepParams) = nullptr;
+  constexpr int kB = PSK_EQ_BURGERS, kUp = PSK_FLUX_UPWIND;
+#define EMU_BC(FL, EQ)                                                                                          \
+  k = with_max ? &psk::step_warp_fused_kernel<6, FL, true, 128, 3, false, EQ, true>                             \
+               : &psk::step_warp_fused_kernel<6, FL, false, 128, 3, false, EQ, true>
+  if (equation == PSK_EQ_ADVECTION && flux == kUp) { EMU_BC(kUp, PSK_EQ_ADVECTION); }
+  else if (equation == PSK_EQ_CONTINUITY && flux == kUp) { EMU_BC(kUp, PSK_EQ_CONTINUITY); }
+  else if (equation == kB && flux == PSK_FLUX_RUSANOV) { EMU_BC(PSK_FLUX_RUSANOV, kB); }
+  else if (equation == kB && flux == kUp) { EMU_BC(kUp, kB); }
+  else if (equation == kB && flux == PSK_FLUX_ENGQUIST_OSHER) { EMU_BC(PSK_FLUX_ENGQUIST_OSHER, kB); }
+  else return -1;
+#undef EMU_BC
+  q.chunks_per_row = (n + psk::StepGeometry<6>::kEmit - 1) / psk::StepGeometry<6>::kEmit;
+  int wpc = 4;
+  if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
+  const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
+  run_grid(gx, static_cast<unsigned>(batch), wpc, [&]() { k(q); });
+  return 0;
+}
+
 int emu_chunks_per_row(int n) { return psk::fast_geometry(n, 8).chunks_per_row; }
 
 }  // extern "C"

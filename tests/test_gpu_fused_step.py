@@ -130,13 +130,57 @@ def test_graph_replay_and_host_to_host_call(nsteps: int) -> None:
     assert torch.equal(c.u[:, G : G + n], ref)
 
 
-@pytest.mark.parametrize("kw", [dict(bc="dirichlet"), dict(flux="lf"), dict(math="strict"), dict(rec="wenojs32")])
+@pytest.mark.parametrize("kw", [dict(bc="neumann"), dict(flux="lf"), dict(math="strict"), dict(rec="wenojs32")])
 def test_other_schemes_keep_the_stage_launches(kw: dict) -> None:
     batch, n = 2, 300
     u0 = _ic(batch, n, seed=2)
     s = _solver(batch, n, **kw)
-    if kw.get("bc") == "dirichlet":
+    if kw.get("bc") == "neumann":
         s.hp.set_ghost(np.zeros(2 * G))
     s.solve_fixed_dt(u0, 1e-4, 2)
     assert s._fused is False and s.launches >= 6
     assert bool(torch.isfinite(s.u[:, G : G + n]).all())
+
+
+@pytest.mark.parametrize("equation,flux", [("burgers", "rusanov"), ("burgers", "godunov"), ("burgers", "eo"),
+                                           ("advection", "godunov"), ("continuity", "godunov")])
+@pytest.mark.parametrize("batch,n,nsteps,per_row", [(4, 4096, 5, True), (3, 333, 4, False), (2, 172, 3, True), (1, 16, 2, False)])
+def test_whole_step_on_dirichlet_rows(equation: str, flux: str, batch: int, n: int, nsteps: int, per_row: bool) -> None:
+    """psk_ssprk33_step_bc: Dirichlet rows (Burgers fluxes, advection, continuity) in one launch per step, the same
+    bits as three stage launches; EnsembleSolver picks it by itself (time-independent data of set_ghost)"""
+    rng = np.random.default_rng(n)
+    u0 = _ic(batch, n, seed=n + 1)
+    kw = {}
+    if equation != "burgers":
+        x = (np.arange(n + 2 * G) - G + 0.5) / n
+        kw["velocity"] = 1.0 + 0.4 * np.sin(2 * np.pi * x + 0.2)
+    ghost = rng.uniform(-0.3, 0.3, size=(batch, 2 * G) if per_row else (2 * G,))
+    dt = 0.3 * (3.0 / n) / max(float(u0.abs().max()), 1.5)
+    with whole_step(7000):
+        a = _solver(batch, n, equation=equation, flux=flux, bc="dirichlet", **kw)
+        a.hp.set_ghost(ghost)
+        a.solve_fixed_dt(u0, dt, nsteps)
+        assert a._fused is False and a.launches == 3 * nsteps
+    b = _solver(batch, n, equation=equation, flux=flux, bc="dirichlet", **kw)
+    b.hp.set_ghost(ghost)
+    b.solve_fixed_dt(u0, dt, nsteps)
+    assert b._fused is True and b.launches == nsteps
+    assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
+
+
+def test_whole_step_with_time_dependent_dirichlet_data() -> None:
+    """the data of the three stage times differ (g(t, x) of the drivers): HotPath.step_fused(ghosts=...) against
+    HotPath.ssprk33_step(ghosts=...) (three launches)"""
+    from pyshocks_b200.path import HotPath
+
+    n, batch = 1000, 3
+    hp = HotPath(equation="burgers", flux="rusanov", rec="wenojs53", bc="dirichlet", n=n, g=G, dx=3.0 / n, eps=1e-12)
+    s = _solver(batch, n, bc="dirichlet")
+    u, out = s.new_states(2)
+    u.copy_(_ic(batch, n, seed=5))
+    rng = np.random.default_rng(0)
+    ghosts = [rng.uniform(-0.3, 0.3, size=(batch, 2 * G)) for _ in range(3)]
+    dt = torch.full((1,), 0.3 * (3.0 / n) / 1.5, dtype=torch.float64, device="cuda")
+    assert hp.step_fused(u, out, dt, ghosts=ghosts)
+    ref = hp.ssprk33_step(u, dt, ghosts=ghosts)
+    assert torch.equal(out[:, G : G + n], ref[:, G : G + n])

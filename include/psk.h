@@ -191,6 +191,15 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
 int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
                         const double *ghost3, const uint8_t *active, double *maxabs, psk_stream_t stream);
 
+/* `nsteps` whole-step launches (psk_ssprk33_step, or psk_ssprk33_step_bc for Dirichlet rows) enqueued back to
+ * back from one call, every state written straight onto the tape: tape[0 * tape_stride ..] holds the initial state,
+ * on return tape[m * tape_stride ..] the state after m steps -- the InMemoryCheckpoint contents of
+ * timestepping.step (timestepping.py:130-131) for step sizes known in advance, without a copy.  dt_table,
+ * ghost_table as in psk_solve_rows_tables.  PSK_E_UNSUPPORTED (nothing launched) where the whole-step kernel
+ * does not exist. */
+int psk_ssprk33_steps_tape(const psk_desc *d, double *tape, int64_t tape_stride, int nsteps, const double *dt_table,
+                           const double *ghost_table, psk_stream_t stream);
+
 /* psk_ssprk33_step that also stores the stage values k1, k2 (timestepping.py:314-317) -- what the reverse
  * sweep recomputes from a checkpointed state before its three psk_ssprk33_stage_adjoint calls -- in one
  * launch instead of two or three.  uout may be NULL (only k1, k2 wanted: the third stage is skipped).

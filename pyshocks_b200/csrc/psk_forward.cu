@@ -1424,6 +1424,27 @@ int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const 
                            nullptr, ghost3);
 }
 
+/* nsteps whole-step launches back to back, every state written straight onto the tape (no copies, no host
+ * round trip): tape[0] = initial state (in), tape[m] = state after m steps (out). */
+int psk_ssprk33_steps_tape(const psk_desc *d, double *tape, int64_t tape_stride, int nsteps, const double *dt_table,
+                           const double *ghost_table, psk_stream_t stream) {
+  if (d == nullptr || tape == nullptr || dt_table == nullptr || nsteps <= 0 || tape_stride <= 0) return PSK_E_INVALID;
+  if (d->bc == PSK_BC_DIRICHLET && ghost_table == nullptr) return PSK_E_INVALID;
+  const int64_t ghost_block = d->ghost_ld != 0 ? static_cast<int64_t>(d->batch) * d->ghost_ld : 2 * d->g;
+  for (int m = 0; m < nsteps; ++m) {
+    const double *u = tape + static_cast<int64_t>(m) * tape_stride;
+    double *un = tape + static_cast<int64_t>(m + 1) * tape_stride;
+    int rc;
+    if (d->bc == PSK_BC_DIRICHLET)
+      rc = psk_ssprk33_step_bc(d, u, un, dt_table + m, 0, ghost_table + static_cast<int64_t>(3) * m * ghost_block, nullptr,
+                               nullptr, stream);
+    else
+      rc = psk_ssprk33_step(d, u, un, dt_table + m, 0, nullptr, nullptr, stream);
+    if (rc != PSK_OK) return rc;  // (PSK_E_UNSUPPORTED can only come from the first step: nothing has run then)
+  }
+  return PSK_OK;
+}
+
 int psk_ssprk33_step_stages(const psk_desc *d, const double *u, double *k1, double *k2, double *uout,
                             const double *dt, int64_t dt_stride, psk_stream_t stream) {
   int rc = check_desc(d);

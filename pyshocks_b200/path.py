@@ -371,6 +371,36 @@ class HotPath:
         )
         return {"t": t_out, "steps": steps, "tape": tp}
 
+    def steps_tape(self, u0: torch.Tensor, dts: torch.Tensor, ghost_table: torch.Tensor | None = None) -> torch.Tensor | None:
+        """``nsteps`` whole-step launches from one call (``psk_ssprk33_steps_tape``), every state written straight
+        onto a freshly allocated tape with the aligned row layout: returns the ``(nsteps + 1, batch, nx)`` view of
+        the states (``[0]`` = ``u0``, ``[-1]`` = the final state), or ``None`` -- nothing launched -- where the
+        whole-step kernel does not exist."""
+        from .ensemble import row_layout
+
+        if u0.dim() == 1:
+            u0 = u0[None, :]
+        batch, nx = u0.shape
+        if nx != self.nx:
+            raise ValueError(f"array has {nx} cells per row, grid has nx = {self.nx}")
+        nsteps = int(dts.numel())
+        col0, ld = row_layout(self.n, self.g)
+        # (zeros: the whole-step kernel writes interior cells only; stored ghost cells are never read)
+        store = torch.zeros((nsteps + 1, batch, ld), dtype=torch.float64, device=u0.device)
+        tape = store[:, :, col0 : col0 + nx]
+        tape[0].copy_(u0)
+        d = self.desc(batch, ld)
+        if ghost_table is not None:
+            if tuple(ghost_table.shape) != (nsteps, 3, 2 * self.g) or not ghost_table.is_contiguous():
+                raise ValueError(f"ghost_table must be contiguous of shape {(nsteps, 3, 2 * self.g)}")
+            d.ghost, d.ghost_ld = L.ptr(ghost_table), 0
+        rc = L.lib().psk_ssprk33_steps_tape(ct.byref(d), L.ptr(tape), batch * ld, nsteps, L.ptr(dts), L.ptr(ghost_table),
+                                            L.stream_ptr())
+        if rc == L.E_UNSUPPORTED:
+            return None
+        L.check("psk_ssprk33_steps_tape", rc)
+        return tape
+
     def adjoint_sweep(self, tape: torch.Tensor, dts: torch.Tensor, p: torch.Tensor, *,
                       ghost_table: torch.Tensor | None = None, p_boundary: "HotPath | None" = None,
                       history: bool = False) -> torch.Tensor | None:
@@ -380,14 +410,18 @@ class HotPath:
         :meth:`solve_rows_tables`; ``p_boundary``: the binding whose boundary kind (and ghost data) is imposed on
         ``p`` after every step.  Returns every intermediate ``p`` (``(nsteps, batch, ld)``) if ``history``."""
         nsteps = int(dts.numel())
-        if tape.dim() != 3 or tape.shape[0] < nsteps + 1 or not tape.is_contiguous():
-            raise ValueError("tape must be contiguous of shape (nsteps + 1, batch, ld)")
-        batch, ld = tape.shape[1], tape.shape[2]
+        if tape.dim() != 3 or tape.shape[0] < nsteps + 1 or tape.shape[2] != self.nx or tape.stride(2) != 1:
+            raise ValueError("tape must be (nsteps + 1, batch, nx) with unit stride along x")
+        batch, ld = tape.shape[1], (tape.stride(1) if tape.shape[1] > 1 else max(tape.stride(1), self.nx))
         pb, pnx, pld = L.rows_of(p)
-        if (pb, pnx, pld if pb > 1 else ld) != (batch, self.nx, ld):
+        if (pb, pnx) != (batch, self.nx) or (pb > 1 and pld != ld):
             raise ValueError("p must be a (batch, nx) view with the row stride of the tape")
         dev = tape.device
-        states = torch.empty((5, batch, ld), dtype=torch.float64, device=dev)
+        # scratch with the row layout of the tape (same stride, same offset of the first cell modulo 16 bytes)
+        lead = (tape.data_ptr() // 8) % 2
+        flat = torch.empty((5 * batch * ld + lead + 2,), dtype=torch.float64, device=dev)
+        off = (lead - (flat.data_ptr() // 8) % 2) % 2
+        states = flat[off : off + 5 * batch * ld]
         hist = torch.empty((nsteps, batch, ld), dtype=torch.float64, device=dev) if history else None
         d = self.desc(batch, ld)
         if ghost_table is not None:
@@ -398,10 +432,11 @@ class HotPath:
         L.check(
             "psk_ssprk33_adjoint_sweep",
             L.lib().psk_ssprk33_adjoint_sweep(
-                ct.byref(d), L.ptr(tape), batch * ld, nsteps, L.ptr(dts), L.ptr(ghost_table),
+                ct.byref(d), L.ptr(tape), tape.stride(0), nsteps, L.ptr(dts), L.ptr(ghost_table),
                 ct.byref(pd) if pd is not None else None, L.ptr(p), L.ptr(states), L.ptr(self._adj_work(batch)),
                 L.ptr(self._lf_work(batch)), L.ptr(hist), L.stream_ptr()),
         )
+        return None if hist is None else hist[:, :, : self.nx]
         return hist
 
     # }}}

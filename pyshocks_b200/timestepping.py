@@ -383,15 +383,29 @@ def solve(
         dts, ts = step_sizes(theta * float(predict_timestep(scheme, grid, bc, 0.0, u)), tfinal, maxit)
         dts_dev = torch.tensor(dts, dtype=torch.float64, device=u.device)
         table = ghost_table(bc, grid, ts, dts)
-        out = hp.solve_rows_tables(u, dts_dev, table, tape=checkpoint)
+        tape = hp.steps_tape(u, dts_dev, table) if checkpoint else None
+        if tape is not None:
+            # one whole-step launch per step, enqueued from one call, every state written straight onto the tape.
+            # The whole-step kernel writes INTERIOR cells only: the ghost cells of these states are zero, not the
+            # values the reference's full-array advance leaves there (zero-padded stencils plus the ghost values
+            # carried over from step to step, schemes.py:346) -- numbers no later step and no adjoint step reads:
+            # every right-hand side starts by overwriting the ghost cells (schemes.py:343)
+            u = tape[len(dts), 0].clone() if u.dim() == 1 else tape[len(dts)].clone()
+            out = {"t": torch.full((tape.shape[1],), ts[-1] + dts[-1], dtype=torch.float64, device=u.device),
+                   "steps": torch.full((tape.shape[1],), len(dts), dtype=torch.int32, device=u.device), "tape": tape}
+        else:
+            out = hp.solve_rows_tables(u, dts_dev, table, tape=checkpoint)
         out["dt"] = dts_dev[None, :]
         out["ghost_table"], out["ts"] = table, ts
     steps = out["steps"]
     if bool((steps < 0).any()):
         raise ValueError("Time step is not finite.")  # timestepping.py:144-145
     nmax = int(steps.max())
+    tape = out["tape"]
+    if tape is not None and tape.shape[-1] != hp.nx:
+        tape = tape[..., : hp.nx]
     res = {"u": u, "t": out["t"], "iteration": steps, "dt": out["dt"][..., :nmax],
-           "states": None if out["tape"] is None else out["tape"][: nmax + 1]}
+           "states": None if tape is None else tape[: nmax + 1]}
     if "ghost_table" in out:
         res["ghost_table"], res["ts"] = out["ghost_table"], out["ts"]
     return res
@@ -495,13 +509,15 @@ def adjoint_solve(
         if gd is not None:
             pb.set_ghost(gd)
         p = pb.apply_boundary(p)  # timestepping.py:186-187
-    # p must share the row stride of the tape
-    buf = torch.zeros((1, tape.shape[2]), dtype=torch.float64, device=p.device) if p.dim() == 1 else None
-    if buf is not None:
-        buf[0, : hp.nx] = p
-        pv = buf[:, : hp.nx]
-    else:
-        pv = p
-    hist = hp.adjoint_sweep(tape.contiguous(), dts, pv, ghost_table=table, p_boundary=pb, history=history)
-    out_p = pv[0].clone() if p0.dim() == 1 else pv
-    return {"p": out_p, "history": None if hist is None else (hist[:, 0, : hp.nx] if p0.dim() == 1 else hist[..., : hp.nx])}
+    # p gets the row layout of the tape (same stride, same position of the first cell in its row)
+    batch = tape.shape[1]
+    ld = tape.stride(1) if batch > 1 else max(tape.stride(1), hp.nx)
+    col = tape.storage_offset() % ld if ld > hp.nx else 0
+    if col + hp.nx > ld:
+        col = 0
+    pbuf = torch.zeros((batch, ld), dtype=torch.float64, device=p.device)
+    pv = pbuf[:, col : col + hp.nx]
+    pv.copy_(p if p.dim() == 2 else p[None, :])
+    hist = hp.adjoint_sweep(tape, dts, pv, ghost_table=table, p_boundary=pb, history=history)
+    out_p = pv[0].clone() if p0.dim() == 1 else pv.clone()
+    return {"p": out_p, "history": None if hist is None else (hist[:, 0] if p0.dim() == 1 else hist)}

@@ -187,9 +187,12 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
  * set for all rows), left ghost cells first; d->ghost is ignored.  Burgers + {Rusanov (nu = 1), upwind,
  * Engquist-Osher}, advection, continuity (upwind flux); WENO-JS5, FAST math, 16-byte aligned rows;
  * PSK_E_UNSUPPORTED elsewhere.  Same bits as three psk_ssprk33_stage calls with those data.  active / maxabs
- * as in psk_ssprk33_step. */
+ * as in psk_ssprk33_step.  k1_out / k2_out (both or neither; then active = maxabs = NULL): the stage values are
+ * stored as well, as psk_ssprk33_step_stages does for periodic rows, and uout may be NULL (third stage skipped):
+ * the recomputation of the reverse sweep in one launch. */
 int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
-                        const double *ghost3, const uint8_t *active, double *maxabs, psk_stream_t stream);
+                        const double *ghost3, const uint8_t *active, double *maxabs, double *k1_out, double *k2_out,
+                        psk_stream_t stream);
 
 /* `nsteps` whole-step launches (psk_ssprk33_step, or psk_ssprk33_step_bc for Dirichlet rows) enqueued back to
  * back from one call, every state written straight onto the tape: tape[0 * tape_stride ..] holds the initial state,

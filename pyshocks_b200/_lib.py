@@ -103,7 +103,7 @@ def _load() -> ct.CDLL:
         "psk_max_abs": ([D, vp, ct.c_int, vp, vp], ct.c_int),
         "psk_ssprk33_stage": ([D, ct.c_int, vp, vp, vp, vp, i64, vp, vp, vp, ct.c_int, vp], ct.c_int),
         "psk_ssprk33_step": ([D, vp, vp, vp, i64, vp, vp, vp], ct.c_int),
-        "psk_ssprk33_step_bc": ([D, vp, vp, vp, i64, vp, vp, vp, vp], ct.c_int),
+        "psk_ssprk33_step_bc": ([D, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp], ct.c_int),
         "psk_ssprk33_steps_tape": ([D, vp, i64, ct.c_int, vp, vp, vp], ct.c_int),
         "psk_ssprk33_step_stages": ([D, vp, vp, vp, vp, vp, i64, vp], ct.c_int),
         "psk_ssprk33_step_adjoint": ([D, vp, vp, vp, i64, vp, vp, vp, vp], ct.c_int),

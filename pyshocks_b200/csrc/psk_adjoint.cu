@@ -644,9 +644,18 @@ int psk_ssprk33_adjoint_sweep(const psk_desc *d, const double *tape, int64_t tap
     psk_desc ds[3] = {*d, *d, *d};  // boundary data at t, t + dt, t + dt / 2
     if (ghost_table != nullptr)
       for (int s = 0; s < 3; ++s) ds[s].ghost = ghost_table + (static_cast<int64_t>(3) * m + s) * ghost_block;
-    rc = psk_ssprk33_stage(&ds[0], 1, u, u, k1, dt, 0, nullptr, lf_work, nullptr, 1, stream);
-    if (rc != PSK_OK) return rc;
-    rc = psk_ssprk33_stage(&ds[1], 2, u, k1, k2, dt, 0, nullptr, lf_work, nullptr, 1, stream);
+    // k1, k2 of the checkpointed state: one launch where the whole-step kernel exists, else two stage launches
+    // (the stored ghost cells of k1, k2 are never read: every stage kernel applies the boundary condition itself)
+    rc = PSK_E_UNSUPPORTED;
+    if (d->bc == PSK_BC_DIRICHLET && ghost_table != nullptr)
+      rc = psk_ssprk33_step_bc(d, u, nullptr, dt, 0, ds[0].ghost, nullptr, nullptr, k1, k2, stream);
+    else if (d->bc == PSK_BC_PERIODIC)
+      rc = psk_ssprk33_step_stages(d, u, k1, k2, nullptr, dt, 0, stream);
+    if (rc == PSK_E_UNSUPPORTED) {
+      rc = psk_ssprk33_stage(&ds[0], 1, u, u, k1, dt, 0, nullptr, lf_work, nullptr, 0, stream);
+      if (rc != PSK_OK) return rc;
+      rc = psk_ssprk33_stage(&ds[1], 2, u, k1, k2, dt, 0, nullptr, lf_work, nullptr, 0, stream);
+    }
     if (rc != PSK_OK) return rc;
     rc = run_adjoint(&ds[2], k2, cur, dt, 0, 2.0 / 3.0, 2.0 / 3.0, nullptr, 0.0, nullptr, 0.0, work, lam2, st);
     if (rc != PSK_OK) return rc;

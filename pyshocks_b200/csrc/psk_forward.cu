@@ -1207,6 +1207,15 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     }
     return PSK_OK;
   }
+  if (d->bc == PSK_BC_DIRICHLET && k1_out != nullptr) {  // ... with the stage values stored (reverse sweep)
+    constexpr int kB = PSK_EQ_BURGERS, kUp = PSK_FLUX_UPWIND;
+    if (d->equation == PSK_EQ_ADVECTION) return launch_step_shape<6, kUp, 128, 3, true, PSK_EQ_ADVECTION, true>(q, d->n, batch, false, st);
+    if (d->equation == PSK_EQ_CONTINUITY) return launch_step_shape<6, kUp, 128, 3, true, PSK_EQ_CONTINUITY, true>(q, d->n, batch, false, st);
+    if (d->flux == PSK_FLUX_UPWIND) return launch_step_shape<6, kUp, 128, 3, true, kB, true>(q, d->n, batch, false, st);
+    if (d->flux == PSK_FLUX_ENGQUIST_OSHER)
+      return launch_step_shape<6, PSK_FLUX_ENGQUIST_OSHER, 128, 3, true, kB, true>(q, d->n, batch, false, st);
+    return launch_step_shape<6, PSK_FLUX_RUSANOV, 128, 3, true, kB, true>(q, d->n, batch, false, st);
+  }
   if (d->bc == PSK_BC_DIRICHLET) {  // rows with boundary data: default shape only
     constexpr int kB = PSK_EQ_BURGERS, kUp = PSK_FLUX_UPWIND;
     if (d->equation == PSK_EQ_ADVECTION) return launch_step_shape<6, kUp, 128, 3, false, PSK_EQ_ADVECTION, true>(q, d->n, batch, mx, st);
@@ -1405,23 +1414,27 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
 }
 
 int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
-                        const double *ghost3, const uint8_t *active, double *maxabs, psk_stream_t stream) {
+                        const double *ghost3, const uint8_t *active, double *maxabs, double *k1_out, double *k2_out,
+                        psk_stream_t stream) {
   if (d == nullptr) return PSK_E_INVALID;
   psk_desc d2 = *d;
   if (ghost3 != nullptr) d2.ghost = ghost3;  // (check_desc wants boundary data for Dirichlet rows)
   int rc = check_desc(&d2);
   if (rc != PSK_OK) return rc;
-  if (u == nullptr || uout == nullptr || dt == nullptr || uout == u || ghost3 == nullptr) return PSK_E_INVALID;
-  const bool aligned = (reinterpret_cast<uintptr_t>(u + d->g) % 16 == 0) &&
-                       (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0) && (d->ld % 2 == 0);
+  if (u == nullptr || dt == nullptr || uout == u || ghost3 == nullptr) return PSK_E_INVALID;
+  if ((k1_out == nullptr) != (k2_out == nullptr) || (uout == nullptr && k1_out == nullptr)) return PSK_E_INVALID;
+  if (k1_out != nullptr && (active != nullptr || maxabs != nullptr || k1_out == u || k2_out == u || k1_out == k2_out))
+    return PSK_E_INVALID;
+  auto al = [&](const double *a) { return a == nullptr || reinterpret_cast<uintptr_t>(a + d->g) % 16 == 0; };
+  const bool aligned = al(u) && al(uout) && al(k1_out) && al(k2_out) && (d->ld % 2 == 0);
   const bool burgers_ok = d->equation == PSK_EQ_BURGERS && d->nu == nullptr &&
                           (d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER);
   const bool linear_ok = d->equation != PSK_EQ_BURGERS && d->flux == PSK_FLUX_UPWIND;
   if (!(burgers_ok || linear_ok) || d->rec != PSK_REC_WENOJS53 || d->math != PSK_MATH_FAST || !aligned ||
       g_step_variant == 0 || d->bc != PSK_BC_DIRICHLET || d->g < 3)
     return PSK_E_UNSUPPORTED;
-  return launch_step_fused(&d2, u, uout, dt, dt_stride, active, maxabs, static_cast<cudaStream_t>(stream), nullptr,
-                           nullptr, ghost3);
+  return launch_step_fused(&d2, u, uout, dt, dt_stride, active, maxabs, static_cast<cudaStream_t>(stream), k1_out,
+                           k2_out, ghost3);
 }
 
 /* nsteps whole-step launches back to back, every state written straight onto the tape (no copies, no host
@@ -1437,7 +1450,7 @@ int psk_ssprk33_steps_tape(const psk_desc *d, double *tape, int64_t tape_stride,
     int rc;
     if (d->bc == PSK_BC_DIRICHLET)
       rc = psk_ssprk33_step_bc(d, u, un, dt_table + m, 0, ghost_table + static_cast<int64_t>(3) * m * ghost_block, nullptr,
-                               nullptr, stream);
+                               nullptr, nullptr, nullptr, stream);
     else
       rc = psk_ssprk33_step(d, u, un, dt_table + m, 0, nullptr, nullptr, stream);
     if (rc != PSK_OK) return rc;  // (PSK_E_UNSUPPORTED can only come from the first step: nothing has run then)

@@ -498,7 +498,7 @@ class HotPath:
             d.ghost, d.ghost_ld = L.ptr(g3), (0 if g3.dim() == 2 else 2 * self.g)
             rc = L.lib().psk_ssprk33_step_bc(
                 ct.byref(d), L.ptr(u), L.ptr(uout), L.ptr(dt), 0 if dt.numel() == 1 else 1, L.ptr(g3),
-                L.raw_ptr(active), L.ptr(maxabs), L.stream_ptr(),
+                L.raw_ptr(active), L.ptr(maxabs), None, None, L.stream_ptr(),
             )
             if rc == L.E_UNSUPPORTED:
                 return False

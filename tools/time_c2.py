@@ -113,11 +113,13 @@ print(json.dumps({
     "config": f"BASELINE configs[1]: advection godunov + wenojs53, Dirichlet exact solution, n = {n}, theta = 0.75, t = 1",
     "steps": nsteps, "cells": n,
     "single_call": {"forward_s": t_fwd, "reverse_s": t_rev, "gradients_per_s": 1.0 / (t_fwd + t_rev),
-                    "device_forward_s": dev_fwd, "device_reverse_s": dev_rev,
-                    "device_gradients_per_s": 1.0 / (dev_fwd + dev_rev),
-                    "forward_cell_updates_per_s": n * nsteps / dev_fwd, "adjoint_cell_updates_per_s": n * nsteps / dev_rev,
-                    "note": "wall clock includes the host evaluation of the user's boundary function at 3 x steps stage "
-                            "times (forward) and the tables of the reverse sweep; device = the two launches / calls alone"},
+                    "forward_cell_updates_per_s": n * nsteps / t_fwd, "adjoint_cell_updates_per_s": n * nsteps / t_rev,
+                    "one_cta_forward_device_s": dev_fwd, "sweep_on_unaligned_tape_device_s": dev_rev,
+                    "note": "wall clock of timestepping.solve(checkpoint=True) (one whole-step launch per step written "
+                            "straight onto the tape, all enqueued from one call) and timestepping.adjoint_solve (5 launches "
+                            "per reverse step from one call), including the host evaluation of the user's boundary "
+                            "function at the 3 x steps stage times; one_cta_forward = psk_solve_rows_tables (the whole "
+                            "loop in ONE launch by one thread block, state in shared memory) for comparison"},
     "step_by_step_api": {"forward_s": t_api_fwd, "reverse_s": t_api_rev, "gradients_per_s": 1.0 / (t_api_fwd + t_api_rev),
                          "same_bits_as_single_call": same},
     "cpu_port_forward_s": t_c, "cpu_port_cell_updates_per_s": n * nsteps / t_c, "cpu_cores": 1,

@@ -219,7 +219,10 @@ int psk_ssprk33_step_stages(const psk_desc *d, const double *u, double *k1, doub
  * (24 B of DRAM traffic per cell instead of the 144 B of five launches).  Rows are periodic RINGS of
  * the n interior cells: only interior cells of u, p_in are read and only interior cells of p_out are
  * written (the gradient of the interior -> interior map; no cotangent lives on ghost cells).
- * Burgers + Rusanov (nu = 1) + WENO-JS5, FAST math, periodic, 16-byte aligned rows, n even;
+ * Boundary kind NONE with g >= 16 ghost cells: the row is a SLAB of a larger grid, the ghost cells of u and p_in
+ * hold the neighbouring slabs' edge cells (the caller's exchange, e.g. psk_halo_push) and p_out is the slab's
+ * part of the gradient -- the transposed stencil needs no "send back and add", every slab gathers.
+ * Burgers + Rusanov (nu = 1) + WENO-JS5, FAST math, periodic or NONE, 16-byte aligned rows, n even;
  * PSK_E_UNSUPPORTED elsewhere (recompute with psk_ssprk33_step_stages and call
  * psk_ssprk33_stage_adjoint three times instead).  k1_out / k2_out: optional (both or neither), the
  * recomputed stage values of the interior cells, bit-identical to psk_ssprk33_stage.

@@ -58,8 +58,8 @@ int psk_ssprk33_step_adjoint(const psk_desc *d, const double *u, const double *p
   auto al = [&](const double *a) { return a == nullptr || reinterpret_cast<uintptr_t>(a + d->g) % 16 == 0; };
   const bool aligned = al(u) && al(p_in) && al(p_out) && al(k1_out) && al(k2_out) && (d->ld % 2 == 0);
   if (d->equation != PSK_EQ_BURGERS || d->flux != PSK_FLUX_RUSANOV || d->rec != PSK_REC_WENOJS53 ||
-      d->math != PSK_MATH_FAST || d->nu != nullptr || d->bc != PSK_BC_PERIODIC || d->g < 3 || !aligned ||
-      d->n % 2 != 0 || d->n < 8)
+      d->math != PSK_MATH_FAST || d->nu != nullptr || !aligned || d->n % 2 != 0 || d->n < 8 ||
+      !((d->bc == PSK_BC_PERIODIC && d->g >= 3) || (d->bc == PSK_BC_NONE && d->g >= kRevHalo)))
     return PSK_E_UNSUPPORTED;
   RevParams p{};
   p.u = u; p.pin = p_in; p.pout = p_out; p.dt = dt; p.dt_stride = dt_stride; p.ld = d->ld;
@@ -67,6 +67,7 @@ int psk_ssprk33_step_adjoint(const psk_desc *d, const double *u, const double *p
   p.eps = d->eps;
   p.n = d->n; p.g = d->g;
   p.dbg_k1 = k1_out; p.dbg_k2 = k2_out;
+  p.bc_none = d->bc == PSK_BC_NONE ? 1 : 0;
   int C = g_reverse_variant;
   if (C == 0) {  // least redundant work; ties go to the shorter run (more warps per SM)
     C = 12;

@@ -55,7 +55,9 @@ struct RevParams {
   double invdx, eps;
   int n, g;
   int tiles_per_row;
-  double *dbg_k1, *dbg_k2;  // tests only: the recomputed stage values of the stored cells (or nullptr)
+  double *dbg_k1, *dbg_k2;  // optional: the recomputed stage values of the stored cells (or nullptr)
+  int bc_none;              // 1: a slab of a larger grid -- window cells beyond the row ends are the row's STORED ghost
+                            // cells (g >= 16, filled by the neighbouring slabs) instead of the periodic images
 };
 
 constexpr int kRevHalo = 16;   // invalid window cells per side (15 needed)
@@ -337,7 +339,15 @@ __device__ __forceinline__ void rev_adjoint_stage(const int MODE, const LaneArra
 // run cells -2 .. C + 1 of one global array into a window array (periodic images beyond the row ends)
 template <int C>
 __device__ __forceinline__ void rev_load_run(const double *__restrict__ src, int64_t base, int r0, int n, bool inside,
-                                             const LaneArray D) {
+                                             const LaneArray D, int none_g = 0) {
+  if (none_g > 0 && !inside) {  // slab: stored ghost cells; further out never reaches a stored cell
+#pragma unroll 1
+    for (int j = -2; j < C + 2; ++j) {
+      const int c = r0 + j;
+      D.st1(j, (c >= -none_g && c < n + none_g) ? src[base + c] : 0.0);
+    }
+    return;
+  }
   if (inside) {
 #pragma unroll
     for (int k = 0; k < RevGeometry<C>::kPairs; ++k) {
@@ -368,9 +378,10 @@ reverse_step_kernel(const RevParams p) {
   double *park = reinterpret_cast<double *>(smem + 3 * (Geo::kArrayDoubles / 2)) + lane;
   const int64_t base = static_cast<int64_t>(row) * p.ld + p.g;
   const int r0 = tile * Geo::kEmit - kRevHalo + C * lane;  // ring coordinate of the lane's first cell
-  const bool inside = (r0 - 2 >= 0) && (r0 + C + 2 <= n);
+  const int none_g = p.bc_none ? p.g : 0;
+  const bool inside = (r0 - 2 >= -none_g) && (r0 + C + 2 <= n + none_g);
 
-  rev_load_run<C>(p.u, base, r0, n, inside, P0);
+  rev_load_run<C>(p.u, base, r0, n, inside, P0, none_g);
 #ifndef PSK_HOST_EMU
   if (inside) {  // p' is needed after the recomputation: have its lines on their way
 #pragma unroll
@@ -402,7 +413,7 @@ reverse_step_kernel(const RevParams p) {
   const double hs = 0.5 * p.invdx * dt;
 #pragma unroll 1
   for (int ph = 0; ph < 3; ++ph) {
-    if (ph != 1) rev_load_run<C>(ph == 0 ? p.pin : p.u, base, r0, n, inside, ph == 0 ? P0 : P2);
+    if (ph != 1) rev_load_run<C>(ph == 0 ? p.pin : p.u, base, r0, n, inside, ph == 0 ? P0 : P2, none_g);
     const double cv = (ph == 0) ? (2.0 / 3.0) : ((ph == 1) ? 0.25 : 1.0);
     const LaneArray X = (ph == 1) ? P1 : P2, V = (ph == 0) ? P0 : ((ph == 1) ? P2 : P1), OUT = (ph == 0) ? P2 : ((ph == 1) ? P1 : P0);
     rev_adjoint_stage<C>(ph == 0 ? 1 : (ph == 1 ? 0 : 2), X, V, OUT, P0, cv, cv * hs, eps9, park);

@@ -677,3 +677,186 @@ class PeerSlabSolver:
 
 
 # }}}
+
+
+# {{{ discrete adjoint on slabs
+
+
+class PeerSlabAdjoint:
+    """Forward sweep with a device tape and the discrete-adjoint reverse sweep of ONE periodic Burgers grid
+    (WENO-JS5 + Rusanov + SSPRK33, fixed ``dt``) that is slab-decomposed over the ranks -- the adjoint of
+    BASELINE config 4 ("adjoint on slabs").
+
+    Every array of a rank carries 16 ghost cells per side in peer-visible memory:
+
+    * forward: one whole-step launch per step (``psk_ssprk33_step``, boundary kind NONE) writes state ``m + 1``
+      straight onto the tape, and ``psk_halo_push`` stores its 16 edge cells into the neighbours' ghost slots
+      of THEIR tape entry ``m + 1`` -- so every checkpoint already holds the neighbours' cells the reverse
+      sweep will need;
+    * reverse: one launch per step (``psk_ssprk33_step_adjoint``, boundary kind NONE) GATHERS the slab's part of
+      ``p^m = (d u^{m+1} / d u^m)^T p^{m+1}`` from ``u^m`` and ``p^{m+1}`` of the slab plus 16 cells of either
+      neighbour; then the 16 edge cells of ``p^m`` go to the neighbours.  SURVEY.md 8(e) sketched the scatter
+      form (ghost contributions "sent back and added" to the owner); recomputing the 16-cell overlap instead
+      needs one exchange per step in the same direction as the forward one and no atomics or adds.
+
+    Epoch flags order the exchange exactly as in :class:`PeerSlabSolver` (``psk_halo_wait`` before a step,
+    ``psk_halo_push`` after it); a neighbour's ghost slots are only overwritten after its push of the step that
+    read them has been observed."""
+
+    G = 16
+
+    def __init__(self, *, n_global: int, rank: int, world: int, dx: float, nsteps: int, eps: float = 1.0e-12,
+                 device: torch.device | str | None = None, timeout_s: float = 20.0) -> None:
+        import ctypes as ct
+
+        if n_global % (2 * world) != 0:
+            raise ValueError("the slab adjoint needs equal slabs of even length (n_global % (2 world) == 0)")
+        self.rank, self.world, self.nsteps = rank, world, int(nsteps)
+        self.first, self.n_local = shard_rows(n_global, rank, world)
+        g = self.G
+        if self.n_local < 2 * g:
+            raise ValueError("slabs must hold at least 32 cells")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = dev
+        self.col0, self.ld = row_layout(self.n_local, g)
+        self.narrays = self.nsteps + 3  # tape 0 .. nsteps, p ping, p pong
+        self.words = self.narrays * self.ld + _FLAG_WORDS
+        ptr = ct.c_void_p()
+        handle = ct.create_string_buffer(64)
+        with torch.cuda.device(dev):
+            L.check("psk_p2p_alloc", L.lib().psk_p2p_alloc(8 * self.words, ct.byref(ptr), handle))
+        self.ptr, self.handle = int(ptr.value), bytes(handle.raw)
+        self._raw = _RawDeviceMemory(self.ptr, self.words, "<f8")
+        flat = torch.as_tensor(self._raw, device=dev)
+        flat.zero_()
+        self.nx = self.n_local + 2 * g
+        self.arrays = flat[: self.narrays * self.ld].view(self.narrays, 1, self.ld)[:, :, self.col0 : self.col0 + self.nx]
+        self.hp = HotPath(equation="burgers", flux="rusanov", rec="wenojs53", bc="none", n=self.n_local, g=g, dx=dx,
+                          eps=eps, math="fast", device=dev)
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.timeout_ns = int(timeout_s * 1e9)
+        self.epoch = 0
+        self.launches = 0
+        self._peers: tuple[int, int] | None = None  # base addresses of the left / right neighbour
+        self._opened: list[int] = []
+        self._group = None
+        self._distributed = False
+
+    # {{{ set-up
+
+    def connect(self, group: dist.ProcessGroup | None = None) -> None:
+        import ctypes as ct
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        descs: list = [None] * world
+        dist.all_gather_object(descs, {"handle": self.handle, "n_local": self.n_local}, group=group)
+        opened: dict[int, int] = {rank: self.ptr}
+        for r in {(rank - 1) % world, (rank + 1) % world} - {rank}:
+            p = ct.c_void_p()
+            with torch.cuda.device(self.device):
+                L.check("psk_p2p_open", L.lib().psk_p2p_open(descs[r]["handle"], ct.byref(p)))
+            opened[r] = int(p.value)
+        self._peers = (opened[(rank - 1) % world], opened[(rank + 1) % world])
+        self._opened = [v for k, v in opened.items() if k != rank]
+        self._group, self._distributed = group, world > 1
+        dist.barrier(group=group)
+
+    def attach_local(self, slabs: Sequence["PeerSlabAdjoint"]) -> None:
+        """Ring between slabs held by one process (single-GPU tests of the same protocol)."""
+        w = len(slabs)
+        self._peers = (slabs[(self.rank - 1) % w].ptr, slabs[(self.rank + 1) % w].ptr)
+
+    def close(self) -> None:
+        torch.cuda.synchronize(self.device)
+        if self._distributed:
+            dist.barrier(group=self._group)
+        for p in self._opened:
+            L.check("psk_p2p_close", L.lib().psk_p2p_close(p))
+        self._opened = []
+        if self._distributed:
+            dist.barrier(group=self._group)
+        self.arrays = None
+        if self.ptr:
+            L.check("psk_p2p_free", L.lib().psk_p2p_free(self.ptr))
+            self.ptr = 0
+
+    # }}}
+
+    def _addr(self, base: int, k: int, cell: int) -> int:
+        """address of interior cell ``cell`` (may be negative / beyond: ghost cells) of array ``k``"""
+        return base + 8 * (k * self.ld + self.col0 + self.G + cell)
+
+    def _push(self, k: int) -> None:
+        """my 16 edge cells of array k -> the neighbours' ghost slots of THEIR array k, then their flags"""
+        lbase, rbase = self._peers
+        g, n = self.G, self.n_local
+        flags = 8 * self.narrays * self.ld
+        self.epoch += 1
+        L.check("psk_halo_push", L.lib().psk_halo_push(
+            self._addr(self.ptr, k, 0), self._addr(lbase, k, n),       # my first cells -> left neighbour's right ghosts
+            self._addr(self.ptr, k, n - g), self._addr(rbase, k, -g),  # my last cells -> right neighbour's left ghosts
+            g, lbase + flags + 8, rbase + flags, self.epoch, L.stream_ptr()))
+        self.launches += 1
+
+    def _wait(self) -> None:
+        flags = self.ptr + 8 * self.narrays * self.ld
+        L.check("psk_halo_wait", L.lib().psk_halo_wait(flags, flags + 8, self.epoch, self.timeout_ns,
+                                                      L.raw_ptr(self.timed_out), L.stream_ptr()))
+        self.launches += 1
+
+    def check(self) -> None:
+        if int(self.timed_out.item()) != 0:
+            raise RuntimeError(f"rank {self.rank}: a neighbour's ghost cells did not arrive within {self.timeout_ns / 1e9:.0f} s")
+
+    def interior(self, k: int) -> torch.Tensor:
+        return self.arrays[k, 0, self.G : self.G + self.n_local]
+
+    # {{{ sweeps (split into phases so that in-process rings can interleave the slabs)
+
+    def forward_begin(self, u0_local: torch.Tensor) -> None:
+        self.interior(0).copy_(u0_local)
+        self._push(0)
+
+    def forward_step(self, m: int, dt: torch.Tensor) -> None:
+        self._wait()
+        if not self.hp.step_fused(self.arrays[m], self.arrays[m + 1], dt):
+            raise RuntimeError("psk_ssprk33_step does not cover this slab")
+        self._push(m + 1)
+        self.launches += 1
+
+    def backward_begin(self, pT_local: torch.Tensor) -> None:
+        self._cur = self.nsteps + 1
+        self.interior(self._cur).copy_(pT_local)
+        self._push(self._cur)
+
+    def backward_step(self, m: int, dt: torch.Tensor) -> None:
+        cur = self._cur
+        nxt = 2 * self.nsteps + 3 - cur  # the other of nsteps + 1, nsteps + 2
+        self._wait()
+        if not self.hp.reverse_step_fused(self.arrays[m], self.arrays[cur], dt, self.arrays[nxt]):
+            raise RuntimeError("psk_ssprk33_step_adjoint does not cover this slab")
+        self._push(nxt)
+        self._cur = nxt
+        self.launches += 1
+
+    def gradient_half_l2(self, u0_local: torch.Tensor, dt: float | torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+        """``J = 1/2 sum u(T)^2`` over this slab and this slab's part of ``dJ / du(0)`` (forward sweep onto the tape,
+        reverse sweep from ``p(T) = u(T)``); every rank calls it at the same time."""
+        if not isinstance(dt, torch.Tensor):
+            dt = torch.full((1,), float(dt), dtype=torch.float64, device=self.device)
+        self.forward_begin(u0_local)
+        for m in range(self.nsteps):
+            self.forward_step(m, dt)
+        uT = self.interior(self.nsteps)
+        J = 0.5 * (uT ** 2).sum()
+        self.backward_begin(uT)
+        for m in range(self.nsteps - 1, -1, -1):
+            self.backward_step(m, dt)
+        self.check()
+        return J, self.interior(self._cur)
+
+    # }}}
+
+
+# }}}
+

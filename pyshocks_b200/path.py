@@ -536,7 +536,8 @@ class HotPath:
         """whether :meth:`reverse_step_fused` exists for this scheme (the conditions of psk_ssprk33_step_adjoint;
         the arrays must also be 16-byte aligned with an even row stride, which EnsembleSolver guarantees)"""
         return (self.equation == "burgers" and self.flux == "rusanov" and self.rec == "wenojs53" and self.math == "fast"
-                and self.bc == "periodic" and self._nu is None and self.n % 2 == 0 and self.n >= 8 and self.g >= 3)
+                and ((self.bc == "periodic" and self.g >= 3) or (self.bc == "none" and self.g >= 16))
+                and self._nu is None and self.n % 2 == 0 and self.n >= 8)
 
     def reverse_step_fused(self, u: torch.Tensor, p: torch.Tensor, dt: torch.Tensor, out: torch.Tensor, *,
                            stages: tuple[torch.Tensor, torch.Tensor] | None = None) -> bool:

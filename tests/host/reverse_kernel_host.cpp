@@ -58,8 +58,10 @@ extern "C" {
 
 // p_out = (d advance / d u)^T p_in on periodic rows (interior cells), launched like launch_reverse<C>
 int emu_reverse_step(int C, int n, int g, int batch, long long ld, double dx, double eps, const double *u,
-                     const double *pin, const double *dt, int dt_stride, double *pout, double *k1, double *k2) {
+                     const double *pin, const double *dt, int dt_stride, double *pout, double *k1, double *k2,
+                     int bc_none) {
   psk::RevParams p{};
+  p.bc_none = bc_none;
   p.u = u; p.pin = pin; p.pout = pout; p.dt = dt; p.dt_stride = dt_stride; p.ld = ld;
   p.invdx = 1.0 / dx; p.eps = eps; p.n = n; p.g = g;
   p.dbg_k1 = k1; p.dbg_k2 = k2;

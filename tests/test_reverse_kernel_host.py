@@ -34,7 +34,7 @@ def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
                     str(ROOT / "tests" / "host" / "reverse_kernel_host.cpp")], check=True)
     lib = ct.CDLL(str(out))
     dp = ct.POINTER(ct.c_double)
-    lib.emu_reverse_step.argtypes = [ct.c_int] * 4 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int, dp, dp, dp]
+    lib.emu_reverse_step.argtypes = [ct.c_int] * 4 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int, dp, dp, dp, ct.c_int]
     lib.emu_reverse_step.restype = ct.c_int
     return lib
 
@@ -77,7 +77,7 @@ def _run(emu, C: int, n: int, u: np.ndarray, p: np.ndarray, dt: float, stages: b
     U, P, OUT, K1, K2 = bufs
     dts = np.full(batch, dt)
     rc = emu.emu_reverse_step(C, n, G, batch, ld, 3.0 / n, EPS, _p(U), _p(P), _p(dts), 1, _p(OUT),
-                              _p(K1) if stages else None, _p(K2) if stages else None)
+                              _p(K1) if stages else None, _p(K2) if stages else None, 0)
     assert rc == 0
     return (OUT, K1, K2) if stages else OUT
 
@@ -125,3 +125,43 @@ def test_recomputed_stage_values_match_the_oracle(emu, C: int, n: int) -> None:
     i = slice(G, G + n)
     assert np.abs(k1[:, i] - r1[:, i]).max() < 1e-13 * np.abs(r1).max()
     assert np.abs(k2[:, i] - r2[:, i]).max() < 1e-13 * np.abs(r2).max()
+
+
+@pytest.mark.parametrize("C", [12, 16])
+@pytest.mark.parametrize("world,n", [(2, 1000), (3, 812)])
+def test_fused_reverse_step_on_slabs_with_sixteen_ghost_cells(emu, C: int, world: int, n: int) -> None:
+    """boundary kind NONE: a slab's window cells beyond its ends are its stored ghost cells (16 per side, the
+    neighbours' edge cells of u and of p'); the slabs together give the periodic row's result -- every slab
+    GATHERS its part of the gradient, nothing is sent back (to round-off: the lane boundaries, hence the order
+    in which a first difference collects its cotangents, sit elsewhere)"""
+    rng = np.random.default_rng(n)
+    u = _state(n, "smooth", n)[None, :]
+    p = rng.standard_normal((1, n + 2 * G))
+    p[:, :G] = 0.0
+    p[:, n + G :] = 0.0
+    dt = 0.3 * (3.0 / n)
+    whole = _run(emu, C, n, u, p, dt)[0, G : G + n]
+    g16, first, parts = 16, 0, []
+    ui, pi = u[0, G : G + n], p[0, G : G + n]
+    for r in range(world):
+        nl = 2 * ((n // world + (1 if r < n % world else 0)) // 2)  # even slab lengths
+        if r == world - 1:
+            nl = n - first
+        idx = np.arange(first - g16, first + nl + g16) % n
+        col0 = (16 - g16) % 16
+        ld = ((col0 + nl + 2 * g16 + 15) // 16) * 16
+        bufs = []
+        for src in (ui[idx], pi[idx], None):
+            raw = np.zeros(ld + 2)
+            off = 0 if (raw.ctypes.data + 8 * (col0 + g16)) % 16 == 0 else 1
+            v = raw[off : off + ld].reshape(1, ld)[:, col0 : col0 + nl + 2 * g16]
+            v[:] = np.nan if src is None else src
+            bufs.append(v)
+        U, P, OUT = bufs
+        dts = np.full(1, dt)
+        assert emu.emu_reverse_step(C, nl, g16, 1, ld, 3.0 / n, EPS, _p(U), _p(P), _p(dts), 1, _p(OUT), None, None, 1) == 0
+        assert np.isnan(OUT[0, :g16]).all() and np.isnan(OUT[0, g16 + nl :]).all()
+        parts.append(OUT[0, g16 : g16 + nl].copy())
+        first += nl
+    got = np.concatenate(parts)
+    assert np.abs(got - whole).max() < 1e-13 * np.abs(whole).max()

@@ -1,0 +1,45 @@
+"""Device-resident throughput of the schemes around the headline configuration (65536 x 4096 ensemble, fixed dt,
+20 steps after 3 warm-up steps): which of them run the whole SSPRK33 step in one launch, which take three (or six)
+stage launches.  One JSON line per scheme (-> profiles/)."""
+import json
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, "/root/repo")
+from pyshocks_b200.ensemble import EnsembleSolver  # noqa: E402
+
+B, N, G = 65536, 4096, 3
+h = 3.0 / N
+x = (torch.arange(N + 2 * G, device="cuda", dtype=torch.float64) - G + 0.5) / N
+rng = np.random.default_rng(0)
+coef = torch.from_numpy(rng.uniform(0.2, 1.0, size=(B, 1))).cuda()
+u0 = 0.3 + coef * torch.sin(2 * np.pi * x)[None, :]
+vel = (1.0 + 0.3 * torch.sin(2 * np.pi * x + 0.3)).cpu().numpy()
+CASES = [
+    ("burgers", "rusanov", "periodic"), ("burgers", "rusanov", "dirichlet"), ("burgers", "godunov", "periodic"),
+    ("burgers", "eo", "dirichlet"), ("burgers", "lf", "periodic"), ("burgers", "rusanov", "neumann"),
+    ("advection", "godunov", "dirichlet"), ("continuity", "godunov", "dirichlet"), ("advection", "godunov", "periodic"),
+]
+for eq, flux, bc in CASES:
+    kw = {"velocity": vel} if eq != "burgers" else {}
+    s = EnsembleSolver(equation=eq, flux=flux, rec="wenojs53", bc=bc, n=N, g=G, dx=h, eps=1e-12, batch=B, **kw)
+    if bc in ("dirichlet", "neumann"):
+        s.hp.set_ghost(np.zeros(2 * G) if bc == "neumann" else np.full(2 * G, 0.3))
+    dt = torch.full((1,), 0.4 * h / 1.5, dtype=torch.float64, device="cuda")
+    s.load(u0)
+    s.solve_fixed_dt(None, dt, 3)
+    torch.cuda.synchronize()
+    l0 = s.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    s.solve_fixed_dt(None, dt, 20)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"equation": eq, "flux": flux, "bc": bc, "launches_per_step": (s.launches - l0) / 20,
+                      "ms_per_step": ms / 20, "cell_updates_per_s": B * N * 20 / (ms * 1e-3),
+                      "finite": bool(torch.isfinite(s.u[:, G : G + N]).all())}), flush=True)
+    del s
+    torch.cuda.empty_cache()

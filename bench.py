@@ -287,6 +287,7 @@ class Ctx:
         self.rank = int(os.environ.get("RANK", "0"))
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        self.fp64: dict | None = None  # DFMA peak measured in this run (rank 0)
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
         torch.cuda.set_device(self.local)
@@ -424,6 +425,7 @@ def measure_ensemble(ctx: Ctx, args: argparse.Namespace) -> dict:
     per_step = launches / max(args.steps, 1)  # 1: whole-step kernel, 3: one launch per stage
     whole = per_step < 2
     fp64 = measure_fp64_peak(dev)
+    ctx.fp64 = fp64
     sc = sass_counts()
     k = sc["kernels"]
     if whole and k.get("step_fused"):
@@ -441,7 +443,7 @@ def measure_ensemble(ctx: Ctx, args: argparse.Namespace) -> dict:
     tf = ROOT / "profiles" / "traffic.json"
     if tf.exists():
         tj = json.loads(tf.read_text())
-        per_cell = tj.get("step_kernel", {}).get("dram_bytes_per_cell_update_measured") if whole else None
+        per_cell = tj.get("step_kernel", {}).get("dram_bytes_per_cell_measured") if whole else None
         if per_cell is not None:
             traffic = per_cell * rows * N_CELLS  # per launch on this rank
     achieved_hbm = per_gpu * ALGO_BYTES_PER_CELL_UPDATE / 1e9
@@ -483,7 +485,8 @@ def measure_ensemble(ctx: Ctx, args: argparse.Namespace) -> dict:
             "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CELL_UPDATE / per_step * rows * N_CELLS,
             "note": "64 algorithmic bytes per cell-update (three streaming stages, SURVEY.md 8d); the whole-step kernel "
-                    "moves 15.4 B of them (traffic: ncu dram bytes per launch, profiles/traffic.json scaled to this launch)",
+                    "moves 15.7 B of them (traffic: ncu dram bytes per cell of one launch, profiles/traffic.json, x the cells of "
+                    "this launch)",
         },
         "e2e": {
             "value": cells_per_step * args.steps / e2e_s, "unit": UNIT,
@@ -720,6 +723,25 @@ def measure_adjoint(ctx: Ctx, args: argparse.Namespace, *, batch_total: int, n: 
     cells = batch_total * n
     adj_rate = cells * nsteps / (bwd_ms * 1e-3)
     achieved = adj_rate / world * ADJ_ALGO_BYTES / 1e9
+    # FP64 pipe (the binding unit): executed FP64 instructions per cell-step of the reverse sweep = the fused reverse
+    # kernel's (ncu, profiles/traffic.json) + the whole-step recomputation of the states inside a tape segment
+    roof = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if rank == 0 and tf.exists() and "1 launch" in mode:
+        tj = json.loads(tf.read_text())
+        fp64 = ctx.fp64 if ctx.fp64 is not None else measure_fp64_peak(dev)
+        rev = tj.get("reverse_kernel", {}).get("fp64_thread_instructions_per_cell_executed")
+        stp = tj.get("step_kernel", {}).get("fp64_thread_instructions_per_cell_executed")
+        if rev and stp:
+            per_cell = rev + stp * (segment - 1) / segment
+            slots = adj_rate / world * per_cell * 2.0 / 1e12
+            roof = {"bound": "fp64", "achieved": slots, "peak": fp64["tflops"], "unit": "TFLOP/s", "frac": slots / fp64["tflops"],
+                    "executed_fp64_instr_per_cell_step": per_cell, "peak_source": fp64["how"],
+                    "traffic_bytes_per_cell_step": tj["reverse_kernel"]["dram_bytes_per_cell_measured"],
+                    "definition": "executed FP64 thread instructions per cell-step (ncu counters of the reverse kernel "
+                                  "at this row length + the whole-step kernel's for the states recomputed inside a tape "
+                                  "segment, profiles/traffic.json) x adjoint cell-updates/s x 2 flop per pipe slot, against "
+                                  "the DFMA peak measured in this run; ncu reports the pipe 81.6 % busy for the kernel alone"}
     return {
         "metric": "adjoint gradients/s", "value": batch_total / ((fwd_ms + bwd_ms) * 1e-3), "unit": "gradients/s",
         "n_gpus": world, "steps": nsteps, "scaling": "strong",
@@ -730,6 +752,7 @@ def measure_adjoint(ctx: Ctx, args: argparse.Namespace, *, batch_total: int, n: 
         "tape_states": tape_states, "segment": segment, "reverse_mode": mode,
         "adjoint_cell_updates_per_s": adj_rate, "forward_cell_updates_per_s": cells * nsteps / (fwd_ms * 1e-3),
         "grad_finite": grad_finite, "parity": parity,
+        "roofline": roof,
         "roofline_hbm": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "algorithmic_bytes_per_cell_step": ADJ_ALGO_BYTES,
                          "note": "reverse sweep only, 144 B per cell-step (SURVEY.md 8d per-stage streaming design); the "
@@ -794,7 +817,7 @@ def run_adjoint(args: argparse.Namespace) -> None:
                           n=args.cells or 8192, nsteps=args.steps, check=not args.no_check)
     if ctx.rank == 0:
         rec.update({"higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                    "config": {"workload": rec["workload"]}, "roofline": rec["roofline_hbm"]})
+                    "config": {"workload": rec["workload"]}, "roofline": rec.get("roofline") or rec["roofline_hbm"]})
         emit(rec)
     ctx.close()
 

@@ -389,9 +389,9 @@ int launch_adjoint_lean(const AdjParams &p, int batch, cudaStream_t st) {
   const int total = chunks + 1;
   const int wpc = total < 4 ? total : 4;
   const unsigned gx = static_cast<unsigned>((total + wpc - 1) / wpc);
-  const unsigned gy = batch < 65535 ? batch : 65535u;
-  if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
-  const dim3 grid(gx, gy, batch / gy);
+  unsigned gy, gz;
+  if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;
+  const dim3 grid(gx, gy, gz);
   adjoint_lean_kernel<MINB, VAR><<<grid, wpc * 32, 0, st>>>(p, chunks);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
@@ -408,9 +408,9 @@ int launch_adjoint_warp(const AdjParams &p, int batch, cudaStream_t st) {
   }
   if (total < wpc) wpc = total;
   const unsigned gx = static_cast<unsigned>((total + wpc - 1) / wpc);
-  const unsigned gy = batch < 65535 ? batch : 65535u;
-  if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
-  const dim3 grid(gx, gy, batch / gy);
+  unsigned gy, gz;
+  if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;
+  const dim3 grid(gx, gy, gz);
   adjoint_warp_kernel<EQ, FLUX><<<grid, wpc * 32, 0, st>>>(p, chunks);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
@@ -481,7 +481,7 @@ int launch_adjoint(const AdjParams &p0, int batch, cudaStream_t st) {
                        (p.acc2 == nullptr || reinterpret_cast<uintptr_t>(p.acc2 + p.bc.g) % 16 == 0) &&
                        (p.ld % 2 == 0);
   if (REC == PSK_REC_WENOJS53 && g_adjoint_variant != 1 && aligned && p.bc.g == 3 &&
-      (batch <= 65535 || batch % 65535 == 0)) {
+      (batch <= 65535 || batch % 65535 == 0 || batch % 32768 == 0)) {
     int rc;
     if (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_RUSANOV && p.nu == nullptr && g_adjoint_variant != 2) {
       p.prescaled = 1;

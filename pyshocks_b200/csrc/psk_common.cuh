@@ -29,6 +29,19 @@ inline int rec_halo(int rec) {
   return rec == PSK_REC_WENOJS53 ? 3 : ((rec == PSK_REC_WENOJS32 || rec == PSK_REC_ESWENO32) ? 2 : 1);
 }
 
+// Rows of a batch over grid.y x grid.z (each <= 65535; a kernel's row is blockIdx.y + blockIdx.z * gridDim.y):
+// the smallest z that divides the batch.  false: no such split (the caller slices the batch or falls back).
+inline bool split_rows(int batch, unsigned &gy, unsigned &gz) {
+  if (batch <= 0) return false;
+  for (unsigned z = (static_cast<unsigned>(batch) + 65534u) / 65535u; z <= 65535u && z <= static_cast<unsigned>(batch); ++z)
+    if (batch % z == 0) {
+      gy = static_cast<unsigned>(batch) / z;
+      gz = z;
+      return true;
+    }
+  return false;
+}
+
 // Validates what every entry point relies on; returns PSK_OK or an error code.
 inline int check_desc(const psk_desc *d) {
   if (d == nullptr) return PSK_E_INVALID;

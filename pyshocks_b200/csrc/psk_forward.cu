@@ -586,9 +586,8 @@ int launch_fast_stage(const StageParams &p, int batch, cudaStream_t st) {
   q.chunks_per_row = geo.chunks_per_row;
   const int wpc = geo.wpc;
   const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
-  const unsigned gy = batch < 65535 ? batch : 65535u;
-  if (batch % gy != 0 && batch > 65535) return PSK_E_UNSUPPORTED;  // caller falls back
-  const unsigned gz = batch / gy;
+  unsigned gy, gz;
+  if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;  // caller falls back
   const dim3 grid(gx, gy, gz);
   const int threads = wpc * 32;
   if (p.maxabs != nullptr)
@@ -751,7 +750,8 @@ int launch_stage_warp(const StageParams &p, int batch, int ghost_rows, cudaStrea
   if (g_use_fast && REC == PSK_REC_WENOJS53 && !STRICT && q.vec_ok && p.nu == nullptr && p.active == nullptr &&
       (batch <= 65535 || batch % 65535 == 0 || batch % 32768 == 0)) {
     int rc = PSK_E_UNSUPPORTED;
-    if (batch <= 65535 || batch % 65535 == 0) {
+    unsigned ty, tz;
+    if (split_rows(batch, ty, tz)) {
       rc = launch_fast<EQ, FLUX>(q, batch, st);
     } else {
       // rows beyond the grid.y limit: split the batch into equal slices of 32768 rows
@@ -1034,9 +1034,9 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
   int wpc = THREADS / 32;
   if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
   const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
-  const unsigned gy = batch < 65535 ? batch : 65535u;
-  if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
-  const dim3 grid(gx, gy, batch / gy);
+  unsigned gy, gz;
+  if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;
+  const dim3 grid(gx, gy, gz);
   if (STAGES)
     step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, STAGES, EQ, DIRICHLET><<<grid, wpc * 32, 0, st>>>(q);
   else if (with_max)
@@ -1189,8 +1189,9 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
   q.bc_none = d->bc == PSK_BC_NONE ? 1 : 0;
   const bool mx = maxabs != nullptr;
   int batch = d->batch;
-  // rows beyond the grid.y limit: equal slices of 32768 rows
-  if (batch > 65535 && batch % 65535 != 0) {
+  // rows beyond the grid limits with no even split over grid.y x grid.z: equal slices of 32768 rows
+  unsigned ty, tz;
+  if (!split_rows(batch, ty, tz)) {
     if (batch % 32768 != 0) return PSK_E_UNSUPPORTED;
     for (int b0 = 0; b0 < batch; b0 += 32768) {
       psk_desc d2 = *d;

@@ -22,9 +22,9 @@ template <int C>
 int launch_reverse(const RevParams &p0, int batch, cudaStream_t st) {
   RevParams p = p0;
   p.tiles_per_row = (p.n + RevGeometry<C>::kEmit - 1) / RevGeometry<C>::kEmit;
-  const unsigned gy = batch < 65535 ? batch : 65535u;
-  if (batch > 65535 && batch % 65535 != 0) return PSK_E_UNSUPPORTED;
-  const dim3 grid(static_cast<unsigned>(p.tiles_per_row), gy, batch / gy);
+  unsigned gy, gz;
+  if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;
+  const dim3 grid(static_cast<unsigned>(p.tiles_per_row), gy, gz);
   reverse_step_kernel<C, rev_min_blocks<C>()><<<grid, 32, 0, st>>>(p);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;

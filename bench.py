@@ -810,6 +810,58 @@ def run_slab(args: argparse.Namespace) -> None:
     ctx.close()
 
 
+def run_slab_adjoint(args: argparse.Namespace) -> None:
+    """The discrete adjoint of BASELINE configs[3]'s solve on slabs (PeerSlabAdjoint): `--workload slab-adjoint
+    [--cells n] [--steps K]`: forward sweep onto per-slab tapes + gathered reverse sweep, one exchange of 16 cells per
+    side per step in either sweep."""
+    ctx = Ctx()
+    torch = ctx.torch
+    from pyshocks_b200.distributed import PeerSlabAdjoint
+
+    n_global = args.cells or (1 << 27)
+    nsteps = args.steps
+    h = (DOMAIN[1] - DOMAIN[0]) / n_global
+    sa = PeerSlabAdjoint(n_global=n_global, rank=ctx.rank, world=ctx.world, dx=h, nsteps=nsteps, device=ctx.dev)
+    if ctx.world > 1:
+        sa.connect()
+    else:
+        sa.attach_local([sa])
+    i = torch.arange(sa.first, sa.first + sa.n_local, device=ctx.dev, dtype=torch.float64)
+    u0 = 0.5 + torch.sin(2.0 * np.pi * (i + 0.5) / n_global)
+    del i
+    dt = torch.full((1,), CFL * h / 1.5, dtype=torch.float64, device=ctx.dev)
+    sa.gradient_half_l2(u0, dt)  # warm-up (every kernel loaded, tape pages touched)
+    ctx.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    sa.forward_begin(u0)
+    for m in range(nsteps):
+        sa.forward_step(m, dt)
+    ev[1].record()
+    sa.backward_begin(sa.interior(nsteps))
+    for m in range(nsteps - 1, -1, -1):
+        sa.backward_step(m, dt)
+    ev[2].record()
+    ctx.barrier()
+    sa.check()
+    fwd_ms, bwd_ms = ctx.max_over_ranks([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])])
+    finite = bool(torch.isfinite(sa.interior(sa._cur)).all())
+    sa.close()
+    if ctx.rank == 0:
+        emit({
+            "metric": "adjoint cell-updates/s (reverse sweep on slabs)", "value": n_global * nsteps / (bwd_ms * 1e-3),
+            "unit": "cell-updates/s", "n_gpus": ctx.world, "steps": nsteps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"discrete adjoint of ONE periodic Burgers grid N={n_global}, slab-decomposed over "
+                                   f"{ctx.world} rank(s), {nsteps} fixed-dt steps, J = 1/2 ||u(T)||^2: forward sweep onto per-slab "
+                                   "tapes, gathered reverse sweep (psk_ssprk33_step_adjoint on slabs with 16 ghost cells)"},
+            "forward_ms": fwd_ms, "reverse_ms": bwd_ms, "forward_cell_updates_per_s": n_global * nsteps / (fwd_ms * 1e-3),
+            "halo_exchanges_per_step": 1, "halo_cells_per_side": 16, "grad_finite": finite,
+            "gpu_launches": 3 * 2 * nsteps + 2,
+        })
+    ctx.close()
+
+
 def run_adjoint(args: argparse.Namespace) -> None:
     """BASELINE.json configs[4] alone: `--workload adjoint [--steps K] [--cells n] [--batch B]`."""
     ctx = Ctx()
@@ -834,7 +886,7 @@ def emit(line: dict) -> None:
 def main() -> None:
     global _JSON_OUT
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", choices=("all", "slab", "adjoint"), default="all",
+    ap.add_argument("--workload", choices=("all", "slab", "adjoint", "slab-adjoint"), default="all",
                     help="all = the headline ensemble + the slab / adjoint sub-records (default); slab / adjoint = "
                          "BASELINE configs 4 and 5 alone")
     ap.add_argument("--transport", choices=("p2p", "p2p-overlap", "p2p-serial", "p2p-step", "p2p-step-fused", "nccl"),
@@ -870,6 +922,8 @@ def main() -> None:
         run_slab(args)
     elif args.workload == "adjoint":
         run_adjoint(args)
+    elif args.workload == "slab-adjoint":
+        run_slab_adjoint(args)
     else:
         run_ours(args)
 

@@ -21,19 +21,13 @@ constexpr int rev_min_blocks() {
 template <int C>
 int launch_reverse(const RevParams &p0, int batch, cudaStream_t st) {
   RevParams p = p0;
-  p.tiles_per_row = (p.n + RevGeometry<C>::kEmit - 1) / RevGeometry<C>::kEmit;
+  rev_tiling(p.n, C, p.tiles_per_row, p.c_last);
   unsigned gy, gz;
   if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;
   const dim3 grid(static_cast<unsigned>(p.tiles_per_row), gy, gz);
   reverse_step_kernel<C, rev_min_blocks<C>()><<<grid, 32, 0, st>>>(p);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
-}
-
-// cells computed per row (windows x window length) for run length C
-static long long rev_work(int n, int C) {
-  const int emit = 32 * C - 2 * kRevHalo;
-  return static_cast<long long>((n + emit - 1) / emit) * 32 * C;
 }
 
 }  // namespace psk
@@ -71,7 +65,7 @@ int psk_ssprk33_step_adjoint(const psk_desc *d, const double *u, const double *p
   int C = g_reverse_variant;
   if (C == 0) {  // least redundant work; ties go to the shorter run (more warps per SM)
     C = 12;
-    for (int c : {16, 20})
+    for (int c : {16, 20, 24})
       if (rev_work(d->n, c) < rev_work(d->n, C)) C = c;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -55,6 +55,7 @@ struct RevParams {
   double invdx, eps;
   int n, g;
   int tiles_per_row;
+  int c_last;               // cells per lane of the LAST window of a row (8 <= c_last <= C, multiple of 4)
   double *dbg_k1, *dbg_k2;  // optional: the recomputed stage values of the stored cells (or nullptr)
   int bc_none;              // 1: a slab of a larger grid -- window cells beyond the row ends are the row's STORED ghost
                             // cells (g >= 16, filled by the neighbouring slabs) instead of the periodic images
@@ -73,6 +74,23 @@ struct RevGeometry {
   static constexpr int kArrayDoubles = kSlots * 32;  // one array of one warp
   static constexpr int kSmemDoubles = 3 * kArrayDoubles + kRevScratch * 32;
 };
+
+// Windows of a row for run length CM: all but the last hold 32 CM cells and store 32 CM - 32; the last one is as
+// short as the cells left over allow (runs of c_last cells), so a row of n = 8192 cells costs 13 x 640 + 384 cells
+// of work at CM = 20 instead of 14 x 640.
+inline void rev_tiling(int n, int CM, int &tiles, int &c_last) {
+  const int emit = 32 * CM - 2 * kRevHalo;
+  tiles = (n + emit - 1) / emit;
+  const int rem = n - (tiles - 1) * emit;
+  c_last = 4 * ((rem + 2 * kRevHalo + 127) / 128);
+  if (c_last < 8) c_last = 8;
+  if (c_last > CM) c_last = CM;
+}
+inline long long rev_work(int n, int CM) {
+  int tiles, c_last;
+  rev_tiling(n, CM, tiles, c_last);
+  return static_cast<long long>(tiles - 1) * 32 * CM + 32 * c_last;
+}
 
 // lane-private view of one window array: run cell j (-2 <= j <= C + 1) of this lane
 struct LaneArray {
@@ -105,13 +123,24 @@ __device__ __forceinline__ double rev_combine(bool stage2, double x, double u0, 
 // and all three adjoint stages execute the same instructions, which keeps the kernel's code inside the
 // 32 KB instruction cache -- with one inlined copy per stage (61 KB) the warps of an SM, each at its own
 // place in the code, stalled on instruction fetch more than on anything else.
-template <int C>
-__device__ __forceinline__ void rev_forward_stage(bool stage2, const LaneArray X, const LaneArray Y, const LaneArray U0,
-                                                  double cdt, double eps9) {
+__device__ __forceinline__ void rev_forward_stage(const int C, bool stage2, const LaneArray X, const LaneArray Y,
+                                                  const LaneArray U0, double cdt, double eps9) {
   constexpr unsigned kFull = 0xffffffffu;
   double ur_prev = 0.0, F_prev = 0.0;  // ur of cell j0 - 1, flux of the face (j0 - 2 | j0 - 1)
   double ul_first = 0.0, F_first = 0.0;  // ul of cell 0 and the flux of the face (0 | 1), for the end of the stream
   double y_prev = 0.0;                   // result of the cell j0 - 2
+  // first differences (in sixths) and second-difference terms are carried from one iteration to the next: every
+  // iteration forms only the four new ones (same expressions, hence the same bits, as forming all of them)
+  double tc0, tc1, tc2, pc0, pc1;
+  {
+    const double2 a = X.ld2(-2), b = X.ld2(0);
+    tc0 = __dmul_rn(1.0 / 6.0, a.y - a.x);
+    tc1 = __dmul_rn(1.0 / 6.0, b.x - a.y);
+    tc2 = __dmul_rn(1.0 / 6.0, b.y - b.x);
+    const double d0 = tc1 - tc0, d1 = tc2 - tc1;
+    pc0 = fma((13.0 / 3.0) * d0, d0, eps9);
+    pc1 = fma((13.0 / 3.0) * d1, d1, eps9);
+  }
 #pragma unroll 1
   for (int j0 = 0; j0 < C; j0 += 4) {
     double w[8];  // cells j0 - 2 .. j0 + 5
@@ -122,13 +151,17 @@ __device__ __forceinline__ void rev_forward_stage(bool stage2, const LaneArray X
       w[2 * k + 1] = q.y;
     }
     double t[7], pq[6];  // t[k]: interval (j0 - 2 + k, j0 - 1 + k); pq[k]: centred at the cell j0 - 1 + k
+    t[0] = tc0; t[1] = tc1; t[2] = tc2;
+    pq[0] = pc0; pq[1] = pc1;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) t[k] = __dmul_rn(1.0 / 6.0, w[k + 1] - w[k]);
+    for (int k = 3; k < 7; ++k) t[k] = __dmul_rn(1.0 / 6.0, w[k + 1] - w[k]);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
+    for (int k = 2; k < 6; ++k) {
       const double dd = t[k + 1] - t[k];
       pq[k] = fma((13.0 / 3.0) * dd, dd, eps9);
     }
+    tc0 = t[4]; tc1 = t[5]; tc2 = t[6];
+    pc0 = pq[4]; pc1 = pq[5];
     double m2[5];  // -2 |w| of the cells j0 - 1 .. j0 + 3
 #pragma unroll
     for (int k = 0; k < 5; ++k) m2[k] = -2.0 * fabs(w[k + 1]);
@@ -186,21 +219,20 @@ __device__ __forceinline__ void rev_forward_stage(bool stage2, const LaneArray X
 // neighbours' values (OUT is the V of the next stage).
 //   MODE 0: as above without A;  MODE 1: also A = 1/3 V + 3/4 OUT (A aliases V: the accumulator
 //   1/3 p' + 3/4 lam2 of the last stage takes the place of p');  MODE 2: with the term + A.
-template <int C>
-__device__ __forceinline__ void rev_adjoint_stage(const int MODE, const LaneArray X, const LaneArray V, const LaneArray OUT,
-                                                  const LaneArray A, double c_v, double hs, double eps9,
-                                                  double *park) {
+__device__ __forceinline__ void rev_adjoint_stage(const int C, const int MODE, const LaneArray X, const LaneArray V,
+                                                  const LaneArray OUT, const LaneArray A, double c_v, double hs,
+                                                  double eps9, double *park) {
   constexpr unsigned kFull = 0xffffffffu;
+  double tc[4], pc[3];  // carried: t of the intervals (j0-2, j0-1) .. (j0+1, j0+2), pq centred at j0-1 .. j0+1
   auto state_at = [&](const double (&w)[6]) {  // state of the cell w[2] from the cells w[0..4] (+ w[5] unused)
-    double t[4], pq[3];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) t[k] = (1.0 / 6.0) * (w[k + 1] - w[k]);
+    for (int k = 0; k < 4; ++k) tc[k] = (1.0 / 6.0) * (w[k + 1] - w[k]);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      const double dd = t[k + 1] - t[k];
-      pq[k] = fma((13.0 / 3.0) * dd, dd, eps9);
+      const double dd = tc[k + 1] - tc[k];
+      pc[k] = fma((13.0 / 3.0) * dd, dd, eps9);
     }
-    return weno53_state(t[0], t[1], t[2], t[3], pq[0], pq[1], pq[2]);
+    return weno53_state(tc[0], tc[1], tc[2], tc[3], pc[0], pc[1], pc[2]);
   };
   // ---- the face values beyond the run ends: ur of my last cell to the right, ul of my first cell to the left
   Weno5State S;  // state of the cell the stream is at
@@ -228,9 +260,10 @@ __device__ __forceinline__ void rev_adjoint_stage(const int MODE, const LaneArra
 #pragma unroll 1
   for (int j0 = 0; j0 < C; j0 += 4) {
     const bool more = (j0 + 4 < C);
-    double w[10];  // cells j0 - 2 .. j0 + 7 (the last two only while another iteration follows)
+    double w[10];  // cells j0 - 2 .. j0 + 7; used: j0 .. j0 + 6 (the last two only while another iteration follows)
+    w[0] = w[1] = 0.0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 1; k < 4; ++k) {
       const double2 q = X.ld2(j0 - 2 + 2 * k);
       w[2 * k] = q.x;
       w[2 * k + 1] = q.y;
@@ -248,14 +281,24 @@ __device__ __forceinline__ void rev_adjoint_stage(const int MODE, const LaneArra
       v[2 * k] = q.x;
       v[2 * k + 1] = q.y;
     }
-    double t[8], pq[7];  // t[k]: interval (j0 - 2 + k, j0 - 1 + k); pq[k]: centred at the cell j0 - 1 + k
+    // t[k]: interval (j0 - 2 + k, j0 - 1 + k); pq[k]: centred at the cell j0 - 1 + k.  The first four / three were
+    // formed by the previous iteration (or with the state of cell 0): only the new ones are computed
+    double t[8], pq[7];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t[k] = (1.0 / 6.0) * (w[k + 1] - w[k]);
+    for (int k = 0; k < 4; ++k) t[k] = tc[k];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
+    for (int k = 0; k < 3; ++k) pq[k] = pc[k];
+#pragma unroll
+    for (int k = 4; k < 8; ++k) t[k] = (1.0 / 6.0) * (w[k + 1] - w[k]);
+#pragma unroll
+    for (int k = 3; k < 7; ++k) {
       const double dd = t[k + 1] - t[k];
       pq[k] = fma((13.0 / 3.0) * dd, dd, eps9);
     }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tc[k] = t[k + 4];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pc[k] = pq[k + 4];
     double T[7];  // cotangents of the intervals (j0 - 2 + k, j0 - 1 + k)
     T[0] = Tc0; T[1] = Tc1; T[2] = Tc2; T[3] = T[4] = T[5] = T[6] = 0.0;
     double o[4], gi[4];
@@ -337,9 +380,9 @@ __device__ __forceinline__ void rev_adjoint_stage(const int MODE, const LaneArra
 
 // ---------------------------------------------------------------------------
 // run cells -2 .. C + 1 of one global array into a window array (periodic images beyond the row ends)
-template <int C>
-__device__ __forceinline__ void rev_load_run(const double *__restrict__ src, int64_t base, int r0, int n, bool inside,
-                                             const LaneArray D, int none_g = 0) {
+template <int CM>
+__device__ __forceinline__ void rev_load_run(const int C, const double *__restrict__ src, int64_t base, int r0, int n,
+                                             bool inside, const LaneArray D, int none_g = 0) {
   if (none_g > 0 && !inside) {  // slab: stored ghost cells; further out never reaches a stored cell
 #pragma unroll 1
     for (int j = -2; j < C + 2; ++j) {
@@ -349,8 +392,11 @@ __device__ __forceinline__ void rev_load_run(const double *__restrict__ src, int
     return;
   }
   if (inside) {
-#pragma unroll
-    for (int k = 0; k < RevGeometry<C>::kPairs; ++k) {
+    // four 16-byte loads in flight per iteration.  Measured (200 reverse steps of config 5): this form 242 ms; two
+    // loads per iteration 248 ms (load latency exposed); fully unrolled and predicated over the longest run, every
+    // load in flight, 254 ms (its code pushes the kernel past the 32 KB instruction cache)
+#pragma unroll 4
+    for (int k = 0; k < (C + 4) / 2; ++k) {
       const double2 a = *reinterpret_cast<const double2 *>(src + base + r0 - 2 + 2 * k);
       D.st2(-2 + 2 * k, a.x, a.y);
     }
@@ -365,15 +411,17 @@ __device__ __forceinline__ void rev_load_run(const double *__restrict__ src, int
   }
 }
 
-template <int C, int MINB>
+template <int CM, int MINB>
 __global__ void __launch_bounds__(32, MINB)
 reverse_step_kernel(const RevParams p) {
-  using Geo = RevGeometry<C>;
+  using Geo = RevGeometry<CM>;
   __shared__ double2 smem[Geo::kSmemDoubles / 2];
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
   const int row = blockIdx.y + blockIdx.z * gridDim.y;
   const int n = p.n;
+  const int C = (tile == p.tiles_per_row - 1) ? p.c_last : CM;  // cells per lane of this window
+  const int window = 32 * C;
   const LaneArray P0{smem + lane}, P1{smem + Geo::kArrayDoubles / 2 + lane}, P2{smem + 2 * (Geo::kArrayDoubles / 2) + lane};
   double *park = reinterpret_cast<double *>(smem + 3 * (Geo::kArrayDoubles / 2)) + lane;
   const int64_t base = static_cast<int64_t>(row) * p.ld + p.g;
@@ -381,10 +429,10 @@ reverse_step_kernel(const RevParams p) {
   const int none_g = p.bc_none ? p.g : 0;
   const bool inside = (r0 - 2 >= -none_g) && (r0 + C + 2 <= n + none_g);
 
-  rev_load_run<C>(p.u, base, r0, n, inside, P0, none_g);
+  rev_load_run<CM>(C, p.u, base, r0, n, inside, P0, none_g);
 #ifndef PSK_HOST_EMU
   if (inside) {  // p' is needed after the recomputation: have its lines on their way
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < C + 4; k += 16)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p.pin + base + r0 - 2 + k));
   }
@@ -395,12 +443,12 @@ reverse_step_kernel(const RevParams p) {
 
   // ---- recomputation of the stage values (timestepping.py:314-317): P0 = u, P1 = k1, P2 = k2
 #pragma unroll 1
-  for (int st = 0; st < 2; ++st) rev_forward_stage<C>(st == 1, st == 0 ? P0 : P1, st == 0 ? P1 : P2, P0, cdt, eps9);
+  for (int st = 0; st < 2; ++st) rev_forward_stage(C, st == 1, st == 0 ? P0 : P1, st == 0 ? P1 : P2, P0, cdt, eps9);
   if (p.dbg_k1 != nullptr) {
 #pragma unroll 1
     for (int j = 0; j < C; ++j) {
       const int wi = C * lane + j, e = tile * Geo::kEmit + wi - kRevHalo;
-      if (wi >= kRevHalo && wi < Geo::kWindow - kRevHalo && e < n) {
+      if (wi >= kRevHalo && wi < window - kRevHalo && e < n) {
         p.dbg_k1[base + e] = P1.ld1(j);
         p.dbg_k2[base + e] = P2.ld1(j);
       }
@@ -413,18 +461,18 @@ reverse_step_kernel(const RevParams p) {
   const double hs = 0.5 * p.invdx * dt;
 #pragma unroll 1
   for (int ph = 0; ph < 3; ++ph) {
-    if (ph != 1) rev_load_run<C>(ph == 0 ? p.pin : p.u, base, r0, n, inside, ph == 0 ? P0 : P2, none_g);
+    if (ph != 1) rev_load_run<CM>(C, ph == 0 ? p.pin : p.u, base, r0, n, inside, ph == 0 ? P0 : P2, none_g);
     const double cv = (ph == 0) ? (2.0 / 3.0) : ((ph == 1) ? 0.25 : 1.0);
     const LaneArray X = (ph == 1) ? P1 : P2, V = (ph == 0) ? P0 : ((ph == 1) ? P2 : P1), OUT = (ph == 0) ? P2 : ((ph == 1) ? P1 : P0);
-    rev_adjoint_stage<C>(ph == 0 ? 1 : (ph == 1 ? 0 : 2), X, V, OUT, P0, cv, cv * hs, eps9, park);
+    rev_adjoint_stage(C, ph == 0 ? 1 : (ph == 1 ? 0 : 2), X, V, OUT, P0, cv, cv * hs, eps9, park);
   }
 
   // ---- p of the stored window cells
   const int e0 = tile * Geo::kEmit + C * lane - kRevHalo;  // interior coordinate of the lane's first cell if stored
-#pragma unroll
+#pragma unroll 1
   for (int j = 0; j < C; j += 2) {
     const int wi = C * lane + j;
-    if (wi >= kRevHalo && wi < Geo::kWindow - kRevHalo && e0 + j < n) {
+    if (wi >= kRevHalo && wi < window - kRevHalo && e0 + j < n) {
       const double2 q = P0.ld2(j);
       if (e0 + j + 1 < n) {
         *reinterpret_cast<double2 *>(p.pout + base + e0 + j) = q;

@@ -47,7 +47,7 @@ void run_grid(unsigned gx, unsigned gy, Body body) {
 
 template <int C>
 void run(psk::RevParams p, int batch) {
-  p.tiles_per_row = (p.n + psk::RevGeometry<C>::kEmit - 1) / psk::RevGeometry<C>::kEmit;
+  psk::rev_tiling(p.n, C, p.tiles_per_row, p.c_last);
   run_grid(static_cast<unsigned>(p.tiles_per_row), static_cast<unsigned>(batch),
            [&]() { psk::reverse_step_kernel<C, 1>(p); });
 }
@@ -70,6 +70,7 @@ int emu_reverse_step(int C, int n, int g, int batch, long long ld, double dx, do
     case 12: run<12>(p, batch); break;
     case 16: run<16>(p, batch); break;
     case 20: run<20>(p, batch); break;
+    case 24: run<24>(p, batch); break;
     default: return -1;
   }
   return 0;

@@ -82,9 +82,9 @@ def _run(emu, C: int, n: int, u: np.ndarray, p: np.ndarray, dt: float, stages: b
     return (OUT, K1, K2) if stages else OUT
 
 
-@pytest.mark.parametrize("C", [8, 12, 16, 20])
+@pytest.mark.parametrize("C", [8, 12, 16, 20, 24])
 @pytest.mark.parametrize("n,kind,tol", [(1000, "smooth", 3e-12), (300, "smooth", 3e-12), (74, "smooth", 3e-12),
-                                        (812, "tophat", 2e-9)])
+                                        (812, "tophat", 2e-9), (1300, "smooth", 3e-12)])
 def test_fused_reverse_step_is_the_transposed_step_jacobian(emu, C: int, n: int, kind: str, tol: float) -> None:
     # tolerance: three chained stages; the worst cells (next to an extremum, beta ~ eps) are the same ones with the
     # same error for every run length C, i.e. round-off of the derivative itself, not of the tiling
@@ -107,7 +107,7 @@ def test_fused_reverse_step_is_the_transposed_step_jacobian(emu, C: int, n: int,
         assert err < tol, (b, err)
 
 
-@pytest.mark.parametrize("C,n", [(16, 1000), (12, 74), (20, 2000)])
+@pytest.mark.parametrize("C,n", [(16, 1000), (12, 74), (20, 2000), (20, 1300), (24, 8192)])
 def test_recomputed_stage_values_match_the_oracle(emu, C: int, n: int) -> None:
     """k1, k2 of timestepping.py:314-317 as the kernel recomputes them (FAST arithmetic: 1e-13 of the C oracle)"""
     from oracle.c_oracle import COracle

@@ -167,6 +167,17 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
                       const uint8_t *active, double *lf_work, double *maxabs,
                       int ghost_rows, psk_stream_t stream);
 
+/* psk_ssprk33_stage for the global Lax-Friedrichs flux (scalar.py:258-278) on PERIODIC rows WITHOUT the reduction
+ * pass: there the speed max |w| over all cells after the boundary condition (scalar.py:277) is max |uin| over the
+ * interior (the ghost cells are copies), which the launch that PRODUCED uin has already reduced into its `maxabs`
+ * output.  speed [batch]: that value (for the first stage of a solve: psk_max_abs, interior); maxabs [batch],
+ * zero-filled by the caller: max |uout| over the interior = the speed of the next stage.  Three launches per step
+ * instead of six, one full read of the state less per stage; same bits.  PSK_E_UNSUPPORTED for other fluxes and
+ * boundary kinds. */
+int psk_ssprk33_stage_lf(const psk_desc *d, int stage, const double *u0, const double *uin, double *uout,
+                         const double *dt, int64_t dt_stride, const double *speed, double *maxabs,
+                         psk_stream_t stream);
+
 /* One whole SSPRK33 step (timestepping.py:312-320: the three stages above) in ONE launch, for the
  * hot configuration only: Burgers with the Rusanov (nu = 1), upwind or Engquist-Osher flux + WENO-JS5,
  * FAST math, periodic rows (g >= 3) or slabs of a larger grid (boundary kind NONE with g >= 9 ghost

@@ -1399,6 +1399,32 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
                                     : dispatch_scheme<false>(d, p, ghost_rows, st);
 }
 
+/* psk_ssprk33_stage for the global Lax-Friedrichs flux on PERIODIC rows without the reduction pass: the speed
+ * max |w| over all cells after the boundary condition (scalar.py:277) equals max |uin| over the interior there (the
+ * ghost cells are copies), which the stage that PRODUCED uin has already reduced into its maxabs output. */
+int psk_ssprk33_stage_lf(const psk_desc *d, int stage, const double *u0, const double *uin, double *uout,
+                         const double *dt, int64_t dt_stride, const double *speed, double *maxabs,
+                         psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (stage < 1 || stage > 3 || uin == nullptr || uout == nullptr || dt == nullptr || speed == nullptr) return PSK_E_INVALID;
+  if (stage >= 2 && u0 == nullptr) return PSK_E_INVALID;
+  if (uout == uin) return PSK_E_INVALID;
+  if (d->equation != PSK_EQ_BURGERS || d->flux != PSK_FLUX_LAX_FRIEDRICHS || d->bc != PSK_BC_PERIODIC)
+    return PSK_E_UNSUPPORTED;
+  StageParams p = make_params(d);
+  p.uin = uin;
+  p.u0 = u0;
+  p.uout = uout;
+  p.dt = dt;
+  p.dt_stride = dt_stride;
+  p.lf_speed = speed;
+  p.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
+  p.stage = stage;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return d->math == PSK_MATH_STRICT ? dispatch_scheme<true>(d, p, 0, st) : dispatch_scheme<false>(d, p, 0, st);
+}
+
 int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const double *dt, int64_t dt_stride,
                      const uint8_t *active, double *maxabs, psk_stream_t stream) {
   int rc = check_desc(d);

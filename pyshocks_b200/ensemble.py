@@ -82,6 +82,13 @@ class EnsembleSolver:
         self._graph_steps = 1
         self.launches = 0  # kernels launched by this solver (bench.py reports it)
         self._fused: bool | None = None  # None: not tried yet; False: psk_ssprk33_step does not cover this scheme
+        # global Lax-Friedrichs flux on periodic rows: every stage leaves max |uout| (the speed of the next stage) in
+        # one of these, so no stage needs its own reduction pass (psk_ssprk33_stage_lf)
+        self._lf_chain = (equation == "burgers" and flux == "lf" and bc == "periodic")
+        self._lf = torch.zeros((2, 3, self.batch), dtype=torch.float64, device=dev) if self._lf_chain else None
+        self._lf_parity = 0
+        self._lf_ready = False  # whether _lf[1 - parity][2] holds max |u| of the current state
+        self._capturing = False  # inside a CUDA-graph capture (the chain alternates buffers: not replayable as one step)
 
     def new_states(self, count: int) -> list[torch.Tensor]:
         """``count`` more ``(batch, nx)`` arrays with the solver's padded, aligned row layout."""
@@ -101,6 +108,7 @@ class EnsembleSolver:
         if tuple(u0.shape) != (self.batch, self.nx):
             raise ValueError(f"expected shape {(self.batch, self.nx)}, got {tuple(u0.shape)}")
         self.u.copy_(u0, non_blocking=non_blocking)
+        self._lf_ready = False
 
     def store(self, out: torch.Tensor, *, non_blocking: bool = False) -> torch.Tensor:
         out.copy_(self.u, non_blocking=non_blocking)
@@ -119,6 +127,23 @@ class EnsembleSolver:
                 self.u, self.k1 = self.k1, self.u
                 self.launches += 1
                 return
+        if self._lf_chain and active is None and maxabs is None and not self._capturing:
+            # three stage launches + one fill, each stage taking its speed from its predecessor's maximum
+            p = self._lf_parity
+            if not self._lf_ready:
+                hp.max_abs(self.u, 1, out=self._lf[1 - p][2])
+                self.launches += 1
+            cur = self._lf[p]
+            cur.zero_()
+            ok = hp.stage_lf(1, self.u, self.u, self.k1, dt, self._lf[1 - p][2], cur[0])
+            if ok:
+                hp.stage_lf(2, self.u, self.k1, self.k2, dt, cur[0], cur[1])
+                hp.stage_lf(3, self.u, self.k2, self.u, dt, cur[1], cur[2])
+                self._lf_parity, self._lf_ready = 1 - p, True
+                self.launches += 4
+                return
+            self._lf_chain = False
+        self._lf_ready = False
         hp.stage(1, self.u, self.u, self.k1, dt, active=active)
         hp.stage(2, self.u, self.k1, self.k2, dt, active=active)
         hp.stage(3, self.u, self.k2, self.u, dt, active=active, maxabs=maxabs)
@@ -146,6 +171,7 @@ class EnsembleSolver:
                 torch.cuda.synchronize()
                 saved = self.u.clone()
                 launches = self.launches
+                self._capturing = True
                 self._step(dt, active=None, maxabs=None)
                 per_graph = 2 if self._fused else 1
                 if self._fused:
@@ -156,8 +182,10 @@ class EnsembleSolver:
                     for _ in range(per_graph):
                         self._step(dt, active=None, maxabs=None)
                 self.u.copy_(saved)
+                self._capturing = False
                 self.launches = launches  # (capture and warm-up are not steps of the solve)
                 self._graph, self._graph_key, self._graph_steps = g, key, per_graph
+            self._lf_ready = False
             for _ in range(nsteps // self._graph_steps):
                 self._graph.replay()
             self.launches += (1 if self._fused else 3) * (nsteps - nsteps % self._graph_steps)
@@ -230,6 +258,7 @@ class EnsembleSolver:
                     u.copy_(cur, non_blocking=True)
         for st in self._streams:
             main.wait_stream(st)
+        self._lf_ready = False
         self.t += float(nsteps) * dt
         return SolveResult(u=self.u, steps=nsteps, t=self.t)
 

@@ -469,6 +469,20 @@ class HotPath:
         )
         return uout
 
+    def stage_lf(self, stage: int, u0: torch.Tensor, uin: torch.Tensor, uout: torch.Tensor, dt: torch.Tensor,
+                 speed: torch.Tensor, maxabs: torch.Tensor) -> bool:
+        """One fused stage with the global Lax-Friedrichs flux on periodic rows, the speed taken from the ``maxabs``
+        output of the launch that produced ``uin`` instead of a reduction pass (``psk_ssprk33_stage_lf``);
+        ``maxabs`` (zero-filled by the caller) receives the speed of the next stage.  ``False`` elsewhere."""
+        batch, ld = self._state(uin)
+        d = self.desc(batch, ld)
+        rc = L.lib().psk_ssprk33_stage_lf(ct.byref(d), stage, L.ptr(u0), L.ptr(uin), L.ptr(uout), L.ptr(dt),
+                                          0 if dt.numel() == 1 else 1, L.ptr(speed), L.ptr(maxabs), L.stream_ptr())
+        if rc == L.E_UNSUPPORTED:
+            return False
+        L.check("psk_ssprk33_stage_lf", rc)
+        return True
+
     def step_fused(
         self,
         u: torch.Tensor,

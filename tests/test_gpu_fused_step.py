@@ -184,3 +184,42 @@ def test_whole_step_with_time_dependent_dirichlet_data() -> None:
     assert hp.step_fused(u, out, dt, ghosts=ghosts)
     ref = hp.ssprk33_step(u, dt, ghosts=ghosts)
     assert torch.equal(out[:, G : G + n], ref[:, G : G + n])
+
+
+def test_lax_friedrichs_without_the_reduction_pass() -> None:
+    """global Lax-Friedrichs flux on periodic rows: every stage takes its speed from the fused maximum of the launch
+    that produced its input (psk_ssprk33_stage_lf: 3 launches + 1 fill per step) -- the bits of the path with one
+    reduction pass per stage (6 launches), also after a reload and from a CUDA graph"""
+    batch, n, nsteps = 4, 2048, 6
+    u0 = _ic(batch, n, seed=11)
+    dt = 0.3 * (3.0 / n) / float(u0.abs().max())
+    a = _solver(batch, n, flux="lf")
+    a._lf_chain = False
+    a.solve_fixed_dt(u0, dt, nsteps)
+    assert a.launches == 6 * nsteps
+    b = _solver(batch, n, flux="lf")
+    b.solve_fixed_dt(u0, dt, nsteps)
+    assert b._lf_chain and b.launches == 4 * nsteps + 1
+    assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
+    b.solve_fixed_dt(u0, dt, 2)       # reload: the chain starts again from a reduction of the new state
+    b.solve_fixed_dt(None, dt, nsteps - 2)
+    assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
+    c = _solver(batch, n, flux="lf")
+    c.solve_fixed_dt(u0, dt, nsteps, graph=True)
+    assert torch.equal(a.u[:, G : G + n], c.u[:, G : G + n])
+
+
+def test_lax_friedrichs_row_blocks_on_several_streams() -> None:
+    """solve_fixed_dt_host cuts the batch into row blocks that run concurrently on several streams: every block
+    needs its own speed buffer (the scratch is keyed by the launching stream); against the single-stream solve"""
+    batch, n, nsteps = 64, 512, 5
+    u0 = _ic(batch, n, seed=3)
+    dt = 0.3 * (3.0 / n) / float(u0.abs().max())
+    a = _solver(batch, n, flux="lf")
+    a.solve_fixed_dt(u0, dt, nsteps)
+    b = _solver(batch, n, flux="lf")
+    host_in = u0.cpu().pin_memory()
+    host_out = torch.empty_like(host_in).pin_memory()
+    b.solve_fixed_dt_host(host_in, host_out, dt, nsteps, groups=8, streams=4)
+    torch.cuda.synchronize()
+    assert torch.equal(host_out[:, G : G + n].cuda(), a.u[:, G : G + n])

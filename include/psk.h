@@ -187,7 +187,12 @@ int psk_ssprk33_stage_lf(const psk_desc *d, int stage, const double *u0, const d
  * uout must not alias u.  active / maxabs as in psk_ssprk33_stage, except that rows with
  * active[r] == 0 are COPIED to uout (the state ping-pongs between two arrays).  Ghost cells of uout
  * are not written.  PSK_E_UNSUPPORTED outside that configuration: call psk_ssprk33_stage three
- * times instead. */
+ * times instead.
+ * Advection / continuity on PERIODIC rows (upwind flux) are covered too, under one condition the caller
+ * guarantees: the velocity's reconstruction is periodic like the state, vel_r[g - 1] == vel_r[g + n - 1] and
+ * vel_l[g + n] == vel_l[g] (true whenever the ghost cells of the velocity array are the periodic images of its
+ * interior).  A window cell beyond a row end is advanced with the velocity data of the interior cell it is the image
+ * of; with that condition those are the numbers the stage kernels read at the row ends, hence the same bits. */
 int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const double *dt,
                      int64_t dt_stride, const uint8_t *active, double *maxabs, psk_stream_t stream);
 

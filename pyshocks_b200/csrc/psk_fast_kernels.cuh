@@ -464,20 +464,31 @@ struct StepVel {
 };
 
 template <int R, int EQ>
-__device__ __forceinline__ void step_load_vel(const StepParams &p, int c0, StepVel<R> &v) {
-  const int nx = p.n + 2 * p.g;
+__device__ __forceinline__ void step_load_vel(const StepParams &p, int c0, bool periodic, StepVel<R> &v) {
+  const int n = p.n, nx = p.n + 2 * p.g;
+  // periodic rows: a window cell beyond the row ends is the image of an interior cell and is advanced with that
+  // cell's velocity data (the caller guarantees that the velocity's reconstruction is periodic too, see
+  // psk_ssprk33_step: then these are the very numbers the stage kernels read at the row ends)
+  auto wrap = [&](int c) {
+    if (!periodic) return c;
+    c %= n;
+    return c < 0 ? c + n : c;
+  };
   v.pos = 0u;
 #pragma unroll
   for (int f = 0; f <= R; ++f) {
-    const int j = p.g + c0 + f - 1;  // array index of the cell left of the face
-    const bool ok = (j >= 0 && j < nx - 1);
-    const double arj = ok ? p.vel_r[j] : 0.0, alp = ok ? p.vel_l[j + 1] : 0.0;
+    const int jl = p.g + wrap(c0 + f - 1), jr = p.g + wrap(c0 + f);  // array indices of the cells left / right of the face
+    const bool ok = periodic || (jl >= 0 && jl < nx - 1);
+    const double arj = ok ? p.vel_r[jl] : 0.0, alp = ok ? p.vel_l[jr] : 0.0;
     if ((arj + alp) > 0.0) v.pos |= 1u << f;
     v.ar[f] = arj;
     v.al[f] = alp;
   }
 #pragma unroll
-  for (int r = 0; r < R; ++r) v.vc[r] = (EQ == PSK_EQ_ADVECTION && c0 + r >= 0 && c0 + r < p.n) ? p.vel[p.g + c0 + r] : 0.0;
+  for (int r = 0; r < R; ++r) {
+    const int c = c0 + r;
+    v.vc[r] = (EQ == PSK_EQ_ADVECTION && (periodic || (c >= 0 && c < n))) ? p.vel[p.g + wrap(c)] : 0.0;
+  }
 }
 
 // Dirichlet rows: the window cells that are ghost cells take the boundary data of `stage` (0, 1, 2); window
@@ -635,7 +646,7 @@ step_warp_fused_kernel(const StepParams p) {
   }
   const double cdt = p.coef * p.dt[static_cast<int64_t>(row) * p.dt_stride];
   StepVel<R> vel;
-  if (EQ != PSK_EQ_BURGERS) step_load_vel<R, EQ>(p, c0, vel);
+  if (EQ != PSK_EQ_BURGERS) step_load_vel<R, EQ>(p, c0, !DIRICHLET && !p.bc_none, vel);
   if (DIRICHLET && !inside) step_fill_ghosts<R>(p, row, 0, c0, u0);
 
   double a[R], dF[R];

@@ -1226,6 +1226,12 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
       return launch_step_shape<6, PSK_FLUX_ENGQUIST_OSHER, 128, 3, false, kB, true>(q, d->n, batch, mx, st);
     return launch_step_shape<6, PSK_FLUX_RUSANOV, 128, 3, false, kB, true>(q, d->n, batch, mx, st);
   }
+  if (d->equation != PSK_EQ_BURGERS) {  // periodic rows, upwind flux with the velocity's reconstruction
+    if (k1_out != nullptr) return PSK_E_UNSUPPORTED;
+    if (d->equation == PSK_EQ_ADVECTION)
+      return launch_step_shape<6, PSK_FLUX_UPWIND, 128, 3, false, PSK_EQ_ADVECTION, false>(q, d->n, batch, mx, st);
+    return launch_step_shape<6, PSK_FLUX_UPWIND, 128, 3, false, PSK_EQ_CONTINUITY, false>(q, d->n, batch, mx, st);
+  }
   if (k1_out != nullptr)  // stage values wanted (reverse sweep): Rusanov, default shape
     return launch_step_shape<6, PSK_FLUX_RUSANOV, 128, 3, true>(q, d->n, batch, false, st);
   // the other Burgers fluxes: default shape only
@@ -1433,8 +1439,10 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
   const bool aligned = (reinterpret_cast<uintptr_t>(u + d->g) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0) && (d->ld % 2 == 0);
   const bool flux_ok = d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER;
-  if (d->equation != PSK_EQ_BURGERS || !flux_ok || d->rec != PSK_REC_WENOJS53 ||
-      d->math != PSK_MATH_FAST || d->nu != nullptr || !aligned || g_step_variant == 0 ||
+  // advection / continuity: periodic rows only (on slabs the velocity would need ghost cells of its own)
+  const bool eq_ok = d->equation == PSK_EQ_BURGERS ? (flux_ok && d->nu == nullptr)
+                                                   : (d->flux == PSK_FLUX_UPWIND && d->bc == PSK_BC_PERIODIC);
+  if (!eq_ok || d->rec != PSK_REC_WENOJS53 || d->math != PSK_MATH_FAST || !aligned || g_step_variant == 0 ||
       !((d->bc == PSK_BC_PERIODIC && d->g >= 3) || (d->bc == PSK_BC_NONE && d->g >= 9)))
     return PSK_E_UNSUPPORTED;
   return launch_step_fused(d, u, uout, dt, dt_stride, active, maxabs, static_cast<cudaStream_t>(stream));

@@ -74,6 +74,7 @@ class HotPath:
         self.dx, self.eps = float(dx), float(eps)
         self._nu = None if nu is None else self._table(nu)
         self._vel = self._vel_l = self._vel_r = None
+        self._vel_periodic = False
         self._ghost: torch.Tensor | None = None
         self._ghost3: torch.Tensor | None = None
         self._ghost_ld = 0
@@ -85,6 +86,11 @@ class HotPath:
             # reconstruct(rec, grid, bc, a, a, a) once: velocity does not depend on time
             # (advection/schemes.py:104-105, continuity/schemes.py:100-101)
             self._vel_l, self._vel_r = self.reconstruct(self._vel)
+            # whether the velocity's reconstruction is periodic like the state (the condition of psk_ssprk33_step
+            # for advection / continuity on periodic rows); false for a velocity array whose ghost cells are not the
+            # images of its interior: three stage launches then
+            g, n = self.g, self.n
+            self._vel_periodic = bool(self._vel_r[g - 1] == self._vel_r[g + n - 1]) and bool(self._vel_l[g + n] == self._vel_l[g])
         elif equation != "burgers":
             raise ValueError(f"{equation} schemes need a velocity array")
 
@@ -518,6 +524,8 @@ class HotPath:
                 return False
             L.check("psk_ssprk33_step_bc", rc)
             return True
+        if self.equation != "burgers" and not self._vel_periodic:
+            return False
         rc = L.lib().psk_ssprk33_step(
             ct.byref(d), L.ptr(u), L.ptr(uout), L.ptr(dt), 0 if dt.numel() == 1 else 1,
             L.raw_ptr(active), L.ptr(maxabs), L.stream_ptr(),

@@ -234,6 +234,31 @@ int emu_fused_step_bc(int equation, int flux, int with_max, int n, int g, int ba
   return 0;
 }
 
+// the whole-step kernel for the advection / continuity equations on PERIODIC rows (psk_ssprk33_step)
+int emu_fused_step_periodic_eq(int equation, int n, int g, int batch, long long ld, double dx, double eps, const double *u,
+                               double *uout, const double *dt, int dt_stride, const double *vel, const double *vel_l,
+                               const double *vel_r) {
+  psk::StepParams q{};
+  q.u = u; q.uout = uout; q.dt = dt;
+  q.ld = ld;
+  q.coef = 1.0 / dx;
+  q.eps9 = eps * (1.0 / 9.0);
+  q.dt_stride = dt_stride;
+  q.n = n;
+  q.g = g;
+  q.vel = vel; q.vel_l = vel_l; q.vel_r = vel_r;
+  void (*k)(const psk::StepParams) = nullptr;
+  if (equation == PSK_EQ_ADVECTION) k = &psk::step_warp_fused_kernel<6, PSK_FLUX_UPWIND, false, 128, 3, false, PSK_EQ_ADVECTION, false>;
+  else if (equation == PSK_EQ_CONTINUITY) k = &psk::step_warp_fused_kernel<6, PSK_FLUX_UPWIND, false, 128, 3, false, PSK_EQ_CONTINUITY, false>;
+  else return -1;
+  q.chunks_per_row = (n + psk::StepGeometry<6>::kEmit - 1) / psk::StepGeometry<6>::kEmit;
+  int wpc = 4;
+  if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
+  const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
+  run_grid(gx, static_cast<unsigned>(batch), wpc, [&]() { k(q); });
+  return 0;
+}
+
 int emu_chunks_per_row(int n) { return psk::fast_geometry(n, 8).chunks_per_row; }
 
 }  // extern "C"

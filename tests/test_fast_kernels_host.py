@@ -46,6 +46,9 @@ def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
     lib.emu_fused_step_bc.argtypes = [ct.c_int] * 6 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int, dp,
                                                       ct.c_longlong, dp, dp, dp, up]
     lib.emu_fused_step_bc.restype = ct.c_int
+    lib.emu_fused_step_periodic_eq.argtypes = [ct.c_int] * 4 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
+                                                               dp, dp, dp]
+    lib.emu_fused_step_periodic_eq.restype = ct.c_int
     lib.emu_chunks_per_row.argtypes = [ct.c_int]
     lib.emu_chunks_per_row.restype = ct.c_int
     return lib
@@ -292,3 +295,31 @@ def test_fused_step_with_dirichlet_data_is_the_three_stages(emu, equation: str, 
     assert np.array_equal(out[:, i], staged[:, i])
     assert np.abs(out[:, i] - ref[:, i]).max() <= 2e-13 * np.abs(ref[:, i]).max()
     assert np.array_equal(maxabs.view(np.float64), np.abs(out[:, i]).max(axis=1))
+
+
+@pytest.mark.parametrize("equation", ["advection", "continuity"])
+@pytest.mark.parametrize("n", [16, 171, 173, 250, 1000])
+def test_fused_step_for_advection_and_continuity_on_periodic_rows(emu, equation: str, n: int) -> None:
+    """psk_ssprk33_step for the linear equations on periodic rows: with a velocity array whose ghost cells are the
+    periodic images of its interior (so that its reconstruction is periodic too) the whole-step kernel -- which
+    advances the image cells of a window with the velocity data of the cells they are images of -- gives the bits
+    of three stage launches"""
+    pb = Problem(equation, "godunov", "periodic", n=n, batch=2, seed=40 + n)
+    # a sign-changing velocity with exactly periodic ghost cells, and the oracle re-bound to it
+    x = (np.arange(n) + 0.5) / n
+    vi = 0.2 + np.sin(2 * np.pi * x + 0.3)
+    v = np.concatenate([vi[n - G :], vi, vi[:G]])
+    pb.co = COracle(equation=equation, flux="godunov", rec="wenojs53", bc="periodic", n=n, g=G, batch=pb.batch, dx=pb.dx,
+                    eps=EPS, velocity=v)
+    k = pb.co.keep
+    assert k["vr"][G - 1] == k["vr"][G + n - 1] and k["vl"][G + n] == k["vl"][G]
+    i = pb.interior
+    staged, _ = pb.step(emu, 2)
+    ref = pb.co.ssprk33_step(pb.u, pb.dt)
+    out = np.full_like(pb.u, np.nan)
+    rc = emu.emu_fused_step_periodic_eq(EQUATION[equation], n, G, pb.batch, pb.nx, pb.dx, EPS, _p(pb.fill(pb.u)), _p(out),
+                                        _p(pb.dt), 1, _p(k["v"]), _p(k["vl"]), _p(k["vr"]))
+    assert rc == 0
+    assert np.isnan(out[:, :G]).all() and np.isnan(out[:, G + n :]).all()
+    assert np.array_equal(out[:, i], staged[:, i])
+    assert np.abs(out[:, i] - ref[:, i]).max() <= 2e-13 * np.abs(ref[:, i]).max()

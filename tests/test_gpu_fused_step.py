@@ -223,3 +223,30 @@ def test_lax_friedrichs_row_blocks_on_several_streams() -> None:
     b.solve_fixed_dt_host(host_in, host_out, dt, nsteps, groups=8, streams=4)
     torch.cuda.synchronize()
     assert torch.equal(host_out[:, G : G + n].cuda(), a.u[:, G : G + n])
+
+
+@pytest.mark.parametrize("equation", ["advection", "continuity"])
+def test_whole_step_for_linear_equations_on_periodic_rows(equation: str) -> None:
+    """one launch per step when the velocity array's ghost cells are the periodic images of its interior (its
+    reconstruction is then periodic too and the bits are those of three stage launches); three stage launches,
+    chosen by the binding itself, for a velocity array that is not periodic in its ghost cells"""
+    batch, n, nsteps = 4, 2048, 5
+    u0 = _ic(batch, n, seed=9)
+    x = (np.arange(n) + 0.5) / n
+    vi = 0.2 + np.sin(2 * np.pi * x + 0.3)
+    vel = np.concatenate([vi[n - G :], vi, vi[:G]])
+    dt = 0.3 * (3.0 / n) / 1.3
+    with whole_step(7000):
+        a = _solver(batch, n, equation=equation, flux="godunov", velocity=vel)
+        a.solve_fixed_dt(u0, dt, nsteps)
+        assert a._fused is False and a.launches == 3 * nsteps
+    b = _solver(batch, n, equation=equation, flux="godunov", velocity=vel)
+    assert b.hp._vel_periodic
+    b.solve_fixed_dt(u0, dt, nsteps)
+    assert b._fused is True and b.launches == nsteps
+    assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
+    xg = (np.arange(n + 2 * G) - G + 0.5) / n
+    c = _solver(batch, n, equation=equation, flux="godunov", velocity=1.0 + 0.3 * xg)  # not periodic
+    assert not c.hp._vel_periodic
+    c.solve_fixed_dt(u0, dt, nsteps)
+    assert c._fused is False and c.launches == 3 * nsteps

@@ -16,11 +16,13 @@ x = (torch.arange(N + 2 * G, device="cuda", dtype=torch.float64) - G + 0.5) / N
 rng = np.random.default_rng(0)
 coef = torch.from_numpy(rng.uniform(0.2, 1.0, size=(B, 1))).cuda()
 u0 = 0.3 + coef * torch.sin(2 * np.pi * x)[None, :]
-vel = (1.0 + 0.3 * torch.sin(2 * np.pi * x + 0.3)).cpu().numpy()
+vi = 1.0 + 0.3 * np.sin(2 * np.pi * (np.arange(N) + 0.5) / N + 0.3)
+vel = np.concatenate([vi[N - G :], vi, vi[:G]])  # ghost cells = periodic images (what psk_ssprk33_step asks for)
 CASES = [
     ("burgers", "rusanov", "periodic"), ("burgers", "rusanov", "dirichlet"), ("burgers", "godunov", "periodic"),
     ("burgers", "eo", "dirichlet"), ("burgers", "lf", "periodic"), ("burgers", "rusanov", "neumann"),
     ("advection", "godunov", "dirichlet"), ("continuity", "godunov", "dirichlet"), ("advection", "godunov", "periodic"),
+    ("continuity", "godunov", "periodic"),
 ]
 for eq, flux, bc in CASES:
     kw = {"velocity": vel} if eq != "burgers" else {}

@@ -5,6 +5,8 @@
 // indexing, the halo traffic and the boundary handling of every layout without a GPU.
 #pragma once
 
+#include <type_traits>
+
 #include "psk_common.cuh"
 #include "psk_math.cuh"
 
@@ -469,26 +471,35 @@ __device__ __forceinline__ void step_load_vel(const StepParams &p, int c0, bool 
   // periodic rows: a window cell beyond the row ends is the image of an interior cell and is advanced with that
   // cell's velocity data (the caller guarantees that the velocity's reconstruction is periodic too, see
   // psk_ssprk33_step: then these are the very numbers the stage kernels read at the row ends)
-  auto wrap = [&](int c) {
-    if (!periodic) return c;
-    c %= n;
-    return c < 0 ? c + n : c;
+  // Only the warps at a row end pay for the modulo: two copies of the loop behind one branch.
+  auto load = [&](auto far) {
+    auto wrap = [&](int c) {
+      if (decltype(far)::value) {
+        c %= n;
+        if (c < 0) c += n;
+      }
+      return c;
+    };
+    v.pos = 0u;
+#pragma unroll
+    for (int f = 0; f <= R; ++f) {
+      const int jl = p.g + wrap(c0 + f - 1), jr = p.g + wrap(c0 + f);  // array indices of the cells left / right of the face
+      const bool ok = periodic || (jl >= 0 && jl < nx - 1);
+      const double arj = ok ? p.vel_r[jl] : 0.0, alp = ok ? p.vel_l[jr] : 0.0;
+      if ((arj + alp) > 0.0) v.pos |= 1u << f;
+      v.ar[f] = arj;
+      v.al[f] = alp;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int c = c0 + r;
+      v.vc[r] = (EQ == PSK_EQ_ADVECTION && (periodic || (c >= 0 && c < n))) ? p.vel[p.g + wrap(c)] : 0.0;
+    }
   };
-  v.pos = 0u;
-#pragma unroll
-  for (int f = 0; f <= R; ++f) {
-    const int jl = p.g + wrap(c0 + f - 1), jr = p.g + wrap(c0 + f);  // array indices of the cells left / right of the face
-    const bool ok = periodic || (jl >= 0 && jl < nx - 1);
-    const double arj = ok ? p.vel_r[jl] : 0.0, alp = ok ? p.vel_l[jr] : 0.0;
-    if ((arj + alp) > 0.0) v.pos |= 1u << f;
-    v.ar[f] = arj;
-    v.al[f] = alp;
-  }
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int c = c0 + r;
-    v.vc[r] = (EQ == PSK_EQ_ADVECTION && (periodic || (c >= 0 && c < n))) ? p.vel[p.g + wrap(c)] : 0.0;
-  }
+  if (periodic && !(c0 - 1 >= 0 && c0 + R < n))
+    load(std::true_type{});
+  else
+    load(std::false_type{});
 }
 
 // Dirichlet rows: the window cells that are ghost cells take the boundary data of `stage` (0, 1, 2); window

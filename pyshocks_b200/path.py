@@ -545,6 +545,17 @@ class HotPath:
             if a is not None and L.rows_of(a)[2] != ld:
                 raise ValueError("all stage arrays must share one row stride")
         d = self.desc(batch, ld)
+        if self.bc == "dirichlet":  # rows with boundary data (the data of set_ghost at all three stage times)
+            g3 = self.ghost3()
+            if g3 is None or (g3.dim() == 3 and g3.shape[1] != batch):
+                return False
+            d.ghost, d.ghost_ld = L.ptr(g3), (0 if g3.dim() == 2 else 2 * self.g)
+            rc = L.lib().psk_ssprk33_step_bc(ct.byref(d), L.ptr(u), L.ptr(uout), L.ptr(dt), 0 if dt.numel() == 1 else 1,
+                                             L.ptr(g3), None, None, L.ptr(k1), L.ptr(k2), L.stream_ptr())
+            if rc == L.E_UNSUPPORTED:
+                return False
+            L.check("psk_ssprk33_step_bc", rc)
+            return True
         rc = L.lib().psk_ssprk33_step_stages(
             ct.byref(d), L.ptr(u), L.ptr(k1), L.ptr(k2), L.ptr(uout), L.ptr(dt), 0 if dt.numel() == 1 else 1,
             L.stream_ptr(),

@@ -193,3 +193,36 @@ def test_optimisation_loop_recovers_an_initial_condition() -> None:
     J0, g0 = adj.gradient(ustar)
     J1, g1 = adj.gradient_half_l2(ustar)
     assert torch.equal(J0, J1) and torch.equal(g0, g1)
+
+
+def test_adjoint_ensemble_on_dirichlet_rows() -> None:
+    """Dirichlet rows: the forward sweep runs psk_ssprk33_step_bc (one launch per step), the reverse sweep recomputes
+    k1, k2 with the same kernel (one launch) and applies three adjoint stage launches; against autograd through the
+    torch twin with the same (time-independent) boundary data"""
+    from pyshocks_b200.ensemble import AdjointEnsemble, EnsembleSolver
+
+    batch, n, nsteps, g = 3, 96, 8, 3
+    grid = po.make_grid(-1.5, 1.5, n, g)
+    rng = np.random.default_rng(5)
+    xh = (grid.x - grid.a) / (grid.b - grid.a)
+    u0 = np.stack([0.3 * b + np.sin(2 * np.pi * xh + b) for b in range(batch)])
+    ghost = rng.uniform(-0.3, 0.3, size=2 * g)
+    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="dirichlet", n=n, g=g, dx=grid.h,
+                            eps=1e-12, batch=batch)
+    solver.hp.set_ghost(ghost)
+    dt = 0.3 * grid.h / np.abs(u0).max()
+    adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=3)
+    assert not adj.fused_reverse
+    J, grad = adj.gradient_half_l2(torch.from_numpy(u0).cuda())
+    assert adj._fused is True  # the forward sweep took the whole-step kernel
+    scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53"))
+    xg = np.concatenate([grid.x[:g], grid.x[-g:]])
+    bc = po.Dirichlet(ga=lambda t, x: np.interp(x, xg, ghost))
+    i = grid.interior
+    for b in range(batch):
+        u = torch.from_numpy(u0[b]).clone().requires_grad_(True)
+        x = u
+        for _ in range(nsteps):
+            x = tt.ssprk33_advance(lambda t_, y: tt.apply_operator(scheme, grid, bc, t_, y), dt, 0.0, x)
+        (gb,) = torch.autograd.grad(0.5 * (x[i] ** 2).sum(), u)
+        assert max_rel(grad[b].cpu().numpy()[i], gb.numpy()[i]) < 1e-12

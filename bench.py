@@ -741,7 +741,8 @@ def measure_adjoint(ctx: Ctx, args: argparse.Namespace, *, batch_total: int, n: 
                     "definition": "executed FP64 thread instructions per cell-step (ncu counters of the reverse kernel "
                                   "at this row length + the whole-step kernel's for the states recomputed inside a tape "
                                   "segment, profiles/traffic.json) x adjoint cell-updates/s x 2 flop per pipe slot, against "
-                                  "the DFMA peak measured in this run; ncu reports the pipe 81.6 % busy for the kernel alone"}
+                                  f"the DFMA peak measured in this run; ncu reports the pipe {tj['reverse_kernel'].get('fp64_pipe_pct', 0):.1f} % busy "
+                                  "for the kernel alone"}
     return {
         "metric": "adjoint gradients/s", "value": batch_total / ((fwd_ms + bwd_ms) * 1e-3), "unit": "gradients/s",
         "n_gpus": world, "steps": nsteps, "scaling": "strong",

@@ -167,6 +167,16 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
                       const uint8_t *active, double *lf_work, double *maxabs,
                       int ghost_rows, psk_stream_t stream);
 
+/* The fused right-hand side with a GENERAL combine,
+ *     uout = ca u0 + cb uin + cc dt L(uin),        L = apply_operator (schemes.py:339-346),
+ * from which the stages of the other steppers of the reference are built (timestepping.py:289-405): ForwardEuler
+ * (1, 0, 1 with u0 = uin), RK44 (y2 = u + dt/2 L(u), ..., u' = acc + 1/3 y4 + dt/6 L(y4)), CKRK45
+ * (k = a_i k + dt L(p)).  Every scheme, reconstruction, boundary kind and math mode of psk_ssprk33_stage;
+ * uout must not alias uin (it may alias u0).  lf_work, ghost_rows as in psk_ssprk33_stage. */
+int psk_rhs_axpby(const psk_desc *d, const double *u0, const double *uin, double *uout, const double *dt,
+                  int64_t dt_stride, double ca, double cb, double cc, double *lf_work, int ghost_rows,
+                  psk_stream_t stream);
+
 /* psk_ssprk33_stage for the global Lax-Friedrichs flux (scalar.py:258-278) on PERIODIC rows WITHOUT the reduction
  * pass: there the speed max |w| over all cells after the boundary condition (scalar.py:277) is max |uin| over the
  * interior (the ghost cells are copies), which the launch that PRODUCED uin has already reduced into its `maxabs`

@@ -63,6 +63,7 @@ struct FastParams {
   int64_t ld;
   double coef;   // 1 / (flux scale * dx)
   double eps9;   // eps / 9
+  double ca, cb, cc;  // STAGE 4: uout = ca u0 + cb uin + cc dt L(uin)  (psk_rhs_axpby)
   int dt_stride;
   int chunks_per_row;
 };
@@ -194,6 +195,8 @@ __device__ __forceinline__ void fast_compute_store(const FastParams &p, int row,
     if (EQ == PSK_EQ_ADVECTION) dF *= (c0 + r >= 0 && c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
     if (STAGE == 0) {
       out[r] = coef * dF;
+    } else if (STAGE == 4) {
+      out[r] = fma(p.cc * coef, dF, fma(p.ca, u0v[r], p.cb * v[r + kHalo]));
     } else {
       const double k = fma(coef, dF, v[r + kHalo]);
       out[r] = (STAGE == 1) ? k
@@ -379,6 +382,8 @@ stage_warp_fast_share_kernel(const FastParams p) {
     if (EQ == PSK_EQ_ADVECTION) dF *= (c0 + r >= 0 && c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
     if (STAGE == 0) {
       out[r] = coef * dF;
+    } else if (STAGE == 4) {
+      out[r] = fma(p.cc * coef, dF, fma(p.ca, u0v[r], p.cb * w[1 + r]));
     } else {
       const double k = fma(coef, dF, w[1 + r]);
       out[r] = (STAGE == 1) ? k

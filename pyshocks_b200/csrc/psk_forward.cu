@@ -50,7 +50,19 @@ struct StageParams {
   int stage;
   int tiles_per_row;
   int vec_ok;  // rows are 16-byte aligned and every tile starts on an even cell
+  double ca, cb, cc;  // stage 4 (psk_rhs_axpby): uout = ca u0 + cb uin + cc dt L(uin)
 };
+
+// stage_combine (psk_math.cuh) plus stage 4, the general combine the other Runge-Kutta methods are built from
+// (timestepping.py:289-405: ForwardEuler, RK44, CKRK45)
+template <bool STRICT>
+__device__ __forceinline__ double stage_combine_p(const StageParams &p, double u0, double w, double dt, double L) {
+  if (p.stage == 4) {
+    if (STRICT) return sadd(sadd(smul(p.ca, u0), smul(p.cb, w)), smul(p.cc, smul(dt, L)));
+    return fma(p.cc * dt, L, fma(p.ca, u0, p.cb * w));
+  }
+  return stage_combine<STRICT>(p.stage, u0, w, dt, L);
+}
 
 template <int R>
 __host__ __device__ __forceinline__ int pad_index(int e) {
@@ -188,7 +200,7 @@ stage_tile_kernel(const StageParams p) {
     double vel = 0.0;
     if (EQ == PSK_EQ_ADVECTION) vel = (c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
     const double L = rhs_from_faces<EQ, STRICT>(F[r], F[r + 1], vel, p.dx, p.invdx);
-    out[r] = stage_combine<STRICT>(p.stage, u0v[r], v[r + kHalo], dt, L);
+    out[r] = stage_combine_p<STRICT>(p, u0v[r], v[r + kHalo], dt, L);
     if (c0 + r < n) {
       const unsigned long long b = abs_bits(out[r]);
       mx = b > mx ? b : mx;
@@ -413,7 +425,7 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
       double vel = 0.0;
       if (EQ == PSK_EQ_ADVECTION) vel = (c0 + r >= 0 && c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
       const double L = rhs_from_faces<EQ, true>(F[r], F[r + 1], vel, p.dx, p.invdx);
-      out[r] = stage_combine<true>(p.stage, u0v[r], v[r + kHalo], dt, L);
+      out[r] = stage_combine_p<true>(p, u0v[r], v[r + kHalo], dt, L);
     }
   } else {
     const double cL = p.invdx * (1.0 / FluxScale<EQ, FLUX>::value);
@@ -424,6 +436,8 @@ __device__ __forceinline__ void chunk_compute(const StageParams &p, const ChunkR
       if (EQ == PSK_EQ_ADVECTION) dF *= (c0 + r >= 0 && c0 + r < n) ? p.vel[g + c0 + r] : 0.0;
       if (p.stage == 0) {
         out[r] = coef * dF;
+      } else if (p.stage == 4) {
+        out[r] = fma(p.cc * coef, dF, fma(p.ca, u0v[r], p.cb * v[r + kHalo]));
       } else {
         const double k = fma(coef, dF, v[r + kHalo]);
         out[r] = (p.stage == 1) ? k
@@ -581,6 +595,7 @@ int launch_fast_stage(const StageParams &p, int batch, cudaStream_t st) {
   q.maxabs = p.maxabs; q.vel = p.vel; q.vel_l = p.vel_l; q.vel_r = p.vel_r; q.bc = p.bc; q.ld = p.ld;
   q.coef = p.invdx / FluxScale<EQ, FLUX>::value;
   q.eps9 = p.eps * (1.0 / 9.0);
+  q.ca = p.ca; q.cb = p.cb; q.cc = p.cc;
   q.dt_stride = static_cast<int>(p.dt_stride);
   const FastGeometry geo = fast_geometry(p.bc.n, g_fast_wpc_max);
   q.chunks_per_row = geo.chunks_per_row;
@@ -604,6 +619,7 @@ int launch_fast(const StageParams &p, int batch, cudaStream_t st) {
     case 0: return launch_fast_stage<EQ, FLUX, 0>(p, batch, st);
     case 1: return launch_fast_stage<EQ, FLUX, 1>(p, batch, st);
     case 2: return launch_fast_stage<EQ, FLUX, 2>(p, batch, st);
+    case 4: return launch_fast_stage<EQ, FLUX, 4>(p, batch, st);
     default: return launch_fast_stage<EQ, FLUX, 3>(p, batch, st);
   }
 }
@@ -689,7 +705,7 @@ __global__ void ghost_rows_kernel(const StageParams p, int batch) {
   const int64_t off = static_cast<int64_t>(row) * p.ld + i;
   const double u0 = (p.stage >= 2) ? p.u0[off] : 0.0;
   // the stage combine uses the RAW stored value of uin, not the boundary-filled one
-  p.uout[off] = stage_combine<STRICT>(p.stage, u0, urow[i], dt, L);
+  p.uout[off] = stage_combine_p<STRICT>(p, u0, urow[i], dt, L);
 }
 
 // ---------------------------------------------------------------------------
@@ -1401,6 +1417,29 @@ int psk_ssprk33_stage(const psk_desc *d, int stage, const double *u0, const doub
   p.lf_speed = lf_work;
   p.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
   p.stage = stage;
+  return d->math == PSK_MATH_STRICT ? dispatch_scheme<true>(d, p, ghost_rows, st)
+                                    : dispatch_scheme<false>(d, p, ghost_rows, st);
+}
+
+/* uout = ca u0 + cb uin + cc dt L(uin): the fused RHS with a general combine (timestepping.py:289-405) */
+int psk_rhs_axpby(const psk_desc *d, const double *u0, const double *uin, double *uout, const double *dt,
+                  int64_t dt_stride, double ca, double cb, double cc, double *lf_work, int ghost_rows,
+                  psk_stream_t stream) {
+  int rc = check_desc(d);
+  if (rc != PSK_OK) return rc;
+  if (u0 == nullptr || uin == nullptr || uout == nullptr || dt == nullptr || uout == uin) return PSK_E_INVALID;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = lf_speed_pass(d, uin, 0, lf_work, st);
+  if (rc != PSK_OK) return rc;
+  StageParams p = make_params(d);
+  p.uin = uin;
+  p.u0 = u0;
+  p.uout = uout;
+  p.dt = dt;
+  p.dt_stride = dt_stride;
+  p.lf_speed = lf_work;
+  p.stage = 4;
+  p.ca = ca; p.cb = cb; p.cc = cc;
   return d->math == PSK_MATH_STRICT ? dispatch_scheme<true>(d, p, ghost_rows, st)
                                     : dispatch_scheme<false>(d, p, ghost_rows, st);
 }

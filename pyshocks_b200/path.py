@@ -79,6 +79,7 @@ class HotPath:
         self._ghost3: torch.Tensor | None = None
         self._ghost_ld = 0
         self._work: dict[tuple, torch.Tensor] = {}
+        self._ends: HotPath | None = None
         if velocity is not None:
             self._vel = self._table(velocity)
             if self._vel.numel() != self.nx:
@@ -475,6 +476,23 @@ class HotPath:
         )
         return uout
 
+    def rhs_axpby(self, u0: torch.Tensor, uin: torch.Tensor, dt: torch.Tensor, ca: float, cb: float, cc: float, *,
+                  out: torch.Tensor | None = None, ghost_rows: bool = False) -> torch.Tensor:
+        """``ca u0 + cb uin + cc dt L(uin)`` in one launch (``psk_rhs_axpby``): the stages of ForwardEuler / RK44 /
+        CKRK45 (timestepping.py:289-405) with their combines fused into the right-hand side."""
+        batch, ld = self._state(uin)
+        res = _like(uin) if out is None else out
+        if L.rows_of(u0)[2] != ld or L.rows_of(res)[2] != ld:
+            raise ValueError("all stage arrays must share one row stride")
+        d = self.desc(batch, ld)
+        L.check(
+            "psk_rhs_axpby",
+            L.lib().psk_rhs_axpby(ct.byref(d), L.ptr(u0), L.ptr(uin), L.ptr(res), L.ptr(dt), 0 if dt.numel() == 1 else 1,
+                                  float(ca), float(cb), float(cc), L.ptr(self._lf_work(batch)), int(ghost_rows),
+                                  L.stream_ptr()),
+        )
+        return res
+
     def stage_lf(self, stage: int, u0: torch.Tensor, uin: torch.Tensor, uout: torch.Tensor, dt: torch.Tensor,
                  speed: torch.Tensor, maxabs: torch.Tensor) -> bool:
         """One fused stage with the global Lax-Friedrichs flux on periodic rows, the speed taken from the ``maxabs``
@@ -534,6 +552,66 @@ class HotPath:
             return False
         L.check("psk_ssprk33_step", rc)
         return True
+
+    _ENDS_W = 32  # cells kept next to each row end by ssprk33_advance: >= 3 stages x (g + 3) cells of dependence
+
+    def _ends_path(self) -> "HotPath":
+        """this path on the ``2 x _ENDS_W`` cells next to the row ends (the cut in the middle is never looked at)"""
+        if self._ends is None:
+            W, g, nx = self._ENDS_W, self.g, self.nx
+            cut = lambda a: None if a is None else torch.cat((a[: g + W], a[nx - g - W :]))  # noqa: E731
+            self._ends = HotPath(equation=self.equation, flux=self.flux, rec=self.rec, bc=self.bc, n=2 * W, g=g,
+                                 dx=self.dx, eps=self.eps, math=self.math, nu=cut(self._nu), velocity=cut(self._vel),
+                                 device=self.device, delta=self.delta)
+        return self._ends
+
+    def ssprk33_advance(self, u: torch.Tensor, dt: torch.Tensor, *,
+                        ghosts: Sequence[np.ndarray | torch.Tensor] | None = None) -> torch.Tensor:
+        """``advance(SSPRK33)`` of the reference (timestepping.py:312-320) INCLUDING the by-products it leaves in the
+        ghost cells of the result: the whole-step kernel writes the interior in one launch, and the three stage
+        launches run only on the ``2 x 32`` cells next to the row ends (the ghost cells of the result depend on
+        nothing farther than ``3 (g + 3)`` cells away), whose ghost cells are copied over.  Falls back to the three
+        full stage launches wherever the whole-step kernel does not exist."""
+        W, g, nx = self._ENDS_W, self.g, self.nx
+        if self.math != "fast" or self.n < 4 * W:
+            return self.ssprk33_step(u, dt, ghosts=ghosts, ghost_rows=True)
+        # the whole-step kernel wants 16-byte aligned interiors: a plain (batch, nx) array of the caller is copied
+        # once into the padded row layout; the result is returned as a view of that layout, so the next advance of
+        # a step() loop finds its input aligned and copies nothing
+        ua = self.aligned(u)
+        out = self._aligned_like(u)
+        if not self.step_fused(ua, out, dt, ghosts=ghosts):
+            return self.ssprk33_step(u, dt, ghosts=ghosts, ghost_rows=True)
+        ends = self._ends_path()
+        if ghosts is None and self._ghost is not None:
+            ends._ghost, ends._ghost3, ends._ghost_ld = self._ghost, None, self._ghost_ld
+        r = ends.ssprk33_step(torch.cat((ua[..., : g + W], ua[..., nx - g - W :]), dim=-1), dt, ghosts=ghosts,
+                              ghost_rows=True)
+        out[..., :g] = r[..., :g]
+        out[..., nx - g :] = r[..., 2 * W + g :]
+        return out
+
+    def _rows_aligned(self, u: torch.Tensor) -> bool:
+        """whether ``u`` already sits in the padded row layout (the arrays of _aligned_like and of EnsembleSolver)"""
+        from .ensemble import row_layout
+
+        return (u.data_ptr() + 8 * self.g) % 16 == 0 and (u.dim() == 1 or L.rows_of(u)[2] == row_layout(self.n, self.g)[1])
+
+    def aligned(self, u: torch.Tensor) -> torch.Tensor:
+        """``u`` itself if it sits in the padded row layout, else a copy that does"""
+        if self._rows_aligned(u):
+            return u
+        ua = self._aligned_like(u)
+        ua.copy_(u)
+        return ua
+
+    def _aligned_like(self, u: torch.Tensor) -> torch.Tensor:
+        """uninitialised ``u.shape`` view of storage in the padded row layout (ensemble.row_layout)"""
+        from .ensemble import row_layout
+
+        col0, ld = row_layout(self.n, self.g)
+        store = torch.empty(tuple(u.shape[:-1]) + (ld,), dtype=torch.float64, device=u.device)
+        return store[..., col0 : col0 + self.nx]
 
     def step_fused_stages(self, u: torch.Tensor, k1: torch.Tensor, k2: torch.Tensor, uout: torch.Tensor | None,
                           dt: torch.Tensor) -> bool:

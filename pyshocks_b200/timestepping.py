@@ -14,6 +14,7 @@ state, then three fused adjoint stage launches.
 
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 from functools import singledispatch
 from typing import Any, Callable, ClassVar, Iterator
@@ -120,6 +121,11 @@ def jit(fun: Callable | None = None, **kwargs: Any) -> Callable:
 def _bound_of(source: Any, probe: tuple | None = None) -> BoundOperator | None:
     if isinstance(source, BoundOperator):
         return source
+    if isinstance(source, functools.partial) and not source.keywords and len(source.args) == 3:
+        from .schemes import apply_operator
+
+        if source.func is apply_operator:  # partial(apply_operator, scheme, grid, bc)
+            return BoundOperator(*source.args)
     b = getattr(source, "bound", None)
     if b is None and probe is not None and hasattr(source, "_traced") and not source._traced:
         source(*probe)  # first call of a jit() wrapper: trace it
@@ -258,6 +264,9 @@ def _advance_forward_euler(stepper: ForwardEuler, dt: ScalarLike, t: ScalarLike,
     from .path import _like
 
     hp = hotpath_for(bound.scheme, bound.grid, bound.bc, t)
+    if hp.math == "fast":  # arrays in the padded row layout: vector loads; nothing to copy from the 2nd step on
+        u = hp.aligned(u)
+        return hp.stage(1, u, u, hp._aligned_like(u), _as_dt(dt, u), ghost_rows=True)
     return hp.stage(1, u, u, _like(u), _as_dt(dt, u), ghost_rows=True)
 
 
@@ -280,7 +289,7 @@ def _advance_ssprk33(stepper: SSPRK33, dt: ScalarLike, t: ScalarLike, u: Array) 
     ghosts = None
     if ghost_data(bound.bc, bound.grid, t) is not None:
         ghosts = [ghost_data(bound.bc, bound.grid, tt) for tt in (t, t + dt, t + 0.5 * dt)]
-    return hp.ssprk33_step(u, _as_dt(dt, u), ghosts=ghosts, ghost_rows=True)
+    return hp.ssprk33_advance(u, _as_dt(dt, u), ghosts=ghosts)
 
 
 # {{{ RK44 / CKRK45 (timestepping.py:325-405): generic steppers -- each RHS is one fused
@@ -293,8 +302,35 @@ class RK44(Stepper):
     """The classic fourth-order Runge-Kutta method with 4 stages (timestepping.py:328-343)."""
 
 
+def _fused_binding(stepper: Stepper, t: ScalarLike, u: Array):
+    """the (scheme, grid, bc) of a source that is exactly one apply_operator call, in FAST math: the stage combines
+    of RK44 / CKRK45 are then fused into the right-hand side kernel (psk_rhs_axpby).  STRICT math keeps the
+    reference's own array expressions below -- bit-identical to its advance, which a fused combine cannot be."""
+    from . import config
+
+    if config.MATH != "fast":
+        return None
+    return _bound_of(stepper.source, (t, u))
+
+
 @advance.register(RK44)
 def _advance_rk44(stepper: RK44, dt: ScalarLike, t: ScalarLike, u: Array) -> Array:
+    bound = _fused_binding(stepper, t, u)
+    if bound is not None:
+        # y2 = u + dt/2 L(t, u), y3 = u + dt/2 L(t + dt/2, y2), y4 = u + dt L(t + dt/2, y3),
+        # u' = u + (k1 + 2 k2 + 2 k3 + k4) / 6 = (-u + y2 + 2 y3) / 3 + y4 / 3 + dt/6 L(t + dt, y4)
+        from .binding import hotpath_for
+
+        dtt = _as_dt(dt, u)
+        hp = hotpath_for(bound.scheme, bound.grid, bound.bc, t)
+        u = hp.aligned(u)  # (arrays in the padded row layout: vector loads in the kernels; no copy from the 2nd step on)
+        y2 = hp.rhs_axpby(u, u, dtt, 1.0, 0.0, 0.5, out=hp._aligned_like(u), ghost_rows=True)
+        hp = hotpath_for(bound.scheme, bound.grid, bound.bc, t + dt / 2)
+        y3 = hp.rhs_axpby(u, y2, dtt, 1.0, 0.0, 0.5, out=hp._aligned_like(u), ghost_rows=True)
+        y4 = hp.rhs_axpby(u, y3, dtt, 1.0, 0.0, 1.0, out=hp._aligned_like(u), ghost_rows=True)
+        acc = torch.add(y2, y3, alpha=2.0, out=y2).sub_(u)  # 3 x the part of u' that needs no further L
+        hp = hotpath_for(bound.scheme, bound.grid, bound.bc, t + dt)
+        return hp.rhs_axpby(acc, y4, dtt, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 6.0, out=y3, ghost_rows=True)
     fn = stepper.source
     k1 = dt * fn(t, u)
     k2 = dt * fn(t + dt / 2, u + k1 / 2)
@@ -335,6 +371,20 @@ class CKRK45(Stepper):
 
 @advance.register(CKRK45)
 def _advance_ckrk45(stepper: CKRK45, dt: ScalarLike, t: ScalarLike, u: Array) -> Array:
+    bound = _fused_binding(stepper, t, u)
+    if bound is not None:
+        # k <- a_i k + dt L(t + c_i dt, p) in one launch, p <- p + b_i k
+        from .binding import hotpath_for
+
+        dtt = _as_dt(dt, u)
+        hp = hotpath_for(bound.scheme, bound.grid, bound.bc, t)
+        p = k = hp.aligned(u)
+        for i in range(len(stepper.a)):
+            hp = hotpath_for(bound.scheme, bound.grid, bound.bc, t + stepper.c[i] * dt)
+            # (k is both u0 and the output from the 2nd stage on: every cell reads its own u0 only)
+            k = hp.rhs_axpby(k, p, dtt, stepper.a[i], 0.0, 1.0, out=hp._aligned_like(u) if i == 0 else k, ghost_rows=True)
+            p = torch.add(p, k, alpha=stepper.b[i], out=hp._aligned_like(u) if i == 0 else p)
+        return p
     fn = stepper.source
     p = k = u
     for i in range(len(stepper.a)):

@@ -250,3 +250,36 @@ def test_whole_step_for_linear_equations_on_periodic_rows(equation: str) -> None
     assert not c.hp._vel_periodic
     c.solve_fixed_dt(u0, dt, nsteps)
     assert c._fused is False and c.launches == 3 * nsteps
+
+
+@pytest.mark.parametrize("equation,flux,bc", [("burgers", "rusanov", "periodic"), ("burgers", "godunov", "dirichlet"),
+                                              ("burgers", "eo", "periodic"), ("advection", "godunov", "periodic"),
+                                              ("continuity", "godunov", "dirichlet"), ("burgers", "lf", "periodic"),
+                                              ("burgers", "rusanov", "neumann")])
+@pytest.mark.parametrize("batch,n", [(3, 1000), (1, 128), (2, 4096), (2, 100)])
+def test_advance_keeps_the_ghost_cell_byproducts_of_the_reference(equation: str, flux: str, bc: str, batch: int, n: int) -> None:
+    """HotPath.ssprk33_advance (what ``advance(SSPRK33)`` launches): the whole-step kernel for the interior plus the
+    three stage launches on the 2 x 32 cells next to the row ends -- the FULL array, ghost cells included, carries
+    the bits of three full stage launches with ghost_rows (the by-products the reference's advance leaves there,
+    timestepping.py:312-320 over schemes.py:339-346); schemes without a whole-step kernel run the three launches"""
+    from pyshocks_b200.path import HotPath
+
+    kw = {}
+    if equation != "burgers":
+        vi = 0.2 + np.sin(2 * np.pi * (np.arange(n) + 0.5) / n + 0.3)
+        kw["velocity"] = np.concatenate([vi[n - G :], vi, vi[:G]])
+    hp = HotPath(equation=equation, flux=flux, rec="wenojs53", bc=bc, n=n, g=G, dx=3.0 / n, eps=1e-12, **kw)
+    s = _solver(batch, n)
+    (u,) = s.new_states(1)
+    u.copy_(_ic(batch, n, seed=n + batch))
+    rng = np.random.default_rng(1)
+    ghosts = None if bc == "periodic" else [rng.uniform(-0.3, 0.3, size=2 * G) for _ in range(3)]
+    dt = torch.full((1,), 0.3 * (3.0 / n) / 2.0, dtype=torch.float64, device="cuda")
+    ref = hp.ssprk33_step(u, dt, ghosts=ghosts, ghost_rows=True)
+    out = hp.ssprk33_advance(u, dt, ghosts=ghosts)
+    assert torch.equal(out, ref)
+    if bc != "periodic":  # the data of set_ghost at all three stage times
+        hp.set_ghost(ghosts[0])
+        assert torch.equal(hp.ssprk33_advance(u, dt), hp.ssprk33_step(u, dt, ghost_rows=True))
+    one = hp.ssprk33_advance(u[0], dt, ghosts=ghosts)  # a single row, 1-D
+    assert torch.equal(one, ref[0])

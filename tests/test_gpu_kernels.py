@@ -86,6 +86,35 @@ def test_rhs_fast_within_tolerance(case: C.Case) -> None:
 
 
 @pytest.mark.parametrize("math", ["strict", "fast"])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.key)
+def test_rhs_axpby_is_the_combine_of_the_reference_rhs(case: C.Case, math: str) -> None:
+    """psk_rhs_axpby: ``ca u0 + cb u + cc dt L(u)`` in one launch, the building block of the fused RK44 / CKRK45
+    stages (timestepping.py:289-405), against the same expression over the recorded reference ``L``: bitwise in
+    STRICT math (every operation rounded once, left to right), within the RHS tolerance in FAST math."""
+    hp, scheme, grid, bc = hotpath_for(case, math)
+    k = case.key
+    u_h = RHS[f"{k}_u"]
+    rng = np.random.default_rng(17)
+    u0_h = u_h + 0.1 * rng.standard_normal(u_h.shape)
+    if case.bc == "dirichlet":
+        hp.set_ghost(C.dirichlet_values(case, case.t, ghost_x(case, grid)))
+    dt = 0.37 * grid.h
+    for ca, cb, cc in [(1.0, 0.0, 0.5), (-0.4178904745, 0.0, 1.0), (1.0, 1.0 / 3.0, 1.0 / 6.0), (0.0, 1.0, 1.0)]:
+        ref = ca * u0_h + cb * u_h + cc * (dt * RHS[f"{k}_L"])
+        out = host(hp.rhs_axpby(dev(u0_h), dev(u_h), dev(np.array([dt])), ca, cb, cc, out=torch.zeros_like(dev(u_h))))
+        it = grid.interior
+        if math == "strict":
+            assert_strict(out[it], ref[it])
+        else:
+            scale = max(np.max(np.abs(dt * RHS[f"{k}_L"])), 1.0e-300)
+            assert np.max(np.abs(out[it] - ref[it])) < FAST_RHS_TOL * max(scale, np.max(np.abs(ref[it])))
+    # the output must not alias the RHS input: its halo is read while neighbours are written
+    uu = dev(u_h)
+    with pytest.raises(Exception, match="psk_rhs_axpby"):
+        hp.rhs_axpby(dev(u0_h), uu, dev(np.array([dt])), 1.0, 0.0, 1.0, out=uu)
+
+
+@pytest.mark.parametrize("math", ["strict", "fast"])
 @pytest.mark.parametrize("case", [c for c in CASES if f"{c.key}_out" in ADV], ids=lambda c: c.key)
 def test_ssprk33_step_matches_reference_advance(case: C.Case, math: str) -> None:
     hp, scheme, grid, bc = hotpath_for(case, math)

@@ -647,7 +647,7 @@ int psk_ssprk33_adjoint_sweep(const psk_desc *d, const double *tape, int64_t tap
     // k1, k2 of the checkpointed state: one launch where the whole-step kernel exists, else two stage launches
     // (the stored ghost cells of k1, k2 are never read: every stage kernel applies the boundary condition itself)
     rc = PSK_E_UNSUPPORTED;
-    if (d->bc == PSK_BC_DIRICHLET && ghost_table != nullptr)
+    if ((d->bc == PSK_BC_DIRICHLET || d->bc == PSK_BC_NEUMANN) && ghost_table != nullptr)
       rc = psk_ssprk33_step_bc(d, u, nullptr, dt, 0, ds[0].ghost, nullptr, nullptr, k1, k2, stream);
     else if (d->bc == PSK_BC_PERIODIC)
       rc = psk_ssprk33_step_stages(d, u, k1, k2, nullptr, dt, 0, stream);

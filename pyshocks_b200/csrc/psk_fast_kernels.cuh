@@ -520,6 +520,46 @@ __device__ __forceinline__ void step_fill_ghosts(const StepParams &p, int row, i
   }
 }
 
+// Neumann rows (scalar.py:472-500): the ghost cell -1 - k takes the stage value of its mirror image k plus the
+// boundary data of `stage`, n + k that of n - 1 - k (k = 0, 1, 2: a stage reaches no farther).  The image sits
+// 2 k + 1 <= 5 < R places to the right (left end) / left (right end) in the window: in a register of the same lane or
+// of its neighbour, both known at compile time -- five shuffles per side, then selects.  `left` / `right` (the window
+// reaches beyond that end of the row) are warp-uniform.  Window cells beyond the three ghost cells never reach a
+// stored cell.
+template <int R>
+__device__ __forceinline__ void step_fill_neumann(const StepParams &p, int row, int stage, int c0, bool left, bool right,
+                                                  double (&a)[R]) {
+  static_assert(R >= 6, "an image is at most five places away");
+  constexpr unsigned kFull = 0xffffffffu;
+  const double *gh = p.ghost3 + static_cast<int64_t>(stage) * p.ghost_block + static_cast<int64_t>(row) * p.ghost_ld;
+  if (left) {
+    double nb[5];  // the first five cells of the next lane
+#pragma unroll
+    for (int j = 0; j < 5; ++j) nb[j] = __shfl_down_sync(kFull, a[j], 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double src = (r + 2 * k + 1 < R) ? a[(r + 2 * k + 1) % R] : nb[(r + 2 * k + 1) % R % 5];
+        if (c0 + r == -1 - k) a[r] = src + gh[p.g - 1 - k];
+      }
+    }
+  }
+  if (right) {
+    double nb[5];  // the last five cells of the previous lane
+#pragma unroll
+    for (int j = 0; j < 5; ++j) nb[j] = __shfl_up_sync(kFull, a[R - 5 + j], 1);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double src = (r - 2 * k - 1 >= 0) ? a[(r - 2 * k - 1 + R) % R] : nb[(r - 2 * k - 1 + 5) % 5];
+        if (c0 + r == p.n + k) a[r] = src + gh[p.g + k];
+      }
+    }
+  }
+}
+
 template <int R>
 struct StepGeometry {
   static constexpr int kWindow = 32 * R;
@@ -607,11 +647,12 @@ __device__ __forceinline__ void step_store(double *dst, bool inside, const bool 
 // the third stage is skipped when no uout is given: the recomputation of the reverse sweep, which needs
 // k1 and k2 of a checkpointed state (and the next state, inside a tape segment), in one launch
 // instead of two or three.
-// EQ / DIRICHLET: the same kernel for the advection and continuity equations (upwind flux with the velocity's
-// reconstruction) and for rows with Dirichlet boundary data -- the window cells that are ghost cells take the data
-// of each stage time before that stage, exactly where apply_boundary writes them (scalar.py:418-427).
+// EQ / BCK: the same kernel for the advection and continuity equations (upwind flux with the velocity's
+// reconstruction) and for rows with boundary data, BCK = 1 Dirichlet, 2 Neumann -- the window cells that are ghost
+// cells take the data of each stage time (Neumann: plus the stage value of their mirror image) before that stage,
+// exactly where apply_boundary writes them (scalar.py:418-427, 472-500).
 template <int R, int FLUX, bool WITH_MAX, int THREADS, int MINB, bool STAGES = false, int EQ = PSK_EQ_BURGERS,
-          bool DIRICHLET = false>
+          int BCK = 0>
 __global__ void __launch_bounds__(THREADS, MINB)
 step_warp_fused_kernel(const StepParams p) {
   using Geo = StepGeometry<R>;
@@ -621,8 +662,11 @@ step_warp_fused_kernel(const StepParams p) {
   if (chunk >= p.chunks_per_row) return;
   const int row = blockIdx.y + blockIdx.z * gridDim.y;
   const int n = p.n;
-  const int c0 = chunk * Geo::kEmit - Geo::kSkip + R * lane;  // first own cell (interior coordinates)
+  constexpr bool DIRICHLET = BCK == 1, NEUMANN = BCK == 2;
+  const int wstart = chunk * Geo::kEmit - Geo::kSkip;  // first window cell (interior coordinates)
+  const int c0 = wstart + R * lane;                    // first own cell
   const bool inside = (c0 >= 0) && (c0 + R <= n);
+  const bool edge = (wstart < 0) || (wstart + Geo::kWindow > n);  // the window reaches beyond the row (warp-uniform)
   const int64_t base = static_cast<int64_t>(row) * p.ld + p.g;
   // which own cells are stored: window cells [kSkip, kWindow - kSkip) that exist in the row
   const int wc0 = R * lane;
@@ -643,7 +687,13 @@ step_warp_fused_kernel(const StepParams p) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       int c = c0 + r;
-      if (DIRICHLET) {
+      if (NEUMANN) {  // apply_boundary straight from the stored state (scalar.py:472-500)
+        const double *gh = p.ghost3 + static_cast<int64_t>(row) * p.ghost_ld;
+        u0[r] = (c >= 0 && c < n)        ? p.u[base + c]
+                : (c >= -3 && c < 0)     ? p.u[base - 1 - c] + gh[p.g + c]
+                : (c >= n && c < n + 3)  ? p.u[base + 2 * n - 1 - c] + gh[p.g + c - n]
+                                         : 0.0;
+      } else if (DIRICHLET) {
         u0[r] = (c >= 0 && c < n) ? p.u[base + c] : 0.0;  // ghost cells: step_fill_ghosts below
       } else if (p.bc_none) {  // ghost cells filled by the neighbouring slabs; further out: never reaches a stored cell
         u0[r] = (c >= -p.g && c < n + p.g) ? p.u[base + c] : 0.0;
@@ -662,7 +712,7 @@ step_warp_fused_kernel(const StepParams p) {
   }
   const double cdt = p.coef * p.dt[static_cast<int64_t>(row) * p.dt_stride];
   StepVel<R> vel;
-  if (EQ != PSK_EQ_BURGERS) step_load_vel<R, EQ>(p, c0, !DIRICHLET && !p.bc_none, vel);
+  if (EQ != PSK_EQ_BURGERS) step_load_vel<R, EQ>(p, c0, BCK == 0 && !p.bc_none, vel);
   if (DIRICHLET && !inside) step_fill_ghosts<R>(p, row, 0, c0, u0);
 
   double a[R], dF[R];
@@ -671,6 +721,9 @@ step_warp_fused_kernel(const StepParams p) {
   for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);  // k1
   if (STAGES) step_store<R>(p.k1_out + base + c0, inside, st, a);
   if (DIRICHLET && !inside) step_fill_ghosts<R>(p, row, 1, c0, a);
+  if constexpr (NEUMANN) {
+    if (edge) step_fill_neumann<R>(p, row, 1, c0, wstart < 0, wstart + Geo::kWindow > n, a);
+  }
   step_stage_rhs<R, FLUX, EQ>(a, p.eps9, dF, &vel);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);  // k2
@@ -679,6 +732,9 @@ step_warp_fused_kernel(const StepParams p) {
     if (p.uout == nullptr) return;
   }
   if (DIRICHLET && !inside) step_fill_ghosts<R>(p, row, 2, c0, a);
+  if constexpr (NEUMANN) {
+    if (edge) step_fill_neumann<R>(p, row, 2, c0, wstart < 0, wstart + Geo::kWindow > n, a);
+  }
   step_stage_rhs<R, FLUX, EQ>(a, p.eps9, dF, &vel);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);  // u'

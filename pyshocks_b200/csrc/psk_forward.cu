@@ -1043,7 +1043,7 @@ __global__ void step_control_kernel(int batch, double theta, double cfl_scale, d
 // 7000 = off (three stage launches)
 static int g_step_variant = 62;  // R = 6, CTAs of 128 threads, 3 per SM (136 registers): 9.0e10 cell-updates/s on B200
 
-template <int R, int FLUX, int THREADS, int MINB, bool STAGES = false, int EQ = PSK_EQ_BURGERS, bool DIRICHLET = false>
+template <int R, int FLUX, int THREADS, int MINB, bool STAGES = false, int EQ = PSK_EQ_BURGERS, int BCK = 0>
 int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cudaStream_t st) {
   StepParams q = q0;
   q.chunks_per_row = (n + StepGeometry<R>::kEmit - 1) / StepGeometry<R>::kEmit;
@@ -1054,11 +1054,11 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
   if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;
   const dim3 grid(gx, gy, gz);
   if (STAGES)
-    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, STAGES, EQ, DIRICHLET><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, STAGES, EQ, BCK><<<grid, wpc * 32, 0, st>>>(q);
   else if (with_max)
-    step_warp_fused_kernel<R, FLUX, true, THREADS, MINB, false, EQ, DIRICHLET><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, true, THREADS, MINB, false, EQ, BCK><<<grid, wpc * 32, 0, st>>>(q);
   else
-    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, false, EQ, DIRICHLET><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, false, EQ, BCK><<<grid, wpc * 32, 0, st>>>(q);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
 }
@@ -1224,23 +1224,25 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     }
     return PSK_OK;
   }
-  if (d->bc == PSK_BC_DIRICHLET && k1_out != nullptr) {  // ... with the stage values stored (reverse sweep)
-    constexpr int kB = PSK_EQ_BURGERS, kUp = PSK_FLUX_UPWIND;
-    if (d->equation == PSK_EQ_ADVECTION) return launch_step_shape<6, kUp, 128, 3, true, PSK_EQ_ADVECTION, true>(q, d->n, batch, false, st);
-    if (d->equation == PSK_EQ_CONTINUITY) return launch_step_shape<6, kUp, 128, 3, true, PSK_EQ_CONTINUITY, true>(q, d->n, batch, false, st);
-    if (d->flux == PSK_FLUX_UPWIND) return launch_step_shape<6, kUp, 128, 3, true, kB, true>(q, d->n, batch, false, st);
-    if (d->flux == PSK_FLUX_ENGQUIST_OSHER)
-      return launch_step_shape<6, PSK_FLUX_ENGQUIST_OSHER, 128, 3, true, kB, true>(q, d->n, batch, false, st);
-    return launch_step_shape<6, PSK_FLUX_RUSANOV, 128, 3, true, kB, true>(q, d->n, batch, false, st);
-  }
-  if (d->bc == PSK_BC_DIRICHLET) {  // rows with boundary data: default shape only
-    constexpr int kB = PSK_EQ_BURGERS, kUp = PSK_FLUX_UPWIND;
-    if (d->equation == PSK_EQ_ADVECTION) return launch_step_shape<6, kUp, 128, 3, false, PSK_EQ_ADVECTION, true>(q, d->n, batch, mx, st);
-    if (d->equation == PSK_EQ_CONTINUITY) return launch_step_shape<6, kUp, 128, 3, false, PSK_EQ_CONTINUITY, true>(q, d->n, batch, mx, st);
-    if (d->flux == PSK_FLUX_UPWIND) return launch_step_shape<6, kUp, 128, 3, false, kB, true>(q, d->n, batch, mx, st);
-    if (d->flux == PSK_FLUX_ENGQUIST_OSHER)
-      return launch_step_shape<6, PSK_FLUX_ENGQUIST_OSHER, 128, 3, false, kB, true>(q, d->n, batch, mx, st);
-    return launch_step_shape<6, PSK_FLUX_RUSANOV, 128, 3, false, kB, true>(q, d->n, batch, mx, st);
+  if (d->bc == PSK_BC_DIRICHLET || d->bc == PSK_BC_NEUMANN) {  // rows with boundary data: default shape only
+    constexpr int kB = PSK_EQ_BURGERS, kUp = PSK_FLUX_UPWIND, kEO = PSK_FLUX_ENGQUIST_OSHER, kRus = PSK_FLUX_RUSANOV;
+    const bool neumann = d->bc == PSK_BC_NEUMANN;
+    const bool mxs = (k1_out != nullptr) ? false : mx;
+    // (k1_out given: the stage values are stored too, for the reverse sweep)
+#define PSK_STEP_BC(FL, EQ)                                                                                      \
+  do {                                                                                                           \
+    if (k1_out != nullptr)                                                                                       \
+      return neumann ? launch_step_shape<6, FL, 128, 3, true, EQ, 2>(q, d->n, batch, false, st)                  \
+                     : launch_step_shape<6, FL, 128, 3, true, EQ, 1>(q, d->n, batch, false, st);                 \
+    return neumann ? launch_step_shape<6, FL, 128, 3, false, EQ, 2>(q, d->n, batch, mxs, st)                     \
+                   : launch_step_shape<6, FL, 128, 3, false, EQ, 1>(q, d->n, batch, mxs, st);                    \
+  } while (0)
+    if (d->equation == PSK_EQ_ADVECTION) PSK_STEP_BC(kUp, PSK_EQ_ADVECTION);
+    if (d->equation == PSK_EQ_CONTINUITY) PSK_STEP_BC(kUp, PSK_EQ_CONTINUITY);
+    if (d->flux == PSK_FLUX_UPWIND) PSK_STEP_BC(kUp, kB);
+    if (d->flux == PSK_FLUX_ENGQUIST_OSHER) PSK_STEP_BC(kEO, kB);
+    PSK_STEP_BC(kRus, kB);
+#undef PSK_STEP_BC
   }
   if (d->equation != PSK_EQ_BURGERS) {  // periodic rows, upwind flux with the velocity's reconstruction
     if (k1_out != nullptr) return PSK_E_UNSUPPORTED;
@@ -1505,7 +1507,7 @@ int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const 
                           (d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER);
   const bool linear_ok = d->equation != PSK_EQ_BURGERS && d->flux == PSK_FLUX_UPWIND;
   if (!(burgers_ok || linear_ok) || d->rec != PSK_REC_WENOJS53 || d->math != PSK_MATH_FAST || !aligned ||
-      g_step_variant == 0 || d->bc != PSK_BC_DIRICHLET || d->g < 3)
+      g_step_variant == 0 || (d->bc != PSK_BC_DIRICHLET && d->bc != PSK_BC_NEUMANN) || d->g < 3 || d->n < d->g)
     return PSK_E_UNSUPPORTED;
   return launch_step_fused(&d2, u, uout, dt, dt_stride, active, maxabs, static_cast<cudaStream_t>(stream), k1_out,
                            k2_out, ghost3);
@@ -1516,13 +1518,13 @@ int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const 
 int psk_ssprk33_steps_tape(const psk_desc *d, double *tape, int64_t tape_stride, int nsteps, const double *dt_table,
                            const double *ghost_table, psk_stream_t stream) {
   if (d == nullptr || tape == nullptr || dt_table == nullptr || nsteps <= 0 || tape_stride <= 0) return PSK_E_INVALID;
-  if (d->bc == PSK_BC_DIRICHLET && ghost_table == nullptr) return PSK_E_INVALID;
+  if ((d->bc == PSK_BC_DIRICHLET || d->bc == PSK_BC_NEUMANN) && ghost_table == nullptr) return PSK_E_INVALID;
   const int64_t ghost_block = d->ghost_ld != 0 ? static_cast<int64_t>(d->batch) * d->ghost_ld : 2 * d->g;
   for (int m = 0; m < nsteps; ++m) {
     const double *u = tape + static_cast<int64_t>(m) * tape_stride;
     double *un = tape + static_cast<int64_t>(m + 1) * tape_stride;
     int rc;
-    if (d->bc == PSK_BC_DIRICHLET)
+    if (d->bc == PSK_BC_DIRICHLET || d->bc == PSK_BC_NEUMANN)
       rc = psk_ssprk33_step_bc(d, u, un, dt_table + m, 0, ghost_table + static_cast<int64_t>(3) * m * ghost_block, nullptr,
                                nullptr, nullptr, nullptr, stream);
     else

@@ -527,10 +527,10 @@ class HotPath:
         if L.rows_of(uout)[2] != ld:
             raise ValueError("all stage arrays must share one row stride")
         d = self.desc(batch, ld)
-        if self.bc == "dirichlet":
+        if self.bc in ("dirichlet", "neumann"):
             g3 = self.ghost3(ghosts)
             if g3 is None:
-                raise ValueError("Dirichlet rows need boundary data (set_ghost or ghosts=)")
+                raise ValueError("Dirichlet / Neumann rows need boundary data (set_ghost or ghosts=)")
             if g3.dim() == 3 and g3.shape[1] != batch:
                 raise ValueError("per-row ghost data does not match the batch size")
             d.ghost, d.ghost_ld = L.ptr(g3), (0 if g3.dim() == 2 else 2 * self.g)
@@ -623,7 +623,7 @@ class HotPath:
             if a is not None and L.rows_of(a)[2] != ld:
                 raise ValueError("all stage arrays must share one row stride")
         d = self.desc(batch, ld)
-        if self.bc == "dirichlet":  # rows with boundary data (the data of set_ghost at all three stage times)
+        if self.bc in ("dirichlet", "neumann"):  # rows with boundary data (the data of set_ghost at all three stage times)
             g3 = self.ghost3()
             if g3 is None or (g3.dim() == 3 and g3.shape[1] != batch):
                 return False

@@ -197,7 +197,7 @@ int emu_fused_step_stages(int n, int g, int batch, long long ld, double dx, doub
 
 // psk_ssprk33_step_bc: the whole-step kernel on rows with Dirichlet data at the three stage times (ghost3: three
 // blocks of batch * ghost_ld or 2 g doubles), Burgers fluxes or the advection / continuity upwind flux.
-int emu_fused_step_bc(int equation, int flux, int with_max, int n, int g, int batch, long long ld, double dx, double eps,
+int emu_fused_step_bc(int equation, int flux, int with_max, int neumann, int n, int g, int batch, long long ld, double dx, double eps,
                       const double *u, double *uout, const double *dt, int dt_stride, const double *ghost3,
                       long long ghost_ld, const double *vel, const double *vel_l, const double *vel_r,
                       unsigned long long *maxabs) {
@@ -217,8 +217,10 @@ int emu_fused_step_bc(int equation, int flux, int with_max, int n, int g, int ba
   void (*k)(const psk::StepParams) = nullptr;
   constexpr int kB = PSK_EQ_BURGERS, kUp = PSK_FLUX_UPWIND;
 #define EMU_BC(FL, EQ)                                                                                          \
-  k = with_max ? &psk::step_warp_fused_kernel<6, FL, true, 128, 3, false, EQ, true>                             \
-               : &psk::step_warp_fused_kernel<6, FL, false, 128, 3, false, EQ, true>
+  k = neumann ? (with_max ? &psk::step_warp_fused_kernel<6, FL, true, 128, 3, false, EQ, 2>                     \
+                          : &psk::step_warp_fused_kernel<6, FL, false, 128, 3, false, EQ, 2>)                   \
+              : (with_max ? &psk::step_warp_fused_kernel<6, FL, true, 128, 3, false, EQ, 1>                     \
+                          : &psk::step_warp_fused_kernel<6, FL, false, 128, 3, false, EQ, 1>)
   if (equation == PSK_EQ_ADVECTION && flux == kUp) { EMU_BC(kUp, PSK_EQ_ADVECTION); }
   else if (equation == PSK_EQ_CONTINUITY && flux == kUp) { EMU_BC(kUp, PSK_EQ_CONTINUITY); }
   else if (equation == kB && flux == PSK_FLUX_RUSANOV) { EMU_BC(PSK_FLUX_RUSANOV, kB); }
@@ -248,8 +250,8 @@ int emu_fused_step_periodic_eq(int equation, int n, int g, int batch, long long 
   q.g = g;
   q.vel = vel; q.vel_l = vel_l; q.vel_r = vel_r;
   void (*k)(const psk::StepParams) = nullptr;
-  if (equation == PSK_EQ_ADVECTION) k = &psk::step_warp_fused_kernel<6, PSK_FLUX_UPWIND, false, 128, 3, false, PSK_EQ_ADVECTION, false>;
-  else if (equation == PSK_EQ_CONTINUITY) k = &psk::step_warp_fused_kernel<6, PSK_FLUX_UPWIND, false, 128, 3, false, PSK_EQ_CONTINUITY, false>;
+  if (equation == PSK_EQ_ADVECTION) k = &psk::step_warp_fused_kernel<6, PSK_FLUX_UPWIND, false, 128, 3, false, PSK_EQ_ADVECTION, 0>;
+  else if (equation == PSK_EQ_CONTINUITY) k = &psk::step_warp_fused_kernel<6, PSK_FLUX_UPWIND, false, 128, 3, false, PSK_EQ_CONTINUITY, 0>;
   else return -1;
   q.chunks_per_row = (n + psk::StepGeometry<6>::kEmit - 1) / psk::StepGeometry<6>::kEmit;
   int wpc = 4;

@@ -43,7 +43,7 @@ def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
     lib.emu_fused_step.restype = ct.c_int
     lib.emu_fused_step_stages.argtypes = [ct.c_int] * 3 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, dp, dp, ct.c_int]
     lib.emu_fused_step_stages.restype = ct.c_int
-    lib.emu_fused_step_bc.argtypes = [ct.c_int] * 6 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int, dp,
+    lib.emu_fused_step_bc.argtypes = [ct.c_int] * 7 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int, dp,
                                                       ct.c_longlong, dp, dp, dp, up]
     lib.emu_fused_step_bc.restype = ct.c_int
     lib.emu_fused_step_periodic_eq.argtypes = [ct.c_int] * 4 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
@@ -269,13 +269,16 @@ def test_fused_step_with_stored_stages(emu, n: int, with_uout: bool) -> None:
                                            ("advection", "godunov"), ("continuity", "godunov")])
 @pytest.mark.parametrize("n", [5, 16, 171, 172, 173, 250, 1000])
 @pytest.mark.parametrize("shared_ghosts", [False, True])
-def test_fused_step_with_dirichlet_data_is_the_three_stages(emu, equation: str, flux: str, n: int, shared_ghosts: bool) -> None:
-    """psk_ssprk33_step_bc's kernel: rows with Dirichlet data that change from stage to stage (the values of the
-    user's g(t, x) at t, t + dt, t + dt / 2), Burgers fluxes and the advection / continuity upwind flux: the bits
-    of three stage launches with those data, the C oracle to round-off, nothing written outside the interior"""
-    pb = Problem(equation, flux, "dirichlet", n=n, batch=3, seed=300 + n)
+@pytest.mark.parametrize("bc", ["dirichlet", "neumann"])
+def test_fused_step_with_boundary_data_is_the_three_stages(emu, equation: str, flux: str, n: int, shared_ghosts: bool,
+                                                           bc: str) -> None:
+    """psk_ssprk33_step_bc's kernel: rows with Dirichlet / Neumann data that change from stage to stage (the values of
+    the user's g(t, x) at t, t + dt, t + dt / 2; Neumann ghost cells also mirror the stage values next to the ends,
+    scalar.py:472-500), Burgers fluxes and the advection / continuity upwind flux: the bits of three stage launches
+    with those data, the C oracle to round-off, nothing written outside the interior"""
+    pb = Problem(equation, flux, bc, n=n, batch=3, seed=300 + n)
     rng = np.random.default_rng(n)
-    g3 = rng.uniform(-0.3, 0.3, size=(3, 1 if shared_ghosts else pb.batch, 2 * G))
+    g3 = rng.uniform(-0.3, 0.3, size=(3, 1 if shared_ghosts else pb.batch, 2 * G)) * (1.0 if bc == "dirichlet" else pb.dx)
     i = pb.interior
     cur = pb.u
     for s in (1, 2, 3):  # three stage launches, each with its own boundary data
@@ -287,7 +290,7 @@ def test_fused_step_with_dirichlet_data_is_the_three_stages(emu, equation: str, 
     maxabs = np.zeros(pb.batch, dtype=np.uint64)
     k = pb.co.keep
     g3c = np.ascontiguousarray(g3)
-    rc = emu.emu_fused_step_bc(EQUATION[equation], FLUX[flux], 1, n, G, pb.batch, pb.nx, pb.dx, EPS, _p(pb.fill(pb.u)),
+    rc = emu.emu_fused_step_bc(EQUATION[equation], FLUX[flux], 1, int(bc == "neumann"), n, G, pb.batch, pb.nx, pb.dx, EPS, _p(pb.fill(pb.u)),
                                _p(out), _p(pb.dt), 1, _p(g3c), 0 if shared_ghosts else 2 * G, _p(k.get("v")),
                                _p(k.get("vl")), _p(k.get("vr")), maxabs.ctypes.data_as(ct.POINTER(ct.c_ulonglong)))
     assert rc == 0

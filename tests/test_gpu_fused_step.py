@@ -130,13 +130,11 @@ def test_graph_replay_and_host_to_host_call(nsteps: int) -> None:
     assert torch.equal(c.u[:, G : G + n], ref)
 
 
-@pytest.mark.parametrize("kw", [dict(bc="neumann"), dict(flux="lf"), dict(math="strict"), dict(rec="wenojs32")])
+@pytest.mark.parametrize("kw", [dict(flux="lf"), dict(math="strict"), dict(rec="wenojs32")])
 def test_other_schemes_keep_the_stage_launches(kw: dict) -> None:
     batch, n = 2, 300
     u0 = _ic(batch, n, seed=2)
     s = _solver(batch, n, **kw)
-    if kw.get("bc") == "neumann":
-        s.hp.set_ghost(np.zeros(2 * G))
     s.solve_fixed_dt(u0, 1e-4, 2)
     assert s._fused is False and s.launches >= 6
     assert bool(torch.isfinite(s.u[:, G : G + n]).all())
@@ -145,23 +143,25 @@ def test_other_schemes_keep_the_stage_launches(kw: dict) -> None:
 @pytest.mark.parametrize("equation,flux", [("burgers", "rusanov"), ("burgers", "godunov"), ("burgers", "eo"),
                                            ("advection", "godunov"), ("continuity", "godunov")])
 @pytest.mark.parametrize("batch,n,nsteps,per_row", [(4, 4096, 5, True), (3, 333, 4, False), (2, 172, 3, True), (1, 16, 2, False)])
-def test_whole_step_on_dirichlet_rows(equation: str, flux: str, batch: int, n: int, nsteps: int, per_row: bool) -> None:
-    """psk_ssprk33_step_bc: Dirichlet rows (Burgers fluxes, advection, continuity) in one launch per step, the same
-    bits as three stage launches; EnsembleSolver picks it by itself (time-independent data of set_ghost)"""
+@pytest.mark.parametrize("bc", ["dirichlet", "neumann"])
+def test_whole_step_on_rows_with_boundary_data(equation: str, flux: str, batch: int, n: int, nsteps: int, per_row: bool,
+                                               bc: str) -> None:
+    """psk_ssprk33_step_bc: Dirichlet / Neumann rows (Burgers fluxes, advection, continuity) in one launch per step,
+    the same bits as three stage launches; EnsembleSolver picks it by itself (time-independent data of set_ghost)"""
     rng = np.random.default_rng(n)
     u0 = _ic(batch, n, seed=n + 1)
     kw = {}
     if equation != "burgers":
         x = (np.arange(n + 2 * G) - G + 0.5) / n
         kw["velocity"] = 1.0 + 0.4 * np.sin(2 * np.pi * x + 0.2)
-    ghost = rng.uniform(-0.3, 0.3, size=(batch, 2 * G) if per_row else (2 * G,))
+    ghost = rng.uniform(-0.3, 0.3, size=(batch, 2 * G) if per_row else (2 * G,)) * (1.0 if bc == "dirichlet" else 3.0 / n)
     dt = 0.3 * (3.0 / n) / max(float(u0.abs().max()), 1.5)
     with whole_step(7000):
-        a = _solver(batch, n, equation=equation, flux=flux, bc="dirichlet", **kw)
+        a = _solver(batch, n, equation=equation, flux=flux, bc=bc, **kw)
         a.hp.set_ghost(ghost)
         a.solve_fixed_dt(u0, dt, nsteps)
         assert a._fused is False and a.launches == 3 * nsteps
-    b = _solver(batch, n, equation=equation, flux=flux, bc="dirichlet", **kw)
+    b = _solver(batch, n, equation=equation, flux=flux, bc=bc, **kw)
     b.hp.set_ghost(ghost)
     b.solve_fixed_dt(u0, dt, nsteps)
     assert b._fused is True and b.launches == nsteps

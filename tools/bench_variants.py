@@ -24,7 +24,10 @@ CASES = [
     ("advection", "godunov", "dirichlet"), ("continuity", "godunov", "dirichlet"), ("advection", "godunov", "periodic"),
     ("continuity", "godunov", "periodic"),
 ]
+ONLY = sys.argv[1:]  # e.g. "neumann": the cases whose equation / flux / boundary kind is named
 for eq, flux, bc in CASES:
+    if ONLY and not any(o in (eq, flux, bc) for o in ONLY):
+        continue
     kw = {"velocity": vel} if eq != "burgers" else {}
     s = EnsembleSolver(equation=eq, flux=flux, rec="wenojs53", bc=bc, n=N, g=G, dx=h, eps=1e-12, batch=B, **kw)
     if bc in ("dirichlet", "neumann"):

@@ -567,10 +567,17 @@ struct StepGeometry {
   static constexpr int kEmit = kWindow - 2 * kSkip;  // stored cells per warp
 };
 
-// one stage on the lane's R cells: a (stage input, own cells) -> L = coef * dF per own cell
-template <int R, int FLUX, int EQ = PSK_EQ_BURGERS>
+// (no global wave speed: every flux but Lax-Friedrichs)
+struct NoSpeed {
+  __device__ __forceinline__ double operator()() const { return 0.0; }
+};
+
+// one stage on the lane's R cells: a (stage input, own cells) -> L = coef * dF per own cell.
+// Lax-Friedrichs: `speed2()` returns -2 max |w| of the row (scalar.py:277) and is called AFTER the reconstruction,
+// right before the fluxes -- the row-wide reduction it may have to wait for overlaps the bulk of the stage.
+template <int R, int FLUX, int EQ = PSK_EQ_BURGERS, class SpeedFn = NoSpeed>
 __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9, double (&dF)[R],
-                                               const StepVel<R> *vel = nullptr) {
+                                               const StepVel<R> *vel = nullptr, SpeedFn speed2 = SpeedFn()) {
   constexpr unsigned kFull = 0xffffffffu;
   double w0 = __shfl_up_sync(kFull, a[R - 1], 1);  // cell own - 1
   double t[R + 3];   // t[k]: interval (own - 2 + k, own - 1 + k); own: k = 1..R
@@ -604,6 +611,8 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
   }
   const double ur_left = __shfl_up_sync(kFull, ur[R - 1], 1);
   const double ul_right = __shfl_down_sync(kFull, ul[0], 1);
+  double lf2 = 0.0;
+  if (EQ == PSK_EQ_BURGERS && FLUX == PSK_FLUX_LAX_FRIEDRICHS) lf2 = speed2();
   double F[R + 1];
 #pragma unroll
   for (int f = 0; f <= R; ++f) {
@@ -614,6 +623,8 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
       F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? __dmul_rn(vel->ar[f], urj) : __dmul_rn(vel->al[f], ulp));
     } else if (FLUX == PSK_FLUX_RUSANOV) {  // 4 F (scalar.py:231-249)
       F[f] = fma(umax_neg(m2[f], m2[f + 1]), ulp - urj, fma(urj, urj, ulp * ulp));
+    } else if (FLUX == PSK_FLUX_LAX_FRIEDRICHS) {  // 4 F (scalar.py:258-278), as in the stage kernels
+      F[f] = fma(lf2, ulp - urj, fma(urj, urj, ulp * ulp));
     } else if (FLUX == PSK_FLUX_UPWIND) {  // 2 F (scalar.py:123-132)
       const double x = (urj + ulp) > 0.0 ? urj : ulp;
       F[f] = __dmul_rn(x, x);  // never contracted with the flux difference (same bits in every kernel)

@@ -1064,6 +1064,252 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
 }
 
 // ---------------------------------------------------------------------------
+// The whole SSPRK33 step with the GLOBAL Lax-Friedrichs flux (scalar.py:258-278) in one launch.  Every stage needs
+// max |w| over the whole row of its input (scalar.py:277) -- a row-wide reduction between the stages, which is what
+// keeps this flux out of step_warp_fused_kernel.  Here one thread-block CLUSTER owns a row (up to 8 CTAs of up to 12
+// warps, one window per warp as in step_warp_fused_kernel) and the partial maxima travel through distributed shared
+// memory:
+//   * every warp reduces the stage input over its STORED cells (they partition the row) and sends the maximum to its
+//     own slot in the shared memory of EVERY CTA of the cluster: st.async, whose bytes complete a transaction
+//     mbarrier of the receiving CTA (one per stage, expecting 8 bytes from every window of the row);
+//   * it then reconstructs the stage input -- most of the stage, none of which needs the speed -- and only waits on
+//     its CTA's mbarrier right before the fluxes (LfSpeed below), where it reduces the row's slots.
+// No cluster barrier and no memory fence between the stages (barrier.cluster.arrive.release costs a MEMBAR.GPU and
+// an L1 invalidation each: measured 4.3-5.3e10 cell-updates/s with them, against 6.2e10 for four launches per step).
+// One cluster barrier at the start publishes the mbarrier initialisation.  A CTA cannot exit before it has received
+// everything addressed to it: its warps wait on all three mbarriers.
+// Arithmetic: step_stage_rhs with the speed of the stage kernels, i.e. the bits of three psk_ssprk33_stage launches.
+constexpr int kLfMaxWindows = 96;  // 8 CTAs x 12 warps
+
+struct LfExchange {
+  unsigned long long vals[3][kLfMaxWindows];  // bit patterns of the windows' max |stage input|
+  unsigned long long mbar[3];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *ptr) { return static_cast<unsigned>(__cvta_generic_to_shared(ptr)); }
+__device__ __forceinline__ unsigned cluster_size_x() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%cluster_nctaid.x;" : "=r"(v));
+  return v;
+}
+// the address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ unsigned cluster_map(unsigned local, unsigned rank) {
+  unsigned remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+
+// max over the warp of 64-bit patterns in two 32-bit hardware reductions (redux.sync): the high words first, then
+// the low words of the lanes that hold the largest high word -- 6 instructions instead of 5 shuffle rounds on pairs
+__device__ __forceinline__ unsigned long long warp_max_bits_redux(unsigned long long v) {
+  const unsigned hi = static_cast<unsigned>(v >> 32), lo = static_cast<unsigned>(v);
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  return (static_cast<unsigned long long>(mhi) << 32) | mlo;
+}
+
+struct LfSpeed {
+  const LfExchange *x;
+  int stage, windows, lane;
+  // -2 max |w| of the row, once the maxima of all its windows have arrived in this CTA
+  __device__ __forceinline__ double operator()() const {
+    mbar_wait(smem_u32(&x->mbar[stage]), 0u);
+    unsigned long long mx = 0ull;
+#pragma unroll
+    for (int k = 0; k < kLfMaxWindows / 32; ++k) {
+      const int i = lane + 32 * k;
+      const unsigned long long b = i < windows ? x->vals[stage][i] : 0ull;
+      mx = b > mx ? b : mx;
+    }
+    return -2.0 * __longlong_as_double(static_cast<long long>(warp_max_bits_redux(mx)));
+  }
+};
+
+template <int R>
+__device__ __forceinline__ void lf_send_stage_max(const StepParams &p, LfExchange *x, int lane, int row, int chunk, int stage,
+                                                  bool dirichlet, const bool (&st)[R], const double (&v)[R]) {
+  unsigned long long mx = 0ull;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if (st[r]) {
+      const unsigned long long b = abs_bits(v[r]);
+      mx = b > mx ? b : mx;
+    }
+  if (dirichlet && chunk == 0) {  // w = apply_boundary(u): the ghost cells hold the data of this stage
+    const double *gh = p.ghost3 + static_cast<int64_t>(stage) * p.ghost_block + static_cast<int64_t>(row) * p.ghost_ld;
+    if (lane < 2 * p.g) {  // (2 g <= 32: checked by the launcher)
+      const unsigned long long b = abs_bits(gh[lane]);
+      mx = b > mx ? b : mx;
+    }
+  }
+  mx = warp_max_bits_redux(mx);
+  if (static_cast<unsigned>(lane) < cluster_size_x()) {  // lane r: to CTA r of the cluster
+    const unsigned dst = cluster_map(smem_u32(&x->vals[stage][chunk]), static_cast<unsigned>(lane));
+    const unsigned bar = cluster_map(smem_u32(&x->mbar[stage]), static_cast<unsigned>(lane));
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst), "l"(mx), "r"(bar)
+                 : "memory");
+  }
+}
+
+template <int R, bool WITH_MAX, int BCK, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+step_lf_cluster_kernel(const StepParams p) {
+  using Geo = StepGeometry<R>;
+  constexpr int kLF = PSK_FLUX_LAX_FRIEDRICHS, kB = PSK_EQ_BURGERS;
+  constexpr bool DIRICHLET = BCK == 1;
+  __shared__ LfExchange xch;
+  const int lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const bool live = chunk < p.chunks_per_row;
+  const int row = blockIdx.y + blockIdx.z * gridDim.y;
+  const int n = p.n;
+  const int c0 = chunk * Geo::kEmit - Geo::kSkip + R * lane;
+  const bool inside = (c0 >= 0) && (c0 + R <= n);
+  const int64_t base = static_cast<int64_t>(row) * p.ld + p.g;
+  const int wc0 = R * lane;
+  bool st[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    st[r] = live && (wc0 + r >= Geo::kSkip) && (wc0 + r < Geo::kWindow - Geo::kSkip) && (c0 + r >= 0) && (c0 + r < n);
+
+  const bool skip = p.active != nullptr && p.active[row] == 0;  // finished row (the whole cluster agrees)
+  if (threadIdx.x == 0 && !skip) {  // one transaction barrier per stage: 8 bytes from every window of the row
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const unsigned bar = smem_u32(&xch.mbar[s]);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8u * static_cast<unsigned>(p.chunks_per_row))
+                   : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+
+  double u0[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) u0[r] = 0.0;
+  if (live) {
+    if (inside) {
+#pragma unroll
+      for (int r = 0; r < R; r += 2) {
+        const double2 q = *reinterpret_cast<const double2 *>(p.u + base + c0 + r);
+        u0[r] = q.x;
+        u0[r + 1] = q.y;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        int c = c0 + r;
+        if (DIRICHLET) {
+          u0[r] = (c >= 0 && c < n) ? p.u[base + c] : 0.0;
+        } else {
+          c %= n;
+          if (c < 0) c += n;
+          u0[r] = p.u[base + c];
+        }
+      }
+    }
+  }
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");  // every CTA's mbarriers are ready
+  if (skip) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r]) p.uout[base + c0 + r] = u0[r];
+    return;
+  }
+  if (!live) return;  // a warp beyond the last window of the row: sends nothing, nobody waits for it
+  const double cdt = p.coef * p.dt[static_cast<int64_t>(row) * p.dt_stride];
+  const bool fill = DIRICHLET && !inside;
+  if (fill) step_fill_ghosts<R>(p, row, 0, c0, u0);
+  const int windows = p.chunks_per_row;
+
+  double a[R], dF[R];
+  lf_send_stage_max<R>(p, &xch, lane, row, chunk, 0, DIRICHLET, st, u0);
+  step_stage_rhs<R, kLF, kB, LfSpeed>(u0, p.eps9, dF, nullptr, LfSpeed{&xch, 0, windows, lane});
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);  // k1
+  if (fill) step_fill_ghosts<R>(p, row, 1, c0, a);
+  lf_send_stage_max<R>(p, &xch, lane, row, chunk, 1, DIRICHLET, st, a);
+  step_stage_rhs<R, kLF, kB, LfSpeed>(a, p.eps9, dF, nullptr, LfSpeed{&xch, 1, windows, lane});
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);  // k2
+  if (fill) step_fill_ghosts<R>(p, row, 2, c0, a);
+  lf_send_stage_max<R>(p, &xch, lane, row, chunk, 2, DIRICHLET, st, a);
+  step_stage_rhs<R, kLF, kB, LfSpeed>(a, p.eps9, dF, nullptr, LfSpeed{&xch, 2, windows, lane});
+#pragma unroll
+  for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);  // u'
+
+  if (inside) {
+#pragma unroll
+    for (int r = 0; r < R; r += 2)
+      if (st[r]) *reinterpret_cast<double2 *>(p.uout + base + c0 + r) = make_double2(a[r], a[r + 1]);
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r]) p.uout[base + c0 + r] = a[r];
+  }
+  if (WITH_MAX) {
+    unsigned long long mx = 0ull;
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      if (st[r]) {
+        const unsigned long long b = abs_bits(a[r]);
+        mx = b > mx ? b : mx;
+      }
+    mx = warp_max_bits(mx);
+    if (lane == 0) atomicMax(p.maxabs + row, mx);
+  }
+}
+
+// cluster shape of a row: CTAs of g_lf_wpc windows (warps) each -- small CTAs, several rows resident per SM, so that
+// the rows' load / compute / barrier phases overlap --, more windows per CTA only where a row would need more than
+// the 8 CTAs of a portable cluster
+static int g_lf_wpc = 4;
+
+template <bool WITH_MAX, int BCK>
+int launch_step_lf(const StepParams &q0, int n, int batch, cudaStream_t st) {
+  constexpr int R = 6, kMaxWarps = 12;
+  StepParams q = q0;
+  q.chunks_per_row = (n + StepGeometry<R>::kEmit - 1) / StepGeometry<R>::kEmit;
+  int wpc = g_lf_wpc;
+  if (wpc * 8 < q.chunks_per_row) wpc = (q.chunks_per_row + 7) / 8;
+  if (wpc > kMaxWarps || q.g > 16) return PSK_E_UNSUPPORTED;  // rows beyond 8 x 12 x 172 = 16512 cells
+  if (wpc > q.chunks_per_row) wpc = q.chunks_per_row;
+  const int cx = (q.chunks_per_row + wpc - 1) / wpc;
+  unsigned gy, gz;
+  if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(cx), gy, gz);
+  cfg.blockDim = dim3(static_cast<unsigned>(wpc * 32));
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cx);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // (CTAs of up to 4 windows: 16 warps per SM within 128 registers; longer rows: one large CTA per SM)
+  if (wpc <= 4)
+    PSK_CUDA_OK(cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 128, 4>, q));
+  else
+    PSK_CUDA_OK(cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 384, 1>, q));
+  return PSK_OK;
+}
+
+// ---------------------------------------------------------------------------
 // The whole-step kernel FUSED with the ghost-cell exchange of a slab-decomposed grid (one row per
 // GPU, boundary kind NONE, 9 ghost cells per side: the three stages of a step reach 9 cells beyond
 // the slab): ONE launch per step and nothing else on the exchange path.
@@ -1197,7 +1443,8 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
   q.k1_out = k1_out; q.k2_out = k2_out;
   q.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
   q.ld = d->ld;
-  q.coef = (1.0 / d->dx) / (d->equation != PSK_EQ_BURGERS ? 1.0 : (d->flux == PSK_FLUX_RUSANOV ? 4.0 : 2.0));  // FluxScale
+  q.coef = (1.0 / d->dx) / (d->equation != PSK_EQ_BURGERS ? 1.0
+                           : ((d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_LAX_FRIEDRICHS) ? 4.0 : 2.0));  // FluxScale
   q.eps9 = d->eps * (1.0 / 9.0);
   q.dt_stride = static_cast<int>(dt_stride);
   q.n = d->n;
@@ -1223,6 +1470,11 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
       if (rc != PSK_OK) return rc;
     }
     return PSK_OK;
+  }
+  if (d->flux == PSK_FLUX_LAX_FRIEDRICHS) {  // one cluster per row (the entry points admit periodic / Dirichlet rows)
+    if (d->bc == PSK_BC_DIRICHLET)
+      return mx ? launch_step_lf<true, 1>(q, d->n, batch, st) : launch_step_lf<false, 1>(q, d->n, batch, st);
+    return mx ? launch_step_lf<true, 0>(q, d->n, batch, st) : launch_step_lf<false, 0>(q, d->n, batch, st);
   }
   if (d->bc == PSK_BC_DIRICHLET || d->bc == PSK_BC_NEUMANN) {  // rows with boundary data: default shape only
     constexpr int kB = PSK_EQ_BURGERS, kUp = PSK_FLUX_UPWIND, kEO = PSK_FLUX_ENGQUIST_OSHER, kRus = PSK_FLUX_RUSANOV;
@@ -1279,6 +1531,11 @@ int psk_version(void) { return PSK_VERSION; }
 /* tuning / A-B switch, not part of the reference-facing surface: 0 = warp-shuffle stage
  * kernel (default), 1 = shared-memory tile kernel */
 int psk_set_stage_variant(int variant) {
+  if (variant >= 8000) {  // 8000 + windows per CTA of the Lax-Friedrichs cluster kernel (1..12)
+    if (variant - 8000 < 1 || variant - 8000 > 12) return PSK_E_INVALID;
+    g_lf_wpc = variant - 8000;
+    return PSK_OK;
+  }
   if (variant >= 7000) {  // whole-step kernel (psk_ssprk33_step): 7062 (default) / 7060 / 7082 = cells per lane and CTA shape, 7000 = off
     const int v = variant - 7000;
     if (v != 0 && v != 60 && v != 62 && v != 82) return PSK_E_INVALID;
@@ -1479,7 +1736,9 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
   if (u == nullptr || uout == nullptr || dt == nullptr || uout == u) return PSK_E_INVALID;
   const bool aligned = (reinterpret_cast<uintptr_t>(u + d->g) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(uout + d->g) % 16 == 0) && (d->ld % 2 == 0);
-  const bool flux_ok = d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER;
+  // (global Lax-Friedrichs: the row-wide maximum of every stage lives in one thread-block cluster -- whole rows only)
+  const bool flux_ok = d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER ||
+                       (d->flux == PSK_FLUX_LAX_FRIEDRICHS && d->bc == PSK_BC_PERIODIC);
   // advection / continuity: periodic rows only (on slabs the velocity would need ghost cells of its own)
   const bool eq_ok = d->equation == PSK_EQ_BURGERS ? (flux_ok && d->nu == nullptr)
                                                    : (d->flux == PSK_FLUX_UPWIND && d->bc == PSK_BC_PERIODIC);
@@ -1504,7 +1763,8 @@ int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const 
   auto al = [&](const double *a) { return a == nullptr || reinterpret_cast<uintptr_t>(a + d->g) % 16 == 0; };
   const bool aligned = al(u) && al(uout) && al(k1_out) && al(k2_out) && (d->ld % 2 == 0);
   const bool burgers_ok = d->equation == PSK_EQ_BURGERS && d->nu == nullptr &&
-                          (d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER);
+                          (d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER ||
+                           (d->flux == PSK_FLUX_LAX_FRIEDRICHS && d->bc == PSK_BC_DIRICHLET && k1_out == nullptr));
   const bool linear_ok = d->equation != PSK_EQ_BURGERS && d->flux == PSK_FLUX_UPWIND;
   if (!(burgers_ok || linear_ok) || d->rec != PSK_REC_WENOJS53 || d->math != PSK_MATH_FAST || !aligned ||
       g_step_variant == 0 || (d->bc != PSK_BC_DIRICHLET && d->bc != PSK_BC_NEUMANN) || d->g < 3 || d->n < d->g)

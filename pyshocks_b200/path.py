@@ -573,7 +573,8 @@ class HotPath:
         nothing farther than ``3 (g + 3)`` cells away), whose ghost cells are copied over.  Falls back to the three
         full stage launches wherever the whole-step kernel does not exist."""
         W, g, nx = self._ENDS_W, self.g, self.nx
-        if self.math != "fast" or self.n < 4 * W:
+        # (global Lax-Friedrichs: the speed is a maximum over the whole row, the row ends alone do not know it)
+        if self.math != "fast" or self.n < 4 * W or self.flux == "lf":
             return self.ssprk33_step(u, dt, ghosts=ghosts, ghost_rows=True)
         # the whole-step kernel wants 16-byte aligned interiors: a plain (batch, nx) array of the caller is copied
         # once into the padded row layout; the result is returned as a view of that layout, so the next advance of

@@ -130,11 +130,13 @@ def test_graph_replay_and_host_to_host_call(nsteps: int) -> None:
     assert torch.equal(c.u[:, G : G + n], ref)
 
 
-@pytest.mark.parametrize("kw", [dict(flux="lf"), dict(math="strict"), dict(rec="wenojs32")])
+@pytest.mark.parametrize("kw", [dict(math="strict"), dict(rec="wenojs32"), dict(flux="lf", bc="neumann")])
 def test_other_schemes_keep_the_stage_launches(kw: dict) -> None:
     batch, n = 2, 300
     u0 = _ic(batch, n, seed=2)
     s = _solver(batch, n, **kw)
+    if kw.get("bc") == "neumann":
+        s.hp.set_ghost(np.zeros(2 * G))
     s.solve_fixed_dt(u0, 1e-4, 2)
     assert s._fused is False and s.launches >= 6
     assert bool(torch.isfinite(s.u[:, G : G + n]).all())
@@ -193,20 +195,75 @@ def test_lax_friedrichs_without_the_reduction_pass() -> None:
     batch, n, nsteps = 4, 2048, 6
     u0 = _ic(batch, n, seed=11)
     dt = 0.3 * (3.0 / n) / float(u0.abs().max())
-    a = _solver(batch, n, flux="lf")
-    a._lf_chain = False
-    a.solve_fixed_dt(u0, dt, nsteps)
-    assert a.launches == 6 * nsteps
-    b = _solver(batch, n, flux="lf")
+    with whole_step(7000):  # (the stage launches: the whole-step cluster kernel is tested below)
+        a = _solver(batch, n, flux="lf")
+        a._lf_chain = False
+        a.solve_fixed_dt(u0, dt, nsteps)
+        assert a.launches == 6 * nsteps
+        b = _solver(batch, n, flux="lf")
+        b.solve_fixed_dt(u0, dt, nsteps)
+        assert b._lf_chain and b.launches == 4 * nsteps + 1
+        assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
+        b.solve_fixed_dt(u0, dt, 2)       # reload: the chain starts again from a reduction of the new state
+        b.solve_fixed_dt(None, dt, nsteps - 2)
+        assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
+        c = _solver(batch, n, flux="lf")
+        c.solve_fixed_dt(u0, dt, nsteps, graph=True)
+        assert torch.equal(a.u[:, G : G + n], c.u[:, G : G + n])
+
+
+@pytest.mark.parametrize("bc", ["periodic", "dirichlet"])
+@pytest.mark.parametrize("batch,n,nsteps", [(4, 4096, 5), (3, 2048, 4), (2, 5000, 3), (2, 10000, 3), (3, 16512, 2), (5, 300, 4),
+                                            (2, 172, 3), (1, 16, 2)])
+def test_whole_step_with_the_global_lax_friedrichs_flux(bc: str, batch: int, n: int, nsteps: int) -> None:
+    """step_lf_cluster_kernel: one thread-block cluster per row, the row-wide max |w| of every stage input
+    (scalar.py:277) exchanged through distributed shared memory behind a split cluster barrier -- one launch per
+    step, the bits of the path with one reduction pass + one stage launch per stage (6 launches); rows of 1, 2, 4
+    and 8 CTAs, with and without idle warps; Dirichlet rows take the ghost data of each stage into the maximum"""
+    u0 = _ic(batch, n, seed=n + 3)
+    dt = 0.3 * (3.0 / n) / max(float(u0.abs().max()), 1.0)
+    rng = np.random.default_rng(n)
+    # (Dirichlet data larger than the state: the speed then comes from the ghost cells)
+    ghost = rng.uniform(-3.0, 3.0, size=(batch, 2 * G)) if bc == "dirichlet" else None
+    with whole_step(7000):
+        a = _solver(batch, n, flux="lf", bc=bc)
+        a._lf_chain = False
+        if ghost is not None:
+            a.hp.set_ghost(ghost)
+        a.solve_fixed_dt(u0, dt, nsteps)
+        assert a._fused is False and a.launches == 6 * nsteps
+    b = _solver(batch, n, flux="lf", bc=bc)
+    if ghost is not None:
+        b.hp.set_ghost(ghost)
     b.solve_fixed_dt(u0, dt, nsteps)
-    assert b._lf_chain and b.launches == 4 * nsteps + 1
+    assert b._fused is True and b.launches == nsteps
     assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
-    b.solve_fixed_dt(u0, dt, 2)       # reload: the chain starts again from a reduction of the new state
-    b.solve_fixed_dt(None, dt, nsteps - 2)
-    assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
-    c = _solver(batch, n, flux="lf")
+    c = _solver(batch, n, flux="lf", bc=bc)
+    if ghost is not None:
+        c.hp.set_ghost(ghost)
     c.solve_fixed_dt(u0, dt, nsteps, graph=True)
     assert torch.equal(a.u[:, G : G + n], c.u[:, G : G + n])
+
+
+def test_lax_friedrichs_whole_step_adaptive_rows_and_long_rows() -> None:
+    """rows that finish early are carried over by the whole cluster; the fused maximum of the new state feeds the
+    next time step; rows beyond 8 x 12 windows fall back to the stage launches"""
+    batch, n = 6, 1000
+    u0 = _ic(batch, n, seed=21)
+    kw = dict(theta=0.8, tfinal=0.02, cfl_scale=0.5 * (3.0 / n), check_every=4, record_dt=True)
+    with whole_step(7000):
+        a = _solver(batch, n, flux="lf")
+        ra = a.solve_adaptive(u0, **kw)
+    b = _solver(batch, n, flux="lf")
+    rb = b.solve_adaptive(u0, **kw)
+    assert b._fused is True
+    assert ra.steps == rb.steps and np.array_equal(ra.steps_per_row, rb.steps_per_row)
+    assert np.array_equal(ra.dt_history, rb.dt_history) and torch.equal(ra.t, rb.t)
+    assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
+    n = 16513
+    c = _solver(1, n, flux="lf")
+    c.solve_fixed_dt(_ic(1, n, seed=1), 1e-6, 1)
+    assert c._fused is False
 
 
 def test_lax_friedrichs_row_blocks_on_several_streams() -> None:

@@ -2,6 +2,7 @@
 20 steps after 3 warm-up steps): which of them run the whole SSPRK33 step in one launch, which take three (or six)
 stage launches.  One JSON line per scheme (-> profiles/)."""
 import json
+import os
 import sys
 
 import numpy as np
@@ -24,6 +25,9 @@ CASES = [
     ("advection", "godunov", "dirichlet"), ("continuity", "godunov", "dirichlet"), ("advection", "godunov", "periodic"),
     ("continuity", "godunov", "periodic"),
 ]
+if os.environ.get("PSK_LF_WPC"):  # windows per CTA of the Lax-Friedrichs cluster kernel (tuning switch)
+    from pyshocks_b200 import _lib
+    assert _lib.lib().psk_set_stage_variant(8000 + int(os.environ["PSK_LF_WPC"])) == 0
 ONLY = sys.argv[1:]  # e.g. "neumann": the cases whose equation / flux / boundary kind is named
 for eq, flux, bc in CASES:
     if ONLY and not any(o in (eq, flux, bc) for o in ONLY):

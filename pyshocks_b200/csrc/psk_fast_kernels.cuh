@@ -458,6 +458,10 @@ struct StepParams {
   int64_t ghost_ld, ghost_block;
   // advection / continuity: velocity and its reconstruction (time independent), nx entries each
   const double *vel, *vel_l, *vel_r;
+  // Rusanov / Lax-Friedrichs with alpha != 1: the artificial viscosity nu = df ** (alpha - 1) of every face (j | j + 1)
+  // of the ARRAY (scalar.py:231-234), nx - 1 entries; NU kernels only (rows with boundary data: on periodic rows the
+  // face at the seam would need two values)
+  const double *nu;
 };
 
 // what the upwind switch of the advection / continuity flux needs at the R + 1 faces of a lane's cells
@@ -560,6 +564,17 @@ __device__ __forceinline__ void step_fill_neumann(const StepParams &p, int row, 
   }
 }
 
+// nu of the R + 1 faces of a lane's cells: face f lies between the cells c0 + f - 1 and c0 + f, i.e. it is face
+// g + c0 + f - 1 of the array; 1 beyond the array (never reaches a stored cell)
+template <int R>
+__device__ __forceinline__ void step_load_nu(const StepParams &p, int c0, double (&nuf)[R + 1]) {
+#pragma unroll
+  for (int f = 0; f <= R; ++f) {
+    const int j = p.g + c0 + f - 1;
+    nuf[f] = (j >= 0 && j < p.n + 2 * p.g - 1) ? p.nu[j] : 1.0;
+  }
+}
+
 template <int R>
 struct StepGeometry {
   static constexpr int kWindow = 32 * R;
@@ -575,9 +590,11 @@ struct NoSpeed {
 // one stage on the lane's R cells: a (stage input, own cells) -> L = coef * dF per own cell.
 // Lax-Friedrichs: `speed2()` returns -2 max |w| of the row (scalar.py:277) and is called AFTER the reconstruction,
 // right before the fluxes -- the row-wide reduction it may have to wait for overlaps the bulk of the stage.
-template <int R, int FLUX, int EQ = PSK_EQ_BURGERS, class SpeedFn = NoSpeed>
+// NU: nuf[f] = nu of the face between the cells own + f - 1 and own + f multiplies the speed (scalar.py:231-249).
+template <int R, int FLUX, int EQ = PSK_EQ_BURGERS, class SpeedFn = NoSpeed, bool NU = false>
 __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9, double (&dF)[R],
-                                               const StepVel<R> *vel = nullptr, SpeedFn speed2 = SpeedFn()) {
+                                               const StepVel<R> *vel = nullptr, SpeedFn speed2 = SpeedFn(),
+                                               const double *nuf = nullptr) {
   constexpr unsigned kFull = 0xffffffffu;
   double w0 = __shfl_up_sync(kFull, a[R - 1], 1);  // cell own - 1
   double t[R + 3];   // t[k]: interval (own - 2 + k, own - 1 + k); own: k = 1..R
@@ -622,9 +639,12 @@ __device__ __forceinline__ void step_stage_rhs(const double (&a)[R], double eps9
       const bool pos = (vel->pos >> f) & 1u;
       F[f] = (EQ == PSK_EQ_ADVECTION) ? (pos ? urj : ulp) : (pos ? __dmul_rn(vel->ar[f], urj) : __dmul_rn(vel->al[f], ulp));
     } else if (FLUX == PSK_FLUX_RUSANOV) {  // 4 F (scalar.py:231-249)
-      F[f] = fma(umax_neg(m2[f], m2[f + 1]), ulp - urj, fma(urj, urj, ulp * ulp));
+      double a2 = umax_neg(m2[f], m2[f + 1]);
+      if (NU) a2 = __dmul_rn(nuf[f], a2);  // -2 (nu a): the bits of `a *= nu` in the stage kernels
+      F[f] = fma(a2, ulp - urj, fma(urj, urj, ulp * ulp));
     } else if (FLUX == PSK_FLUX_LAX_FRIEDRICHS) {  // 4 F (scalar.py:258-278), as in the stage kernels
-      F[f] = fma(lf2, ulp - urj, fma(urj, urj, ulp * ulp));
+      const double a2 = NU ? __dmul_rn(nuf[f], lf2) : lf2;
+      F[f] = fma(a2, ulp - urj, fma(urj, urj, ulp * ulp));
     } else if (FLUX == PSK_FLUX_UPWIND) {  // 2 F (scalar.py:123-132)
       const double x = (urj + ulp) > 0.0 ? urj : ulp;
       F[f] = __dmul_rn(x, x);  // never contracted with the flux difference (same bits in every kernel)
@@ -663,7 +683,7 @@ __device__ __forceinline__ void step_store(double *dst, bool inside, const bool 
 // cells take the data of each stage time (Neumann: plus the stage value of their mirror image) before that stage,
 // exactly where apply_boundary writes them (scalar.py:418-427, 472-500).
 template <int R, int FLUX, bool WITH_MAX, int THREADS, int MINB, bool STAGES = false, int EQ = PSK_EQ_BURGERS,
-          int BCK = 0>
+          int BCK = 0, bool NU = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 step_warp_fused_kernel(const StepParams p) {
   using Geo = StepGeometry<R>;
@@ -724,10 +744,12 @@ step_warp_fused_kernel(const StepParams p) {
   const double cdt = p.coef * p.dt[static_cast<int64_t>(row) * p.dt_stride];
   StepVel<R> vel;
   if (EQ != PSK_EQ_BURGERS) step_load_vel<R, EQ>(p, c0, BCK == 0 && !p.bc_none, vel);
+  double nuf[R + 1];
+  if constexpr (NU) step_load_nu<R>(p, c0, nuf);
   if (DIRICHLET && !inside) step_fill_ghosts<R>(p, row, 0, c0, u0);
 
   double a[R], dF[R];
-  step_stage_rhs<R, FLUX, EQ>(u0, p.eps9, dF, &vel);
+  step_stage_rhs<R, FLUX, EQ, NoSpeed, NU>(u0, p.eps9, dF, &vel, NoSpeed(), nuf);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);  // k1
   if (STAGES) step_store<R>(p.k1_out + base + c0, inside, st, a);
@@ -735,7 +757,7 @@ step_warp_fused_kernel(const StepParams p) {
   if constexpr (NEUMANN) {
     if (edge) step_fill_neumann<R>(p, row, 1, c0, wstart < 0, wstart + Geo::kWindow > n, a);
   }
-  step_stage_rhs<R, FLUX, EQ>(a, p.eps9, dF, &vel);
+  step_stage_rhs<R, FLUX, EQ, NoSpeed, NU>(a, p.eps9, dF, &vel, NoSpeed(), nuf);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);  // k2
   if (STAGES) {
@@ -746,7 +768,7 @@ step_warp_fused_kernel(const StepParams p) {
   if constexpr (NEUMANN) {
     if (edge) step_fill_neumann<R>(p, row, 2, c0, wstart < 0, wstart + Geo::kWindow > n, a);
   }
-  step_stage_rhs<R, FLUX, EQ>(a, p.eps9, dF, &vel);
+  step_stage_rhs<R, FLUX, EQ, NoSpeed, NU>(a, p.eps9, dF, &vel, NoSpeed(), nuf);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);  // u'
 

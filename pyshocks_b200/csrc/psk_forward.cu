@@ -1043,7 +1043,7 @@ __global__ void step_control_kernel(int batch, double theta, double cfl_scale, d
 // 7000 = off (three stage launches)
 static int g_step_variant = 62;  // R = 6, CTAs of 128 threads, 3 per SM (136 registers): 9.0e10 cell-updates/s on B200
 
-template <int R, int FLUX, int THREADS, int MINB, bool STAGES = false, int EQ = PSK_EQ_BURGERS, int BCK = 0>
+template <int R, int FLUX, int THREADS, int MINB, bool STAGES = false, int EQ = PSK_EQ_BURGERS, int BCK = 0, bool NU = false>
 int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cudaStream_t st) {
   StepParams q = q0;
   q.chunks_per_row = (n + StepGeometry<R>::kEmit - 1) / StepGeometry<R>::kEmit;
@@ -1054,11 +1054,11 @@ int launch_step_shape(const StepParams &q0, int n, int batch, bool with_max, cud
   if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;
   const dim3 grid(gx, gy, gz);
   if (STAGES)
-    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, STAGES, EQ, BCK><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, STAGES, EQ, BCK, NU><<<grid, wpc * 32, 0, st>>>(q);
   else if (with_max)
-    step_warp_fused_kernel<R, FLUX, true, THREADS, MINB, false, EQ, BCK><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, true, THREADS, MINB, false, EQ, BCK, NU><<<grid, wpc * 32, 0, st>>>(q);
   else
-    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, false, EQ, BCK><<<grid, wpc * 32, 0, st>>>(q);
+    step_warp_fused_kernel<R, FLUX, false, THREADS, MINB, false, EQ, BCK, NU><<<grid, wpc * 32, 0, st>>>(q);
   PSK_CUDA_OK(cudaGetLastError());
   return PSK_OK;
 }
@@ -1136,23 +1136,18 @@ struct LfSpeed {
   }
 };
 
+// `extra`: what else enters the maximum (Dirichlet rows, first window: |boundary data| of this stage, loaded at the
+// start of the kernel -- a load here would sit on the critical path of every warp of the row)
 template <int R>
-__device__ __forceinline__ void lf_send_stage_max(const StepParams &p, LfExchange *x, int lane, int row, int chunk, int stage,
-                                                  bool dirichlet, const bool (&st)[R], const double (&v)[R]) {
-  unsigned long long mx = 0ull;
+__device__ __forceinline__ void lf_send_stage_max(LfExchange *x, int lane, int chunk, int stage, unsigned long long extra,
+                                                  const bool (&st)[R], const double (&v)[R]) {
+  unsigned long long mx = extra;
 #pragma unroll
   for (int r = 0; r < R; ++r)
     if (st[r]) {
       const unsigned long long b = abs_bits(v[r]);
       mx = b > mx ? b : mx;
     }
-  if (dirichlet && chunk == 0) {  // w = apply_boundary(u): the ghost cells hold the data of this stage
-    const double *gh = p.ghost3 + static_cast<int64_t>(stage) * p.ghost_block + static_cast<int64_t>(row) * p.ghost_ld;
-    if (lane < 2 * p.g) {  // (2 g <= 32: checked by the launcher)
-      const unsigned long long b = abs_bits(gh[lane]);
-      mx = b > mx ? b : mx;
-    }
-  }
   mx = warp_max_bits_redux(mx);
   if (static_cast<unsigned>(lane) < cluster_size_x()) {  // lane r: to CTA r of the cluster
     const unsigned dst = cluster_map(smem_u32(&x->vals[stage][chunk]), static_cast<unsigned>(lane));
@@ -1162,7 +1157,18 @@ __device__ __forceinline__ void lf_send_stage_max(const StepParams &p, LfExchang
   }
 }
 
-template <int R, bool WITH_MAX, int BCK, int THREADS, int MINB>
+// step_fill_ghosts from the warp's copy of the row's 2 g <= 32 boundary data of one stage
+template <int R>
+__device__ __forceinline__ void lf_fill_ghosts(const StepParams &p, const double (&gh)[32], int c0, double (&a)[R]) {
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int c = c0 + r;
+    if (c < 0) a[r] = (c >= -p.g) ? gh[c + p.g] : 0.0;
+    if (c >= p.n) a[r] = (c < p.n + p.g) ? gh[p.g + c - p.n] : 0.0;
+  }
+}
+
+template <int R, bool WITH_MAX, int BCK, int THREADS, int MINB, bool NU>
 __global__ void __launch_bounds__(THREADS, MINB)
 step_lf_cluster_kernel(const StepParams p) {
   using Geo = StepGeometry<R>;
@@ -1196,6 +1202,22 @@ step_lf_cluster_kernel(const StepParams p) {
   }
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
+  // Dirichlet rows: w = apply_boundary(u) holds the boundary data of the stage in its ghost cells (scalar.py:277)
+  // Every warp whose window reaches beyond the row keeps the data of the three stage times in shared memory: the
+  // fills in front of stages 2 and 3 must not wait for global loads -- the WHOLE row waits for its slowest warp.
+  __shared__ double gdata[DIRICHLET ? 12 : 1][3][32];
+  double(&gmine)[3][32] = gdata[DIRICHLET ? (threadIdx.x >> 5) : 0];
+  unsigned long long gbits[3] = {0ull, 0ull, 0ull};
+  const bool edge = live && ((chunk == 0) || ((chunk + 1) * Geo::kEmit + Geo::kSkip > n));
+  if (DIRICHLET && edge && lane < 2 * p.g && !skip) {
+    const double *gh = p.ghost3 + static_cast<int64_t>(row) * p.ghost_ld + lane;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const double v = gh[s * p.ghost_block];
+      gmine[s][lane] = v;
+      if (chunk == 0) gbits[s] = abs_bits(v);
+    }
+  }
   double u0[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) u0[r] = 0.0;
@@ -1231,22 +1253,27 @@ step_lf_cluster_kernel(const StepParams p) {
   if (!live) return;  // a warp beyond the last window of the row: sends nothing, nobody waits for it
   const double cdt = p.coef * p.dt[static_cast<int64_t>(row) * p.dt_stride];
   const bool fill = DIRICHLET && !inside;
-  if (fill) step_fill_ghosts<R>(p, row, 0, c0, u0);
   const int windows = p.chunks_per_row;
+  double nuf[R + 1];
+  if constexpr (NU) step_load_nu<R>(p, c0, nuf);
 
   double a[R], dF[R];
-  lf_send_stage_max<R>(p, &xch, lane, row, chunk, 0, DIRICHLET, st, u0);
-  step_stage_rhs<R, kLF, kB, LfSpeed>(u0, p.eps9, dF, nullptr, LfSpeed{&xch, 0, windows, lane});
+  // (the maximum goes out BEFORE the ghost cells of this warp are filled: stored cells only enter it, and the loads
+  // of the fill stay off the critical path of the row)
+  if (DIRICHLET) __syncwarp();
+  lf_send_stage_max<R>(&xch, lane, chunk, 0, gbits[0], st, u0);
+  if (fill) lf_fill_ghosts<R>(p, gmine[0], c0, u0);
+  step_stage_rhs<R, kLF, kB, LfSpeed, NU>(u0, p.eps9, dF, nullptr, LfSpeed{&xch, 0, windows, lane}, nuf);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);  // k1
-  if (fill) step_fill_ghosts<R>(p, row, 1, c0, a);
-  lf_send_stage_max<R>(p, &xch, lane, row, chunk, 1, DIRICHLET, st, a);
-  step_stage_rhs<R, kLF, kB, LfSpeed>(a, p.eps9, dF, nullptr, LfSpeed{&xch, 1, windows, lane});
+  lf_send_stage_max<R>(&xch, lane, chunk, 1, gbits[1], st, a);
+  if (fill) lf_fill_ghosts<R>(p, gmine[1], c0, a);
+  step_stage_rhs<R, kLF, kB, LfSpeed, NU>(a, p.eps9, dF, nullptr, LfSpeed{&xch, 1, windows, lane}, nuf);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);  // k2
-  if (fill) step_fill_ghosts<R>(p, row, 2, c0, a);
-  lf_send_stage_max<R>(p, &xch, lane, row, chunk, 2, DIRICHLET, st, a);
-  step_stage_rhs<R, kLF, kB, LfSpeed>(a, p.eps9, dF, nullptr, LfSpeed{&xch, 2, windows, lane});
+  lf_send_stage_max<R>(&xch, lane, chunk, 2, gbits[2], st, a);
+  if (fill) lf_fill_ghosts<R>(p, gmine[2], c0, a);
+  step_stage_rhs<R, kLF, kB, LfSpeed, NU>(a, p.eps9, dF, nullptr, LfSpeed{&xch, 2, windows, lane}, nuf);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);  // u'
 
@@ -1277,7 +1304,7 @@ step_lf_cluster_kernel(const StepParams p) {
 // the 8 CTAs of a portable cluster
 static int g_lf_wpc = 4;
 
-template <bool WITH_MAX, int BCK>
+template <bool WITH_MAX, int BCK, bool NU = false>
 int launch_step_lf(const StepParams &q0, int n, int batch, cudaStream_t st) {
   constexpr int R = 6, kMaxWarps = 12;
   StepParams q = q0;
@@ -1303,9 +1330,9 @@ int launch_step_lf(const StepParams &q0, int n, int batch, cudaStream_t st) {
   cfg.numAttrs = 1;
   // (CTAs of up to 4 windows: 16 warps per SM within 128 registers; longer rows: one large CTA per SM)
   if (wpc <= 4)
-    PSK_CUDA_OK(cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 128, 4>, q));
+    PSK_CUDA_OK(cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 128, 4, NU>, q));
   else
-    PSK_CUDA_OK(cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 384, 1>, q));
+    PSK_CUDA_OK(cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 384, 1, NU>, q));
   return PSK_OK;
 }
 
@@ -1440,6 +1467,7 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
   q.ghost_ld = d->ghost_ld;
   q.ghost_block = d->ghost_ld != 0 ? static_cast<int64_t>(d->batch) * d->ghost_ld : 2 * d->g;
   q.vel = d->velocity; q.vel_l = d->vel_l; q.vel_r = d->vel_r;
+  q.nu = d->nu;
   q.k1_out = k1_out; q.k2_out = k2_out;
   q.maxabs = reinterpret_cast<unsigned long long *>(maxabs);
   q.ld = d->ld;
@@ -1472,6 +1500,8 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     return PSK_OK;
   }
   if (d->flux == PSK_FLUX_LAX_FRIEDRICHS) {  // one cluster per row (the entry points admit periodic / Dirichlet rows)
+    if (d->bc == PSK_BC_DIRICHLET && d->nu != nullptr)  // alpha != 1 (the reference's burgers-adjoint defaults)
+      return mx ? launch_step_lf<true, 1, true>(q, d->n, batch, st) : launch_step_lf<false, 1, true>(q, d->n, batch, st);
     if (d->bc == PSK_BC_DIRICHLET)
       return mx ? launch_step_lf<true, 1>(q, d->n, batch, st) : launch_step_lf<false, 1>(q, d->n, batch, st);
     return mx ? launch_step_lf<true, 0>(q, d->n, batch, st) : launch_step_lf<false, 0>(q, d->n, batch, st);
@@ -1493,6 +1523,13 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     if (d->equation == PSK_EQ_CONTINUITY) PSK_STEP_BC(kUp, PSK_EQ_CONTINUITY);
     if (d->flux == PSK_FLUX_UPWIND) PSK_STEP_BC(kUp, kB);
     if (d->flux == PSK_FLUX_ENGQUIST_OSHER) PSK_STEP_BC(kEO, kB);
+    if (d->nu != nullptr) {  // Rusanov with alpha != 1: nu of every face
+      if (k1_out != nullptr)
+        return neumann ? launch_step_shape<6, kRus, 128, 3, true, kB, 2, true>(q, d->n, batch, false, st)
+                       : launch_step_shape<6, kRus, 128, 3, true, kB, 1, true>(q, d->n, batch, false, st);
+      return neumann ? launch_step_shape<6, kRus, 128, 3, false, kB, 2, true>(q, d->n, batch, mxs, st)
+                     : launch_step_shape<6, kRus, 128, 3, false, kB, 1, true>(q, d->n, batch, mxs, st);
+    }
     PSK_STEP_BC(kRus, kB);
 #undef PSK_STEP_BC
   }
@@ -1762,8 +1799,10 @@ int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const 
     return PSK_E_INVALID;
   auto al = [&](const double *a) { return a == nullptr || reinterpret_cast<uintptr_t>(a + d->g) % 16 == 0; };
   const bool aligned = al(u) && al(uout) && al(k1_out) && al(k2_out) && (d->ld % 2 == 0);
-  const bool burgers_ok = d->equation == PSK_EQ_BURGERS && d->nu == nullptr &&
-                          (d->flux == PSK_FLUX_RUSANOV || d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER ||
+  // (nu: Rusanov / Lax-Friedrichs with alpha != 1 take the viscosity of every face; no other flux has one)
+  const bool burgers_ok = d->equation == PSK_EQ_BURGERS &&
+                          (d->flux == PSK_FLUX_RUSANOV ||
+                           (d->nu == nullptr && (d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER)) ||
                            (d->flux == PSK_FLUX_LAX_FRIEDRICHS && d->bc == PSK_BC_DIRICHLET && k1_out == nullptr));
   const bool linear_ok = d->equation != PSK_EQ_BURGERS && d->flux == PSK_FLUX_UPWIND;
   if (!(burgers_ok || linear_ok) || d->rec != PSK_REC_WENOJS53 || d->math != PSK_MATH_FAST || !aligned ||

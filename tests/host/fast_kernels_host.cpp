@@ -200,8 +200,9 @@ int emu_fused_step_stages(int n, int g, int batch, long long ld, double dx, doub
 int emu_fused_step_bc(int equation, int flux, int with_max, int neumann, int n, int g, int batch, long long ld, double dx, double eps,
                       const double *u, double *uout, const double *dt, int dt_stride, const double *ghost3,
                       long long ghost_ld, const double *vel, const double *vel_l, const double *vel_r,
-                      unsigned long long *maxabs) {
+                      unsigned long long *maxabs, const double *nu) {
   psk::StepParams q{};
+  q.nu = nu;
   q.u = u; q.uout = uout; q.dt = dt;
   q.maxabs = with_max ? maxabs : nullptr;
   q.ld = ld;
@@ -223,6 +224,10 @@ int emu_fused_step_bc(int equation, int flux, int with_max, int neumann, int n, 
                           : &psk::step_warp_fused_kernel<6, FL, false, 128, 3, false, EQ, 1>)
   if (equation == PSK_EQ_ADVECTION && flux == kUp) { EMU_BC(kUp, PSK_EQ_ADVECTION); }
   else if (equation == PSK_EQ_CONTINUITY && flux == kUp) { EMU_BC(kUp, PSK_EQ_CONTINUITY); }
+  else if (equation == kB && flux == PSK_FLUX_RUSANOV && nu != nullptr) {  // alpha != 1: nu of every face
+    k = neumann ? &psk::step_warp_fused_kernel<6, PSK_FLUX_RUSANOV, false, 128, 3, false, kB, 2, true>
+                : &psk::step_warp_fused_kernel<6, PSK_FLUX_RUSANOV, false, 128, 3, false, kB, 1, true>;
+  }
   else if (equation == kB && flux == PSK_FLUX_RUSANOV) { EMU_BC(PSK_FLUX_RUSANOV, kB); }
   else if (equation == kB && flux == kUp) { EMU_BC(kUp, kB); }
   else if (equation == kB && flux == PSK_FLUX_ENGQUIST_OSHER) { EMU_BC(PSK_FLUX_ENGQUIST_OSHER, kB); }

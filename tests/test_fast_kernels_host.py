@@ -44,7 +44,7 @@ def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
     lib.emu_fused_step_stages.argtypes = [ct.c_int] * 3 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, dp, dp, ct.c_int]
     lib.emu_fused_step_stages.restype = ct.c_int
     lib.emu_fused_step_bc.argtypes = [ct.c_int] * 7 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int, dp,
-                                                      ct.c_longlong, dp, dp, dp, up]
+                                                      ct.c_longlong, dp, dp, dp, up, dp]
     lib.emu_fused_step_bc.restype = ct.c_int
     lib.emu_fused_step_periodic_eq.argtypes = [ct.c_int] * 4 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
                                                                dp, dp, dp]
@@ -292,12 +292,42 @@ def test_fused_step_with_boundary_data_is_the_three_stages(emu, equation: str, f
     g3c = np.ascontiguousarray(g3)
     rc = emu.emu_fused_step_bc(EQUATION[equation], FLUX[flux], 1, int(bc == "neumann"), n, G, pb.batch, pb.nx, pb.dx, EPS, _p(pb.fill(pb.u)),
                                _p(out), _p(pb.dt), 1, _p(g3c), 0 if shared_ghosts else 2 * G, _p(k.get("v")),
-                               _p(k.get("vl")), _p(k.get("vr")), maxabs.ctypes.data_as(ct.POINTER(ct.c_ulonglong)))
+                               _p(k.get("vl")), _p(k.get("vr")), maxabs.ctypes.data_as(ct.POINTER(ct.c_ulonglong)), None)
     assert rc == 0
     assert np.isnan(out[:, :G]).all() and np.isnan(out[:, G + n :]).all()
     assert np.array_equal(out[:, i], staged[:, i])
     assert np.abs(out[:, i] - ref[:, i]).max() <= 2e-13 * np.abs(ref[:, i]).max()
     assert np.array_equal(maxabs.view(np.float64), np.abs(out[:, i]).max(axis=1))
+
+
+@pytest.mark.parametrize("bc", ["dirichlet", "neumann"])
+@pytest.mark.parametrize("n", [16, 171, 173, 250, 1000])
+def test_fused_step_with_the_viscosity_of_every_face(emu, bc: str, n: int) -> None:
+    """Rusanov with alpha != 1 (scalar.py:231-234: nu = df ** (alpha - 1), one value per face of the array, not all
+    equal in the last bit) on rows with boundary data: the whole-step kernel multiplies the speed of every face by
+    its own nu, against the C oracle bound to the same array (the bit-identity with the stage launches is a GPU
+    test: the general stage kernel is not part of the emulated header)"""
+    pb = Problem("burgers", "rusanov", bc, n=n, batch=3, seed=500 + n)
+    rng = np.random.default_rng(n)
+    nu = (pb.dx ** (0.995 - 1.0)) * (1.0 + 1e-3 * rng.standard_normal(pb.nx - 1))
+    pb.co = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc=bc, n=n, g=G, batch=pb.batch, dx=pb.dx, eps=EPS,
+                    nu=nu)
+    pb.co.set_ghost(pb.ghost)  # (per-row boundary data: the layout ghost3 is read with)
+    g3 = rng.uniform(-0.3, 0.3, size=(3, pb.batch, 2 * G)) * (1.0 if bc == "dirichlet" else pb.dx)
+    pb.dt = pb.dt / nu.max()
+    ref = pb.co.ssprk33_step(pb.u, pb.dt, ghost3=np.ascontiguousarray(g3))
+    one = COracle(equation="burgers", flux="rusanov", rec="wenojs53", bc=bc, n=n, g=G, batch=pb.batch, dx=pb.dx, eps=EPS)
+    one.set_ghost(pb.ghost)
+    assert np.abs(one.ssprk33_step(pb.u, pb.dt, ghost3=np.ascontiguousarray(g3)) - ref).max() > 1e-6  # nu matters
+    out = np.full_like(pb.u, np.nan)
+    maxabs = np.zeros(pb.batch, dtype=np.uint64)
+    i = pb.interior
+    g3c, uin = np.ascontiguousarray(g3), pb.fill(pb.u)  # (kept alive across the call)
+    rc = emu.emu_fused_step_bc(EQUATION["burgers"], FLUX["rusanov"], 0, int(bc == "neumann"), n, G, pb.batch, pb.nx, pb.dx, EPS,
+                               _p(uin), _p(out), _p(pb.dt), 1, _p(g3c), 2 * G, None, None, None,
+                               maxabs.ctypes.data_as(ct.POINTER(ct.c_ulonglong)), _p(nu))
+    assert rc == 0
+    assert np.abs(out[:, i] - ref[:, i]).max() <= 2e-13 * np.abs(ref[:, i]).max()
 
 
 @pytest.mark.parametrize("equation", ["advection", "continuity"])

@@ -340,3 +340,43 @@ def test_advance_keeps_the_ghost_cell_byproducts_of_the_reference(equation: str,
         assert torch.equal(hp.ssprk33_advance(u, dt), hp.ssprk33_step(u, dt, ghost_rows=True))
     one = hp.ssprk33_advance(u[0], dt, ghosts=ghosts)  # a single row, 1-D
     assert torch.equal(one, ref[0])
+
+
+@pytest.mark.parametrize("flux", ["rusanov", "lf"])
+@pytest.mark.parametrize("bc", ["dirichlet", "neumann", "periodic"])
+@pytest.mark.parametrize("batch,n,nsteps", [(3, 4096, 4), (2, 1000, 3), (2, 172, 2)])
+def test_whole_step_with_the_viscosity_of_every_face(flux: str, bc: str, batch: int, n: int, nsteps: int) -> None:
+    """alpha != 1 (scalar.py:231-234; the burgers-adjoint driver of the reference runs Lax-Friedrichs with
+    alpha = 0.995 on Dirichlet rows): nu = df ** (alpha - 1) per face of the array -- its entries differ in the last
+    bit, diff of computed cell centres -- multiplies the speed of every face.  Rows with boundary data: one launch per
+    step, the bits of the stage launches.  Periodic rows (the face at the seam has two entries) and Lax-Friedrichs on
+    Neumann rows keep the stage launches."""
+    x = -1.37 + 3.1 * (np.arange(n + 2 * G) - G + 0.5) / n
+    nu = np.diff(x) ** (0.995 - 1.0)
+    assert np.unique(nu).size > 1
+    u0 = _ic(batch, n, seed=n + 7)
+    rng = np.random.default_rng(n)
+    ghost = None if bc == "periodic" else rng.uniform(-0.3, 0.3, size=(batch, 2 * G)) * (1.0 if bc == "dirichlet" else 3.0 / n)
+    dt = 0.3 * (3.0 / n) / max(float(u0.abs().max()), 1.0) / float(nu.max())
+
+    def solver():
+        s = _solver(batch, n, flux=flux, bc=bc, nu=nu)
+        if ghost is not None:
+            s.hp.set_ghost(ghost)
+        return s
+
+    with whole_step(7000):
+        a = solver()
+        a._lf_chain = False
+        a.solve_fixed_dt(u0, dt, nsteps)
+        assert a._fused is False
+    b = solver()
+    b.solve_fixed_dt(u0, dt, nsteps)
+    fused = bc == "dirichlet" or (bc == "neumann" and flux == "rusanov")
+    assert b._fused is fused and (b.launches == nsteps) == fused
+    assert torch.equal(a.u[:, G : G + n], b.u[:, G : G + n])
+    one = _solver(batch, n, flux=flux, bc=bc)  # nu = 1 is a different scheme
+    if ghost is not None:
+        one.hp.set_ghost(ghost)
+    one.solve_fixed_dt(u0, dt, nsteps)
+    assert float((one.u[:, G : G + n] - b.u[:, G : G + n]).abs().max()) > 1e-9

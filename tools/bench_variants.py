@@ -24,15 +24,20 @@ CASES = [
     ("burgers", "eo", "dirichlet"), ("burgers", "lf", "periodic"), ("burgers", "rusanov", "neumann"),
     ("advection", "godunov", "dirichlet"), ("continuity", "godunov", "dirichlet"), ("advection", "godunov", "periodic"),
     ("continuity", "godunov", "periodic"),
+    # alpha = 0.995: nu = df ** (alpha - 1) per face (the scheme of the reference's burgers-adjoint driver: lf, Dirichlet)
+    ("burgers", "lf", "dirichlet", 0.995), ("burgers", "rusanov", "dirichlet", 0.995), ("burgers", "lf", "dirichlet"),
 ]
 if os.environ.get("PSK_LF_WPC"):  # windows per CTA of the Lax-Friedrichs cluster kernel (tuning switch)
     from pyshocks_b200 import _lib
     assert _lib.lib().psk_set_stage_variant(8000 + int(os.environ["PSK_LF_WPC"])) == 0
 ONLY = sys.argv[1:]  # e.g. "neumann": the cases whose equation / flux / boundary kind is named
-for eq, flux, bc in CASES:
-    if ONLY and not any(o in (eq, flux, bc) for o in ONLY):
+for eq, flux, bc, *rest in CASES:
+    alpha = rest[0] if rest else 1.0
+    if ONLY and not any(o in (eq, flux, bc, f"alpha={alpha}") for o in ONLY):
         continue
     kw = {"velocity": vel} if eq != "burgers" else {}
+    if alpha != 1.0:
+        kw["nu"] = np.diff(-1.37 + 3.1 * (np.arange(N + 2 * G) - G + 0.5) / N) ** (alpha - 1.0)
     s = EnsembleSolver(equation=eq, flux=flux, rec="wenojs53", bc=bc, n=N, g=G, dx=h, eps=1e-12, batch=B, **kw)
     if bc in ("dirichlet", "neumann"):
         s.hp.set_ghost(np.zeros(2 * G) if bc == "neumann" else np.full(2 * G, 0.3))
@@ -47,7 +52,7 @@ for eq, flux, bc in CASES:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(json.dumps({"equation": eq, "flux": flux, "bc": bc, "launches_per_step": (s.launches - l0) / 20,
+    print(json.dumps({"equation": eq, "flux": flux, "bc": bc, "alpha": alpha, "launches_per_step": (s.launches - l0) / 20,
                       "ms_per_step": ms / 20, "cell_updates_per_s": B * N * 20 / (ms * 1e-3),
                       "finite": bool(torch.isfinite(s.u[:, G : G + N]).all())}), flush=True)
     del s

@@ -192,7 +192,9 @@ int psk_ssprk33_stage_lf(const psk_desc *d, int stage, const double *u0, const d
  * hot configuration only: Burgers with the Rusanov (nu = 1), upwind or Engquist-Osher flux + WENO-JS5,
  * FAST math, periodic rows (g >= 3) or slabs of a larger grid (boundary kind NONE with g >= 9 ghost
  * cells per side, filled by the caller before the call: the three stages reach 9 cells beyond the row),
- * 16-byte aligned rows.  u is read once and uout written once; the stage values stay in registers
+ * 16-byte aligned rows.  Also the global Lax-Friedrichs flux (scalar.py:258-278, nu = 1) on PERIODIC rows of at
+ * most 16 512 cells: one thread-block cluster per row, the row-wide max |w| of every stage input (scalar.py:277)
+ * exchanged through distributed shared memory.  u is read once and uout written once; the stage values stay in registers
  * (temporal blocking, psk_fast_kernels.cuh).  Bit-identical to three psk_ssprk33_stage calls.
  * uout must not alias u.  active / maxabs as in psk_ssprk33_stage, except that rows with
  * active[r] == 0 are COPIED to uout (the state ping-pongs between two arrays).  Ghost cells of uout
@@ -206,12 +208,14 @@ int psk_ssprk33_stage_lf(const psk_desc *d, int stage, const double *u0, const d
 int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const double *dt,
                      int64_t dt_stride, const uint8_t *active, double *maxabs, psk_stream_t stream);
 
-/* psk_ssprk33_step for rows with DIRICHLET boundary data (scalar.py:418-427) and for the advection / continuity
- * equations: the whole step in one launch, the ghost cells of every stage input taking the data of that stage's
- * time.  ghost3: three consecutive blocks of (d->ghost_ld != 0 ? batch * d->ghost_ld : 2 g) doubles -- what the
+/* psk_ssprk33_step for rows with DIRICHLET or NEUMANN boundary data (scalar.py:418-427, 472-500) and for the
+ * advection / continuity equations: the whole step in one launch, the ghost cells of every stage input taking the
+ * data of that stage's time (Neumann: plus the stage value of their mirror image).  ghost3: three consecutive blocks of (d->ghost_ld != 0 ? batch * d->ghost_ld : 2 g) doubles -- what the
  * user's g(t, x) returns at t, t + dt, t + dt / 2 (timestepping.py:314-319), rows at stride d->ghost_ld (0: one
- * set for all rows), left ghost cells first; d->ghost is ignored.  Burgers + {Rusanov (nu = 1), upwind,
- * Engquist-Osher}, advection, continuity (upwind flux); WENO-JS5, FAST math, 16-byte aligned rows;
+ * set for all rows), left ghost cells first; d->ghost is ignored.  Burgers + {Rusanov, upwind,
+ * Engquist-Osher; global Lax-Friedrichs on Dirichlet rows of at most 16 512 cells, without k1_out / k2_out},
+ * advection, continuity (upwind flux); WENO-JS5, FAST math, 16-byte aligned rows, g <= 16.  d->nu (Rusanov /
+ * Lax-Friedrichs with alpha != 1, scalar.py:231-234): the viscosity of every face of the array, nx - 1 values.
  * PSK_E_UNSUPPORTED elsewhere.  Same bits as three psk_ssprk33_stage calls with those data.  active / maxabs
  * as in psk_ssprk33_step.  k1_out / k2_out (both or neither; then active = maxabs = NULL): the stage values are
  * stored as well, as psk_ssprk33_step_stages does for periodic rows, and uout may be NULL (third stage skipped):
@@ -318,7 +322,8 @@ int psk_dfma_probe(double *out, int ctas, int iters, psk_stream_t stream);
 
 /* out = J_L(u)^T v, the vector-Jacobian product of apply_operator w.r.t. u (all nx
  * rows, boundary condition included); what jax.vjp(apply_operator) returns, and the
- * building block of the reference's adjoint_step (timestepping.py:174, :205-206).
+ * building block of the reference's adjoint_step (timestepping.py:174, :205-206).  Every equation, flux and
+ * reconstruction of the forward entry points, the ESWENO32 reconstruction and the Burgers ESWENO32 scheme included.
  * work: batch * (2 g + 2) doubles of scratch.  out must not alias u or v. */
 int psk_apply_operator_vjp(const psk_desc *d, const double *u, const double *v, double *out,
                            double *work, psk_stream_t stream);

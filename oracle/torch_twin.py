@@ -69,9 +69,46 @@ def _weno_js_side(s: dict, eps: float, f: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _smoothness(s: dict, f: torch.Tensor) -> list[torch.Tensor]:
+    # weno.py:134-140
+    beta = []
+    for i in range(s["b"].shape[0]):
+        acc = None
+        for j in range(s["a"].size):
+            term = float(s["a"][j]) * _conv_same(f, s["b"][i, j, :]) ** 2
+            acc = term if acc is None else acc + term
+        beta.append(acc)
+    return beta
+
+
+def es_weno_weights(s: dict, f: torch.Tensor, eps: float) -> list[torch.Tensor]:
+    # weno.py:284-296: alpha_k = d_k (1 + tau / (eps + beta_k)), tau zero at the two ends of the array
+    beta = _smoothness(s, f)
+    tau = torch.nn.functional.pad((f[2:] - 2 * f[1:-1] + f[:-2]) ** 2, (1, 1))
+    alpha = [float(s["d"][i, 0]) * (1 + tau / (eps + beta[i])) for i in range(len(beta))]
+    total = alpha[0]
+    for i in range(1, len(alpha)):
+        total = total + alpha[i]
+    return [a / total for a in alpha]
+
+
+def _es_weno_side(s: dict, eps: float, f: torch.Tensor) -> torch.Tensor:
+    # reconstruction.py:413-417
+    omega = es_weno_weights(s, f, eps)
+    out = None
+    for i in range(len(omega)):
+        term = omega[i] * _conv_same(f, s["c"][i, :])
+        out = term if out is None else out + term
+    return out
+
+
 def reconstruct(rec: po.Reconstruction, f: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
     if rec.name == "constant":
         return f, f
+    if rec.name == "esweno32":  # reconstruction.py:420-439
+        fr = _es_weno_side(po._JS32, rec.eps, f)
+        fl = torch.flip(_es_weno_side(po._JS32, rec.eps, torch.flip(f, (0,))), (0,))
+        return fl, fr
     s = po._JS53 if rec.name == "wenojs53" else po._JS32
     fr = _weno_js_side(s, rec.eps, f)
     fl = torch.flip(_weno_js_side(s, rec.eps, torch.flip(f, (0,))), (0,))
@@ -116,10 +153,16 @@ def numerical_flux(scheme: po.Scheme, grid: po.OracleGrid, u: torch.Tensor) -> t
     rec = scheme.rec
     if scheme.equation == "burgers":
         ul, ur = reconstruct(rec, u)
-        if scheme.flux == "godunov":
+        if scheme.flux in ("godunov", "esweno32"):
             fl, fr = _physical_flux(scheme, ul), _physical_flux(scheme, ur)
             aavg = (ur[:-1] + ul[1:]) / 2
-            return pad(torch.where(aavg > 0, fr[:-1], fl[1:]), (1, 1))
+            fnum = pad(torch.where(aavg > 0, fr[:-1], fl[1:]), (1, 1))
+            if scheme.flux == "esweno32":  # burgers/schemes.py:230-256: + the dissipative flux of ESWENO
+                omega = es_weno_weights(po._JS32, u, rec.eps)[0]
+                dom = omega[1:] - omega[:-1]
+                mu = torch.sqrt(dom**2 + rec.delta**2) / 8.0
+                fnum = fnum + pad(-(mu + dom / 8.0) * (u[1:] - u[:-1]), (1, 1))
+            return fnum
         if scheme.flux in ("rusanov", "lf"):
             if abs(scheme.alpha - 1.0) > 1.0e-8:
                 nu = _t(grid.df ** (scheme.alpha - 1))

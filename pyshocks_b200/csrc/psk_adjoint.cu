@@ -86,21 +86,31 @@ adjoint_tile_kernel(const AdjParams p) {
   }
 
   // ---- pass 1: face values of the owned cells, neighbour exchange
+  // (ESWENO32: tau is zero in the first and the last cell of the array, weno.py:292)
+  auto tz = [&](int i) { return REC == PSK_REC_ESWENO32 && (i <= 0 || i >= nx - 1); };
   double ul[R], ur[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int m = r + kAdjHalo;
-    Weno5Pair o = reconstruct_cell<REC, false>(w[m - 2], w[m - 1], w[m], w[m + 1], w[m + 2], p.eps);
+    Weno5Pair o = reconstruct_cell<REC, false>(w[m - 2], w[m - 1], w[m], w[m + 1], w[m + 2], p.eps, tz(c0 + r));
     ul[r] = o.ul;
     ur[r] = o.ur;
   }
   xl[t] = ul[0];
   xr[t + 1] = ur[R - 1];
-  if (t == 0) xr[0] = reconstruct_cell<REC, false>(w[0], w[1], w[2], w[3], w[4], p.eps).ur;
+  if (t == 0) xr[0] = reconstruct_cell<REC, false>(w[0], w[1], w[2], w[3], w[4], p.eps, tz(c0 - 1)).ur;
   if (t == nthreads - 1)
     xl[nthreads] =
-        reconstruct_cell<REC, false>(w[R + 1], w[R + 2], w[R + 3], w[R + 4], w[R + 5], p.eps).ul;
+        reconstruct_cell<REC, false>(w[R + 1], w[R + 2], w[R + 3], w[R + 4], w[R + 5], p.eps, tz(c0 + R)).ul;
   __syncthreads();
+  // the Burgers ESWENO32 scheme: omega_0 of the cells c0 - 1 .. c0 + R for the dissipative flux of their faces
+  double om[R + 2], gom[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) gom[r] = 0.0;
+  if (FLUX == PSK_FLUX_ESWENO) {
+#pragma unroll
+    for (int k = 0; k < R + 2; ++k) om[k] = esweno32_cell<false>(w[k + 1], w[k + 2], w[k + 3], p.eps, tz(c0 - 1 + k)).om0;
+  }
   const double ur_left = xr[t];
   const double ul_right = xl[t + 1];
 
@@ -140,6 +150,17 @@ adjoint_tile_kernel(const AdjParams p) {
     if (f >= 1) dir[f - 1] = fma(gF, fg.d_wj, dir[f - 1]);
     if (f <= R - 1) dir[f] = fma(gF, fg.d_wp, dir[f]);
     if (FLUX == PSK_FLUX_LAX_FRIEDRICHS && f >= 1 && writer) ga_part = fma(gF, fg.d_speed, ga_part);
+    if (FLUX == PSK_FLUX_ESWENO) {  // + g(om_j, om_p, w_j, w_p) (burgers/schemes.py:243-256)
+      const EsGnumGrad eg = esweno_gnum_grad(om[f], om[f + 1], w[f + kAdjHalo - 1], w[f + kAdjHalo], p.delta);
+      if (f >= 1) {
+        dir[f - 1] = fma(gF, eg.d_wj, dir[f - 1]);
+        gom[f - 1] = fma(gF, eg.d_omj, gom[f - 1]);
+      }
+      if (f <= R - 1) {
+        dir[f] = fma(gF, eg.d_wp, dir[f]);
+        gom[f] = fma(gF, eg.d_omp, gom[f]);
+      }
+    }
   }
 
   // ---- pass 2: through the reconstruction, 5-point scatter kept in registers
@@ -150,7 +171,7 @@ adjoint_tile_kernel(const AdjParams p) {
   for (int r = 0; r < R; ++r) {
     const int m = r + kAdjHalo;
     const Weno5Vjp d = reconstruct_cell_vjp<REC>(w[m - 2], w[m - 1], w[m], w[m + 1], w[m + 2], p.eps,
-                                                 gur[r + 1], gul[r]);
+                                                 gur[r + 1], gul[r], tz(c0 + r), gom[r]);
 #pragma unroll
     for (int q = 0; q < 5; ++q) accw[r + q] += d.d[q];
   }
@@ -528,6 +549,7 @@ int adjoint_rec(int rec, const AdjParams &p, int batch, cudaStream_t st) {
   switch (rec) {
     case PSK_REC_CONSTANT: return launch_adjoint<EQ, FLUX, PSK_REC_CONSTANT>(p, batch, st);
     case PSK_REC_WENOJS32: return launch_adjoint<EQ, FLUX, PSK_REC_WENOJS32>(p, batch, st);
+    case PSK_REC_ESWENO32: return launch_adjoint<EQ, FLUX, PSK_REC_ESWENO32>(p, batch, st);
     default: return launch_adjoint<EQ, FLUX, PSK_REC_WENOJS53>(p, batch, st);
   }
 }
@@ -543,8 +565,8 @@ static int run_adjoint(const psk_desc *d, const double *x, const double *v, cons
   if (rc != PSK_OK) return rc;
   if (x == nullptr || v == nullptr || out == nullptr || work == nullptr) return PSK_E_INVALID;
   if (out == x || out == v) return PSK_E_INVALID;  // tiles read their neighbours' cells
-  // the adjoint drivers of the reference run WENO-JS schemes; no ESWENO32 transpose is built
-  if (d->rec == PSK_REC_ESWENO32 || d->flux == PSK_FLUX_ESWENO) return PSK_E_UNSUPPORTED;
+  // the ESWENO32 scheme is the upwind flux of the ESWENO32 reconstruction plus a dissipative flux of its weights
+  if (d->flux == PSK_FLUX_ESWENO && (d->rec != PSK_REC_ESWENO32 || d->equation != PSK_EQ_BURGERS)) return PSK_E_INVALID;
   AdjParams p{};
   p.x = x;
   p.v = v;
@@ -568,6 +590,7 @@ static int run_adjoint(const psk_desc *d, const double *x, const double *v, cons
   p.ld = d->ld;
   p.invdx = 1.0 / d->dx;
   p.eps = d->eps;
+  p.delta = d->delta;
   const bool lf = d->equation == PSK_EQ_BURGERS && d->flux == PSK_FLUX_LAX_FRIEDRICHS;
   if (lf) {
     rc = launch_max_abs_public(d, x, 2, p.speed, st);
@@ -584,6 +607,7 @@ static int run_adjoint(const psk_desc *d, const double *x, const double *v, cons
     case PSK_FLUX_LAX_FRIEDRICHS:
       return adjoint_rec<PSK_EQ_BURGERS, PSK_FLUX_LAX_FRIEDRICHS>(d->rec, p, b, st);
     case PSK_FLUX_UPWIND: return adjoint_rec<PSK_EQ_BURGERS, PSK_FLUX_UPWIND>(d->rec, p, b, st);
+    case PSK_FLUX_ESWENO: return launch_adjoint<PSK_EQ_BURGERS, PSK_FLUX_ESWENO, PSK_REC_ESWENO32>(p, b, st);
     default: return adjoint_rec<PSK_EQ_BURGERS, PSK_FLUX_ENGQUIST_OSHER>(d->rec, p, b, st);
   }
 }

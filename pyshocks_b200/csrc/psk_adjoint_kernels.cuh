@@ -31,6 +31,7 @@ struct AdjParams {
   BcView bc;
   int64_t ld;
   double invdx, eps;
+  double delta;  // ESWENO32 scheme only (burgers/schemes.py:243)
   int tiles_per_row;
   int prescaled;  // gspill already carries the factor c_g dt (lean kernel)
 };

@@ -545,12 +545,70 @@ __device__ __forceinline__ Weno5Vjp weno53_pair_vjp_sixths(double tm2, double tm
   return o;
 }
 
+// ESWENO32 (weno.py:284-296, reconstruction.py:413-439), the FAST form of esweno32_cell differentiated by hand:
+// cotangents g_ur, g_ul of the face values and g_om of omega_0 (right-value weights: what the dissipative flux of
+// the Burgers ESWENO32 scheme reads, burgers/schemes.py:237-247) -> cotangents of (m1, c, p1) in d[1..3].
+//   d0 = c - m1, d1 = p1 - c, e_k = eps + d_k^2, tau = (d1 - d0)^2 (zero at the array ends),
+//   A0 = (e0 + tau) e1, A1 = (e1 + tau) e0,
+//   ur = c + (A0 d0 + 2 A1 d1) / (2 (A0 + 2 A1)),  ul = c - (A1 d1 + 2 A0 d0) / (2 (A1 + 2 A0)),  om0 = A0 / (A0 + 2 A1)
+__device__ __forceinline__ Weno5Vjp esweno32_cell_vjp(double m1, double c, double p1, double eps, bool tau_zero,
+                                                      double g_ur, double g_ul, double g_om) {
+  const double d0 = c - m1, d1 = p1 - c;
+  const double e0 = fma(d0, d0, eps), e1 = fma(d1, d1, eps);
+  const double tt = d1 - d0;
+  const double tau = tau_zero ? 0.0 : tt * tt;
+  const double A0 = (e0 + tau) * e1, A1 = (e1 + tau) * e0;
+  const double DR = fma(2.0, A1, A0), DL = fma(2.0, A0, A1);
+  const double iR = 1.0 / DR, iL = 1.0 / DL;
+  const double NR = fma(A0, d0, 2.0 * (A1 * d1)), NL = fma(A1, d1, 2.0 * (A0 * d0));
+  // through the quotients
+  const double gNR = 0.5 * g_ur * iR, gNL = -0.5 * g_ul * iL;
+  const double gDR = -(gNR * NR + g_om * A0 * iR) * iR, gDL = -(gNL * NL) * iL;
+  double gA0 = fma(gNR, d0, gDR) + g_om * iR + 2.0 * fma(gNL, d0, gDL);
+  double gA1 = 2.0 * fma(gNR, d1, gDR) + fma(gNL, d1, gDL);
+  double gd0 = gNR * A0 + 2.0 * (gNL * A0);
+  double gd1 = 2.0 * (gNR * A1) + gNL * A1;
+  // A0 = (e0 + tau) e1, A1 = (e1 + tau) e0
+  const double ge0 = fma(gA0, e1, gA1 * (e1 + tau));
+  const double ge1 = fma(gA0, e0 + tau, gA1 * e0);
+  const double gtau = fma(gA0, e1, gA1 * e0);
+  gd0 = fma(2.0 * d0, ge0, gd0);
+  gd1 = fma(2.0 * d1, ge1, gd1);
+  if (!tau_zero) {
+    const double gtt = 2.0 * tt * gtau;
+    gd1 += gtt;
+    gd0 -= gtt;
+  }
+  Weno5Vjp o;
+  o.d[0] = o.d[4] = 0.0;
+  o.d[1] = -gd0;
+  o.d[2] = (gd0 - gd1) + (g_ur + g_ul);
+  o.d[3] = gd1;
+  return o;
+}
+
+// partial derivatives of the dissipative flux g of esweno_gnum (unscaled) wrt (om_j, om_p, w_j, w_p)
+struct EsGnumGrad {
+  double d_omj, d_omp, d_wj, d_wp;
+};
+__device__ __forceinline__ EsGnumGrad esweno_gnum_grad(double omj, double omp, double wj, double wp, double delta) {
+  const double dom = omp - omj;
+  const double S = sqrt(fma(dom, dom, delta * delta));
+  EsGnumGrad g;
+  g.d_wp = -0.125 * (S + dom);
+  g.d_wj = -g.d_wp;
+  g.d_omp = -0.125 * (dom / S + 1.0) * (wp - wj);
+  g.d_omj = -g.d_omp;
+  return g;
+}
+
 template <int REC>
 __device__ __forceinline__ Weno5Vjp reconstruct_cell_vjp(double m2, double m1, double c, double p1,
                                                          double p2, double eps, double g_ur,
-                                                         double g_ul) {
+                                                         double g_ul, bool tau_zero = false, double g_om = 0.0) {
   if (REC == PSK_REC_WENOJS53) return weno53_pair_vjp(m2, m1, c, p1, p2, eps, g_ur, g_ul);
   if (REC == PSK_REC_WENOJS32) return weno32_pair_vjp(m1, c, p1, eps, g_ur, g_ul);
+  if (REC == PSK_REC_ESWENO32) return esweno32_cell_vjp(m1, c, p1, eps, tau_zero, g_ur, g_ul, g_om);
   Weno5Vjp o;
   o.d[0] = o.d[1] = o.d[3] = o.d[4] = 0.0;
   o.d[2] = g_ur + g_ul;
@@ -587,7 +645,7 @@ __device__ __forceinline__ FaceGrad face_flux_grad(double urj, double ulp, doubl
         g.d_wj = d_a * sj * sign0(wj);
         g.d_wp = d_a * (1.0 - sj) * sign0(wp);
       }
-    } else if (FLUX == PSK_FLUX_UPWIND) {
+    } else if (FLUX == PSK_FLUX_UPWIND || FLUX == PSK_FLUX_ESWENO) {  // (ESWENO: + esweno_gnum_grad)
       const bool pos = 0.5 * (urj + ulp) > 0.0;  // jnp.where: selected branch only
       g.d_ur = pos ? urj : 0.0;
       g.d_ul = pos ? 0.0 : ulp;

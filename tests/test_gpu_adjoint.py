@@ -26,12 +26,15 @@ from test_oracle_golden import ADJ, ADJ_KEYS, adjoint_setup
 
 pytestmark = pytest.mark.gpu
 
-# ESWENO32 has no transposed kernels (the reference's adjoint drivers run WENO-JS schemes);
-# tests/test_gpu_api.py checks that asking for its VJP raises
-CASES = [c for c in C.rhs_cases() if c.rec != "esweno32"]
+# (round 2: ESWENO32 -- the reconstruction under every flux and the Burgers ESWENO32 scheme with its dissipative flux --
+# has transposed kernels too, although the reference's adjoint drivers only ever run WENO-JS schemes)
+CASES = C.rhs_cases()
 
 
 def tol_for(case: C.Case) -> float:
+    if case.rec == "esweno32":
+        # eps of the bound ESWENO32 scheme is O(dx^2) and 1e-6 otherwise: the weights' derivative is well conditioned
+        return 1.0e-11
     return 1.0e-12 if case.state == "smooth" else 1.0e-9
 
 
@@ -107,9 +110,10 @@ def test_adjoint_step_sweep_vs_reference_golden(key: str) -> None:
     assert worst < tol
 
 
-def test_step_adjoint_is_transpose_of_step_jacobian() -> None:
+@pytest.mark.parametrize("flux,rec", [("rusanov", "wenojs53"), ("esweno32", "esweno32"), ("godunov", "esweno32")])
+def test_step_adjoint_is_transpose_of_step_jacobian(flux: str, rec: str) -> None:
     """dense check on a small periodic Burgers problem: (J^T p) for unit vectors p rebuilds J"""
-    case = C.Case("burgers", "rusanov", "wenojs53", "periodic", n=24, state="smooth")
+    case = C.Case("burgers", flux, rec, "periodic", n=24, state="smooth")
     hp, scheme, grid, bc = hotpath_for(case, "fast")
     u = C.state_for(case)
     dt = 0.01
@@ -118,4 +122,4 @@ def test_step_adjoint_is_transpose_of_step_jacobian() -> None:
     U = np.tile(u, (grid.nx, 1))
     out = host(hp.ssprk33_step_adjoint(dev(U), dev(np.array([dt])), dev(P)))
     # row r of out = J^T e_r = r-th row of J
-    assert max_rel(out, J) < 1.0e-12
+    assert max_rel(out, J) < (1.0e-12 if rec == "wenojs53" else 1.0e-11)

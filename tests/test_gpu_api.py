@@ -546,12 +546,18 @@ def test_burgers_esweno32_scheme_through_the_api(bc_name: str, math: str) -> Non
             assert max_rel(F, RHS[f"{k}_f"]) < 5e-13
             assert max_rel(L, RHS[f"{k}_L"]) < 5e-13
             assert max_rel(out, ADV[f"{k}_out"]) < 1e-13
-        # no transposed ESWENO32 kernels: the adjoint raises like an unregistered type does
+        # the transposed ESWENO32 kernels (round 2), through the bound path, against reverse-mode differentiation of
+        # the reference arithmetic (oracle/torch_twin.py)
+        from common import oracle_setup
+        from oracle import torch_twin as tt
         from pyshocks_b200.binding import hotpath_for
 
-        hp = hotpath_for(scheme, grid, bc)
-        with pytest.raises(Exception, match="outside"):
-            hp.apply_operator_vjp(u, torch.ones_like(u))
+        hp = hotpath_for(scheme, grid, bc, case.t)
+        v = np.random.default_rng(3).standard_normal(u.shape[0])
+        got = hp.apply_operator_vjp(u, torch.from_numpy(v).cuda()).cpu().numpy()
+        oscheme, ogrid, obc = oracle_setup(case)
+        ref = tt.rhs_vjp(oscheme, ogrid, obc, case.t, u.cpu().numpy(), v)
+        assert max_rel(got, ref) < 1e-10
     finally:
         config.set_math("fast")
 

@@ -248,3 +248,30 @@ def test_other_steppers_numpy_oracle_bitwise(case: C.Case) -> None:
     for name in C.STEPPERS:
         out = po.STEPPER_ADVANCE[name](lambda t, x: po.apply_operator(scheme, grid, bc, t, x), dt, case.t, u)
         assert np.array_equal(out, G[f"{k}_{name}"]), name
+
+
+@pytest.mark.parametrize("case", [c for c in C.rhs_cases() if c.rec == "esweno32"], ids=lambda c: c.key)
+def test_torch_twin_esweno32_is_the_numpy_oracle(case: C.Case) -> None:
+    """the autograd twin of the ESWENO32 reconstruction and of the Burgers ESWENO32 scheme (weno.py:284-296,
+    burgers/schemes.py:230-256) evaluates the NumPy oracle's RHS -- itself pinned to the reference's golden vectors --
+    to the last bit: its reverse-mode derivative is the truth the transposed ESWENO32 kernels are held to"""
+    import torch
+
+    from common import oracle_setup
+    from oracle import torch_twin as tt
+
+    scheme, grid, bc = oracle_setup(case)
+    u = C.state_for(case)
+    L = po.apply_operator(scheme, grid, bc, case.t, u)
+    Lt = tt.apply_operator(scheme, grid, bc, case.t, torch.from_numpy(u)).numpy()
+    assert np.array_equal(L, Lt)
+    # and the vector-Jacobian product agrees with central differences of the oracle
+    rng = np.random.default_rng(1)
+    v, d = rng.standard_normal(grid.nx), rng.standard_normal(grid.nx)
+    jtv = tt.rhs_vjp(scheme, grid, bc, case.t, u, v)
+    if case.state == "smooth":
+        h = 1e-6
+        f = lambda x: po.apply_operator(scheme, grid, bc, case.t, x)  # noqa: E731
+        jd = (f(u + h * d) - f(u - h * d)) / (2 * h)
+        lhs, rhs = float(v @ jd), float(jtv @ d)
+        assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0)

@@ -530,6 +530,78 @@ def measure_weak(ctx: Ctx, args: argparse.Namespace) -> dict:
             "rows_per_gpu": args.batch, "ms_per_step": ms / args.steps, "scaling": "weak"}
 
 
+# the other schemes of the path, each ONE launch per step since round 2: (equation, flux, boundary kind, alpha)
+SCHEMES = [
+    ("burgers", "godunov", "periodic", 1.0), ("burgers", "rusanov", "dirichlet", 1.0), ("burgers", "rusanov", "neumann", 1.0),
+    ("burgers", "eo", "dirichlet", 1.0), ("burgers", "lf", "periodic", 1.0),
+    ("burgers", "lf", "dirichlet", 0.995),  # the scheme of the reference's burgers-adjoint driver (drivers/burgers-adjoint.py:408)
+    ("advection", "godunov", "periodic", 1.0), ("continuity", "godunov", "dirichlet", 1.0),
+]
+
+
+def measure_schemes(ctx: Ctx, args: argparse.Namespace) -> dict:
+    """The configs[2] ensemble (same rows, same initial data, strong scaling) under the OTHER fluxes, boundary kinds and
+    equations of the path: device-resident throughput, launches per step, and the first
+    rows after W + K steps against the C restatement bound to the same scheme."""
+    torch = ctx.torch
+    from oracle import c_oracle
+    from oracle.c_oracle import COracle
+    from pyshocks_b200.ensemble import EnsembleSolver
+
+    h = (DOMAIN[1] - DOMAIN[0]) / N_CELLS
+    r0, rows = shard(args.batch, ctx.rank, ctx.world)
+    nx = N_CELLS + 2 * GHOSTS
+    coef_h = ensemble_coefficients(args.batch, 20261017)[r0 : r0 + rows]
+    coef = torch.from_numpy(coef_h).to(ctx.dev)
+    u0 = device_initial_condition(coef, N_CELLS, GHOSTS, nx, ctx.dev)
+    nsample = min(8, rows)
+    u0_sample = u0[:nsample].cpu().numpy()
+    x = (np.arange(N_CELLS) + 0.5) / N_CELLS
+    vi = 0.2 + np.sin(2.0 * np.pi * x + 0.3)  # changes sign; ghost cells = periodic images
+    vel = np.concatenate([vi[N_CELLS - GHOSTS :], vi, vi[:GHOSTS]])
+    ghost = np.array([0.31, -0.12, 0.05, -0.22, 0.17, 0.08])
+    c_oracle.set_threads(max(1, host_threads() // ctx.world))
+    out = []
+    for eq, flux, bc, alpha in SCHEMES:
+        kw: dict = {}
+        if eq != "burgers":
+            kw["velocity"] = vel
+        if alpha != 1.0:  # nu = df ** (alpha - 1) per face (scalar.py:231-234)
+            xc = DOMAIN[0] + (DOMAIN[1] - DOMAIN[0]) * (np.arange(nx) - GHOSTS + 0.5) / N_CELLS
+            kw["nu"] = np.diff(xc) ** (alpha - 1.0)
+        gh = None if bc == "periodic" else (ghost * (h if bc == "neumann" else 1.0))
+        solver = EnsembleSolver(equation=eq, flux=flux, rec="wenojs53", bc=bc, n=N_CELLS, g=GHOSTS, dx=h, eps=EPS,
+                                batch=rows, math="fast", device=ctx.dev, **kw)
+        if gh is not None:
+            solver.hp.set_ghost(gh)
+        dt_host = CFL * h / 3.0 / (float(kw["nu"].max()) if "nu" in kw else 1.0)
+        dt = torch.full((1,), dt_host, dtype=torch.float64, device=ctx.dev)
+        solver.load(u0)
+        solver.solve_fixed_dt(None, dt, args.warmup)
+        l0 = solver.launches
+        ms = timed_steps(ctx, lambda k, s=solver, d=dt: s.solve_fixed_dt(None, d, k), args.steps)
+        launches = (solver.launches - l0) / args.steps
+        co = COracle(equation=eq, flux=flux, rec="wenojs53", bc=bc, n=N_CELLS, g=GHOSTS, batch=nsample, dx=h, eps=EPS,
+                     **kw)
+        if gh is not None:
+            co.set_ghost(gh)
+        ref = co.solve_fixed_dt(u0_sample, dt_host, args.warmup + args.steps)
+        got = solver.u[:nsample].cpu().numpy()
+        i = slice(GHOSTS, GHOSTS + N_CELLS)
+        rel = float(np.abs(got[:, i] - ref[:, i]).max() / np.abs(ref[:, i]).max())
+        rel = ctx.max_over_ranks([rel if np.isfinite(rel) else 1e300])[0]
+        out.append({"scheme": f"{eq}/{flux}/{bc}" + ("" if alpha == 1.0 else f"/alpha={alpha}"),
+                    "value": args.batch * N_CELLS * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
+                    "launches_per_step": launches, "parity_max_rel": rel})
+        del solver
+        torch.cuda.empty_cache()
+    del u0
+    torch.cuda.empty_cache()
+    return {"unit": UNIT, "rows_total": args.batch, "cells": N_CELLS, "steps": args.steps, "scaling": "strong",
+            "parity": f"first {nsample} rows of every rank after W + K steps against oracle/psk_oracle.c bound to the same "
+                      "scheme, max over ranks", "list": out}
+
+
 # }}}
 
 # {{{ single huge grid (configs[3])
@@ -788,6 +860,7 @@ def run_ours(args: argparse.Namespace) -> None:
     sub("slab", lambda: measure_slab(ctx, args, n_global=args.cells or (1 << 30), transport=args.transport,
                                      steps=max(args.steps, 10), warmup=args.warmup))
     sub("adjoint", lambda: measure_adjoint(ctx, args, batch_total=4096, n=8192, nsteps=args.adjoint_steps))
+    sub("schemes", lambda: measure_schemes(ctx, args))
     if ctx.rank == 0:
         line.update(subs)
         if not args.no_cpu_baseline:
@@ -900,7 +973,7 @@ def main() -> None:
     ap.add_argument("--adjoint-steps", type=int, default=1000, help="steps of the adjoint sub-record (configs[4]: 1000)")
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--batch", type=int, default=BATCH, help="rows of the WHOLE ensemble (default: the named config)")
-    ap.add_argument("--skip", default="", help="comma list of sub-records to skip: weak,slab,adjoint")
+    ap.add_argument("--skip", default="", help="comma list of sub-records to skip: weak,slab,adjoint,schemes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="slab / adjoint workloads: skip the oracle checks")
     args = ap.parse_args()

@@ -1149,7 +1149,13 @@ __device__ __forceinline__ void lf_send_stage_max(LfExchange *x, int lane, int c
       mx = b > mx ? b : mx;
     }
   mx = warp_max_bits_redux(mx);
-  if (static_cast<unsigned>(lane) < cluster_size_x()) {  // lane r: to CTA r of the cluster
+  const unsigned nc = cluster_size_x();
+  if (nc == 1) {  // a row of one CTA: a plain store and an arrival (the mbarrier then counts the windows, not bytes)
+    if (lane == 0) {
+      x->vals[stage][chunk] = mx;
+      asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&x->mbar[stage])) : "memory");
+    }
+  } else if (static_cast<unsigned>(lane) < nc) {  // lane r: to CTA r of the cluster
     const unsigned dst = cluster_map(smem_u32(&x->vals[stage][chunk]), static_cast<unsigned>(lane));
     const unsigned bar = cluster_map(smem_u32(&x->mbar[stage]), static_cast<unsigned>(lane));
     asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(dst), "l"(mx), "r"(bar)
@@ -1191,12 +1197,18 @@ step_lf_cluster_kernel(const StepParams p) {
 
   const bool skip = p.active != nullptr && p.active[row] == 0;  // finished row (the whole cluster agrees)
   if (threadIdx.x == 0 && !skip) {  // one transaction barrier per stage: 8 bytes from every window of the row
+    const bool solo = cluster_size_x() == 1;  // (a row of one CTA: one arrival per window instead, see lf_send_stage_max)
 #pragma unroll
     for (int s = 0; s < 3; ++s) {
       const unsigned bar = smem_u32(&xch.mbar[s]);
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8u * static_cast<unsigned>(p.chunks_per_row))
-                   : "memory");
+      if (solo) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(static_cast<unsigned>(p.chunks_per_row)) : "memory");
+      } else {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                     "r"(8u * static_cast<unsigned>(p.chunks_per_row))
+                     : "memory");
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }

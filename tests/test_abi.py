@@ -133,3 +133,15 @@ def test_no_cpu_fallback_without_the_library(tmp_path: pathlib.Path) -> None:
     res = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True)
     assert res.returncode != 0
     assert "no CPU fallback" in res.stderr
+
+
+def test_static_instruction_counts_cover_the_kernels_bench_reports_on() -> None:
+    """profiles/sass_counts.json (regenerated by every build) must hold the whole-step, stage and reverse kernels:
+    bench.py's FP64-pipe roofline uses the whole-step count and would otherwise fall back to the stage kernels'"""
+    import json
+    import pathlib
+
+    d = json.loads((pathlib.Path(__file__).resolve().parents[1] / "profiles" / "sass_counts.json").read_text())
+    for key in ("step_fused", "step_fused_stages", "stage1", "stage2", "stage3", "reverse_step"):
+        assert d["kernels"].get(key), key
+    assert d["kernels"]["step_fused"][0]["fp64"] > 800

@@ -31,8 +31,8 @@ OUT = ROOT / "profiles" / "sass_counts.json"
 
 # demangled-name prefixes of the kernels bench.py reports on
 WANTED = {
-    "step_fused": "void psk::step_warp_fused_kernel<6, 0, false, 128, 3, false>",
-    "step_fused_stages": "void psk::step_warp_fused_kernel<6, 0, false, 128, 3, true>",
+    "step_fused": "void psk::step_warp_fused_kernel<6, 0, false, 128, 3, false, 0, 0, false>",
+    "step_fused_stages": "void psk::step_warp_fused_kernel<6, 0, false, 128, 3, true, 0, 0, false>",
     "stage1": "void psk::stage_warp_fast_share_kernel<0, 0, 1, false, 0>",
     "stage2": "void psk::stage_warp_fast_share_kernel<0, 0, 2, false, 0>",
     "stage3": "void psk::stage_warp_fast_share_kernel<0, 0, 3, false, 0>",
@@ -64,6 +64,9 @@ def main() -> None:
                 "ldl": c["LDL"], "stl": c["STL"], "bra": c["BRA"], "total": len(ks[name]),
                 "resources": regs.get(name, ""),
             })
+    missing = [key for key in WANTED if key not in out["kernels"]]
+    if missing:  # a template signature changed: bench.py would silently fall back to other counts
+        raise SystemExit(f"tools/sass_counts.py: no kernel in {LIB.name} matches {[WANTED[k] for k in missing]}")
     OUT.write_text(json.dumps(out, indent=1) + "\n")
     print(f"wrote {OUT} ({sum(len(v) for v in out['kernels'].values())} kernels)")
 

@@ -30,6 +30,9 @@ CASES = [
 if os.environ.get("PSK_LF_WPC"):  # windows per CTA of the Lax-Friedrichs cluster kernel (tuning switch)
     from pyshocks_b200 import _lib
     assert _lib.lib().psk_set_stage_variant(8000 + int(os.environ["PSK_LF_WPC"])) == 0
+if os.environ.get("PSK_STEP_VARIANT"):  # CTA shape of the whole-step kernel (tuning switch)
+    from pyshocks_b200 import _lib
+    assert _lib.lib().psk_set_stage_variant(7000 + int(os.environ["PSK_STEP_VARIANT"])) == 0
 ONLY = sys.argv[1:]  # e.g. "neumann": the cases whose equation / flux / boundary kind is named
 for eq, flux, bc, *rest in CASES:
     alpha = rest[0] if rest else 1.0

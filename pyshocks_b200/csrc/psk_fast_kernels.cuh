@@ -33,7 +33,7 @@ inline FastGeometry fast_geometry(int n, int wpc_max) {
   FastGeometry geo;
   geo.chunks_per_row = (n + 119) / 120;
   int wpc = 8, best_waste = 1 << 30;
-  for (int w = wpc_max; w >= 4; --w) {
+  for (int w = wpc_max; w >= (wpc_max < 4 ? wpc_max : 4); --w) {
     const int waste = ((geo.chunks_per_row + w - 1) / w) * w - geo.chunks_per_row;
     if (waste < best_waste) { best_waste = waste; wpc = w; }
   }

@@ -16,6 +16,11 @@ from pyshocks_b200 import burgers  # noqa: E402
 from pyshocks_b200.reconstruction import make_reconstruction_from_name  # noqa: E402
 from pyshocks_b200.scalar import PeriodicBoundary  # noqa: E402
 
+import os  # noqa: E402
+
+if os.environ.get("PSK_FAST_WPC"):  # warps per CTA of the specialised stage kernels (tuning switch)
+    from pyshocks_b200 import _lib
+    assert _lib.lib().psk_set_stage_variant(4000 + int(os.environ["PSK_FAST_WPC"])) == 0
 B, N, G = 16384, 4096, 3
 grid = ps.make_uniform_cell_grid(a=-1.5, b=1.5, n=N, nghosts=G)
 scheme = burgers.Rusanov(rec=make_reconstruction_from_name("wenojs53"), alpha=1.0)

@@ -1322,30 +1322,53 @@ int launch_step_lf(const StepParams &q0, int n, int batch, cudaStream_t st) {
   constexpr int R = 6, kMaxWarps = 12;
   StepParams q = q0;
   q.chunks_per_row = (n + StepGeometry<R>::kEmit - 1) / StepGeometry<R>::kEmit;
-  int wpc = g_lf_wpc;
-  if (wpc * 8 < q.chunks_per_row) wpc = (q.chunks_per_row + 7) / 8;
-  if (wpc > kMaxWarps || q.g > 16) return PSK_E_UNSUPPORTED;  // rows beyond 8 x 12 x 172 = 16512 cells
-  if (wpc > q.chunks_per_row) wpc = q.chunks_per_row;
-  const int cx = (q.chunks_per_row + wpc - 1) / wpc;
+  if (q.g > 16) return PSK_E_UNSUPPORTED;
   unsigned gy, gz;
   if (!split_rows(batch, gy, gz)) return PSK_E_UNSUPPORTED;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(cx), gy, gz);
-  cfg.blockDim = dim3(static_cast<unsigned>(wpc * 32));
-  cfg.dynamicSmemBytes = 0;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = static_cast<unsigned>(cx);
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  // (CTAs of up to 4 windows: 16 warps per SM within 128 registers; longer rows: one large CTA per SM)
-  if (wpc <= 4)
-    PSK_CUDA_OK(cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 128, 4, NU>, q));
-  else
-    PSK_CUDA_OK(cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 384, 1, NU>, q));
+  // try 0: small CTAs in a cluster of up to 16 (beyond the portable 8: rows of 5505 .. 11 008 cells keep the 4-warp
+  // CTAs that way); try 1: the portable cluster of at most 8 CTAs, as many windows per CTA as that takes
+  static bool big_clusters_ok = true;
+  for (int attempt = big_clusters_ok ? 0 : 1; attempt < 2; ++attempt) {
+    const int cmax = attempt == 0 ? 16 : 8;
+    int wpc = g_lf_wpc;
+    if (wpc * cmax < q.chunks_per_row) wpc = (q.chunks_per_row + cmax - 1) / cmax;
+    if (wpc > kMaxWarps) return PSK_E_UNSUPPORTED;  // rows beyond 8 x 12 x 172 = 16512 cells
+    if (wpc > q.chunks_per_row) wpc = q.chunks_per_row;
+    const int cx = (q.chunks_per_row + wpc - 1) / wpc;
+    if (attempt == 0 && (cx <= 8 || wpc > 4)) continue;  // nothing gained over the portable shape
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(cx), gy, gz);
+    cfg.blockDim = dim3(static_cast<unsigned>(wpc * 32));
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(cx);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // (CTAs of up to 4 windows: 16 warps per SM within 128 registers; longer rows: one large CTA per SM)
+    cudaError_t err;
+    if (wpc <= 4) {
+      auto kernel = step_lf_cluster_kernel<R, WITH_MAX, BCK, 128, 4, NU>;
+      if (cx > 8) {
+        err = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (err == cudaSuccess) err = cudaLaunchKernelEx(&cfg, kernel, q);
+      } else {
+        err = cudaLaunchKernelEx(&cfg, kernel, q);
+      }
+    } else {
+      err = cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 384, 1, NU>, q);
+    }
+    if (err == cudaSuccess) return PSK_OK;
+    if (attempt == 0) {  // this device does not place clusters of that size: never ask again
+      (void)cudaGetLastError();
+      big_clusters_ok = false;
+      continue;
+    }
+    PSK_CUDA_OK(err);
+  }
   return PSK_OK;
 }
 

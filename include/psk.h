@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PSK_VERSION 103 /* 0.1.3: psk_ssprk33_step_adjoint */
+#define PSK_VERSION 104 /* 0.1.4: psk_ssprk33_step_adjoint_bc */
 
 typedef void *psk_stream_t; /* cudaStream_t */
 
@@ -252,7 +252,7 @@ int psk_ssprk33_step_stages(const psk_desc *d, const double *u, double *k1, doub
  * Boundary kind NONE with g >= 16 ghost cells: the row is a SLAB of a larger grid, the ghost cells of u and p_in
  * hold the neighbouring slabs' edge cells (the caller's exchange, e.g. psk_halo_push) and p_out is the slab's
  * part of the gradient -- the transposed stencil needs no "send back and add", every slab gathers.
- * Burgers + Rusanov (nu = 1) + WENO-JS5, FAST math, periodic or NONE, 16-byte aligned rows, n even;
+ * Burgers + Rusanov (nu = 1) + WENO-JS5, FAST math, periodic or NONE (DIRICHLET: see below), 16-byte aligned rows, n even;
  * PSK_E_UNSUPPORTED elsewhere (recompute with psk_ssprk33_step_stages and call
  * psk_ssprk33_stage_adjoint three times instead).  k1_out / k2_out: optional (both or neither), the
  * recomputed stage values of the interior cells, bit-identical to psk_ssprk33_stage.
@@ -260,6 +260,19 @@ int psk_ssprk33_step_stages(const psk_desc *d, const double *u, double *k1, doub
 int psk_ssprk33_step_adjoint(const psk_desc *d, const double *u, const double *p_in, const double *dt,
                              int64_t dt_stride, double *p_out, double *k1_out, double *k2_out,
                              psk_stream_t stream);
+
+/* psk_ssprk33_step_adjoint on DIRICHLET rows (scalar.py:418-427; the boundary kind of the reference's own
+ * burgers-adjoint template, drivers/burgers-adjoint.py:68-97): the ghost cells of the stage inputs u, k1, k2 take
+ * the data of the stage times t, t + dt, t + dt / 2 (ghost3: three blocks laid out as in psk_ssprk33_step_bc;
+ * NULL: d->ghost for all three), and since these data do not depend on the state no cotangent lives on them:
+ *     p_out = (d advance(dt, u)[interior] / d u[interior])^T p_in[interior].
+ * Only interior cells of p_in are read (its ghost cells count as zero -- what apply_boundary with homogeneous
+ * Dirichlet data makes of the adjoint variable after every step, timestepping.py:208-209) and only interior
+ * cells of p_out are written.  g = 3; otherwise the conditions, options and status codes of
+ * psk_ssprk33_step_adjoint, whose plain form also accepts DIRICHLET rows with d->ghost. */
+int psk_ssprk33_step_adjoint_bc(const psk_desc *d, const double *u, const double *p_in, const double *dt,
+                                int64_t dt_stride, const double *ghost3, double *p_out, double *k1_out,
+                                double *k2_out, psk_stream_t stream);
 
 /* A/B switch of psk_ssprk33_step_adjoint: cells per lane of its windows (12, 16, 20, 24; 0 = automatic). */
 int psk_set_reverse_variant(int variant);

@@ -109,6 +109,7 @@ def _load() -> ct.CDLL:
         "psk_ssprk33_steps_tape": ([D, vp, i64, ct.c_int, vp, vp, vp], ct.c_int),
         "psk_ssprk33_step_stages": ([D, vp, vp, vp, vp, vp, i64, vp], ct.c_int),
         "psk_ssprk33_step_adjoint": ([D, vp, vp, vp, i64, vp, vp, vp, vp], ct.c_int),
+        "psk_ssprk33_step_adjoint_bc": ([D, vp, vp, vp, i64, vp, vp, vp, vp, vp], ct.c_int),
         "psk_set_reverse_variant": ([ct.c_int], ct.c_int),
         "psk_step_control": ([i32, f64, f64, f64, vp, vp, vp, vp, vp, vp, vp], ct.c_int),
         "psk_solve_rows": ([D, vp, ct.c_int, f64, f64, f64, f64, ct.c_int, vp, vp, vp, vp, vp], ct.c_int),
@@ -145,7 +146,7 @@ if os.environ.get("PSK_STAGE_VARIANT"):  # A/B measurements only
 EXPORTS = (
     "psk_version", "psk_status_string", "psk_last_cuda_error", "psk_set_stage_variant", "psk_set_adjoint_variant", "psk_apply_boundary",
     "psk_reconstruct", "psk_numerical_flux", "psk_apply_operator", "psk_max_abs",
-    "psk_ssprk33_stage", "psk_rhs_axpby", "psk_ssprk33_stage_lf", "psk_ssprk33_step", "psk_ssprk33_step_bc", "psk_ssprk33_steps_tape", "psk_ssprk33_step_stages", "psk_ssprk33_step_adjoint", "psk_set_reverse_variant", "psk_step_control", "psk_solve_rows", "psk_solve_rows_tables", "psk_ssprk33_adjoint_sweep", "psk_dfma_probe", "psk_apply_operator_vjp",
+    "psk_ssprk33_stage", "psk_rhs_axpby", "psk_ssprk33_stage_lf", "psk_ssprk33_step", "psk_ssprk33_step_bc", "psk_ssprk33_steps_tape", "psk_ssprk33_step_stages", "psk_ssprk33_step_adjoint", "psk_ssprk33_step_adjoint_bc", "psk_set_reverse_variant", "psk_step_control", "psk_solve_rows", "psk_solve_rows_tables", "psk_ssprk33_adjoint_sweep", "psk_dfma_probe", "psk_apply_operator_vjp",
     "psk_ssprk33_stage_adjoint", "psk_p2p_alloc", "psk_p2p_free", "psk_p2p_open", "psk_p2p_close",
     "psk_halo_push", "psk_halo_wait", "psk_ssprk33_stage_p2p", "psk_ssprk33_step_p2p",
 )

@@ -59,6 +59,11 @@ struct RevParams {
   double *dbg_k1, *dbg_k2;  // optional: the recomputed stage values of the stored cells (or nullptr)
   int bc_none;              // 1: a slab of a larger grid -- window cells beyond the row ends are the row's STORED ghost
                             // cells (g >= 16, filled by the neighbouring slabs) instead of the periodic images
+  // Dirichlet rows (reverse_step_kernel<.., DIR = true>; scalar.py:418-427): the three ghost cells per side of the
+  // stage inputs u, k1, k2 hold the data of the stage times t, t + dt, t + dt / 2 (timestepping.py:314-319), block
+  // s of `ghost3` at ghost3 + s * ghost_block, row r at + r * ghost_ld, left ghost cells first (psk_ssprk33_step_bc)
+  const double *ghost3;
+  int64_t ghost_ld, ghost_block;
 };
 
 constexpr int kRevHalo = 16;   // invalid window cells per side (15 needed)
@@ -380,9 +385,41 @@ __device__ __forceinline__ void rev_adjoint_stage(const int C, const int MODE, c
 
 // ---------------------------------------------------------------------------
 // run cells -2 .. C + 1 of one global array into a window array (periodic images beyond the row ends)
+// Dirichlet rows: the value of the window cell c < 0 or c >= n of a STATE array -- the boundary data of its stage in
+// the three ghost cells, the outermost one repeated beyond them (cells no stored result depends on; finite filler)
+__device__ __forceinline__ double rev_dirichlet_value(const double *__restrict__ gh, int c, int n) {
+  int k = (c < 0) ? c + 3 : c - n + 3;
+  k = k < 0 ? 0 : (k > 5 ? 5 : k);
+  return gh[k];
+}
+
+// Dirichlet rows, lanes whose run reaches beyond the row: the cells beyond [0, n) of a state array take the data
+// `gh` of its stage (apply_boundary at the top of the next right-hand side, schemes.py:343); of a cotangent array
+// (gh == nullptr) they are zero -- the boundary data do not depend on the state
+__device__ __forceinline__ void rev_dirichlet_fix(const int C, const LaneArray D, const double *__restrict__ gh, int r0,
+                                                  int n) {
+#pragma unroll 1
+  for (int j = -2; j < C + 2; ++j) {
+    const int c = r0 + j;
+    if (c < 0 || c >= n) D.st1(j, gh != nullptr ? rev_dirichlet_value(gh, c, n) : 0.0);
+  }
+}
+
 template <int CM>
 __device__ __forceinline__ void rev_load_run(const int C, const double *__restrict__ src, int64_t base, int r0, int n,
-                                             bool inside, const LaneArray D, int none_g = 0) {
+                                             bool inside, const LaneArray D, int none_g = 0, bool dir = false,
+                                             const double *__restrict__ gh = nullptr) {
+  if (dir && !inside) {  // Dirichlet row end: interior cells as stored, boundary data (state) or zero (cotangent) beyond
+#pragma unroll 1
+    for (int j = -2; j < C + 2; ++j) {
+      const int c = r0 + j;
+      double v;
+      if (c >= 0 && c < n) v = src[base + c];
+      else v = (gh != nullptr) ? rev_dirichlet_value(gh, c, n) : 0.0;
+      D.st1(j, v);
+    }
+    return;
+  }
   if (none_g > 0 && !inside) {  // slab: stored ghost cells; further out never reaches a stored cell
 #pragma unroll 1
     for (int j = -2; j < C + 2; ++j) {
@@ -411,7 +448,7 @@ __device__ __forceinline__ void rev_load_run(const int C, const double *__restri
   }
 }
 
-template <int CM, int MINB>
+template <int CM, int MINB, bool DIR = false>
 __global__ void __launch_bounds__(32, MINB)
 reverse_step_kernel(const RevParams p) {
   using Geo = RevGeometry<CM>;
@@ -428,8 +465,16 @@ reverse_step_kernel(const RevParams p) {
   const int r0 = tile * Geo::kEmit - kRevHalo + C * lane;  // ring coordinate of the lane's first cell
   const int none_g = p.bc_none ? p.g : 0;
   const bool inside = (r0 - 2 >= -none_g) && (r0 + C + 2 <= n + none_g);
+  // Dirichlet rows: the boundary data of this row at the three stage times
+  const double *gh0 = nullptr, *gh1 = nullptr, *gh2 = nullptr;
+  if (DIR) {
+    gh0 = p.ghost3 + static_cast<int64_t>(row) * p.ghost_ld;
+    gh1 = gh0 + p.ghost_block;
+    gh2 = gh1 + p.ghost_block;
+  }
+  const bool fix = DIR && !inside;
 
-  rev_load_run<CM>(C, p.u, base, r0, n, inside, P0, none_g);
+  rev_load_run<CM>(C, p.u, base, r0, n, inside, P0, none_g, DIR, gh0);
 #ifndef PSK_HOST_EMU
   if (inside) {  // p' is needed after the recomputation: have its lines on their way
 #pragma unroll 1
@@ -443,7 +488,10 @@ reverse_step_kernel(const RevParams p) {
 
   // ---- recomputation of the stage values (timestepping.py:314-317): P0 = u, P1 = k1, P2 = k2
 #pragma unroll 1
-  for (int st = 0; st < 2; ++st) rev_forward_stage(C, st == 1, st == 0 ? P0 : P1, st == 0 ? P1 : P2, P0, cdt, eps9);
+  for (int st = 0; st < 2; ++st) {
+    rev_forward_stage(C, st == 1, st == 0 ? P0 : P1, st == 0 ? P1 : P2, P0, cdt, eps9);
+    if (fix) rev_dirichlet_fix(C, st == 0 ? P1 : P2, st == 0 ? gh1 : gh2, r0, n);
+  }
   if (p.dbg_k1 != nullptr) {
 #pragma unroll 1
     for (int j = 0; j < C; ++j) {
@@ -461,10 +509,12 @@ reverse_step_kernel(const RevParams p) {
   const double hs = 0.5 * p.invdx * dt;
 #pragma unroll 1
   for (int ph = 0; ph < 3; ++ph) {
-    if (ph != 1) rev_load_run<CM>(C, ph == 0 ? p.pin : p.u, base, r0, n, inside, ph == 0 ? P0 : P2, none_g);
+    if (ph != 1)
+      rev_load_run<CM>(C, ph == 0 ? p.pin : p.u, base, r0, n, inside, ph == 0 ? P0 : P2, none_g, DIR, ph == 0 ? nullptr : gh0);
     const double cv = (ph == 0) ? (2.0 / 3.0) : ((ph == 1) ? 0.25 : 1.0);
     const LaneArray X = (ph == 1) ? P1 : P2, V = (ph == 0) ? P0 : ((ph == 1) ? P2 : P1), OUT = (ph == 0) ? P2 : ((ph == 1) ? P1 : P0);
     rev_adjoint_stage(C, ph == 0 ? 1 : (ph == 1 ? 0 : 2), X, V, OUT, P0, cv, cv * hs, eps9, park);
+    if (fix && ph != 2) rev_dirichlet_fix(C, OUT, nullptr, r0, n);  // no cotangent lives on the boundary data
   }
 
   // ---- p of the stored window cells

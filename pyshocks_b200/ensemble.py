@@ -344,7 +344,7 @@ class AdjointEnsemble:
         # stage values then never touch HBM, so the tape holds states only and the segment can be shorter
         can = solver.hp.reverse_step_supported()
         if fused_reverse and not can:
-            raise ValueError("the fused reverse step needs burgers + rusanov (alpha = 1) + wenojs53, fast math, periodic rows, even n")
+            raise ValueError("the fused reverse step needs burgers + rusanov (alpha = 1) + wenojs53, fast math, periodic or Dirichlet rows, even n")
         self.fused_reverse = can if fused_reverse is None else bool(fused_reverse)
         self.reverse_mode = ("1 launch per reverse step (psk_ssprk33_step_adjoint: recompute + 3 adjoint stages fused)"
                              if self.fused_reverse else

@@ -645,25 +645,45 @@ class HotPath:
         return True
 
     def reverse_step_supported(self) -> bool:
-        """whether :meth:`reverse_step_fused` exists for this scheme (the conditions of psk_ssprk33_step_adjoint;
-        the arrays must also be 16-byte aligned with an even row stride, which EnsembleSolver guarantees)"""
+        """whether :meth:`reverse_step_fused` exists for this scheme (the conditions of psk_ssprk33_step_adjoint /
+        psk_ssprk33_step_adjoint_bc; the arrays must also be 16-byte aligned with an even row stride, which
+        EnsembleSolver guarantees)"""
         return (self.equation == "burgers" and self.flux == "rusanov" and self.rec == "wenojs53" and self.math == "fast"
-                and ((self.bc == "periodic" and self.g >= 3) or (self.bc == "none" and self.g >= 16))
+                and ((self.bc == "periodic" and self.g >= 3) or (self.bc == "none" and self.g >= 16)
+                     or (self.bc == "dirichlet" and self.g == 3))
                 and self._nu is None and self.n % 2 == 0 and self.n >= 8)
 
     def reverse_step_fused(self, u: torch.Tensor, p: torch.Tensor, dt: torch.Tensor, out: torch.Tensor, *,
-                           stages: tuple[torch.Tensor, torch.Tensor] | None = None) -> bool:
+                           stages: tuple[torch.Tensor, torch.Tensor] | None = None,
+                           ghosts: Sequence[np.ndarray | torch.Tensor] | torch.Tensor | None = None) -> bool:
         """``out = (d advance(dt, u) / d u)^T p`` for one SSPRK33 step from the checkpointed state ``u`` in ONE
         launch (``psk_ssprk33_step_adjoint``: ``k1, k2`` recomputed and the three adjoint stages applied inside
-        the kernel; timestepping.py:198-209 without the dense Jacobian).  Interior cells only (periodic rings);
-        ``stages``: optional arrays that receive the recomputed ``k1, k2``.  ``False`` -- nothing launched --
-        outside its configuration (the caller then runs :meth:`ssprk33_step_adjoint`)."""
+        the kernel; timestepping.py:198-209 without the dense Jacobian).  Interior cells only (periodic rings;
+        Dirichlet rows -- ``psk_ssprk33_step_adjoint_bc``, ``ghosts`` as in :meth:`step_fused` -- whose boundary
+        data carry no cotangent: the ghost cells of ``p`` count as zero); ``stages``: optional arrays that receive the
+        recomputed ``k1, k2``.  ``False`` -- nothing launched -- outside its configuration (the caller then runs
+        :meth:`ssprk33_step_adjoint`)."""
         batch, ld = self._state(u)
         for a in (p, out) + (tuple(stages) if stages is not None else ()):
             if L.rows_of(a)[2] != ld:
                 raise ValueError("all arrays must share one row stride")
         d = self.desc(batch, ld)
         k1, k2 = stages if stages is not None else (None, None)
+        if self.bc == "dirichlet":
+            g3 = self.ghost3(ghosts)
+            if g3 is None:
+                raise ValueError("Dirichlet rows need boundary data (set_ghost or ghosts=)")
+            if g3.dim() == 3 and g3.shape[1] != batch:
+                raise ValueError("per-row ghost data does not match the batch size")
+            d.ghost, d.ghost_ld = L.ptr(g3), (0 if g3.dim() == 2 else 2 * self.g)
+            rc = L.lib().psk_ssprk33_step_adjoint_bc(
+                ct.byref(d), L.ptr(u), L.ptr(p), L.ptr(dt), 0 if dt.numel() == 1 else 1, L.ptr(g3), L.ptr(out),
+                L.ptr(k1), L.ptr(k2), L.stream_ptr(),
+            )
+            if rc == L.E_UNSUPPORTED:
+                return False
+            L.check("psk_ssprk33_step_adjoint_bc", rc)
+            return True
         rc = L.lib().psk_ssprk33_step_adjoint(
             ct.byref(d), L.ptr(u), L.ptr(p), L.ptr(dt), 0 if dt.numel() == 1 else 1, L.ptr(out), L.ptr(k1), L.ptr(k2),
             L.stream_ptr(),

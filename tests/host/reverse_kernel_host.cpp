@@ -48,20 +48,24 @@ void run_grid(unsigned gx, unsigned gy, Body body) {
 template <int C>
 void run(psk::RevParams p, int batch) {
   psk::rev_tiling(p.n, C, p.tiles_per_row, p.c_last);
-  run_grid(static_cast<unsigned>(p.tiles_per_row), static_cast<unsigned>(batch),
-           [&]() { psk::reverse_step_kernel<C, 1>(p); });
+  run_grid(static_cast<unsigned>(p.tiles_per_row), static_cast<unsigned>(batch), [&]() {
+    if (p.ghost3 != nullptr) psk::reverse_step_kernel<C, 1, true>(p);
+    else psk::reverse_step_kernel<C, 1>(p);
+  });
 }
 
 }  // namespace
 
 extern "C" {
 
-// p_out = (d advance / d u)^T p_in on periodic rows (interior cells), launched like launch_reverse<C>
+// p_out = (d advance / d u)^T p_in on periodic rows (interior cells) or, with ghost3, Dirichlet rows; launched like
+// launch_reverse<C>
 int emu_reverse_step(int C, int n, int g, int batch, long long ld, double dx, double eps, const double *u,
                      const double *pin, const double *dt, int dt_stride, double *pout, double *k1, double *k2,
-                     int bc_none) {
+                     int bc_none, const double *ghost3, long long ghost_ld, long long ghost_block) {
   psk::RevParams p{};
   p.bc_none = bc_none;
+  p.ghost3 = ghost3; p.ghost_ld = ghost_ld; p.ghost_block = ghost_block;  // Dirichlet rows (ghost3 != NULL)
   p.u = u; p.pin = pin; p.pout = pout; p.dt = dt; p.dt_stride = dt_stride; p.ld = ld;
   p.invdx = 1.0 / dx; p.eps = eps; p.n = n; p.g = g;
   p.dbg_k1 = k1; p.dbg_k2 = k2;

@@ -195,10 +195,12 @@ def test_optimisation_loop_recovers_an_initial_condition() -> None:
     assert torch.equal(J0, J1) and torch.equal(g0, g1)
 
 
-def test_adjoint_ensemble_on_dirichlet_rows() -> None:
-    """Dirichlet rows: the forward sweep runs psk_ssprk33_step_bc (one launch per step), the reverse sweep recomputes
-    k1, k2 with the same kernel (one launch) and applies three adjoint stage launches; against autograd through the
-    torch twin with the same (time-independent) boundary data"""
+@pytest.mark.parametrize("fused_reverse", [False, True])
+def test_adjoint_ensemble_on_dirichlet_rows(fused_reverse: bool) -> None:
+    """Dirichlet rows: the forward sweep runs psk_ssprk33_step_bc (one launch per step); the reverse sweep either
+    recomputes k1, k2 with the same kernel (one launch) and applies three adjoint stage launches, or (the default)
+    runs psk_ssprk33_step_adjoint_bc, one launch per reverse step; against autograd through the torch twin with
+    the same (time-independent) boundary data"""
     from pyshocks_b200.ensemble import AdjointEnsemble, EnsembleSolver
 
     batch, n, nsteps, g = 3, 96, 8, 3
@@ -211,10 +213,12 @@ def test_adjoint_ensemble_on_dirichlet_rows() -> None:
                             eps=1e-12, batch=batch)
     solver.hp.set_ghost(ghost)
     dt = 0.3 * grid.h / np.abs(u0).max()
-    adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=3)
-    assert not adj.fused_reverse
+    adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=3, fused_reverse=None if fused_reverse else False)
+    assert adj.fused_reverse == fused_reverse
     J, grad = adj.gradient_half_l2(torch.from_numpy(u0).cuda())
     assert adj._fused is True  # the forward sweep took the whole-step kernel
+    if fused_reverse:  # forward nsteps + recomputed states inside the segments + one launch per reverse step
+        assert adj.launches == nsteps + (2 + 2 + 1) + nsteps
     scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53"))
     xg = np.concatenate([grid.x[:g], grid.x[-g:]])
     bc = po.Dirichlet(ga=lambda t, x: np.interp(x, xg, ghost))
@@ -226,3 +230,63 @@ def test_adjoint_ensemble_on_dirichlet_rows() -> None:
             x = tt.ssprk33_advance(lambda t_, y: tt.apply_operator(scheme, grid, bc, t_, y), dt, 0.0, x)
         (gb,) = torch.autograd.grad(0.5 * (x[i] ** 2).sum(), u)
         assert max_rel(grad[b].cpu().numpy()[i], gb.numpy()[i]) < 1e-12
+
+
+@pytest.mark.parametrize("n,variant", [(256, 0), (250, 12), (1000, 16), (1000, 20), (4096, 0), (74, 12), (600, 24), (8192, 0)])
+def test_fused_reverse_step_on_dirichlet_rows_matches_the_five_launch_path(n: int, variant: int) -> None:
+    """psk_ssprk33_step_adjoint_bc with per-row boundary data that differ at the three stage times (t, t + dt,
+    t + dt / 2: timestepping.py:314-319) against psk_ssprk33_step_bc (stage outputs) + 3 x psk_ssprk33_stage_adjoint
+    with the data of each stage: recomputed stage values bit-identical, cotangent equal to round-off, and the
+    torch twin with the same boundary function for one row"""
+    from pyshocks_b200 import _lib as L
+    from pyshocks_b200.ensemble import EnsembleSolver
+
+    batch, g = 4, 3
+    grid = po.make_grid(-1.5, 1.5, n, g)
+    rng = np.random.default_rng(n + 1)
+    xh = (grid.x - grid.a) / (grid.b - grid.a)
+    u0 = np.stack([0.2 * b + np.sin(2 * np.pi * xh + b) + 0.3 * np.cos(6 * np.pi * xh) for b in range(batch)])
+    dt = 0.3 * grid.h / np.abs(u0).max()
+    xg = np.concatenate([grid.x[:g], grid.x[-g:]])
+    amp = rng.uniform(0.2, 0.9, size=batch)
+
+    def data(b: int, t: float, x: np.ndarray) -> np.ndarray:
+        return amp[b] * np.cos(2.0 * x - 40.0 * t) + 0.1 * b
+
+    g3 = np.stack([np.stack([data(b, t, xg) for b in range(batch)]) for t in (0.0, dt, 0.5 * dt)])
+    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="dirichlet", n=n, g=g, dx=grid.h,
+                            eps=1e-12, batch=batch)
+    hp = solver.hp
+    assert hp.reverse_step_supported()
+    assert L.lib().psk_set_reverse_variant(variant) == 0
+    try:
+        u, k1, k2, k1f, k2f, p, out, lam2, lam1, ref = solver.new_states(10)
+        u.copy_(torch.from_numpy(u0).cuda())
+        i = slice(g, g + n)
+        p[:, i] = torch.from_numpy(rng.standard_normal((batch, n))).cuda()
+        dtt = torch.full((1,), dt, dtype=torch.float64, device="cuda")
+        g3d = torch.from_numpy(g3).cuda()
+        out.fill_(float("nan"))
+        assert hp.reverse_step_fused(u, p, dtt, out, stages=(k1f, k2f), ghosts=g3d)
+        # five launches: the stage values from the whole-step kernel, then the three transposed stages, each with
+        # the boundary data of its own stage time
+        k1r, k2r, _ = hp.ssprk33_step(u, dtt, ghosts=[g3[0], g3[1], g3[2]], keep_stages=True)
+        assert torch.equal(k1f[:, i], k1r[:, i]) and torch.equal(k2f[:, i], k2r[:, i])
+        hp.set_ghost(g3[2])
+        hp.stage_adjoint(k2r, p, dtt, 2.0 / 3.0, lam2)
+        hp.set_ghost(g3[1])
+        hp.stage_adjoint(k1r, lam2, dtt, 1.0 / 4.0, lam1)
+        hp.set_ghost(g3[0])
+        hp.stage_adjoint(u, lam1, dtt, 1.0, ref, acc=p, c_acc=1.0 / 3.0, acc2=lam2, c_acc2=3.0 / 4.0)
+        # both are ~1e-12 from the exact derivative (cells next to an extremum, beta ~ eps); the maximum over four
+        # rows of 8192 cells came out at 2.5e-12
+        assert max_rel(out[:, i].cpu().numpy(), ref[:, i].cpu().numpy()) < (2e-12 if n <= 4096 else 5e-12)
+        assert bool(torch.isnan(out[:, :g]).all()) and bool(torch.isnan(out[:, g + n : g + n + g]).all())  # not written
+        if n <= 1000:
+            scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53"))
+            b = batch - 1
+            bc = po.Dirichlet(lambda t, x, b=b: data(b, t, x))
+            want = tt.step_vjp(scheme, grid, bc, dt, 0.0, u0[b], p[b, : n + 2 * g].cpu().numpy())
+            assert max_rel(out[b, i].cpu().numpy(), want[i]) < 3e-12
+    finally:
+        L.lib().psk_set_reverse_variant(0)

@@ -34,7 +34,8 @@ def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
                     str(ROOT / "tests" / "host" / "reverse_kernel_host.cpp")], check=True)
     lib = ct.CDLL(str(out))
     dp = ct.POINTER(ct.c_double)
-    lib.emu_reverse_step.argtypes = [ct.c_int] * 4 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int, dp, dp, dp, ct.c_int]
+    lib.emu_reverse_step.argtypes = ([ct.c_int] * 4 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int, dp, dp, dp,
+                                      ct.c_int, dp, ct.c_longlong, ct.c_longlong])
     lib.emu_reverse_step.restype = ct.c_int
     return lib
 
@@ -62,7 +63,8 @@ def _aligned(batch: int, n: int) -> tuple[np.ndarray, int, int]:
     return raw[off : off + batch * ld].reshape(batch, ld), col0, ld
 
 
-def _run(emu, C: int, n: int, u: np.ndarray, p: np.ndarray, dt: float, stages: bool = False):
+def _run(emu, C: int, n: int, u: np.ndarray, p: np.ndarray, dt: float, stages: bool = False,
+         ghost3: np.ndarray | None = None):
     batch = u.shape[0]
     nx = n + 2 * G
     bufs = []
@@ -77,7 +79,8 @@ def _run(emu, C: int, n: int, u: np.ndarray, p: np.ndarray, dt: float, stages: b
     U, P, OUT, K1, K2 = bufs
     dts = np.full(batch, dt)
     rc = emu.emu_reverse_step(C, n, G, batch, ld, 3.0 / n, EPS, _p(U), _p(P), _p(dts), 1, _p(OUT),
-                              _p(K1) if stages else None, _p(K2) if stages else None, 0)
+                              _p(K1) if stages else None, _p(K2) if stages else None, 0,
+                              _p(ghost3), 0 if ghost3 is None else 2 * G, 0 if ghost3 is None else batch * 2 * G)
     assert rc == 0
     return (OUT, K1, K2) if stages else OUT
 
@@ -159,9 +162,50 @@ def test_fused_reverse_step_on_slabs_with_sixteen_ghost_cells(emu, C: int, world
             bufs.append(v)
         U, P, OUT = bufs
         dts = np.full(1, dt)
-        assert emu.emu_reverse_step(C, nl, g16, 1, ld, 3.0 / n, EPS, _p(U), _p(P), _p(dts), 1, _p(OUT), None, None, 1) == 0
+        assert emu.emu_reverse_step(C, nl, g16, 1, ld, 3.0 / n, EPS, _p(U), _p(P), _p(dts), 1, _p(OUT), None, None, 1,
+                                    None, 0, 0) == 0
         assert np.isnan(OUT[0, :g16]).all() and np.isnan(OUT[0, g16 + nl :]).all()
         parts.append(OUT[0, g16 : g16 + nl].copy())
         first += nl
     got = np.concatenate(parts)
     assert np.abs(got - whole).max() < 1e-13 * np.abs(whole).max()
+
+
+@pytest.mark.parametrize("C", [8, 12, 16, 20, 24])
+@pytest.mark.parametrize("n,kind,tol", [(1000, "smooth", 3e-12), (74, "smooth", 3e-12), (300, "tophat", 2e-9),
+                                        (1300, "smooth", 3e-12)])
+def test_fused_reverse_step_on_dirichlet_rows(emu, C: int, n: int, kind: str, tol: float) -> None:
+    """Dirichlet rows (scalar.py:418-427) with data that change from stage to stage (t, t + dt, t + dt / 2,
+    timestepping.py:314-319): the ghost cells of u, k1, k2 take the data of their stage inside the kernel and carry
+    no cotangent; against reverse-mode differentiation of the reference arithmetic with the same boundary
+    function, interior cells (the ghost cells of p' are zero, those of the result are not written)"""
+    rng = np.random.default_rng(3 * n + C)
+    batch = 2
+    u = np.stack([_state(n, kind, 10 * n + b) for b in range(batch)])
+    p = rng.standard_normal((batch, n + 2 * G))
+    p[:, :G] = 0.0
+    p[:, n + G :] = 0.0
+    dt = 0.3 * (3.0 / n)
+    grid = po.make_grid(-1.5, 1.5, n, G)
+    scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53", EPS))
+    xg = np.concatenate([grid.x[:G], grid.x[-G:]])
+    amp = rng.uniform(0.2, 0.9, size=batch)
+
+    def data(b: int, t: float) -> np.ndarray:
+        return amp[b] * np.cos(2.0 * xg - 40.0 * t) + 0.1 * b
+
+    # block s of ghost3: the data of every row at the stage time s (t, t + dt, t + dt / 2), rows 2 G apart
+    ghost3 = np.stack([np.stack([data(b, t) for b in range(batch)]) for t in (0.0, dt, 0.5 * dt)]).copy()
+    out, k1, k2 = _run(emu, C, n, u, p, dt, stages=True, ghost3=ghost3)
+    i = slice(G, G + n)
+    assert np.isfinite(out[:, i]).all()
+    assert np.isnan(out[:, :G]).all() and np.isnan(out[:, n + G :]).all()
+    for b in range(batch):
+        bc = po.Dirichlet(lambda t, x, b=b: amp[b] * np.cos(2.0 * x - 40.0 * t) + 0.1 * b)
+        ref = tt.step_vjp(scheme, grid, bc, dt, 0.0, u[b], p[b])
+        err = np.abs(out[b, i] - ref[i]).max() / np.abs(ref[i]).max()
+        assert err < tol, (b, err)
+        # the recomputed stage values next to the row ends saw the boundary data of their stage
+        w = po.apply_boundary(bc, grid, 0.0, u[b])
+        r1 = u[b] + dt * po.apply_operator(scheme, grid, bc, 0.0, w)
+        assert np.abs(k1[b, i] - r1[i]).max() < 1e-13 * np.abs(r1).max()

@@ -864,7 +864,9 @@ def run_ours(args: argparse.Namespace) -> None:
     if ctx.rank == 0:
         line.update(subs)
         if not args.no_cpu_baseline:
-            res = cpu_port_steps(3, 1)
+            # the reference arm's protocol (`--impl reference`: K steps after W warm-up, one step per call) on a shorter
+            # run; 3 steps after 1 warm-up read 20-30 % low (first-touch page faults, OpenMP threads spinning up)
+            res = cpu_port_steps(10, 3)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)
     ctx.close()

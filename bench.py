@@ -18,7 +18,8 @@ same process right after the headline:
   `slab`     BASELINE configs[3]: ONE periodic Burgers grid of 2^30 cells, slab-decomposed over
              the N ranks, ghost cells exchanged through NVLink peer memory;
   `adjoint`  BASELINE configs[4]: B = 4096 x N = 8192 ensemble (rows sharded over the ranks),
-             1000 fixed-dt steps forward with a device tape + the reverse sweep: gradients/s;
+             1000 fixed-dt steps forward with a device tape + the reverse sweep: gradients/s
+             (`adjoint.dirichlet`: the same ensemble on Dirichlet rows, 100 steps);
   `parity`   64 sampled rows of the timed ensemble state against the C restatement of the
              reference (oracle/psk_oracle.c) on the identical initial rows.
 
@@ -712,9 +713,11 @@ def measure_slab(ctx: Ctx, args: argparse.Namespace, *, n_global: int, transport
 # {{{ adjoint (configs[4])
 
 
-def adjoint_twin_check(dev, n: int, h: float, dt: float, u0_rows: np.ndarray, nsteps: int, kw: dict) -> dict:
+def adjoint_twin_check(dev, n: int, h: float, dt: float, u0_rows: np.ndarray, nsteps: int, kw: dict,
+                       ghost: np.ndarray | None = None) -> dict:
     """The product's gradient of J = 1/2 ||u(T)||^2 on a few rows of the benchmarked ensemble over a few
-    steps against reverse-mode differentiation of the reference arithmetic (oracle/torch_twin.py)."""
+    steps against reverse-mode differentiation of the reference arithmetic (oracle/torch_twin.py).
+    `ghost`: (rows, 2 g) Dirichlet data (time-independent) -- Dirichlet rows instead of periodic ones."""
     import torch
 
     from oracle import pyshocks_oracle as po
@@ -722,16 +725,19 @@ def adjoint_twin_check(dev, n: int, h: float, dt: float, u0_rows: np.ndarray, ns
     from pyshocks_b200.ensemble import AdjointEnsemble, EnsembleSolver
 
     rows = u0_rows.shape[0]
-    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic", n=n, g=GHOSTS,
-                            dx=h, eps=EPS, batch=rows, device=dev)
+    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic" if ghost is None else "dirichlet",
+                            n=n, g=GHOSTS, dx=h, eps=EPS, batch=rows, device=dev)
+    if ghost is not None:
+        solver.hp.set_ghost(ghost)
     adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, **(kw | {"segment": 2}))
     _, grad = adj.gradient_half_l2(torch.from_numpy(u0_rows).to(dev))
     grad = grad.cpu().numpy()
     grid = po.make_grid(DOMAIN[0], DOMAIN[1], n, GHOSTS)
     scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53"))
-    bc = po.Periodic()
+    xg = np.concatenate([grid.x[:GHOSTS], grid.x[-GHOSTS:]])
     worst = 0.0
     for b in range(rows):
+        bc = po.Periodic() if ghost is None else po.Dirichlet(ga=lambda t, x, b=b: np.interp(x, xg, ghost[b]))
         u = torch.from_numpy(u0_rows[b]).clone().requires_grad_(True)
         x = u
         for _ in range(nsteps):
@@ -743,6 +749,61 @@ def adjoint_twin_check(dev, n: int, h: float, dt: float, u0_rows: np.ndarray, ns
     return {"max_rel": worst, "tol": 1.0e-12, "ok": bool(worst <= 1.0e-12),
             "what": f"dJ/du0 of {rows} rows of this ensemble over {nsteps} steps (same kernels, two-level tape) against "
                     "torch autograd through oracle/torch_twin.py (the stand-in for jax.jacfwd of the reference's advance)"}
+
+
+def measure_adjoint_dirichlet(ctx: Ctx, *, batch_total: int, n: int, nsteps: int, kw: dict, check: bool) -> dict:
+    """configs[4] on DIRICHLET rows -- the boundary kind of the reference's own burgers-adjoint template
+    (drivers/burgers-adjoint.py:68-97) -- over `nsteps` steps with every state kept: whole-step forward launches
+    (psk_ssprk33_step_bc) and one launch per reverse step (psk_ssprk33_step_adjoint_bc).  Same rows and initial data
+    as the periodic record; every row's boundary data are its own mean value c_b (time-independent)."""
+    torch = ctx.torch
+    from pyshocks_b200.ensemble import AdjointEnsemble, EnsembleSolver
+
+    dev, rank, world = ctx.dev, ctx.rank, ctx.world
+    first, rows = shard(batch_total, rank, world)
+    h = (DOMAIN[1] - DOMAIN[0]) / n
+    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="dirichlet", n=n, g=GHOSTS,
+                            dx=h, eps=EPS, batch=rows, device=dev)
+    coef_host = ensemble_coefficients(batch_total, 20261018)
+    ghost_host = np.repeat(coef_host[first : first + rows, :1], 2 * GHOSTS, axis=1)
+    solver.hp.set_ghost(ghost_host)
+    coef = torch.from_numpy(coef_host[first : first + rows]).to(dev)
+    u0 = device_initial_condition(coef, n, GHOSTS, solver.nx, dev)
+    umax = u0.abs().max()
+    if world > 1:
+        ctx.dist.all_reduce(umax, op=ctx.dist.ReduceOp.MAX)
+    dt = CFL * h / float(umax)
+    adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=1, **kw)
+    small = AdjointEnsemble(solver, nsteps=2, dt=dt, segment=1, **kw)
+    small.gradient_half_l2(u0)  # warm-up
+    del small
+    ctx.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    uT = adj.forward(u0)
+    ev[1].record()
+    pT = adj.lam1
+    pT.zero_()
+    pT[:, GHOSTS : GHOSTS + n] = uT[:, GHOSTS : GHOSTS + n]
+    grad = adj.backward(pT)
+    ev[2].record()
+    ctx.barrier()
+    fwd_ms, bwd_ms = ctx.max_over_ranks([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])])
+    out = {
+        "workload": f"the same ensemble on Dirichlet rows (boundary data = the row's mean value), {nsteps} steps, every state kept",
+        "steps": nsteps, "forward_ms": fwd_ms, "reverse_ms": bwd_ms, "reverse_mode": adj.reverse_mode,
+        "gradients_per_s_at_these_steps": batch_total / ((fwd_ms + bwd_ms) * 1e-3),
+        "adjoint_cell_updates_per_s": batch_total * n * nsteps / (bwd_ms * 1e-3),
+        "forward_cell_updates_per_s": batch_total * n * nsteps / (fwd_ms * 1e-3),
+        "grad_finite": bool(torch.isfinite(grad).all()), "gpu_launches": adj.launches,
+    }
+    u0_rows = u0[:2].cpu().numpy()
+    del adj, grad, uT, pT, u0, solver
+    torch.cuda.empty_cache()
+    if check and rank == 0:
+        out["parity"] = adjoint_twin_check(dev, n, h, dt, u0_rows, 6, kw, ghost=ghost_host[:2])
+    torch.cuda.empty_cache()
+    return out
 
 
 def measure_adjoint(ctx: Ctx, args: argparse.Namespace, *, batch_total: int, n: int, nsteps: int, check: bool = True) -> dict:
@@ -815,6 +876,14 @@ def measure_adjoint(ctx: Ctx, args: argparse.Namespace, *, batch_total: int, n: 
                                   "segment, profiles/traffic.json) x adjoint cell-updates/s x 2 flop per pipe slot, against "
                                   f"the DFMA peak measured in this run; ncu reports the pipe {tj['reverse_kernel'].get('fp64_pipe_pct', 0):.1f} % busy "
                                   "for the kernel alone"}
+    try:
+        dirichlet = measure_adjoint_dirichlet(ctx, batch_total=batch_total, n=n, nsteps=min(nsteps, 100), kw=kw, check=check)
+    except Exception as exc:  # noqa: BLE001  (must not take the named record with it)
+        import traceback
+
+        traceback.print_exc()
+        dirichlet = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
     return {
         "metric": "adjoint gradients/s", "value": batch_total / ((fwd_ms + bwd_ms) * 1e-3), "unit": "gradients/s",
         "n_gpus": world, "steps": nsteps, "scaling": "strong",
@@ -831,6 +900,7 @@ def measure_adjoint(ctx: Ctx, args: argparse.Namespace, *, batch_total: int, n: 
                          "note": "reverse sweep only, 144 B per cell-step (SURVEY.md 8d per-stage streaming design); the "
                                  "segment recompute of the two-level tape is extra work inside reverse_ms, not extra credit"},
         "gpu_launches": launches,
+        "dirichlet": dirichlet,
     }
 
 

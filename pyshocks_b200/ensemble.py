@@ -12,7 +12,6 @@ Rows are stored with a padded stride so that the first interior cell of every ro
 
 from __future__ import annotations
 
-import ctypes as ct
 from dataclasses import dataclass
 
 import numpy as np

@@ -14,7 +14,7 @@ import pathlib
 import torch
 
 CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
-LIB_PATH = CSRC / "libpsk.so"
+LIB_PATH = pathlib.Path(os.environ["PSK_LIB"]) if os.environ.get("PSK_LIB") else CSRC / "libpsk.so"  # PSK_LIB: A/B builds
 
 # enum values of include/psk.h
 EQ_BURGERS, EQ_ADVECTION, EQ_CONTINUITY = 0, 1, 2

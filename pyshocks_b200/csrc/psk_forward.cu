@@ -1039,9 +1039,14 @@ __global__ void step_control_kernel(int batch, double theta, double cfl_scale, d
 }
 
 // ---- whole-step kernel (step_warp_fused_kernel): cells per lane and CTA shape, tuning switch
-// psk_set_stage_variant(7000 + 10 R + shape): 62 = R 6, 128 x 3 (default), 60 = R 6, 256 x 2, 82 = R 8, 192 x 2;
+// psk_set_stage_variant(7000 + 10 R + shape): 66 = R 6, 32 x 16 (default), 61 = R 6, 32 x 12, 62 = R 6, 128 x 3, 60 = R 6, 256 x 2,
+// 82 = R 8, 192 x 2;
 // 7000 = off (three stage launches)
-static int g_step_variant = 61;  // R = 6, CTAs of ONE warp, 12 per SM (130 registers): 9.0e10 cell-updates/s on B200
+#ifndef PSK_STEP_MINB
+#define PSK_STEP_MINB 16  // resident one-warp CTAs per SM the whole-step kernels are compiled for (16: within 128 registers)
+#endif
+static int g_step_variant = 66;  // R = 6, CTAs of ONE warp, 16 per SM (126 registers): 9.16e10 cell-updates/s on B200 (61: 12 per
+                                 // SM at 130 registers, 9.03e10)
                                  // (62: CTAs of 128 threads, 3 per SM: 0.5 % slower -- a CTA waits for its slowest warp)
 
 template <int R, int FLUX, int THREADS, int MINB, bool STAGES = false, int EQ = PSK_EQ_BURGERS, int BCK = 0, bool NU = false>
@@ -1482,7 +1487,10 @@ step_warp_fused_p2p_kernel(const StepParams p, const HaloLink h) {
 
 template <int FLUX>
 int launch_step_p2p(const StepParams &q, const HaloLink &h, bool with_max, cudaStream_t st) {
-  constexpr int kThreads = 128, kMinB = 3;
+#ifndef PSK_P2P_MINB
+#define PSK_P2P_MINB 4  // CTAs of four warps per SM: 4 = within 128 registers (16 warps per SM), 3 = up to 168
+#endif
+  constexpr int kThreads = 128, kMinB = PSK_P2P_MINB;
   int wpc = kThreads / 32;
   if (q.chunks_per_row < wpc) wpc = q.chunks_per_row;
   const unsigned gx = static_cast<unsigned>((q.chunks_per_row + wpc - 1) / wpc);
@@ -1553,10 +1561,10 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
 #define PSK_STEP_BC(FL, EQ)                                                                                      \
   do {                                                                                                           \
     if (k1_out != nullptr)                                                                                       \
-      return neumann ? launch_step_shape<6, FL, 32, 12, true, EQ, 2>(q, d->n, batch, false, st)                  \
-                     : launch_step_shape<6, FL, 32, 12, true, EQ, 1>(q, d->n, batch, false, st);                 \
-    return neumann ? launch_step_shape<6, FL, 32, 12, false, EQ, 2>(q, d->n, batch, mxs, st)                     \
-                   : launch_step_shape<6, FL, 32, 12, false, EQ, 1>(q, d->n, batch, mxs, st);                    \
+      return neumann ? launch_step_shape<6, FL, 32, PSK_STEP_MINB, true, EQ, 2>(q, d->n, batch, false, st)                  \
+                     : launch_step_shape<6, FL, 32, PSK_STEP_MINB, true, EQ, 1>(q, d->n, batch, false, st);                 \
+    return neumann ? launch_step_shape<6, FL, 32, PSK_STEP_MINB, false, EQ, 2>(q, d->n, batch, mxs, st)                     \
+                   : launch_step_shape<6, FL, 32, PSK_STEP_MINB, false, EQ, 1>(q, d->n, batch, mxs, st);                    \
   } while (0)
     if (d->equation == PSK_EQ_ADVECTION) PSK_STEP_BC(kUp, PSK_EQ_ADVECTION);
     if (d->equation == PSK_EQ_CONTINUITY) PSK_STEP_BC(kUp, PSK_EQ_CONTINUITY);
@@ -1564,10 +1572,10 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     if (d->flux == PSK_FLUX_ENGQUIST_OSHER) PSK_STEP_BC(kEO, kB);
     if (d->nu != nullptr) {  // Rusanov with alpha != 1: nu of every face
       if (k1_out != nullptr)
-        return neumann ? launch_step_shape<6, kRus, 32, 12, true, kB, 2, true>(q, d->n, batch, false, st)
-                       : launch_step_shape<6, kRus, 32, 12, true, kB, 1, true>(q, d->n, batch, false, st);
-      return neumann ? launch_step_shape<6, kRus, 32, 12, false, kB, 2, true>(q, d->n, batch, mxs, st)
-                     : launch_step_shape<6, kRus, 32, 12, false, kB, 1, true>(q, d->n, batch, mxs, st);
+        return neumann ? launch_step_shape<6, kRus, 32, PSK_STEP_MINB, true, kB, 2, true>(q, d->n, batch, false, st)
+                       : launch_step_shape<6, kRus, 32, PSK_STEP_MINB, true, kB, 1, true>(q, d->n, batch, false, st);
+      return neumann ? launch_step_shape<6, kRus, 32, PSK_STEP_MINB, false, kB, 2, true>(q, d->n, batch, mxs, st)
+                     : launch_step_shape<6, kRus, 32, PSK_STEP_MINB, false, kB, 1, true>(q, d->n, batch, mxs, st);
     }
     PSK_STEP_BC(kRus, kB);
 #undef PSK_STEP_BC
@@ -1575,21 +1583,22 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
   if (d->equation != PSK_EQ_BURGERS) {  // periodic rows, upwind flux with the velocity's reconstruction
     if (k1_out != nullptr) return PSK_E_UNSUPPORTED;
     if (d->equation == PSK_EQ_ADVECTION)
-      return launch_step_shape<6, PSK_FLUX_UPWIND, 32, 12, false, PSK_EQ_ADVECTION, false>(q, d->n, batch, mx, st);
-    return launch_step_shape<6, PSK_FLUX_UPWIND, 32, 12, false, PSK_EQ_CONTINUITY, false>(q, d->n, batch, mx, st);
+      return launch_step_shape<6, PSK_FLUX_UPWIND, 32, PSK_STEP_MINB, false, PSK_EQ_ADVECTION, false>(q, d->n, batch, mx, st);
+    return launch_step_shape<6, PSK_FLUX_UPWIND, 32, PSK_STEP_MINB, false, PSK_EQ_CONTINUITY, false>(q, d->n, batch, mx, st);
   }
   if (k1_out != nullptr)  // stage values wanted (reverse sweep): Rusanov, default shape
-    return launch_step_shape<6, PSK_FLUX_RUSANOV, 32, 12, true>(q, d->n, batch, false, st);
+    return launch_step_shape<6, PSK_FLUX_RUSANOV, 32, PSK_STEP_MINB, true>(q, d->n, batch, false, st);
   // the other Burgers fluxes: default shape only
-  if (d->flux == PSK_FLUX_UPWIND) return launch_step_shape<6, PSK_FLUX_UPWIND, 32, 12>(q, d->n, batch, mx, st);
+  if (d->flux == PSK_FLUX_UPWIND) return launch_step_shape<6, PSK_FLUX_UPWIND, 32, PSK_STEP_MINB>(q, d->n, batch, mx, st);
   if (d->flux == PSK_FLUX_ENGQUIST_OSHER)
-    return launch_step_shape<6, PSK_FLUX_ENGQUIST_OSHER, 32, 12>(q, d->n, batch, mx, st);
+    return launch_step_shape<6, PSK_FLUX_ENGQUIST_OSHER, 32, PSK_STEP_MINB>(q, d->n, batch, mx, st);
   constexpr int kRus = PSK_FLUX_RUSANOV;
   switch (g_step_variant) {
     case 60: return launch_step_shape<6, kRus, 256, 2>(q, d->n, batch, mx, st);
     case 62: return launch_step_shape<6, kRus, 128, 3>(q, d->n, batch, mx, st);
     case 61: return launch_step_shape<6, kRus, 32, 12>(q, d->n, batch, mx, st);
     case 64: return launch_step_shape<6, kRus, 64, 6>(q, d->n, batch, mx, st);
+    case 66: return launch_step_shape<6, kRus, 32, 16>(q, d->n, batch, mx, st);  // 128 registers, 16 warps per SM
     case 82: return launch_step_shape<8, kRus, 192, 2>(q, d->n, batch, mx, st);
     default: return PSK_E_UNSUPPORTED;
   }
@@ -1614,9 +1623,9 @@ int psk_set_stage_variant(int variant) {
     g_lf_wpc = variant - 8000;
     return PSK_OK;
   }
-  if (variant >= 7000) {  // whole-step kernel (psk_ssprk33_step): 7061 (default) / 7062 / 7064 / 7060 / 7082 = cells per lane and CTA shape, 7000 = off
+  if (variant >= 7000) {  // whole-step kernel (psk_ssprk33_step): 7066 (default) / 7061 / 7062 / 7064 / 7060 / 7082 = cells per lane and CTA shape, 7000 = off
     const int v = variant - 7000;
-    if (v != 0 && v != 60 && v != 61 && v != 62 && v != 64 && v != 82) return PSK_E_INVALID;
+    if (v != 0 && v != 60 && v != 61 && v != 62 && v != 64 && v != 66 && v != 82) return PSK_E_INVALID;
     g_step_variant = v;
     return PSK_OK;
   }

@@ -31,8 +31,8 @@ OUT = ROOT / "profiles" / "sass_counts.json"
 
 # demangled-name prefixes of the kernels bench.py reports on
 WANTED = {
-    "step_fused": "void psk::step_warp_fused_kernel<6, 0, false, 32, 12, false, 0, 0, false>",
-    "step_fused_stages": "void psk::step_warp_fused_kernel<6, 0, false, 32, 12, true, 0, 0, false>",
+    "step_fused": "void psk::step_warp_fused_kernel<6, 0, false, 32, 16, false, 0, 0, false>",
+    "step_fused_stages": "void psk::step_warp_fused_kernel<6, 0, false, 32, 16, true, 0, 0, false>",
     "stage1": "void psk::stage_warp_fast_share_kernel<0, 0, 1, false, 0>",
     "stage2": "void psk::stage_warp_fast_share_kernel<0, 0, 2, false, 0>",
     "stage3": "void psk::stage_warp_fast_share_kernel<0, 0, 3, false, 0>",

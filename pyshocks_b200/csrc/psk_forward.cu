@@ -1599,6 +1599,8 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     case 61: return launch_step_shape<6, kRus, 32, 12>(q, d->n, batch, mx, st);
     case 64: return launch_step_shape<6, kRus, 64, 6>(q, d->n, batch, mx, st);
     case 66: return launch_step_shape<6, kRus, 32, 16>(q, d->n, batch, mx, st);  // 128 registers, 16 warps per SM
+    case 68: return launch_step_shape<6, kRus, 32, 20>(q, d->n, batch, mx, st);  // 96 registers, 21 warps per SM
+    case 69: return launch_step_shape<6, kRus, 32, 24>(q, d->n, batch, mx, st);
     case 82: return launch_step_shape<8, kRus, 192, 2>(q, d->n, batch, mx, st);
     default: return PSK_E_UNSUPPORTED;
   }
@@ -1625,7 +1627,7 @@ int psk_set_stage_variant(int variant) {
   }
   if (variant >= 7000) {  // whole-step kernel (psk_ssprk33_step): 7066 (default) / 7061 / 7062 / 7064 / 7060 / 7082 = cells per lane and CTA shape, 7000 = off
     const int v = variant - 7000;
-    if (v != 0 && v != 60 && v != 61 && v != 62 && v != 64 && v != 66 && v != 82) return PSK_E_INVALID;
+    if (v != 0 && v != 60 && v != 61 && v != 62 && v != 64 && v != 66 && v != 68 && v != 69 && v != 82) return PSK_E_INVALID;
     g_step_variant = v;
     return PSK_OK;
   }

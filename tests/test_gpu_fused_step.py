@@ -45,7 +45,7 @@ def _ic(batch: int, n: int, seed: int) -> torch.Tensor:
     return torch.from_numpy(u).cuda()
 
 
-@pytest.mark.parametrize("code", [7060, 7061, 7062, 7064, 7066, 7082])
+@pytest.mark.parametrize("code", [7060, 7061, 7062, 7064, 7066, 7068, 7082])
 @pytest.mark.parametrize("batch,n,nsteps", [(5, 4096, 7), (3, 1000, 4), (2, 172, 3), (4, 50, 5), (1, 16, 2)])
 def test_whole_step_equals_three_stage_launches(code: int, batch: int, n: int, nsteps: int) -> None:
     u0 = _ic(batch, n, seed=n + nsteps)

@@ -83,6 +83,36 @@ __device__ __forceinline__ LeanFace lean_face(double hG, double urj, double ulp,
   return o;
 }
 
+// The same face with the viscosity nu of the face (scalar.py:231-234: the speed is multiplied by grid.df ** (alpha - 1))
+__device__ __forceinline__ LeanFace lean_face_nu(double hG, double urj, double ulp, double wj, double wp, double nu) {
+  const unsigned long long bj = static_cast<unsigned long long>(__double_as_longlong(wj)) & 0x7fffffffffffffffull;
+  const unsigned long long bp = static_cast<unsigned long long>(__double_as_longlong(wp)) & 0x7fffffffffffffffull;
+  const double a = nu * __longlong_as_double(static_cast<long long>(bj > bp ? bj : bp));
+  LeanFace o;
+  o.gR = hG * (urj + a);
+  o.gL = hG * (ulp - a);
+  const double da = (hG * nu) * (urj - ulp);
+  const unsigned ej = bj > bp ? 0x3FF00000u : ((bj == bp && bj != 0ull) ? 0x3FE00000u : 0u);
+  const unsigned ep = bp > bj ? 0x3FF00000u : ((bj == bp && bp != 0ull) ? 0x3FE00000u : 0u);
+  o.dj = da * signed_unit(wj, ej);
+  o.dp = da * signed_unit(wp, ep);
+  return o;
+}
+
+// Global Lax-Friedrichs flux (scalar.py:258-278): the speed `a` = nu max |w| over the whole row is the same number at
+// every face, so a face has no direct terms on its two cells; `dj` carries the cotangent of the row's speed instead
+// (hG nu (urj - ulp): summed over the faces of the row into AdjParams::ga, distributed to the arg-max cells by
+// adjoint_boundary_kernel<true>), `dp` is zero
+__device__ __forceinline__ LeanFace lean_face_lf(double hG, double urj, double ulp, double speed, double nu) {
+  const double a = nu * speed;
+  LeanFace o;
+  o.gR = hG * (urj + a);
+  o.gL = hG * (ulp - a);
+  o.dj = (hG * nu) * (urj - ulp);
+  o.dp = 0.0;
+  return o;
+}
+
 // own cells of a lane: state, cotangent, linear part of the result; plus the one cell the
 // two edge lanes need beyond the shuffled halo (lane 0: cell c0 - 1, lane 31: cell c0 + R)
 struct LeanIn {
@@ -147,7 +177,8 @@ __device__ __forceinline__ void lean_load(const AdjParams &p, int row, int c0, i
 // slin: where the linear part was parked (shared memory, stride 128 doubles) or nullptr (in.lin);
 // RECOMP3: recompute the forward state of cell 3 before its faces instead of holding it since
 // the exchange at the top (39 more FP64 instructions per lane, 26 registers fewer in between)
-template <bool RECOMP3>
+// FLUX: PSK_FLUX_RUSANOV or PSK_FLUX_LAX_FRIEDRICHS; NU: AdjParams::nu holds the viscosity of every face (alpha != 1)
+template <bool RECOMP3, int FLUX = PSK_FLUX_RUSANOV, bool NU = false>
 __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, int c0, int lane, bool inside,
                                                    const LeanIn &in, const double *slin) {
   constexpr int R = 4;
@@ -174,12 +205,22 @@ __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, 
 
   // ---- (1/2) c_g dt (v_k - v_{k-1}) / dx for the faces of the lane; zero at the array ends
   const double hs = 0.5 * cgdt * p.invdx;
-  double hG[R + 1];
+  double hG[R + 1], nuf[R + 1];
 #pragma unroll
   for (int f = 0; f <= R; ++f) {
     const int k = g + c0 + f;  // array index of the face: between cells k - 1 and k
-    hG[f] = (k >= 1 && k <= nx - 1) ? (vc[f + 1] - vc[f]) * hs : 0.0;
+    const bool valid = (k >= 1 && k <= nx - 1);
+    hG[f] = valid ? (vc[f + 1] - vc[f]) * hs : 0.0;
+    nuf[f] = (NU && valid) ? p.nu[k - 1] : 1.0;
   }
+  constexpr bool kLF = FLUX == PSK_FLUX_LAX_FRIEDRICHS;
+  const double speed = kLF ? p.speed[row] : 0.0;
+  // the face between the window cells (f + 2 | f + 3)
+  auto face = [&](int f, double urj, double ulp, double wj, double wp) -> LeanFace {
+    if (kLF) return lean_face_lf(hG[f], urj, ulp, speed, nuf[f]);
+    if (NU) return lean_face_nu(hG[f], urj, ulp, wj, wp, nuf[f]);
+    return lean_face(hG[f], urj, ulp, wj, wp);
+  };
 
   // ---- first differences in sixths (t[k]: cells k, k+1 of the window) and (13/3) dd^2 + eps/9
   const double eps9 = p.eps * (1.0 / 9.0);
@@ -203,15 +244,15 @@ __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, 
   const double ur_left = __shfl_up_sync(kFull, ur3, 1);
   const double ul_right = __shfl_down_sync(kFull, ul0, 1);
 
-  const LeanFace f0 = lean_face(hG[0], ur_left, ul0, w[2], w[3]);
+  const LeanFace f0 = face(0, ur_left, ul0, w[2], w[3]);
   const Weno5State F1 = weno53_state(t[2], t[3], t[4], t[5], pq[2], pq[3], pq[4]);
-  const LeanFace f1 = lean_face(hG[1], w[3] + F0.uR, w[4] + F1.uL, w[3], w[4]);
-  o[0] = (f0.dp + f1.dj) + (f1.gR + f0.gL);
+  const LeanFace f1 = face(1, w[3] + F0.uR, w[4] + F1.uL, w[3], w[4]);
+  o[0] = kLF ? (f1.gR + f0.gL) : (f0.dp + f1.dj) + (f1.gR + f0.gL);
   weno53_vjp_acc(F0, t[1], t[2], t[3], t[4], f1.gR, f0.gL, Tk[0], Tk[1], Tk[2], Tk[3]);
 
   const Weno5State F2 = weno53_state(t[3], t[4], t[5], t[6], pq[3], pq[4], pq[5]);
-  const LeanFace f2 = lean_face(hG[2], w[4] + F1.uR, w[5] + F2.uL, w[4], w[5]);
-  o[1] = (f1.dp + f2.dj) + (f2.gR + f1.gL);
+  const LeanFace f2 = face(2, w[4] + F1.uR, w[5] + F2.uL, w[4], w[5]);
+  o[1] = kLF ? (f2.gR + f1.gL) : (f1.dp + f2.dj) + (f2.gR + f1.gL);
   weno53_vjp_acc(F1, t[2], t[3], t[4], t[5], f2.gR, f1.gL, Tk[1], Tk[2], Tk[3], Tk[4]);
 
   double t7b = t[7];
@@ -219,14 +260,22 @@ __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, 
   if (RECOMP3) asm volatile("" : "+d"(t7b));  // keeps the compiler from merging the two evaluations
 #endif
   const Weno5State F3b = RECOMP3 ? weno53_state(t[4], t[5], t[6], t7b, pq[4], pq[5], pq[6]) : F3;
-  const LeanFace f3 = lean_face(hG[3], w[5] + F2.uR, w[6] + F3b.uL, w[5], w[6]);
-  o[2] = (f2.dp + f3.dj) + (f3.gR + f2.gL);
+  const LeanFace f3 = face(3, w[5] + F2.uR, w[6] + F3b.uL, w[5], w[6]);
+  o[2] = kLF ? (f3.gR + f2.gL) : (f2.dp + f3.dj) + (f3.gR + f2.gL);
   weno53_vjp_acc(F2, t[3], t[4], t[5], t[6], f3.gR, f2.gL, Tk[2], Tk[3], Tk[4], Tk[5]);
 
-  const LeanFace f4 = lean_face(hG[4], RECOMP3 ? w[6] + F3b.uR : ur3, ul_right, w[6], w[7]);
-  o[3] = (f3.dp + f4.dj) + (f4.gR + f3.gL);
+  const LeanFace f4 = face(4, RECOMP3 ? w[6] + F3b.uR : ur3, ul_right, w[6], w[7]);
+  o[3] = kLF ? (f4.gR + f3.gL) : (f3.dp + f4.dj) + (f4.gR + f3.gL);
   weno53_vjp_acc(F3b, t[4], t[5], t[6], t7b, f4.gR, f3.gL, Tk[3], Tk[4], Tk[5], Tk[6]);
 
+  if (kLF) {
+    // cotangent of the row's speed: every face of the row once (faces 1..4 of the lanes that store; face 0 is the
+    // previous lane's face 4), already scaled by c_g dt like everything here (AdjParams::prescaled)
+    double ga_part = (lane >= 1 && lane <= 30) ? ((f1.dj + f2.dj) + (f3.dj + f4.dj)) : 0.0;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) ga_part += __shfl_xor_sync(kFull, ga_part, o2);
+    if (lane == 0) atomicAdd(p.ga + row, ga_part);
+  }
   // ---- contributions of the neighbour lanes' cells to the first differences around my cells
   const double fl5 = __shfl_up_sync(kFull, Tk[5], 1);
   const double fl6 = __shfl_up_sync(kFull, Tk[6], 1);
@@ -268,7 +317,7 @@ __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, 
 }
 
 // VAR bit 0: park the linear part in shared memory; bit 1: recompute the state of cell 3
-template <int MINB, int VAR>
+template <int MINB, int VAR, int FLUX = PSK_FLUX_RUSANOV, bool NU = false>
 __global__ void __launch_bounds__(128, MINB)
 adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
   constexpr int R = 4;
@@ -284,9 +333,9 @@ adjoint_lean_kernel(const AdjParams p, int chunks_per_row) {
     __shared__ double slin[4][128];
 #pragma unroll
     for (int r = 0; r < 4; ++r) slin[r][threadIdx.x] = in.lin[r];
-    lean_compute_store<(VAR & 2) != 0>(p, row, c0, lane, inside, in, &slin[0][threadIdx.x]);
+    lean_compute_store<(VAR & 2) != 0, FLUX, NU>(p, row, c0, lane, inside, in, &slin[0][threadIdx.x]);
   } else {
-    lean_compute_store<(VAR & 2) != 0>(p, row, c0, lane, inside, in, nullptr);
+    lean_compute_store<(VAR & 2) != 0, FLUX, NU>(p, row, c0, lane, inside, in, nullptr);
   }
 }
 

@@ -87,4 +87,55 @@ int emu_adjoint_lean(int variant, int n, int g, int batch, long long ld, double 
   return 0;
 }
 
+// The Lax-Friedrichs (flux = 1) and alpha != 1 (nu != NULL: the viscosity of every face) forms of the lean kernel, on
+// periodic (bck = 0) or Dirichlet (bck = 1, ghost: 2 g data per row) rows, followed by what adjoint_boundary_kernel
+// does on the GPU: the transpose of the periodic fill and, for Lax-Friedrichs, the cotangent of the row's speed
+// max |w| shared equally between the arg-max cells (ghost cells pass theirs on to the cells they copy; Dirichlet
+// data drop it).
+int emu_adjoint_lean_flux(int flux, int bck, int n, int g, int batch, long long ld, double dx, double eps, const double *x,
+                          const double *v, const double *dt, int dt_stride, double c_v, double c_g, const double *nu,
+                          const double *ghost, double *gspill, double *out) {
+  psk::AdjParams p{};
+  p.x = x; p.v = v; p.out = out; p.dt = dt; p.dt_stride = dt_stride;
+  p.c_v = c_v; p.c_g = c_g;
+  p.gspill = gspill;
+  p.nu = nu;
+  p.bc.ghost = ghost; p.bc.ghost_ld = ghost != nullptr ? 2 * g : 0;
+  p.bc.bc = bck == 0 ? PSK_BC_PERIODIC : PSK_BC_DIRICHLET; p.bc.n = n; p.bc.g = g; p.bc.nx = n + 2 * g;
+  p.ld = ld;
+  p.invdx = 1.0 / dx;
+  p.eps = eps;
+  p.prescaled = 1;
+  const int nx = n + 2 * g;
+  std::vector<double> speed(batch, 0.0), ga(batch, 0.0);
+  for (int row = 0; row < batch; ++row)
+    for (int i = 0; i < nx; ++i) speed[row] = std::fmax(speed[row], std::fabs(psk::load_w(p.bc, x + row * ld, row, i)));
+  p.speed = speed.data();
+  p.ga = ga.data();
+  const int chunks = (n + g + 119) / 120;
+  const int total = chunks + 1;
+  const int wpc = total < 4 ? total : 4;
+  const unsigned gx = static_cast<unsigned>((total + wpc - 1) / wpc);
+  void (*k)(const psk::AdjParams, int) = nullptr;
+  if (flux == 1) k = nu != nullptr ? &psk::adjoint_lean_kernel<4, 3, PSK_FLUX_LAX_FRIEDRICHS, true>
+                                   : &psk::adjoint_lean_kernel<4, 3, PSK_FLUX_LAX_FRIEDRICHS, false>;
+  else k = nu != nullptr ? &psk::adjoint_lean_kernel<4, 3, PSK_FLUX_RUSANOV, true> : &psk::adjoint_lean_kernel<4, 3>;
+  run_grid(gx, static_cast<unsigned>(batch), wpc, [&]() { k(p, chunks); });
+  auto source = [&](int i) { return (i >= g && i < nx - g) ? i : (bck == 0 ? (i < g ? i + n : i - n) : -1); };
+  for (int row = 0; row < batch; ++row) {
+    double *orow = out + static_cast<long long>(row) * ld;
+    if (bck == 0)
+      for (int kk = 0; kk < 2 * g; ++kk) orow[source(kk < g ? kk : nx - 2 * g + kk)] += gspill[static_cast<long long>(row) * 2 * g + kk];
+    if (flux == 1) {
+      int count = 0;
+      for (int i = 0; i < nx; ++i) count += std::fabs(psk::load_w(p.bc, x + row * ld, row, i)) == speed[row];
+      for (int i = 0; i < nx; ++i) {
+        const double wi = psk::load_w(p.bc, x + row * ld, row, i);
+        if (std::fabs(wi) == speed[row] && source(i) >= 0) orow[source(i)] += ga[row] / count * (wi > 0.0 ? 1.0 : (wi < 0.0 ? -1.0 : 0.0));
+      }
+    }
+  }
+  return 0;
+}
+
 }  // extern "C"

@@ -76,6 +76,18 @@ inline unsigned long long atomicMax(unsigned long long *addr, unsigned long long
   return old;
 }
 
+inline double atomicAdd(double *addr, double v) {  // only one lane per warp calls it in the kernels under test
+  unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+  unsigned long long old = __atomic_load_n(a, __ATOMIC_RELAXED), want;
+  double cur;
+  do {
+    std::memcpy(&cur, &old, 8);
+    const double sum = cur + v;
+    std::memcpy(&want, &sum, 8);
+  } while (!__atomic_compare_exchange_n(a, &old, want, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+  return cur;
+}
+
 inline long long __double_as_longlong(double x) {
   long long r;
   std::memcpy(&r, &x, 8);

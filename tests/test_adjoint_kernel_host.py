@@ -37,6 +37,9 @@ def emu(tmp_path_factory: pytest.TempPathFactory) -> ct.CDLL:
     lib.emu_adjoint_lean.argtypes = [ct.c_int] * 4 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
                                                       ct.c_double, ct.c_double, dp, ct.c_double, dp, ct.c_double, dp, dp]
     lib.emu_adjoint_lean.restype = ct.c_int
+    lib.emu_adjoint_lean_flux.argtypes = [ct.c_int] * 5 + [ct.c_longlong, ct.c_double, ct.c_double, dp, dp, dp, ct.c_int,
+                                                           ct.c_double, ct.c_double, dp, dp, dp, dp]
+    lib.emu_adjoint_lean_flux.restype = ct.c_int
     return lib
 
 
@@ -103,3 +106,34 @@ def test_lean_adjoint_stage_linear_terms(emu) -> None:
     assert np.abs(got - (2.0 / 3.0) * base).max() <= 1e-14 * np.abs(base).max()
     got = _run(emu, 3, n, x, v, dt, 0.25, 1.0, acc=acc, c_acc=-2.0)
     assert np.abs(got - (-2.0 * acc + 0.25 * v + (base - v))).max() <= 1e-14 * np.abs(base).max()
+
+
+@pytest.mark.parametrize("flux,alpha", [("lf", 1.0), ("lf", 0.995), ("rusanov", 0.995)])
+@pytest.mark.parametrize("bc", ["periodic", "dirichlet"])
+@pytest.mark.parametrize("n,kind,tol", [(250, "smooth", 1e-12), (121, "smooth", 1e-12), (500, "tophat", 1e-9)])
+def test_lean_adjoint_stage_with_the_global_speed_and_the_viscosity_of_every_face(emu, flux: str, alpha: float, bc: str,
+                                                                                  n: int, kind: str, tol: float) -> None:
+    """the Lax-Friedrichs (scalar.py:258-278) and alpha != 1 (scalar.py:231-234) forms of the lean kernel: the speed
+    cotangent summed over the faces of a row and handed to the arg-max cells, nu per face; periodic and Dirichlet rows"""
+    rng = np.random.default_rng(n + int(1000 * alpha))
+    batch = 2
+    x = np.stack([_state(n, kind, 10 * n + b) for b in range(batch)])
+    v = rng.standard_normal((batch, n + 2 * G))
+    dt = 0.3 * (3.0 / n)
+    grid = po.make_grid(-1.5, 1.5, n, G)
+    scheme = po.Scheme("burgers", flux, po.make_reconstruction("wenojs53", EPS), alpha=alpha)
+    nu = None if alpha == 1.0 else (np.diff(grid.x) ** (alpha - 1.0)).copy()
+    ghost = rng.uniform(-0.4, 0.4, size=(batch, 2 * G)) if bc == "dirichlet" else None
+    nx = n + 2 * G
+    out = np.full((batch, nx), np.nan)
+    gspill = np.zeros((batch, 2 * G))
+    dts = np.full(batch, dt)
+    assert emu.emu_adjoint_lean_flux(1 if flux == "lf" else 0, 0 if bc == "periodic" else 1, n, G, batch, nx, grid.h, EPS,
+                                     _p(x), _p(v), _p(dts), 1, 1.0, 1.0, _p(nu), _p(ghost), _p(gspill), _p(out)) == 0
+    assert np.isfinite(out).all()
+    xg = np.concatenate([grid.x[:G], grid.x[-G:]])
+    for b in range(batch):
+        obc = po.Periodic() if bc == "periodic" else po.Dirichlet(ga=lambda t, xx, b=b: np.interp(xx, xg, ghost[b]))
+        ref = v[b] + dt * tt.rhs_vjp(scheme, grid, obc, 0.0, x[b], v[b])
+        err = np.abs(out[b] - ref).max() / np.abs(ref).max()
+        assert err < tol, (flux, alpha, bc, b, err)

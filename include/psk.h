@@ -337,7 +337,7 @@ int psk_dfma_probe(double *out, int ctas, int iters, psk_stream_t stream);
  * rows, boundary condition included); what jax.vjp(apply_operator) returns, and the
  * building block of the reference's adjoint_step (timestepping.py:174, :205-206).  Every equation, flux and
  * reconstruction of the forward entry points, the ESWENO32 reconstruction and the Burgers ESWENO32 scheme included.
- * work: batch * (2 g + 2) doubles of scratch.  out must not alias u or v. */
+ * work: batch * (2 g + 3) doubles of scratch.  out must not alias u or v. */
 int psk_apply_operator_vjp(const psk_desc *d, const double *u, const double *v, double *out,
                            double *work, psk_stream_t stream);
 
@@ -348,7 +348,7 @@ int psk_apply_operator_vjp(const psk_desc *d, const double *u, const double *v, 
  *   lam1 = 1/4 (lam2 + dt J(k1)^T lam2)
  *   p    = 1/3 p' + 3/4 lam2 + (lam1 + dt J(u)^T lam1)
  * acc / acc2 may be NULL (their coefficient is then ignored).  dt as in
- * psk_ssprk33_stage.  work: batch * (2 g + 2) doubles of scratch.  out must not alias
+ * psk_ssprk33_stage.  work: batch * (2 g + 3) doubles of scratch.  out must not alias
  * x or v. */
 int psk_ssprk33_stage_adjoint(const psk_desc *d, const double *x, const double *v,
                               const double *dt, int64_t dt_stride, double c_v,

@@ -465,6 +465,15 @@ __global__ void adjoint_boundary_kernel(const AdjParams p) {
   if (LF) {
     // jnp.max(jnp.abs(w)): the cotangent is shared equally between the tied arg-max cells
     const double speed = p.speed[row];
+    // the lean kernel counted the arg-max cells and kept the index of one: a single one needs no scan of the row
+    if (p.amax != nullptr && p.amax[2 * row] == 1u) {
+      if (threadIdx.x == 0) {
+        const int i = static_cast<int>(p.amax[2 * row + 1]);
+        const int src = source(i);
+        if (src >= 0) atomicAdd(orow + src, cgdt * p.ga[row] * sign0(load_w(p.bc, xrow, row, i)));
+      }
+      return;
+    }
     __shared__ int count;
     if (threadIdx.x == 0) count = 0;
     __syncthreads();
@@ -589,6 +598,7 @@ static int run_adjoint(const psk_desc *d, const double *x, const double *v, cons
   p.c_acc2 = c_acc2;
   p.speed = work;
   p.ga = work + d->batch;
+  p.amax = nullptr;
   p.gspill = work + 2 * static_cast<int64_t>(d->batch);
   p.nu = d->nu;
   p.vel = d->velocity;
@@ -604,6 +614,9 @@ static int run_adjoint(const psk_desc *d, const double *x, const double *v, cons
     rc = launch_max_abs_public(d, x, 2, p.speed, st);
     if (rc != PSK_OK) return rc;
     PSK_CUDA_OK(cudaMemsetAsync(p.ga, 0, sizeof(double) * d->batch, st));
+    // (count, index) of the row's arg-max cells, behind the ghost-cell cotangents
+    p.amax = reinterpret_cast<unsigned *>(work + (2 + 2 * static_cast<int64_t>(d->g)) * d->batch);
+    PSK_CUDA_OK(cudaMemsetAsync(p.amax, 0, sizeof(double) * d->batch, st));
   }
   const int b = d->batch;
   if (d->equation == PSK_EQ_ADVECTION)

@@ -23,6 +23,8 @@ struct AdjParams {
   double c_v, c_g, c_acc, c_acc2;
   double *speed;   // [batch] global LF speed (input)
   double *ga;      // [batch] cotangent of the LF speed (accumulated here)
+  unsigned *amax;  // [batch][2] Lax-Friedrichs, lean kernel: how many cells of the row hold the speed max |w| and the
+                   // array index of one of them (adjoint_boundary_kernel scans the row only when there are several)
   double *gspill;  // [batch][2g] cotangents that landed on ghost cells
   const double *nu;
   const double *vel;
@@ -268,6 +270,17 @@ __device__ __forceinline__ void lean_compute_store(const AdjParams &p, int row, 
   o[3] = kLF ? (f4.gR + f3.gL) : (f3.dp + f4.dj) + (f4.gR + f3.gL);
   weno53_vjp_acc(F3b, t[4], t[5], t[6], t7b, f4.gR, f3.gL, Tk[3], Tk[4], Tk[5], Tk[6]);
 
+  if (kLF && p.amax != nullptr && lane >= 1 && lane <= 30) {
+    // the arg-max cells of the row among the cells this lane stores (ghost cells included, like jnp.max over the array)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = g + c0 + r;
+      if (i >= 0 && i < nx && fabs(w[3 + r]) == speed) {
+        atomicAdd(p.amax + 2 * row, 1u);
+        atomicMax(p.amax + 2 * row + 1, static_cast<unsigned>(i));
+      }
+    }
+  }
   if (kLF) {
     // cotangent of the row's speed: every face of the row once (faces 1..4 of the lanes that store; face 0 is the
     // previous lane's face 4), already scaled by c_g dt like everything here (AdjParams::prescaled)

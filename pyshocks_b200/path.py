@@ -231,7 +231,7 @@ class HotPath:
     # {{{ discrete adjoint
 
     def _adj_work(self, batch: int) -> torch.Tensor:
-        return self.workspace(f"adj@{torch.cuda.current_stream(self.device).cuda_stream}", (batch * (2 * self.g + 2),))
+        return self.workspace(f"adj@{torch.cuda.current_stream(self.device).cuda_stream}", (batch * (2 * self.g + 3),))
 
     def apply_operator_vjp(self, u: torch.Tensor, v: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """``J_L(u)^T v`` for ``L = apply_operator`` (what ``jax.vjp(apply_operator)`` returns)."""

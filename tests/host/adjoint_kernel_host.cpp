@@ -112,6 +112,8 @@ int emu_adjoint_lean_flux(int flux, int bck, int n, int g, int batch, long long 
     for (int i = 0; i < nx; ++i) speed[row] = std::fmax(speed[row], std::fabs(psk::load_w(p.bc, x + row * ld, row, i)));
   p.speed = speed.data();
   p.ga = ga.data();
+  std::vector<unsigned> amax(2 * static_cast<size_t>(batch), 0u);
+  p.amax = amax.data();
   const int chunks = (n + g + 119) / 120;
   const int total = chunks + 1;
   const int wpc = total < 4 ? total : 4;
@@ -126,9 +128,15 @@ int emu_adjoint_lean_flux(int flux, int bck, int n, int g, int batch, long long 
     double *orow = out + static_cast<long long>(row) * ld;
     if (bck == 0)
       for (int kk = 0; kk < 2 * g; ++kk) orow[source(kk < g ? kk : nx - 2 * g + kk)] += gspill[static_cast<long long>(row) * 2 * g + kk];
-    if (flux == 1) {
+    if (flux == 1 && amax[2 * row] == 1u) {  // a single arg-max cell: the index the kernel recorded, no scan
+      const int i = static_cast<int>(amax[2 * row + 1]);
+      const double wi = psk::load_w(p.bc, x + row * ld, row, i);
+      if (std::fabs(wi) != speed[row]) return -2;
+      if (source(i) >= 0) orow[source(i)] += ga[row] * (wi > 0.0 ? 1.0 : (wi < 0.0 ? -1.0 : 0.0));
+    } else if (flux == 1) {
       int count = 0;
       for (int i = 0; i < nx; ++i) count += std::fabs(psk::load_w(p.bc, x + row * ld, row, i)) == speed[row];
+      if (static_cast<unsigned>(count) != amax[2 * row]) return -3;  // the kernel counted every arg-max cell of the array once
       for (int i = 0; i < nx; ++i) {
         const double wi = psk::load_w(p.bc, x + row * ld, row, i);
         if (std::fabs(wi) == speed[row] && source(i) >= 0) orow[source(i)] += ga[row] / count * (wi > 0.0 ? 1.0 : (wi < 0.0 ? -1.0 : 0.0));

@@ -76,6 +76,13 @@ inline unsigned long long atomicMax(unsigned long long *addr, unsigned long long
   return old;
 }
 
+inline unsigned atomicAdd(unsigned *addr, unsigned v) { return __atomic_fetch_add(addr, v, __ATOMIC_RELAXED); }
+inline unsigned atomicMax(unsigned *addr, unsigned v) {
+  unsigned old = __atomic_load_n(addr, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(addr, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+  }
+  return old;
+}
 inline double atomicAdd(double *addr, double v) {  // only one lane per warp calls it in the kernels under test
   unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
   unsigned long long old = __atomic_load_n(a, __ATOMIC_RELAXED), want;

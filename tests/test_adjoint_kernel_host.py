@@ -54,6 +54,8 @@ def _state(n: int, kind: str, seed: int) -> np.ndarray:
                                      for k in range(1, 4))
     if kind == "tophat":
         u = u + np.where((x > 0.3) & (x < 0.6), 0.8, 0.0)
+    if kind == "plateau":  # several cells hold max |u| exactly (the speed cotangent is shared between them)
+        u = np.minimum(u, 0.9 * np.abs(u).max())
     return u
 
 
@@ -110,7 +112,8 @@ def test_lean_adjoint_stage_linear_terms(emu) -> None:
 
 @pytest.mark.parametrize("flux,alpha", [("lf", 1.0), ("lf", 0.995), ("rusanov", 0.995)])
 @pytest.mark.parametrize("bc", ["periodic", "dirichlet"])
-@pytest.mark.parametrize("n,kind,tol", [(250, "smooth", 1e-12), (121, "smooth", 1e-12), (500, "tophat", 1e-9)])
+@pytest.mark.parametrize("n,kind,tol", [(250, "smooth", 1e-12), (121, "smooth", 1e-12), (500, "tophat", 1e-9),
+                                        (250, "plateau", 1e-9)])
 def test_lean_adjoint_stage_with_the_global_speed_and_the_viscosity_of_every_face(emu, flux: str, alpha: float, bc: str,
                                                                                   n: int, kind: str, tol: float) -> None:
     """the Lax-Friedrichs (scalar.py:258-278) and alpha != 1 (scalar.py:231-234) forms of the lean kernel: the speed

@@ -213,7 +213,7 @@ int psk_ssprk33_step(const psk_desc *d, const double *u, double *uout, const dou
  * data of that stage's time (Neumann: plus the stage value of their mirror image).  ghost3: three consecutive blocks of (d->ghost_ld != 0 ? batch * d->ghost_ld : 2 g) doubles -- what the
  * user's g(t, x) returns at t, t + dt, t + dt / 2 (timestepping.py:314-319), rows at stride d->ghost_ld (0: one
  * set for all rows), left ghost cells first; d->ghost is ignored.  Burgers + {Rusanov, upwind,
- * Engquist-Osher; global Lax-Friedrichs on Dirichlet rows of at most 16 512 cells, without k1_out / k2_out},
+ * Engquist-Osher; global Lax-Friedrichs on Dirichlet rows of at most 16 512 cells},
  * advection, continuity (upwind flux); WENO-JS5, FAST math, 16-byte aligned rows, g <= 16.  d->nu (Rusanov /
  * Lax-Friedrichs with alpha != 1, scalar.py:231-234): the viscosity of every face of the array, nx - 1 values.
  * PSK_E_UNSUPPORTED elsewhere.  Same bits as three psk_ssprk33_stage calls with those data.  active / maxabs

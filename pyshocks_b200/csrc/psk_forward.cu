@@ -1180,7 +1180,9 @@ __device__ __forceinline__ void lf_fill_ghosts(const StepParams &p, const double
   }
 }
 
-template <int R, bool WITH_MAX, int BCK, int THREADS, int MINB, bool NU>
+// STAGES: the stage values k1, k2 are stored too (p.k1_out, p.k2_out: what the reverse sweep recomputes from a
+// checkpointed state); with p.uout == nullptr the third stage is skipped -- nothing is sent for it and nobody waits
+template <int R, bool WITH_MAX, int BCK, int THREADS, int MINB, bool NU, bool STAGES = false>
 __global__ void __launch_bounds__(THREADS, MINB)
 step_lf_cluster_kernel(const StepParams p) {
   using Geo = StepGeometry<R>;
@@ -1284,26 +1286,34 @@ step_lf_cluster_kernel(const StepParams p) {
   step_stage_rhs<R, kLF, kB, LfSpeed, NU>(u0, p.eps9, dF, nullptr, LfSpeed{&xch, 0, windows, lane}, nuf);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(cdt, dF[r], u0[r]);  // k1
+  auto store_cells = [&](double *dst, const double(&v)[R]) {
+    if (inside) {
+#pragma unroll
+      for (int r = 0; r < R; r += 2)
+        if (st[r]) *reinterpret_cast<double2 *>(dst + base + c0 + r) = make_double2(v[r], v[r + 1]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (st[r]) dst[base + c0 + r] = v[r];
+    }
+  };
+  if (STAGES) store_cells(p.k1_out, a);
   lf_send_stage_max<R>(&xch, lane, chunk, 1, gbits[1], st, a);
   if (fill) lf_fill_ghosts<R>(p, gmine[1], c0, a);
   step_stage_rhs<R, kLF, kB, LfSpeed, NU>(a, p.eps9, dF, nullptr, LfSpeed{&xch, 1, windows, lane}, nuf);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(0.25, fma(cdt, dF[r], a[r]), 0.75 * u0[r]);  // k2
+  if (STAGES) {
+    store_cells(p.k2_out, a);
+    if (p.uout == nullptr) return;  // (every message addressed to this CTA arrived before its warps left stage 2)
+  }
   lf_send_stage_max<R>(&xch, lane, chunk, 2, gbits[2], st, a);
   if (fill) lf_fill_ghosts<R>(p, gmine[2], c0, a);
   step_stage_rhs<R, kLF, kB, LfSpeed, NU>(a, p.eps9, dF, nullptr, LfSpeed{&xch, 2, windows, lane}, nuf);
 #pragma unroll
   for (int r = 0; r < R; ++r) a[r] = fma(2.0 / 3.0, fma(cdt, dF[r], a[r]), (1.0 / 3.0) * u0[r]);  // u'
 
-  if (inside) {
-#pragma unroll
-    for (int r = 0; r < R; r += 2)
-      if (st[r]) *reinterpret_cast<double2 *>(p.uout + base + c0 + r) = make_double2(a[r], a[r + 1]);
-  } else {
-#pragma unroll
-    for (int r = 0; r < R; ++r)
-      if (st[r]) p.uout[base + c0 + r] = a[r];
-  }
+  store_cells(p.uout, a);
   if (WITH_MAX) {
     unsigned long long mx = 0ull;
 #pragma unroll
@@ -1322,7 +1332,7 @@ step_lf_cluster_kernel(const StepParams p) {
 // the 8 CTAs of a portable cluster
 static int g_lf_wpc = 4;
 
-template <bool WITH_MAX, int BCK, bool NU = false>
+template <bool WITH_MAX, int BCK, bool NU = false, bool STAGES = false>
 int launch_step_lf(const StepParams &q0, int n, int batch, cudaStream_t st) {
   constexpr int R = 6, kMaxWarps = 12;
   StepParams q = q0;
@@ -1356,7 +1366,7 @@ int launch_step_lf(const StepParams &q0, int n, int batch, cudaStream_t st) {
     // (CTAs of up to 4 windows: 16 warps per SM within 128 registers; longer rows: one large CTA per SM)
     cudaError_t err;
     if (wpc <= 4) {
-      auto kernel = step_lf_cluster_kernel<R, WITH_MAX, BCK, 128, 4, NU>;
+      auto kernel = step_lf_cluster_kernel<R, WITH_MAX, BCK, 128, 4, NU, STAGES>;
       if (cx > 8) {
         err = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         if (err == cudaSuccess) err = cudaLaunchKernelEx(&cfg, kernel, q);
@@ -1364,7 +1374,7 @@ int launch_step_lf(const StepParams &q0, int n, int batch, cudaStream_t st) {
         err = cudaLaunchKernelEx(&cfg, kernel, q);
       }
     } else {
-      err = cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 384, 1, NU>, q);
+      err = cudaLaunchKernelEx(&cfg, step_lf_cluster_kernel<R, WITH_MAX, BCK, 384, 1, NU, STAGES>, q);
     }
     if (err == cudaSuccess) return PSK_OK;
     if (attempt == 0) {  // this device does not place clusters of that size: never ask again
@@ -1544,6 +1554,11 @@ int launch_step_fused(const psk_desc *d, const double *u, double *uout, const do
     return PSK_OK;
   }
   if (d->flux == PSK_FLUX_LAX_FRIEDRICHS) {  // one cluster per row (the entry points admit periodic / Dirichlet rows)
+    if (k1_out != nullptr) {  // stage values for the reverse sweep (Dirichlet rows: psk_ssprk33_step_bc)
+      if (d->bc != PSK_BC_DIRICHLET) return PSK_E_UNSUPPORTED;
+      return d->nu != nullptr ? launch_step_lf<false, 1, true, true>(q, d->n, batch, st)
+                              : launch_step_lf<false, 1, false, true>(q, d->n, batch, st);
+    }
     if (d->bc == PSK_BC_DIRICHLET && d->nu != nullptr)  // alpha != 1 (the reference's burgers-adjoint defaults)
       return mx ? launch_step_lf<true, 1, true>(q, d->n, batch, st) : launch_step_lf<false, 1, true>(q, d->n, batch, st);
     if (d->bc == PSK_BC_DIRICHLET)
@@ -1855,7 +1870,7 @@ int psk_ssprk33_step_bc(const psk_desc *d, const double *u, double *uout, const 
   const bool burgers_ok = d->equation == PSK_EQ_BURGERS &&
                           (d->flux == PSK_FLUX_RUSANOV ||
                            (d->nu == nullptr && (d->flux == PSK_FLUX_UPWIND || d->flux == PSK_FLUX_ENGQUIST_OSHER)) ||
-                           (d->flux == PSK_FLUX_LAX_FRIEDRICHS && d->bc == PSK_BC_DIRICHLET && k1_out == nullptr));
+                           (d->flux == PSK_FLUX_LAX_FRIEDRICHS && d->bc == PSK_BC_DIRICHLET));
   const bool linear_ok = d->equation != PSK_EQ_BURGERS && d->flux == PSK_FLUX_UPWIND;
   if (!(burgers_ok || linear_ok) || d->rec != PSK_REC_WENOJS53 || d->math != PSK_MATH_FAST || !aligned ||
       g_step_variant == 0 || (d->bc != PSK_BC_DIRICHLET && d->bc != PSK_BC_NEUMANN) || d->g < 3 || d->n < d->g)

@@ -290,3 +290,65 @@ def test_fused_reverse_step_on_dirichlet_rows_matches_the_five_launch_path(n: in
             assert max_rel(out[b, i].cpu().numpy(), want[i]) < 3e-12
     finally:
         L.lib().psk_set_reverse_variant(0)
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.995])
+@pytest.mark.parametrize("n", [96, 700, 4096])
+def test_adjoint_ensemble_in_the_scheme_of_the_reference_driver(alpha: float, n: int) -> None:
+    """The scheme of the reference's own burgers-adjoint driver (drivers/burgers-adjoint.py:68-97, :408: global
+    Lax-Friedrichs flux, alpha = 0.995, Dirichlet rows): the forward sweep is one cluster launch per step, the reverse
+    sweep recomputes k1, k2 with the same kernel (psk_ssprk33_step_bc with stage outputs: bit-identical to the stage
+    launches) and applies three lean Lax-Friedrichs adjoint stages; against autograd through the torch twin."""
+    from pyshocks_b200.ensemble import AdjointEnsemble, EnsembleSolver
+
+    batch, nsteps, g = 3, 6, 3
+    grid = po.make_grid(-1.5, 1.5, n, g)
+    rng = np.random.default_rng(n)
+    xh = (grid.x - grid.a) / (grid.b - grid.a)
+    # (phases that keep the row's max |u| away from a tie between two cells: a tie decided by round-off would hand the
+    # speed's cotangent to different cells here and in the twin)
+    u0 = np.stack([0.3 * b + np.sin(2 * np.pi * xh + b + 0.37) for b in range(batch)])
+    ghost = rng.uniform(-0.3, 0.3, size=2 * g)
+    nu = None if alpha == 1.0 else np.diff(grid.x) ** (alpha - 1.0)
+    dt = 0.3 * grid.h / np.abs(u0).max()
+    grads = []
+    for fused_recompute in (False, True):
+        solver = EnsembleSolver(equation="burgers", flux="lf", rec="wenojs53", bc="dirichlet", n=n, g=g, dx=grid.h,
+                                eps=1e-12, batch=batch, nu=nu)
+        solver.hp.set_ghost(ghost)
+        adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=3, fused_recompute=fused_recompute)
+        assert not adj.fused_reverse
+        _, grad = adj.gradient_half_l2(torch.from_numpy(u0).cuda())
+        assert adj._fused is True  # forward: one cluster launch per step
+        grads.append((grad.clone(), adj.launches))
+    # (the cotangent of a row's speed is summed with one atomic per warp: the order, hence the last bits, may differ)
+    assert max_rel(grads[0][0].cpu().numpy(), grads[1][0].cpu().numpy()) < 1e-13
+    assert grads[1][1] < grads[0][1]
+    # the stage values of the one-launch recomputation are those of the stage launches, bit for bit
+    hp = solver.hp
+    u, k1, k2, k1s, k2s, un, uns = solver.new_states(7)
+    u.copy_(torch.from_numpy(u0).cuda())
+    dtt = torch.full((1,), dt, dtype=torch.float64, device="cuda")
+    assert hp.step_fused_stages(u, k1, k2, un, dtt)
+    hp.stage(1, u, u, k1s, dtt)
+    hp.stage(2, u, k1s, k2s, dtt)
+    hp.stage(3, u, k2s, uns, dtt)
+    i = slice(g, g + n)
+    assert torch.equal(k1[:, i], k1s[:, i]) and torch.equal(k2[:, i], k2s[:, i]) and torch.equal(un[:, i], uns[:, i])
+    k1.zero_()
+    k2.zero_()
+    assert hp.step_fused_stages(u, k1, k2, None, dtt)  # third stage skipped
+    assert torch.equal(k1[:, i], k1s[:, i]) and torch.equal(k2[:, i], k2s[:, i])
+    if n <= 700:
+        scheme = po.Scheme("burgers", "lf", po.make_reconstruction("wenojs53"), alpha=alpha)
+        xg = np.concatenate([grid.x[:g], grid.x[-g:]])
+        bc = po.Dirichlet(ga=lambda t, x: np.interp(x, xg, ghost))
+        i = grid.interior
+        for b in range(batch):
+            u = torch.from_numpy(u0[b]).clone().requires_grad_(True)
+            x = u
+            for _ in range(nsteps):
+                x = tt.ssprk33_advance(lambda t_, y: tt.apply_operator(scheme, grid, bc, t_, y), dt, 0.0, x)
+            (gb,) = torch.autograd.grad(0.5 * (x[i] ** 2).sum(), u)
+            # (random boundary data: the reconstruction next to the row ends is not smooth; 1.03e-12 measured)
+            assert max_rel(grads[1][0][b].cpu().numpy()[i], gb.numpy()[i]) < 3e-12

@@ -19,7 +19,8 @@ same process right after the headline:
              the N ranks, ghost cells exchanged through NVLink peer memory;
   `adjoint`  BASELINE configs[4]: B = 4096 x N = 8192 ensemble (rows sharded over the ranks),
              1000 fixed-dt steps forward with a device tape + the reverse sweep: gradients/s
-             (`adjoint.dirichlet`: the same ensemble on Dirichlet rows, 100 steps);
+             (`adjoint.dirichlet`: the same ensemble on Dirichlet rows, 100 steps; `adjoint.reference_driver_scheme`:
+             the scheme of drivers/burgers-adjoint.py itself -- global Lax-Friedrichs, alpha = 0.995, Dirichlet rows);
   `parity`   64 sampled rows of the timed ensemble state against the C restatement of the
              reference (oracle/psk_oracle.c) on the identical initial rows.
 
@@ -714,7 +715,7 @@ def measure_slab(ctx: Ctx, args: argparse.Namespace, *, n_global: int, transport
 
 
 def adjoint_twin_check(dev, n: int, h: float, dt: float, u0_rows: np.ndarray, nsteps: int, kw: dict,
-                       ghost: np.ndarray | None = None) -> dict:
+                       ghost: np.ndarray | None = None, flux: str = "rusanov", alpha: float = 1.0) -> dict:
     """The product's gradient of J = 1/2 ||u(T)||^2 on a few rows of the benchmarked ensemble over a few
     steps against reverse-mode differentiation of the reference arithmetic (oracle/torch_twin.py).
     `ghost`: (rows, 2 g) Dirichlet data (time-independent) -- Dirichlet rows instead of periodic ones."""
@@ -725,15 +726,16 @@ def adjoint_twin_check(dev, n: int, h: float, dt: float, u0_rows: np.ndarray, ns
     from pyshocks_b200.ensemble import AdjointEnsemble, EnsembleSolver
 
     rows = u0_rows.shape[0]
-    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="periodic" if ghost is None else "dirichlet",
-                            n=n, g=GHOSTS, dx=h, eps=EPS, batch=rows, device=dev)
+    grid = po.make_grid(DOMAIN[0], DOMAIN[1], n, GHOSTS)
+    nu = None if alpha == 1.0 else np.diff(grid.x) ** (alpha - 1.0)  # grid.df ** (alpha - 1), scalar.py:231-232
+    solver = EnsembleSolver(equation="burgers", flux=flux, rec="wenojs53", bc="periodic" if ghost is None else "dirichlet",
+                            n=n, g=GHOSTS, dx=h, eps=EPS, batch=rows, device=dev, nu=nu)
     if ghost is not None:
         solver.hp.set_ghost(ghost)
     adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, **(kw | {"segment": 2}))
     _, grad = adj.gradient_half_l2(torch.from_numpy(u0_rows).to(dev))
     grad = grad.cpu().numpy()
-    grid = po.make_grid(DOMAIN[0], DOMAIN[1], n, GHOSTS)
-    scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53"))
+    scheme = po.Scheme("burgers", flux, po.make_reconstruction("wenojs53"), alpha=alpha)
     xg = np.concatenate([grid.x[:GHOSTS], grid.x[-GHOSTS:]])
     worst = 0.0
     for b in range(rows):
@@ -746,12 +748,18 @@ def adjoint_twin_check(dev, n: int, h: float, dt: float, u0_rows: np.ndarray, ns
         gb = gb.numpy()
         i = grid.interior
         worst = max(worst, float(np.abs(grad[b][i] - gb[i]).max() / np.abs(gb[i]).max()))
-    return {"max_rel": worst, "tol": 1.0e-12, "ok": bool(worst <= 1.0e-12),
+    # periodic rows of smooth data: 1e-12; Dirichlet rows whose boundary data (the row's mean) jump against the interior:
+    # the suite's tolerance for non-smooth data (tests/test_gpu_adjoint.py tol_for: the derivative of the weights
+    # amplifies round-off where beta ~ eps next to a jump, here in the cells at the row ends)
+    tol = 1.0e-12 if ghost is None else 1.0e-9
+    return {"max_rel": worst, "tol": tol, "ok": bool(worst <= tol),
             "what": f"dJ/du0 of {rows} rows of this ensemble over {nsteps} steps (same kernels, two-level tape) against "
-                    "torch autograd through oracle/torch_twin.py (the stand-in for jax.jacfwd of the reference's advance)"}
+                    "torch autograd through oracle/torch_twin.py (the stand-in for jax.jacfwd of the reference's advance)"
+                    + ("" if ghost is None else "; Dirichlet rows: non-smooth at the row ends, tolerance of the suite's non-smooth cases")}
 
 
-def measure_adjoint_dirichlet(ctx: Ctx, *, batch_total: int, n: int, nsteps: int, kw: dict, check: bool) -> dict:
+def measure_adjoint_dirichlet(ctx: Ctx, *, batch_total: int, n: int, nsteps: int, kw: dict, check: bool,
+                              flux: str = "rusanov", alpha: float = 1.0) -> dict:
     """configs[4] on DIRICHLET rows -- the boundary kind of the reference's own burgers-adjoint template
     (drivers/burgers-adjoint.py:68-97) -- over `nsteps` steps with every state kept: whole-step forward launches
     (psk_ssprk33_step_bc) and one launch per reverse step (psk_ssprk33_step_adjoint_bc).  Same rows and initial data
@@ -762,8 +770,10 @@ def measure_adjoint_dirichlet(ctx: Ctx, *, batch_total: int, n: int, nsteps: int
     dev, rank, world = ctx.dev, ctx.rank, ctx.world
     first, rows = shard(batch_total, rank, world)
     h = (DOMAIN[1] - DOMAIN[0]) / n
-    solver = EnsembleSolver(equation="burgers", flux="rusanov", rec="wenojs53", bc="dirichlet", n=n, g=GHOSTS,
-                            dx=h, eps=EPS, batch=rows, device=dev)
+    xc = DOMAIN[0] + h * (np.arange(n + 2 * GHOSTS) - GHOSTS + 0.5)
+    nu = None if alpha == 1.0 else np.diff(xc) ** (alpha - 1.0)  # grid.df ** (alpha - 1), scalar.py:231-232
+    solver = EnsembleSolver(equation="burgers", flux=flux, rec="wenojs53", bc="dirichlet", n=n, g=GHOSTS,
+                            dx=h, eps=EPS, batch=rows, device=dev, nu=nu)
     coef_host = ensemble_coefficients(batch_total, 20261018)
     ghost_host = np.repeat(coef_host[first : first + rows, :1], 2 * GHOSTS, axis=1)
     solver.hp.set_ghost(ghost_host)
@@ -773,6 +783,8 @@ def measure_adjoint_dirichlet(ctx: Ctx, *, batch_total: int, n: int, nsteps: int
     if world > 1:
         ctx.dist.all_reduce(umax, op=ctx.dist.ReduceOp.MAX)
     dt = CFL * h / float(umax)
+    if flux != "rusanov":
+        kw = {k: v for k, v in kw.items() if k != "fused_reverse"}
     adj = AdjointEnsemble(solver, nsteps=nsteps, dt=dt, segment=1, **kw)
     small = AdjointEnsemble(solver, nsteps=2, dt=dt, segment=1, **kw)
     small.gradient_half_l2(u0)  # warm-up
@@ -790,7 +802,8 @@ def measure_adjoint_dirichlet(ctx: Ctx, *, batch_total: int, n: int, nsteps: int
     ctx.barrier()
     fwd_ms, bwd_ms = ctx.max_over_ranks([ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])])
     out = {
-        "workload": f"the same ensemble on Dirichlet rows (boundary data = the row's mean value), {nsteps} steps, every state kept",
+        "workload": f"the same ensemble on Dirichlet rows (boundary data = the row's mean value), {flux} flux, alpha = {alpha}, "
+                    f"{nsteps} steps, every state kept",
         "steps": nsteps, "forward_ms": fwd_ms, "reverse_ms": bwd_ms, "reverse_mode": adj.reverse_mode,
         "gradients_per_s_at_these_steps": batch_total / ((fwd_ms + bwd_ms) * 1e-3),
         "adjoint_cell_updates_per_s": batch_total * n * nsteps / (bwd_ms * 1e-3),
@@ -801,7 +814,7 @@ def measure_adjoint_dirichlet(ctx: Ctx, *, batch_total: int, n: int, nsteps: int
     del adj, grad, uT, pT, u0, solver
     torch.cuda.empty_cache()
     if check and rank == 0:
-        out["parity"] = adjoint_twin_check(dev, n, h, dt, u0_rows, 6, kw, ghost=ghost_host[:2])
+        out["parity"] = adjoint_twin_check(dev, n, h, dt, u0_rows, 6, kw, ghost=ghost_host[:2], flux=flux, alpha=alpha)
     torch.cuda.empty_cache()
     return out
 
@@ -884,6 +897,15 @@ def measure_adjoint(ctx: Ctx, args: argparse.Namespace, *, batch_total: int, n: 
         traceback.print_exc()
         dirichlet = {"error": f"{type(exc).__name__}: {exc}"}
         torch.cuda.empty_cache()
+    try:  # the scheme of the reference's own driver (drivers/burgers-adjoint.py:68-97, :408): lf, alpha = 0.995, Dirichlet
+        driver = measure_adjoint_dirichlet(ctx, batch_total=batch_total, n=n, nsteps=min(nsteps, 100), kw=kw, check=check,
+                                           flux="lf", alpha=0.995)
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+
+        traceback.print_exc()
+        driver = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
     return {
         "metric": "adjoint gradients/s", "value": batch_total / ((fwd_ms + bwd_ms) * 1e-3), "unit": "gradients/s",
         "n_gpus": world, "steps": nsteps, "scaling": "strong",
@@ -901,6 +923,7 @@ def measure_adjoint(ctx: Ctx, args: argparse.Namespace, *, batch_total: int, n: 
                                  "segment recompute of the two-level tape is extra work inside reverse_ms, not extra credit"},
         "gpu_launches": launches,
         "dirichlet": dirichlet,
+        "reference_driver_scheme": driver,
     }
 
 

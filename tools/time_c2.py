@@ -116,8 +116,8 @@ print(json.dumps({
                     "forward_cell_updates_per_s": n * nsteps / t_fwd, "adjoint_cell_updates_per_s": n * nsteps / t_rev,
                     "one_cta_forward_device_s": dev_fwd, "sweep_on_unaligned_tape_device_s": dev_rev,
                     "note": "wall clock of timestepping.solve(checkpoint=True) (one whole-step launch per step written "
-                            "straight onto the tape, all enqueued from one call) and timestepping.adjoint_solve (5 launches "
-                            "per reverse step from one call), including the host evaluation of the user's boundary "
+                            "straight onto the tape, all enqueued from one call) and timestepping.adjoint_solve (4 launches "
+                            "per reverse step from one call: the no-op boundary launch on p is dropped), including the host evaluation of the user's boundary "
                             "function at the 3 x steps stage times; one_cta_forward = psk_solve_rows_tables (the whole "
                             "loop in ONE launch by one thread block, state in shared memory) for comparison"},
     "step_by_step_api": {"forward_s": t_api_fwd, "reverse_s": t_api_rev, "gradients_per_s": 1.0 / (t_api_fwd + t_api_rev),

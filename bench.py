@@ -56,7 +56,8 @@ CFL = 0.4
 ALGO_BYTES_PER_CELL_UPDATE = 64.0  # 16 + 24 + 24 B over the three stages
 ALGO_FLOPS_PER_CELL_UPDATE = 456.0  # 152 per cell-stage, divisions counted as 1
 ADJ_ALGO_BYTES = 144.0  # reverse sweep per cell-step, per-stage streaming design
-CPU_SAMPLE_ROWS = 16384  # rows of the ensemble the CPU arm advances per step (0.55 GB: not cache resident)
+# rows of the ensemble the CPU arm advances per step (0.55 GB: not cache resident); PSK_BENCH_CPU_ROWS: tests only
+CPU_SAMPLE_ROWS = int(os.environ.get("PSK_BENCH_CPU_ROWS", "16384"))
 PARITY_ROWS = 64
 PARITY_TOL = 1.0e-12
 SMS, FP64_LANES_PER_SM = 148, 64

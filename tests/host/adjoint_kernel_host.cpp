@@ -88,7 +88,8 @@ int emu_adjoint_lean(int variant, int n, int g, int batch, long long ld, double 
 }
 
 // The Lax-Friedrichs (flux = 1) and alpha != 1 (nu != NULL: the viscosity of every face) forms of the lean kernel, on
-// periodic (bck = 0) or Dirichlet (bck = 1, ghost: 2 g data per row) rows, followed by what adjoint_boundary_kernel
+// periodic (bck = 0), Dirichlet (bck = 1, ghost: 2 g data per row) or Neumann (bck = 2, ghost: 2 g offsets per row) rows,
+// followed by what adjoint_boundary_kernel
 // does on the GPU: the transpose of the periodic fill and, for Lax-Friedrichs, the cotangent of the row's speed
 // max |w| shared equally between the arg-max cells (ghost cells pass theirs on to the cells they copy; Dirichlet
 // data drop it).
@@ -101,7 +102,7 @@ int emu_adjoint_lean_flux(int flux, int bck, int n, int g, int batch, long long 
   p.gspill = gspill;
   p.nu = nu;
   p.bc.ghost = ghost; p.bc.ghost_ld = ghost != nullptr ? 2 * g : 0;
-  p.bc.bc = bck == 0 ? PSK_BC_PERIODIC : PSK_BC_DIRICHLET; p.bc.n = n; p.bc.g = g; p.bc.nx = n + 2 * g;
+  p.bc.bc = bck == 0 ? PSK_BC_PERIODIC : (bck == 1 ? PSK_BC_DIRICHLET : PSK_BC_NEUMANN); p.bc.n = n; p.bc.g = g; p.bc.nx = n + 2 * g;
   p.ld = ld;
   p.invdx = 1.0 / dx;
   p.eps = eps;
@@ -123,10 +124,16 @@ int emu_adjoint_lean_flux(int flux, int bck, int n, int g, int batch, long long 
                                    : &psk::adjoint_lean_kernel<4, 3, PSK_FLUX_LAX_FRIEDRICHS, false>;
   else k = nu != nullptr ? &psk::adjoint_lean_kernel<4, 3, PSK_FLUX_RUSANOV, true> : &psk::adjoint_lean_kernel<4, 3>;
   run_grid(gx, static_cast<unsigned>(batch), wpc, [&]() { k(p, chunks); });
-  auto source = [&](int i) { return (i >= g && i < nx - g) ? i : (bck == 0 ? (i < g ? i + n : i - n) : -1); };
+  // where apply_boundary copied ghost cell i from (periodic image, Neumann mirror image; Dirichlet data: from nowhere)
+  auto source = [&](int i) {
+    if (i >= g && i < nx - g) return i;
+    if (bck == 0) return i < g ? i + n : i - n;
+    if (bck == 2) return i < g ? 2 * g - 1 - i : 2 * (nx - g) - 1 - i;
+    return -1;
+  };
   for (int row = 0; row < batch; ++row) {
     double *orow = out + static_cast<long long>(row) * ld;
-    if (bck == 0)
+    if (bck != 1)
       for (int kk = 0; kk < 2 * g; ++kk) orow[source(kk < g ? kk : nx - 2 * g + kk)] += gspill[static_cast<long long>(row) * 2 * g + kk];
     if (flux == 1 && amax[2 * row] == 1u) {  // a single arg-max cell: the index the kernel recorded, no scan
       const int i = static_cast<int>(amax[2 * row + 1]);

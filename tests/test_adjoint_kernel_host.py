@@ -111,7 +111,7 @@ def test_lean_adjoint_stage_linear_terms(emu) -> None:
 
 
 @pytest.mark.parametrize("flux,alpha", [("lf", 1.0), ("lf", 0.995), ("rusanov", 0.995)])
-@pytest.mark.parametrize("bc", ["periodic", "dirichlet"])
+@pytest.mark.parametrize("bc", ["periodic", "dirichlet", "neumann"])
 @pytest.mark.parametrize("n,kind,tol", [(250, "smooth", 1e-12), (121, "smooth", 1e-12), (500, "tophat", 1e-9),
                                         (250, "plateau", 1e-9)])
 def test_lean_adjoint_stage_with_the_global_speed_and_the_viscosity_of_every_face(emu, flux: str, alpha: float, bc: str,
@@ -127,16 +127,28 @@ def test_lean_adjoint_stage_with_the_global_speed_and_the_viscosity_of_every_fac
     scheme = po.Scheme("burgers", flux, po.make_reconstruction("wenojs53", EPS), alpha=alpha)
     nu = None if alpha == 1.0 else (np.diff(grid.x) ** (alpha - 1.0)).copy()
     ghost = rng.uniform(-0.4, 0.4, size=(batch, 2 * G)) if bc == "dirichlet" else None
+    slope = rng.uniform(-0.5, 0.5, size=batch)
+    if bc == "neumann":  # scalar.py:472-500: ghost = mirror image + side * (x[ifrom] - x[ito]) * g(t)
+        gi = np.arange(G)
+        dxl = grid.x[2 * G - 1 - gi] - grid.x[gi]
+        ir = grid.nx - G + gi
+        dxr = grid.x[2 * (grid.nx - G) - 1 - ir] - grid.x[ir]
+        ghost = np.stack([np.concatenate([-slope[b] * dxl, slope[b] * dxr]) for b in range(batch)])
     nx = n + 2 * G
     out = np.full((batch, nx), np.nan)
     gspill = np.zeros((batch, 2 * G))
     dts = np.full(batch, dt)
-    assert emu.emu_adjoint_lean_flux(1 if flux == "lf" else 0, 0 if bc == "periodic" else 1, n, G, batch, nx, grid.h, EPS,
+    assert emu.emu_adjoint_lean_flux(1 if flux == "lf" else 0, {"periodic": 0, "dirichlet": 1, "neumann": 2}[bc], n, G, batch, nx, grid.h, EPS,
                                      _p(x), _p(v), _p(dts), 1, 1.0, 1.0, _p(nu), _p(ghost), _p(gspill), _p(out)) == 0
     assert np.isfinite(out).all()
     xg = np.concatenate([grid.x[:G], grid.x[-G:]])
     for b in range(batch):
-        obc = po.Periodic() if bc == "periodic" else po.Dirichlet(ga=lambda t, xx, b=b: np.interp(xx, xg, ghost[b]))
+        if bc == "periodic":
+            obc = po.Periodic()
+        elif bc == "dirichlet":
+            obc = po.Dirichlet(ga=lambda t, xx, b=b: np.interp(xx, xg, ghost[b]))
+        else:
+            obc = po.Neumann(ga=lambda t, b=b: slope[b])
         ref = v[b] + dt * tt.rhs_vjp(scheme, grid, obc, 0.0, x[b], v[b])
         err = np.abs(out[b] - ref).max() / np.abs(ref).max()
         assert err < tol, (flux, alpha, bc, b, err)

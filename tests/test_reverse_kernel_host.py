@@ -209,3 +209,35 @@ def test_fused_reverse_step_on_dirichlet_rows(emu, C: int, n: int, kind: str, to
         w = po.apply_boundary(bc, grid, 0.0, u[b])
         r1 = u[b] + dt * po.apply_operator(scheme, grid, bc, 0.0, w)
         assert np.abs(k1[b, i] - r1[i]).max() < 1e-13 * np.abs(r1).max()
+
+
+def test_fused_reverse_step_on_dirichlet_rows_with_time_independent_data(emu) -> None:
+    """ghost_block = 0: one set of boundary data serves the three stage times (psk_ssprk33_step_adjoint on Dirichlet
+    rows with the descriptor's data, psk_ssprk33_step_adjoint_bc with ghost3 = NULL)"""
+    n, C, batch = 300, 12, 2
+    rng = np.random.default_rng(11)
+    u = np.stack([_state(n, "smooth", 3 * n + b) for b in range(batch)])
+    p = rng.standard_normal((batch, n + 2 * G))
+    p[:, :G] = 0.0
+    p[:, n + G :] = 0.0
+    dt = 0.3 * (3.0 / n)
+    ghost = rng.uniform(-0.4, 0.4, size=(batch, 2 * G))
+    nx = n + 2 * G
+    bufs = []
+    for src in (u, p, None):
+        a, col0, ld = _aligned(batch, n)
+        v = a[:, col0 : col0 + nx]
+        v[:] = np.nan if src is None else src
+        bufs.append(v)
+    U, P, OUT = bufs
+    dts = np.full(batch, dt)
+    assert emu.emu_reverse_step(C, n, G, batch, ld, 3.0 / n, EPS, _p(U), _p(P), _p(dts), 1, _p(OUT), None, None, 0,
+                                _p(ghost), 2 * G, 0) == 0
+    grid = po.make_grid(-1.5, 1.5, n, G)
+    scheme = po.Scheme("burgers", "rusanov", po.make_reconstruction("wenojs53", EPS))
+    xg = np.concatenate([grid.x[:G], grid.x[-G:]])
+    i = slice(G, G + n)
+    for b in range(batch):
+        bc = po.Dirichlet(ga=lambda t, x, b=b: np.interp(x, xg, ghost[b]))
+        ref = tt.step_vjp(scheme, grid, bc, dt, 0.0, u[b], p[b])
+        assert np.abs(OUT[b, i] - ref[i]).max() / np.abs(ref[i]).max() < 3e-12
